@@ -1,0 +1,211 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE ONLY — see bsk_oracle.c).
+
+May be imported only by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs.  The product package (bsplinekit.jl_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KIND_PLAIN, KIND_PERIODIC, KIND_RECOMBINED = 0, 1, 2
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libbsk_oracle.so")
+        src_m = max(os.path.getmtime(os.path.join(_HERE, f))
+                    for f in ("bsk_oracle.c", "bsk_oracle_tmpl.h"))
+        if not os.path.exists(path) or os.path.getmtime(path) < src_m:
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_basis_function.restype = C.c_double
+        _LIB.orc_collocation_matrix.restype = C.c_int64
+        _LIB.orc_collocation_cyclic.restype = C.c_int64
+        _LIB.orc_banded_lu.restype = C.c_int64
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _np(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+_SFX = {("f64", "f64"): "dd", ("f64", "f32"): "df", ("f32", "f32"): "ff"}
+_DT = {"f64": np.float64, "f32": np.float32}
+
+
+class Recomb:
+    """Corner description of a RecombineMatrix (matrices.jl:70-110)."""
+
+    def __init__(self, cl, cr, nl, nr, ul, lr):
+        self.cl, self.cr, self.nl, self.nr = cl, cr, nl, nr
+        self.ul = np.asfortranarray(np.asarray(ul, dtype=np.float64).reshape(-1, nl) if nl else np.zeros((cl, 0)))
+        self.lr = np.asfortranarray(np.asarray(lr, dtype=np.float64).reshape(-1, nr) if nr else np.zeros((cr, 0)))
+
+
+def find_knot_interval(kind, k, t, x, kt="f64"):
+    t = _np(t, _DT[kt]); x = _np(x, _DT[kt])
+    idx = np.empty(x.size, np.int64); zone = np.empty(x.size, np.int8)
+    getattr(lib(), "orc_find_knot_interval_" + _SFX[(kt, kt)])(
+        C.c_int(kind), C.c_int(k), _p(t), C.c_int64(t.size), _p(x), C.c_int64(x.size), _p(idx), _p(zone))
+    return idx, zone
+
+
+def evaluate_all(kind, k, t, x, nderiv=0, kt="f64", vt="f64", ileft=None, recomb=None):
+    t = _np(t, _DT[kt]); x = _np(x, _DT[kt])
+    n = x.size
+    idx = np.empty(n, np.int64); bs = np.empty((n, k), _DT[vt])
+    il = _np(ileft, np.int64) if ileft is not None else None
+    sfx = _SFX[(kt, vt)]
+    if recomb is None:
+        getattr(lib(), "orc_evaluate_all_" + sfx)(
+            C.c_int(kind), C.c_int(k), _p(t), C.c_int64(t.size), _p(x), C.c_int64(n),
+            C.c_int(nderiv), _p(il), _p(idx), _p(bs))
+    else:
+        r = recomb
+        getattr(lib(), "orc_evaluate_all_recombined_" + sfx)(
+            C.c_int(k), _p(t), C.c_int64(t.size), C.c_int(r.cl), C.c_int(r.cr), C.c_int(r.nl),
+            C.c_int(r.nr), C.c_int(r.ul.shape[0]), _p(r.ul), C.c_int(r.lr.shape[0]), _p(r.lr),
+            _p(x), C.c_int64(n), C.c_int(nderiv), _p(il), _p(idx), _p(bs))
+    return idx, bs
+
+
+def spline_eval(kind, k, t, coefs, x, kt="f64"):
+    t = _np(t, _DT[kt]); x = _np(x, _DT[kt]); c = _np(coefs, _DT[kt])
+    out = np.empty(x.size, _DT[kt])
+    getattr(lib(), "orc_spline_eval_" + _SFX[(kt, kt)])(
+        C.c_int(kind), C.c_int(k), _p(t), C.c_int64(t.size), _p(c), C.c_int64(c.size),
+        _p(x), C.c_int64(x.size), _p(out))
+    return out
+
+
+def spline_derivative(kind, k, t, coefs, nd, kt="f64"):
+    """Returns (new_k, new_knots, new_coefs) of Derivative(nd) * S."""
+    t = _np(t, _DT[kt]); c = _np(coefs, _DT[kt])
+    out = np.empty(c.size - nd if kind == KIND_PLAIN else c.size, _DT[kt])
+    rc = getattr(lib(), "orc_spline_derivative_" + _SFX[(kt, kt)])(
+        C.c_int(kind), C.c_int(k), _p(t), C.c_int64(t.size), _p(c), C.c_int64(c.size),
+        C.c_int(nd), _p(out))
+    if rc != 0:
+        raise ValueError("cannot differentiate order %d spline %d times" % (k, nd))
+    tn = t[nd:t.size - nd].copy() if kind == KIND_PLAIN else t.copy()
+    return k - nd, tn, out
+
+
+def basis_function(k, t, i, x, nd=0):
+    t = _np(t, np.float64)
+    return lib().orc_basis_function(C.c_int(k), _p(t), C.c_int64(t.size), C.c_int64(i),
+                                    C.c_double(x), C.c_int(nd))
+
+
+def collocation_matrix(kind, k, t, x, nderiv=0, clip=np.finfo(np.float64).eps, recomb=None):
+    """Band storage (2k-3, ncols) column-major (returned as Fortran-ordered array)."""
+    t = _np(t, np.float64); x = _np(x, np.float64)
+    r = recomb if recomb is not None else Recomb(0, 0, 0, 0, np.zeros((0, 0)), np.zeros((0, 0)))
+    ncols = t.size - k - r.cl - r.cr
+    band = np.zeros((2 * k - 3, ncols), np.float64, order="F")
+    nout = lib().orc_collocation_matrix(
+        C.c_int(kind), C.c_int(k), _p(t), C.c_int64(t.size), C.c_int(r.cl), C.c_int(r.cr),
+        C.c_int(r.nl), C.c_int(r.nr), C.c_int(r.ul.shape[0]), _p(r.ul), C.c_int(r.lr.shape[0]),
+        _p(r.lr), _p(x), C.c_int64(x.size), C.c_int(nderiv), C.c_double(clip), _p(band),
+        C.c_int64(ncols))
+    return band, int(nout)
+
+
+def collocation_cyclic(k, data, x, nderiv=0, clip=np.finfo(np.float64).eps):
+    data = _np(data, np.float64); x = _np(x, np.float64)
+    n = data.size - 1
+    a = np.empty(n); b = np.empty(n); c = np.empty(n)
+    nout = lib().orc_collocation_cyclic(C.c_int(k), _p(data), C.c_int64(data.size), _p(x),
+                                        C.c_int64(x.size), C.c_int(nderiv), C.c_double(clip),
+                                        _p(a), _p(b), _p(c))
+    return a, b, c, int(nout)
+
+
+def banded_lu(band):
+    """In place on a Fortran-ordered (l+u+1, n) array, l == u. Returns info (0 = ok)."""
+    assert band.flags.f_contiguous and band.dtype == np.float64
+    h = (band.shape[0] - 1) // 2
+    return int(lib().orc_banded_lu(_p(band), C.c_int(h), C.c_int(h), C.c_int64(band.shape[1])))
+
+
+def banded_solve(band_lu, rhs):
+    """rhs: C-ordered (n, nrhs) array (rhs index fastest), solved in place."""
+    assert band_lu.flags.f_contiguous and rhs.flags.c_contiguous and rhs.dtype == np.float64
+    h = (band_lu.shape[0] - 1) // 2
+    n = band_lu.shape[1]
+    r2 = rhs.reshape(n, -1)
+    lib().orc_banded_solve(_p(band_lu), C.c_int(h), C.c_int(h), C.c_int64(n), _p(r2),
+                           C.c_int64(r2.shape[1]))
+    return rhs
+
+
+def banded_matvec(band, x):
+    h = (band.shape[0] - 1) // 2
+    n = band.shape[1]
+    x2 = np.ascontiguousarray(x, dtype=np.float64).reshape(n, -1)
+    y = np.empty_like(x2)
+    lib().orc_banded_matvec(_p(band), C.c_int(h), C.c_int(h), C.c_int64(n), _p(x2), _p(y),
+                            C.c_int64(x2.shape[1]))
+    return y.reshape(np.shape(x))
+
+
+def cyclic_solve(a, b, c, d):
+    a = _np(a, np.float64); b = _np(b, np.float64); c = _np(c, np.float64)
+    n = a.size
+    d2 = np.array(d, dtype=np.float64, order="C").reshape(n, -1)
+    x = np.empty_like(d2)
+    lib().orc_cyclic_solve(_p(a), _p(b), _p(c), C.c_int64(n), _p(d2), _p(x), C.c_int64(d2.shape[1]))
+    return x.reshape(np.shape(d))
+
+
+def make_knots(x, k):
+    x = _np(x, np.float64)
+    t = np.empty(x.size + k)
+    lib().orc_make_knots(_p(x), C.c_int64(x.size), C.c_int(k), _p(t))
+    return t
+
+
+def make_knots_periodic(x, k, L):
+    x = _np(x, np.float64)
+    t = np.empty(x.size + 1)
+    lib().orc_make_knots_periodic(_p(x), C.c_int64(x.size), C.c_int(k), C.c_double(L), _p(t))
+    return t
+
+
+def greville(kind, k, t, cl=0, N=None):
+    t = _np(t, np.float64)
+    if N is None:
+        N = t.size - k
+    out = np.empty(N)
+    lib().orc_greville(C.c_int(kind), C.c_int(k), _p(t), C.c_int64(t.size), C.c_int(cl),
+                       C.c_int64(N), _p(out))
+    return out
+
+
+def robin_corners(k, t, alpha):
+    """Corner blocks for a single BC op = sum_m alpha[m] D^m on both sides."""
+    t = _np(t, np.float64); alpha = _np(alpha, np.float64)
+    q = alpha.size - 1
+    ul = np.zeros((q + 1, q), order="F"); lr = np.zeros((q + 1, q), order="F")
+    lib().orc_robin_corners(C.c_int(k), _p(t), C.c_int64(t.size), _p(alpha), C.c_int(q), _p(ul), _p(lr))
+    return Recomb(1, 1, q, q, ul, lr)
+
+
+def augment_knots(breaks, k):
+    """augment_knots! (knots.jl:68-84): pad both ends to multiplicity k."""
+    b = np.asarray(breaks)
+    return np.concatenate([np.repeat(b[:1], k - 1), b, np.repeat(b[-1:], k - 1)])
