@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the spline-evaluation hot path (BASELINE.json configs[1]):
+k = 4 spline on 1,000 non-uniform breakpoints, value + first derivative at 2^28 random Float64
+points per GPU, one process per GPU.  One JSON line on stdout (rank 0).
+
+  python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the reference
+
+A "step" is one fused pass (S(x) and S'(x)) over the 2^28 device-resident points.  `value`
+is whole-job Gpoints/s with inputs resident in HBM; `e2e` is the same metric through the
+host-buffer C-ABI call (pinned host arrays, H2D and D2H inside the timed region).
+The batched-interpolation solve (configs[2]) is timed in the same run and reported under
+"extra" with its own roofline fraction.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "bsplinekit.jl_b200"))
+
+METRIC = "Gpoints/s spline eval (k=4, 2^28 pts, value + 1st derivative, Float64)"
+UNIT = "Gpoints/s"
+BYTES_PER_POINT = 24.0          # 8 B read + 2 x 8 B written
+SOLVE_BYTES_PER_ELEM = 16.0     # read y + write c
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def workload_c2(bk, synth):
+    import numpy as np
+    k = 4
+    br = synth.breakpoints(3, 1000)
+    B = bk.BSplineBasis(k, br)
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    return k, B, c
+
+
+def cpu_reference_rate(npts_sample, nthreads):
+    """The reference algorithm on the host cores: de Boor value + derivative spline, OpenMP over
+    points (oracle/bsk_oracle.c).  Returns (Gpoints/s, seconds)."""
+    import numpy as np
+    from oracle import oracle as O
+    from bsplinekit_b200 import synth
+    os.environ.setdefault("OMP_NUM_THREADS", str(nthreads))
+    k = 4
+    br = synth.breakpoints(3, 1000)
+    t = O.augment_knots(br, k)
+    c = 2 * synth.u_numpy(4, 0, t.size - k) - 1
+    kd, td, cd = O.spline_derivative(0, k, t, c, 1)
+    x = synth.u_numpy(5, 0, npts_sample)
+    O.spline_eval(0, k, t, c, x[:1000])
+    t0 = time.perf_counter()
+    O.spline_eval(0, k, t, c, x)
+    O.spline_eval(0, kd, td, cd, x)
+    dt = time.perf_counter() - t0
+    return npts_sample / dt / 1e9, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 1 << 24
+    rates, times = [], []
+    for _ in range(args.warmup):
+        cpu_reference_rate(1 << 20, cores)
+    for _ in range(args.steps):
+        r, dt = cpu_reference_rate(sample, cores)
+        rates.append(r)
+        times.append(dt)
+    tot = sum(times)
+    value = sample * len(times) / tot / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C2 cubic eval value+derivative, k=4, 1000 non-uniform breakpoints",
+                   "points_per_step": sample, "note": "bounded sample of the 2^28-point workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "2^24 points per step, OpenMP over points, all host cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import bsplinekit_b200 as bk
+    from bsplinekit_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    npts = args.points
+    k, B, c = workload_c2(bk, synth)
+    S = bk.Spline(B, c)
+    # each rank generates its own slice of the point stream on its device
+    xd = synth.u_torch(5, rank * npts, npts)
+    v = torch.empty_like(xd)
+    dv = torch.empty_like(xd)
+    outs = [v, dv]
+    algo = {"auto": bk.EVAL_AUTO, "pp": bk.EVAL_PP, "deboor": bk.EVAL_DEBOOR}[args.algo]
+
+    for _ in range(args.warmup):
+        S.evaluate(xd, (0, 1), algo=algo, out=outs)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        S.evaluate(xd, (0, 1), algo=algo, out=outs)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    value = world * npts / (ms_step * 1e-3) / 1e9
+    launches_per_step = 1 if args.algo != "deboor" else 2
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_POINT * npts / (ms_step * 1e-3) / 1e9      # per GPU, GB/s
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("k_spline_pp_bytes_per_launch")
+    except Exception:
+        pass
+
+    # parity spot check on what was just computed (not timed)
+    chk = {}
+    if rank == 0:
+        from oracle import oracle as O
+        m = 1 << 16
+        xh = xd[:m].cpu().numpy()
+        ref = O.spline_eval(0, k, B.knots(), c, xh)
+        kd, td, cd = O.spline_derivative(0, k, B.knots(), c, 1)
+        refd = O.spline_eval(0, kd, td, cd, xh)
+        chk = {"value_relerr": float(np.max(np.abs(v[:m].cpu().numpy() - ref)) / np.max(np.abs(ref))),
+               "deriv_relerr": float(np.max(np.abs(dv[:m].cpu().numpy() - refd)) / np.max(np.abs(refd)))}
+
+    # ---- e2e: host buffers through the C-ABI host call (H2D + kernel + D2H, pipelined) ----------
+    e2e = None
+    if not args.no_e2e:
+        ne = min(npts, args.e2e_points)
+        xh = torch.empty(ne, dtype=torch.float64, pin_memory=True)
+        xh.copy_(xd[:ne])
+        oh = [torch.empty(ne, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        xnp, onp = xh.numpy(), [o.numpy() for o in oh]
+        S.evaluate(xnp, (0, 1), algo=algo, out=onp)       # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(ke):
+            S.evaluate(xnp, (0, 1), algo=algo, out=onp)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0) / ke
+        assert np.array_equal(onp[0][:1024], v[:1024].cpu().numpy())
+        e2e = {"value": world * ne / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * ne,
+               "d2h_bytes_per_step": 16 * ne, "points_per_step": ne, "steps": ke,
+               "ms_per_step": 1e3 * dt}
+        del xh, oh
+
+    # ---- extra: batched interpolation solve, configs[2] -------------------------------------------
+    extra = {}
+    if not args.no_solve:
+        del xd, v, dv
+        torch.cuda.empty_cache()
+        n, kk, nrhs = 4096, 6, args.nrhs
+        xdata = synth.breakpoints(6, n)
+        Bi = bk.BSplineBasis(kk, bk.make_knots(xdata, kk), augment=False)
+        t_f0 = time.perf_counter()
+        itp = bk.SplineInterpolation(Bi, xdata)          # assemble + LU, once
+        torch.cuda.synchronize()
+        factor_ms = 1e3 * (time.perf_counter() - t_f0)
+        Y0 = (2 * synth.u_torch(7, rank * n * nrhs, n * nrhs) - 1).reshape(n, nrhs)
+        Y = torch.empty_like(Y0)
+        res = {}
+        for name, salgo in (("windowed", bk.SOLVE_WINDOWED), ("twopass", bk.SOLVE_TWOPASS)):
+            if name == "windowed" and itp.C.halo == 0:
+                continue
+            tot = 0.0
+            for it in range(args.warmup + args.solve_steps):
+                Y.copy_(Y0)
+                barrier()
+                s0 = torch.cuda.Event(enable_timing=True)
+                s1 = torch.cuda.Event(enable_timing=True)
+                s0.record()
+                itp.C.ldiv_(Y, algo=salgo)
+                s1.record()
+                torch.cuda.synchronize()
+                if it >= args.warmup:
+                    tot += s0.elapsed_time(s1)
+            ms = max_over_ranks(tot / args.solve_steps)
+            res[name] = {"ms": ms, "rhs_per_s": world * nrhs / (ms * 1e-3),
+                         "achieved_gbs": SOLVE_BYTES_PER_ELEM * n * nrhs / (ms * 1e-3) / 1e9,
+                         "frac": SOLVE_BYTES_PER_ELEM * n * nrhs / (ms * 1e-3) / 1e9 / peak}
+            if rank == 0 and name == "windowed":
+                keep = Y[:, :256].cpu().numpy()
+        if rank == 0:
+            from oracle import oracle as O
+            band, _ = O.collocation_matrix(0, kk, Bi.knots(), xdata)
+            O.banded_lu(band)
+            ref = O.banded_solve(band, Y0[:, :256].cpu().numpy().copy())
+            got = keep if "windowed" in res else Y[:, :256].cpu().numpy()
+            chk["solve_relerr"] = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
+        best = min(res.values(), key=lambda r: r["ms"])
+        extra = {"c3_batched_solve": {"metric": "RHS/s (n=4096, k=6, %d RHS per GPU, Float64)" % nrhs,
+                                      "value": best["rhs_per_s"], "unit": "RHS/s",
+                                      "roofline_frac": best["frac"], "algos": res,
+                                      "factor_once_ms": factor_ms, "halo_rows": itp.C.halo}}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        sample = 1 << 25
+        r, dt = cpu_reference_rate(sample, cores)
+        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "2^25 of the 2^28 points, value + derivative, OpenMP over points (%.1f s)" % dt}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: k=4 spline, 1000 non-uniform breakpoints, value + 1st derivative "
+                                   "at %d random Float64 points per GPU" % npts,
+                       "points_per_gpu": npts, "algo": args.algo,
+                       "l2": "inputs (%.2f GB per step) larger than the 126 MB L2" % (8e-9 * npts),
+                       "parallelism": "points sharded, basis replicated, no collective"},
+            "clocks": clocks, "gpu_launches": args.steps * launches_per_step,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "k_spline_pp<4,0,double,2>" if args.algo != "deboor" else "k_spline_deboor",
+                         "algorithmic_bytes_per_launch": BYTES_PER_POINT * npts},
+            "e2e": e2e, "cpu_baseline": cpu, "parity": chk, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1 << 28)
+    ap.add_argument("--algo", default="auto", choices=["auto", "pp", "deboor"])
+    ap.add_argument("--nrhs", type=int, default=65536)
+    ap.add_argument("--solve-steps", type=int, default=10)
+    ap.add_argument("--e2e-points", type=int, default=1 << 28)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,13 @@
+"""bsplinekit_b200 — host-side mirror of the BSplineKit.jl interface over libbsplinekit_b200.so.
+
+See api.py.  Importing this package loads the CUDA shared library and fails loudly if it
+has not been built (no CPU fallback).
+"""
+from ._lib import (ArgumentError, DimensionMismatch, ZeroPivotException, CudaError, UnsupportedError,
+                   EVAL_AUTO, EVAL_DEBOOR, EVAL_PP, SOLVE_AUTO, SOLVE_TWOPASS, SOLVE_WINDOWED,
+                   LIB_PATH, device_count, version)
+from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, period,
+                  BSplineBasis, PeriodicBSplineBasis, RecombinedBSplineBasis, augment_knots,
+                  knots, order, boundaries, find_knot_interval, evaluate_all,
+                  Spline, collocation_points, collocation_matrix, CollocationMatrix,
+                  CyclicTridiagonalMatrix, lu, ldiv, make_knots, SplineInterpolation, interpolate)

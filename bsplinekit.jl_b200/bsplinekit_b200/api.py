@@ -1,0 +1,883 @@
+"""Host-side mirror of the BSplineKit.jl interface for the two hot paths.
+
+Julia is not available in this image, so this module is the executable stand-in for the
+Julia shim (julia/BSplineKitB200.jl): same names, argument meaning and error behaviour
+as the reference, every numerical body delegated to libbsplinekit_b200.so through the
+C ABI (include/bsk.h).  Only constructor / type logic lives here (knot augmentation,
+make_knots, Greville points, recombination corner blocks) — exactly the part that stays
+Julia in the reference-side integration.  torch is used for device memory and streams.
+
+Reference citations are relative to the BSplineKit.jl source tree (v0.19.2).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ArgumentError, DimensionMismatch, ZeroPivotException, check, lib,
+                   BSK_F32, BSK_F64, BASIS_PLAIN, BASIS_PERIODIC, BASIS_RECOMBINED,
+                   EVAL_AUTO, EVAL_DEBOOR, EVAL_PP, SOLVE_AUTO, SOLVE_TWOPASS, SOLVE_WINDOWED)
+
+_NP = {BSK_F32: np.float32, BSK_F64: np.float64}
+_TORCH = {BSK_F32: torch.float32, BSK_F64: torch.float64}
+
+
+def _dtype_code(dt):
+    dt = np.dtype(dt)
+    if dt == np.float32:
+        return BSK_F32
+    if dt == np.float64:
+        return BSK_F64
+    raise ArgumentError("unsupported element type %s (Float32 / Float64 only)" % dt)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.CudaError("no CUDA device available (there is no CPU fallback)")
+    return torch.cuda.current_device()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _to_device(x, dtype_code):
+    """Accept a CUDA tensor (used in place), a CPU tensor or anything numpy understands."""
+    tdt = _TORCH[dtype_code]
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            if x.dtype != tdt:
+                raise ArgumentError("device vector has dtype %s, expected %s" % (x.dtype, tdt))
+            return x.contiguous(), True
+        return x.to(tdt).contiguous().cuda(), False
+    arr = np.ascontiguousarray(np.asarray(x, dtype=_NP[dtype_code]))
+    return torch.from_numpy(arr).cuda(), False
+
+
+# ---- operator / order vocabulary (DifferentialOps.jl:88-160, BSplines.jl:106-108) ----------
+
+class BSplineOrder:
+    def __init__(self, k):
+        self.k = int(k)
+
+    def __eq__(self, o):
+        return isinstance(o, BSplineOrder) and o.k == self.k
+
+
+class DifferentialOp:
+    """sum_m alpha[m] D^m  (Derivative, ScaledDerivative, DifferentialOpSum)."""
+
+    def __init__(self, terms):
+        self.terms = dict(terms)           # order -> coefficient, insertion order kept
+
+    def __add__(self, o):
+        t = dict(self.terms)
+        for m, a in o.terms.items():
+            t[m] = t.get(m, 0.0) + a
+        return DifferentialOp(t)
+
+    def __sub__(self, o):
+        return self + (-1.0) * o
+
+    def __rmul__(self, a):
+        if isinstance(a, (int, float)):
+            if a == 0:
+                raise ArgumentError("scale factor cannot be zero")      # DifferentialOps.jl:117-119
+            return DifferentialOp({m: a * c for m, c in self.terms.items()})
+        return NotImplemented
+
+    def __neg__(self):
+        return (-1.0) * self
+
+    @property
+    def max_order(self):
+        return max(self.terms) if self.terms else -1
+
+
+class Derivative(DifferentialOp):
+    def __init__(self, n=1):
+        super().__init__({int(n): 1.0})
+        self.n = int(n)
+
+    def __mul__(self, S):
+        if isinstance(S, Spline):
+            return S.derivative(self.n)                                 # spline.jl:272-282
+        if isinstance(S, (int, float)):
+            return S * DifferentialOp(self.terms)
+        return NotImplemented
+
+    def __eq__(self, o):
+        return isinstance(o, Derivative) and o.n == self.n
+
+    def __hash__(self):
+        return hash(("D", self.n))
+
+    def __repr__(self):
+        return "D{%d}" % self.n
+
+
+class Periodic:
+    """BoundaryConditions.Periodic(L) (BoundaryConditions.jl:50-61)."""
+
+    def __init__(self, L):
+        self.L = L
+
+
+def period(x):
+    return x.L if isinstance(x, Periodic) else x.period
+
+
+class Natural:
+    """BoundaryConditions.Natural (BoundaryConditions.jl:36-48) — not yet on the device path."""
+
+
+def _order(k):
+    return k.k if isinstance(k, BSplineOrder) else int(k)
+
+
+# ---- bases ------------------------------------------------------------------------------------
+
+def augment_knots(breaks, k):
+    """augment_knots! (BSplines/knots.jl:68-84)."""
+    b = np.asarray(breaks)
+    return np.concatenate([np.repeat(b[:1], k - 1), b, np.repeat(b[-1:], k - 1)])
+
+
+class AbstractBSplineBasis:
+    _handle = None
+
+    def __del__(self):
+        h, self._handle = self._handle, None
+        if h is not None:
+            try:
+                lib.bsk_basis_destroy(h)
+            except Exception:
+                pass
+
+    def __len__(self):
+        return self._len
+
+    def __call__(self, x, *args, **kw):                                 # BSplines.jl:84-85
+        return evaluate_all(self, x, *args, **kw)
+
+    @property
+    def dtype(self):
+        return _NP[self._dt]
+
+
+def _create_basis(kind, k, knots, recomb=None):
+    dt = _dtype_code(knots.dtype)
+    out = C.c_void_p()
+    desc = None
+    keep = None
+    if recomb is not None:
+        ul = np.asfortranarray(recomb["ul"], dtype=np.float64)
+        lr = np.asfortranarray(recomb["lr"], dtype=np.float64)
+        keep = (ul, lr)
+        desc = _lib.RecombDesc(recomb["cl"], recomb["cr"], recomb["nl"], recomb["nr"],
+                               ul.shape[0], lr.shape[0],
+                               ul.ctypes.data_as(C.POINTER(C.c_double)),
+                               lr.ctypes.data_as(C.POINTER(C.c_double)))
+    kn = np.ascontiguousarray(knots)
+    check(lib.bsk_basis_create(kind, k, dt, kn.ctypes.data_as(C.c_void_p), kn.size,
+                               C.byref(desc) if desc is not None else None, _device(), C.byref(out)))
+    del keep
+    return out, dt
+
+
+class BSplineBasis(AbstractBSplineBasis):
+    """BSplineBasis(BSplineOrder(k), knots; augment=Val(true))  (BSplines/basis.jl:70-90)."""
+
+    def __init__(self, order, knots, augment=True):
+        k = _order(order)
+        if k <= 0:
+            raise ArgumentError("B-spline order must be k ≥ 1")
+        t = np.asarray(knots)
+        if not np.issubdtype(t.dtype, np.floating):
+            t = t.astype(np.float64)
+        self.k = k
+        self.t = augment_knots(t, k) if augment else t.copy()
+        self._len = self.t.size - k
+        self._handle, self._dt = _create_basis(BASIS_PLAIN, k, self.t)
+
+    def knots(self):
+        return self.t
+
+    def boundaries(self):                                               # basis.jl:217-222
+        return self.t[self.k - 1], self.t[self._len]
+
+
+class PeriodicBSplineBasis(AbstractBSplineBasis):
+    """PeriodicBSplineBasis(BSplineOrder(k), ts) with ts including the endpoint
+    (BSplines/periodic.jl:181-205)."""
+
+    def __init__(self, order, breaks):
+        k = _order(order)
+        if k <= 0:
+            raise ArgumentError("B-spline order must be k ≥ 1")
+        t = np.asarray(breaks)
+        if not np.issubdtype(t.dtype, np.floating):
+            t = t.astype(np.float64)
+        self.k = k
+        self.t = t.copy()
+        self._len = t.size - 1
+        self.period = t[-1] - t[0]
+        self._handle, self._dt = _create_basis(BASIS_PERIODIC, k, self.t)
+
+    def knots(self):
+        return self.t
+
+    def boundaries(self):
+        return self.t[0], self.t[-1]
+
+
+def _bfun_value(k, t, i, x):
+    """_evaluate(::BSplineOrder{k}, t, i, x, T), i 1-based (BSplines/basis_function.jl:200-256)."""
+    T = t.dtype.type
+    tend = t[-1]
+
+    def supp(ta, tb):
+        return (ta <= x < tb) or (x == tb == tend)
+    if k == 1:
+        return T(1) if supp(t[i - 1], t[i]) else T(0)
+    ta, tb = t[i - 1], t[i + k - 1]
+    if not supp(ta, tb):
+        return T(0)
+    ta1, tb1 = t[i], t[i + k - 2]
+    y = T(0)
+    if tb1 != ta:
+        y = y + _bfun_value(k - 1, t, i, x) * (x - ta) / (tb1 - ta)
+    if ta1 != tb:
+        y = y + _bfun_value(k - 1, t, i + 1, x) * (tb - x) / (tb - ta1)
+    return y
+
+
+def _bfun_diff(nd, k, t, i, x):
+    """evaluate_diff(::Derivative{N}, ...) (BSplines/basis_function.jl:138-170)."""
+    if nd == 0:
+        return _bfun_value(k, t, i, x)
+    T = t.dtype.type
+    y = T(0)
+    dt = t[i + k - 2] - t[i - 1]
+    if dt != 0:
+        y = y + _bfun_diff(nd - 1, k - 1, t, i, x) / dt
+    dt = t[i + k - 1] - t[i]
+    if dt != 0:
+        y = y - _bfun_diff(nd - 1, k - 1, t, i + 1, x) / dt
+    return y * T(k - 1)
+
+
+def _eval_op(op, k, t, i, x, left):
+    """evaluate(B, i, x, dot(op, LeftNormal())) (DifferentialOps.jl:128-131,160;
+    BSplines/basis_function.jl:178-191): each term alpha * D^m b_i, summed left to right;
+    odd derivatives change sign on the left boundary."""
+    T = t.dtype.type
+    s = None
+    for m, a in op.terms.items():
+        am = -a if (left and m % 2 == 1) else a
+        v = T(am) * _bfun_diff(m, k, t, i, x)
+        s = v if s is None else s + v
+    return s
+
+
+def _make_submatrix(ops, B, side):
+    """_make_submatrix (Recombinations/matrices.jl:219-313, 331-357).
+    Returns (ndrop, nconstraints, A) with A the corner block (rows x recombined functions)."""
+    T = B.t.dtype.type
+    ops = list(ops)
+    nc = len(ops)
+    if nc == 0:
+        return 0, 0, np.zeros((0, 0))                                  # free boundary (:219-223)
+    for o in ops:
+        if not isinstance(o, DifferentialOp):
+            raise ArgumentError("boundary condition must be a differential operator")
+    if max(o.max_order for o in ops) >= B.k:
+        raise ArgumentError("cannot resolve operators with B-splines of order %d" % B.k)   # :321-329
+    last = ops[-1]
+    is_d = lambda o, n: isinstance(o, Derivative) and o.n == n
+    if nc == 1 and is_d(last, 0):
+        return 1, 1, np.zeros((1, 0))                                  # Dirichlet (:227-231)
+    if nc == 1 and is_d(last, 1):
+        return 0, 1, np.ones((2, 1))                                   # Neumann (:234-238)
+    if nc == 1:
+        ndrop = 0                                                      # :332
+    else:
+        for j, o in enumerate(ops[:-1]):
+            if not is_d(o, j):
+                raise ArgumentError("unsupported combination of boundary conditions")   # :338-343
+        m = nc - 1
+        if is_d(last, m):
+            ndrop = m + 1
+        elif last.max_order <= m:
+            raise ArgumentError("order of last operator is too low")   # :351-354
+        else:
+            ndrop = m
+    nmax = last.max_order
+    if nmax + 1 == ndrop:
+        return ndrop, nc, np.zeros((nc, 0))                            # (D0..D(n-1)) (:263-271)
+    q = nmax - ndrop
+    A = np.zeros((q + nc, q), dtype=np.float64)
+    k, t = B.k, B.t
+    if side == "left":
+        x = t[k - 1]
+        idx = [ndrop + d for d in range(1, q + 2)]
+        bs = [_eval_op(last, k, t, i, x, True) for i in idx]
+        for l in range(1, q + 1):
+            b0, b1 = bs[l - 1], bs[l]
+            r = T(2) / (b0 - b1)
+            A[l + nc - 2, l - 1] = -b1 * r
+            A[l + nc - 1, l - 1] = b0 * r
+    else:
+        N = len(B)
+        x = t[N]
+        M = N - ndrop
+        idx = [M - d + 1 for d in range(1, q + 2)]
+        bs = [_eval_op(last, k, t, i, x, False) for i in idx]
+        for l in range(1, q + 1):
+            b0, b1 = bs[q - l + 1], bs[q - l]
+            r = T(2) / (b0 - b1)
+            A[l - 1, l - 1] = -b1 * r
+            A[l, l - 1] = b0 * r
+    return ndrop, nc, A
+
+
+class RecombinedBSplineBasis(AbstractBSplineBasis):
+    """RecombinedBSplineBasis(B, ops) / (B, ops_left, ops_right)  (Recombinations/bases.jl:223-245).
+
+    ops: a DifferentialOp, a tuple of them, or () / None for a free boundary."""
+
+    def __init__(self, B, ops_left, ops_right="same"):
+        if not isinstance(B, BSplineBasis):
+            raise ArgumentError("parent must be a BSplineBasis")
+        if ops_right == "same":
+            ops_right = ops_left
+        norm = lambda o: () if o is None else ((o,) if isinstance(o, DifferentialOp) else tuple(o))
+        self.parent = B
+        self.k = B.k
+        self.t = B.t
+        self.ops = (norm(ops_left), norm(ops_right))
+        ldrop, cl, ul = _make_submatrix(self.ops[0], B, "left")
+        rdrop, cr, lr = _make_submatrix(self.ops[1], B, "right")
+        self.cl, self.cr = cl, cr
+        self.nl, self.nr = ul.shape[1], lr.shape[1]
+        self.ul, self.lr = ul, lr
+        self._len = len(B) - cl - cr
+        self._handle, self._dt = _create_basis(
+            BASIS_RECOMBINED, self.k, self.t,
+            dict(cl=cl, cr=cr, nl=self.nl, nr=self.nr, ul=ul, lr=lr))
+
+    def knots(self):
+        return self.t
+
+    def boundaries(self):
+        return self.parent.boundaries()
+
+    def num_constraints(self):
+        return self.cl, self.cr
+
+    def recombination_matrix(self):
+        """Dense RecombineMatrix (N x M) for tests (Recombinations/matrices.jl:416-452)."""
+        N, M = len(self.parent), len(self)
+        A = np.zeros((N, M))
+        for j in range(self.nl):
+            A[:self.ul.shape[0], j] = self.ul[:, j]
+        for j in range(self.nl, M - self.nr):
+            A[j + self.cl, j] = 1.0
+        h = M - self.nr
+        for j in range(self.nr):
+            A[h + self.cl:h + self.cl + self.lr.shape[0], h + j] = self.lr[:, j]
+        return A
+
+
+def knots(B):
+    return B.knots()
+
+
+def order(B):
+    return B.k
+
+
+def boundaries(B):
+    return B.boundaries()
+
+
+def find_knot_interval(B, x):
+    """find_knot_interval(knots(B), x) broadcast over x (BSplines/evaluate_all.jl:102-119,
+    periodic.jl:85-100).  Returns (i, zone): int64 / int8 arrays (CUDA tensors if x is one)."""
+    xd, on_dev = _to_device(x, B._dt)
+    xd = xd.reshape(-1)
+    idx = torch.empty(xd.numel(), dtype=torch.int64, device=xd.device)
+    zone = torch.empty(xd.numel(), dtype=torch.int8, device=xd.device)
+    check(lib.bsk_find_knot_interval(B._handle, _ptr(xd), xd.numel(), _ptr(idx), _ptr(zone), _stream()))
+    if on_dev:
+        return idx, zone
+    return idx.cpu().numpy(), zone.cpu().numpy()
+
+
+def evaluate_all(B, x, op=None, T=None, ileft=None):
+    """evaluate_all(B, x, [op], [T]; [ileft]) -> (i, bs)  (BSplines/evaluate_all.jl:9-64).
+
+    x may be a scalar (returns (int, tuple) like the reference) or a vector / CUDA tensor
+    (returns int64[n] and T[n, k], reversed order per row as in the reference)."""
+    if op is not None and not isinstance(op, DifferentialOp):
+        op, T = None, op                                                # evaluate_all(B, x, T)
+    nd = 0 if op is None else op.n
+    scalar = np.isscalar(x)
+    xin = [x] if scalar else x
+    out_dt = B._dt if T is None else _dtype_code(T)
+    xd, on_dev = _to_device(xin, B._dt)
+    xd = xd.reshape(-1)
+    n = xd.numel()
+    idx = torch.empty(n, dtype=torch.int64, device=xd.device)
+    bs = torch.empty((n, B.k), dtype=_TORCH[out_dt], device=xd.device)
+    il = None
+    if ileft is not None:
+        il, _ = (ileft, True) if isinstance(ileft, torch.Tensor) and ileft.is_cuda else (
+            torch.as_tensor(np.atleast_1d(np.asarray(ileft, dtype=np.int64))).cuda(), False)
+        if il.numel() != n:
+            raise DimensionMismatch("ileft must have one entry per point")
+    check(lib.bsk_evaluate_all(B._handle, _ptr(xd), n, nd, out_dt, _ptr(il) if il is not None else None,
+                               _ptr(idx), _ptr(bs), _stream()))
+    if scalar:
+        return int(idx[0].item()), tuple(bs[0].cpu().numpy().tolist()) if out_dt == BSK_F64 else \
+            tuple(np.float32(v) for v in bs[0].cpu().numpy())
+    if on_dev:
+        return idx, bs
+    return idx.cpu().numpy(), bs.cpu().numpy()
+
+
+# ---- splines ----------------------------------------------------------------------------------
+
+class Spline:
+    """Spline(B, coefs) (Splines/spline.jl:41-60); callable (spline.jl:144)."""
+
+    def __init__(self, B, coefs=None, _handle=None, _basis_info=None):
+        self.basis = B
+        if _handle is not None:
+            self._handle = _handle
+            self._dt, self.k = _basis_info
+            return
+        self._dt = B._dt
+        self.k = B.k
+        c = np.ascontiguousarray(np.asarray(coefs, dtype=_NP[B._dt]))
+        if c.ndim != 1 or c.size != len(B):
+            raise DimensionMismatch("wrong number of coefficients")     # spline.jl:52-56
+        out = C.c_void_p()
+        check(lib.bsk_spline_create(B._handle, c.ctypes.data_as(C.c_void_p), c.size, C.byref(out)))
+        self._handle = out
+        self._coefs = c
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None:
+            try:
+                lib.bsk_spline_destroy(h)
+            except Exception:
+                pass
+
+    def order(self):
+        return self.k
+
+    def _meta(self):
+        k, nc, nk = C.c_int32(), C.c_int64(), C.c_int64()
+        check(lib.bsk_spline_order(self._handle, C.byref(k), C.byref(nc), C.byref(nk)))
+        return k.value, nc.value, nk.value
+
+    def coefficients(self):
+        """Coefficients in the evaluation basis (parent basis for recombined splines)."""
+        _, nc, _ = self._meta()
+        out = np.empty(nc, dtype=_NP[self._dt])
+        check(lib.bsk_spline_coefficients(self._handle, out.ctypes.data_as(C.c_void_p), nc))
+        return out
+
+    def knots(self):
+        _, _, nk = self._meta()
+        out = np.empty(nk, dtype=_NP[self._dt])
+        check(lib.bsk_spline_knots(self._handle, out.ctypes.data_as(C.c_void_p), nk))
+        return out
+
+    def set_coefficients_device(self, d_coefs, stride=1):
+        """Re-point at device-resident coefficients (e.g. a column of a batched solve)."""
+        n = len(self.basis)
+        check(lib.bsk_spline_set_coefs_device(self._handle, _ptr(d_coefs), n, stride, _stream()))
+
+    def derivative(self, n=1):
+        """Derivative(n) * S (Splines/spline.jl:272-330)."""
+        if n == 0:
+            return self
+        out = C.c_void_p()
+        check(lib.bsk_spline_derivative(self._handle, int(n), C.byref(out)))
+        return Spline(self.basis, _handle=out, _basis_info=(self._dt, self.k - n))
+
+    def evaluate(self, x, derivs=(0,), algo=EVAL_AUTO, out=None):
+        """Evaluate D^d S for every d in `derivs` at all points, in one pass over x.
+        x: scalar, numpy array (host path, pipelined H2D/kernel/D2H) or CUDA tensor."""
+        derivs = [int(d) for d in derivs]
+        nout = len(derivs)
+        dv = (C.c_int32 * nout)(*derivs)
+        scalar = np.isscalar(x)
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            if x.dtype != _TORCH[self._dt]:
+                raise ArgumentError("device vector has dtype %s, expected %s" % (x.dtype, _TORCH[self._dt]))
+            xd = x.contiguous().reshape(-1)
+            outs = out if out is not None else [torch.empty_like(xd) for _ in derivs]
+            ptrs = (C.c_void_p * nout)(*[o.data_ptr() for o in outs])
+            check(lib.bsk_spline_eval(self._handle, _ptr(xd), xd.numel(), nout, dv, ptrs, algo, _stream()))
+            return [o.reshape(x.shape) for o in outs]
+        xh = np.ascontiguousarray(np.atleast_1d(np.asarray(x, dtype=_NP[self._dt])))
+        outs = out if out is not None else [np.empty_like(xh) for _ in derivs]
+        ptrs = (C.c_void_p * nout)(*[o.ctypes.data for o in outs])
+        _device()
+        check(lib.bsk_spline_eval_host(self._handle, xh.ctypes.data_as(C.c_void_p), xh.size, nout, dv,
+                                       ptrs, algo))
+        if scalar:
+            return [o[0] for o in outs]
+        return outs
+
+    def __call__(self, x, algo=EVAL_AUTO):
+        return self.evaluate(x, (0,), algo)[0]
+
+
+# ---- collocation ----------------------------------------------------------------------------------
+
+def collocation_points(B):
+    """collocation_points(B) (Collocation/points.jl:46-126,164-225): Greville sites with the
+    two-step Kahan sliding sum; periodic even order -> the knots themselves."""
+    if isinstance(B, PeriodicBSplineBasis):
+        if B.k % 2 == 0:
+            return B.t[:-1].copy()                                      # SameAsKnots (points.jl:176)
+        raise _lib.UnsupportedError("AvgKnots for odd-order periodic bases is not implemented")
+    k, t = B.k, B.t
+    T = t.dtype.type
+    N = len(B)
+    cl = B.cl if isinstance(B, RecombinedBSplineBasis) else 0
+    a, b = B.boundaries()
+    x = np.empty(N, dtype=t.dtype)
+    tsum = T(0)
+    comp = T(0)
+    for i in range(N):
+        ii = i + cl
+        if i == 0:
+            tsum = T(0)
+            for j in range(2, k + 1):
+                tsum = tsum + t[ii + j - 1]
+        else:
+            prev = tsum
+            y = t[ii + k - 1] - comp
+            tsum = prev + y
+            comp = (tsum - prev) - y
+            prev = tsum
+            y = -t[ii] - comp
+            tsum = prev + y
+            comp = (tsum - prev) - y
+        xi = T(tsum / T(k - 1))
+        if isinstance(B, BSplineBasis):                                 # ensure_points_at_boundaries
+            if i == 0:
+                xi = a
+            elif i == N - 1:
+                xi = b
+        x[i] = min(max(xi, a), b)
+    return x
+
+
+class CollocationMatrix:
+    """CollocationMatrix band store (2k-3) x n, column-major, on the device
+    (Collocation/matrix.jl:40-117), with lu! / ldiv! (matrix.jl:132-271)."""
+
+    def __init__(self, band, _handle=None):
+        self._handle = _handle
+        self.factored = False
+        if band is None:
+            return
+        if isinstance(band, torch.Tensor) and band.is_cuda:
+            # torch tensor of shape (n, nbands) row-major == (nbands, n) column-major
+            nb, n = band.shape[1], band.shape[0]
+            out = C.c_void_p()
+            check(lib.bsk_banded_create(_ptr(band), n, (nb - 1) // 2, (nb - 1) // 2, _device(), C.byref(out)))
+        else:
+            bh = np.asfortranarray(np.asarray(band, dtype=np.float64))
+            if bh.shape[0] % 2 != 1:
+                raise ArgumentError("odd number of bands expected")
+            nb, n = bh.shape
+            out = C.c_void_p()
+            check(lib.bsk_banded_create_host(bh.ctypes.data_as(C.c_void_p), n, (nb - 1) // 2, (nb - 1) // 2,
+                                             _device(), C.byref(out)))
+        self._handle = out
+        self.n, self.nbands = n, nb
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None:
+            try:
+                lib.bsk_banded_destroy(h)
+            except Exception:
+                pass
+
+    @property
+    def bandwidths(self):
+        h = (self.nbands - 1) // 2
+        return h, h
+
+    def data(self):
+        """(nbands, n) Fortran-ordered copy of the band store (factors after lu!)."""
+        out = np.empty((self.nbands, self.n), dtype=np.float64, order="F")
+        check(lib.bsk_banded_data(self._handle, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def dense(self):
+        w = self.data()
+        l, u = self.bandwidths
+        A = np.zeros((self.n, self.n))
+        for j in range(self.n):
+            for i in range(max(0, j - u), min(self.n, j + l + 1)):
+                A[i, j] = w[u + i - j, j]
+        return A
+
+    def lu_(self):
+        """lu!(C) (Collocation/matrix.jl:132-201)."""
+        info = C.c_int64(0)
+        st = lib.bsk_banded_lu(self._handle, C.byref(info))
+        check(st, info.value)
+        self.factored = True
+        return self
+
+    @property
+    def halo(self):
+        h = C.c_int32(0)
+        check(lib.bsk_banded_halo(self._handle, C.byref(h)))
+        return h.value
+
+    def ldiv_(self, Y, algo=SOLVE_AUTO):
+        """ldiv!(F, Y) in place; Y is (n, nrhs) with the RHS index fastest (matrix.jl:218-271)."""
+        if isinstance(Y, torch.Tensor) and Y.is_cuda:
+            if Y.dtype != torch.float64 or not Y.is_contiguous():
+                raise ArgumentError("Y must be a contiguous float64 CUDA tensor")
+            if Y.shape[0] != self.n:
+                raise DimensionMismatch("vectors `x` and `y` must have length %d" % self.n)
+            nrhs = Y.numel() // self.n if self.n else 0
+            check(lib.bsk_banded_solve(self._handle, _ptr(Y), nrhs, algo, _stream()))
+            return Y
+        if not (isinstance(Y, np.ndarray) and Y.dtype == np.float64 and Y.flags.c_contiguous):
+            raise ArgumentError("Y must be a C-contiguous float64 array (solved in place)")
+        if Y.shape[0] != self.n:
+            raise DimensionMismatch("vectors `x` and `y` must have length %d" % self.n)
+        _device()
+        check(lib.bsk_banded_solve_host(self._handle, Y.ctypes.data_as(C.c_void_p), Y.size // self.n, algo))
+        return Y
+
+
+class CyclicTridiagonalMatrix:
+    """CyclicTridiagonalMatrix(a, b, c) + ldiv! (Collocation/cyclic.jl:21-33,112-197),
+    factored once."""
+
+    def __init__(self, a, b, c):
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            self.n = a.numel()
+            out = C.c_void_p()
+            check(lib.bsk_cyclic_create_device(_ptr(a), _ptr(b), _ptr(c), self.n, _device(), C.byref(out)))
+            self.a, self.b, self.c = (v.cpu().numpy() for v in (a, b, c))
+        else:
+            a, b, c = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, b, c))
+            if not (a.size == b.size == c.size):
+                raise DimensionMismatch("all diagonals must have the same length")
+            self.n = a.size
+            out = C.c_void_p()
+            check(lib.bsk_cyclic_create(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                        c.ctypes.data_as(C.c_void_p), self.n, _device(), C.byref(out)))
+            self.a, self.b, self.c = a, b, c
+        self._handle = out
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None:
+            try:
+                lib.bsk_cyclic_destroy(h)
+            except Exception:
+                pass
+
+    def dense(self):
+        n = self.n
+        A = np.zeros((n, n))
+        for i in range(n):
+            A[i, i] = self.b[i]
+            A[i, (i - 1) % n] = self.a[i]
+            A[i, (i + 1) % n] = self.c[i]
+        return A
+
+    def ldiv_(self, Y):
+        if isinstance(Y, torch.Tensor) and Y.is_cuda:
+            if Y.dtype != torch.float64 or not Y.is_contiguous() or Y.shape[0] != self.n:
+                raise DimensionMismatch("all vectors must have length %d" % self.n)
+            check(lib.bsk_cyclic_solve(self._handle, _ptr(Y), Y.numel() // self.n, _stream()))
+            return Y
+        Yh = np.asarray(Y, dtype=np.float64)
+        if Yh.shape[0] != self.n:
+            raise DimensionMismatch("all vectors must have length %d" % self.n)
+        d = torch.from_numpy(np.ascontiguousarray(Yh)).cuda()
+        check(lib.bsk_cyclic_solve(self._handle, _ptr(d), d.numel() // self.n, _stream()))
+        Y[...] = d.cpu().numpy()
+        return Y
+
+
+def collocation_matrix(B, x, deriv=None, clip_threshold=None, return_outside=False):
+    """collocation_matrix(B, x, [Derivative(n)]; clip_threshold = eps(T))
+    (Collocation/Collocation.jl:111-120,209-251).  Periodic cubic bases give a
+    CyclicTridiagonalMatrix (Collocation.jl:138-146)."""
+    nd = 0 if deriv is None else deriv.n
+    clip = float(np.finfo(np.float64).eps) if clip_threshold is None else float(clip_threshold)
+    if B._dt != BSK_F64:
+        raise _lib.UnsupportedError("collocation assembly needs a Float64 basis")
+    xd, _ = _to_device(x, BSK_F64)
+    xd = xd.reshape(-1)
+    if xd.numel() != len(B):
+        raise ArgumentError("wrong dimensions of collocation matrix")   # Collocation.jl:214-216
+    nout = C.c_int64(0)
+    if isinstance(B, PeriodicBSplineBasis):
+        if B.k != 4:
+            raise _lib.UnsupportedError(
+                "periodic collocation is implemented for cubic splines only (the reference uses "
+                "SparseMatrixCSC + UMFPACK for other orders)")
+        n = len(B)
+        a = torch.empty(n, dtype=torch.float64, device="cuda")
+        b = torch.empty_like(a)
+        c = torch.empty_like(a)
+        check(lib.bsk_collocation_cyclic(B._handle, _ptr(xd), n, nd, clip, _ptr(a), _ptr(b), _ptr(c),
+                                         C.byref(nout), _stream()))
+        if nout.value:
+            raise ArgumentError("DomainError: %d entries outside of the matrix bands" % nout.value)
+        M = CyclicTridiagonalMatrix(a, b, c)
+        return (M, nout.value) if return_outside else M
+    k = B.k
+    nb = 2 * k - 3
+    band = torch.empty((len(B), nb), dtype=torch.float64, device="cuda")   # == (nb, n) column-major
+    check(lib.bsk_collocation_matrix(B._handle, _ptr(xd), xd.numel(), nd, clip, _ptr(band),
+                                     C.byref(nout), _stream()))
+    if nout.value:
+        import warnings
+        warnings.warn("Non-zero value outside of matrix bands (%d entries)" % nout.value)   # :239-244
+    M = CollocationMatrix(band)
+    return (M, nout.value) if return_outside else M
+
+
+def lu(C_):
+    return C_.lu_()
+
+
+def ldiv(F, Y, **kw):
+    return F.ldiv_(Y, **kw)
+
+
+# ---- interpolation ----------------------------------------------------------------------------------
+
+def make_knots(x, k, bc=None):
+    """make_knots (SplineInterpolations/SplineInterpolations.jl:302-326, 333-371)."""
+    x = np.asarray(x)
+    T = np.float64 if not np.issubdtype(x.dtype, np.floating) else x.dtype.type
+    x = x.astype(T)
+    N = x.size
+    if bc is None:
+        t = np.empty(N + k, dtype=T)
+        t[:k] = x[0]
+        t[N:] = x[-1]
+        kinv = T(1) / T(k - 1)
+        for i in range(1, N - k + 1):
+            ti = T(0)
+            for j in range(1, k):
+                ti = ti + x[i + j - 1]
+            t[k + i - 1] = ti * kinv
+        return t
+    L = T(bc.L)
+    if not (x[0] + L > x[-1]):
+        raise ArgumentError("endpoint x₁ + L must *not* be included in the interpolation points")
+    ts = np.empty(N + 1, dtype=T)
+    if k % 2 == 0:
+        ts[:-1] = x
+        ts[-1] = x[0] + L
+        return ts
+    x0 = x[0]
+    xn = x0 + L
+    xprev = x0
+    for i in range(1, N):
+        ts[i - 1] = (xprev + x[i]) / T(2)
+        xprev = x[i]
+    ts[N - 1] = (xprev + xn) / T(2)
+    ts[0] = x0
+    ts[N] = xn
+    return ts
+
+
+class SplineInterpolation:
+    """SplineInterpolation (SplineInterpolations.jl:56-119): basis + factorised collocation
+    matrix, reusable for many data sets on the same x through interpolate_ (= interpolate!)."""
+
+    def __init__(self, B, x):
+        N = len(B)
+        x = np.asarray(x)
+        if x.size != N:
+            raise DimensionMismatch("incompatible lengths of B-spline basis and collocation points")
+        self.basis = B
+        self.x = x
+        Cm = collocation_matrix(B, x)
+        self.C = Cm if isinstance(Cm, CyclicTridiagonalMatrix) else Cm.lu_()
+        self.spline = None
+        self.coefs = None
+
+    def interpolate_(self, y, algo=SOLVE_AUTO):
+        """interpolate!(itp, y) (SplineInterpolations.jl:140-152).  y: length-N vector, or an
+        (N, M) batch with the data-set index fastest (== Vector{SVector{M}}); CUDA tensors are
+        solved in place and stay on the device."""
+        N = len(self.basis)
+        if isinstance(y, torch.Tensor) and y.is_cuda:
+            if y.shape[0] != N:
+                raise DimensionMismatch("input data has incorrect length")
+            Y = y
+        else:
+            yh = np.asarray(y)
+            if yh.shape[0] != N:
+                raise DimensionMismatch("input data has incorrect length")
+            Y = torch.from_numpy(np.ascontiguousarray(yh, dtype=np.float64)).cuda()
+        if isinstance(self.C, CyclicTridiagonalMatrix):
+            self.C.ldiv_(Y)
+        else:
+            self.C.ldiv_(Y, algo=algo)
+        self.coefs = Y
+        if Y.dim() == 1:
+            self.spline = Spline(self.basis, Y.cpu().numpy())
+        else:
+            self.spline = None
+        return self
+
+    def spline_of(self, column=0):
+        """Spline for one data set of a batch (device-resident coefficients, strided)."""
+        Y = self.coefs
+        if Y.dim() == 1:
+            return self.spline
+        M = Y.shape[1]
+        S = Spline(self.basis, np.zeros(len(self.basis)))
+        S.set_coefficients_device(Y.reshape(-1)[column:], stride=M)
+        return S
+
+    def __call__(self, x, **kw):
+        return self.spline(x, **kw)
+
+
+def interpolate(x, y, order, bc=None):
+    """interpolate(x, y, BSplineOrder(k), [bc]) (SplineInterpolations.jl:260-297)."""
+    k = _order(order)
+    x = np.asarray(x)
+    xf = x.astype(np.float64) if not np.issubdtype(x.dtype, np.floating) else x
+    if bc is None:
+        t = make_knots(xf, k, None)
+        B = BSplineBasis(k, t, augment=False)
+    elif isinstance(bc, Periodic):
+        ts = make_knots(xf, k, bc)
+        B = PeriodicBSplineBasis(k, ts)
+    else:
+        raise _lib.UnsupportedError("Natural() interpolation is not on the device path yet")
+    itp = SplineInterpolation(B, xf)
+    return itp.interpolate_(y)

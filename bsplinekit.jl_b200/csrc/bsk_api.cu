@@ -1,0 +1,255 @@
+// bsk_api.cu — library utilities, basis handles, search-LUT construction.
+#include <algorithm>
+
+#include "handles.cuh"
+
+namespace bsk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace bsk
+
+using namespace bsk;
+
+extern "C" {
+
+const char *bsk_version(void) { return "bsplinekit_b200 0.1.0 (sm_100a)"; }
+
+size_t bsk_last_error(char *buf, size_t buflen) {
+    size_t n = strlen(g_err);
+    if (buf && buflen) {
+        size_t m = n < buflen - 1 ? n : buflen - 1;
+        memcpy(buf, g_err, m);
+        buf[m] = 0;
+    }
+    return n;
+}
+
+bsk_status bsk_device_count(int32_t *count) {
+    BSK_REQUIRE(count, BSK_ERR_ARGUMENT, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+        return BSK_ERR_CUDA;
+    }
+    *count = n;
+    return BSK_OK;
+}
+
+bsk_status bsk_malloc(int32_t device, size_t nbytes, void **d_ptr) {
+    BSK_REQUIRE(d_ptr, BSK_ERR_ARGUMENT, "d_ptr is NULL");
+    BSK_CUDA(cudaSetDevice(device));
+    BSK_CUDA(cudaMalloc(d_ptr, nbytes ? nbytes : 1));
+    return BSK_OK;
+}
+
+bsk_status bsk_free(int32_t device, void *d_ptr) {
+    BSK_CUDA(cudaSetDevice(device));
+    BSK_CUDA(cudaFree(d_ptr));
+    return BSK_OK;
+}
+
+bsk_status bsk_memcpy_h2d(int32_t device, void *d_dst, const void *h_src, size_t nbytes, void *stream) {
+    BSK_CUDA(cudaSetDevice(device));
+    BSK_CUDA(cudaMemcpyAsync(d_dst, h_src, nbytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return BSK_OK;
+}
+
+bsk_status bsk_memcpy_d2h(int32_t device, void *h_dst, const void *d_src, size_t nbytes, void *stream) {
+    BSK_CUDA(cudaSetDevice(device));
+    BSK_CUDA(cudaMemcpyAsync(h_dst, d_src, nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return BSK_OK;
+}
+
+bsk_status bsk_stream_create(int32_t device, void **stream) {
+    BSK_REQUIRE(stream, BSK_ERR_ARGUMENT, "stream is NULL");
+    BSK_CUDA(cudaSetDevice(device));
+    cudaStream_t s;
+    BSK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return BSK_OK;
+}
+
+bsk_status bsk_stream_destroy(int32_t device, void *stream) {
+    BSK_CUDA(cudaSetDevice(device));
+    BSK_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return BSK_OK;
+}
+
+bsk_status bsk_stream_sync(int32_t device, void *stream) {
+    BSK_CUDA(cudaSetDevice(device));
+    BSK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return BSK_OK;
+}
+
+bsk_status bsk_event_create(int32_t device, void **event) {
+    BSK_REQUIRE(event, BSK_ERR_ARGUMENT, "event is NULL");
+    BSK_CUDA(cudaSetDevice(device));
+    cudaEvent_t e;
+    BSK_CUDA(cudaEventCreate(&e));
+    *event = (void *)e;
+    return BSK_OK;
+}
+
+bsk_status bsk_event_record(void *event, void *stream) {
+    BSK_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return BSK_OK;
+}
+
+bsk_status bsk_event_elapsed_ms(void *start, void *stop, float *ms) {
+    BSK_REQUIRE(ms, BSK_ERR_ARGUMENT, "ms is NULL");
+    BSK_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+    BSK_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return BSK_OK;
+}
+
+bsk_status bsk_event_destroy(void *event) {
+    BSK_CUDA(cudaEventDestroy((cudaEvent_t)event));
+    return BSK_OK;
+}
+
+}  // extern "C"
+
+// ---- search LUT -----------------------------------------------------------------------
+// For each of `ncell` uniform cells over [v[0], v[n-1]] store a bracket [lo, hi] that is
+// guaranteed to contain searchsortedlast(v, x) for every x whose *computed* cell index is
+// c; `margin` (in cells) absorbs the rounding of (x - v[0]) * scale in the knot dtype.
+namespace bsk {
+
+static void build_lut(const std::vector<double> &v, int dtype, std::vector<uint32_t> &lut,
+                      int &ncell, double &scale) {
+    const int n = (int)v.size();
+    lut.clear();
+    ncell = 0;
+    scale = 0;
+    double range = v[n - 1] - v[0];
+    if (!(range > 0) || !std::isfinite(range) || n >= (1 << 24)) return;
+    int nc = 64;
+    while (nc < 4 * n && nc < 65536) nc <<= 1;
+    double sc = (double)nc / range;
+    if (dtype == BSK_F32) sc = (double)(float)sc;
+    if (!std::isfinite(sc) || !(sc > 0)) return;
+    const double margin = (dtype == BSK_F32) ? 0.05 : 1e-6;
+    lut.resize(nc);
+    for (int c = 0; c < nc; ++c) {
+        double e_lo = v[0] + ((double)c - margin) / sc;
+        double e_hi = v[0] + ((double)c + 1.0 + margin) / sc;
+        // lo = #{v < e_lo}, hi = #{v <= e_hi}
+        int lo = (int)(std::lower_bound(v.begin(), v.end(), e_lo) - v.begin());
+        int hi = (int)(std::upper_bound(v.begin(), v.end(), e_hi) - v.begin());
+        if (c == 0) lo = 0;
+        if (c == nc - 1) hi = n;
+        int w = hi - lo;
+        if (w > 254) w = 255;
+        lut[c] = (uint32_t)lo | ((uint32_t)w << 24);
+    }
+    ncell = nc;
+    scale = sc;
+}
+
+}  // namespace bsk
+
+extern "C" {
+
+bsk_status bsk_basis_create(int32_t kind, int32_t k, int32_t dtype, const void *h_knots,
+                            int64_t nknots, const bsk_recomb_desc *recomb, int32_t device,
+                            bsk_basis **out) {
+    BSK_REQUIRE(out, BSK_ERR_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    BSK_REQUIRE(kind >= 0 && kind <= 2, BSK_ERR_ARGUMENT, "unknown basis kind %d", kind);
+    BSK_REQUIRE(k >= 1, BSK_ERR_ARGUMENT, "B-spline order must be k >= 1");   // basis.jl:80-82
+    BSK_REQUIRE(k <= BSK_MAXK, BSK_ERR_UNSUPPORTED, "orders 1..%d are supported (got %d)",
+                BSK_MAXK, k);
+    BSK_REQUIRE(dtype == BSK_F32 || dtype == BSK_F64, BSK_ERR_ARGUMENT, "bad dtype");
+    BSK_REQUIRE(h_knots, BSK_ERR_ARGUMENT, "knots is NULL");
+    if (kind == BSK_BASIS_PERIODIC)
+        BSK_REQUIRE(nknots >= 2, BSK_ERR_ARGUMENT, "periodic basis needs >= 2 breakpoints");
+    else
+        BSK_REQUIRE(nknots >= 2 * (int64_t)k, BSK_ERR_ARGUMENT, "knot vector too short: %lld < 2k",
+                    (long long)nknots);
+    BSK_REQUIRE(nknots < (1ll << 30), BSK_ERR_UNSUPPORTED, "too many knots");
+    BSK_REQUIRE((kind == BSK_BASIS_RECOMBINED) == (recomb != nullptr), BSK_ERR_ARGUMENT,
+                "recombination descriptor must be given for (and only for) a recombined basis");
+
+    bsk_basis *b = new bsk_basis();
+    b->kind = kind; b->k = k; b->dtype = dtype; b->device = device;
+    b->nt = nknots;
+    b->N = (kind == BSK_BASIS_PERIODIC) ? nknots - 1 : nknots - k;
+    b->len = b->N;
+    b->h_knots.resize(nknots);
+    for (int64_t i = 0; i < nknots; ++i)
+        b->h_knots[i] = dtype == BSK_F64 ? ((const double *)h_knots)[i] : (double)((const float *)h_knots)[i];
+    b->d_knots = nullptr; b->d_lut = nullptr; b->ncell = 0; b->lut_scale = 0;
+    memset(&b->rv, 0, sizeof(b->rv));
+
+    if (kind == BSK_BASIS_RECOMBINED) {
+        const bsk_recomb_desc *r = recomb;
+        bool ok = r->cl >= 0 && r->cr >= 0 && r->nl >= 0 && r->nr >= 0 && r->ul_rows * r->nl <= 36 &&
+                  r->lr_rows * r->nr <= 36 && (r->nl == 0 || r->ul) && (r->nr == 0 || r->lr);
+        if (!ok) { delete b; set_error("bad recombination descriptor"); return BSK_ERR_ARGUMENT; }
+        b->rv.enabled = 1;
+        b->rv.cl = r->cl; b->rv.cr = r->cr; b->rv.nl = r->nl; b->rv.nr = r->nr;
+        b->rv.ul_rows = r->ul_rows; b->rv.lr_rows = r->lr_rows;
+        b->rv.M = (int)(b->N - r->cl - r->cr);
+        for (int i = 0; i < r->ul_rows * r->nl; ++i) b->rv.ul[i] = r->ul[i];
+        for (int i = 0; i < r->lr_rows * r->nr; ++i) b->rv.lr[i] = r->lr[i];
+        b->len = b->rv.M;
+    }
+
+    // walk-back target of find_knot_interval (evaluate_all.jl:108-115)
+    {
+        int64_t i = nknots;   // 1-based
+        double tlast = b->h_knots[nknots - 1];
+        do { i -= 1; } while (i > 1 && b->h_knots[i - 1] == tlast);
+        b->ilast = (int)i;
+    }
+
+    cudaError_t e = cudaSetDevice(device);
+    size_t es = dtype == BSK_F64 ? 8 : 4;
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_knots, es * nknots);
+    if (e == cudaSuccess) e = cudaMemcpy(b->d_knots, h_knots, es * nknots, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        std::vector<uint32_t> lut;
+        build_lut(b->h_knots, dtype, lut, b->ncell, b->lut_scale);
+        if (b->ncell > 0) {
+            e = cudaMalloc((void **)&b->d_lut, sizeof(uint32_t) * lut.size());
+            if (e == cudaSuccess)
+                e = cudaMemcpy(b->d_lut, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice);
+        }
+    }
+    if (e != cudaSuccess) {
+        set_error("basis upload failed: %s", cudaGetErrorString(e));
+        if (b->d_knots) cudaFree(b->d_knots);
+        if (b->d_lut) cudaFree(b->d_lut);
+        delete b;
+        return BSK_ERR_CUDA;
+    }
+    *out = b;
+    return BSK_OK;
+}
+
+bsk_status bsk_basis_destroy(bsk_basis *b) {
+    if (!b) return BSK_OK;
+    cudaSetDevice(b->device);
+    if (b->d_knots) cudaFree(b->d_knots);
+    if (b->d_lut) cudaFree(b->d_lut);
+    delete b;
+    return BSK_OK;
+}
+
+bsk_status bsk_basis_length(const bsk_basis *b, int64_t *len) {
+    BSK_REQUIRE(b && len, BSK_ERR_ARGUMENT, "NULL argument");
+    *len = b->len;
+    return BSK_OK;
+}
+
+}  // extern "C"

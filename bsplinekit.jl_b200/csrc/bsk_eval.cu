@@ -1,0 +1,914 @@
+// bsk_eval.cu — K1 knot_interval, K2 evaluate_all, K3 spline_eval (de Boor and
+// local-polynomial table), spline handles, Derivative(n) * S.
+//
+// Reference bodies replaced (paths relative to the BSplineKit.jl tree):
+//   find_knot_interval      src/BSplines/evaluate_all.jl:102-126, periodic.jl:85-100
+//   _evaluate_all           src/BSplines/evaluate_all.jl:128-204, 271-314
+//   evaluate_all(::Recombined...) src/Recombinations/bases.jl:386-420
+//   (S::Spline)(x)          src/Splines/spline.jl:144-209
+//   Derivative(n) * S       src/Splines/spline.jl:272-330, Splines/periodic.jl:76-117
+#include <algorithm>
+
+#include "handles.cuh"
+
+using namespace bsk;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr size_t kSmemStageLimit = 200 * 1024;   // per-CTA budget for staged tables
+
+template <typename KT>
+KnotView<KT> make_view(const bsk_basis *b) {
+    KnotView<KT> kv;
+    kv.t = (const KT *)b->d_knots;
+    kv.nt = (int)b->nt;
+    kv.N = (int)b->N;
+    kv.k = b->k;
+    kv.kind = b->kind == BSK_BASIS_PERIODIC ? 1 : 0;
+    kv.ilast = b->ilast;
+    kv.a = (KT)b->h_knots.front();
+    kv.b = (KT)b->h_knots.back();
+    kv.period = (KT)((KT)b->h_knots.back() - (KT)b->h_knots.front());
+    kv.lut = b->d_lut;
+    kv.ncell = b->ncell;
+    kv.lut_scale = (KT)b->lut_scale;
+    return kv;
+}
+
+inline int grid_for(int64_t n, int device, int ctas_per_sm) {
+    int64_t want = (n + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)sm_count(device) * ctas_per_sm;
+    return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+// Stage knots (+ LUT) into dynamic shared memory; returns the knot pointer to use.
+template <typename KT>
+__device__ __forceinline__ const KT *stage_knots(KnotView<KT> &kv, unsigned char *smem, int stage,
+                                                 size_t &off) {
+    if (!stage) return kv.t;
+    KT *st = (KT *)(smem + off);
+    for (int i = threadIdx.x; i < kv.nt; i += blockDim.x) st[i] = kv.t[i];
+    off += ((size_t)kv.nt * sizeof(KT) + 15) & ~(size_t)15;
+    if (kv.lut) {
+        uint32_t *sl = (uint32_t *)(smem + off);
+        for (int i = threadIdx.x; i < kv.ncell; i += blockDim.x) sl[i] = kv.lut[i];
+        off += (size_t)kv.ncell * 4;
+        kv.lut = sl;
+    }
+    return st;
+}
+
+template <typename KT>
+size_t knots_smem_bytes(const bsk_basis *b) {
+    return (((size_t)b->nt * sizeof(KT) + 15) & ~(size_t)15) + (size_t)b->ncell * 4;
+}
+
+// ---- K1 ---------------------------------------------------------------------------------
+template <int KIND, typename KT>
+__global__ void __launch_bounds__(kThreads)
+k_find_interval(KnotView<KT> kv, const KT *__restrict__ x, int64_t n, int64_t *__restrict__ idx,
+                int8_t *__restrict__ zone, int stage) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    size_t off = 0;
+    const KT *t = stage_knots(kv, smem, stage, off);
+    __syncthreads();
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        int z;
+        int i = find_interval<KIND>(kv, t, x[p], z);
+        idx[p] = i;
+        if (zone) zone[p] = (int8_t)z;
+    }
+}
+
+// ---- K2 ---------------------------------------------------------------------------------
+template <int K, int KIND, typename KT, typename VT>
+__global__ void __launch_bounds__(kThreads)
+k_evaluate_all(KnotView<KT> kv, RecombView rv, const KT *__restrict__ x, int64_t n, int deriv,
+               const int64_t *__restrict__ ileft, int64_t *__restrict__ idx, VT *__restrict__ bs,
+               int stage) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    size_t off = 0;
+    const KT *t = stage_knots(kv, smem, stage, off);
+    __syncthreads();
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        VT bq[K];
+        long long il = ileft ? ileft[p] : 0;
+        if (rv.enabled && il != 0) il += rv.cl;          // bases.jl:393-395
+        int i = eval_all_point<K, KIND, KT, VT>(kv, t, x[p], deriv, il, bq);
+        if (rv.enabled) {
+            VT ph[K];
+            i = recombine_point<K, KT, VT>(rv, i, bq, ph);
+#pragma unroll
+            for (int j = 0; j < K; ++j) bq[j] = ph[j];
+        }
+        idx[p] = i;
+#pragma unroll
+        for (int j = 0; j < K; ++j) bs[p * K + j] = bq[j];
+    }
+}
+
+// ---- K3a: de Boor, reference operation order ------------------------------------------------
+template <int K, int KIND, typename T>
+__global__ void __launch_bounds__(kThreads)
+k_spline_deboor(KnotView<T> kv, const T *__restrict__ coefs, int ncoef, const T *__restrict__ x,
+                int64_t n, T *__restrict__ out, int stage) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    size_t off = 0;
+    const T *t = stage_knots(kv, smem, stage, off);
+    const T *c = coefs;
+    if (stage) {
+        T *sc = (T *)(smem + off);
+        for (int i = threadIdx.x; i < ncoef; i += blockDim.x) sc[i] = coefs[i];
+        c = sc;
+    }
+    __syncthreads();
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        T xv = x[p];
+        int z;
+        int i = find_interval<KIND>(kv, t, xv, z);
+        T r = (T)0;
+        // i < K can only happen for knot vectors without full end multiplicity, where the
+        // reference reads coefficients out of bounds; we return 0 there.
+        if (z == 0 && (KIND == 1 || (i >= K && i <= ncoef)))
+            r = deboor_point<K, KIND, T>(kv, t, c, ncoef, 1, i, xv);
+        out[p] = r;
+    }
+}
+
+// ---- K3b: local-polynomial (pp) table -------------------------------------------------------
+// Record r (REC values of T, 16-byte aligned): { t_lo, t_hi, c_0 .. c_{K-1}, pad }.
+// On [t_lo, t_hi):  D^d S(x) = sum_{m>=d} m!/(m-d)! c_m u^(m-d),  u = x - (t_lo + t_hi)/2.
+__constant__ double c_ff[BSK_MAXK][BSK_MAXK];   // falling factorials m!/(m-d)!
+
+template <int K, typename T> struct PPRec {
+    static constexpr int VPA = 16 / (int)sizeof(T);                 // values per 16 bytes
+    static constexpr int REC = ((K + 2 + VPA - 1) / VPA) * VPA;     // record length in values
+};
+
+constexpr int kMaxOut = 4;
+struct EvalOuts {
+    void *out[kMaxOut];
+    const void *dcoefs[kMaxOut];   // coefficients of Derivative(deriv) * S (periodic slow path)
+    int deriv[kMaxOut];
+    int nout;
+};
+
+template <int K, int KIND, typename T, int PTS>
+__global__ void __launch_bounds__(kThreads)
+k_spline_pp(KnotView<T> kv, int ncoef, const T *__restrict__ pp,
+            int nrec, const uint32_t *__restrict__ pplut, int ncell, T lut_scale,
+            const T *__restrict__ x, int64_t n, EvalOuts outs, int stage) {
+    constexpr int REC = PPRec<K, T>::REC;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const T *rec = pp;
+    const uint32_t *lut = pplut;
+    if (stage) {
+        T *sr = (T *)smem;
+        const int nvals = nrec * REC;
+        // 16-byte copies
+        const int4 *src = (const int4 *)pp;
+        int4 *dst = (int4 *)sr;
+        const int n16 = nvals * (int)sizeof(T) / 16;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+        uint32_t *sl = (uint32_t *)(smem + (size_t)n16 * 16);
+        for (int i = threadIdx.x; i < ncell; i += blockDim.x) sl[i] = pplut[i];
+        rec = sr;
+        lut = sl;
+    }
+    __syncthreads();
+    const T xa = kv.a, xb = kv.b;
+    const T x0 = rec[0];
+
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * PTS;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PTS; base < n; base += stride) {
+        T xv[PTS];
+        const bool full = base + PTS <= n;
+        if (full) {
+            if (PTS * sizeof(T) == 16) {
+                int4 raw = *(const int4 *)(x + base);
+                memcpy(xv, &raw, 16);
+            } else {
+#pragma unroll
+                for (int q = 0; q < PTS; ++q) xv[q] = x[base + q];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < PTS; ++q) xv[q] = base + q < n ? x[base + q] : xa;
+        }
+        T res[kMaxOut][PTS];
+#pragma unroll
+        for (int q = 0; q < PTS; ++q) {
+            T xq = xv[q];
+            bool slow = false;      // periodic point outside the main period
+            bool zero = false;
+            if (KIND == 1) {
+                if (!(xq >= xa && xq < xb)) slow = true;
+            } else {
+                if (!(xq >= xa && xq <= xb)) zero = true;      // zone != 0 (NaN handled below)
+            }
+            if (!(xq == xq)) { zero = false; slow = false; }
+            T xs = (slow || zero || !(xq == xq)) ? xa : xq;
+            // --- interval search over record left ends, LUT-bracketed
+            int c = (int)((xs - x0) * lut_scale);
+            c = c < 0 ? 0 : (c >= ncell ? ncell - 1 : c);
+            uint32_t e = lut[c];
+            int lo = (int)(e & 0xFFFFFFu);
+            int w = (int)(e >> 24);
+            int hi = (w != 255) ? lo + w : nrec;
+            hi = hi > nrec ? nrec : hi;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (xs < rec[mid * REC]) hi = mid; else lo = mid + 1;
+            }
+            int r = lo - 1;
+            r = r < 0 ? 0 : (r >= nrec ? nrec - 1 : r);
+            const T *R = rec + r * REC;
+            T cm[K];
+            T tlo, thi;
+            {
+                // vector loads of the record
+                T buf[REC];
+                const int4 *R4 = (const int4 *)R;
+#pragma unroll
+                for (int v = 0; v < REC * (int)sizeof(T) / 16; ++v) {
+                    int4 raw = R4[v];
+                    memcpy(&buf[v * (16 / (int)sizeof(T))], &raw, 16);
+                }
+                tlo = buf[0]; thi = buf[1];
+#pragma unroll
+                for (int m = 0; m < K; ++m) cm[m] = buf[2 + m];
+            }
+            T u = xs - (T)0.5 * (tlo + thi);
+#pragma unroll
+            for (int o = 0; o < kMaxOut; ++o) {
+                if (o < outs.nout) {
+                    const int d = outs.deriv[o];
+                    T acc = (T)0;
+#pragma unroll
+                    for (int m = K - 1; m >= 0; --m) {
+                        if (m >= d) {
+                            T cf = (d == 0) ? cm[m] : cm[m] * (T)c_ff[m][d];
+                            acc = fma(acc, u, cf);
+                        }
+                    }
+                    if (zero) acc = (T)0;
+                    if (!(xq == xq)) acc = xq;
+                    res[o][q] = acc;
+                }
+            }
+            if (KIND == 1 && slow) {
+                // Outside the main period: follow the reference exactly (knots shifted by
+                // multiples of L, x NOT wrapped; BSplines/periodic.jl:85-115), using the
+                // coefficient-differenced derivative splines.
+#pragma unroll
+                for (int o = 0; o < kMaxOut; ++o) {
+                    if (o < outs.nout) {
+                        KnotView<T> kd = kv;
+                        kd.k = K - outs.deriv[o];
+                        int z;
+                        int i = find_interval<1>(kd, kd.t, xq, z);
+                        res[o][q] = deboor_generic<1, T>(kd, kd.t, (const T *)outs.dcoefs[o], ncoef, 1,
+                                                         kd.k, i, xq);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) {
+            if (o < outs.nout) {
+                T *op = (T *)outs.out[o];
+                if (full && PTS * sizeof(T) == 16) {
+                    int4 raw;
+                    memcpy(&raw, res[o], 16);
+                    *(int4 *)(op + base) = raw;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < PTS; ++q)
+                        if (base + q < n) op[base + q] = res[o][q];
+                }
+            }
+        }
+    }
+}
+
+
+// ---- host-side helpers ---------------------------------------------------------------------
+
+#define BSK_DISPATCH_K(kval, ...)                                  \
+    switch (kval) {                                                \
+        case 1: { constexpr int K = 1; __VA_ARGS__; } break;       \
+        case 2: { constexpr int K = 2; __VA_ARGS__; } break;       \
+        case 3: { constexpr int K = 3; __VA_ARGS__; } break;       \
+        case 4: { constexpr int K = 4; __VA_ARGS__; } break;       \
+        case 5: { constexpr int K = 5; __VA_ARGS__; } break;       \
+        case 6: { constexpr int K = 6; __VA_ARGS__; } break;       \
+        case 7: { constexpr int K = 7; __VA_ARGS__; } break;       \
+        case 8: { constexpr int K = 8; __VA_ARGS__; } break;       \
+        default: break;                                            \
+    }
+
+template <typename F>
+cudaError_t set_smem(F func, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// Derivative coefficients, _derivative (Splines/spline.jl:293-330; periodic: Splines/periodic.jl:76-117)
+// computed in T (the reference differentiates in the coefficient type).  t = stored knots
+// (plain: full vector; periodic: breakpoints incl. endpoint).  Output: plain ncoef - nd, periodic ncoef.
+template <typename T>
+void derivative_coefs(int kind, int k, const std::vector<double> &tk, const std::vector<double> &c,
+                      int nd, std::vector<double> &out) {
+    const int64_t n = (int64_t)c.size();
+    std::vector<T> du(n);
+    if (kind == 0) {
+        for (int64_t i = 0; i < n; ++i) du[i] = (T)c[i];
+        for (int m = 1; m <= nd; ++m)
+            for (int64_t i = n; i >= 1; --i) {
+                T dt = (T)tk[i + k - m - 1] - (T)tk[i - 1];
+                if (dt == (T)0 || i == 1) du[i - 1] = (T)0;
+                else du[i - 1] = (T)(k - m) * (du[i - 1] - du[i - 2]) / dt;
+            }
+        out.resize(n - nd);
+        for (int64_t i = 0; i < n - nd; ++i) out[i] = (double)du[i + nd];
+    } else {
+        // knots(B') : same breakpoints, order k - nd (BSplines/periodic.jl:255-260)
+        std::vector<T> tt(tk.size());
+        for (size_t i = 0; i < tk.size(); ++i) tt[i] = (T)tk[i];
+        KnotView<T> kd;
+        kd.t = tt.data(); kd.nt = (int)tt.size(); kd.N = (int)tt.size() - 1; kd.k = k - nd; kd.kind = 1;
+        kd.ilast = 0; kd.a = tt.front(); kd.b = tt.back(); kd.period = tt.back() - tt.front();
+        kd.lut = nullptr; kd.ncell = 0; kd.lut_scale = 0;
+        const int64_t N = n;
+        const int delta = k / 2 - (k - nd) / 2;
+        for (int64_t i = 1; i <= N; ++i) {
+            int64_t j = i - delta;
+            while (j < 1) j += N;
+            while (j > N) j -= N;
+            du[j - 1] = (T)c[i - 1];
+        }
+        for (int m = 1; m <= nd; ++m) {
+            T du0 = du[N - 1];
+            for (int64_t i = N; i >= 1; --i) {
+                T dt = knot_at<1>(kd, kd.t, (int)(i + k - m)) - knot_at<1>(kd, kd.t, (int)i);
+                T prev = (i == 1) ? du0 : du[i - 2];
+                du[i - 1] = (T)(k - m) * (du[i - 1] - prev) / dt;
+            }
+        }
+        out.resize(N);
+        for (int64_t i = 0; i < N; ++i) out[i] = (double)du[i];
+    }
+}
+
+bsk_status clone_basis(const bsk_basis *b, int kind, int k, const std::vector<double> &knots,
+                       bsk_basis **out) {
+    if (b->dtype == BSK_F64)
+        return bsk_basis_create(kind, k, b->dtype, knots.data(), (int64_t)knots.size(), nullptr, b->device, out);
+    std::vector<float> kf(knots.begin(), knots.end());
+    return bsk_basis_create(kind, k, b->dtype, kf.data(), (int64_t)kf.size(), nullptr, b->device, out);
+}
+
+bsk_status upload_coefs(bsk_spline *s) {
+    const bsk_basis *b = s->basis;
+    size_t es = b->dtype == BSK_F64 ? 8 : 4;
+    BSK_CUDA(cudaSetDevice(b->device));
+    if (!s->d_coefs) BSK_CUDA(cudaMalloc(&s->d_coefs, es * std::max<int64_t>(1, s->ncoef)));
+    if (b->dtype == BSK_F64) {
+        BSK_CUDA(cudaMemcpy(s->d_coefs, s->h_coefs.data(), es * s->ncoef, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> cf(s->h_coefs.begin(), s->h_coefs.end());
+        BSK_CUDA(cudaMemcpy(s->d_coefs, cf.data(), es * s->ncoef, cudaMemcpyHostToDevice));
+    }
+    return BSK_OK;
+}
+
+void invalidate(bsk_spline *s) {
+    for (bsk_spline *d : s->derivs)
+        if (d) bsk_spline_destroy(d);
+    s->derivs.clear();
+    s->pp_valid = false;
+}
+
+// parent_coefficients (Recombinations/splines.jl:32-56): y = [ul * x[1:nl]; x[nl+1:H]; lr * x[H+1:N]]
+template <typename T>
+void parent_coefficients(const RecombView &rv, const std::vector<double> &x, std::vector<double> &y) {
+    const int N = (int)x.size();
+    const int Na = rv.nl, Nc = rv.nr, H = N - Nc;
+    y.clear();
+    for (int i = 0; i < rv.ul_rows; ++i) {
+        T acc = (T)0;
+        for (int j = 0; j < Na; ++j) {
+            T term = (T)rv.ul[i + j * rv.ul_rows] * (T)x[j];
+            acc = (j == 0) ? term : acc + term;
+        }
+        y.push_back((double)acc);
+    }
+    for (int i = Na; i < H; ++i) y.push_back(x[i]);
+    for (int i = 0; i < rv.lr_rows; ++i) {
+        T acc = (T)0;
+        for (int j = 0; j < Nc; ++j) {
+            T term = (T)rv.lr[i + j * rv.lr_rows] * (T)x[H + j];
+            acc = (j == 0) ? term : acc + term;
+        }
+        y.push_back((double)acc);
+    }
+}
+
+// set host coefficients given in the USER basis (recombined -> parent)
+bsk_status set_host_coefs(bsk_spline *s, const bsk_basis *user_basis, const std::vector<double> &c) {
+    if (user_basis->kind == BSK_BASIS_RECOMBINED) {
+        if (user_basis->dtype == BSK_F64) parent_coefficients<double>(user_basis->rv, c, s->h_coefs);
+        else parent_coefficients<float>(user_basis->rv, c, s->h_coefs);
+    } else {
+        s->h_coefs = c;
+    }
+    BSK_REQUIRE((int64_t)s->h_coefs.size() == s->ncoef, BSK_ERR_DIMENSION,
+                "internal: parent coefficient count %lld != %lld", (long long)s->h_coefs.size(),
+                (long long)s->ncoef);
+    invalidate(s);
+    return upload_coefs(s);
+}
+
+// ---- local-polynomial table ------------------------------------------------------------------
+bool pp_eligible(const bsk_spline *s) {
+    const bsk_basis *b = s->basis;
+    if (b->kind == BSK_BASIS_PERIODIC) return b->N >= 1;
+    // plain: need full multiplicity k at both ends so that [t1, tend] == [t_k, t_{N+1}]
+    const auto &t = b->h_knots;
+    return t[0] == t[b->k - 1] && t[b->N] == t[b->nt - 1] && t[0] < t[b->nt - 1];
+}
+
+template <typename T>
+bsk_status build_pp(bsk_spline *s) {
+    bsk_basis *b = s->basis;
+    const int k = b->k;
+    const int kind = b->kind == BSK_BASIS_PERIODIC ? 1 : 0;
+    const int VPA = 16 / (int)sizeof(T);
+    const int REC = ((k + 2 + VPA - 1) / VPA) * VPA;
+    // derivative chain in double
+    std::vector<std::vector<double>> dc(k);
+    dc[0] = s->h_coefs;
+    for (int m = 1; m < k; ++m) derivative_coefs<double>(kind, k, b->h_knots, s->h_coefs, m, dc[m]);
+    std::vector<T> recs;
+    std::vector<double> xi;   // record left ends
+    auto emit = [&](double lo, double hi, int i_plain_or_s) {
+        T tlo = (T)lo, thi = (T)hi;
+        T midT = (T)0.5 * (tlo + thi);
+        double mid = (double)midT;
+        size_t base = recs.size();
+        recs.resize(base + REC, (T)0);
+        recs[base] = tlo; recs[base + 1] = thi;
+        double fact = 1.0;
+        for (int m = 0; m < k; ++m) {
+            if (m > 0) fact *= (double)m;
+            KnotView<double> kd;
+            kd.kind = kind; kd.k = k - m; kd.lut = nullptr; kd.ncell = 0; kd.lut_scale = 0; kd.ilast = 0;
+            double val;
+            if (kind == 0) {
+                // knots of D^m basis: t[1+m : end-m]; interval index i - m
+                kd.t = b->h_knots.data() + m; kd.nt = (int)b->nt - 2 * m; kd.N = kd.nt - kd.k;
+                kd.a = kd.t[0]; kd.b = kd.t[kd.nt - 1]; kd.period = 0;
+                val = deboor_generic<0, double>(kd, kd.t, dc[m].data(), (int)dc[m].size(), 1, kd.k,
+                                                i_plain_or_s - m, mid);
+            } else {
+                kd.t = b->h_knots.data(); kd.nt = (int)b->nt; kd.N = (int)b->N;
+                kd.a = kd.t[0]; kd.b = kd.t[kd.nt - 1]; kd.period = kd.b - kd.a;
+                val = deboor_generic<1, double>(kd, kd.t, dc[m].data(), (int)dc[m].size(), 1, kd.k,
+                                                i_plain_or_s + kd.k / 2, mid);
+            }
+            recs[base + 2 + m] = (T)(val / fact);
+        }
+        xi.push_back((double)tlo);
+    };
+    const auto &t = b->h_knots;
+    if (kind == 0) {
+        for (int64_t i = k; i <= b->N; ++i)
+            if (t[i - 1] < t[i]) emit(t[i - 1], t[i], (int)i);
+    } else {
+        for (int64_t sidx = 1; sidx <= b->N; ++sidx)
+            if (t[sidx - 1] < t[sidx]) emit(t[sidx - 1], t[sidx], (int)sidx);
+    }
+    const int64_t nrec = (int64_t)xi.size();
+    BSK_REQUIRE(nrec >= 1, BSK_ERR_ARGUMENT, "spline has no non-empty knot interval");
+    xi.push_back(t[b->nt - 1]);
+    // LUT over the record left ends (+ right end of the domain)
+    std::vector<uint32_t> lut;
+    int ncell = 0;
+    double scale = 0;
+    {
+        // same construction as the knot LUT (bsk_api.cu), local copy to stay self-contained
+        const int n = (int)xi.size();
+        double range = xi[n - 1] - xi[0];
+        int nc = 64;
+        while (nc < 4 * n && nc < 65536) nc <<= 1;
+        double sc = (double)nc / range;
+        if (sizeof(T) == 4) sc = (double)(float)sc;
+        const double margin = sizeof(T) == 4 ? 0.05 : 1e-6;
+        lut.resize(nc);
+        for (int c = 0; c < nc; ++c) {
+            double e_lo = xi[0] + ((double)c - margin) / sc;
+            double e_hi = xi[0] + ((double)c + 1.0 + margin) / sc;
+            int lo = (int)(std::lower_bound(xi.begin(), xi.end(), e_lo) - xi.begin());
+            int hi = (int)(std::upper_bound(xi.begin(), xi.end(), e_hi) - xi.begin());
+            if (c == 0) lo = 0;
+            if (c == nc - 1) hi = n;
+            int w = hi - lo;
+            if (w > 254) w = 255;
+            lut[c] = (uint32_t)lo | ((uint32_t)w << 24);
+        }
+        ncell = nc;
+        scale = sc;
+    }
+    BSK_CUDA(cudaSetDevice(b->device));
+    if (s->d_pp) { cudaFree(s->d_pp); s->d_pp = nullptr; }
+    if (s->d_pp_lut) { cudaFree(s->d_pp_lut); s->d_pp_lut = nullptr; }
+    BSK_CUDA(cudaMalloc(&s->d_pp, recs.size() * sizeof(T)));
+    BSK_CUDA(cudaMemcpy(s->d_pp, recs.data(), recs.size() * sizeof(T), cudaMemcpyHostToDevice));
+    BSK_CUDA(cudaMalloc((void **)&s->d_pp_lut, lut.size() * 4));
+    BSK_CUDA(cudaMemcpy(s->d_pp_lut, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice));
+    s->pp_nrec = nrec;
+    s->pp_ncell = ncell;
+    s->pp_scale = scale;
+    s->pp_rec = REC;
+    s->pp_valid = true;
+    return BSK_OK;
+}
+
+bool g_ff_init[64] = {false};
+bsk_status init_ff(int device) {
+    if (device >= 0 && device < 64 && g_ff_init[device]) return BSK_OK;
+    double ff[BSK_MAXK][BSK_MAXK];
+    for (int m = 0; m < BSK_MAXK; ++m)
+        for (int d = 0; d < BSK_MAXK; ++d) {
+            double v = 0;
+            if (d <= m) { v = 1; for (int q = 0; q < d; ++q) v *= (double)(m - q); }
+            ff[m][d] = v;
+        }
+    BSK_CUDA(cudaMemcpyToSymbol(c_ff, ff, sizeof(ff)));
+    if (device >= 0 && device < 64) g_ff_init[device] = true;
+    return BSK_OK;
+}
+
+bsk_status get_derivative(const bsk_spline *s_const, int nd, bsk_spline **out) {
+    bsk_spline *s = const_cast<bsk_spline *>(s_const);
+    if ((int)s->derivs.size() <= nd) s->derivs.resize(nd + 1, nullptr);
+    if (!s->derivs[nd]) {
+        bsk_spline *d = nullptr;
+        bsk_status st = bsk_spline_derivative(s, nd, &d);
+        if (st != BSK_OK) return st;
+        s->derivs[nd] = d;
+    }
+    *out = s->derivs[nd];
+    return BSK_OK;
+}
+
+template <int K, int KIND, typename T>
+bsk_status launch_deboor(const bsk_spline *s, const T *d_x, int64_t n, T *d_out, cudaStream_t st) {
+    const bsk_basis *b = s->basis;
+    KnotView<T> kv = make_view<T>(b);
+    size_t smem = knots_smem_bytes<T>(b) + (size_t)s->ncoef * sizeof(T);
+    int stage = smem <= kSmemStageLimit ? 1 : 0;
+    if (!stage) smem = 0;
+    auto kern = k_spline_deboor<K, KIND, T>;
+    BSK_CUDA(set_smem(kern, smem));
+    int ctas = stage ? std::max<int>(1, (int)std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem, 1))) : 8;
+    int grid = grid_for(n, b->device, ctas);
+    kern<<<grid, kThreads, smem, st>>>(kv, (const T *)s->d_coefs, (int)s->ncoef, d_x, n, d_out, stage);
+    BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+template <typename T>
+bsk_status eval_deboor_t(const bsk_spline *s, const T *d_x, int64_t n, T *d_out, cudaStream_t st) {
+    const bsk_basis *b = s->basis;
+    bsk_status rc = BSK_ERR_UNSUPPORTED;
+    if (b->kind == BSK_BASIS_PERIODIC) {
+        BSK_DISPATCH_K(b->k, rc = (launch_deboor<K, 1, T>(s, d_x, n, d_out, st)))
+    } else {
+        BSK_DISPATCH_K(b->k, rc = (launch_deboor<K, 0, T>(s, d_x, n, d_out, st)))
+    }
+    if (rc == BSK_ERR_UNSUPPORTED) set_error("unsupported order %d", b->k);
+    return rc;
+}
+
+template <int K, int KIND, typename T>
+bsk_status launch_pp(const bsk_spline *s, const T *d_x, int64_t n, const EvalOuts &outs, bool force,
+                     cudaStream_t st, bool *used) {
+    constexpr int REC = PPRec<K, T>::REC;
+    constexpr int PTS = 16 / (int)sizeof(T);
+    const bsk_basis *b = s->basis;
+    size_t smem = (size_t)s->pp_nrec * REC * sizeof(T) + (size_t)s->pp_ncell * 4;
+    int stage = smem <= kSmemStageLimit ? 1 : 0;
+    if (!stage && !force) { *used = false; return BSK_OK; }
+    if (!stage) smem = 0;
+    *used = true;
+    KnotView<T> kv = make_view<T>(b);
+    bool aligned = (((uintptr_t)d_x) & 15) == 0;
+    for (int o = 0; o < outs.nout; ++o) aligned = aligned && ((((uintptr_t)outs.out[o]) & 15) == 0);
+    int ctas = stage ? std::max<int>(1, (int)std::min<size_t>(4, (220 * 1024) / std::max<size_t>(smem, 1))) : 4;
+    if (aligned) {
+        auto kern = k_spline_pp<K, KIND, T, PTS>;
+        BSK_CUDA(set_smem(kern, smem));
+        int grid = grid_for((n + PTS - 1) / PTS, b->device, ctas);
+        kern<<<grid, kThreads, smem, st>>>(kv, (int)s->ncoef, (const T *)s->d_pp, (int)s->pp_nrec,
+                                            s->d_pp_lut, s->pp_ncell, (T)s->pp_scale, d_x, n, outs, stage);
+    } else {
+        auto kern = k_spline_pp<K, KIND, T, 1>;
+        BSK_CUDA(set_smem(kern, smem));
+        int grid = grid_for(n, b->device, ctas);
+        kern<<<grid, kThreads, smem, st>>>(kv, (int)s->ncoef, (const T *)s->d_pp, (int)s->pp_nrec,
+                                            s->d_pp_lut, s->pp_ncell, (T)s->pp_scale, d_x, n, outs, stage);
+    }
+    BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+template <typename T>
+bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout, const int32_t *derivs,
+                         void *const *d_outs, int algo, cudaStream_t st) {
+    const bsk_basis *b = s->basis;
+    bool try_pp = (algo == BSK_EVAL_AUTO || algo == BSK_EVAL_PP) && pp_eligible(s);
+    if (algo == BSK_EVAL_PP && !try_pp) {
+        set_error("local-polynomial path needs full end-knot multiplicity");
+        return BSK_ERR_UNSUPPORTED;
+    }
+    if (try_pp) {
+        bsk_spline *sm = const_cast<bsk_spline *>(s);
+        if (!s->pp_valid) {
+            bsk_status rc = build_pp<T>(sm);
+            if (rc != BSK_OK) return rc;
+        }
+        bsk_status rc = init_ff(b->device);
+        if (rc != BSK_OK) return rc;
+        EvalOuts outs;
+        memset(&outs, 0, sizeof(outs));
+        outs.nout = nout;
+        for (int o = 0; o < nout; ++o) {
+            outs.out[o] = d_outs[o];
+            outs.deriv[o] = derivs[o];
+            outs.dcoefs[o] = s->d_coefs;
+            if (b->kind == BSK_BASIS_PERIODIC && derivs[o] > 0) {
+                bsk_spline *ds = nullptr;
+                rc = get_derivative(s, derivs[o], &ds);
+                if (rc != BSK_OK) return rc;
+                outs.dcoefs[o] = ds->d_coefs;
+            }
+        }
+        bool used = false;
+        rc = BSK_ERR_UNSUPPORTED;
+        if (b->kind == BSK_BASIS_PERIODIC) {
+            BSK_DISPATCH_K(b->k, rc = (launch_pp<K, 1, T>(s, d_x, n, outs, algo == BSK_EVAL_PP, st, &used)))
+        } else {
+            BSK_DISPATCH_K(b->k, rc = (launch_pp<K, 0, T>(s, d_x, n, outs, algo == BSK_EVAL_PP, st, &used)))
+        }
+        if (rc != BSK_OK) return rc;
+        if (used) return BSK_OK;
+    }
+    // de Boor in the reference's operation order, one pass per requested derivative
+    for (int o = 0; o < nout; ++o) {
+        const bsk_spline *ds = s;
+        if (derivs[o] > 0) {
+            bsk_spline *tmp = nullptr;
+            bsk_status rc = get_derivative(s, derivs[o], &tmp);
+            if (rc != BSK_OK) return rc;
+            ds = tmp;
+        }
+        bsk_status rc = eval_deboor_t<T>(ds, d_x, n, (T *)d_outs[o], st);
+        if (rc != BSK_OK) return rc;
+    }
+    return BSK_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+bsk_status bsk_find_knot_interval(const bsk_basis *b, const void *d_x, int64_t n, int64_t *d_idx,
+                                  int8_t *d_zone, void *stream) {
+    BSK_REQUIRE(b && (n == 0 || (d_x && d_idx)), BSK_ERR_ARGUMENT, "NULL argument");
+    if (n == 0) return BSK_OK;
+    BSK_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int periodic = b->kind == BSK_BASIS_PERIODIC;
+    if (b->dtype == BSK_F64) {
+        KnotView<double> kv = make_view<double>(b);
+        size_t smem = knots_smem_bytes<double>(b);
+        int stage = smem <= kSmemStageLimit;
+        if (!stage) smem = 0;
+        int grid = grid_for(n, b->device, 8);
+        if (periodic) {
+            BSK_CUDA(set_smem(k_find_interval<1, double>, smem));
+            k_find_interval<1, double><<<grid, kThreads, smem, st>>>(kv, (const double *)d_x, n, d_idx, d_zone, stage);
+        } else {
+            BSK_CUDA(set_smem(k_find_interval<0, double>, smem));
+            k_find_interval<0, double><<<grid, kThreads, smem, st>>>(kv, (const double *)d_x, n, d_idx, d_zone, stage);
+        }
+    } else {
+        KnotView<float> kv = make_view<float>(b);
+        size_t smem = knots_smem_bytes<float>(b);
+        int stage = smem <= kSmemStageLimit;
+        if (!stage) smem = 0;
+        int grid = grid_for(n, b->device, 8);
+        if (periodic) {
+            BSK_CUDA(set_smem(k_find_interval<1, float>, smem));
+            k_find_interval<1, float><<<grid, kThreads, smem, st>>>(kv, (const float *)d_x, n, d_idx, d_zone, stage);
+        } else {
+            BSK_CUDA(set_smem(k_find_interval<0, float>, smem));
+            k_find_interval<0, float><<<grid, kThreads, smem, st>>>(kv, (const float *)d_x, n, d_idx, d_zone, stage);
+        }
+    }
+    BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <int K, int KIND, typename KT, typename VT>
+bsk_status launch_eval_all(const bsk_basis *b, const KT *d_x, int64_t n, int deriv, const int64_t *d_ileft,
+                           int64_t *d_idx, VT *d_bs, cudaStream_t st) {
+    KnotView<KT> kv = make_view<KT>(b);
+    size_t smem = knots_smem_bytes<KT>(b);
+    int stage = smem <= kSmemStageLimit;
+    if (!stage) smem = 0;
+    auto kern = k_evaluate_all<K, KIND, KT, VT>;
+    BSK_CUDA(set_smem(kern, smem));
+    int grid = grid_for(n, b->device, 4);
+    kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs, stage);
+    BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+template <typename KT, typename VT>
+bsk_status eval_all_t(const bsk_basis *b, const void *d_x, int64_t n, int deriv, const int64_t *d_ileft,
+                      int64_t *d_idx, void *d_bs, cudaStream_t st) {
+    bsk_status rc = BSK_ERR_UNSUPPORTED;
+    if (b->kind == BSK_BASIS_PERIODIC) {
+        BSK_DISPATCH_K(b->k, rc = (launch_eval_all<K, 1, KT, VT>(b, (const KT *)d_x, n, deriv, d_ileft, d_idx, (VT *)d_bs, st)))
+    } else {
+        BSK_DISPATCH_K(b->k, rc = (launch_eval_all<K, 0, KT, VT>(b, (const KT *)d_x, n, deriv, d_ileft, d_idx, (VT *)d_bs, st)))
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+bsk_status bsk_evaluate_all(const bsk_basis *b, const void *d_x, int64_t n, int32_t deriv, int32_t out_dtype,
+                            const int64_t *d_ileft, int64_t *d_idx, void *d_bs, void *stream) {
+    BSK_REQUIRE(b && (n == 0 || (d_x && d_idx && d_bs)), BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(deriv >= 0, BSK_ERR_ARGUMENT, "derivative order must be >= 0");
+    BSK_REQUIRE(out_dtype == BSK_F32 || out_dtype == BSK_F64, BSK_ERR_ARGUMENT, "bad out_dtype");
+    BSK_REQUIRE(!(b->dtype == BSK_F32 && out_dtype == BSK_F64), BSK_ERR_UNSUPPORTED,
+                "Float64 output from a Float32 basis is not supported");
+    if (n == 0) return BSK_OK;
+    BSK_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (b->dtype == BSK_F64 && out_dtype == BSK_F64) return eval_all_t<double, double>(b, d_x, n, deriv, d_ileft, d_idx, d_bs, st);
+    if (b->dtype == BSK_F64 && out_dtype == BSK_F32) return eval_all_t<double, float>(b, d_x, n, deriv, d_ileft, d_idx, d_bs, st);
+    return eval_all_t<float, float>(b, d_x, n, deriv, d_ileft, d_idx, d_bs, st);
+}
+
+bsk_status bsk_spline_create(const bsk_basis *b, const void *h_coefs, int64_t ncoef, bsk_spline **out) {
+    BSK_REQUIRE(b && h_coefs && out, BSK_ERR_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    BSK_REQUIRE(ncoef == b->len, BSK_ERR_DIMENSION,
+                "wrong number of coefficients: got %lld, basis has length %lld",   // spline.jl:52-56
+                (long long)ncoef, (long long)b->len);
+    bsk_spline *s = new bsk_spline();
+    s->basis = nullptr; s->d_coefs = nullptr; s->owns_coefs = true; s->d_pp = nullptr;
+    s->d_pp_lut = nullptr; s->pp_valid = false; s->pp_nrec = 0; s->pp_ncell = 0; s->pp_scale = 0; s->pp_rec = 0;
+    int ekind = b->kind == BSK_BASIS_PERIODIC ? BSK_BASIS_PERIODIC : BSK_BASIS_PLAIN;
+    bsk_status rc = clone_basis(b, ekind, b->k, b->h_knots, &s->basis);
+    if (rc != BSK_OK) { delete s; return rc; }
+    s->ncoef = s->basis->N;
+    std::vector<double> c(ncoef);
+    for (int64_t i = 0; i < ncoef; ++i)
+        c[i] = b->dtype == BSK_F64 ? ((const double *)h_coefs)[i] : (double)((const float *)h_coefs)[i];
+    s->user_basis_kind = b->kind;
+    s->user_rv = b->rv;
+    s->user_len = b->len;
+    rc = set_host_coefs(s, b, c);
+    if (rc != BSK_OK) { bsk_spline_destroy(s); return rc; }
+    *out = s;
+    return BSK_OK;
+}
+
+bsk_status bsk_spline_set_coefs_device(bsk_spline *s, const void *d_coefs, int64_t ncoef, int64_t stride,
+                                       void *stream) {
+    BSK_REQUIRE(s && d_coefs, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(ncoef == s->user_len, BSK_ERR_DIMENSION, "wrong number of coefficients: got %lld, expected %lld",
+                (long long)ncoef, (long long)s->user_len);
+    BSK_REQUIRE(stride >= 1, BSK_ERR_ARGUMENT, "stride must be >= 1");
+    const bsk_basis *b = s->basis;
+    size_t es = b->dtype == BSK_F64 ? 8 : 4;
+    BSK_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<unsigned char> raw(es * ncoef);
+    BSK_CUDA(cudaMemcpy2DAsync(raw.data(), es, d_coefs, es * stride, es, ncoef, cudaMemcpyDeviceToHost, st));
+    BSK_CUDA(cudaStreamSynchronize(st));
+    std::vector<double> c(ncoef);
+    for (int64_t i = 0; i < ncoef; ++i)
+        c[i] = b->dtype == BSK_F64 ? ((const double *)raw.data())[i] : (double)((const float *)raw.data())[i];
+    bsk_basis ub;   // minimal view of the user basis for the recombination step
+    ub.kind = s->user_basis_kind; ub.dtype = b->dtype; ub.rv = s->user_rv;
+    return set_host_coefs(s, &ub, c);
+}
+
+bsk_status bsk_spline_destroy(bsk_spline *s) {
+    if (!s) return BSK_OK;
+    if (s->basis) cudaSetDevice(s->basis->device);
+    for (bsk_spline *d : s->derivs)
+        if (d) bsk_spline_destroy(d);
+    if (s->d_coefs && s->owns_coefs) cudaFree(s->d_coefs);
+    if (s->d_pp) cudaFree(s->d_pp);
+    if (s->d_pp_lut) cudaFree(s->d_pp_lut);
+    if (s->basis) bsk_basis_destroy(s->basis);
+    delete s;
+    return BSK_OK;
+}
+
+bsk_status bsk_spline_coefficients(const bsk_spline *s, void *h_out, int64_t ncoef) {
+    BSK_REQUIRE(s && h_out, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(ncoef == s->ncoef, BSK_ERR_DIMENSION, "expected %lld coefficients", (long long)s->ncoef);
+    for (int64_t i = 0; i < ncoef; ++i) {
+        if (s->basis->dtype == BSK_F64) ((double *)h_out)[i] = s->h_coefs[i];
+        else ((float *)h_out)[i] = (float)s->h_coefs[i];
+    }
+    return BSK_OK;
+}
+
+bsk_status bsk_spline_order(const bsk_spline *s, int32_t *k, int64_t *ncoef, int64_t *nknots) {
+    BSK_REQUIRE(s, BSK_ERR_ARGUMENT, "NULL argument");
+    if (k) *k = s->basis->k;
+    if (ncoef) *ncoef = s->ncoef;
+    if (nknots) *nknots = s->basis->nt;
+    return BSK_OK;
+}
+
+bsk_status bsk_spline_knots(const bsk_spline *s, void *h_out, int64_t nknots) {
+    BSK_REQUIRE(s && h_out, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(nknots == s->basis->nt, BSK_ERR_DIMENSION, "expected %lld knots", (long long)s->basis->nt);
+    for (int64_t i = 0; i < nknots; ++i) {
+        if (s->basis->dtype == BSK_F64) ((double *)h_out)[i] = s->basis->h_knots[i];
+        else ((float *)h_out)[i] = (float)s->basis->h_knots[i];
+    }
+    return BSK_OK;
+}
+
+bsk_status bsk_spline_derivative(const bsk_spline *s, int32_t nd, bsk_spline **out) {
+    BSK_REQUIRE(s && out, BSK_ERR_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    const bsk_basis *b = s->basis;
+    BSK_REQUIRE(nd >= 1, BSK_ERR_ARGUMENT, "derivative order must be >= 1");
+    BSK_REQUIRE(nd < b->k, BSK_ERR_ARGUMENT, "cannot differentiate order %d spline %d times!", b->k, nd);  // spline.jl:303-306
+    const int kind = b->kind == BSK_BASIS_PERIODIC ? 1 : 0;
+    std::vector<double> dc;
+    if (b->dtype == BSK_F64) derivative_coefs<double>(kind, b->k, b->h_knots, s->h_coefs, nd, dc);
+    else derivative_coefs<float>(kind, b->k, b->h_knots, s->h_coefs, nd, dc);
+    std::vector<double> tk;
+    if (kind == 0) tk.assign(b->h_knots.begin() + nd, b->h_knots.end() - nd);   // basis.jl:104-111
+    else tk = b->h_knots;
+    bsk_spline *d = new bsk_spline();
+    d->basis = nullptr; d->d_coefs = nullptr; d->owns_coefs = true; d->d_pp = nullptr;
+    d->d_pp_lut = nullptr; d->pp_valid = false; d->pp_nrec = 0; d->pp_ncell = 0; d->pp_scale = 0; d->pp_rec = 0;
+    bsk_status rc = clone_basis(b, kind ? BSK_BASIS_PERIODIC : BSK_BASIS_PLAIN, b->k - nd, tk, &d->basis);
+    if (rc != BSK_OK) { delete d; return rc; }
+    d->ncoef = (int64_t)dc.size();
+    d->user_basis_kind = d->basis->kind;
+    memset(&d->user_rv, 0, sizeof(d->user_rv));
+    d->user_len = d->ncoef;
+    d->h_coefs = dc;
+    rc = upload_coefs(d);
+    if (rc != BSK_OK) { bsk_spline_destroy(d); return rc; }
+    *out = d;
+    return BSK_OK;
+}
+
+bsk_status bsk_spline_eval(const bsk_spline *s, const void *d_x, int64_t n, int32_t nout, const int32_t *derivs,
+                           void *const *d_outs, int32_t algo, void *stream) {
+    BSK_REQUIRE(s && derivs && d_outs, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(nout >= 1 && nout <= kMaxOut, BSK_ERR_ARGUMENT, "nout must be in 1..%d", kMaxOut);
+    BSK_REQUIRE(algo >= 0 && algo <= 2, BSK_ERR_ARGUMENT, "unknown algo %d", algo);
+    for (int o = 0; o < nout; ++o) {
+        BSK_REQUIRE(derivs[o] >= 0, BSK_ERR_ARGUMENT, "derivative order must be >= 0");
+        BSK_REQUIRE(derivs[o] < s->basis->k, BSK_ERR_ARGUMENT, "cannot differentiate order %d spline %d times!",
+                    s->basis->k, derivs[o]);
+        BSK_REQUIRE(n == 0 || d_outs[o], BSK_ERR_ARGUMENT, "NULL output");
+    }
+    if (n == 0) return BSK_OK;
+    BSK_REQUIRE(d_x, BSK_ERR_ARGUMENT, "NULL points");
+    BSK_CUDA(cudaSetDevice(s->basis->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->basis->dtype == BSK_F64) return spline_eval_t<double>(s, (const double *)d_x, n, nout, derivs, d_outs, algo, st);
+    return spline_eval_t<float>(s, (const float *)d_x, n, nout, derivs, d_outs, algo, st);
+}
+
+}  // extern "C"

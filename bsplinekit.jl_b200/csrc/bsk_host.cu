@@ -1,0 +1,113 @@
+// bsk_host.cu — host-buffer entry points: chunked, multi-stream pipelines that overlap the
+// host->device copy of chunk i+1, the kernel of chunk i and the device->host copy of chunk i-1.
+// These are what a caller with ordinary (ideally pinned) host arrays uses; they are also the
+// "e2e" leg of bench.py.
+#include <algorithm>
+
+#include "handles.cuh"
+
+using namespace bsk;
+
+namespace {
+constexpr int kSlots = 3;
+}
+
+extern "C" {
+
+bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n, int32_t nout,
+                                const int32_t *derivs, void *const *h_outs, int32_t algo) {
+    BSK_REQUIRE(s && derivs && h_outs, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(nout >= 1 && nout <= 4, BSK_ERR_ARGUMENT, "nout must be in 1..4");
+    if (n == 0) return BSK_OK;
+    BSK_REQUIRE(h_x, BSK_ERR_ARGUMENT, "NULL points");
+    const int device = s->basis->device;
+    const size_t es = s->basis->dtype == BSK_F64 ? 8 : 4;
+    BSK_CUDA(cudaSetDevice(device));
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 23);
+    cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
+    void *dx[kSlots] = {nullptr, nullptr, nullptr};
+    void *dout[kSlots][4] = {{nullptr}};
+    bsk_status rc = BSK_OK;
+    cudaError_t e = cudaSuccess;
+    const int nslots = (int)std::min<int64_t>(kSlots, (n + chunk - 1) / chunk);
+    for (int i = 0; i < nslots && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&dx[i], es * chunk);
+        for (int o = 0; o < nout && e == cudaSuccess; ++o) e = cudaMalloc(&dout[i][o], es * chunk);
+    }
+    if (e == cudaSuccess) {
+        int64_t off = 0;
+        for (int64_t ci = 0; off < n && rc == BSK_OK; ++ci, off += chunk) {
+            const int slot = (int)(ci % nslots);
+            const int64_t m = std::min(chunk, n - off);
+            // stream order on the slot guarantees the previous use of its buffers is finished
+            e = cudaMemcpyAsync(dx[slot], (const char *)h_x + es * off, es * m, cudaMemcpyHostToDevice, st[slot]);
+            if (e != cudaSuccess) break;
+            rc = bsk_spline_eval(s, dx[slot], m, nout, derivs, dout[slot], algo, (void *)st[slot]);
+            if (rc != BSK_OK) break;
+            for (int o = 0; o < nout && e == cudaSuccess; ++o)
+                e = cudaMemcpyAsync((char *)h_outs[o] + es * off, dout[slot][o], es * m, cudaMemcpyDeviceToHost, st[slot]);
+            if (e != cudaSuccess) break;
+        }
+    }
+    for (int i = 0; i < nslots; ++i)
+        if (st[i]) {
+            cudaError_t e2 = cudaStreamSynchronize(st[i]);
+            if (e == cudaSuccess) e = e2;
+        }
+    for (int i = 0; i < nslots; ++i) {
+        if (dx[i]) cudaFree(dx[i]);
+        for (int o = 0; o < 4; ++o)
+            if (dout[i][o]) cudaFree(dout[i][o]);
+        if (st[i]) cudaStreamDestroy(st[i]);
+    }
+    if (rc != BSK_OK) return rc;
+    if (e != cudaSuccess) { set_error("bsk_spline_eval_host failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
+    return BSK_OK;
+}
+
+bsk_status bsk_banded_solve_host(const bsk_banded *h, double *h_rhs, int64_t nrhs, int32_t algo) {
+    BSK_REQUIRE(h && (nrhs == 0 || h_rhs), BSK_ERR_ARGUMENT, "NULL argument");
+    if (nrhs == 0) return BSK_OK;
+    BSK_CUDA(cudaSetDevice(h->device));
+    const int64_t n = h->n;
+    // column blocks of ~128 MB
+    int64_t cb = std::max<int64_t>(32, ((int64_t)128 << 20) / (8 * n));
+    cb = std::min(nrhs, (cb / 32) * 32 > 0 ? (cb / 32) * 32 : cb);
+    const int nslots = (int)std::min<int64_t>(kSlots, (nrhs + cb - 1) / cb);
+    cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
+    double *d[kSlots] = {nullptr, nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    bsk_status rc = BSK_OK;
+    for (int i = 0; i < nslots && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&d[i], 8 * (size_t)n * cb);
+    }
+    if (e == cudaSuccess) {
+        int64_t c0 = 0;
+        for (int64_t ci = 0; c0 < nrhs && rc == BSK_OK; ++ci, c0 += cb) {
+            const int slot = (int)(ci % nslots);
+            const int64_t w = std::min(cb, nrhs - c0);
+            e = cudaMemcpy2DAsync(d[slot], 8 * w, h_rhs + c0, 8 * nrhs, 8 * w, n, cudaMemcpyHostToDevice, st[slot]);
+            if (e != cudaSuccess) break;
+            rc = bsk_banded_solve(h, d[slot], w, algo, (void *)st[slot]);
+            if (rc != BSK_OK) break;
+            e = cudaMemcpy2DAsync(h_rhs + c0, 8 * nrhs, d[slot], 8 * w, 8 * w, n, cudaMemcpyDeviceToHost, st[slot]);
+            if (e != cudaSuccess) break;
+        }
+    }
+    for (int i = 0; i < nslots; ++i)
+        if (st[i]) {
+            cudaError_t e2 = cudaStreamSynchronize(st[i]);
+            if (e == cudaSuccess) e = e2;
+        }
+    for (int i = 0; i < nslots; ++i) {
+        if (d[i]) cudaFree(d[i]);
+        if (st[i]) cudaStreamDestroy(st[i]);
+    }
+    if (rc != BSK_OK) return rc;
+    if (e != cudaSuccess) { set_error("bsk_banded_solve_host failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
+    return BSK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,776 @@
+// bsk_solve.cu — K4 collocation assembly, K5 banded LU (BANFAC), K6 multi-RHS banded
+// solve (BANSLV order two-pass, and single-pass windowed), K7 cyclic tridiagonal.
+//
+// Reference bodies replaced (paths relative to the BSplineKit.jl tree):
+//   collocation_matrix!   src/Collocation/Collocation.jl:209-251
+//   lu!(::CollocationMatrix)  src/Collocation/matrix.jl:132-201
+//   ldiv!(x, F, y)        src/Collocation/matrix.jl:218-271
+//   ldiv!(x, ::CyclicTridiagonalMatrix, d)  src/Collocation/cyclic.jl:112-197
+#include <algorithm>
+#include <cstdlib>
+
+#include "handles.cuh"
+
+using namespace bsk;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename KT>
+KnotView<KT> make_view_s(const bsk_basis *b) {
+    KnotView<KT> kv;
+    kv.t = (const KT *)b->d_knots;
+    kv.nt = (int)b->nt;
+    kv.N = (int)b->N;
+    kv.k = b->k;
+    kv.kind = b->kind == BSK_BASIS_PERIODIC ? 1 : 0;
+    kv.ilast = b->ilast;
+    kv.a = (KT)b->h_knots.front();
+    kv.b = (KT)b->h_knots.back();
+    kv.period = (KT)((KT)b->h_knots.back() - (KT)b->h_knots.front());
+    kv.lut = b->d_lut;
+    kv.ncell = b->ncell;
+    kv.lut_scale = (KT)b->lut_scale;
+    return kv;
+}
+
+#define BSK_DISPATCH_K(kval, ...)                                  \
+    switch (kval) {                                                \
+        case 1: { constexpr int K = 1; __VA_ARGS__; } break;       \
+        case 2: { constexpr int K = 2; __VA_ARGS__; } break;       \
+        case 3: { constexpr int K = 3; __VA_ARGS__; } break;       \
+        case 4: { constexpr int K = 4; __VA_ARGS__; } break;       \
+        case 5: { constexpr int K = 5; __VA_ARGS__; } break;       \
+        case 6: { constexpr int K = 6; __VA_ARGS__; } break;       \
+        case 7: { constexpr int K = 7; __VA_ARGS__; } break;       \
+        case 8: { constexpr int K = 8; __VA_ARGS__; } break;       \
+        default: break;                                            \
+    }
+
+// ---- K4: collocation assembly ----------------------------------------------------------
+// One thread per row (collocation point).  The band store must be zero-filled before.
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+k_collocation(KnotView<double> kv, RecombView rv, double dom_a, double dom_b,
+              const double *__restrict__ x, int nx, int deriv, double clip, double *__restrict__ band,
+              int ncols, unsigned long long *__restrict__ n_outside) {
+    const int l = K - 2 < 0 ? 0 : K - 2, u = l;
+    const int nroww = l + u + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i <= nx; i += gridDim.x * blockDim.x) {
+        const double xi = x[i - 1];
+        if (!(xi >= dom_a && xi <= dom_b)) continue;          // isindomain (basis.jl:229-234)
+        double bq[K];
+        int jlast = eval_all_point<K, 0, double, double>(kv, kv.t, xi, deriv, 0, bq);
+        if (rv.enabled) {
+            double ph[K];
+            jlast = recombine_point<K, double, double>(rv, jlast, bq, ph);
+#pragma unroll
+            for (int j = 0; j < K; ++j) bq[j] = ph[j];
+        }
+#pragma unroll
+        for (int dj = 1; dj <= K; ++dj) {
+            const int j = jlast + 1 - dj;
+            const double bj = bq[dj - 1];
+            if (fabs(bj) <= clip) continue;                   // Collocation.jl:237
+            if ((i > j && i - j > l) || (i < j && j - i > u) || j < 1 || j > ncols) {
+                atomicAdd(n_outside, 1ull);                   // reference: @warn (Collocation.jl:239-244)
+                continue;
+            }
+            band[(u + i - j) + (size_t)(j - 1) * nroww] = bj;  // matrix.jl:105-117
+        }
+    }
+}
+
+// Periodic cubic: CyclicTridiagonalMatrix (cyclic.jl:21-33, setindex! :77-92)
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+k_collocation_cyclic(KnotView<double> kv, const double *__restrict__ x, int nx, int deriv, double clip,
+                     double *__restrict__ a, double *__restrict__ b, double *__restrict__ c,
+                     unsigned long long *__restrict__ n_outside) {
+    const int n = kv.N;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i <= nx; i += gridDim.x * blockDim.x) {
+        double bq[K];
+        int jlast = eval_all_point<K, 1, double, double>(kv, kv.t, x[i - 1], deriv, 0, bq);
+        const int im = (i == 1) ? n : i - 1, ip = (i == n) ? 1 : i + 1;
+#pragma unroll
+        for (int dj = 1; dj <= K; ++dj) {
+            int j = jlast + 1 - dj;
+            while (j < 1) j += n;                             // basis_to_array_index (periodic.jl:245-253)
+            while (j > n) j -= n;
+            const double bj = bq[dj - 1];
+            if (fabs(bj) <= clip) continue;
+            if (i == j) b[i - 1] = bj;
+            else if (j == im) a[i - 1] = bj;
+            else if (j == ip) c[i - 1] = bj;
+            else atomicAdd(n_outside, 1ull);                  // reference: DomainError
+        }
+    }
+}
+
+// ---- K5: BANFAC (matrix.jl:132-201), a strictly serial recurrence: one thread -----------
+__global__ void k_banded_lu(double *__restrict__ w, int nbandl, int nbandu, int nrow, long long *info) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int nroww = nbandl + nbandu + 1;
+    const int middle = nbandu + 1;
+#define W(r, c) w[((r) - 1) + (size_t)((c) - 1) * nroww]
+    *info = 0;
+    if (nrow == 1) { if (W(middle, 1) == 0.0) *info = 1; return; }
+    if (nbandl == 0) {
+        for (int i = 1; i <= nrow; ++i)
+            if (W(middle, i) == 0.0) { *info = i; return; }
+        return;
+    }
+    for (int i = 1; i <= nrow - 1; ++i) {
+        const double pivot = W(middle, i);
+        if (pivot == 0.0) { *info = i; return; }
+        const double ipiv = xdiv(1.0, pivot);
+        const int jmax = min(nbandl, nrow - i);
+        for (int j = 1; j <= jmax; ++j) W(middle + j, i) = xmul(W(middle + j, i), ipiv);
+        const int kmax = min(nbandu, nrow - i);
+        for (int kk = 1; kk <= kmax; ++kk) {
+            const double factor = W(middle - kk, i + kk);
+            for (int j = 1; j <= jmax; ++j)
+                W(middle - kk + j, i + kk) = xsub(W(middle - kk + j, i + kk), xmul(factor, W(middle + j, i)));
+        }
+    }
+    if (W(middle, nrow) == 0.0) *info = nrow;
+#undef W
+}
+
+// Repack the factors row-wise for the solve kernels:
+//   lrow[r][j-1] = L(r, r-j) = w[mid + j, r - j],  urow[r][j-1] = U(r, r+j) = w[mid - j, r + j]
+__global__ void k_repack(const double *__restrict__ w, int bw, int n, double *__restrict__ lrow,
+                         double *__restrict__ urow, double *__restrict__ diag, double *__restrict__ dinv) {
+    const int nroww = 2 * bw + 1, middle = bw + 1;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x + 1; r <= n; r += gridDim.x * blockDim.x) {
+        for (int j = 1; j <= bw; ++j) {
+            lrow[(size_t)(r - 1) * bw + j - 1] = (r - j >= 1) ? w[(middle + j - 1) + (size_t)(r - j - 1) * nroww] : 0.0;
+            urow[(size_t)(r - 1) * bw + j - 1] = (r + j <= n) ? w[(middle - j - 1) + (size_t)(r + j - 1) * nroww] : 0.0;
+        }
+        const double d = w[(middle - 1) + (size_t)(r - 1) * nroww];
+        diag[r - 1] = d;
+        dinv[r - 1] = 1.0 / d;
+    }
+}
+
+// ---- K6a: BANSLV order, two passes over HBM, one thread per right-hand side ----------------
+// rhs is interleaved: rhs[r * nrhs + c].  Bit-faithful to matrix.jl:218-271 (mul, then sub,
+// true division by the pivot).
+template <int BW, int UNROLL>
+__global__ void __launch_bounds__(kThreads)
+k_banded_forward(const double *__restrict__ lrow, double *__restrict__ rhs, int64_t nrhs, int n) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        double zw[BW > 0 ? BW : 1];
+#pragma unroll
+        for (int j = 0; j < BW; ++j) zw[j] = 0.0;
+        double *p = rhs + c;
+        int r = 0;
+        for (; r + UNROLL <= n; r += UNROLL) {
+            double y[UNROLL];
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) y[q] = p[(int64_t)(r + q) * nrhs];
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) {
+                double z = y[q];
+                const double *lr = lrow + (size_t)(r + q) * BW;
+#pragma unroll
+                for (int j = BW; j >= 1; --j) z = xsub(z, xmul(zw[j - 1], __ldg(lr + j - 1)));
+#pragma unroll
+                for (int j = BW - 1; j >= 1; --j) zw[j] = zw[j - 1];
+                if (BW > 0) zw[0] = z;
+                y[q] = z;
+            }
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) p[(int64_t)(r + q) * nrhs] = y[q];
+        }
+        for (; r < n; ++r) {
+            double z = p[(int64_t)r * nrhs];
+            const double *lr = lrow + (size_t)r * BW;
+#pragma unroll
+            for (int j = BW; j >= 1; --j) z = xsub(z, xmul(zw[j - 1], __ldg(lr + j - 1)));
+#pragma unroll
+            for (int j = BW - 1; j >= 1; --j) zw[j] = zw[j - 1];
+            if (BW > 0) zw[0] = z;
+            p[(int64_t)r * nrhs] = z;
+        }
+    }
+}
+
+template <int BW, int UNROLL>
+__global__ void __launch_bounds__(kThreads)
+k_banded_backward(const double *__restrict__ urow, const double *__restrict__ diag,
+                  double *__restrict__ rhs, int64_t nrhs, int n) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        double xw[BW > 0 ? BW : 1];
+#pragma unroll
+        for (int j = 0; j < BW; ++j) xw[j] = 0.0;
+        double *p = rhs + c;
+        int r = n - 1;
+        for (; r - UNROLL + 1 >= 0; r -= UNROLL) {
+            double y[UNROLL];
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) y[q] = p[(int64_t)(r - q) * nrhs];
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) {
+                double acc = y[q];
+                const double *ur = urow + (size_t)(r - q) * BW;
+#pragma unroll
+                for (int j = BW; j >= 1; --j) acc = xsub(acc, xmul(xw[j - 1], __ldg(ur + j - 1)));
+                const double xr = xdiv(acc, __ldg(diag + (r - q)));
+#pragma unroll
+                for (int j = BW - 1; j >= 1; --j) xw[j] = xw[j - 1];
+                if (BW > 0) xw[0] = xr;
+                y[q] = xr;
+            }
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) p[(int64_t)(r - q) * nrhs] = y[q];
+        }
+        for (; r >= 0; --r) {
+            double acc = p[(int64_t)r * nrhs];
+            const double *ur = urow + (size_t)r * BW;
+#pragma unroll
+            for (int j = BW; j >= 1; --j) acc = xsub(acc, xmul(xw[j - 1], __ldg(ur + j - 1)));
+            const double xr = xdiv(acc, __ldg(diag + r));
+#pragma unroll
+            for (int j = BW - 1; j >= 1; --j) xw[j] = xw[j - 1];
+            if (BW > 0) xw[0] = xr;
+            p[(int64_t)r * nrhs] = xr;
+        }
+    }
+}
+
+// ---- K6b: single pass, windowed backward sweep ------------------------------------------------
+// One thread per right-hand side.  The forward sweep streams down the rows exactly as BANSLV
+// does; its results are kept in a per-thread ring of (M + H) rows in shared memory.  The
+// backward recurrence is restarted every M rows from H rows further down with a zero state:
+// the influence of that (wrong) state on the rows that are kept decays like |U^{-1}| away from
+// the diagonal and was bounded below 1e-17 at factor time for this H (bsk_banded_lu), i.e. far
+// under one ulp.  HBM traffic: each element read once and written once.
+template <int BW, int TB>
+__global__ void __launch_bounds__(TB)
+k_banded_windowed(const double *__restrict__ lrow, const double *__restrict__ urow,
+                  const double *__restrict__ dinv, double *__restrict__ rhs, int64_t nrhs, int n,
+                  int M, int H) {
+    extern __shared__ __align__(16) double ring[];        // (M + H) x TB
+    const int RW = M + H;
+    const int tid = threadIdx.x;
+    const int nblk = (n + M - 1) / M;
+    const int hb = H / M;
+    const int64_t ngroups = (nrhs + TB - 1) / TB;
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t c = g * TB + tid;
+        const bool active = c < nrhs;
+        double *p = rhs + (active ? c : 0);
+        double zw[BW > 0 ? BW : 1];
+#pragma unroll
+        for (int j = 0; j < BW; ++j) zw[j] = 0.0;
+        for (int b = 0; b < nblk + hb; ++b) {
+            if (b < nblk) {
+                const int r0 = b * M, r1 = min(n, r0 + M);
+                int r = r0;
+                for (; r + 8 <= r1; r += 8) {
+                    double y[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) y[q] = active ? p[(int64_t)(r + q) * nrhs] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        double z = y[q];
+                        const double *lr = lrow + (size_t)(r + q) * BW;
+#pragma unroll
+                        for (int j = BW; j >= 1; --j) z = fma(-zw[j - 1], __ldg(lr + j - 1), z);
+#pragma unroll
+                        for (int j = BW - 1; j >= 1; --j) zw[j] = zw[j - 1];
+                        if (BW > 0) zw[0] = z;
+                        ring[((r + q) % RW) * TB + tid] = z;
+                    }
+                }
+                for (; r < r1; ++r) {
+                    double z = active ? p[(int64_t)r * nrhs] : 0.0;
+                    const double *lr = lrow + (size_t)r * BW;
+#pragma unroll
+                    for (int j = BW; j >= 1; --j) z = fma(-zw[j - 1], __ldg(lr + j - 1), z);
+#pragma unroll
+                    for (int j = BW - 1; j >= 1; --j) zw[j] = zw[j - 1];
+                    if (BW > 0) zw[0] = z;
+                    ring[(r % RW) * TB + tid] = z;
+                }
+            }
+            const int bb = b - hb;
+            if (bb >= 0) {
+                const int keep_hi = min(n, (bb + 1) * M);          // rows [bb*M, keep_hi) are final
+                const int r_hi = min(n, (bb + 1) * M + H) - 1;
+                double xw[BW > 0 ? BW : 1];
+#pragma unroll
+                for (int j = 0; j < BW; ++j) xw[j] = 0.0;
+                for (int r = r_hi; r >= bb * M; --r) {
+                    double acc = ring[(r % RW) * TB + tid];
+                    const double *ur = urow + (size_t)r * BW;
+#pragma unroll
+                    for (int j = BW; j >= 1; --j) acc = fma(-xw[j - 1], __ldg(ur + j - 1), acc);
+                    const double xr = acc * __ldg(dinv + r);
+#pragma unroll
+                    for (int j = BW - 1; j >= 1; --j) xw[j] = xw[j - 1];
+                    if (BW > 0) xw[0] = xr;
+                    if (r < keep_hi && active) p[(int64_t)r * nrhs] = xr;
+                }
+            }
+        }
+    }
+}
+
+// ---- K7: cyclic tridiagonal, factor-once Sherman-Morrison ------------------------------------
+// x = y - alpha q,  T y = d,  alpha = (g . d) / denom  with g = T^{-T} v  (so that alpha is known
+// when the backward sweep starts and x is produced in the same pass as y).
+template <int UNROLL>
+__global__ void __launch_bounds__(kThreads)
+k_cyclic_forward(const double *__restrict__ w, const double *__restrict__ gvec, double *__restrict__ rhs,
+                 double *__restrict__ alpha_out, int64_t nrhs, int n, double inv_denom) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        double *p = rhs + c;
+        double prev = 0.0, dot = 0.0;
+        int r = 0;
+        for (; r + UNROLL <= n; r += UNROLL) {
+            double y[UNROLL];
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) y[q] = p[(int64_t)(r + q) * nrhs];
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) {
+                dot = fma(__ldg(gvec + r + q), y[q], dot);
+                const double z = xsub(y[q], xmul(__ldg(w + r + q), prev));   // d[i] - w*d[i-1] (cyclic.jl:182-186)
+                prev = z;
+                y[q] = z;
+            }
+#pragma unroll
+            for (int q = 0; q < UNROLL; ++q) p[(int64_t)(r + q) * nrhs] = y[q];
+        }
+        for (; r < n; ++r) {
+            const double y = p[(int64_t)r * nrhs];
+            dot = fma(__ldg(gvec + r), y, dot);
+            const double z = xsub(y, xmul(__ldg(w + r), prev));
+            prev = z;
+            p[(int64_t)r * nrhs] = z;
+        }
+        alpha_out[c] = dot * inv_denom;
+    }
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(kThreads)
+k_cyclic_backward(const double *__restrict__ cdiag, const double *__restrict__ bp,
+                  const double *__restrict__ q, const double *__restrict__ alpha_in,
+                  double *__restrict__ rhs, int64_t nrhs, int n) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        double *p = rhs + c;
+        const double alpha = alpha_in[c];
+        double next = 0.0;    // y[i+1]
+        int r = n - 1;
+        for (; r - UNROLL + 1 >= 0; r -= UNROLL) {
+            double y[UNROLL];
+#pragma unroll
+            for (int qq = 0; qq < UNROLL; ++qq) y[qq] = p[(int64_t)(r - qq) * nrhs];
+#pragma unroll
+            for (int qq = 0; qq < UNROLL; ++qq) {
+                const int i = r - qq;
+                // x[i] = (d[i] - c[i] * x[i+1]) / b[i]   (cyclic.jl:191-195); c[n-1] term is 0 via next = 0
+                const double yi = xdiv(xsub(y[qq], xmul(__ldg(cdiag + i), next)), __ldg(bp + i));
+                next = yi;
+                y[qq] = xsub(yi, xmul(alpha, __ldg(q + i)));
+            }
+#pragma unroll
+            for (int qq = 0; qq < UNROLL; ++qq) p[(int64_t)(r - qq) * nrhs] = y[qq];
+        }
+        for (; r >= 0; --r) {
+            const double yi = xdiv(xsub(p[(int64_t)r * nrhs], xmul(__ldg(cdiag + r), next)), __ldg(bp + r));
+            next = yi;
+            p[(int64_t)r * nrhs] = xsub(yi, xmul(alpha, __ldg(q + r)));
+        }
+    }
+}
+
+inline int grid_cols(int64_t ncols, int device, int per_sm) {
+    int64_t want = (ncols + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)sm_count(device) * per_sm;
+    return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+// Decay of the backward recurrence: for a start at row s with unit state errors, the largest
+// |error| that reaches rows <= s - h.  Returns the smallest multiple of `step` (<= hmax) for
+// which the bound is <= tol, or 0.
+int decay_halo(const std::vector<double> &urow, const std::vector<double> &dinv, int n, int bw,
+               double tol, int step, int hmax) {
+    if (bw == 0) return step;
+    if (n <= step) return 0;
+    int need = 0;
+    std::vector<double> win(bw);
+    for (int s = n - 1; s >= 1; --s) {
+        // |e_r| <= |1/U_rr| * sum_j |U(r, r+j)| |e_{r+j}|, started from an all-ones state
+        // (bounds any state error of size <= 1 per entry, by linearity).
+        for (int j = 0; j < bw; ++j) win[j] = 1.0;
+        int h = 0;
+        bool ok = false;
+        for (int r = s; r >= 0 && h < hmax; --r) {
+            double acc = 0.0;
+            for (int j = 1; j <= bw; ++j) acc += std::fabs(urow[(size_t)r * bw + j - 1]) * win[j - 1];
+            acc *= std::fabs(dinv[r]);
+            for (int j = bw - 1; j >= 1; --j) win[j] = win[j - 1];
+            win[0] = acc;
+            ++h;
+            double mx = 0.0;
+            for (int j = 0; j < bw; ++j) mx = std::max(mx, win[j]);
+            if (mx <= tol) { ok = true; break; }
+        }
+        if (!ok && h >= hmax) return 0;          // no decay within hmax rows
+        if (ok) need = std::max(need, h);        // (running off row 0 first is harmless)
+    }
+    int H = ((need + step - 1) / step) * step;
+    if (H == 0) H = step;
+    return H <= hmax ? H : 0;
+}
+
+template <int BW>
+bsk_status solve_dispatch(const bsk_banded *h, double *d_rhs, int64_t nrhs, int algo, cudaStream_t st) {
+    const int n = (int)h->n;
+    bool windowed = (algo == BSK_SOLVE_WINDOWED) || (algo == BSK_SOLVE_AUTO && h->halo > 0 && nrhs >= 1024);
+    if (algo == BSK_SOLVE_WINDOWED && h->halo == 0) {
+        set_error("windowed solve unavailable: the decay bound of U^{-1} was not met for this matrix");
+        return BSK_ERR_UNSUPPORTED;
+    }
+    if (windowed) {
+        constexpr int TB = 32;
+        const int H = h->halo;
+        int M = (H % 64 == 0) ? 64 : 32;
+        if (const char *env = getenv("BSK_WINDOW_M")) {      // tuning knob (must divide H)
+            int m = atoi(env);
+            if (m >= 8 && m % 8 == 0 && H % m == 0) M = m;
+        }
+        size_t smem = (size_t)(M + H) * TB * sizeof(double);
+        auto kern = k_banded_windowed<BW, TB>;
+        if (smem > 48 * 1024)
+            BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (224 * 1024) / smem));
+        int64_t ngroups = (nrhs + TB - 1) / TB;
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ngroups, (int64_t)sm_count(h->device) * per_sm));
+        kern<<<grid, TB, smem, st>>>(h->d_lrow, h->d_urow, h->d_dinv, d_rhs, nrhs, n, M, H);
+        BSK_CUDA(cudaGetLastError());
+        return BSK_OK;
+    }
+    int grid = grid_cols(nrhs, h->device, 8);
+    k_banded_forward<BW, 8><<<grid, kThreads, 0, st>>>(h->d_lrow, d_rhs, nrhs, n);
+    BSK_CUDA(cudaGetLastError());
+    k_banded_backward<BW, 8><<<grid, kThreads, 0, st>>>(h->d_urow, h->d_diag, d_rhs, nrhs, n);
+    BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+bsk_status bsk_collocation_matrix(const bsk_basis *b, const double *d_x, int64_t nx, int32_t deriv,
+                                  double clip_threshold, double *d_band, int64_t *h_n_outside, void *stream) {
+    BSK_REQUIRE(b && d_x && d_band, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(b->dtype == BSK_F64, BSK_ERR_UNSUPPORTED, "collocation assembly needs a Float64 basis");
+    BSK_REQUIRE(b->kind != BSK_BASIS_PERIODIC, BSK_ERR_UNSUPPORTED,
+                "periodic bases: use bsk_collocation_cyclic (k = 4)");
+    BSK_REQUIRE(nx == b->len, BSK_ERR_ARGUMENT, "wrong dimensions of collocation matrix");   // Collocation.jl:214-216
+    BSK_REQUIRE(deriv >= 0, BSK_ERR_ARGUMENT, "derivative order must be >= 0");
+    BSK_REQUIRE(b->k >= 2, BSK_ERR_UNSUPPORTED, "order must be >= 2");
+    BSK_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nroww = 2 * (b->k - 2) + 1;
+    BSK_CUDA(cudaMemsetAsync(d_band, 0, sizeof(double) * (size_t)nroww * (size_t)b->len, st));
+    unsigned long long *d_cnt = nullptr;
+    BSK_CUDA(cudaMalloc((void **)&d_cnt, 8));
+    BSK_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
+    KnotView<double> kv = make_view_s<double>(b);
+    const double dom_a = b->h_knots[b->k - 1], dom_b = b->h_knots[b->N];   // boundaries (basis.jl:217-222)
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nx + kThreads - 1) / kThreads, 148 * 8));
+    BSK_DISPATCH_K(b->k, (k_collocation<K><<<grid, kThreads, 0, st>>>(kv, b->rv, dom_a, dom_b, d_x, (int)nx, deriv,
+                                                                      clip_threshold, d_band, (int)b->len, d_cnt)))
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && h_n_outside) {
+        unsigned long long cnt = 0;
+        e = cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        *h_n_outside = (int64_t)cnt;
+    }
+    cudaFreeAsync(d_cnt, st);
+    if (e != cudaSuccess) { set_error("collocation kernel failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
+    return BSK_OK;
+}
+
+bsk_status bsk_collocation_cyclic(const bsk_basis *b, const double *d_x, int64_t nx, int32_t deriv,
+                                  double clip_threshold, double *d_a, double *d_b, double *d_c,
+                                  int64_t *h_n_outside, void *stream) {
+    BSK_REQUIRE(b && d_x && d_a && d_b && d_c, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(b->dtype == BSK_F64, BSK_ERR_UNSUPPORTED, "collocation assembly needs a Float64 basis");
+    BSK_REQUIRE(b->kind == BSK_BASIS_PERIODIC, BSK_ERR_ARGUMENT, "basis is not periodic");
+    BSK_REQUIRE(nx == b->len, BSK_ERR_ARGUMENT, "wrong dimensions of collocation matrix");
+    BSK_REQUIRE(b->N >= 3, BSK_ERR_ARGUMENT, "cyclic tridiagonal matrix needs n >= 3");
+    BSK_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    BSK_CUDA(cudaMemsetAsync(d_a, 0, 8 * (size_t)nx, st));
+    BSK_CUDA(cudaMemsetAsync(d_b, 0, 8 * (size_t)nx, st));
+    BSK_CUDA(cudaMemsetAsync(d_c, 0, 8 * (size_t)nx, st));
+    unsigned long long *d_cnt = nullptr;
+    BSK_CUDA(cudaMalloc((void **)&d_cnt, 8));
+    BSK_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
+    KnotView<double> kv = make_view_s<double>(b);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nx + kThreads - 1) / kThreads, 148 * 8));
+    BSK_DISPATCH_K(b->k, (k_collocation_cyclic<K><<<grid, kThreads, 0, st>>>(kv, d_x, (int)nx, deriv, clip_threshold,
+                                                                             d_a, d_b, d_c, d_cnt)))
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && h_n_outside) {
+        unsigned long long cnt = 0;
+        e = cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        *h_n_outside = (int64_t)cnt;
+    }
+    cudaFreeAsync(d_cnt, st);
+    if (e != cudaSuccess) { set_error("collocation kernel failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
+    return BSK_OK;
+}
+
+static bsk_status banded_alloc(int64_t n, int32_t l, int32_t u, int32_t device, bsk_banded **out) {
+    BSK_REQUIRE(out, BSK_ERR_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    BSK_REQUIRE(n >= 1, BSK_ERR_ARGUMENT, "matrix is empty");                       // matrix.jl:145
+    BSK_REQUIRE(l == u, BSK_ERR_ARGUMENT, "expected same number of lower and upper bands");   // matrix.jl:58-60
+    BSK_REQUIRE(l >= 0 && l <= BSK_MAXK - 2, BSK_ERR_UNSUPPORTED, "bandwidths 0..%d are supported", BSK_MAXK - 2);
+    BSK_REQUIRE(n < (1ll << 30), BSK_ERR_UNSUPPORTED, "matrix too large");
+    BSK_CUDA(cudaSetDevice(device));
+    bsk_banded *h = new bsk_banded();
+    h->device = device; h->n = n; h->l = l; h->u = u; h->factored = false; h->halo = 0;
+    h->d_w = h->d_lrow = h->d_urow = h->d_dinv = h->d_diag = nullptr;
+    size_t nw = (size_t)(l + u + 1) * n, nb = (size_t)std::max(1, l) * n;
+    cudaError_t e = cudaMalloc((void **)&h->d_w, 8 * nw);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_lrow, 8 * nb);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_urow, 8 * nb);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_dinv, 8 * n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_diag, 8 * n);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
+        bsk_banded_destroy(h);
+        return BSK_ERR_ALLOC;
+    }
+    *out = h;
+    return BSK_OK;
+}
+
+bsk_status bsk_banded_create(const double *d_band, int64_t n, int32_t l, int32_t u, int32_t device,
+                             bsk_banded **out) {
+    BSK_REQUIRE(d_band, BSK_ERR_ARGUMENT, "NULL band data");
+    bsk_status rc = banded_alloc(n, l, u, device, out);
+    if (rc != BSK_OK) return rc;
+    BSK_CUDA(cudaMemcpy((*out)->d_w, d_band, 8 * (size_t)(l + u + 1) * n, cudaMemcpyDeviceToDevice));
+    return BSK_OK;
+}
+
+bsk_status bsk_banded_create_host(const double *h_band, int64_t n, int32_t l, int32_t u, int32_t device,
+                                  bsk_banded **out) {
+    BSK_REQUIRE(h_band, BSK_ERR_ARGUMENT, "NULL band data");
+    bsk_status rc = banded_alloc(n, l, u, device, out);
+    if (rc != BSK_OK) return rc;
+    BSK_CUDA(cudaMemcpy((*out)->d_w, h_band, 8 * (size_t)(l + u + 1) * n, cudaMemcpyHostToDevice));
+    return BSK_OK;
+}
+
+bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot) {
+    BSK_REQUIRE(h, BSK_ERR_ARGUMENT, "NULL handle");
+    BSK_REQUIRE(!h->factored, BSK_ERR_ARGUMENT, "matrix is already factorised");
+    BSK_CUDA(cudaSetDevice(h->device));
+    long long *d_info = nullptr;
+    BSK_CUDA(cudaMalloc((void **)&d_info, 8));
+    k_banded_lu<<<1, 1>>>(h->d_w, h->l, h->u, (int)h->n, d_info);
+    long long info = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(&info, d_info, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_info);
+    if (e != cudaSuccess) { set_error("banded LU failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
+    if (info_pivot) *info_pivot = info;
+    if (info != 0) {
+        set_error("ZeroPivotException(%lld)", info);
+        return BSK_ERR_ZERO_PIVOT;
+    }
+    const int n = (int)h->n, bw = h->l;
+    int grid = std::max(1, std::min((n + kThreads - 1) / kThreads, 148 * 4));
+    k_repack<<<grid, kThreads>>>(h->d_w, bw, n, h->d_lrow, h->d_urow, h->d_diag, h->d_dinv);
+    BSK_CUDA(cudaGetLastError());
+    // decay bound for the windowed solve
+    std::vector<double> urow((size_t)std::max(1, bw) * n), dinv(n);
+    BSK_CUDA(cudaMemcpy(urow.data(), h->d_urow, 8 * (size_t)std::max(1, bw) * n, cudaMemcpyDeviceToHost));
+    BSK_CUDA(cudaMemcpy(dinv.data(), h->d_dinv, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+    h->halo = decay_halo(urow, dinv, n, bw, 1e-17, 32, 448);
+    h->factored = true;
+    return BSK_OK;
+}
+
+bsk_status bsk_banded_data(const bsk_banded *h, double *h_out) {
+    BSK_REQUIRE(h && h_out, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_CUDA(cudaSetDevice(h->device));
+    BSK_CUDA(cudaMemcpy(h_out, h->d_w, 8 * (size_t)(h->l + h->u + 1) * h->n, cudaMemcpyDeviceToHost));
+    return BSK_OK;
+}
+
+bsk_status bsk_banded_halo(const bsk_banded *h, int32_t *halo) {
+    BSK_REQUIRE(h && halo, BSK_ERR_ARGUMENT, "NULL argument");
+    *halo = h->halo;
+    return BSK_OK;
+}
+
+bsk_status bsk_banded_solve(const bsk_banded *h, double *d_rhs, int64_t nrhs, int32_t algo, void *stream) {
+    BSK_REQUIRE(h && (nrhs == 0 || d_rhs), BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(h->factored, BSK_ERR_ARGUMENT, "matrix is not factorised: call bsk_banded_lu first");
+    BSK_REQUIRE(algo >= 0 && algo <= 2, BSK_ERR_ARGUMENT, "unknown algo %d", algo);
+    BSK_REQUIRE(nrhs >= 0, BSK_ERR_DIMENSION, "negative number of right-hand sides");
+    if (nrhs == 0) return BSK_OK;
+    BSK_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->l) {
+        case 0: return solve_dispatch<0>(h, d_rhs, nrhs, algo, st);
+        case 1: return solve_dispatch<1>(h, d_rhs, nrhs, algo, st);
+        case 2: return solve_dispatch<2>(h, d_rhs, nrhs, algo, st);
+        case 3: return solve_dispatch<3>(h, d_rhs, nrhs, algo, st);
+        case 4: return solve_dispatch<4>(h, d_rhs, nrhs, algo, st);
+        case 5: return solve_dispatch<5>(h, d_rhs, nrhs, algo, st);
+        case 6: return solve_dispatch<6>(h, d_rhs, nrhs, algo, st);
+    }
+    set_error("unsupported bandwidth %d", h->l);
+    return BSK_ERR_UNSUPPORTED;
+}
+
+bsk_status bsk_banded_destroy(bsk_banded *h) {
+    if (!h) return BSK_OK;
+    cudaSetDevice(h->device);
+    if (h->d_w) cudaFree(h->d_w);
+    if (h->d_lrow) cudaFree(h->d_lrow);
+    if (h->d_urow) cudaFree(h->d_urow);
+    if (h->d_dinv) cudaFree(h->d_dinv);
+    if (h->d_diag) cudaFree(h->d_diag);
+    delete h;
+    return BSK_OK;
+}
+
+// ---- cyclic -----------------------------------------------------------------------------------
+static bsk_status cyclic_build(const std::vector<double> &a, const std::vector<double> &b_in,
+                               const std::vector<double> &c, int32_t device, bsk_cyclic **out) {
+    const int64_t n = (int64_t)a.size();
+    BSK_REQUIRE(n >= 3, BSK_ERR_ARGUMENT, "cyclic tridiagonal matrix needs n >= 3");
+    // Collocation/cyclic.jl:121-146
+    std::vector<double> b(b_in);
+    const double a1 = a[0], cn = c[n - 1];
+    const double ac = a1 * cn;
+    const double gamma = std::sqrt(ac);
+    BSK_REQUIRE(gamma == gamma && gamma != 0.0, BSK_ERR_ARGUMENT,
+                "cyclic solve needs a[1]*c[n] > 0 (got %g)", ac);
+    const double vn = a1 / gamma;
+    b[0] -= gamma;
+    b[n - 1] -= ac / gamma;
+    std::vector<double> w(n, 0.0), q(n, 0.0), g(n, 0.0);
+    q[0] = gamma; q[n - 1] = cn;
+    // Thomas elimination of the matrix and of q (solve_thomas!, cyclic.jl:168-197)
+    for (int64_t i = 1; i < n; ++i) {
+        w[i] = a[i] / b[i - 1];
+        b[i] = b[i] - w[i] * c[i - 1];
+        q[i] = q[i] - w[i] * q[i - 1];
+    }
+    for (int64_t i = 0; i < n; ++i)
+        BSK_REQUIRE(b[i] != 0.0 && b[i] == b[i], BSK_ERR_ZERO_PIVOT, "zero pivot in cyclic elimination at row %lld",
+                    (long long)(i + 1));
+    q[n - 1] = q[n - 1] / b[n - 1];
+    for (int64_t i = n - 2; i >= 0; --i) q[i] = (q[i] - c[i] * q[i + 1]) / b[i];
+    const double vq = 1.0 * q[0] + vn * q[n - 1];
+    const double denom = 1.0 + vq;
+    // g = T^{-T} v, v = (1, 0, ..., 0, vn):  T = L U (unit-lower L with multipliers w, upper U with
+    // diagonal b' and super-diagonal c), so  U^T z = v (forward), then L^T g = z (backward).
+    std::vector<double> z(n, 0.0);
+    z[0] = 1.0 / b[0];
+    for (int64_t i = 1; i < n; ++i) {
+        double vi = (i == n - 1) ? vn : 0.0;
+        z[i] = (vi - c[i - 1] * z[i - 1]) / b[i];
+    }
+    g[n - 1] = z[n - 1];
+    for (int64_t i = n - 2; i >= 0; --i) g[i] = z[i] - w[i + 1] * g[i + 1];
+
+    BSK_CUDA(cudaSetDevice(device));
+    bsk_cyclic *h = new bsk_cyclic();
+    h->device = device; h->n = n; h->vn = vn; h->denom = denom;
+    h->d_w = h->d_bp = h->d_c = h->d_q = h->d_g = nullptr;
+    auto up = [&](double **dst, const std::vector<double> &src) {
+        cudaError_t e = cudaMalloc((void **)dst, 8 * (size_t)n);
+        if (e == cudaSuccess) e = cudaMemcpy(*dst, src.data(), 8 * (size_t)n, cudaMemcpyHostToDevice);
+        return e;
+    };
+    cudaError_t e = up(&h->d_w, w);
+    if (e == cudaSuccess) e = up(&h->d_bp, b);
+    if (e == cudaSuccess) e = up(&h->d_c, c);
+    if (e == cudaSuccess) e = up(&h->d_q, q);
+    if (e == cudaSuccess) e = up(&h->d_g, g);
+    if (e != cudaSuccess) {
+        set_error("cyclic upload failed: %s", cudaGetErrorString(e));
+        bsk_cyclic_destroy(h);
+        return BSK_ERR_CUDA;
+    }
+    *out = h;
+    return BSK_OK;
+}
+
+bsk_status bsk_cyclic_create(const double *h_a, const double *h_b, const double *h_c, int64_t n, int32_t device,
+                             bsk_cyclic **out) {
+    BSK_REQUIRE(h_a && h_b && h_c && out, BSK_ERR_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    BSK_REQUIRE(n >= 3, BSK_ERR_ARGUMENT, "cyclic tridiagonal matrix needs n >= 3");
+    std::vector<double> a(h_a, h_a + n), b(h_b, h_b + n), c(h_c, h_c + n);
+    return cyclic_build(a, b, c, device, out);
+}
+
+bsk_status bsk_cyclic_create_device(const double *d_a, const double *d_b, const double *d_c, int64_t n,
+                                    int32_t device, bsk_cyclic **out) {
+    BSK_REQUIRE(d_a && d_b && d_c && out, BSK_ERR_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    BSK_REQUIRE(n >= 3, BSK_ERR_ARGUMENT, "cyclic tridiagonal matrix needs n >= 3");
+    BSK_CUDA(cudaSetDevice(device));
+    std::vector<double> a(n), b(n), c(n);
+    BSK_CUDA(cudaMemcpy(a.data(), d_a, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+    BSK_CUDA(cudaMemcpy(b.data(), d_b, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+    BSK_CUDA(cudaMemcpy(c.data(), d_c, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+    return cyclic_build(a, b, c, device, out);
+}
+
+bsk_status bsk_cyclic_solve(const bsk_cyclic *h, double *d_rhs, int64_t nrhs, void *stream) {
+    BSK_REQUIRE(h && (nrhs == 0 || d_rhs), BSK_ERR_ARGUMENT, "NULL argument");
+    if (nrhs == 0) return BSK_OK;
+    BSK_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double *d_alpha = nullptr;
+    BSK_CUDA(cudaMallocAsync((void **)&d_alpha, 8 * (size_t)nrhs, st));
+    int grid = grid_cols(nrhs, h->device, 8);
+    k_cyclic_forward<8><<<grid, kThreads, 0, st>>>(h->d_w, h->d_g, d_rhs, d_alpha, nrhs, (int)h->n, 1.0 / h->denom);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        k_cyclic_backward<8><<<grid, kThreads, 0, st>>>(h->d_c, h->d_bp, h->d_q, d_alpha, d_rhs, nrhs, (int)h->n);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(d_alpha, st);
+    if (e != cudaSuccess) { set_error("cyclic solve failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
+    return BSK_OK;
+}
+
+bsk_status bsk_cyclic_destroy(bsk_cyclic *h) {
+    if (!h) return BSK_OK;
+    cudaSetDevice(h->device);
+    if (h->d_w) cudaFree(h->d_w);
+    if (h->d_bp) cudaFree(h->d_bp);
+    if (h->d_c) cudaFree(h->d_c);
+    if (h->d_q) cudaFree(h->d_q);
+    if (h->d_g) cudaFree(h->d_g);
+    delete h;
+    return BSK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// handles.cuh — opaque handle layouts, error plumbing and launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bsk.h"
+#include "core.cuh"
+
+namespace bsk {
+
+void set_error(const char *fmt, ...);
+
+#define BSK_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            bsk::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                           __LINE__);                                                        \
+            return BSK_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define BSK_REQUIRE(cond, code, ...)      \
+    do {                                  \
+        if (!(cond)) {                    \
+            bsk::set_error(__VA_ARGS__);  \
+            return (code);                \
+        }                                 \
+    } while (0)
+
+inline int sm_count(int device) {
+    static int cached[64] = {0};
+    if (device < 0 || device >= 64) return 148;
+    if (cached[device] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0)
+            n = 148;
+        cached[device] = n;
+    }
+    return cached[device];
+}
+
+}  // namespace bsk
+
+struct bsk_basis {
+    int kind;       // BSK_BASIS_*
+    int k;
+    int dtype;      // BSK_F32 / BSK_F64
+    int device;
+    int64_t nt;     // stored knots: plain N+k, periodic N+1
+    int64_t N;      // length of the (parent) basis
+    int64_t len;    // length(B) as the user sees it (recombined: N - cl - cr)
+    std::vector<double> h_knots;   // always kept in double on the host (exact for f32 input)
+    void *d_knots;                 // device copy in `dtype`
+    int ilast;                     // walk-back target (plain)
+    // search LUT
+    uint32_t *d_lut;
+    int ncell;
+    double lut_scale;
+    // recombination
+    bsk::RecombView rv;
+};
+
+struct bsk_spline {
+    bsk_basis *basis;     // owned evaluation basis (the PARENT basis for a recombined spline)
+    int64_t ncoef;        // number of coefficients in the evaluation basis
+    std::vector<double> h_coefs;   // host mirror (double; exact for f32)
+    void *d_coefs;        // device, basis dtype, contiguous
+    bool owns_coefs;
+    // what the user handed us (needed again by bsk_spline_set_coefs_device)
+    int user_basis_kind;
+    bsk::RecombView user_rv;
+    int64_t user_len;
+    // local-polynomial table (built lazily): per non-empty knot interval one record
+    //   { t_lo, t_hi, c_0 .. c_{k-1}, pad }  with S(x) = sum_m c_m (x - mid)^m on [t_lo, t_hi)
+    void *d_pp;
+    uint32_t *d_pp_lut;   // search LUT over the record left ends
+    int64_t pp_nrec;
+    int pp_ncell;
+    double pp_scale;
+    int pp_rec;
+    bool pp_valid;
+    std::vector<bsk_spline *> derivs;   // cached Derivative(n) * S, index n (0 unused)
+};
+
+struct bsk_banded {
+    int device;
+    int64_t n;
+    int l, u;
+    double *d_w;          // (l+u+1) x n column-major: raw matrix, LU factors after bsk_banded_lu
+    bool factored;
+    // solve-ready repack (built by bsk_banded_lu): row-major per-row multipliers
+    double *d_lrow;       // n x l : lrow[i][j-1] = L(i, i-j)      (multiplier of x[i-j] in row i)
+    double *d_urow;       // n x u : urow[i][j-1] = U(i, i+j)
+    double *d_dinv;       // n     : 1 / U(i,i)
+    double *d_diag;       // n     : U(i,i)
+    int halo;             // decay halo (rows) validated for the windowed solve, 0 = not usable
+};
+
+struct bsk_cyclic {
+    int device;
+    int64_t n;
+    // factor-once form of the Sherman-Morrison solve (Collocation/cyclic.jl:112-161)
+    double *d_w;      // n: forward multipliers a[i]/b'[i-1]
+    double *d_bp;     // n: b'[i] after elimination
+    double *d_c;      // n: super-diagonal
+    double *d_q;      // n: T^{-1} u
+    double *d_g;      // n: T^{-T} v
+    double vn;        // a1 / gamma
+    double denom;     // 1 + v.q
+};

@@ -1,0 +1,216 @@
+/*
+ * bsk.h — C ABI of libbsplinekit_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for the two data-parallel hot paths of BSplineKit.jl v0.19.2:
+ * many-point spline evaluation and shared-xdata batched interpolation.  The
+ * reference has no FFI of its own (it is pure Julia, extended by multiple dispatch),
+ * so every entry point below names the reference *method* whose body it replaces
+ * (file:line relative to the BSplineKit.jl source tree); the Julia-side `ccall`
+ * overloads that bind them are in bsplinekit.jl_b200/julia/BSplineKitB200.jl and
+ * are walked through in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only; every function returns bsk_status (0 = ok, < 0 = error,
+ *    text via bsk_last_error, thread-local).
+ *  - all indices that cross the ABI are 1-based int64, exactly what the Julia
+ *    reference returns.
+ *  - pointers named d_* are DEVICE pointers on the handle's device; h_* are host
+ *    pointers.  *_create copies what it needs; host arrays stay owned by the caller.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Kernels
+ *    are enqueued and the call returns without synchronising, except the *_host
+ *    convenience calls, which stage through device memory and synchronise.
+ *  - there is no CPU fallback: with no CUDA device every compute call fails with
+ *    BSK_ERR_CUDA.
+ */
+#ifndef BSK_H
+#define BSK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t bsk_status;
+
+enum {
+    BSK_OK = 0,
+    BSK_ERR_ARGUMENT = -1,   /* -> Julia ArgumentError    (e.g. BSplines/basis.jl:80-82)     */
+    BSK_ERR_DIMENSION = -2,  /* -> Julia DimensionMismatch (Collocation/matrix.jl:134-138)   */
+    BSK_ERR_CUDA = -3,       /* -> ErrorException(bsk_last_error())                          */
+    BSK_ERR_ZERO_PIVOT = -4, /* -> ZeroPivotException(i)   (Collocation/matrix.jl:150-198)   */
+    BSK_ERR_ALLOC = -5,
+    BSK_ERR_UNSUPPORTED = -6
+};
+
+enum { BSK_F32 = 0, BSK_F64 = 1 };
+
+/* basis kinds */
+enum {
+    BSK_BASIS_PLAIN = 0,      /* BSplineBasis           (BSplines/basis.jl:70-90)       */
+    BSK_BASIS_PERIODIC = 1,   /* PeriodicBSplineBasis   (BSplines/periodic.jl:181-205)  */
+    BSK_BASIS_RECOMBINED = 2  /* RecombinedBSplineBasis (Recombinations/bases.jl:223-245) */
+};
+
+/* evaluation algorithm selector for bsk_spline_eval */
+enum {
+    BSK_EVAL_AUTO = 0,    /* fastest path whose result is within the stated tolerance       */
+    BSK_EVAL_DEBOOR = 1,  /* de Boor triangle in the reference's operation order (bit-faithful)*/
+    BSK_EVAL_PP = 2       /* per-interval local-polynomial table staged in shared memory    */
+};
+
+/* banded multi-RHS solve algorithm selector */
+enum {
+    BSK_SOLVE_AUTO = 0,
+    BSK_SOLVE_TWOPASS = 1,  /* BANSLV order, forward sweep then backward sweep over HBM      */
+    BSK_SOLVE_WINDOWED = 2  /* single pass: forward sweep + windowed backward sweep on chip  */
+};
+
+typedef struct bsk_basis bsk_basis;
+typedef struct bsk_spline bsk_spline;
+typedef struct bsk_banded bsk_banded;
+typedef struct bsk_cyclic bsk_cyclic;
+
+/* Corner blocks of a RecombineMatrix (Recombinations/matrices.jl:70-110):
+ * ul is ul_rows x nl, lr is lr_rows x nr, column-major doubles. */
+typedef struct {
+    int32_t cl, cr;           /* number of constraints left / right  (num_constraints) */
+    int32_t nl, nr;           /* number of recombined functions       (num_recombined)  */
+    int32_t ul_rows, lr_rows;
+    const double *ul, *lr;
+} bsk_recomb_desc;
+
+/* ---- library / device utilities -------------------------------------------------- */
+const char *bsk_version(void);
+size_t bsk_last_error(char *buf, size_t buflen);
+bsk_status bsk_device_count(int32_t *count);
+bsk_status bsk_malloc(int32_t device, size_t nbytes, void **d_ptr);
+bsk_status bsk_free(int32_t device, void *d_ptr);
+bsk_status bsk_memcpy_h2d(int32_t device, void *d_dst, const void *h_src, size_t nbytes, void *stream);
+bsk_status bsk_memcpy_d2h(int32_t device, void *h_dst, const void *d_src, size_t nbytes, void *stream);
+bsk_status bsk_stream_create(int32_t device, void **stream);
+bsk_status bsk_stream_destroy(int32_t device, void *stream);
+bsk_status bsk_stream_sync(int32_t device, void *stream);
+
+/* ---- bases ------------------------------------------------------------------------
+ * kind PLAIN / RECOMBINED: h_knots = full knot vector t[1..N+k] (already augmented,
+ *   BSplines/knots.jl:68-84), dtype BSK_F32/BSK_F64.  RECOMBINED additionally takes the
+ *   corner blocks; knots are the parent's (Recombinations/bases.jl:300).
+ * kind PERIODIC: h_knots = breakpoints in one period INCLUDING the endpoint
+ *   (length N+1; BSplines/periodic.jl:37-55).
+ * Replaces: the BSplineBasis / PeriodicBSplineBasis / RecombinedBSplineBasis structs as
+ * seen by evaluate_all / find_knot_interval / Spline evaluation. */
+bsk_status bsk_basis_create(int32_t kind, int32_t k, int32_t dtype, const void *h_knots,
+                            int64_t nknots, const bsk_recomb_desc *recomb, int32_t device,
+                            bsk_basis **out);
+bsk_status bsk_basis_destroy(bsk_basis *b);
+bsk_status bsk_basis_length(const bsk_basis *b, int64_t *len); /* length(B) */
+
+/* find_knot_interval(ts, x)  — BSplines/evaluate_all.jl:102-119, periodic.jl:85-100,
+ * knots.jl:32-41.  d_x: n abscissae of the basis dtype; d_idx: n int64 (1-based);
+ * d_zone: n int8 in {-1,0,1} or NULL. */
+bsk_status bsk_find_knot_interval(const bsk_basis *b, const void *d_x, int64_t n,
+                                  int64_t *d_idx, int8_t *d_zone, void *stream);
+
+/* evaluate_all(B, x, Derivative(deriv), T; ileft) — BSplines/evaluate_all.jl:53-64,
+ * 128-204; periodic.jl:228-236; Recombinations/bases.jl:386-420.
+ * out_dtype = T (BSK_F32 allowed with an F64 basis: knot differences are formed in
+ * F64 then rounded, evaluate_all.jl:152-155).  d_bs is [n][k] with k fastest, i.e.
+ * Julia's NTuple{k,T} per point, in the reference's REVERSED order (b_i .. b_{i-k+1}).
+ * d_ileft: optional n int64 known interval indices (NULL = search). */
+bsk_status bsk_evaluate_all(const bsk_basis *b, const void *d_x, int64_t n, int32_t deriv,
+                            int32_t out_dtype, const int64_t *d_ileft, int64_t *d_idx,
+                            void *d_bs, void *stream);
+
+/* ---- splines ----------------------------------------------------------------------
+ * Spline(B, coefs) — Splines/spline.jl:41-60.  h_coefs: length(B) values of the basis
+ * dtype (for a recombined basis they are converted to parent coefficients once here,
+ * Recombinations/splines.jl:32-65).  bsk_spline_set_coefs_device re-points the handle at
+ * device-resident coefficients (e.g. one column of a bsk_banded_solve result with
+ * element stride `stride`). */
+bsk_status bsk_spline_create(const bsk_basis *b, const void *h_coefs, int64_t ncoef,
+                             bsk_spline **out);
+bsk_status bsk_spline_set_coefs_device(bsk_spline *s, const void *d_coefs, int64_t ncoef,
+                                       int64_t stride, void *stream);
+bsk_status bsk_spline_destroy(bsk_spline *s);
+/* copy of coefficients(S) in the spline's own basis (parent basis for recombined) */
+bsk_status bsk_spline_coefficients(const bsk_spline *s, void *h_out, int64_t ncoef);
+bsk_status bsk_spline_order(const bsk_spline *s, int32_t *k, int64_t *ncoef, int64_t *nknots);
+bsk_status bsk_spline_knots(const bsk_spline *s, void *h_out, int64_t nknots);
+
+/* Derivative(n) * S — Splines/spline.jl:272-330, Splines/periodic.jl:76-117,
+ * BSplines/basis.jl:104-111.  Returns a NEW spline of order k - n. */
+bsk_status bsk_spline_derivative(const bsk_spline *s, int32_t n, bsk_spline **out);
+
+/* (S::Spline)(x) broadcast over a device vector — Splines/spline.jl:144-209.
+ * Evaluates nout derivative orders derivs[j] (0 = value) of S at the n points in d_x in
+ * ONE pass over the points; d_outs[j] receives n values of the spline dtype.  Points
+ * outside the knot domain give 0 (spline.jl:164-168); periodic bases wrap.
+ * algo: BSK_EVAL_*. */
+bsk_status bsk_spline_eval(const bsk_spline *s, const void *d_x, int64_t n, int32_t nout,
+                           const int32_t *derivs, void *const *d_outs, int32_t algo,
+                           void *stream);
+/* Same through HOST buffers (H2D, kernel, D2H, synchronise). */
+bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n, int32_t nout,
+                                const int32_t *derivs, void *const *h_outs, int32_t algo);
+
+/* ---- collocation --------------------------------------------------------------------
+ * collocation_matrix!(C, B, x, Derivative(deriv); clip_threshold) —
+ * Collocation/Collocation.jl:209-251 into CollocationMatrix band storage
+ * data[u+1+i-j, j], (2k-3) x length(B) column-major (Collocation/matrix.jl:105-117,
+ * Collocation.jl:165-198).  d_x: nx F64 points (nx must equal length(B)).
+ * *h_n_outside (optional) receives the number of non-clipped entries that fell outside
+ * the bands (the reference emits one @warn each, Collocation.jl:239-244).  Synchronises
+ * only if h_n_outside != NULL. */
+bsk_status bsk_collocation_matrix(const bsk_basis *b, const double *d_x, int64_t nx,
+                                  int32_t deriv, double clip_threshold, double *d_band,
+                                  int64_t *h_n_outside, void *stream);
+/* Periodic cubic: CyclicTridiagonalMatrix diagonals a, b, c (Collocation/cyclic.jl:21-33). */
+bsk_status bsk_collocation_cyclic(const bsk_basis *b, const double *d_x, int64_t nx,
+                                  int32_t deriv, double clip_threshold, double *d_a, double *d_b,
+                                  double *d_c, int64_t *h_n_outside, void *stream);
+
+/* ---- banded LU + multi-RHS solve ----------------------------------------------------
+ * CollocationMatrix / lu! / ldiv!  — Collocation/matrix.jl:40-117,132-201,218-271.
+ * d_band: (l+u+1) x n column-major F64 with l == u; copied into the handle. */
+bsk_status bsk_banded_create(const double *d_band, int64_t n, int32_t l, int32_t u, int32_t device,
+                             bsk_banded **out);
+bsk_status bsk_banded_create_host(const double *h_band, int64_t n, int32_t l, int32_t u,
+                                  int32_t device, bsk_banded **out);
+/* lu!(C): BANFAC without pivoting, in place in the handle.  On a zero pivot returns
+ * BSK_ERR_ZERO_PIVOT and *info_pivot = 1-based row (ZeroPivotException(i)). */
+bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot);
+bsk_status bsk_banded_data(const bsk_banded *h, double *h_out); /* (l+u+1) x n copy */
+/* Rows of halo validated at factor time for BSK_SOLVE_WINDOWED (0 = windowed unavailable). */
+bsk_status bsk_banded_halo(const bsk_banded *h, int32_t *halo);
+/* ldiv!(F, Y): BANSLV on nrhs right-hand sides stored interleaved, d_rhs[(i-1)*nrhs + c]
+ * (== Vector{SVector{nrhs,Float64}}; test/interpolation.jl:57), solved IN PLACE.
+ * algo: BSK_SOLVE_*. */
+bsk_status bsk_banded_solve(const bsk_banded *h, double *d_rhs, int64_t nrhs, int32_t algo,
+                            void *stream);
+bsk_status bsk_banded_solve_host(const bsk_banded *h, double *h_rhs, int64_t nrhs, int32_t algo);
+bsk_status bsk_banded_destroy(bsk_banded *h);
+
+/* ---- cyclic tridiagonal (periodic cubic interpolation) -------------------------------
+ * CyclicTridiagonalMatrix + ldiv! — Collocation/cyclic.jl:21-33,112-197.  The reference
+ * re-eliminates the matrix for every right-hand side (SplineInterpolations.jl:147-149);
+ * here it is factored once at create. */
+bsk_status bsk_cyclic_create(const double *h_a, const double *h_b, const double *h_c, int64_t n,
+                             int32_t device, bsk_cyclic **out);
+bsk_status bsk_cyclic_create_device(const double *d_a, const double *d_b, const double *d_c,
+                                    int64_t n, int32_t device, bsk_cyclic **out);
+/* d_rhs interleaved [n][nrhs], solved in place. */
+bsk_status bsk_cyclic_solve(const bsk_cyclic *h, double *d_rhs, int64_t nrhs, void *stream);
+bsk_status bsk_cyclic_destroy(bsk_cyclic *h);
+
+/* ---- timing helper (CUDA events on `stream`) ----------------------------------------- */
+bsk_status bsk_event_create(int32_t device, void **event);
+bsk_status bsk_event_record(void *event, void *stream);
+bsk_status bsk_event_elapsed_ms(void *start, void *stop, float *ms); /* synchronises stop */
+bsk_status bsk_event_destroy(void *event);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSK_H */

@@ -1,0 +1,568 @@
+"""GPU parity tests: every CUDA path, called through the C ABI (via the ctypes host mirror),
+against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): knot-interval indices bit-exact; Float64 within 1e-13
+relative; Float32 within 1e-5 relative.  The bit-faithful paths (de Boor, evaluate_all,
+collocation, LU, two-pass solve) are additionally required to be BIT-EXACT here.
+Relative error = max|gpu - ref| / max|ref| over the output array.
+"""
+import numpy as np
+import pytest
+
+from conftest import dec_range
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-13
+TOL32 = 1e-5
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+def _points(synth, seed, n, a, b, extra=()):
+    x = a + (b - a) * synth.u_numpy(seed, 0, n)
+    return np.concatenate([x, np.asarray(extra, dtype=np.float64)])
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from bsplinekit_b200 import synth as s
+    return s
+
+
+# ------------------------------------------------------------------------------------------------
+# K1: knot search
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [2, 4, 5, 8])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_find_knot_interval_plain(bk, oracle, synth, k, dt):
+    npdt = np.float64 if dt == "f64" else np.float32
+    br = synth.breakpoints(3, 200).astype(npdt)
+    B = bk.BSplineBasis(k, br)
+    t = B.knots()
+    x = _points(synth, 11, 200000, -0.1, 1.1, extra=list(t) + [t[0] - 1, t[-1] + 1, np.nan]).astype(npdt)
+    i_ref, z_ref = oracle.find_knot_interval(0, k, t, x, kt=dt)
+    i, z = bk.find_knot_interval(B, x)
+    assert np.array_equal(i, i_ref)
+    assert np.array_equal(z, z_ref)
+    # reference's own assertions (test/bsplines.jl:18-30)
+    a, b = t[0], t[-1]
+    N = len(B)
+    ii, zz = bk.find_knot_interval(B, np.array([a - 1, a, b, b + 1], dtype=npdt))
+    assert list(zip(ii.tolist(), zz.tolist())) == [(1, -1), (k, 0), (N, 0), (N, 1)]
+
+
+@pytest.mark.parametrize("k", [3, 4, 6])
+def test_find_knot_interval_periodic(bk, oracle, synth, k):
+    br = 2.0 * synth.breakpoints(8, 101) - 1.0
+    B = bk.PeriodicBSplineBasis(k, br)
+    x = _points(synth, 12, 100000, -5.0, 7.0, extra=list(br) + [br[0] - 2.0, br[-1] + 2.0])
+    i_ref, z_ref = oracle.find_knot_interval(1, k, br, x)
+    i, z = bk.find_knot_interval(B, x)
+    assert np.array_equal(i, i_ref)
+    assert np.all(z == 0)
+
+
+def test_find_knot_interval_large_no_smem(bk, oracle, synth):
+    """10^5 knots: the knot vector does not fit in shared memory (global-memory path)."""
+    br = synth.breakpoints(10, 99996)
+    B = bk.BSplineBasis(8, br)
+    x = _points(synth, 13, 300000, 0.0, 1.0, extra=list(br[::97]))
+    i_ref, z_ref = oracle.find_knot_interval(0, 8, B.knots(), x)
+    i, z = bk.find_knot_interval(B, x)
+    assert np.array_equal(i, i_ref) and np.array_equal(z, z_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# K2: evaluate_all
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 8])
+def test_evaluate_all_plain_bitexact(bk, oracle, synth, k):
+    br = synth.breakpoints(3, 64)
+    B = bk.BSplineBasis(k, br)
+    t = B.knots()
+    x = _points(synth, 14, 20000, -0.05, 1.05, extra=list(t) + [np.nan])
+    for nd in range(0, k + 1):
+        i_ref, bs_ref = oracle.evaluate_all(0, k, t, x, nderiv=nd)
+        i, bs = bk.evaluate_all(B, x, bk.Derivative(nd))
+        assert np.array_equal(i, i_ref), (k, nd)
+        assert np.array_equal(bs, bs_ref, equal_nan=True), (k, nd)
+    # partition of unity inside the domain (test/bsplines.jl:84-90)
+    xin = x[(x >= 0) & (x <= 1)]
+    _, bs = bk.evaluate_all(B, xin)
+    assert np.max(np.abs(bs.sum(axis=1) - 1)) < 1e-14
+
+
+@pytest.mark.parametrize("k", [4, 6, 8])
+def test_evaluate_all_float32_output(bk, oracle, synth, k):
+    """T = Float32 with Float64 knots: knot differences in F64, rounded, triangle in F32."""
+    br = synth.breakpoints(3, 64)
+    B = bk.BSplineBasis(k, br)
+    x = _points(synth, 15, 20000, 0.0, 1.0)
+    for nd in (0, 1, 2):
+        i_ref, bs_ref = oracle.evaluate_all(0, k, B.knots(), x, nderiv=nd, vt="f32")
+        i, bs = bk.evaluate_all(B, x, bk.Derivative(nd), np.float32)
+        assert bs.dtype == np.float32
+        assert np.array_equal(i, i_ref)
+        assert np.array_equal(bs, bs_ref)
+        _, bs64 = oracle.evaluate_all(0, k, B.knots(), x, nderiv=nd)
+        assert relerr(bs, bs64) < TOL32
+
+
+@pytest.mark.parametrize("k", [4, 8])
+def test_evaluate_all_float32_basis(bk, oracle, synth, k):
+    br = synth.breakpoints(3, 64).astype(np.float32)
+    B = bk.BSplineBasis(k, br)
+    x = _points(synth, 16, 20000, 0.0, 1.0).astype(np.float32)
+    i_ref, bs_ref = oracle.evaluate_all(0, k, B.knots(), x, kt="f32", vt="f32")
+    i, bs = bk.evaluate_all(B, x)
+    assert np.array_equal(i, i_ref) and np.array_equal(bs, bs_ref)
+
+
+def test_evaluate_all_ileft(bk, oracle, synth):
+    br = dec_range(-1, 1, 21)
+    B = bk.BSplineBasis(4, br)
+    i, bs = B(0.42)
+    assert i == 18
+    i2, bs2 = B(0.44, ileft=i)
+    i_ref, bs_ref = oracle.evaluate_all(0, 4, B.knots(), [0.44], ileft=[18])
+    assert i2 == 18 and np.array_equal(np.array(bs2), bs_ref[0])
+
+
+@pytest.mark.parametrize("k", [3, 4, 6])
+def test_evaluate_all_periodic_bitexact(bk, oracle, synth, k):
+    br = 2.0 * synth.breakpoints(8, 41) - 1.0
+    B = bk.PeriodicBSplineBasis(k, br)
+    x = _points(synth, 17, 20000, -5.0, 7.0, extra=list(br))
+    for nd in range(0, k):
+        i_ref, bs_ref = oracle.evaluate_all(1, k, br, x, nderiv=nd)
+        i, bs = bk.evaluate_all(B, x, bk.Derivative(nd))
+        assert np.array_equal(i, i_ref)
+        assert np.array_equal(bs, bs_ref)
+
+
+def test_docstring_goldens_on_gpu(bk):
+    """Class-A goldens of the reference docstrings, through the CUDA path, bit for bit
+    (src/BSplines/BSplines.jl:56-79; src/BSplines/periodic.jl:157-161)."""
+    B = bk.BSplineBasis(bk.BSplineOrder(4), dec_range(-1, 1, 21))
+    assert B(0.42) == (18, (0.0013333333333333268, 0.28266666666666657, 0.6306666666666667, 0.08533333333333339))
+    assert B(0.44, ileft=18) == (18, (0.01066666666666666, 0.4146666666666667, 0.5386666666666665, 0.03599999999999999))
+    i, bs = B(0.42, np.float32)
+    assert i == 18 and [float(v) for v in bs] == [float(np.float32(v)) for v in
+                                                   (0.0013333336, 0.28266668, 0.6306667, 0.085333325)]
+    assert B(0.42, bk.Derivative(1)) == (18, (0.19999999999999937, 6.4, -3.3999999999999977, -3.200000000000001))
+    P = bk.PeriodicBSplineBasis(bk.BSplineOrder(4), dec_range(-1, 1, 11))
+    assert P(-0.42) == (5, (0.12150000000000002, 0.6571666666666667, 0.22116666666666668, 0.00016666666666666563))
+    assert P(-0.42 + 2) == (15, (0.12150000000000015, 0.6571666666666667, 0.22116666666666657, 0.00016666666666666674))
+
+
+def _robin(bk, oracle, k, br):
+    B = bk.BSplineBasis(k, br)
+    R = bk.RecombinedBSplineBasis(B, bk.Derivative(0) + 3 * bk.Derivative(1))
+    rc = oracle.robin_corners(k, B.knots(), [1.0, 3.0])
+    return B, R, rc
+
+
+@pytest.mark.parametrize("k", [4, 5, 8])
+def test_evaluate_all_recombined_robin(bk, oracle, synth, k):
+    br = synth.breakpoints(10, 50)
+    B, R, rc = _robin(bk, oracle, k, br)
+    assert np.array_equal(R.ul, rc.ul) and np.array_equal(R.lr, rc.lr)
+    x = _points(synth, 18, 20000, 0.0, 1.0, extra=[0.0, 1.0] + list(br[:4]) + list(br[-4:]))
+    for nd in (0, 1, 2):
+        i_ref, bs_ref = oracle.evaluate_all(0, k, B.knots(), x, nderiv=nd, recomb=rc)
+        i, bs = bk.evaluate_all(R, x, bk.Derivative(nd))
+        assert np.array_equal(i, i_ref)
+        assert np.array_equal(bs, bs_ref)
+        i32, bs32 = bk.evaluate_all(R, x, bk.Derivative(nd), np.float32)
+        _, bs32_ref = oracle.evaluate_all(0, k, B.knots(), x, nderiv=nd, vt="f32", recomb=rc)
+        assert np.array_equal(bs32, bs32_ref)
+        assert relerr(bs32, bs_ref) < TOL32
+
+
+@pytest.mark.parametrize("ops", ["dirichlet", "neumann", "mixed01"])
+def test_evaluate_all_recombined_simple(bk, oracle, synth, ops):
+    k = 5
+    br = synth.breakpoints(10, 30)
+    B = bk.BSplineBasis(k, br)
+    if ops == "dirichlet":
+        R = bk.RecombinedBSplineBasis(B, bk.Derivative(0))
+        rc = oracle.Recomb(1, 1, 0, 0, np.zeros((1, 0)), np.zeros((1, 0)))
+    elif ops == "neumann":
+        R = bk.RecombinedBSplineBasis(B, bk.Derivative(1))
+        rc = oracle.Recomb(1, 1, 1, 1, np.ones((2, 1)), np.ones((2, 1)))
+    else:
+        R = bk.RecombinedBSplineBasis(B, (bk.Derivative(0), bk.Derivative(1)))
+        rc = oracle.Recomb(2, 2, 0, 0, np.zeros((2, 0)), np.zeros((2, 0)))
+    assert len(R) == len(B) - rc.cl - rc.cr
+    x = _points(synth, 19, 5000, 0.0, 1.0, extra=[0.0, 1.0])
+    i_ref, bs_ref = oracle.evaluate_all(0, k, B.knots(), x, recomb=rc)
+    i, bs = bk.evaluate_all(R, x)
+    assert np.array_equal(i, i_ref) and np.array_equal(bs, bs_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# K3: spline evaluation
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 7, 8])
+def test_spline_eval_deboor_bitexact(bk, oracle, synth, k):
+    br = synth.breakpoints(3, 100)
+    B = bk.BSplineBasis(k, br)
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    x = _points(synth, 20, 100001, -0.05, 1.05, extra=list(B.knots()) + [np.nan])
+    ref = oracle.spline_eval(0, k, B.knots(), c, x)
+    got = S(x, algo=bk.EVAL_DEBOOR)
+    assert np.array_equal(got, ref, equal_nan=True)
+    for nd in range(1, k):
+        kd, td, cd = oracle.spline_derivative(0, k, B.knots(), c, nd)
+        dS = bk.Derivative(nd) * S
+        assert np.array_equal(dS.coefficients(), cd)
+        assert np.array_equal(dS.knots(), td)
+        refd = oracle.spline_eval(0, kd, td, cd, x)
+        assert np.array_equal(dS(x, algo=bk.EVAL_DEBOOR), refd, equal_nan=True)
+    with pytest.raises(bk.ArgumentError):
+        bk.Derivative(k) * S
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 7, 8])
+def test_spline_eval_pp_tolerance(bk, oracle, synth, k):
+    """Local-polynomial fast path: value and all derivatives in one pass, within 1e-13."""
+    br = synth.breakpoints(3, 300)
+    B = bk.BSplineBasis(k, br)
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    x = _points(synth, 21, 200003, -0.02, 1.02, extra=list(B.knots()) + [np.nan])
+    derivs = list(range(0, min(k, 4)))
+    outs = S.evaluate(x, derivs, algo=bk.EVAL_PP)
+    for nd, got in zip(derivs, outs):
+        kd, td, cd = (k, B.knots(), c) if nd == 0 else oracle.spline_derivative(0, k, B.knots(), c, nd)
+        ref = oracle.spline_eval(0, kd, td, cd, x)
+        assert np.isnan(got[-1])
+        e = relerr(got[:-1], ref[:-1])
+        assert e < TOL64, (k, nd, e)
+    # outside the domain -> exact zeros (spline.jl:164-168)
+    assert np.all(outs[0][x[:-1] < 0] == 0) and np.all(outs[0][x[:-1] > 1] == 0)
+
+
+def test_spline_eval_device_vectors(bk, oracle, synth):
+    """Device-resident x and outputs (the DeviceVector path of the Julia shim)."""
+    import torch
+    k = 4
+    br = synth.breakpoints(3, 1000)
+    B = bk.BSplineBasis(k, br)
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    n = (1 << 22) + 3
+    xd = synth.u_torch(5, 0, n)
+    v, dv = S.evaluate(xd, (0, 1))
+    assert v.is_cuda and v.shape == xd.shape
+    xh = synth.u_numpy(5, 0, n)
+    assert np.array_equal(xd.cpu().numpy(), xh)
+    ref = oracle.spline_eval(0, k, B.knots(), c, xh)
+    kd, td, cd = oracle.spline_derivative(0, k, B.knots(), c, 1)
+    refd = oracle.spline_eval(0, kd, td, cd, xh)
+    assert relerr(v.cpu().numpy(), ref) < TOL64
+    assert relerr(dv.cpu().numpy(), refd) < TOL64
+    # unaligned device views take the scalar path
+    v2 = S.evaluate(xd[1:], (0,))[0]
+    assert np.array_equal(v2.cpu().numpy(), v.cpu().numpy()[1:])
+    # faithful path on the same points is bit-exact
+    vb = S.evaluate(xd, (0,), algo=bk.EVAL_DEBOOR)[0]
+    assert np.array_equal(vb.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("k", [3, 4, 6])
+def test_spline_eval_periodic(bk, oracle, synth, k):
+    L = 2.0
+    br = L * synth.breakpoints(8, 201) - 1.0
+    B = bk.PeriodicBSplineBasis(k, br)
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    x = _points(synth, 22, 100000, -1.0 - 2 * L, 1.0 + 2 * L, extra=list(br))
+    ref = oracle.spline_eval(1, k, br, c, x)
+    assert np.array_equal(S(x, algo=bk.EVAL_DEBOOR), ref)
+    derivs = list(range(0, k))[:4]
+    outs = S.evaluate(x, derivs)       # AUTO -> pp in the main period, de Boor outside
+    for nd, got in zip(derivs, outs):
+        if nd == 0:
+            r = ref
+        else:
+            kd, td, cd = oracle.spline_derivative(1, k, br, c, nd)
+            dS = bk.Derivative(nd) * S
+            assert np.array_equal(dS.coefficients(), cd)
+            r = oracle.spline_eval(1, kd, td, cd, x)
+            assert np.array_equal(dS(x, algo=bk.EVAL_DEBOOR), r)
+        assert relerr(got, r) < TOL64, (k, nd)
+    # closed curve: S(a) == S(b) (test/periodic.jl:8-23)
+    assert S(np.array([-1.0]))[0] == pytest.approx(S(np.array([1.0]))[0], abs=1e-14)
+
+
+@pytest.mark.parametrize("k", [4, 8])
+def test_spline_eval_float32(bk, oracle, synth, k):
+    br = synth.breakpoints(10, 500).astype(np.float32)
+    B = bk.BSplineBasis(k, br)
+    c = (2 * synth.u_numpy(4, 0, len(B)) - 1).astype(np.float32)
+    S = bk.Spline(B, c)
+    x = synth.u_numpy(11, 0, 100000).astype(np.float32)
+    ref = oracle.spline_eval(0, k, B.knots(), c, x, kt="f32")
+    got = S(x, algo=bk.EVAL_DEBOOR)
+    assert got.dtype == np.float32 and np.array_equal(got, ref)
+    ref64 = oracle.spline_eval(0, k, B.knots().astype(np.float64), c.astype(np.float64), x.astype(np.float64))
+    assert relerr(S(x), ref64) < TOL32          # fast path vs a Float64 evaluation
+    assert relerr(ref, ref64) < TOL32
+
+
+def test_spline_eval_recombined(bk, oracle, synth):
+    """Recombined spline == parent spline with converted coefficients (Recombinations/splines.jl:32-65)."""
+    k = 6
+    br = synth.breakpoints(10, 80)
+    B, R, rc = _robin(bk, oracle, k, br)
+    cr_ = 2 * synth.u_numpy(4, 0, len(R)) - 1
+    S = bk.Spline(R, cr_)
+    A = R.recombination_matrix()
+    cp = S.coefficients()
+    assert np.allclose(cp, A @ cr_, rtol=0, atol=1e-15)
+    x = _points(synth, 23, 50000, 0.0, 1.0, extra=[0.0, 1.0])
+    ref = oracle.spline_eval(0, k, B.knots(), cp, x)
+    assert np.array_equal(S(x, algo=bk.EVAL_DEBOOR), ref)
+    # the Robin condition u + 3 du/dn = 0 holds at both ends (test/recombination.jl:284-305)
+    v, dv = S.evaluate(np.array([0.0, 1.0]), (0, 1), algo=bk.EVAL_DEBOOR)
+    assert abs(v[0] - 3 * dv[0]) < 1e-9 * max(1, abs(dv[0]))
+    assert abs(v[1] + 3 * dv[1]) < 1e-9 * max(1, abs(dv[1]))
+    with pytest.raises(bk.DimensionMismatch):
+        bk.Spline(R, np.zeros(len(R) + 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# K4: collocation assembly
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [3, 4, 6, 8])
+def test_collocation_matrix_plain(bk, oracle, synth, k):
+    br = synth.breakpoints(6, 300)
+    B = bk.BSplineBasis(k, br)
+    x = bk.collocation_points(B)
+    assert np.array_equal(x, oracle.greville(0, k, B.knots()))
+    for nd in (0, 1, 2):
+        if nd >= k:
+            continue
+        ref, nout_ref = oracle.collocation_matrix(0, k, B.knots(), x, nderiv=nd)
+        Cm, nout = bk.collocation_matrix(B, x, bk.Derivative(nd), return_outside=True)
+        assert nout == nout_ref
+        assert np.array_equal(Cm.data(), ref)
+    # rows sum to one; out-of-domain rows are zero (test/collocation.jl:112-121)
+    x2 = x.copy(); x2[0] = -1.0; x2[-1] = 2.0
+    Cm = bk.collocation_matrix(B, x2)
+    D = Cm.dense()
+    assert np.all(D[0] == 0) and np.all(D[-1] == 0)
+    assert np.allclose(D[1:-1].sum(axis=1), 1.0, atol=1e-14)
+
+
+def test_collocation_matrix_robin_c5_shape(bk, oracle, synth):
+    """Config C5 (scaled down here; full size in test_full_size): Robin D0 + 3 D1, k = 8, Derivative(2)."""
+    k = 8
+    br = synth.breakpoints(10, 2000)
+    B, R, rc = _robin(bk, oracle, k, br)
+    x = bk.collocation_points(R)
+    assert np.array_equal(x, oracle.greville(2, k, B.knots(), cl=1, N=len(R)))
+    for nd in (0, 2):
+        ref, nout_ref = oracle.collocation_matrix(2, k, B.knots(), x, nderiv=nd, recomb=rc)
+        Cm, nout = bk.collocation_matrix(R, x, bk.Derivative(nd), return_outside=True)
+        assert nout == nout_ref == 0
+        assert np.array_equal(Cm.data(), ref)
+    with pytest.raises(bk.ArgumentError):
+        bk.collocation_matrix(R, x[:-1])
+
+
+def test_collocation_cyclic(bk, oracle, synth):
+    br = synth.breakpoints(8, 1001)
+    B = bk.PeriodicBSplineBasis(4, br)
+    x = bk.collocation_points(B)
+    a, b, c, nout = oracle.collocation_cyclic(4, br, x)
+    M = bk.collocation_matrix(B, x)
+    assert nout == 0
+    assert np.array_equal(M.a, a) and np.array_equal(M.b, b) and np.array_equal(M.c, c)
+    assert np.allclose(M.dense().sum(axis=1), 1.0, atol=1e-14)       # test/periodic.jl:166-170
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 / K6: banded LU and multi-RHS solve
+# ------------------------------------------------------------------------------------------------
+def _interp_system(bk, oracle, synth, n, k, seed=6):
+    xdata = synth.breakpoints(seed, n)
+    t = bk.make_knots(xdata, k)
+    assert np.array_equal(t, oracle.make_knots(xdata, k))
+    B = bk.BSplineBasis(k, t, augment=False)
+    Cm = bk.collocation_matrix(B, xdata)
+    ref, _ = oracle.collocation_matrix(0, k, t, xdata)
+    assert np.array_equal(Cm.data(), ref)
+    return xdata, t, B, Cm, ref
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 6, 8])
+def test_banded_lu_bitexact(bk, oracle, synth, k):
+    xdata, t, B, Cm, ref = _interp_system(bk, oracle, synth, 257, k)
+    lu_ref = ref.copy(order="F")
+    assert oracle.banded_lu(lu_ref) == 0
+    Cm.lu_()
+    assert np.array_equal(Cm.data(), lu_ref)
+
+
+def test_banded_lu_special_cases(bk):
+    """test/collocation.jl:4-53: 1x1, zero pivots, wrong dimensions."""
+    C1 = bk.CollocationMatrix(np.array([[2.0]]))
+    C1.lu_()
+    y = np.array([[3.0]])
+    C1.ldiv_(y)
+    assert y[0, 0] == 1.5
+    with pytest.raises(bk.ZeroPivotException) as ei:
+        bk.CollocationMatrix(np.array([[0.0]])).lu_()
+    assert ei.value.info == 1
+    band = np.zeros((3, 4), order="F")
+    band[1, :] = [1.0, 2.0, 0.0, 4.0]            # diagonal with a zero at i = 3, no off-diagonals
+    with pytest.raises(bk.ZeroPivotException) as ei:
+        bk.CollocationMatrix(band).lu_()
+    assert ei.value.info == 3
+    band[1, 2] = 3.0
+    Cm = bk.CollocationMatrix(band).lu_()
+    with pytest.raises(bk.DimensionMismatch):
+        Cm.ldiv_(np.zeros((5, 2)))
+    y = np.ones((4, 3))
+    Cm.ldiv_(y)
+    assert np.allclose(y[:, 0], [1.0, 0.5, 1 / 3, 0.25])
+
+
+@pytest.mark.parametrize("k,n,nrhs", [(4, 300, 37), (6, 513, 1030), (8, 200, 5), (2, 64, 70), (3, 100, 33)])
+def test_banded_solve_twopass_bitexact(bk, oracle, synth, k, n, nrhs):
+    xdata, t, B, Cm, ref = _interp_system(bk, oracle, synth, n, k)
+    lu_ref = ref.copy(order="F")
+    oracle.banded_lu(lu_ref)
+    Cm.lu_()
+    Y = (2 * synth.u_numpy(7, 0, n * nrhs) - 1).reshape(n, nrhs)
+    Yref = oracle.banded_solve(lu_ref, Y.copy())
+    Yg = Y.copy()
+    Cm.ldiv_(Yg, algo=bk.SOLVE_TWOPASS)
+    assert np.array_equal(Yg, Yref)
+    # residual ||C c - y|| (test/splines.jl:170-187)
+    res = oracle.banded_matvec(ref, Yg) - Y
+    assert np.max(np.abs(res)) < 1e-12
+
+
+@pytest.mark.parametrize("k,n,nrhs", [(6, 4096, 2048), (4, 2000, 1500), (8, 3000, 1100)])
+def test_banded_solve_windowed_tolerance(bk, oracle, synth, k, n, nrhs):
+    """Single-pass windowed solve: coefficients within 1e-13 of BANSLV (in practice ~1e-16)."""
+    import torch
+    xdata, t, B, Cm, ref = _interp_system(bk, oracle, synth, n, k)
+    lu_ref = ref.copy(order="F")
+    oracle.banded_lu(lu_ref)
+    Cm.lu_()
+    assert Cm.halo > 0, "decay bound not met for a well-conditioned interpolation matrix"
+    Y = (2 * synth.u_numpy(7, 0, n * nrhs) - 1).reshape(n, nrhs)
+    Yref = oracle.banded_solve(lu_ref, Y.copy())
+    Yd = torch.from_numpy(Y).cuda()
+    Cm.ldiv_(Yd, algo=bk.SOLVE_WINDOWED)
+    got = Yd.cpu().numpy()
+    e = relerr(got, Yref)
+    assert e < TOL64, e
+    colmax = np.max(np.abs(Yref), axis=0)
+    assert np.max(np.max(np.abs(got - Yref), axis=0) / colmax) < TOL64
+    Yd2 = torch.from_numpy(Y).cuda()
+    Cm.ldiv_(Yd2)                       # AUTO
+    assert relerr(Yd2.cpu().numpy(), Yref) < TOL64
+
+
+def test_interpolate_readme_case_c1(bk, oracle, synth):
+    """Config C1: xdata = (0:10).^2, k = 4 (README.md:41-46, test/interpolation.jl:61-66)."""
+    xdata = np.arange(11) ** 2
+    ydata = synth.u_numpy(1, 0, 11)
+    itp = bk.interpolate(xdata, ydata, bk.BSplineOrder(4))
+    S = itp.spline
+    got = S(xdata.astype(np.float64), algo=bk.EVAL_DEBOOR)
+    assert np.allclose(got, ydata, rtol=1e-12, atol=1e-13)           # S.(xs) ≈ ys
+    # against the oracle chain
+    xf = xdata.astype(np.float64)
+    t = oracle.make_knots(xf, 4)
+    band, _ = oracle.collocation_matrix(0, 4, t, xf)
+    oracle.banded_lu(band)
+    c = oracle.banded_solve(band, ydata.copy().reshape(-1, 1)).ravel()
+    assert np.array_equal(S.coefficients(), c)
+    xs = 100 * synth.u_numpy(2, 0, 1000000)
+    ref = oracle.spline_eval(0, 4, t, c, xs)
+    assert np.array_equal(S(xs, algo=bk.EVAL_DEBOOR), ref)
+    assert relerr(S(xs), ref) < TOL64
+
+
+def test_interpolate_docstring_goldens(bk):
+    """src/SplineInterpolations/SplineInterpolations.jl:201-257 (class B: cospi inputs)."""
+    xs = dec_range(-1, 1, 21)
+    ys = np.cos(np.pi * xs)
+    S = bk.interpolate(xs, ys, bk.BSplineOrder(4)).spline
+    assert S(np.array([-1.0]), algo=bk.EVAL_DEBOOR)[0] == -1.0
+    assert S(np.array([-0.99]))[0] == pytest.approx(-0.9996420091470221, abs=2e-15)
+    assert S(np.array([0.998]))[0] == pytest.approx(-1.0000122303614758, abs=2e-15)
+    d1 = (bk.Derivative(1) * S)(np.array([-1.0]))[0]
+    d2 = (bk.Derivative(2) * S)(np.array([-1.0]))[0]
+    assert d1 == pytest.approx(-0.01663433622896893, abs=5e-13)
+    assert d2 == pytest.approx(10.527273287554928, abs=5e-11)
+    xp = dec_range(-1, 0.9, 20)
+    Sp = bk.interpolate(xp, np.cos(np.pi * xp), bk.BSplineOrder(4), bk.Periodic(2.0)).spline
+    assert Sp(np.array([-0.99]))[0] == pytest.approx(-0.9995032595823043, abs=2e-15)
+    assert Sp(np.array([0.998]))[0] == pytest.approx(-0.9999801044078943, abs=2e-15)
+
+
+def test_batched_interpolation_and_eval(bk, oracle, synth):
+    """interpolate!(itp, Y) on a batch + evaluating one data set from device-resident coefficients."""
+    import torch
+    n, k, M = 512, 6, 96
+    xdata = synth.breakpoints(6, n)
+    B = bk.BSplineBasis(k, bk.make_knots(xdata, k), augment=False)
+    itp = bk.SplineInterpolation(B, xdata)
+    Y = (2 * synth.u_numpy(7, 0, n * M) - 1).reshape(n, M)
+    Yd = torch.from_numpy(Y).cuda()
+    itp.interpolate_(Yd, algo=bk.SOLVE_TWOPASS)
+    S = itp.spline_of(5)
+    got = S(xdata, algo=bk.EVAL_DEBOOR)
+    assert np.allclose(got, Y[:, 5], rtol=0, atol=1e-12)
+    with pytest.raises(bk.DimensionMismatch):
+        itp.interpolate_(np.zeros(n + 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# K7: cyclic tridiagonal
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,nrhs", [(20, 1), (1000, 65), (10000, 300)])
+def test_cyclic_solve(bk, oracle, synth, n, nrhs):
+    br = synth.breakpoints(8, n + 1)
+    B = bk.PeriodicBSplineBasis(4, br)
+    x = bk.collocation_points(B)
+    M = bk.collocation_matrix(B, x)
+    D = (2 * synth.u_numpy(9, 0, n * nrhs) - 1).reshape(n, nrhs)
+    ref = oracle.cyclic_solve(M.a, M.b, M.c, D.copy())
+    got = D.copy()
+    M.ldiv_(got)
+    assert relerr(got, ref) < TOL64
+    if n <= 1000:
+        assert np.max(np.abs(M.dense() @ got - D)) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# errors / no silent fallback
+# ------------------------------------------------------------------------------------------------
+def test_error_mapping(bk):
+    with pytest.raises(bk.ArgumentError):
+        bk.BSplineBasis(0, np.linspace(0, 1, 5))
+    B = bk.BSplineBasis(4, np.linspace(0, 1, 10))
+    with pytest.raises(bk.DimensionMismatch):
+        bk.Spline(B, np.zeros(3))
+    with pytest.raises(bk.ArgumentError):
+        bk.collocation_matrix(B, np.linspace(0, 1, 5))
+
+
+def test_native_library_is_loaded(bk):
+    """The parity tests above must have run through the in-tree CUDA library."""
+    with open("/proc/self/maps") as f:
+        assert "libbsplinekit_b200.so" in f.read()
