@@ -47,7 +47,7 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.002)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=1.0)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Small driver for ncu captures: runs a few launches of one hot kernel (no timing claims).
+  python tools/prof.py eval   [--points N] [--algo auto|deboor]
+  python tools/prof.py solve  [--nrhs M] [--algo windowed|twopass]
+  python tools/prof.py cyclic / evalc4 / evalf32
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "bsplinekit.jl_b200"))
+
+import numpy as np
+import torch
+import bsplinekit_b200 as bk
+from bsplinekit_b200 import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("what")
+ap.add_argument("--points", type=int, default=1 << 28)
+ap.add_argument("--nrhs", type=int, default=65536)
+ap.add_argument("--algo", default="auto")
+ap.add_argument("--reps", type=int, default=3)
+args = ap.parse_args()
+
+
+def timed(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+if args.what == "eval":
+    B = bk.BSplineBasis(4, synth.breakpoints(3, 1000))
+    S = bk.Spline(B, 2 * synth.u_numpy(4, 0, len(B)) - 1)
+    xd = synth.u_torch(5, 0, args.points)
+    outs = [torch.empty_like(xd), torch.empty_like(xd)]
+    algo = {"auto": bk.EVAL_AUTO, "deboor": bk.EVAL_DEBOOR, "pp": bk.EVAL_PP}[args.algo]
+    ms = timed(lambda: S.evaluate(xd, (0, 1), algo=algo, out=outs), args.reps)
+    print("eval %s: %.3f ms  %.1f Gpt/s  %.1f GB/s" % (args.algo, ms, args.points / ms / 1e6, 24 * args.points / ms / 1e6))
+elif args.what == "evalc4":
+    br = synth.breakpoints(8, 10001)
+    B = bk.PeriodicBSplineBasis(4, br)
+    S = bk.Spline(B, 2 * synth.u_numpy(4, 0, len(B)) - 1)
+    xd = synth.u_torch(9, 0, args.points)
+    outs = [torch.empty_like(xd)]
+    algo = {"auto": bk.EVAL_AUTO, "deboor": bk.EVAL_DEBOOR, "pp": bk.EVAL_PP}[args.algo]
+    ms = timed(lambda: S.evaluate(xd, (0,), algo=algo, out=outs), args.reps)
+    print("evalc4 %s: %.3f ms  %.1f Gpt/s  %.1f GB/s" % (args.algo, ms, args.points / ms / 1e6, 16 * args.points / ms / 1e6))
+elif args.what == "evalf32":
+    br = synth.breakpoints(10, 99996).astype(np.float32)
+    B = bk.BSplineBasis(8, br)
+    S = bk.Spline(B, (2 * synth.u_numpy(4, 0, len(B)) - 1).astype(np.float32))
+    xd = synth.u_torch(11, 0, args.points, dtype=torch.float32)
+    outs = [torch.empty_like(xd)]
+    algo = {"auto": bk.EVAL_AUTO, "deboor": bk.EVAL_DEBOOR, "pp": bk.EVAL_PP}[args.algo]
+    ms = timed(lambda: S.evaluate(xd, (0,), algo=algo, out=outs), args.reps)
+    print("evalf32 %s: %.3f ms  %.1f Gpt/s  %.1f GB/s" % (args.algo, ms, args.points / ms / 1e6, 8 * args.points / ms / 1e6))
+elif args.what == "solve":
+    n, k = 4096, 6
+    xdata = synth.breakpoints(6, n)
+    Bi = bk.BSplineBasis(k, bk.make_knots(xdata, k), augment=False)
+    itp = bk.SplineInterpolation(Bi, xdata)
+    Y0 = (2 * synth.u_torch(7, 0, n * args.nrhs) - 1).reshape(n, args.nrhs)
+    Y = Y0.clone()
+    algo = {"auto": bk.SOLVE_AUTO, "windowed": bk.SOLVE_WINDOWED, "twopass": bk.SOLVE_TWOPASS}[args.algo]
+    tot = 0.0
+    for it in range(args.reps + 1):
+        Y.copy_(Y0)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); itp.C.ldiv_(Y, algo=algo); e1.record(); torch.cuda.synchronize()
+        if it > 0:
+            tot += e0.elapsed_time(e1)
+    ms = tot / args.reps
+    print("solve %s halo=%d: %.3f ms  %.2f M RHS/s  %.1f GB/s (16 B/elem)" % (
+        args.algo, itp.C.halo, ms, args.nrhs / ms / 1e3, 16 * n * args.nrhs / ms / 1e6))
+elif args.what == "cyclic":
+    n = 10000
+    br = synth.breakpoints(8, n + 1)
+    B = bk.PeriodicBSplineBasis(4, br)
+    M = bk.collocation_matrix(B, bk.collocation_points(B))
+    nrhs = 16384
+    Y0 = (2 * synth.u_torch(9, 0, n * nrhs) - 1).reshape(n, nrhs)
+    Y = Y0.clone()
+    tot = 0.0
+    for it in range(args.reps + 1):
+        Y.copy_(Y0)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); M.ldiv_(Y); e1.record(); torch.cuda.synchronize()
+        if it > 0:
+            tot += e0.elapsed_time(e1)
+    ms = tot / args.reps
+    print("cyclic: %.3f ms  %.2f M RHS/s  %.1f GB/s (16 B/elem)" % (ms, nrhs / ms / 1e3, 16 * n * nrhs / ms / 1e6))
