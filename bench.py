@@ -320,7 +320,7 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k_spline_pp<4,0,double,2>" if args.algo != "deboor" else "k_spline_deboor",
+                         "kernel": "k_spline_cell<4,0,double,3>" if args.algo != "deboor" else "k_spline_deboor<4,0,double>",
                          "algorithmic_bytes_per_launch": BYTES_PER_POINT * npts},
             "e2e": e2e, "cpu_baseline": cpu, "parity": chk, "extra": extra,
         }

@@ -1,0 +1,304 @@
+// bsk_eval_cell.cu — K3c: spline evaluation from a uniform-cell local-polynomial table staged
+// in shared memory (the headline cubic-evaluation kernel).
+//
+// The knot domain [a, b] is cut into `ncell` uniform cells (ncell ~ 4-5x the number of knot
+// intervals, sized so that the whole table fits in the 227 KB of shared memory of one SM).
+// Cell c stores the Taylor coefficients, about the cell centre, of the polynomial piece that
+// covers the cell's left edge.  The cell index is ONE multiply-add and a float->int conversion:
+// the O(1) arithmetic lookup of the uniform-grid case, extended to non-uniform knots.
+// Cells that contain a knot carry a flag (the least significant mantissa bit of the last
+// coefficient) and an entry in a side table {knot, right-hand piece}; the knot is then compared
+// exactly, so the selected knot interval is exactly the one `searchsortedlast` finds
+// (src/BSplines/evaluate_all.jl:102-119) whatever the rounding of the cell index.  Cells with
+// two or more knots (clustered knots) fall back to the per-interval table in global memory.
+//
+// Replaces the body of (S::Spline)(x) broadcast over many points
+// (src/Splines/spline.jl:144-209) and of (Derivative(n) * S).(x) (spline.jl:272-330) fused in
+// the same pass.  Result differs from the reference's de Boor triangle only by rounding
+// (few ulp; tests/test_gpu_parity.py bounds it at 1e-13 relative).
+#include <algorithm>
+
+#include "handles.cuh"
+#include "pp.cuh"
+
+using namespace bsk;
+
+namespace {
+
+constexpr int kCellThreads = 1024;
+
+template <typename T> struct Bits;
+template <> struct Bits<double> {
+    static __device__ __forceinline__ int flag(double v) { return __double2loint(v) & 1; }
+};
+template <> struct Bits<float> {
+    static __device__ __forceinline__ int flag(float v) { return __float_as_int(v) & 1; }
+};
+
+template <int K, typename T> struct CellRec {
+    static constexpr int VPA = 16 / (int)sizeof(T);
+    static constexpr int RECV = ((K + VPA - 1) / VPA) * VPA;      // values per cell record
+};
+
+template <typename T>
+struct CellView {
+    // Both tables are stored CHUNK-MAJOR: the w-th 16-byte chunk of record c sits at
+    // [(w * count + c) * VEC], so that one LDS.128 of a warp spreads over all eight 16-byte
+    // bank groups (a 32-byte record stride would only ever touch every other group).
+    const T *rec;             // (RECV/VEC) x ncell x VEC
+    const T *rc;              // (RECV/VEC) x nside x VEC   right-hand pieces of flagged cells
+    const T *xi;              // nside          the knot inside the flagged cell
+    const uint16_t *sideidx;  // ncell          0xFFFF: two or more knots -> fallback
+    int ncell, nside;
+    T x0, scale, cw;
+    T a, b;                   // domain
+};
+
+// Horner evaluation of D^d of  sum_m c_m u^m  for the derivative orders selected at compile
+// time by DMASK (bit d set -> output), or at run time (DMASK == 0).
+template <int K, typename T, int DMASK>
+__device__ __forceinline__ void horner_outputs(const T *cm, T u, const EvalOuts &outs, T *res) {
+    if (DMASK != 0) {
+        int o = 0;
+#pragma unroll
+        for (int d = 0; d < K; ++d) {
+            if (DMASK & (1 << d)) {
+                // falling factorial m!/(m-d)! as a compile-time constant
+                T acc = (T)0;
+#pragma unroll
+                for (int m = K - 1; m >= d; --m) {
+                    T ff = (T)1;
+#pragma unroll
+                    for (int q = 0; q < d; ++q) ff *= (T)(m - q);
+                    acc = fma(acc, u, d == 0 ? cm[m] : cm[m] * ff);
+                }
+                res[o++] = acc;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int o = 0; o < kMaxOut; ++o) {
+            if (o < outs.nout) {
+                const int d = outs.deriv[o];
+                T acc = (T)0;
+#pragma unroll
+                for (int m = K - 1; m >= 0; --m)
+                    if (m >= d) acc = fma(acc, u, d == 0 ? cm[m] : cm[m] * falling<T>(m, d));
+                res[o] = acc;
+            }
+        }
+    }
+}
+
+template <int DMASK> struct MaskCount {
+    static constexpr int value = (DMASK & 1) + ((DMASK >> 1) & 1) + ((DMASK >> 2) & 1) + ((DMASK >> 3) & 1) +
+                                 ((DMASK >> 4) & 1) + ((DMASK >> 5) & 1) + ((DMASK >> 6) & 1) + ((DMASK >> 7) & 1);
+};
+
+// Rare path, kept out of line: per-interval table in global memory (pp.cuh).
+template <int K, typename T>
+__device__ __noinline__ void fallback_interval(const PPView<T> pv, T xs, T *cm, T *u) {
+    pp_lookup<K, T>(pv, xs, cm, u);
+}
+
+template <int K, int KIND, typename T, int DMASK>
+__global__ void __launch_bounds__(kCellThreads, 1)
+k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *__restrict__ x,
+              int64_t nvec, EvalOuts outs) {
+    constexpr int RECV = CellRec<K, T>::RECV;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int NOUT = DMASK ? MaskCount<DMASK>::value : kMaxOut;
+    extern __shared__ __align__(16) unsigned char smem[];
+    // ---- stage the tables ------------------------------------------------------------------
+    T *s_rec = (T *)smem;
+    T *s_rc = s_rec + (size_t)cv.ncell * RECV;
+    T *s_xi = s_rc + (size_t)cv.nside * RECV;
+    uint16_t *s_idx = (uint16_t *)(s_xi + ((cv.nside + VEC - 1) / VEC) * VEC);
+    {
+        const int4 *src = (const int4 *)cv.rec;
+        int4 *dst = (int4 *)s_rec;
+        const int n16 = cv.ncell * RECV / VEC;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+        src = (const int4 *)cv.rc;
+        dst = (int4 *)s_rc;
+        const int m16 = cv.nside * RECV / VEC;
+        for (int i = threadIdx.x; i < m16; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < cv.nside; i += blockDim.x) s_xi[i] = cv.xi[i];
+        for (int i = threadIdx.x; i < cv.ncell; i += blockDim.x) s_idx[i] = cv.sideidx[i];
+    }
+    __syncthreads();
+
+    const T xa = cv.a, xb = cv.b, x0 = cv.x0, scale = cv.scale, cw = cv.cw;
+    const int ncell1 = cv.ncell - 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int4 *x4 = (const int4 *)x;
+    int4 raw_next;
+    if (v < nvec) raw_next = x4[v];
+    for (; v < nvec; v += stride) {
+        const int4 raw = raw_next;
+        if (v + stride < nvec) raw_next = x4[v + stride];     // software prefetch of the next vector
+        T xv[VEC];
+        memcpy(xv, &raw, 16);
+        T res[NOUT][VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            const T xq = xv[q];
+            const bool isnan_ = !(xq == xq);
+            bool outside;                  // plain: zone != 0; periodic: outside the main period
+            if (KIND == 1) outside = !(xq >= xa && xq < xb);
+            else outside = !(xq >= xa && xq <= xb);
+            const T xs = outside ? xa : xq;
+            int c = (int)((xs - x0) * scale);
+            c = c < 0 ? 0 : (c > ncell1 ? ncell1 : c);
+            T cm[K];
+            {
+                T buf[RECV];
+                const int4 *R4 = (const int4 *)s_rec + c;
+#pragma unroll
+                for (int w = 0; w < RECV / VEC; ++w) {
+                    int4 r = R4[w * cv.ncell];
+                    memcpy(&buf[w * VEC], &r, 16);
+                }
+#pragma unroll
+                for (int m = 0; m < K; ++m) cm[m] = buf[m];
+            }
+            T u = xs - fma((T)c + (T)0.5, cw, x0);
+            if (Bits<T>::flag(cm[K - 1])) {
+                const int j = s_idx[c];
+                if (j == 0xFFFF) {
+                    T cm2[K], u2;              // separate locals: keep cm[] itself in registers
+                    fallback_interval<K, T>(pv, xs, cm2, &u2);
+#pragma unroll
+                    for (int m = 0; m < K; ++m) cm[m] = cm2[m];
+                    u = u2;
+                } else if (!(xs < s_xi[j])) {
+                    T buf[RECV];
+                    const int4 *R4 = (const int4 *)s_rc + j;
+#pragma unroll
+                    for (int w = 0; w < RECV / VEC; ++w) {
+                        int4 r = R4[w * cv.nside];
+                        memcpy(&buf[w * VEC], &r, 16);
+                    }
+#pragma unroll
+                    for (int m = 0; m < K; ++m) cm[m] = buf[m];
+                }
+            }
+            T r1[NOUT];
+            horner_outputs<K, T, DMASK>(cm, u, outs, r1);
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) {
+                T val = r1[o];
+                if (KIND == 0 && outside) val = (T)0;       // Splines/spline.jl:164-168
+                if (isnan_) val = xq;
+                res[o][q] = val;
+            }
+            if (KIND == 1 && outside && !isnan_) {
+                // outside the main period: the reference's own arithmetic (knots shifted by
+                // multiples of L, x not wrapped; BSplines/periodic.jl:85-115)
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) {
+                    if (DMASK != 0 || o < outs.nout) {
+                        KnotView<T> kd = kv;
+                        kd.k = K - outs.deriv[o];
+                        int z;
+                        int i = find_interval<1>(kd, kd.t, xq, z);
+                        res[o][q] = deboor_generic<1, T>(kd, kd.t, (const T *)outs.dcoefs[o], ncoef, 1, kd.k, i, xq);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            if (DMASK != 0 || o < outs.nout) {
+                int4 rawo;
+                memcpy(&rawo, res[o], 16);
+                ((int4 *)outs.out[o])[v] = rawo;
+            }
+        }
+    }
+}
+
+template <int K, int KIND, typename T, int DMASK>
+bsk_status launch_cell_mask(const bsk_spline *s, const CellView<T> &cv, const PPView<T> &pv,
+                            const KnotView<T> &kv, const T *d_x, int64_t nvec, const EvalOuts &outs,
+                            cudaStream_t st) {
+    auto kern = k_spline_cell<K, KIND, T, DMASK>;
+    const size_t smem = s->cell_smem;
+    BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = sm_count(s->basis->device);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nvec + kCellThreads - 1) / kCellThreads, sms));
+    kern<<<grid, kCellThreads, smem, st>>>(cv, pv, kv, (int)s->ncoef, d_x, nvec, outs);
+    BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+template <int K, int KIND, typename T>
+bsk_status launch_cell_k(const bsk_spline *s, const KnotView<T> &kv, const T *d_x, int64_t nvec,
+                         const EvalOuts &outs, cudaStream_t st) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    CellView<T> cv;
+    cv.rec = (const T *)s->d_cell_rec;
+    cv.rc = (const T *)s->d_cell_rc;
+    cv.xi = (const T *)s->d_cell_xi;
+    cv.sideidx = s->d_cell_idx;
+    cv.ncell = s->cell_ncell;
+    cv.nside = s->cell_nside;
+    cv.x0 = (T)s->cell_x0;
+    cv.scale = (T)s->cell_scale;
+    cv.cw = (T)s->cell_cw;
+    cv.a = (T)s->cell_x0;
+    cv.b = (T)s->cell_b;
+    (void)VEC;
+    PPView<T> pv = make_ppview<T>(s);
+    // derivative mask: outputs must be listed in increasing order for the compiled masks
+    int mask = 0;
+    bool increasing = true;
+    for (int o = 0; o < outs.nout; ++o) {
+        if (o > 0 && outs.deriv[o] <= outs.deriv[o - 1]) increasing = false;
+        mask |= 1 << outs.deriv[o];
+    }
+    if (increasing && mask == 1) return launch_cell_mask<K, KIND, T, 1>(s, cv, pv, kv, d_x, nvec, outs, st);
+    if (increasing && mask == 3 && K >= 2) return launch_cell_mask<K, KIND, T, (K >= 2 ? 3 : 1)>(s, cv, pv, kv, d_x, nvec, outs, st);
+    return launch_cell_mask<K, KIND, T, 0>(s, cv, pv, kv, d_x, nvec, outs, st);
+}
+
+}  // namespace
+
+namespace bsk {
+
+#define BSK_DISPATCH_K(kval, ...)                                  \
+    switch (kval) {                                                \
+        case 1: { constexpr int K = 1; __VA_ARGS__; } break;       \
+        case 2: { constexpr int K = 2; __VA_ARGS__; } break;       \
+        case 3: { constexpr int K = 3; __VA_ARGS__; } break;       \
+        case 4: { constexpr int K = 4; __VA_ARGS__; } break;       \
+        case 5: { constexpr int K = 5; __VA_ARGS__; } break;       \
+        case 6: { constexpr int K = 6; __VA_ARGS__; } break;       \
+        case 7: { constexpr int K = 7; __VA_ARGS__; } break;       \
+        case 8: { constexpr int K = 8; __VA_ARGS__; } break;       \
+        default: break;                                            \
+    }
+
+// Launch on `nvec` 16-byte vectors of points (d_x and every output 16-byte aligned).
+template <typename T>
+bsk_status launch_cell(const bsk_spline *s, const KnotView<T> &kv, const T *d_x, int64_t nvec,
+                       const EvalOuts &outs, cudaStream_t st) {
+    bsk_status rc = BSK_ERR_UNSUPPORTED;
+    if (s->basis->kind == BSK_BASIS_PERIODIC) {
+        BSK_DISPATCH_K(s->basis->k, rc = (launch_cell_k<K, 1, T>(s, kv, d_x, nvec, outs, st)))
+    } else {
+        BSK_DISPATCH_K(s->basis->k, rc = (launch_cell_k<K, 0, T>(s, kv, d_x, nvec, outs, st)))
+    }
+    return rc;
+}
+
+#ifdef BSK_CELL_F32
+template bsk_status launch_cell<float>(const bsk_spline *, const KnotView<float> &, const float *, int64_t,
+                                       const EvalOuts &, cudaStream_t);
+#else
+template bsk_status launch_cell<double>(const bsk_spline *, const KnotView<double> &, const double *, int64_t,
+                                        const EvalOuts &, cudaStream_t);
+#endif
+
+}  // namespace bsk

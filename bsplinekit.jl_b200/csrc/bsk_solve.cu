@@ -141,7 +141,8 @@ __global__ void k_banded_lu(double *__restrict__ w, int nbandl, int nbandu, int 
 // Repack the factors row-wise for the solve kernels:
 //   lrow[r][j-1] = L(r, r-j) = w[mid + j, r - j],  urow[r][j-1] = U(r, r+j) = w[mid - j, r + j]
 __global__ void k_repack(const double *__restrict__ w, int bw, int n, double *__restrict__ lrow,
-                         double *__restrict__ urow, double *__restrict__ diag, double *__restrict__ dinv) {
+                         double *__restrict__ urow, double *__restrict__ diag, double *__restrict__ dinv,
+                         double *__restrict__ urow_s) {
     const int nroww = 2 * bw + 1, middle = bw + 1;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x + 1; r <= n; r += gridDim.x * blockDim.x) {
         for (int j = 1; j <= bw; ++j) {
@@ -151,243 +152,104 @@ __global__ void k_repack(const double *__restrict__ w, int bw, int n, double *__
         const double d = w[(middle - 1) + (size_t)(r - 1) * nroww];
         diag[r - 1] = d;
         dinv[r - 1] = 1.0 / d;
+        for (int j = 1; j <= bw; ++j)      // rows pre-scaled by 1/U(r,r) for the single-FMA backward chain
+            urow_s[(size_t)(r - 1) * bw + j - 1] = urow[(size_t)(r - 1) * bw + j - 1] * (1.0 / d);
     }
 }
 
 // ---- K6a: BANSLV order, two passes over HBM, one thread per right-hand side ----------------
 // rhs is interleaved: rhs[r * nrhs + c].  Bit-faithful to matrix.jl:218-271 (mul, then sub,
 // true division by the pivot).
-template <int BW, int UNROLL>
+template <int BW, int U>
 __global__ void __launch_bounds__(kThreads)
-k_banded_forward(const double *__restrict__ lrow, double *__restrict__ rhs, int64_t nrhs, int n) {
+k_banded_forward(const double *__restrict__ lrow, double *__restrict__ rhs, int64_t nrhs, int64_t ld, int n) {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
          c += (int64_t)gridDim.x * blockDim.x) {
         double zw[BW > 0 ? BW : 1];
 #pragma unroll
         for (int j = 0; j < BW; ++j) zw[j] = 0.0;
         double *p = rhs + c;
-        int r = 0;
-        for (; r + UNROLL <= n; r += UNROLL) {
-            double y[UNROLL];
+        double cur[U], nxt[U];
 #pragma unroll
-            for (int q = 0; q < UNROLL; ++q) y[q] = p[(int64_t)(r + q) * nrhs];
+        for (int q = 0; q < U; ++q) cur[q] = q < n ? p[(int64_t)q * ld] : 0.0;
+        for (int r = 0; r < n; r += U) {
+            // prefetch the next batch of rows while this one is being eliminated
 #pragma unroll
-            for (int q = 0; q < UNROLL; ++q) {
-                double z = y[q];
-                const double *lr = lrow + (size_t)(r + q) * BW;
+            for (int q = 0; q < U; ++q) nxt[q] = (r + U + q < n) ? p[(int64_t)(r + U + q) * ld] : 0.0;
 #pragma unroll
-                for (int j = BW; j >= 1; --j) z = xsub(z, xmul(zw[j - 1], __ldg(lr + j - 1)));
+            for (int q = 0; q < U; ++q) {
+                if (r + q < n) {
+                    double z = cur[q];
+                    const double *lr = lrow + (size_t)(r + q) * BW;
 #pragma unroll
-                for (int j = BW - 1; j >= 1; --j) zw[j] = zw[j - 1];
-                if (BW > 0) zw[0] = z;
-                y[q] = z;
+                    for (int j = BW; j >= 1; --j) z = xsub(z, xmul(zw[j - 1], __ldg(lr + j - 1)));
+#pragma unroll
+                    for (int j = BW - 1; j >= 1; --j) zw[j] = zw[j - 1];
+                    if (BW > 0) zw[0] = z;
+                    p[(int64_t)(r + q) * ld] = z;
+                }
             }
 #pragma unroll
-            for (int q = 0; q < UNROLL; ++q) p[(int64_t)(r + q) * nrhs] = y[q];
-        }
-        for (; r < n; ++r) {
-            double z = p[(int64_t)r * nrhs];
-            const double *lr = lrow + (size_t)r * BW;
-#pragma unroll
-            for (int j = BW; j >= 1; --j) z = xsub(z, xmul(zw[j - 1], __ldg(lr + j - 1)));
-#pragma unroll
-            for (int j = BW - 1; j >= 1; --j) zw[j] = zw[j - 1];
-            if (BW > 0) zw[0] = z;
-            p[(int64_t)r * nrhs] = z;
+            for (int q = 0; q < U; ++q) cur[q] = nxt[q];
         }
     }
 }
 
-template <int BW, int UNROLL>
+template <int BW, int U>
 __global__ void __launch_bounds__(kThreads)
 k_banded_backward(const double *__restrict__ urow, const double *__restrict__ diag,
-                  double *__restrict__ rhs, int64_t nrhs, int n) {
+                  double *__restrict__ rhs, int64_t nrhs, int64_t ld, int n) {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
          c += (int64_t)gridDim.x * blockDim.x) {
         double xw[BW > 0 ? BW : 1];
 #pragma unroll
         for (int j = 0; j < BW; ++j) xw[j] = 0.0;
         double *p = rhs + c;
-        int r = n - 1;
-        for (; r - UNROLL + 1 >= 0; r -= UNROLL) {
-            double y[UNROLL];
+        double cur[U], nxt[U];
 #pragma unroll
-            for (int q = 0; q < UNROLL; ++q) y[q] = p[(int64_t)(r - q) * nrhs];
+        for (int q = 0; q < U; ++q) cur[q] = (n - 1 - q >= 0) ? p[(int64_t)(n - 1 - q) * ld] : 0.0;
+        for (int r = n - 1; r >= 0; r -= U) {
 #pragma unroll
-            for (int q = 0; q < UNROLL; ++q) {
-                double acc = y[q];
-                const double *ur = urow + (size_t)(r - q) * BW;
+            for (int q = 0; q < U; ++q) nxt[q] = (r - U - q >= 0) ? p[(int64_t)(r - U - q) * ld] : 0.0;
 #pragma unroll
-                for (int j = BW; j >= 1; --j) acc = xsub(acc, xmul(xw[j - 1], __ldg(ur + j - 1)));
-                const double xr = xdiv(acc, __ldg(diag + (r - q)));
+            for (int q = 0; q < U; ++q) {
+                if (r - q >= 0) {
+                    double acc = cur[q];
+                    const double *ur = urow + (size_t)(r - q) * BW;
 #pragma unroll
-                for (int j = BW - 1; j >= 1; --j) xw[j] = xw[j - 1];
-                if (BW > 0) xw[0] = xr;
-                y[q] = xr;
-            }
-#pragma unroll
-            for (int q = 0; q < UNROLL; ++q) p[(int64_t)(r - q) * nrhs] = y[q];
-        }
-        for (; r >= 0; --r) {
-            double acc = p[(int64_t)r * nrhs];
-            const double *ur = urow + (size_t)r * BW;
-#pragma unroll
-            for (int j = BW; j >= 1; --j) acc = xsub(acc, xmul(xw[j - 1], __ldg(ur + j - 1)));
-            const double xr = xdiv(acc, __ldg(diag + r));
-#pragma unroll
-            for (int j = BW - 1; j >= 1; --j) xw[j] = xw[j - 1];
-            if (BW > 0) xw[0] = xr;
-            p[(int64_t)r * nrhs] = xr;
-        }
-    }
-}
-
-// ---- K6b: single pass, windowed backward sweep ------------------------------------------------
-// One thread per right-hand side.  The forward sweep streams down the rows exactly as BANSLV
-// does; its results are kept in a per-thread ring of (M + H) rows in shared memory.  The
-// backward recurrence is restarted every M rows from H rows further down with a zero state:
-// the influence of that (wrong) state on the rows that are kept decays like |U^{-1}| away from
-// the diagonal and was bounded below 1e-17 at factor time for this H (bsk_banded_lu), i.e. far
-// under one ulp.  HBM traffic: each element read once and written once.
-template <int BW, int TB>
-__global__ void __launch_bounds__(TB)
-k_banded_windowed(const double *__restrict__ lrow, const double *__restrict__ urow,
-                  const double *__restrict__ dinv, double *__restrict__ rhs, int64_t nrhs, int n,
-                  int M, int H) {
-    extern __shared__ __align__(16) double ring[];        // (M + H) x TB
-    const int RW = M + H;
-    const int tid = threadIdx.x;
-    const int nblk = (n + M - 1) / M;
-    const int hb = H / M;
-    const int64_t ngroups = (nrhs + TB - 1) / TB;
-    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        const int64_t c = g * TB + tid;
-        const bool active = c < nrhs;
-        double *p = rhs + (active ? c : 0);
-        double zw[BW > 0 ? BW : 1];
-#pragma unroll
-        for (int j = 0; j < BW; ++j) zw[j] = 0.0;
-        for (int b = 0; b < nblk + hb; ++b) {
-            if (b < nblk) {
-                const int r0 = b * M, r1 = min(n, r0 + M);
-                int r = r0;
-                for (; r + 8 <= r1; r += 8) {
-                    double y[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) y[q] = active ? p[(int64_t)(r + q) * nrhs] : 0.0;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        double z = y[q];
-                        const double *lr = lrow + (size_t)(r + q) * BW;
-#pragma unroll
-                        for (int j = BW; j >= 1; --j) z = fma(-zw[j - 1], __ldg(lr + j - 1), z);
-#pragma unroll
-                        for (int j = BW - 1; j >= 1; --j) zw[j] = zw[j - 1];
-                        if (BW > 0) zw[0] = z;
-                        ring[((r + q) % RW) * TB + tid] = z;
-                    }
-                }
-                for (; r < r1; ++r) {
-                    double z = active ? p[(int64_t)r * nrhs] : 0.0;
-                    const double *lr = lrow + (size_t)r * BW;
-#pragma unroll
-                    for (int j = BW; j >= 1; --j) z = fma(-zw[j - 1], __ldg(lr + j - 1), z);
-#pragma unroll
-                    for (int j = BW - 1; j >= 1; --j) zw[j] = zw[j - 1];
-                    if (BW > 0) zw[0] = z;
-                    ring[(r % RW) * TB + tid] = z;
-                }
-            }
-            const int bb = b - hb;
-            if (bb >= 0) {
-                const int keep_hi = min(n, (bb + 1) * M);          // rows [bb*M, keep_hi) are final
-                const int r_hi = min(n, (bb + 1) * M + H) - 1;
-                double xw[BW > 0 ? BW : 1];
-#pragma unroll
-                for (int j = 0; j < BW; ++j) xw[j] = 0.0;
-                for (int r = r_hi; r >= bb * M; --r) {
-                    double acc = ring[(r % RW) * TB + tid];
-                    const double *ur = urow + (size_t)r * BW;
-#pragma unroll
-                    for (int j = BW; j >= 1; --j) acc = fma(-xw[j - 1], __ldg(ur + j - 1), acc);
-                    const double xr = acc * __ldg(dinv + r);
+                    for (int j = BW; j >= 1; --j) acc = xsub(acc, xmul(xw[j - 1], __ldg(ur + j - 1)));
+                    const double xr = xdiv(acc, __ldg(diag + (r - q)));
 #pragma unroll
                     for (int j = BW - 1; j >= 1; --j) xw[j] = xw[j - 1];
                     if (BW > 0) xw[0] = xr;
-                    if (r < keep_hi && active) p[(int64_t)r * nrhs] = xr;
+                    p[(int64_t)(r - q) * ld] = xr;
                 }
             }
+#pragma unroll
+            for (int q = 0; q < U; ++q) cur[q] = nxt[q];
         }
     }
 }
 
-// ---- K7: cyclic tridiagonal, factor-once Sherman-Morrison ------------------------------------
-// x = y - alpha q,  T y = d,  alpha = (g . d) / denom  with g = T^{-T} v  (so that alpha is known
-// when the backward sweep starts and x is produced in the same pass as y).
-template <int UNROLL>
-__global__ void __launch_bounds__(kThreads)
-k_cyclic_forward(const double *__restrict__ w, const double *__restrict__ gvec, double *__restrict__ rhs,
-                 double *__restrict__ alpha_out, int64_t nrhs, int n, double inv_denom) {
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
-         c += (int64_t)gridDim.x * blockDim.x) {
-        double *p = rhs + c;
-        double prev = 0.0, dot = 0.0;
-        int r = 0;
-        for (; r + UNROLL <= n; r += UNROLL) {
-            double y[UNROLL];
-#pragma unroll
-            for (int q = 0; q < UNROLL; ++q) y[q] = p[(int64_t)(r + q) * nrhs];
-#pragma unroll
-            for (int q = 0; q < UNROLL; ++q) {
-                dot = fma(__ldg(gvec + r + q), y[q], dot);
-                const double z = xsub(y[q], xmul(__ldg(w + r + q), prev));   // d[i] - w*d[i-1] (cyclic.jl:182-186)
-                prev = z;
-                y[q] = z;
-            }
-#pragma unroll
-            for (int q = 0; q < UNROLL; ++q) p[(int64_t)(r + q) * nrhs] = y[q];
-        }
-        for (; r < n; ++r) {
-            const double y = p[(int64_t)r * nrhs];
-            dot = fma(__ldg(gvec + r), y, dot);
-            const double z = xsub(y, xmul(__ldg(w + r), prev));
-            prev = z;
-            p[(int64_t)r * nrhs] = z;
-        }
-        alpha_out[c] = dot * inv_denom;
-    }
-}
+// ---- K6b (single-pass windowed solve) lives in bsk_solve_win.cu --------------------------------
 
-template <int UNROLL>
+// ---- K7: cyclic tridiagonal, factor-once Sherman-Morrison -------------------------------------
+// A = T + u v^T with T tridiagonal (Collocation/cyclic.jl:121-146).  T is LU-factored once
+// (a bsk_banded with l = u = 1) and T y = d goes through the banded multi-RHS solve; the
+// rank-one correction x = y - q (y_1 + v_n y_n) / (1 + q_1 + v_n q_n)  (cyclic.jl:152-158) only
+// touches the rows where q = T^{-1} u is not negligible, i.e. a few rows at both ends.
 __global__ void __launch_bounds__(kThreads)
-k_cyclic_backward(const double *__restrict__ cdiag, const double *__restrict__ bp,
-                  const double *__restrict__ q, const double *__restrict__ alpha_in,
-                  double *__restrict__ rhs, int64_t nrhs, int n) {
+k_cyclic_correct(const double *__restrict__ q, double *__restrict__ rhs, int64_t nrhs, int n, int zone,
+                 double vn, double inv_denom) {
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
          c += (int64_t)gridDim.x * blockDim.x) {
         double *p = rhs + c;
-        const double alpha = alpha_in[c];
-        double next = 0.0;    // y[i+1]
-        int r = n - 1;
-        for (; r - UNROLL + 1 >= 0; r -= UNROLL) {
-            double y[UNROLL];
-#pragma unroll
-            for (int qq = 0; qq < UNROLL; ++qq) y[qq] = p[(int64_t)(r - qq) * nrhs];
-#pragma unroll
-            for (int qq = 0; qq < UNROLL; ++qq) {
-                const int i = r - qq;
-                // x[i] = (d[i] - c[i] * x[i+1]) / b[i]   (cyclic.jl:191-195); c[n-1] term is 0 via next = 0
-                const double yi = xdiv(xsub(y[qq], xmul(__ldg(cdiag + i), next)), __ldg(bp + i));
-                next = yi;
-                y[qq] = xsub(yi, xmul(alpha, __ldg(q + i)));
-            }
-#pragma unroll
-            for (int qq = 0; qq < UNROLL; ++qq) p[(int64_t)(r - qq) * nrhs] = y[qq];
-        }
-        for (; r >= 0; --r) {
-            const double yi = xdiv(xsub(p[(int64_t)r * nrhs], xmul(__ldg(cdiag + r), next)), __ldg(bp + r));
-            next = yi;
-            p[(int64_t)r * nrhs] = xsub(yi, xmul(alpha, __ldg(q + r)));
+        const double alpha = (p[0] + vn * p[(int64_t)(n - 1) * nrhs]) * inv_denom;
+        if (2 * zone >= n) {
+            for (int r = 0; r < n; ++r) p[(int64_t)r * nrhs] -= alpha * __ldg(q + r);
+        } else {
+            for (int r = 0; r < zone; ++r) p[(int64_t)r * nrhs] -= alpha * __ldg(q + r);
+            for (int r = n - zone; r < n; ++r) p[(int64_t)r * nrhs] -= alpha * __ldg(q + r);
         }
     }
 }
@@ -435,35 +297,30 @@ int decay_halo(const std::vector<double> &urow, const std::vector<double> &dinv,
 template <int BW>
 bsk_status solve_dispatch(const bsk_banded *h, double *d_rhs, int64_t nrhs, int algo, cudaStream_t st) {
     const int n = (int)h->n;
-    bool windowed = (algo == BSK_SOLVE_WINDOWED) || (algo == BSK_SOLVE_AUTO && h->halo > 0 && nrhs >= 1024);
+    bool windowed = (algo == BSK_SOLVE_WINDOWED) || (algo == BSK_SOLVE_AUTO && h->halo > 0 && nrhs >= 2048);
     if (algo == BSK_SOLVE_WINDOWED && h->halo == 0) {
         set_error("windowed solve unavailable: the decay bound of U^{-1} was not met for this matrix");
         return BSK_ERR_UNSUPPORTED;
     }
-    if (windowed) {
-        constexpr int TB = 32;
-        const int H = h->halo;
-        int M = (H % 64 == 0) ? 64 : 32;
-        if (const char *env = getenv("BSK_WINDOW_M")) {      // tuning knob (must divide H)
-            int m = atoi(env);
-            if (m >= 8 && m % 8 == 0 && H % m == 0) M = m;
-        }
-        size_t smem = (size_t)(M + H) * TB * sizeof(double);
-        auto kern = k_banded_windowed<BW, TB>;
-        if (smem > 48 * 1024)
-            BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (224 * 1024) / smem));
-        int64_t ngroups = (nrhs + TB - 1) / TB;
-        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ngroups, (int64_t)sm_count(h->device) * per_sm));
-        kern<<<grid, TB, smem, st>>>(h->d_lrow, h->d_urow, h->d_dinv, d_rhs, nrhs, n, M, H);
-        BSK_CUDA(cudaGetLastError());
-        return BSK_OK;
+    int64_t done = 0;                                         // columns handled by the windowed kernel
+    if (windowed && (((uintptr_t)d_rhs) & 15) == 0 && nrhs % 2 == 0 && nrhs >= 32) {
+        const int64_t ngroups = nrhs / 32;
+        bsk_status rc = windowed_solve(h, d_rhs, ngroups, nrhs, st);
+        if (rc != BSK_OK) return rc;
+        done = ngroups * 32;
+    } else if (algo == BSK_SOLVE_WINDOWED) {
+        set_error("windowed solve needs a 16-byte aligned RHS block with an even number (>= 32) of columns");
+        return BSK_ERR_UNSUPPORTED;
     }
-    int grid = grid_cols(nrhs, h->device, 8);
-    k_banded_forward<BW, 8><<<grid, kThreads, 0, st>>>(h->d_lrow, d_rhs, nrhs, n);
-    BSK_CUDA(cudaGetLastError());
-    k_banded_backward<BW, 8><<<grid, kThreads, 0, st>>>(h->d_urow, h->d_diag, d_rhs, nrhs, n);
-    BSK_CUDA(cudaGetLastError());
+    const int64_t rest = nrhs - done;                         // remaining columns: BANSLV-order two-pass
+    if (rest > 0) {
+        const int bs = rest >= 148 * 2 * 256 ? 128 : 64;
+        int grid = (int)std::max<int64_t>(1, (rest + bs - 1) / bs);
+        k_banded_forward<BW, 16><<<grid, bs, 0, st>>>(h->d_lrow, d_rhs + done, rest, nrhs, n);
+        BSK_CUDA(cudaGetLastError());
+        k_banded_backward<BW, 16><<<grid, bs, 0, st>>>(h->d_urow, h->d_diag, d_rhs + done, rest, nrhs, n);
+        BSK_CUDA(cudaGetLastError());
+    }
     return BSK_OK;
 }
 
@@ -546,11 +403,13 @@ static bsk_status banded_alloc(int64_t n, int32_t l, int32_t u, int32_t device, 
     BSK_CUDA(cudaSetDevice(device));
     bsk_banded *h = new bsk_banded();
     h->device = device; h->n = n; h->l = l; h->u = u; h->factored = false; h->halo = 0;
-    h->d_w = h->d_lrow = h->d_urow = h->d_dinv = h->d_diag = nullptr;
+    h->d_w = h->d_lrow = h->d_urow = h->d_dinv = h->d_diag = h->d_urow_s = h->d_lrec = h->d_urec = nullptr;
+    h->n_pad = 0;
     size_t nw = (size_t)(l + u + 1) * n, nb = (size_t)std::max(1, l) * n;
     cudaError_t e = cudaMalloc((void **)&h->d_w, 8 * nw);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_lrow, 8 * nb);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_urow, 8 * nb);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_urow_s, 8 * nb);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_dinv, 8 * n);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_diag, 8 * n);
     if (e != cudaSuccess) {
@@ -599,13 +458,17 @@ bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot) {
     }
     const int n = (int)h->n, bw = h->l;
     int grid = std::max(1, std::min((n + kThreads - 1) / kThreads, 148 * 4));
-    k_repack<<<grid, kThreads>>>(h->d_w, bw, n, h->d_lrow, h->d_urow, h->d_diag, h->d_dinv);
+    k_repack<<<grid, kThreads>>>(h->d_w, bw, n, h->d_lrow, h->d_urow, h->d_diag, h->d_dinv, h->d_urow_s);
     BSK_CUDA(cudaGetLastError());
     // decay bound for the windowed solve
     std::vector<double> urow((size_t)std::max(1, bw) * n), dinv(n);
     BSK_CUDA(cudaMemcpy(urow.data(), h->d_urow, 8 * (size_t)std::max(1, bw) * n, cudaMemcpyDeviceToHost));
     BSK_CUDA(cudaMemcpy(dinv.data(), h->d_dinv, 8 * (size_t)n, cudaMemcpyDeviceToHost));
     h->halo = decay_halo(urow, dinv, n, bw, 1e-17, 32, 448);
+    if (h->halo > 0) {
+        bsk_status rc = windowed_prepare(h);
+        if (rc != BSK_OK) return rc;
+    }
     h->factored = true;
     return BSK_OK;
 }
@@ -650,6 +513,9 @@ bsk_status bsk_banded_destroy(bsk_banded *h) {
     if (h->d_w) cudaFree(h->d_w);
     if (h->d_lrow) cudaFree(h->d_lrow);
     if (h->d_urow) cudaFree(h->d_urow);
+    if (h->d_urow_s) cudaFree(h->d_urow_s);
+    if (h->d_lrec) cudaFree(h->d_lrec);
+    if (h->d_urec) cudaFree(h->d_urec);
     if (h->d_dinv) cudaFree(h->d_dinv);
     if (h->d_diag) cudaFree(h->d_diag);
     delete h;
@@ -671,46 +537,36 @@ static bsk_status cyclic_build(const std::vector<double> &a, const std::vector<d
     const double vn = a1 / gamma;
     b[0] -= gamma;
     b[n - 1] -= ac / gamma;
-    std::vector<double> w(n, 0.0), q(n, 0.0), g(n, 0.0);
-    q[0] = gamma; q[n - 1] = cn;
-    // Thomas elimination of the matrix and of q (solve_thomas!, cyclic.jl:168-197)
-    for (int64_t i = 1; i < n; ++i) {
-        w[i] = a[i] / b[i - 1];
-        b[i] = b[i] - w[i] * c[i - 1];
-        q[i] = q[i] - w[i] * q[i - 1];
+    // band storage of the (non-cyclic) tridiagonal T: data[u + 1 + i - j, j], l = u = 1
+    std::vector<double> band((size_t)3 * n, 0.0);
+    for (int64_t j = 0; j < n; ++j) {
+        if (j >= 1) band[0 + 3 * j] = c[j - 1];      // T(j-1, j)
+        band[1 + 3 * j] = b[j];                      // T(j, j)
+        if (j + 1 < n) band[2 + 3 * j] = a[j + 1];   // T(j+1, j)
     }
+    bsk_banded *tri = nullptr;
+    bsk_status rc = bsk_banded_create_host(band.data(), n, 1, 1, device, &tri);
+    if (rc != BSK_OK) return rc;
+    int64_t info = 0;
+    rc = bsk_banded_lu(tri, &info);
+    if (rc != BSK_OK) { bsk_banded_destroy(tri); return rc; }
+    // q = T^{-1} u, u = gamma e_1 + c_n e_n (cyclic.jl:131-135), through the same factorisation
+    std::vector<double> q(n, 0.0);
+    q[0] = gamma;
+    q[n - 1] = cn;
+    rc = bsk_banded_solve_host(tri, q.data(), 1, BSK_SOLVE_TWOPASS);
+    if (rc != BSK_OK) { bsk_banded_destroy(tri); return rc; }
+    const double denom = 1.0 + (q[0] + vn * q[n - 1]);
+    double qmax = 0.0;
+    for (int64_t i = 0; i < n; ++i) qmax = std::max(qmax, std::fabs(q[i]));
+    int zone = 0;          // rows from each end where q is not negligible
     for (int64_t i = 0; i < n; ++i)
-        BSK_REQUIRE(b[i] != 0.0 && b[i] == b[i], BSK_ERR_ZERO_PIVOT, "zero pivot in cyclic elimination at row %lld",
-                    (long long)(i + 1));
-    q[n - 1] = q[n - 1] / b[n - 1];
-    for (int64_t i = n - 2; i >= 0; --i) q[i] = (q[i] - c[i] * q[i + 1]) / b[i];
-    const double vq = 1.0 * q[0] + vn * q[n - 1];
-    const double denom = 1.0 + vq;
-    // g = T^{-T} v, v = (1, 0, ..., 0, vn):  T = L U (unit-lower L with multipliers w, upper U with
-    // diagonal b' and super-diagonal c), so  U^T z = v (forward), then L^T g = z (backward).
-    std::vector<double> z(n, 0.0);
-    z[0] = 1.0 / b[0];
-    for (int64_t i = 1; i < n; ++i) {
-        double vi = (i == n - 1) ? vn : 0.0;
-        z[i] = (vi - c[i - 1] * z[i - 1]) / b[i];
-    }
-    g[n - 1] = z[n - 1];
-    for (int64_t i = n - 2; i >= 0; --i) g[i] = z[i] - w[i + 1] * g[i + 1];
-
+        if (std::fabs(q[i]) > 1e-19 * qmax) zone = std::max<int>(zone, (int)std::min<int64_t>(i + 1, n - i));
     BSK_CUDA(cudaSetDevice(device));
     bsk_cyclic *h = new bsk_cyclic();
-    h->device = device; h->n = n; h->vn = vn; h->denom = denom;
-    h->d_w = h->d_bp = h->d_c = h->d_q = h->d_g = nullptr;
-    auto up = [&](double **dst, const std::vector<double> &src) {
-        cudaError_t e = cudaMalloc((void **)dst, 8 * (size_t)n);
-        if (e == cudaSuccess) e = cudaMemcpy(*dst, src.data(), 8 * (size_t)n, cudaMemcpyHostToDevice);
-        return e;
-    };
-    cudaError_t e = up(&h->d_w, w);
-    if (e == cudaSuccess) e = up(&h->d_bp, b);
-    if (e == cudaSuccess) e = up(&h->d_c, c);
-    if (e == cudaSuccess) e = up(&h->d_q, q);
-    if (e == cudaSuccess) e = up(&h->d_g, g);
+    h->device = device; h->n = n; h->vn = vn; h->denom = denom; h->tri = tri; h->zone = zone; h->d_q = nullptr;
+    cudaError_t e = cudaMalloc((void **)&h->d_q, 8 * (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_q, q.data(), 8 * (size_t)n, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         set_error("cyclic upload failed: %s", cudaGetErrorString(e));
         bsk_cyclic_destroy(h);
@@ -747,28 +603,20 @@ bsk_status bsk_cyclic_solve(const bsk_cyclic *h, double *d_rhs, int64_t nrhs, vo
     if (nrhs == 0) return BSK_OK;
     BSK_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    double *d_alpha = nullptr;
-    BSK_CUDA(cudaMallocAsync((void **)&d_alpha, 8 * (size_t)nrhs, st));
-    int grid = grid_cols(nrhs, h->device, 8);
-    k_cyclic_forward<8><<<grid, kThreads, 0, st>>>(h->d_w, h->d_g, d_rhs, d_alpha, nrhs, (int)h->n, 1.0 / h->denom);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) {
-        k_cyclic_backward<8><<<grid, kThreads, 0, st>>>(h->d_c, h->d_bp, h->d_q, d_alpha, d_rhs, nrhs, (int)h->n);
-        e = cudaGetLastError();
-    }
-    cudaFreeAsync(d_alpha, st);
-    if (e != cudaSuccess) { set_error("cyclic solve failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
+    bsk_status rc = bsk_banded_solve(h->tri, d_rhs, nrhs, BSK_SOLVE_AUTO, stream);   // T y = d
+    if (rc != BSK_OK) return rc;
+    const int bs = nrhs >= 148 * 2 * 256 ? 256 : 64;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nrhs + bs - 1) / bs, 148 * 16));
+    k_cyclic_correct<<<grid, bs, 0, st>>>(h->d_q, d_rhs, nrhs, (int)h->n, h->zone, h->vn, 1.0 / h->denom);
+    BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }
 
 bsk_status bsk_cyclic_destroy(bsk_cyclic *h) {
     if (!h) return BSK_OK;
     cudaSetDevice(h->device);
-    if (h->d_w) cudaFree(h->d_w);
-    if (h->d_bp) cudaFree(h->d_bp);
-    if (h->d_c) cudaFree(h->d_c);
     if (h->d_q) cudaFree(h->d_q);
-    if (h->d_g) cudaFree(h->d_g);
+    if (h->tri) bsk_banded_destroy(h->tri);
     delete h;
     return BSK_OK;
 }

@@ -1,0 +1,360 @@
+// bsk_solve_win.cu — K6b: single-pass multi-RHS banded solve (windowed backward sweep).
+//
+// Replaces ldiv!(x, F::CollocationLU, y) (src/Collocation/matrix.jl:218-271) for batches of
+// right-hand sides stored interleaved (RHS index fastest == Vector{SVector{M,Float64}},
+// test/interpolation.jl:57).
+//
+// One warp per CTA, one right-hand side (column) per lane.  Three TMA streams (1-D bulk async
+// copies, cp.async.bulk, completion on mbarriers) feed the warp from HBM / L2 without touching
+// registers or L1:
+//   A  the column group's rows, 8 rows (8 x 256 B) per chunk, PG chunks ahead, landing in the
+//      warp's ring of (M + H + 8 PG) rows in shared memory;
+//   B  the per-row records {L(r,r-bw..r-1), 1/U(r,r)} of the same 8 rows (same mbarrier as A);
+//   C  the per-row records {U(r,r+bw..r+1)/U(r,r)} of the same rows, kept beside the ring for
+//      as long as the rows are (the backward sweeps read them 1 + H/M times).
+// The forward sweep (BANSLV's recurrence, FMA-contracted) runs in place in the ring; the
+// backward recurrence is restarted every M rows from H rows further down with a zero state.
+// The influence of that wrong start state on the rows that are kept decays like |U^{-1}| away
+// from the diagonal and was bounded below 1e-17 (relative to the solution's magnitude) at
+// factor time for this H (bsk_banded_lu), i.e. far below one ulp.
+// HBM traffic: every element is read once and written once (16 B per element); the two-pass
+// BANSLV-order kernels (bsk_solve.cu) move 32 B per element.
+//
+// Everything in the inner loops is organised in chunks of 8 rows that never straddle a ring
+// wrap, so ring accesses use immediate offsets, and the records are read from shared memory
+// with conflict-free broadcast loads.
+#include <algorithm>
+#include <cstdlib>
+
+#include "handles.cuh"
+
+using namespace bsk;
+
+namespace {
+
+constexpr int G = 8;   // rows per chunk
+
+template <int BW> struct RecW {
+    static constexpr int LW = ((BW + 1 + 1) / 2) * 2;           // {l_BW .. l_1, dinv} padded to even
+    static constexpr int UW = BW == 0 ? 2 : ((BW + 1) / 2) * 2;  // {u'_BW .. u'_1} padded to even
+};
+
+// Column-oriented ("right-looking", exactly BANSLV's own loop order, matrix.jl:246-266) records:
+//   lrec[i] = { L(i+1,i), ..., L(i+BW,i), 1/U(i,i), pad }      multipliers applied once z_i is final
+//   urec[r] = { U(r-1,r)/U(r-1,r-1), ..., U(r-BW,r)/U(r-BW,r-BW), pad }   (targets pre-scaled)
+// rows r > n are identity rows (zero multipliers, unit pivot).
+template <int BW>
+__global__ void k_win_repack(const double *__restrict__ w, int n, int n_pad, double *__restrict__ lrec,
+                             double *__restrict__ urec) {
+    constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
+    const int nroww = 2 * BW + 1, middle = BW + 1;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x + 1; r <= n_pad; r += gridDim.x * blockDim.x) {
+        double *lr = lrec + (size_t)(r - 1) * LW;
+        double *ur = urec + (size_t)(r - 1) * UW;
+        for (int j = 0; j < LW; ++j) lr[j] = 0.0;
+        for (int j = 0; j < UW; ++j) ur[j] = 0.0;
+        if (r > n) { lr[BW] = 1.0; continue; }
+        lr[BW] = 1.0 / w[(middle - 1) + (size_t)(r - 1) * nroww];
+        for (int j = 1; j <= BW; ++j) {
+            if (r + j <= n) lr[j - 1] = w[(middle + j - 1) + (size_t)(r - 1) * nroww];
+            if (r - j >= 1)
+                ur[j - 1] = w[(middle - j - 1) + (size_t)(r - 1) * nroww] / w[(middle - 1) + (size_t)(r - j - 1) * nroww];
+        }
+    }
+}
+
+// ---- TMA (bulk async copy) + mbarrier plumbing ----------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void *gsrc, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int W>
+__device__ __forceinline__ void load_rec_s(const double *p, double *out) {      // shared memory, 16-B aligned
+#pragma unroll
+    for (int i = 0; i < W / 2; ++i) {
+        const double2 v = *((const double2 *)p + i);
+        out[2 * i] = v.x;
+        out[2 * i + 1] = v.y;
+    }
+}
+
+// `ld` = elements between consecutive rows of rhs.
+template <int BW, int PG>
+__global__ void __launch_bounds__(32)
+k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ urec,
+                  double *__restrict__ rhs, int64_t ngroups, int64_t ld, int n, int n_pad, int M, int H) {
+    constexpr int TB = 32;
+    constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
+    extern __shared__ __align__(128) double smem_d[];
+    const int RW = M + H + PG * G;
+    // shared-memory layout (doubles): ring[RW][32] | cur[RW][UW] | cfw[PG][8*LW] | mbar[PG]
+    // cur = backward records of the rows currently in the ring (same slot index as the data)
+    double *const ring = smem_d;
+    double *const cur = ring + (size_t)RW * TB;
+    double *const cfw = cur + (size_t)RW * UW;
+    const int lane = threadIdx.x;
+    const int nblk = (n_pad + M - 1) / M;
+    const int hb = H / M;
+    double *const my = ring + lane;                          // my[slot * TB]
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const unsigned cur_s = (unsigned)__cvta_generic_to_shared(cur);
+    const unsigned cfw_s = (unsigned)__cvta_generic_to_shared(cfw);
+    const unsigned barA_s = cfw_s + (unsigned)(PG * G * LW * 8);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < PG; ++i) mbar_init(barA_s + 8 * i, 1);
+        fence_proxy_async();
+    }
+    __syncwarp();
+    unsigned issA = 0, conA = 0;                             // chunk counters (mbarrier = counter % PG)
+
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        double *const p = rhs + g * TB + lane;
+        const double *const grow = rhs + g * TB;             // row 0 of this column group (256 B rows)
+    
+        // ---- producer: 8 data rows + their forward and backward records, one mbarrier phase --------
+        int pf_row = 0, pf_slot = 0;
+        auto issue_fwd = [&]() {
+            const unsigned i = issA % PG;
+            const unsigned bar = barA_s + 8 * i;
+            const int nvalid = min(G, n - pf_row);           // rows that exist in HBM
+            if (nvalid < G && pf_row < n_pad) {              // identity padding rows
+#pragma unroll
+                for (int q = 0; q < G; ++q)
+                    if (q >= nvalid) my[(pf_slot + q) * TB] = 0.0;
+            }
+            __syncwarp();                                    // all lanes are done with these slots
+            if (lane == 0) {
+                if (pf_row < n_pad) {
+                    fence_proxy_async();                     // generic accesses before async writes
+                    mbar_expect_tx(bar, (unsigned)(nvalid * TB * 8 + G * (LW + UW) * 8));
+                    bulk_g2s(cfw_s + i * (G * LW * 8), lrec + (size_t)pf_row * LW, G * LW * 8, bar);
+                    bulk_g2s(cur_s + (unsigned)(pf_slot * UW * 8), urec + (size_t)pf_row * UW, G * UW * 8, bar);
+                    const double *src = grow + (int64_t)pf_row * ld;
+                    const unsigned dst = ring_s + (unsigned)(pf_slot * TB * 8);
+                    if (nvalid == G) {
+#pragma unroll
+                        for (int q = 0; q < G; ++q) bulk_g2s(dst + q * TB * 8, src + (int64_t)q * ld, TB * 8, bar);
+                    } else {
+                        for (int q = 0; q < nvalid; ++q) bulk_g2s(dst + q * TB * 8, src + (int64_t)q * ld, TB * 8, bar);
+                    }
+                } else {
+                    mbar_arrive(bar);
+                }
+            }
+            ++issA;
+            pf_row += G;
+            pf_slot += G;
+            if (pf_slot == RW) pf_slot = 0;
+        };
+#pragma unroll 1
+        for (int gg = 0; gg < PG; ++gg) issue_fwd();
+
+        int f_slot = 0;                                      // ring slot of the next forward row
+        double tf[BW > 0 ? BW : 1];                          // rows r0 .. r0+BW-1, partially eliminated
+        {
+            mbar_wait(barA_s + 8 * (conA % PG), (conA / PG) & 1);      // chunk 0
+            ++conA;
+#pragma unroll
+            for (int j = 0; j < BW; ++j) tf[j] = my[j * TB];
+        }
+        for (int b = 0; b < nblk + hb; ++b) {
+            // ---- forward sweep over block b (right-looking: z_i final -> update rows i+1..i+BW) ----
+            if (b < nblk) {
+                const int r1 = min(n_pad, (b + 1) * M);
+#pragma unroll 1
+                for (int r0 = b * M; r0 < r1; r0 += G) {
+                    const unsigned i = (conA - 1) % PG;                    // chunk of rows r0 .. r0+7
+                    mbar_wait(barA_s + 8 * (conA % PG), (conA / PG) & 1);  // next chunk (look-ahead rows)
+                    ++conA;
+                    double *const rs = my + f_slot * TB;
+                    const double *const lr = cfw + i * (G * LW);
+                    int n_slot = f_slot + G;
+                    if (n_slot == RW) n_slot = 0;
+                    double t[G + BW];
+#pragma unroll
+                    for (int j = 0; j < BW; ++j) t[j] = tf[j];
+#pragma unroll
+                    for (int q = BW; q < G; ++q) t[q] = rs[q * TB];
+                    if (r0 + G < n_pad) {
+#pragma unroll
+                        for (int j = 0; j < BW; ++j) t[G + j] = my[(n_slot + j) * TB];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BW; ++j) t[G + j] = 0.0;
+                    }
+                    double rec[G][LW];
+#pragma unroll
+                    for (int q = 0; q < G; ++q) load_rec_s<LW>(lr + q * LW, rec[q]);
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        const double z = t[q];
+#pragma unroll
+                        for (int j = 1; j <= BW; ++j) t[q + j] = fma(-z, rec[q][j - 1], t[q + j]);
+                        rs[q * TB] = z * rec[q][BW];         // stored pre-scaled by 1/U(r,r)
+                    }
+#pragma unroll
+                    for (int j = 0; j < BW; ++j) tf[j] = t[G + j];
+                    f_slot = n_slot;
+                    issue_fwd();
+                }
+            }
+            // ---- backward sweep that finalises block bb = b - hb ------------------------------
+            const int bb = b - hb;
+            if (bb >= 0) {
+                const int keep_lo = bb * M;
+                const int keep_hi = min(n_pad, (bb + 1) * M);
+                const int r_top = min(n_pad, (bb + 1) * M + H);   // exclusive, multiple of 8
+                double tb[BW > 0 ? BW : 1];                  // rows rc-1 .. rc-BW, partially eliminated
+                int slot = r_top % RW;                       // once per block
+                slot = (slot == 0 ? RW : slot) - G;
+                double *dst = p + (int64_t)(keep_hi - 1) * ld;
+#pragma unroll 1
+                for (int rc = r_top - G; rc >= keep_lo; rc -= G) {
+                    const double *const rs = my + slot * TB;
+                    const double *const ur = cur + slot * UW;
+                    const int p_slot = (slot == 0 ? RW : slot) - G;
+                    double t[G];
+                    double la[BW > 0 ? BW : 1];
+                    if (rc == r_top - G) {                   // start of the sweep: zero state above
+#pragma unroll
+                        for (int q = 0; q < G; ++q) t[q] = rs[q * TB];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BW; ++j) t[G - 1 - j] = tb[j];
+#pragma unroll
+                        for (int q = 0; q < G - BW; ++q) t[q] = rs[q * TB];
+                    }
+                    if (rc > keep_lo) {
+#pragma unroll
+                        for (int j = 0; j < BW; ++j) la[j] = my[(p_slot + G - 1 - j) * TB];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BW; ++j) la[j] = 0.0;
+                    }
+                    double rec[G][UW];
+#pragma unroll
+                    for (int q = 0; q < G; ++q) load_rec_s<UW>(ur + q * UW, rec[q]);
+#pragma unroll
+                    for (int q = G - 1; q >= 0; --q) {
+                        const double xq = t[q];
+#pragma unroll
+                        for (int j = 1; j <= BW; ++j) {
+                            if (q - j >= 0) t[q - j] = fma(-xq, rec[q][j - 1], t[q - j]);
+                            else la[j - q - 1] = fma(-xq, rec[q][j - 1], la[j - q - 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < BW; ++j) tb[j] = la[j];
+                    if (rc < keep_hi) {                      // kept rows (warp-uniform branch): store
+#pragma unroll
+                        for (int q = G - 1; q >= 0; --q) {
+                            if (rc + q < n) *dst = t[q];
+                            dst -= ld;
+                        }
+                    }
+                    slot = p_slot;
+                }
+            }
+        }
+        // drain the chunks issued past the end of this column group
+        while (conA < issA) { mbar_wait(barA_s + 8 * (conA % PG), (conA / PG) & 1); ++conA; }
+    }
+}
+
+template <int BW>
+bsk_status prepare_t(bsk_banded *h) {
+    constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
+    const int n = (int)h->n;
+    const int n_pad = ((n + G - 1) / G) * G;
+    h->n_pad = n_pad;
+    BSK_CUDA(cudaMalloc((void **)&h->d_lrec, sizeof(double) * (size_t)n_pad * LW));
+    BSK_CUDA(cudaMalloc((void **)&h->d_urec, sizeof(double) * (size_t)n_pad * UW));
+    int grid = std::max(1, std::min((n_pad + 255) / 256, 148 * 4));
+    k_win_repack<BW><<<grid, 256>>>(h->d_w, n, n_pad, h->d_lrec, h->d_urec);
+    BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+template <int BW>
+bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st) {
+    constexpr int PG = 4;                                     // 4 chunks x 8 rows in flight
+    constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
+    const int H = h->halo;
+    int M = (H % 48 == 0) ? 48 : H;                           // measured best on B200 for H = 96
+    int per_sm_cap = 16;
+    if (const char *env = getenv("BSK_WINDOW_M")) {           // tuning knobs
+        int m = atoi(env);
+        if (m >= 8 && m % 8 == 0 && H % m == 0) M = m;
+    }
+    if (const char *env = getenv("BSK_WINDOW_CTAS")) per_sm_cap = std::max(1, atoi(env));
+    const size_t smem = ((size_t)(M + H + PG * G) * (32 + UW) + (size_t)PG * G * LW + PG) * sizeof(double);
+    auto kern = k_banded_windowed<BW, PG>;
+    if (smem > 48 * 1024)
+        BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(per_sm_cap, (226 * 1024) / (smem + 1024)));
+    const int64_t slots = (int64_t)sm_count(h->device) * per_sm;
+    const int64_t rounds = (ngroups + slots - 1) / slots;
+    const int grid = (int)std::max<int64_t>(1, (ngroups + rounds - 1) / rounds);   // balanced rounds
+    kern<<<grid, 32, smem, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H);
+    BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+}  // namespace
+
+namespace bsk {
+
+bsk_status windowed_prepare(bsk_banded *h) {
+    switch (h->l) {
+        case 0: return prepare_t<0>(h);
+        case 1: return prepare_t<1>(h);
+        case 2: return prepare_t<2>(h);
+        case 3: return prepare_t<3>(h);
+        case 4: return prepare_t<4>(h);
+        case 5: return prepare_t<5>(h);
+        case 6: return prepare_t<6>(h);
+    }
+    return BSK_ERR_UNSUPPORTED;
+}
+
+// Solves the first 32 * ngroups columns of an interleaved RHS block whose rows are `ld`
+// elements apart.  Requires 16-byte aligned rows (d_rhs 16-byte aligned, ld even).
+bsk_status windowed_solve(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st) {
+    switch (h->l) {
+        case 0: return solve_t<0>(h, d_rhs, ngroups, ld, st);
+        case 1: return solve_t<1>(h, d_rhs, ngroups, ld, st);
+        case 2: return solve_t<2>(h, d_rhs, ngroups, ld, st);
+        case 3: return solve_t<3>(h, d_rhs, ngroups, ld, st);
+        case 4: return solve_t<4>(h, d_rhs, ngroups, ld, st);
+        case 5: return solve_t<5>(h, d_rhs, ngroups, ld, st);
+        case 6: return solve_t<6>(h, d_rhs, ngroups, ld, st);
+    }
+    return BSK_ERR_UNSUPPORTED;
+}
+
+}  // namespace bsk

@@ -85,6 +85,13 @@ struct bsk_spline {
     double pp_scale;
     int pp_rec;
     bool pp_valid;
+    // uniform-cell table (bsk_eval_cell.cu)
+    void *d_cell_rec, *d_cell_rc, *d_cell_xi;
+    uint16_t *d_cell_idx;
+    int cell_ncell, cell_nside;
+    double cell_x0, cell_b, cell_scale, cell_cw;
+    size_t cell_smem;
+    bool cell_valid;
     std::vector<bsk_spline *> derivs;   // cached Derivative(n) * S, index n (0 unused)
 };
 
@@ -97,20 +104,26 @@ struct bsk_banded {
     // solve-ready repack (built by bsk_banded_lu): row-major per-row multipliers
     double *d_lrow;       // n x l : lrow[i][j-1] = L(i, i-j)      (multiplier of x[i-j] in row i)
     double *d_urow;       // n x u : urow[i][j-1] = U(i, i+j)
+    double *d_urow_s;     // n x u : urow scaled by 1/U(i,i) (windowed solve)
     double *d_dinv;       // n     : 1 / U(i,i)
     double *d_diag;       // n     : U(i,i)
+    double *d_lrec, *d_urec;   // padded per-row records of the windowed solve (bsk_solve_win.cu)
+    int n_pad;
     int halo;             // decay halo (rows) validated for the windowed solve, 0 = not usable
 };
+
+namespace bsk {
+bsk_status windowed_prepare(bsk_banded *h);
+bsk_status windowed_solve(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st);
+}  // namespace bsk
 
 struct bsk_cyclic {
     int device;
     int64_t n;
     // factor-once form of the Sherman-Morrison solve (Collocation/cyclic.jl:112-161)
-    double *d_w;      // n: forward multipliers a[i]/b'[i-1]
-    double *d_bp;     // n: b'[i] after elimination
-    double *d_c;      // n: super-diagonal
+    bsk_banded *tri;  // LU of the tridiagonal part T (l = u = 1)
     double *d_q;      // n: T^{-1} u
-    double *d_g;      // n: T^{-T} v
+    int zone;         // rows from each end where q is not negligible
     double vn;        // a1 / gamma
     double denom;     // 1 + v.q
 };

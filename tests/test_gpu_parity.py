@@ -269,9 +269,13 @@ def test_spline_eval_device_vectors(bk, oracle, synth):
     refd = oracle.spline_eval(0, kd, td, cd, xh)
     assert relerr(v.cpu().numpy(), ref) < TOL64
     assert relerr(dv.cpu().numpy(), refd) < TOL64
-    # unaligned device views take the scalar path
-    v2 = S.evaluate(xd[1:], (0,))[0]
-    assert np.array_equal(v2.cpu().numpy(), v.cpu().numpy()[1:])
+    # unaligned device views: scalar head / tail around the vectorised body
+    v2, dv2 = S.evaluate(xd[1:], (0, 1))
+    assert relerr(v2.cpu().numpy(), ref[1:]) < TOL64
+    assert relerr(dv2.cpu().numpy(), refd[1:]) < TOL64
+    o1 = torch.empty(n + 1, dtype=torch.float64, device="cuda")[1:]     # output phase != input phase
+    S.evaluate(xd, (0,), out=[o1])
+    assert relerr(o1.cpu().numpy(), ref) < TOL64
     # faithful path on the same points is bit-exact
     vb = S.evaluate(xd, (0,), algo=bk.EVAL_DEBOOR)[0]
     assert np.array_equal(vb.cpu().numpy(), ref)
