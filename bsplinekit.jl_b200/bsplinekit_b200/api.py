@@ -545,18 +545,13 @@ class Spline:
 
 # ---- collocation ----------------------------------------------------------------------------------
 
-def collocation_points(B):
-    """collocation_points(B) (Collocation/points.jl:46-126,164-225): Greville sites with the
-    two-step Kahan sliding sum; periodic even order -> the knots themselves."""
-    if isinstance(B, PeriodicBSplineBasis):
-        if B.k % 2 == 0:
-            return B.t[:-1].copy()                                      # SameAsKnots (points.jl:176)
-        raise _lib.UnsupportedError("AvgKnots for odd-order periodic bases is not implemented")
-    k, t = B.k, B.t
+def greville_points(k, t, N, cl=0, force_ends=True):
+    """Greville sites (t[i+1] + ... + t[i+k-1]) / (k - 1) with the reference's two-step Kahan
+    sliding sum (Collocation/points.jl:56-126).  Pure host arithmetic in the knot dtype.
+    cl: constraints on the left of a recombined basis (boundary points skipped);
+    force_ends: put the first / last point exactly on the boundaries (regular BSplineBasis)."""
     T = t.dtype.type
-    N = len(B)
-    cl = B.cl if isinstance(B, RecombinedBSplineBasis) else 0
-    a, b = B.boundaries()
+    a, b = t[k - 1], t[t.size - k]
     x = np.empty(N, dtype=t.dtype)
     tsum = T(0)
     comp = T(0)
@@ -576,13 +571,24 @@ def collocation_points(B):
             tsum = prev + y
             comp = (tsum - prev) - y
         xi = T(tsum / T(k - 1))
-        if isinstance(B, BSplineBasis):                                 # ensure_points_at_boundaries
+        if force_ends:                                                  # ensure_points_at_boundaries
             if i == 0:
                 xi = a
             elif i == N - 1:
                 xi = b
         x[i] = min(max(xi, a), b)
     return x
+
+
+def collocation_points(B):
+    """collocation_points(B) (Collocation/points.jl:46-126,164-225): Greville sites; periodic
+    bases of even order -> the knots themselves (SameAsKnots)."""
+    if isinstance(B, PeriodicBSplineBasis):
+        if B.k % 2 == 0:
+            return B.t[:-1].copy()                                      # points.jl:176
+        raise _lib.UnsupportedError("AvgKnots for odd-order periodic bases is not implemented")
+    cl = B.cl if isinstance(B, RecombinedBSplineBasis) else 0
+    return greville_points(B.k, B.t, len(B), cl, isinstance(B, BSplineBasis))
 
 
 class CollocationMatrix:

@@ -1,0 +1,265 @@
+"""CPU tests: the oracle against the reference's golden vectors and restated property tests.
+
+These pin the oracle (oracle/bsk_oracle.c) before it is trusted as the checker of the CUDA
+path: class-A docstring goldens bit for bit, class-B to the printed precision, and the
+reference's own property tests (test/bsplines.jl, test/splines.jl, test/collocation.jl,
+test/periodic.jl, test/recombination.jl) restated on seeded inputs.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import dec_range
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "docstring_goldens.json")))
+
+
+def rng_vals(seed, n):
+    # the product's generator is not imported here on purpose: numpy only
+    return np.random.default_rng(seed).random(n)
+
+
+def test_class_a_basis(oracle):
+    g = GOLD["class_A"]["basis_k4_range_m1_0p1_1"]
+    br = dec_range(g["breaks"]["a"], g["breaks"]["b"], g["breaks"]["n"])
+    t = oracle.augment_knots(br, g["k"])
+    i, bs = oracle.evaluate_all(0, 4, t, [0.42])
+    assert [int(i[0]), bs[0].tolist()] == g["B(0.42)"]
+    assert bs[0].sum() == g["sum(bs)"]
+    i, bs = oracle.evaluate_all(0, 4, t, [0.44], ileft=[18])
+    assert [int(i[0]), bs[0].tolist()] == g["B(0.44;ileft=18)"]
+    i, bs = oracle.evaluate_all(0, 4, t, [0.42], vt="f32")
+    assert int(i[0]) == 18 and bs.dtype == np.float32
+    assert bs[0].tolist() == [float(np.float32(v)) for v in g["B(0.42,Float32)"][1]]
+    i, bs = oracle.evaluate_all(0, 4, t, [0.42], nderiv=1)
+    assert [int(i[0]), bs[0].tolist()] == g["B(0.42,Derivative(1))"]
+    # bs[1] - B[i](0.42) == 0.0 and bs[2] - B[i-1](0.42) == -5.55e-17 (BSplines.jl:66-70)
+    _, bs = oracle.evaluate_all(0, 4, t, [0.42])
+    assert bs[0][0] - oracle.basis_function(4, t, 18, 0.42) == 0.0
+    assert bs[0][1] - oracle.basis_function(4, t, 17, 0.42) == -5.551115123125783e-17
+
+
+def test_class_a_basis_function(oracle):
+    g = GOLD["class_A"]["basis_function_B6"]
+    t = oracle.augment_knots(dec_range(-1, 1, 21), 4)
+    assert oracle.basis_function(4, t, 6, -0.5) == g["B[6](-0.5)"]
+    assert oracle.basis_function(4, t, 6, -0.5, 1) == g["B[6](-0.5,Derivative(1))"]
+
+
+def test_class_a_periodic(oracle):
+    g = GOLD["class_A"]["periodic_k4_range_m1_0p2_1"]
+    br = dec_range(g["breaks"]["a"], g["breaks"]["b"], g["breaks"]["n"])
+    i, bs = oracle.evaluate_all(1, 4, br, [-0.42])
+    assert [int(i[0]), bs[0].tolist()] == g["B(-0.42)"]
+    i, bs = oracle.evaluate_all(1, 4, br, [-0.42 + 2])
+    assert [int(i[0]), bs[0].tolist()] == g["B(-0.42+2)"]
+
+
+def test_class_a_knot_layouts(oracle):
+    g = GOLD["class_A"]["knot_layouts"]
+    assert oracle.augment_knots(np.array([0, 0.1, 0.2, 0.6, 1.0]), 3).tolist() == g["BSplineBasis(3, [0, 0.1, 0.2, 0.6, 1])"]
+
+
+def test_class_b_interpolation(oracle):
+    g = GOLD["class_B"]["interpolate_cospi"]
+    xs = dec_range(g["xs"]["a"], g["xs"]["b"], g["xs"]["n"])
+    ys = np.cos(np.pi * xs)
+    k = g["k"]
+    t = oracle.make_knots(xs, k)
+    band, nout = oracle.collocation_matrix(0, k, t, xs)
+    assert nout == 0 and oracle.banded_lu(band) == 0
+    c = oracle.banded_solve(band, ys.copy().reshape(-1, 1)).ravel()
+    assert np.allclose(c[:5], g["coefs_head_6digits"], rtol=6e-6)
+    ev = lambda x: oracle.spline_eval(0, k, t, c, [x])[0]
+    assert ev(-1.0) == g["S(-1)"]
+    assert ev(-0.99) == pytest.approx(g["S(-0.99)"], abs=2e-15)
+    assert ev(0.998) == pytest.approx(g["S(0.998)"], abs=2e-15)
+    k1, t1, c1 = oracle.spline_derivative(0, k, t, c, 1)
+    k2, t2, c2 = oracle.spline_derivative(0, k, t, c, 2)
+    assert oracle.spline_eval(0, k1, t1, c1, [-1.0])[0] == pytest.approx(g["D1S(-1)"], abs=5e-13)
+    assert oracle.spline_eval(0, k2, t2, c2, [-1.0])[0] == pytest.approx(g["D2S(-1)"], abs=5e-11)
+    p = g["periodic"]
+    xp = dec_range(p["xp"]["a"], p["xp"]["b"], p["xp"]["n"])
+    tp = oracle.make_knots_periodic(xp, 4, p["L"])
+    a, b, cc, nout = oracle.collocation_cyclic(4, tp, xp)
+    assert nout == 0
+    cp = oracle.cyclic_solve(a, b, cc, np.cos(np.pi * xp))
+    assert np.allclose(cp[:5], p["coefs_head_6digits"], rtol=6e-6)
+    assert oracle.spline_eval(1, 4, tp, cp, [-0.99])[0] == pytest.approx(p["Sper(-0.99)"], abs=2e-15)
+    assert oracle.spline_eval(1, 4, tp, cp, [0.998])[0] == pytest.approx(p["Sper(0.998)"], abs=2e-15)
+
+
+@pytest.mark.parametrize("k", [2, 4, 5, 6, 8])
+def test_find_knot_interval_identities(oracle, k):
+    """test/bsplines.jl:18-30."""
+    br = np.sort(rng_vals(1, 30)); br[0], br[-1] = 0.0, 1.0
+    t = oracle.augment_knots(br, k)
+    N = t.size - k
+    a, b = t[0], t[-1]
+    i, z = oracle.find_knot_interval(0, k, t, [a - 1, a, b, b + 1])
+    assert list(zip(i.tolist(), z.tolist())) == [(1, -1), (k, 0), (N, 0), (N, 1)]
+    x = (a + b) / 3
+    i, z = oracle.find_knot_interval(0, k, t, [x])
+    assert (i[0], z[0]) == (np.searchsorted(t, x, side="right"), 0)
+    j = t.size // 2
+    i, z = oracle.find_knot_interval(0, k, t, [t[j - 1]])
+    assert (i[0], z[0]) == (np.searchsorted(t, t[j - 1], side="right"), 0)
+
+
+@pytest.mark.parametrize("k", [2, 4, 5, 6, 8])
+def test_evaluate_all_properties(oracle, k):
+    """test/bsplines.jl:49-123: partition of unity, match with the recursive evaluator,
+    dot(cs, bs) == (op * S)(x), Float32 variant."""
+    br = np.sort(rng_vals(2, 25)); br[0], br[-1] = 0.0, 1.0
+    t = oracle.augment_knots(br, k)
+    N = t.size - k
+    c = rng_vals(3, N) - 0.5
+    xs = np.array([t[0], t[k + 2], 0.2 * t[k + 2] + 0.8 * t[k + 3], t[-1]])
+    for nd in (0, 1, 2):
+        if nd >= k:
+            continue
+        i, bs = oracle.evaluate_all(0, k, t, xs, nderiv=nd)
+        i32, bs32 = oracle.evaluate_all(0, k, t, xs, nderiv=nd, vt="f32")
+        assert np.array_equal(i, i32)
+        assert np.allclose(bs, bs32, rtol=2e-5, atol=1e-4 * max(1.0, np.abs(bs).max()))
+        tot = bs.sum(axis=1)
+        if nd == 0:
+            assert np.allclose(tot, 1.0, atol=1e-14)
+        else:
+            assert np.allclose(tot, 0.0, atol=1e-9 * np.abs(bs).max())
+        kd, td, cd = (k, t, c) if nd == 0 else oracle.spline_derivative(0, k, t, c, nd)
+        sv = oracle.spline_eval(0, kd, td, cd, xs)
+        for p, x in enumerate(xs):
+            for d in range(k):
+                j = i[p] - d
+                if 1 <= j <= N:
+                    assert bs[p, d] == pytest.approx(oracle.basis_function(k, t, j, x, nd),
+                                                     rel=1e-10, abs=1e-10 * max(1, np.abs(bs).max()))
+            dot = sum(c[i[p] - d - 1] * bs[p, d] for d in range(k) if 1 <= i[p] - d <= N)
+            assert dot == pytest.approx(sv[p], rel=1e-9, abs=1e-9 * max(1, np.abs(bs).max()))
+
+
+@pytest.mark.parametrize("k", [3, 4, 6])
+def test_periodic_matches_regular_far_from_boundaries(oracle, k):
+    """test/periodic.jl:127-157: a periodic basis equals a regular one (bit for bit) away from
+    the boundaries, with index shift delta = (k - 1) - k ÷ 2."""
+    br = np.linspace(-1.0, 1.0, 41)
+    t = oracle.augment_knots(br, k)
+    xs = np.linspace(-0.3, 0.3, 17)
+    i_r, bs_r = oracle.evaluate_all(0, k, t, xs)
+    i_p, bs_p = oracle.evaluate_all(1, k, br, xs)
+    assert np.array_equal(bs_r, bs_p)
+    assert np.all(i_r - i_p == (k - 1) - k // 2)
+    # partition of unity and periodic shift ilast' == ilast + nN (test/periodic.jl:77-122)
+    x = 2 * rng_vals(4, 50) - 1
+    i0, b0 = oracle.evaluate_all(1, k, br, x)
+    i1, b1 = oracle.evaluate_all(1, k, br, x + 2 * 3)
+    assert np.allclose(b0.sum(axis=1), 1, atol=1e-14)
+    assert np.all(i1 == i0 + 3 * 40)
+    assert np.allclose(b0, b1, atol=1e-12)
+
+
+def test_banded_lu_cases(oracle):
+    """test/collocation.jl:4-53."""
+    w = np.array([[2.0]], order="F")
+    assert oracle.banded_lu(w) == 0
+    w = np.array([[0.0]], order="F")
+    assert oracle.banded_lu(w) == 1
+    band = np.zeros((3, 4), order="F"); band[1] = [1, 2, 0, 4]
+    assert oracle.banded_lu(band) == 3
+    # random diagonally dominant system: L*U == A and A*(F\y) == y
+    n, h = 40, 3
+    r = np.random.default_rng(5)
+    band = np.asfortranarray(r.random((2 * h + 1, n)))
+    band[h] += 2 * h + 1
+    A = np.zeros((n, n))
+    for j in range(n):
+        for i in range(max(0, j - h), min(n, j + h + 1)):
+            A[i, j] = band[h + i - j, j]
+    lu = band.copy(order="F")
+    assert oracle.banded_lu(lu) == 0
+    L = np.eye(n); U = np.zeros((n, n))
+    for j in range(n):
+        for i in range(max(0, j - h), min(n, j + h + 1)):
+            if i > j: L[i, j] = lu[h + i - j, j]
+            else: U[i, j] = lu[h + i - j, j]
+    assert np.allclose(L @ U, A, atol=1e-13)
+    y = r.random((n, 3))
+    x = oracle.banded_solve(lu, y.copy())
+    assert np.allclose(A @ x, y, atol=1e-12)
+    assert np.allclose(oracle.banded_matvec(band, x), y, atol=1e-12)
+
+
+@pytest.mark.parametrize("k", [3, 4, 6, 8])
+def test_polynomial_reproduction(oracle, k):
+    """test/splines.jl:14-78: interpolating a degree k-1 polynomial at the Greville sites
+    reproduces P and P' on 9N+42 points."""
+    br = np.sort(rng_vals(6, 12)); br[0], br[-1] = -1.0, 1.0
+    t = oracle.augment_knots(br, k)
+    N = t.size - k
+    xc = oracle.greville(0, k, t)
+    assert xc[0] == t[0] and xc[-1] == t[-1] and np.all(np.diff(xc) > 0)
+    pc = rng_vals(7, k) - 0.5
+    P = np.polynomial.Polynomial(pc)
+    band, nout = oracle.collocation_matrix(0, k, t, xc)
+    assert nout == 0
+    dense_rows = oracle.banded_matvec(band, np.ones(N))
+    assert np.allclose(dense_rows, 1.0, atol=1e-14)          # rows sum to one
+    assert oracle.banded_lu(band) == 0
+    c = oracle.banded_solve(band, P(xc).reshape(-1, 1).copy()).ravel()
+    xs = np.linspace(-1, 1, 9 * N + 42)
+    assert np.allclose(oracle.spline_eval(0, k, t, c, xs), P(xs), atol=1e-12)
+    k1, t1, c1 = oracle.spline_derivative(0, k, t, c, 1)
+    assert np.allclose(oracle.spline_eval(0, k1, t1, c1, xs), P.deriv()(xs), atol=1e-10)
+
+
+@pytest.mark.parametrize("k", [4, 5, 8])
+def test_robin_recombination_satisfies_bc(oracle, k):
+    """test/recombination.jl:150-172,284-305: every recombined function satisfies
+    u + 3 du/dn = 0 at both ends (d/dn = -d/dx on the left)."""
+    br = np.sort(rng_vals(8, 15)); br[0], br[-1] = 0.0, 1.0
+    t = oracle.augment_knots(br, k)
+    N = t.size - k
+    rc = oracle.robin_corners(k, t, [1.0, 3.0])
+    # column sums of the corner blocks are 2 (normalisation r = 2/(b0-b1), matrices.jl:288-309)
+    assert rc.ul.sum() == pytest.approx(2.0) and rc.lr.sum() == pytest.approx(2.0)
+    for x, sign in ((0.0, -1.0), (1.0, 1.0)):
+        _, v = oracle.evaluate_all(0, k, t, [x], recomb=rc)
+        _, d = oracle.evaluate_all(0, k, t, [x], nderiv=1, recomb=rc)
+        resid = v[0] + 3 * sign * d[0]
+        assert np.max(np.abs(resid)) < 1e-9 * max(1.0, np.abs(d).max())
+    # collocation rows of the recombined basis are column combinations of the parent's
+    M = N - 2
+    xcol = oracle.greville(2, k, t, cl=1, N=M)
+    assert np.all((xcol > 0) & (xcol < 1))
+    band_r, nout = oracle.collocation_matrix(2, k, t, xcol, recomb=rc)
+    assert nout == 0 and band_r.shape == (2 * k - 3, M)
+
+
+def test_cyclic_solve_against_dense(oracle):
+    """test/periodic.jl:159-182: cond(C) < 1e3, rows sum to one, C x == y."""
+    br = np.sort(rng_vals(9, 31)); br[0], br[-1] = 0.0, 1.0
+    x = br[:-1].copy()
+    a, b, c, nout = oracle.collocation_cyclic(4, br, x)
+    n = a.size
+    A = np.zeros((n, n))
+    for i in range(n):
+        A[i, i] = b[i]; A[i, (i - 1) % n] = a[i]; A[i, (i + 1) % n] = c[i]
+    assert nout == 0 and np.allclose(A.sum(axis=1), 1.0, atol=1e-14)
+    assert np.linalg.cond(A) < 1e3
+    d = rng_vals(10, n * 3).reshape(n, 3)
+    sol = oracle.cyclic_solve(a, b, c, d.copy())
+    assert np.allclose(A @ sol, d, atol=1e-12)
+
+
+def test_greville_kahan_and_make_knots(oracle):
+    x = np.cumsum(rng_vals(11, 40))
+    for k in (3, 4, 6):
+        t = oracle.make_knots(x, k)
+        assert t.size == x.size + k and np.all(t[:k] == x[0]) and np.all(t[-k:] == x[-1])
+        assert np.all(np.diff(t) >= 0)
+        kinv = 1.0 / (k - 1)
+        assert t[k] == sum(x[1:k].tolist(), 0.0) * kinv or t[k] == pytest.approx(np.sum(x[1:k]) * kinv, rel=1e-15)
