@@ -211,7 +211,9 @@ def run_ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("k_spline_pp_bytes_per_launch")
+            t = json.load(f).get("k_spline_cell_bytes_per_launch")
+            if t is not None and args.algo != "deboor":
+                traffic = t * (npts / float(1 << 28))      # captured on 2^28 points
     except Exception:
         pass
 

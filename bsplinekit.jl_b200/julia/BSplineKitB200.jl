@@ -1,0 +1,275 @@
+# BSplineKitB200.jl — Julia-side shim that binds libbsplinekit_b200.so (include/bsk.h) behind
+# BSplineKit's own call signatures, by adding METHODS (multiple dispatch is the reference's
+# plugin interface; nothing in BSplineKit is edited).
+#
+# NOTE: Julia is not installed in the build image, so this file has been reviewed but never
+# executed; the executable stand-in with the same structure is the Python mirror
+# (bsplinekit_b200/api.py), which the test-suite drives through the same C ABI.
+#
+# Usage:
+#   using BSplineKit, BSplineKitB200
+#   xs = DeviceVector(rand(2^28))                 # host -> device once
+#   S  = interpolate(x, y, BSplineOrder(4)) |> spline
+#   v  = S.(xs)            # or S(xs): device-resident values   (Splines/spline.jl:144)
+#   dv = (Derivative(1) * S)(xs)
+#   v, dv = evaluate(S, xs, (0, 1))              # fused, one pass over the points
+#   itp = interpolate(x, DeviceMatrix(Y), BSplineOrder(6))   # Y is M x N: M data sets interleaved
+module BSplineKitB200
+
+using BSplineKit
+using BSplineKit: BSplines, Splines, Collocation, SplineInterpolations, Recombinations
+using BSplineKit.BSplines: BSplineBasis, PeriodicBSplineBasis, AbstractBSplineBasis, knots, order
+using BSplineKit.Recombinations: RecombinedBSplineBasis, recombination_matrix, num_constraints,
+    num_recombined, submatrices
+using LinearAlgebra
+
+export DeviceVector, DeviceMatrix, device_spline, evaluate
+
+const lib = get(ENV, "BSPLINEKIT_B200_LIB", "libbsplinekit_b200")
+
+# ---- status -> exception (include/bsk.h: bsk_status) ---------------------------------------
+function last_error()
+    buf = Vector{UInt8}(undef, 512)
+    n = ccall((:bsk_last_error, lib), Csize_t, (Ptr{UInt8}, Csize_t), buf, 512)
+    String(buf[1:min(n, 511)])
+end
+
+function check(st::Int32, info = nothing)
+    st == 0 && return nothing
+    msg = last_error()
+    st == -1 && throw(ArgumentError(msg))
+    st == -2 && throw(DimensionMismatch(msg))
+    st == -4 && throw(LinearAlgebra.ZeroPivotException(something(info, -1)))
+    st == -5 && throw(OutOfMemoryError())
+    error("libbsplinekit_b200: $msg (status $st)")        # -3 CUDA, -6 unsupported
+end
+
+dtype_code(::Type{Float32}) = Int32(0)
+dtype_code(::Type{Float64}) = Int32(1)
+
+# ---- device arrays: raw device pointer + owner finaliser (no CUDA.jl) -----------------------
+mutable struct DeviceVector{T} <: AbstractVector{T}
+    ptr::Ptr{T}
+    len::Int
+    device::Int32
+    function DeviceVector{T}(::UndefInitializer, n::Integer; device = Int32(0)) where {T}
+        p = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:bsk_malloc, lib), Int32, (Int32, Csize_t, Ptr{Ptr{Cvoid}}), device, n * sizeof(T), p))
+        v = new{T}(convert(Ptr{T}, p[]), n, device)
+        finalizer(x -> ccall((:bsk_free, lib), Int32, (Int32, Ptr{Cvoid}), x.device, x.ptr), v)
+    end
+end
+Base.size(v::DeviceVector) = (v.len,)
+Base.getindex(::DeviceVector, i...) = error("scalar indexing of a DeviceVector is not supported; use Array(v)")
+
+function DeviceVector(h::Vector{T}; device = Int32(0)) where {T <: Union{Float32, Float64, Int64, Int8}}
+    v = DeviceVector{T}(undef, length(h); device)
+    GC.@preserve h check(ccall((:bsk_memcpy_h2d, lib), Int32, (Int32, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                               device, v.ptr, pointer(h), sizeof(h), C_NULL))
+    check(ccall((:bsk_stream_sync, lib), Int32, (Int32, Ptr{Cvoid}), device, C_NULL))
+    v
+end
+
+function Base.Array(v::DeviceVector{T}) where {T}
+    h = Vector{T}(undef, v.len)
+    GC.@preserve h check(ccall((:bsk_memcpy_d2h, lib), Int32, (Int32, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                               v.device, pointer(h), v.ptr, sizeof(h), C_NULL))
+    check(ccall((:bsk_stream_sync, lib), Int32, (Int32, Ptr{Cvoid}), v.device, C_NULL))
+    h
+end
+
+# M x N matrix, column-major: column i holds the M interleaved values of data point i, i.e. the
+# memory layout of Vector{SVector{M,T}} (test/interpolation.jl:57).
+struct DeviceMatrix{T}
+    data::DeviceVector{T}
+    M::Int
+    N::Int
+end
+DeviceMatrix(h::Matrix{T}) where {T} = DeviceMatrix{T}(DeviceVector(vec(h)), size(h, 1), size(h, 2))
+
+# ---- bases ----------------------------------------------------------------------------------
+mutable struct BasisHandle
+    ptr::Ptr{Cvoid}
+end
+destroy!(h::BasisHandle) = ccall((:bsk_basis_destroy, lib), Int32, (Ptr{Cvoid},), h.ptr)
+
+struct RecombDesc
+    cl::Int32; cr::Int32; nl::Int32; nr::Int32; ul_rows::Int32; lr_rows::Int32
+    ul::Ptr{Float64}; lr::Ptr{Float64}
+end
+
+const _basis_cache = IdDict{Any, BasisHandle}()
+
+function handle(B::BSplineBasis{k, T}; device = Int32(0)) where {k, T}
+    get!(_basis_cache, B) do
+        t = collect(T, knots(B))                       # materialises AugmentedKnots (knots.jl:43-48)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve t check(ccall((:bsk_basis_create, lib), Int32,
+            (Int32, Int32, Int32, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}),
+            0, k, dtype_code(T), pointer(t), length(t), C_NULL, device, out))
+        finalizer(destroy!, BasisHandle(out[]))
+    end
+end
+
+function handle(B::PeriodicBSplineBasis{k, T}; device = Int32(0)) where {k, T}
+    get!(_basis_cache, B) do
+        ξ = collect(T, parent(knots(B)))               # breakpoints incl. endpoint (periodic.jl:37-55)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve ξ check(ccall((:bsk_basis_create, lib), Int32,
+            (Int32, Int32, Int32, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}),
+            1, k, dtype_code(T), pointer(ξ), length(ξ), C_NULL, device, out))
+        finalizer(destroy!, BasisHandle(out[]))
+    end
+end
+
+function handle(R::RecombinedBSplineBasis{k, T}; device = Int32(0)) where {k, T}
+    get!(_basis_cache, R) do
+        A = recombination_matrix(R)
+        ul, lr = map(m -> Matrix{Float64}(m), submatrices(A))      # corner blocks (matrices.jl:70-110)
+        cl, cr = num_constraints(A); nl, nr = num_recombined(A)
+        t = collect(T, knots(parent(R)))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve t ul lr begin
+            desc = Ref(RecombDesc(cl, cr, nl, nr, size(ul, 1), size(lr, 1), pointer(ul), pointer(lr)))
+            check(ccall((:bsk_basis_create, lib), Int32,
+                (Int32, Int32, Int32, Ptr{Cvoid}, Int64, Ptr{RecombDesc}, Int32, Ptr{Ptr{Cvoid}}),
+                2, k, dtype_code(T), pointer(t), length(t), desc, device, out))
+        end
+        finalizer(destroy!, BasisHandle(out[]))
+    end
+end
+
+# find_knot_interval(ts, xs)  (BSplines/evaluate_all.jl:102-119, periodic.jl:85-100)
+function BSplines.find_knot_interval(B::AbstractBSplineBasis, xs::DeviceVector{T}) where {T}
+    is = DeviceVector{Int64}(undef, length(xs)); zs = DeviceVector{Int8}(undef, length(xs))
+    check(ccall((:bsk_find_knot_interval, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int8}, Ptr{Cvoid}),
+        handle(B).ptr, xs.ptr, length(xs), is.ptr, zs.ptr, C_NULL))
+    is, zs
+end
+
+# evaluate_all(B, xs, [op], [T]; [ileft])  (BSplines/evaluate_all.jl:53-64, periodic.jl:228,
+# Recombinations/bases.jl:386): returns (is::DeviceVector{Int64}, bs::DeviceMatrix{T} k x n)
+function BSplines.evaluate_all(B::AbstractBSplineBasis, xs::DeviceVector{Tx},
+                               op::Derivative{n} = Derivative(0), ::Type{T} = Tx;
+                               ileft::Union{Nothing, DeviceVector{Int64}} = nothing) where {Tx, n, T}
+    k = order(B)
+    is = DeviceVector{Int64}(undef, length(xs))
+    bs = DeviceVector{T}(undef, k * length(xs))
+    check(ccall((:bsk_evaluate_all, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Ptr{Cvoid}),
+        handle(B).ptr, xs.ptr, length(xs), n, dtype_code(T),
+        ileft === nothing ? Ptr{Int64}(C_NULL) : ileft.ptr, is.ptr, bs.ptr, C_NULL))
+    is, DeviceMatrix{T}(bs, k, length(xs))
+end
+(B::AbstractBSplineBasis)(xs::DeviceVector, args...; kws...) = BSplines.evaluate_all(B, xs, args...; kws...)
+
+# ---- splines --------------------------------------------------------------------------------
+mutable struct SplineHandle
+    ptr::Ptr{Cvoid}
+end
+const _spline_cache = IdDict{Any, SplineHandle}()
+
+function device_spline(S::Spline{T}) where {T <: Union{Float32, Float64}}
+    get!(_spline_cache, S) do
+        B = Splines.basis(S)
+        c = collect(T, Splines.unwrap_coefficients(S))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve c check(ccall((:bsk_spline_create, lib), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}), handle(B).ptr, pointer(c), length(c), out))
+        finalizer(h -> ccall((:bsk_spline_destroy, lib), Int32, (Ptr{Cvoid},), h.ptr), SplineHandle(out[]))
+    end
+end
+
+"""
+    evaluate(S::Spline, xs::DeviceVector, derivs::NTuple{N,Int}) -> NTuple{N,DeviceVector}
+
+`D^d S` for every `d` in `derivs`, in one pass over the points (fused value + derivatives).
+"""
+function evaluate(S::Spline{T}, xs::DeviceVector{T}, derivs::NTuple{N, Int} = (0,); algo = 0) where {T, N}
+    outs = ntuple(_ -> DeviceVector{T}(undef, length(xs)), Val(N))
+    ptrs = Ptr{Cvoid}[o.ptr for o in outs]
+    ds = Int32[d for d in derivs]
+    GC.@preserve ptrs ds check(ccall((:bsk_spline_eval, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Int32, Ptr{Cvoid}),
+        device_spline(S).ptr, xs.ptr, length(xs), N, ds, ptrs, algo, C_NULL))
+    outs
+end
+
+# (S::Spline)(x) and S.(xs)  (Splines/spline.jl:69,144): device vectors take the batched path.
+(S::Spline)(xs::DeviceVector) = evaluate(S, xs, (0,))[1]
+Base.Broadcast.broadcasted(S::Spline, xs::DeviceVector) = S(xs)
+# Derivative(n) * S stays the reference's host code (O(N n), spline.jl:272-330); the resulting
+# Spline is uploaded on first use by device_spline.
+
+# Host arrays, staged and pipelined inside the library (H2D | kernel | D2H overlapped):
+function evaluate(S::Spline{T}, xs::Vector{T}, derivs::NTuple{N, Int} = (0,); algo = 0) where {T, N}
+    outs = ntuple(_ -> Vector{T}(undef, length(xs)), Val(N))
+    ptrs = Ptr{Cvoid}[pointer(o) for o in outs]
+    ds = Int32[d for d in derivs]
+    GC.@preserve xs outs ptrs ds check(ccall((:bsk_spline_eval_host, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Int32),
+        device_spline(S).ptr, pointer(xs), length(xs), N, ds, ptrs, algo))
+    outs
+end
+
+# ---- collocation + banded LU / solve ------------------------------------------------------------
+"""Device-resident CollocationMatrix (band store (2k-3) x n) and its LU; `<: Factorization` so that
+`SplineInterpolation` accepts it exactly like `CyclicLUWrapper` (SplineInterpolations.jl:56-88)."""
+mutable struct DeviceBandedLU{T} <: Factorization{T}
+    ptr::Ptr{Cvoid}
+    n::Int
+end
+Base.size(F::DeviceBandedLU) = (F.n, F.n)
+
+function Collocation.collocation_matrix(B::AbstractBSplineBasis, xs::DeviceVector{Float64},
+                                        deriv::Derivative{n} = Derivative(0);
+                                        clip_threshold = eps(Float64)) where {n}
+    k = order(B)
+    N = length(B)
+    length(xs) == N || throw(ArgumentError("wrong dimensions of collocation matrix"))
+    band = DeviceVector{Float64}(undef, (2k - 3) * N)
+    nout = Ref{Int64}(0)
+    check(ccall((:bsk_collocation_matrix, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Float64, Ptr{Float64}, Ptr{Int64}, Ptr{Cvoid}),
+        handle(B).ptr, xs.ptr, N, n, clip_threshold, band.ptr, nout, C_NULL))
+    nout[] > 0 && @warn "Non-zero value outside of matrix bands ($(nout[]) entries)"    # Collocation.jl:239-244
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:bsk_banded_create, lib), Int32, (Ptr{Float64}, Int64, Int32, Int32, Int32, Ptr{Ptr{Cvoid}}),
+                band.ptr, N, k - 2, k - 2, xs.device, out))
+    F = DeviceBandedLU{Float64}(out[], N)
+    finalizer(f -> ccall((:bsk_banded_destroy, lib), Int32, (Ptr{Cvoid},), f.ptr), F)
+end
+
+function LinearAlgebra.lu!(F::DeviceBandedLU)                       # Collocation/matrix.jl:132-201
+    info = Ref{Int64}(0)
+    st = ccall((:bsk_banded_lu, lib), Int32, (Ptr{Cvoid}, Ptr{Int64}), F.ptr, info)
+    check(st, info[])
+    F
+end
+
+# ldiv!(F, Y): Y is M x N (M data sets interleaved), solved in place   (Collocation/matrix.jl:218-271)
+function LinearAlgebra.ldiv!(F::DeviceBandedLU, Y::DeviceMatrix{Float64}; algo = 0)
+    Y.N == F.n || throw(DimensionMismatch("vectors `x` and `y` must have length $(F.n)"))
+    check(ccall((:bsk_banded_solve, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Cvoid}),
+                F.ptr, Y.data.ptr, Y.M, algo, C_NULL))
+    Y
+end
+
+"""
+    interpolate(x, Y::DeviceMatrix, BSplineOrder(k)) -> (B, F, Y)
+
+Batched `interpolate` (SplineInterpolations.jl:260-273): knots from `make_knots` (host), one
+collocation assembly + LU on the device, then every data set of `Y` is solved in place; column
+`j` of the result holds the B-spline coefficients of data set `j`.
+"""
+function SplineInterpolations.interpolate(x::AbstractVector, Y::DeviceMatrix{Float64}, ord::BSplineOrder{k}) where {k}
+    t = SplineInterpolations.make_knots(x, ord, nothing)            # :302-326, stays host code
+    B = BSplineBasis(ord, t; augment = Val(false))
+    xs = DeviceVector(collect(Float64, x))
+    F = lu!(Collocation.collocation_matrix(B, xs))
+    ldiv!(F, Y)
+    B, F, Y
+end
+
+end # module
