@@ -1,0 +1,176 @@
+"""GPU tests at BASELINE.json's full sizes (configs C2..C5): size-independent properties on the
+whole problem + comparison with the oracle on subsets the oracle finishes in seconds."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-13
+TOL32 = 1e-5
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from bsplinekit_b200 import synth as s
+    return s
+
+
+def test_c2_full_size_eval(bk, oracle, synth):
+    """C2: k = 4, 1000 non-uniform breakpoints, value + 1st derivative at 2^28 points."""
+    import torch
+    n = 1 << 28
+    k = 4
+    B = bk.BSplineBasis(k, synth.breakpoints(3, 1000))
+    c1 = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    c2 = 2 * synth.u_numpy(40, 0, len(B)) - 1
+    S1, S2, S12 = bk.Spline(B, c1), bk.Spline(B, c2), bk.Spline(B, 0.5 * c1 - 2.0 * c2)
+    xd = synth.u_torch(5, 0, n)
+    v1, d1 = S1.evaluate(xd, (0, 1))
+    # oracle on strided subsets of the whole range
+    idx = torch.arange(0, n, 4099, device="cuda")
+    xs = xd[idx].cpu().numpy()
+    ref = oracle.spline_eval(0, k, B.knots(), c1, xs)
+    kd, td, cd = oracle.spline_derivative(0, k, B.knots(), c1, 1)
+    refd = oracle.spline_eval(0, kd, td, cd, xs)
+    assert relerr(v1[idx].cpu().numpy(), ref) < TOL64
+    assert relerr(d1[idx].cpu().numpy(), refd) < TOL64
+    # linearity over ALL points: S(0.5 c1 - 2 c2) == 0.5 S(c1) - 2 S(c2)
+    v2, d2 = S2.evaluate(xd, (0, 1))
+    v12, d12 = S12.evaluate(xd, (0, 1))
+    err_v = (v12 - (0.5 * v1 - 2.0 * v2)).abs().max().item()
+    err_d = (d12 - (0.5 * d1 - 2.0 * d2)).abs().max().item()
+    assert err_v < 1e-14 * 4 and err_d < 1e-13 * d12.abs().max().item()
+    # range: |S| <= max|c| (convex combinations), exact zeros nowhere inside the domain by accident
+    assert v1.abs().max().item() <= np.abs(c1).max() * (1 + 1e-14)
+    # fused == separate calls
+    v_only = S1.evaluate(xd, (0,))[0]
+    d_only = S1.evaluate(xd, (1,))[0]
+    assert torch.equal(v_only, v1) and torch.equal(d_only, d1)
+    # bit-faithful kernel on the full stream agrees with the fast one
+    vb = S1.evaluate(xd, (0,), algo=bk.EVAL_DEBOOR)[0]
+    assert ((vb - v1).abs().max() / v1.abs().max()).item() < TOL64
+    assert np.array_equal(vb[idx].cpu().numpy(), ref)
+
+
+def test_c3_full_size_batched_solve(bk, oracle, synth):
+    """C3: 65 536 data sets sharing 4 096 non-uniform xdata, k = 6: one LU + multi-RHS solve."""
+    import torch
+    n, k, nrhs = 4096, 6, 65536
+    xdata = synth.breakpoints(6, n)
+    t = bk.make_knots(xdata, k)
+    B = bk.BSplineBasis(k, t, augment=False)
+    itp = bk.SplineInterpolation(B, xdata)
+    assert itp.C.halo > 0
+    Y0 = (2 * synth.u_torch(7, 0, n * nrhs) - 1).reshape(n, nrhs)
+    band, nout = oracle.collocation_matrix(0, k, t, xdata)
+    assert nout == 0
+    lu = band.copy(order="F")
+    assert oracle.banded_lu(lu) == 0
+    cols = np.r_[0:256, 32768:33024, nrhs - 256:nrhs]
+    ref = oracle.banded_solve(lu, np.ascontiguousarray(Y0[:, cols].cpu().numpy()))
+    bw = k - 2
+    bd = torch.from_numpy(np.ascontiguousarray(band)).cuda()       # (2bw+1, n): band[u+i-j, j]
+    for algo, exact in ((bk.SOLVE_WINDOWED, False), (bk.SOLVE_TWOPASS, True), (bk.SOLVE_AUTO, False)):
+        Y = Y0.clone()
+        itp.C.ldiv_(Y, algo=algo)
+        got = Y[:, cols].cpu().numpy()
+        if exact:
+            assert np.array_equal(got, ref)
+        else:
+            assert relerr(got, ref) < TOL64
+            assert np.max(np.max(np.abs(got - ref), axis=0) / np.max(np.abs(ref), axis=0)) < TOL64
+        # residual of the WHOLE batch: C * c - y, with C applied diagonal by diagonal
+        R = -Y0.clone()
+        for d in range(-bw, bw + 1):          # entries C[i, i+d] = band[bw - d, i + d]
+            lo, hi = max(0, -d), min(n, n - d)
+            R[lo:hi] += bd[bw - d, lo + d:hi + d, None] * Y[lo + d:hi + d]
+        assert R.abs().max().item() < 5e-13
+        del R, Y
+
+
+def test_c4_periodic_full(bk, oracle, synth):
+    """C4: PeriodicBSplineBasis, k = 4, 10^4 breakpoints: cyclic solve + evaluation."""
+    import torch
+    n = 10000
+    br = synth.breakpoints(8, n + 1)
+    B = bk.PeriodicBSplineBasis(4, br)
+    x = bk.collocation_points(B)
+    M = bk.collocation_matrix(B, x)
+    a, b, c, nout = oracle.collocation_cyclic(4, br, x)
+    assert nout == 0 and np.array_equal(M.a, a) and np.array_equal(M.b, b) and np.array_equal(M.c, c)
+    # (i) solve: 1 RHS (latency case) and 16 384 interleaved RHS
+    d1 = 2 * synth.u_numpy(9, 0, n) - 1
+    got1 = d1.copy().reshape(n, 1)
+    M.ldiv_(got1)
+    assert relerr(got1.ravel(), oracle.cyclic_solve(a, b, c, d1.copy())) < TOL64
+    nrhs = 16384
+    D0 = (2 * synth.u_torch(9, 0, n * nrhs) - 1).reshape(n, nrhs)
+    D = D0.clone()
+    M.ldiv_(D)
+    cols = np.r_[0:128, nrhs - 128:nrhs]
+    ref = oracle.cyclic_solve(a, b, c, np.ascontiguousarray(D0[:, cols].cpu().numpy()))
+    assert relerr(D[:, cols].cpu().numpy(), ref) < TOL64
+    ad, bd, cd = (torch.from_numpy(v).cuda() for v in (a, b, c))
+    R = bd[:, None] * D + ad[:, None] * torch.roll(D, 1, 0) + cd[:, None] * torch.roll(D, -1, 0) - D0
+    assert R.abs().max().item() < 1e-12
+    # (ii) evaluation of the interpolant of data set 0 at 2^28 points + wrap subset in [-2L, 3L)
+    coefs = D[:, 0].cpu().numpy()
+    S = bk.Spline(B, coefs)
+    assert relerr(S(x, algo=bk.EVAL_DEBOOR), D0[:, 0].cpu().numpy()) < 1e-12        # I.(xs) ≈ ys
+    xd = synth.u_torch(9, 1 << 40, 1 << 28)
+    v = S.evaluate(xd, (0,))[0]
+    idx = torch.arange(0, 1 << 28, 8191, device="cuda")
+    ref = oracle.spline_eval(1, 4, br, coefs, xd[idx].cpu().numpy())
+    assert relerr(v[idx].cpu().numpy(), ref) < TOL64
+    xw = -2.0 + 5.0 * synth.u_numpy(9, 1 << 41, 1 << 20)
+    refw = oracle.spline_eval(1, 4, br, coefs, xw)
+    assert relerr(S(xw), refw) < TOL64
+    assert np.array_equal(S(xw, algo=bk.EVAL_DEBOOR), refw)
+
+
+def test_c5_recombined_robin_full(bk, oracle, synth):
+    """C5: RecombinedBSplineBasis, Robin D(0) + 3 D(1), k = 8, collocation_matrix with Derivative(2)
+    at 10^5 points + Float32 sweeps."""
+    import torch
+    k = 8
+    br = synth.breakpoints(10, 99996)
+    B = bk.BSplineBasis(k, br)
+    R = bk.RecombinedBSplineBasis(B, bk.Derivative(0) + 3 * bk.Derivative(1))
+    assert len(B) == 100002 and len(R) == 100000
+    rc = oracle.robin_corners(k, B.knots(), [1.0, 3.0])
+    assert np.array_equal(R.ul, rc.ul) and np.array_equal(R.lr, rc.lr)
+    x = bk.collocation_points(R)
+    assert np.array_equal(x, oracle.greville(2, k, B.knots(), cl=1, N=len(R)))
+    ref, nout_ref = oracle.collocation_matrix(2, k, B.knots(), x, nderiv=2, recomb=rc)
+    Cm, nout = bk.collocation_matrix(R, x, bk.Derivative(2), return_outside=True)
+    assert nout == nout_ref == 0
+    got = Cm.data()
+    assert got.shape == (13, 100000) and np.array_equal(got, ref)
+    assert np.count_nonzero(got) <= 8 * 100000
+    # evaluate_all(R, x, Derivative(n), Float32), n = 0..2 (the `T` reading of "Float32 sweep")
+    for nd in (0, 1, 2):
+        i_ref, bs_ref = oracle.evaluate_all(0, k, B.knots(), x, nderiv=nd, vt="f32", recomb=rc)
+        i, bs = bk.evaluate_all(R, x, bk.Derivative(nd), np.float32)
+        assert np.array_equal(i, i_ref) and np.array_equal(bs, bs_ref)
+        _, bs64 = oracle.evaluate_all(0, k, B.knots(), x, nderiv=nd, recomb=rc)
+        assert relerr(bs, bs64) < TOL32
+    # Float32 basis + Float32 spline evaluated at 2^28 Float32 points
+    brf = br.astype(np.float32)
+    Bf = bk.BSplineBasis(k, brf)
+    cf = (2 * synth.u_numpy(4, 0, len(Bf)) - 1).astype(np.float32)
+    Sf = bk.Spline(Bf, cf)
+    xd = synth.u_torch(11, 0, 1 << 28, dtype=torch.float32)
+    v = Sf.evaluate(xd, (0,))[0]
+    idx = torch.arange(0, 1 << 28, 16381, device="cuda")
+    xs = xd[idx].cpu().numpy()
+    ref64 = oracle.spline_eval(0, k, Bf.knots().astype(np.float64), cf.astype(np.float64), xs.astype(np.float64))
+    assert relerr(v[idx].cpu().numpy(), ref64) < TOL32
+    ref32 = oracle.spline_eval(0, k, Bf.knots(), cf, xs, kt="f32")
+    assert np.array_equal(Sf.evaluate(xd[idx].contiguous(), (0,), algo=bk.EVAL_DEBOOR)[0].cpu().numpy(), ref32)
+    assert v.abs().max().item() <= 1.0 + 1e-5
