@@ -99,13 +99,25 @@ def workload_c2(bk, synth):
     return k, B, c
 
 
+def omp_threads(nthreads):
+    """Use all host cores for the CPU arm (torchrun exports OMP_NUM_THREADS=1); must run before
+    the oracle library is first loaded.  Returns the thread count OpenMP will actually use."""
+    os.environ["OMP_NUM_THREADS"] = str(nthreads)
+    try:
+        import ctypes
+        g = ctypes.CDLL("libgomp.so.1")
+        g.omp_set_num_threads(int(nthreads))
+        return int(g.omp_get_max_threads())
+    except Exception:
+        return nthreads
+
+
 def cpu_reference_rate(npts_sample, nthreads):
     """The reference algorithm on the host cores: de Boor value + derivative spline, OpenMP over
     points (oracle/bsk_oracle.c).  Returns (Gpoints/s, seconds)."""
     import numpy as np
     from oracle import oracle as O
     from bsplinekit_b200 import synth
-    os.environ.setdefault("OMP_NUM_THREADS", str(nthreads))
     k = 4
     br = synth.breakpoints(3, 1000)
     t = O.augment_knots(br, k)
@@ -124,7 +136,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = omp_threads(os.cpu_count() or 1)
     sample = 1 << 24
     rates, times = [], []
     for _ in range(args.warmup):
@@ -300,10 +312,63 @@ def run_ours(args):
                                       "roofline_frac": best["frac"], "algos": res,
                                       "factor_once_ms": factor_ms, "halo_rows": itp.C.halo}}
 
+    # ---- extra: configs[3] (periodic cubic) and configs[4] (Robin k = 8 + Float32 sweep) ------------
+    if not args.no_extra_configs:
+        def timed(fn, reps, setup=None):
+            tot = 0.0
+            for it in range(reps + 1):
+                if setup is not None:
+                    setup()
+                torch.cuda.synchronize()
+                a = torch.cuda.Event(enable_timing=True)
+                b_ = torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b_.record()
+                torch.cuda.synchronize()
+                if it > 0:
+                    tot += a.elapsed_time(b_)
+            return max_over_ranks(tot / reps)
+
+        torch.cuda.empty_cache()
+        n4 = 10000
+        br4 = synth.breakpoints(8, n4 + 1)
+        B4 = bk.PeriodicBSplineBasis(4, br4)
+        M4 = bk.collocation_matrix(B4, bk.collocation_points(B4))
+        nrhs4 = 16384
+        D0 = (2 * synth.u_torch(9, rank * n4 * nrhs4, n4 * nrhs4) - 1).reshape(n4, nrhs4)
+        D = torch.empty_like(D0)
+        ms = timed(lambda: M4.ldiv_(D), 5, setup=lambda: D.copy_(D0))
+        extra["c4_cyclic_solve"] = {"metric": "RHS/s (periodic cubic, n=10^4, 16384 RHS per GPU)", "ms": ms,
+                                    "value": world * nrhs4 / (ms * 1e-3), "unit": "RHS/s",
+                                    "roofline_frac": 16.0 * n4 * nrhs4 / (ms * 1e-3) / 1e9 / peak}
+        S4 = bk.Spline(B4, D[:, 0].cpu().numpy())
+        del D, D0
+        x4 = synth.u_torch(9, (1 << 40) + rank * npts, npts)
+        o4 = [torch.empty_like(x4)]
+        ms = timed(lambda: S4.evaluate(x4, (0,), out=o4), 5)
+        extra["c4_periodic_eval"] = {"metric": "Gpoints/s (periodic cubic, 10^4 knots, 2^28 F64 points)", "ms": ms,
+                                     "value": world * npts / (ms * 1e-3) / 1e9, "unit": "Gpoints/s",
+                                     "roofline_frac": 16.0 * npts / (ms * 1e-3) / 1e9 / peak}
+        del x4, o4
+        B5 = bk.BSplineBasis(8, synth.breakpoints(10, 99996))
+        R5 = bk.RecombinedBSplineBasis(B5, bk.Derivative(0) + 3 * bk.Derivative(1))
+        x5 = torch.from_numpy(bk.collocation_points(R5)).cuda()
+        ms = timed(lambda: bk.collocation_matrix(R5, x5, bk.Derivative(2)), 5)
+        extra["c5_collocation_assembly"] = {"metric": "ms per collocation_matrix(R, x, Derivative(2)), 10^5 x k=8 "
+                                                      "(assembly + band handle; launch-bound)", "ms": ms}
+        B5f = bk.BSplineBasis(8, synth.breakpoints(10, 99996).astype(np.float32))
+        S5f = bk.Spline(B5f, (2 * synth.u_numpy(4, 0, len(B5f)) - 1).astype(np.float32))
+        x5f = synth.u_torch(11, rank * npts, npts, dtype=torch.float32)
+        o5 = [torch.empty_like(x5f)]
+        ms = timed(lambda: S5f.evaluate(x5f, (0,), out=o5), 5)
+        extra["c5_float32_eval"] = {"metric": "Gpoints/s (k=8, 10^5 knots, 2^28 F32 points)", "ms": ms,
+                                    "value": world * npts / (ms * 1e-3) / 1e9, "unit": "Gpoints/s",
+                                    "roofline_frac": 8.0 * npts / (ms * 1e-3) / 1e9 / peak}
+        del x5f, o5
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = omp_threads(os.cpu_count() or 1)
         sample = 1 << 25
         r, dt = cpu_reference_rate(sample, cores)
         cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
@@ -346,6 +411,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

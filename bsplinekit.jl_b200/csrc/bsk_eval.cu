@@ -514,6 +514,10 @@ bsk_status build_pp(bsk_spline *s) {
                                (RECV * sizeof(T) + 2));
         nc = std::min<int64_t>(nc, 16 * nrec);
         nc = std::min<int64_t>(nc, 60000);
+        // Too many intervals for shared memory: keep the same tables in global memory (L2-resident,
+        // ~4.5 cells per interval); the side index is 16-bit, hence the cap on the interval count.
+        const bool in_global = nc < 3 * nrec && nrec <= 30000 && getenv("BSK_NO_GLOBAL_CELL") == nullptr;
+        if (in_global) nc = (nrec * 9) / 2;
         for (int attempt = 0; attempt < 6 && nc >= 3 * nrec && nc >= 8; ++attempt, nc = nc * 9 / 10) {
             const T x0 = (T)a;
             const T cwT = (T)((bb - a) / (double)nc);
@@ -551,7 +555,7 @@ bsk_status build_pp(bsk_spline *s) {
             const int nside = (int)xs.size();
             const size_t smem = (size_t)nc * RECV * sizeof(T) + (size_t)nside * RECV * sizeof(T) +
                                 (size_t)((nside + VPA - 1) / VPA) * VPA * sizeof(T) + (size_t)nc * 2 + 16;
-            if (smem > 226 * 1024) continue;                    // retry with fewer cells
+            if (!in_global && smem > 226 * 1024) continue;      // retry with fewer cells
             if (nmulti * 50 > nc) break;                        // clustered knots: not worth it
             // chunk-major device layout (see CellView in bsk_eval_cell.cu)
             std::vector<T> crec_cm(crec.size()), rc_cm(rcv.size());
@@ -577,7 +581,7 @@ bsk_status build_pp(bsk_spline *s) {
             s->cell_b = (double)(T)bb;
             s->cell_scale = (double)scT;
             s->cell_cw = (double)cwT;
-            s->cell_smem = smem;
+            s->cell_smem = in_global ? 0 : smem;
             s->cell_valid = true;
             break;
         }

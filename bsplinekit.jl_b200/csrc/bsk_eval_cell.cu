@@ -101,7 +101,7 @@ __device__ __noinline__ void fallback_interval(const PPView<T> pv, T xs, T *cm, 
     pp_lookup<K, T>(pv, xs, cm, u);
 }
 
-template <int K, int KIND, typename T, int DMASK>
+template <int K, int KIND, typename T, int DMASK, int STAGE>
 __global__ void __launch_bounds__(kCellThreads, 1)
 k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *__restrict__ x,
               int64_t nvec, EvalOuts outs) {
@@ -109,24 +109,29 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int NOUT = DMASK ? MaskCount<DMASK>::value : kMaxOut;
     extern __shared__ __align__(16) unsigned char smem[];
-    // ---- stage the tables ------------------------------------------------------------------
-    T *s_rec = (T *)smem;
-    T *s_rc = s_rec + (size_t)cv.ncell * RECV;
-    T *s_xi = s_rc + (size_t)cv.nside * RECV;
-    uint16_t *s_idx = (uint16_t *)(s_xi + ((cv.nside + VEC - 1) / VEC) * VEC);
-    {
+    // ---- tables: staged in shared memory (STAGE = 1), or, when they are too large for it, read
+    //      in place from global memory through L1/L2 by the very same code (STAGE = 0) ----------
+    T *const d_rec = (T *)smem;
+    T *const d_rc = d_rec + (size_t)cv.ncell * RECV;
+    T *const d_xi = d_rc + (size_t)cv.nside * RECV;
+    uint16_t *const d_idx = (uint16_t *)(d_xi + ((cv.nside + VEC - 1) / VEC) * VEC);
+    if (STAGE) {
         const int4 *src = (const int4 *)cv.rec;
-        int4 *dst = (int4 *)s_rec;
+        int4 *dst = (int4 *)d_rec;
         const int n16 = cv.ncell * RECV / VEC;
         for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
         src = (const int4 *)cv.rc;
-        dst = (int4 *)s_rc;
+        dst = (int4 *)d_rc;
         const int m16 = cv.nside * RECV / VEC;
         for (int i = threadIdx.x; i < m16; i += blockDim.x) dst[i] = src[i];
-        for (int i = threadIdx.x; i < cv.nside; i += blockDim.x) s_xi[i] = cv.xi[i];
-        for (int i = threadIdx.x; i < cv.ncell; i += blockDim.x) s_idx[i] = cv.sideidx[i];
+        for (int i = threadIdx.x; i < cv.nside; i += blockDim.x) d_xi[i] = cv.xi[i];
+        for (int i = threadIdx.x; i < cv.ncell; i += blockDim.x) d_idx[i] = cv.sideidx[i];
+        __syncthreads();
     }
-    __syncthreads();
+    const T *const s_rec = STAGE ? d_rec : cv.rec;
+    const T *const s_rc = STAGE ? d_rc : cv.rc;
+    const T *const s_xi = STAGE ? d_xi : cv.xi;
+    const uint16_t *const s_idx = STAGE ? d_idx : cv.sideidx;
 
     const T xa = cv.a, xb = cv.b, x0 = cv.x0, scale = cv.scale, cw = cv.cw;
     const int ncell1 = cv.ncell - 1;
@@ -223,12 +228,17 @@ template <int K, int KIND, typename T, int DMASK>
 bsk_status launch_cell_mask(const bsk_spline *s, const CellView<T> &cv, const PPView<T> &pv,
                             const KnotView<T> &kv, const T *d_x, int64_t nvec, const EvalOuts &outs,
                             cudaStream_t st) {
-    auto kern = k_spline_cell<K, KIND, T, DMASK>;
-    const size_t smem = s->cell_smem;
-    BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = s->cell_smem;                    // 0: tables stay in global memory
     const int sms = sm_count(s->basis->device);
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nvec + kCellThreads - 1) / kCellThreads, sms));
-    kern<<<grid, kCellThreads, smem, st>>>(cv, pv, kv, (int)s->ncoef, d_x, nvec, outs);
+    if (smem > 0) {
+        auto kern = k_spline_cell<K, KIND, T, DMASK, 1>;
+        BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kCellThreads, smem, st>>>(cv, pv, kv, (int)s->ncoef, d_x, nvec, outs);
+    } else {
+        auto kern = k_spline_cell<K, KIND, T, DMASK, 0>;
+        kern<<<grid, kCellThreads, 0, st>>>(cv, pv, kv, (int)s->ncoef, d_x, nvec, outs);
+    }
     BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }

@@ -1,16 +1,52 @@
 // bsk_host.cu — host-buffer entry points: chunked, multi-stream pipelines that overlap the
 // host->device copy of chunk i+1, the kernel of chunk i and the device->host copy of chunk i-1.
 // These are what a caller with ordinary (ideally pinned) host arrays uses; they are also the
-// "e2e" leg of bench.py.
+// "e2e" leg of bench.py.  Staging buffers and streams are cached per device (grow-only) so that
+// repeated calls do not pay cudaMalloc / cudaFree (which synchronises the device).
 #include <algorithm>
+#include <mutex>
 
 #include "handles.cuh"
 
 using namespace bsk;
 
 namespace {
+
 constexpr int kSlots = 3;
+constexpr int kBufs = 5;          // x + up to 4 outputs (eval); buffer 0 only (solve)
+constexpr int kMaxDev = 16;
+
+struct Pool {
+    cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
+    void *buf[kSlots][kBufs] = {{nullptr}};
+    size_t cap[kSlots][kBufs] = {{0}};
+};
+Pool g_pool[kMaxDev];
+std::mutex g_pool_mu[kMaxDev];
+
+cudaError_t pool_get(Pool &p, int slot, int b, size_t bytes, void **out) {
+    if (p.cap[slot][b] < bytes) {
+        if (p.buf[slot][b]) cudaFree(p.buf[slot][b]);
+        p.buf[slot][b] = nullptr;
+        p.cap[slot][b] = 0;
+        cudaError_t e = cudaMalloc(&p.buf[slot][b], bytes);
+        if (e != cudaSuccess) return e;
+        p.cap[slot][b] = bytes;
+    }
+    *out = p.buf[slot][b];
+    return cudaSuccess;
 }
+
+cudaError_t pool_stream(Pool &p, int slot, cudaStream_t *out) {
+    if (!p.st[slot]) {
+        cudaError_t e = cudaStreamCreateWithFlags(&p.st[slot], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+    }
+    *out = p.st[slot];
+    return cudaSuccess;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -21,19 +57,22 @@ bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n,
     if (n == 0) return BSK_OK;
     BSK_REQUIRE(h_x, BSK_ERR_ARGUMENT, "NULL points");
     const int device = s->basis->device;
+    BSK_REQUIRE(device >= 0 && device < kMaxDev, BSK_ERR_UNSUPPORTED, "device index out of range");
     const size_t es = s->basis->dtype == BSK_F64 ? 8 : 4;
     BSK_CUDA(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lock(g_pool_mu[device]);
+    Pool &pool = g_pool[device];
     const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 23);
+    const int nslots = (int)std::min<int64_t>(kSlots, (n + chunk - 1) / chunk);
     cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
     void *dx[kSlots] = {nullptr, nullptr, nullptr};
     void *dout[kSlots][4] = {{nullptr}};
     bsk_status rc = BSK_OK;
     cudaError_t e = cudaSuccess;
-    const int nslots = (int)std::min<int64_t>(kSlots, (n + chunk - 1) / chunk);
     for (int i = 0; i < nslots && e == cudaSuccess; ++i) {
-        e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc(&dx[i], es * chunk);
-        for (int o = 0; o < nout && e == cudaSuccess; ++o) e = cudaMalloc(&dout[i][o], es * chunk);
+        e = pool_stream(pool, i, &st[i]);
+        if (e == cudaSuccess) e = pool_get(pool, i, 0, es * chunk, &dx[i]);
+        for (int o = 0; o < nout && e == cudaSuccess; ++o) e = pool_get(pool, i, 1 + o, es * chunk, &dout[i][o]);
     }
     if (e == cudaSuccess) {
         int64_t off = 0;
@@ -55,12 +94,6 @@ bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n,
             cudaError_t e2 = cudaStreamSynchronize(st[i]);
             if (e == cudaSuccess) e = e2;
         }
-    for (int i = 0; i < nslots; ++i) {
-        if (dx[i]) cudaFree(dx[i]);
-        for (int o = 0; o < 4; ++o)
-            if (dout[i][o]) cudaFree(dout[i][o]);
-        if (st[i]) cudaStreamDestroy(st[i]);
-    }
     if (rc != BSK_OK) return rc;
     if (e != cudaSuccess) { set_error("bsk_spline_eval_host failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
     return BSK_OK;
@@ -69,19 +102,22 @@ bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n,
 bsk_status bsk_banded_solve_host(const bsk_banded *h, double *h_rhs, int64_t nrhs, int32_t algo) {
     BSK_REQUIRE(h && (nrhs == 0 || h_rhs), BSK_ERR_ARGUMENT, "NULL argument");
     if (nrhs == 0) return BSK_OK;
+    BSK_REQUIRE(h->device >= 0 && h->device < kMaxDev, BSK_ERR_UNSUPPORTED, "device index out of range");
     BSK_CUDA(cudaSetDevice(h->device));
+    std::lock_guard<std::mutex> lock(g_pool_mu[h->device]);
+    Pool &pool = g_pool[h->device];
     const int64_t n = h->n;
-    // column blocks of ~128 MB
-    int64_t cb = std::max<int64_t>(32, ((int64_t)128 << 20) / (8 * n));
-    cb = std::min(nrhs, (cb / 32) * 32 > 0 ? (cb / 32) * 32 : cb);
+    // column blocks of ~128 MB, multiples of 32 columns
+    int64_t cb = std::max<int64_t>(32, (((int64_t)128 << 20) / (8 * n)) / 32 * 32);
+    cb = std::min(nrhs, cb);
     const int nslots = (int)std::min<int64_t>(kSlots, (nrhs + cb - 1) / cb);
     cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
     double *d[kSlots] = {nullptr, nullptr, nullptr};
     cudaError_t e = cudaSuccess;
     bsk_status rc = BSK_OK;
     for (int i = 0; i < nslots && e == cudaSuccess; ++i) {
-        e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&d[i], 8 * (size_t)n * cb);
+        e = pool_stream(pool, i, &st[i]);
+        if (e == cudaSuccess) e = pool_get(pool, i, 0, 8 * (size_t)n * cb, (void **)&d[i]);
     }
     if (e == cudaSuccess) {
         int64_t c0 = 0;
@@ -101,10 +137,6 @@ bsk_status bsk_banded_solve_host(const bsk_banded *h, double *h_rhs, int64_t nrh
             cudaError_t e2 = cudaStreamSynchronize(st[i]);
             if (e == cudaSuccess) e = e2;
         }
-    for (int i = 0; i < nslots; ++i) {
-        if (d[i]) cudaFree(d[i]);
-        if (st[i]) cudaStreamDestroy(st[i]);
-    }
     if (rc != BSK_OK) return rc;
     if (e != cudaSuccess) { set_error("bsk_banded_solve_host failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
     return BSK_OK;

@@ -260,30 +260,40 @@ inline int grid_cols(int64_t ncols, int device, int per_sm) {
     return (int)std::max<int64_t>(1, std::min(want, cap));
 }
 
-// Decay of the backward recurrence: for a start at row s with unit state errors, the largest
-// |error| that reaches rows <= s - h.  Returns the smallest multiple of `step` (<= hmax) for
-// which the bound is <= tol, or 0.
+// Decay of the backward recurrence.  A backward sweep restarted at row s with a wrong state
+// (errors e_{s+1..s+bw}) propagates  e_r = -(sum_j U(r,r+j) e_{r+j}) / U(r,r)  downwards; the error
+// that reaches row s - h is T_{s,h} e with a bw x bw transfer matrix T.  We carry T explicitly
+// (signed, exact recurrence in double) and bound |T e| <= max_row sum_col |T| for |e|_inf <= 1.
+// Returns the smallest multiple of `step` (<= hmax) such that the bound is <= tol for every
+// start row, or 0 when the recurrence does not decay (windowed solve unavailable).
 int decay_halo(const std::vector<double> &urow, const std::vector<double> &dinv, int n, int bw,
                double tol, int step, int hmax) {
     if (bw == 0) return step;
-    if (n <= step) return 0;
+    if (n <= 2 * step) return 0;
     int need = 0;
-    std::vector<double> win(bw);
+    std::vector<double> win((size_t)bw * bw), acc(bw);      // win[j*bw + c]: e_{r+1+j} = sum_c win * e0_c
     for (int s = n - 1; s >= 1; --s) {
-        // |e_r| <= |1/U_rr| * sum_j |U(r, r+j)| |e_{r+j}|, started from an all-ones state
-        // (bounds any state error of size <= 1 per entry, by linearity).
-        for (int j = 0; j < bw; ++j) win[j] = 1.0;
+        std::fill(win.begin(), win.end(), 0.0);
+        for (int j = 0; j < bw; ++j) win[(size_t)j * bw + j] = 1.0;
         int h = 0;
         bool ok = false;
         for (int r = s; r >= 0 && h < hmax; --r) {
-            double acc = 0.0;
-            for (int j = 1; j <= bw; ++j) acc += std::fabs(urow[(size_t)r * bw + j - 1]) * win[j - 1];
-            acc *= std::fabs(dinv[r]);
-            for (int j = bw - 1; j >= 1; --j) win[j] = win[j - 1];
-            win[0] = acc;
+            for (int c = 0; c < bw; ++c) {
+                double a = 0.0;
+                for (int j = 1; j <= bw; ++j) a -= urow[(size_t)r * bw + j - 1] * win[(size_t)(j - 1) * bw + c];
+                acc[c] = a * dinv[r];
+            }
+            for (int j = bw - 1; j >= 1; --j)
+                for (int c = 0; c < bw; ++c) win[(size_t)j * bw + c] = win[(size_t)(j - 1) * bw + c];
+            for (int c = 0; c < bw; ++c) win[c] = acc[c];
             ++h;
             double mx = 0.0;
-            for (int j = 0; j < bw; ++j) mx = std::max(mx, win[j]);
+            for (int j = 0; j < bw; ++j) {
+                double rs = 0.0;
+                for (int c = 0; c < bw; ++c) rs += std::fabs(win[(size_t)j * bw + c]);
+                mx = std::max(mx, rs);
+            }
+            if (!(mx == mx)) return 0;
             if (mx <= tol) { ok = true; break; }
         }
         if (!ok && h >= hmax) return 0;          // no decay within hmax rows
@@ -464,7 +474,7 @@ bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot) {
     std::vector<double> urow((size_t)std::max(1, bw) * n), dinv(n);
     BSK_CUDA(cudaMemcpy(urow.data(), h->d_urow, 8 * (size_t)std::max(1, bw) * n, cudaMemcpyDeviceToHost));
     BSK_CUDA(cudaMemcpy(dinv.data(), h->d_dinv, 8 * (size_t)n, cudaMemcpyDeviceToHost));
-    h->halo = decay_halo(urow, dinv, n, bw, 1e-17, 32, 448);
+    h->halo = decay_halo(urow, dinv, n, bw, 1e-17, 8, 448);
     if (h->halo > 0) {
         bsk_status rc = windowed_prepare(h);
         if (rc != BSK_OK) return rc;

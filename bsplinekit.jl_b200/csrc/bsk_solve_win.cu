@@ -304,14 +304,16 @@ template <int BW>
 bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st) {
     constexpr int PG = 4;                                     // 4 chunks x 8 rows in flight
     constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
-    const int H = h->halo;
-    int M = (H % 48 == 0) ? 48 : H;                           // measured best on B200 for H = 96
+    // halo validated at factor time (multiple of 8); the kernel restarts every M rows and needs
+    // the effective halo to be a multiple of M
+    int M = h->halo <= 64 ? h->halo : ((h->halo + 1) / 2 + 7) / 8 * 8;
     int per_sm_cap = 16;
     if (const char *env = getenv("BSK_WINDOW_M")) {           // tuning knobs
         int m = atoi(env);
-        if (m >= 8 && m % 8 == 0 && H % m == 0) M = m;
+        if (m >= 8 && m % 8 == 0) M = m;
     }
     if (const char *env = getenv("BSK_WINDOW_CTAS")) per_sm_cap = std::max(1, atoi(env));
+    const int H = ((h->halo + M - 1) / M) * M;
     const size_t smem = ((size_t)(M + H + PG * G) * (32 + UW) + (size_t)PG * G * LW + PG) * sizeof(double);
     auto kern = k_banded_windowed<BW, PG>;
     if (smem > 48 * 1024)
