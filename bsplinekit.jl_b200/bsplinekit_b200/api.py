@@ -133,7 +133,8 @@ def period(x):
 
 
 class Natural:
-    """BoundaryConditions.Natural (BoundaryConditions.jl:36-48) — not yet on the device path."""
+    """BoundaryConditions.Natural (BoundaryConditions.jl:36-48): generalised natural BCs,
+    derivatives 2 .. k/2 vanish at the boundary (even k only)."""
 
 
 def _order(k):
@@ -346,6 +347,45 @@ def _make_submatrix(ops, B, side):
     return ndrop, nc, A
 
 
+def _natural_submatrix(B, side):
+    """_make_submatrix(::Natural, ...) (Recombinations/natural.jl:9-134).  The derivatives of the
+    boundary B-splines come from the device evaluate_all (reference arithmetic); the two small
+    (h+1) x (h+1) systems are solved on the host (the reference uses StaticArrays `\\`)."""
+    k = B.k
+    if k % 2 == 1:
+        raise ArgumentError("`Natural` boundary condition only supported for even-order splines (got k = %d)" % k)
+    T = B.t.dtype.type
+    h = k // 2
+    N = len(B)
+    x = B.t[k - 1] if side == "left" else B.t[N]
+    js = list(range(1, h + 2)) if side == "left" else list(range(N - h, N + 1))
+    D = np.zeros((h - 1, h + 1), dtype=B.t.dtype)                     # _natural_eval_derivatives
+    for i in range(1, h):
+        jlast, bs = evaluate_all(B, float(x) if T is np.float64 else T(x), Derivative(i + 1))
+        for n, j in enumerate(js):
+            dj = jlast + 1 - j
+            if 1 <= dj <= k:
+                D[i - 1, n] = bs[dj - 1]
+    rhs = np.zeros(h + 1, dtype=B.t.dtype)
+    rhs[0] = h
+    cols = []
+    for which in (1, 2):                                               # _natural_system_matrix
+        M = np.zeros((h + 1, h + 1), dtype=B.t.dtype)
+        M[0, :] = 1
+        for i in range(2, h + 1):
+            d = D[i - 2]
+            M[i - 1] = d / np.max(np.abs(d))
+        if which == 1:
+            M[h, h] = 1
+        else:
+            M[h, 0] = 1
+        v = np.linalg.solve(M, rhs)
+        eps_ = 10 * np.finfo(B.t.dtype).eps * np.max(np.abs(v))       # _remove_near_zeros
+        v[np.abs(v) < eps_] = 0
+        cols.append(v)
+    return 0, h - 1, np.stack(cols, axis=1).astype(np.float64)
+
+
 class RecombinedBSplineBasis(AbstractBSplineBasis):
     """RecombinedBSplineBasis(B, ops) / (B, ops_left, ops_right)  (Recombinations/bases.jl:223-245).
 
@@ -356,13 +396,16 @@ class RecombinedBSplineBasis(AbstractBSplineBasis):
             raise ArgumentError("parent must be a BSplineBasis")
         if ops_right == "same":
             ops_right = ops_left
-        norm = lambda o: () if o is None else ((o,) if isinstance(o, DifferentialOp) else tuple(o))
+        norm = lambda o: () if o is None else (o if isinstance(o, Natural) else
+                                               ((o,) if isinstance(o, DifferentialOp) else tuple(o)))
         self.parent = B
         self.k = B.k
         self.t = B.t
         self.ops = (norm(ops_left), norm(ops_right))
-        ldrop, cl, ul = _make_submatrix(self.ops[0], B, "left")
-        rdrop, cr, lr = _make_submatrix(self.ops[1], B, "right")
+        sub = lambda ops, side: (_natural_submatrix(B, side) if isinstance(ops, Natural)
+                                 else _make_submatrix(ops, B, side))
+        ldrop, cl, ul = sub(self.ops[0], "left")
+        rdrop, cr, lr = sub(self.ops[1], "right")
         self.cl, self.cr = cl, cr
         self.nl, self.nr = ul.shape[1], lr.shape[1]
         self.ul, self.lr = ul, lr
@@ -828,8 +871,14 @@ class SplineInterpolation:
             raise DimensionMismatch("incompatible lengths of B-spline basis and collocation points")
         self.basis = B
         self.x = x
-        Cm = collocation_matrix(B, x)
-        self.C = Cm if isinstance(Cm, CyclicTridiagonalMatrix) else Cm.lu_()
+        if isinstance(B, PeriodicBSplineBasis) and B.k == 2:
+            # the collocation matrix is the identity (Collocation/Collocation.jl:147-157)
+            if not np.array_equal(B.t[:-1], x):
+                raise ArgumentError("expected collocation points to match B-spline knots")
+            self.C = None
+        else:
+            Cm = collocation_matrix(B, x)
+            self.C = Cm if isinstance(Cm, CyclicTridiagonalMatrix) else Cm.lu_()
         self.spline = None
         self.coefs = None
 
@@ -847,7 +896,9 @@ class SplineInterpolation:
             if yh.shape[0] != N:
                 raise DimensionMismatch("input data has incorrect length")
             Y = torch.from_numpy(np.ascontiguousarray(yh, dtype=np.float64)).cuda()
-        if isinstance(self.C, CyclicTridiagonalMatrix):
+        if self.C is None:
+            pass                                                        # identity
+        elif isinstance(self.C, CyclicTridiagonalMatrix):
             self.C.ldiv_(Y)
         else:
             self.C.ldiv_(Y, algo=algo)
@@ -883,7 +934,10 @@ def interpolate(x, y, order, bc=None):
     elif isinstance(bc, Periodic):
         ts = make_knots(xf, k, bc)
         B = PeriodicBSplineBasis(k, ts)
+    elif isinstance(bc, Natural):
+        # knots = data points (SplineInterpolations.jl:275-285)
+        B = RecombinedBSplineBasis(BSplineBasis(k, xf.copy()), Natural())
     else:
-        raise _lib.UnsupportedError("Natural() interpolation is not on the device path yet")
+        raise ArgumentError("unknown boundary condition")
     itp = SplineInterpolation(B, xf)
     return itp.interpolate_(y)

@@ -571,3 +571,54 @@ def test_native_library_is_loaded(bk):
     """The parity tests above must have run through the in-tree CUDA library."""
     with open("/proc/self/maps") as f:
         assert "libbsplinekit_b200.so" in f.read()
+
+
+# ------------------------------------------------------------------------------------------------
+# Natural boundary conditions (src/Recombinations/natural.jl; SURVEY §8f N3)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [2, 4, 6, 8])
+def test_natural_recombination(bk, synth, k):
+    """test/natural.jl:10-54: derivatives 2..k/2 of a natural spline vanish at the boundaries."""
+    ts = np.linspace(-1.0, 1.0, 21)
+    B = bk.BSplineBasis(k, ts)
+    R = bk.RecombinedBSplineBasis(B, bk.Natural())
+    assert len(R) == len(B) - 2 * (k // 2 - 1)
+    if k == 2:
+        assert np.array_equal(R.recombination_matrix(), np.eye(len(B)))
+    S = bk.Spline(R, 1 + synth.u_numpy(42, 0, len(R)))
+    for x in R.boundaries():
+        xs = np.array([x])
+        Sx = S(xs, algo=bk.EVAL_DEBOOR)[0]
+        assert Sx > 1
+        eps_ = 2e-8 * Sx
+        assert abs((bk.Derivative(1) * S)(xs, algo=bk.EVAL_DEBOOR)[0]) > eps_
+        for n in range(2, k // 2 + 1):
+            assert abs((bk.Derivative(n) * S)(xs, algo=bk.EVAL_DEBOOR)[0]) < eps_
+    with pytest.raises(bk.ArgumentError):
+        bk.RecombinedBSplineBasis(bk.BSplineBasis(5, ts), bk.Natural())
+
+
+def test_natural_interpolation_docstring(bk):
+    """src/SplineInterpolations/SplineInterpolations.jl:218-257 (class B goldens)."""
+    xs = dec_range(-1, 1, 21)
+    ys = np.cos(np.pi * xs)
+    itp = bk.interpolate(xs, ys, bk.BSplineOrder(4), bk.Natural())
+    S = itp.spline
+    assert S(np.array([-1.0]), algo=bk.EVAL_DEBOOR)[0] == pytest.approx(-1.0, abs=1e-15)
+    assert (bk.Derivative(1) * S)(np.array([-1.0]))[0] == pytest.approx(0.2872618670889516, abs=1e-12)
+    assert abs((bk.Derivative(2) * S)(np.array([-1.0]))[0]) < 1e-11
+    assert S(np.array([-0.99]))[0] == pytest.approx(-0.9971071640321145, abs=1e-14)
+    assert S(np.array([0.998]))[0] == pytest.approx(-0.9994253145274461, abs=1e-14)
+    assert np.allclose(S(xs), ys, atol=1e-13)                       # S.(xs) ≈ ys
+
+
+def test_periodic_linear_interpolation_is_identity(bk, oracle, synth):
+    """k = 2 periodic: IdentityMatrix collocation (src/Collocation/Collocation.jl:147-157)."""
+    xp = 2.0 * synth.breakpoints(8, 33)[:-1] - 1.0
+    yp = synth.u_numpy(3, 0, xp.size)
+    itp = bk.interpolate(xp, yp, bk.BSplineOrder(2), bk.Periodic(2.0))
+    assert np.array_equal(itp.spline.coefficients(), yp)
+    assert np.allclose(itp.spline(xp, algo=bk.EVAL_DEBOOR), yp, atol=1e-15)
+    tp = oracle.make_knots_periodic(xp, 2, 2.0)
+    xs = -3.0 + 6.0 * synth.u_numpy(4, 0, 1000)
+    assert np.array_equal(itp.spline(xs, algo=bk.EVAL_DEBOOR), oracle.spline_eval(1, 2, tp, yp, xs))
