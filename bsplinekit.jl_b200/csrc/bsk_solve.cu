@@ -412,7 +412,7 @@ static bsk_status banded_alloc(int64_t n, int32_t l, int32_t u, int32_t device, 
     BSK_REQUIRE(n < (1ll << 30), BSK_ERR_UNSUPPORTED, "matrix too large");
     BSK_CUDA(cudaSetDevice(device));
     bsk_banded *h = new bsk_banded();
-    h->device = device; h->n = n; h->l = l; h->u = u; h->factored = false; h->halo = 0;
+    h->device = device; h->n = n; h->l = l; h->u = u; h->factored = false; h->halo = 0; h->halo_f = 0;
     h->d_w = h->d_lrow = h->d_urow = h->d_dinv = h->d_diag = h->d_urow_s = h->d_lrec = h->d_urec = nullptr;
     h->n_pad = 0;
     size_t nw = (size_t)(l + u + 1) * n, nb = (size_t)std::max(1, l) * n;
@@ -475,6 +475,17 @@ bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot) {
     BSK_CUDA(cudaMemcpy(urow.data(), h->d_urow, 8 * (size_t)std::max(1, bw) * n, cudaMemcpyDeviceToHost));
     BSK_CUDA(cudaMemcpy(dinv.data(), h->d_dinv, 8 * (size_t)n, cudaMemcpyDeviceToHost));
     h->halo = decay_halo(urow, dinv, n, bw, 1e-17, 8, 448);
+    h->halo_f = 0;
+    if (h->halo > 0 && bw > 0) {
+        // same bound for the forward recurrence (unit-diagonal L), by reversing the row order
+        std::vector<double> lrow((size_t)bw * n), lrev((size_t)bw * n), ones(n, 1.0);
+        BSK_CUDA(cudaMemcpy(lrow.data(), h->d_lrow, 8 * (size_t)bw * n, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < n; ++r)
+            for (int j = 0; j < bw; ++j) lrev[(size_t)(n - 1 - r) * bw + j] = lrow[(size_t)r * bw + j];
+        h->halo_f = decay_halo(lrev, ones, n, bw, 1e-17, 8, 448);
+    } else if (bw == 0) {
+        h->halo_f = 8;
+    }
     if (h->halo > 0) {
         bsk_status rc = windowed_prepare(h);
         if (rc != BSK_OK) return rc;

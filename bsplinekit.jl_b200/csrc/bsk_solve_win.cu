@@ -134,8 +134,9 @@ __device__ __forceinline__ void load_rec_s(const double *p, double *out) {      
 template <int BW, int PG>
 __global__ void __launch_bounds__(32)
 k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ urec,
-                  double *__restrict__ rhs, int64_t ngroups, int64_t ld, int n, int n_pad, int M, int H,
-                  const __grid_constant__ CUtensorMap tmap, int use_tmap) {
+                  double *__restrict__ rhs, int64_t ngroups, int64_t ld, int n, int n_pad_all, int M, int H,
+                  const __grid_constant__ CUtensorMap tmap, int use_tmap, int nseg, int SEG, int HF,
+                  const double *__restrict__ scratch, const __grid_constant__ CUtensorMap tmap_s) {
     constexpr int TB = 32;
     constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
     extern __shared__ __align__(128) double smem_d[];
@@ -146,7 +147,6 @@ k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ ur
     double *const cur = ring + (size_t)RW * TB;
     double *const cfw = cur + (size_t)RW * UW;
     const int lane = threadIdx.x;
-    const int nblk = (n_pad + M - 1) / M;
     const int hb = H / M;
     double *const my = ring + lane;                          // my[slot * TB]
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
@@ -161,16 +161,33 @@ k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ ur
     __syncwarp();
     unsigned issA = 0, conA = 0;                             // chunk counters (mbarrier = counter % PG)
 
-    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        double *const p = rhs + g * TB + lane;
-        const double *const grow = rhs + g * TB;             // row 0 of this column group (256 B rows)
-    
+    // Work item = (column group g, row segment seg).  A segment finalises the rows [k0, k1); its
+    // forward sweep starts HF rows earlier from a zero state (the forward recurrence forgets its
+    // start state like |L^{-1}| decays; HF validated at factor time like H) and runs H rows past
+    // k1 for the last backward restart.  With nseg == 1 this is the whole column, exactly.
+    // The solve is in place, so the halo rows of a segment (which belong to its neighbours and
+    // may already hold their results) are read from `scratch`, a copy of the rows
+    // [kb - HF, kb + H) around every segment boundary kb taken before the kernel started.
+    for (int64_t w = blockIdx.x; w < ngroups * nseg; w += gridDim.x) {
+        const int64_t g = w / nseg;
+        const int seg = (int)(w - g * nseg);
+        const int k0 = seg * SEG, k1 = min(n_pad_all, k0 + SEG);
+        const int f0 = max(0, k0 - HF);                      // first row of the forward sweep
+        const int n_pad = min(n_pad_all, k1 + H) - f0;       // local number of rows (multiple of 8)
+        const int nloc = min(n, f0 + n_pad) - f0;            // local rows that exist in HBM
+        const int kl0 = k0 - f0, kl1 = k1 - f0;              // kept rows, local
+        const int nblk = (n_pad + M - 1) / M;
+        double *const p = rhs + (int64_t)f0 * ld + g * TB + lane;
+        const double *const grow = rhs + (int64_t)f0 * ld + g * TB;   // local row 0 of this column group
+        const double *const lrec_l = lrec + (size_t)f0 * LW;
+        const double *const urec_l = urec + (size_t)f0 * UW;
+
         // ---- producer: 8 data rows + their forward and backward records, one mbarrier phase --------
         int pf_row = 0, pf_slot = 0;
         auto issue_fwd = [&]() {
             const unsigned i = issA % PG;
             const unsigned bar = barA_s + 8 * i;
-            const int nvalid = min(G, n - pf_row);           // rows that exist in HBM
+            const int nvalid = min(G, nloc - pf_row);        // rows that exist in HBM
             if (!use_tmap && nvalid < G && pf_row < n_pad) { // identity padding rows (TMA zero-fills them)
 #pragma unroll
                 for (int q = 0; q < G; ++q)
@@ -182,12 +199,17 @@ k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ ur
                     // result tiles stored from these slots (a ring lap ago) must have been read out
                     fence_proxy_async();                     // generic accesses before async writes
                     const unsigned dst = ring_s + (unsigned)(pf_slot * TB * 8);
+                    // halo chunk of a segment -> scratch copy (chunks never straddle k0 / k1)
+                    const int ra = f0 + pf_row;
+                    const bool halo = (nseg > 1) && (ra < k0 || ra >= k1);
+                    const int srow = halo ? ((ra < k0 ? seg - 1 : seg) * (HF + H) + ra - ((ra < k0 ? k0 : k1) - HF)) : 0;
                     if (use_tmap) {
                         mbar_expect_tx(bar, (unsigned)(G * TB * 8 + G * (LW + UW) * 8));
-                        tma_load_2d(dst, &tmap, (int)(g * TB), pf_row, bar);
+                        if (halo) tma_load_2d(dst, &tmap_s, (int)(g * TB), srow, bar);
+                        else tma_load_2d(dst, &tmap, (int)(g * TB), ra, bar);
                     } else {
                         mbar_expect_tx(bar, (unsigned)(nvalid * TB * 8 + G * (LW + UW) * 8));
-                        const double *src = grow + (int64_t)pf_row * ld;
+                        const double *src = halo ? scratch + (int64_t)srow * ld + g * TB : grow + (int64_t)pf_row * ld;
                         if (nvalid == G) {
 #pragma unroll
                             for (int q = 0; q < G; ++q) bulk_g2s(dst + q * TB * 8, src + (int64_t)q * ld, TB * 8, bar);
@@ -195,8 +217,8 @@ k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ ur
                             for (int q = 0; q < nvalid; ++q) bulk_g2s(dst + q * TB * 8, src + (int64_t)q * ld, TB * 8, bar);
                         }
                     }
-                    bulk_g2s(cfw_s + i * (G * LW * 8), lrec + (size_t)pf_row * LW, G * LW * 8, bar);
-                    bulk_g2s(cur_s + (unsigned)(pf_slot * UW * 8), urec + (size_t)pf_row * UW, G * UW * 8, bar);
+                    bulk_g2s(cfw_s + i * (G * LW * 8), lrec_l + (size_t)pf_row * LW, G * LW * 8, bar);
+                    bulk_g2s(cur_s + (unsigned)(pf_slot * UW * 8), urec_l + (size_t)pf_row * UW, G * UW * 8, bar);
                 } else {
                     mbar_arrive(bar);
                 }
@@ -260,7 +282,7 @@ k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ ur
             }
             // ---- backward sweep that finalises block bb = b - hb ------------------------------
             const int bb = b - hb;
-            if (bb >= 0) {
+            if (bb >= 0 && bb * M >= kl0 && bb * M < kl1) {
                 const int keep_lo = bb * M;
                 const int keep_hi = min(n_pad, (bb + 1) * M);
                 const int r_top = min(n_pad, (bb + 1) * M + H);   // exclusive, multiple of 8
@@ -308,7 +330,7 @@ k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ ur
                     if (rc < keep_hi) {                      // kept rows (warp-uniform branch): store
 #pragma unroll
                             for (int q = G - 1; q >= 0; --q) {
-                                if (rc + q < n) *dst = t[q];
+                                if (rc + q < nloc) *dst = t[q];
                                 dst -= ld;
                             }
                     }
@@ -388,13 +410,56 @@ bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t 
         BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(per_sm_cap, (226 * 1024) / (smem + 1024)));
     const int64_t slots = (int64_t)sm_count(h->device) * per_sm;
-    const int64_t rounds = (ngroups + slots - 1) / slots;
-    const int grid = (int)std::max<int64_t>(1, (ngroups + rounds - 1) / rounds);   // balanced rounds
-    CUtensorMap tmap;
+    // Row segments: only when there are too few column groups to fill the machine and the forward
+    // recurrence decays too (halo_f > 0).  Redundant work per segment: (HF + H) rows.
+    int nseg = 1, SEG = h->n_pad, HF = 0;
+    if (h->halo_f > 0 && ngroups < slots && getenv("BSK_NO_SEGMENTS") == nullptr) {
+        HF = ((h->halo_f + M - 1) / M) * M;
+        int want = (int)((3 * slots / 2 + ngroups - 1) / ngroups);
+        int most = std::max(1, h->n_pad / (6 * (HF + H)));          // keep redundancy below ~1/6
+        nseg = std::max(1, std::min(want, most));
+        if (const char *env = getenv("BSK_WINDOW_NSEG")) nseg = std::max(1, atoi(env));
+        SEG = ((h->n_pad + nseg - 1) / nseg + M - 1) / M * M;
+        nseg = (h->n_pad + SEG - 1) / SEG;
+        if (nseg == 1) { SEG = h->n_pad; HF = 0; }
+    }
+    const int64_t nwork = ngroups * nseg;
+    const int64_t rounds = (nwork + slots - 1) / slots;
+    const int grid = (int)std::max<int64_t>(1, (nwork + rounds - 1) / rounds);   // balanced rounds
+    CUtensorMap tmap, tmap_s;
     memset(&tmap, 0, sizeof(tmap));
-    const int use_tmap = make_rhs_tensor_map(&tmap, d_rhs, ngroups * 32, ld, h->n) ? 1 : 0;
-    kern<<<grid, 32, smem, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap, use_tmap);
-    BSK_CUDA(cudaGetLastError());
+    memset(&tmap_s, 0, sizeof(tmap_s));
+    int use_tmap = make_rhs_tensor_map(&tmap, d_rhs, ngroups * 32, ld, h->n) ? 1 : 0;
+    double *scratch = nullptr;
+    if (nseg > 1) {
+        // copy of the rows around every segment boundary (contiguous in memory: full rows)
+        const int HS = HF + H;
+        static bool pool_set[64] = {false};
+        if (h->device >= 0 && h->device < 64 && !pool_set[h->device]) {
+            // keep freed scratch blocks cached in the stream-ordered pool (default: returned to the
+            // OS at every synchronisation, which makes the next cudaMallocAsync cost ~1 ms)
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+                uint64_t thr = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            pool_set[h->device] = true;
+        }
+        BSK_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * (size_t)(nseg - 1) * HS * ld, st));
+        for (int b = 0; b + 1 < nseg; ++b) {
+            const int64_t kb = (int64_t)(b + 1) * SEG;
+            const int64_t r0 = kb - HF, r1 = std::min<int64_t>(h->n, kb + H);
+            if (r1 > r0)
+                BSK_CUDA(cudaMemcpyAsync(scratch + (size_t)b * HS * ld, d_rhs + r0 * ld, sizeof(double) * (size_t)(r1 - r0) * ld,
+                                         cudaMemcpyDeviceToDevice, st));
+        }
+        if (use_tmap && !make_rhs_tensor_map(&tmap_s, scratch, ngroups * 32, ld, (int64_t)(nseg - 1) * HS)) use_tmap = 0;
+    }
+    kern<<<grid, 32, smem, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap, use_tmap,
+                                 nseg, SEG, HF, scratch, tmap_s);
+    cudaError_t le = cudaGetLastError();
+    if (scratch) cudaFreeAsync(scratch, st);
+    BSK_CUDA(le);
     return BSK_OK;
 }
 

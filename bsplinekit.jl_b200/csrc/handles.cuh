@@ -109,6 +109,7 @@ struct bsk_banded {
     double *d_diag;       // n     : U(i,i)
     double *d_lrec, *d_urec;   // padded per-row records of the windowed solve (bsk_solve_win.cu)
     int n_pad;
+    int halo_f;           // decay halo of the forward recurrence (row-segmented windowed solve)
     int halo;             // decay halo (rows) validated for the windowed solve, 0 = not usable
 };
 

@@ -457,7 +457,7 @@ def test_banded_solve_twopass_bitexact(bk, oracle, synth, k, n, nrhs):
     assert np.max(np.abs(res)) < 1e-12
 
 
-@pytest.mark.parametrize("k,n,nrhs", [(6, 4096, 2048), (4, 2000, 1500), (8, 3000, 1100)])
+@pytest.mark.parametrize("k,n,nrhs", [(6, 4096, 2048), (4, 2000, 1500), (8, 3000, 1100), (6, 16384, 2048), (4, 30001, 96)])
 def test_banded_solve_windowed_tolerance(bk, oracle, synth, k, n, nrhs):
     """Single-pass windowed solve: coefficients within 1e-13 of BANSLV (in practice ~1e-16)."""
     import torch
