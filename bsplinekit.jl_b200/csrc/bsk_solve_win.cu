@@ -343,6 +343,242 @@ k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ ur
     }
 }
 
+// ---- TMEM-resident ring --------------------------------------------------------------------------
+// Same algorithm, but the per-lane ring of z' values lives in Tensor Memory instead of shared
+// memory: tcgen05.st / tcgen05.ld with the 32x32b shape give every lane of a warp private access to
+// "its" TMEM lane, 512 x 32-bit columns per SM-quarter, i.e. lane-private on-chip storage that does
+// not compete with shared memory.  A CTA of 4 warps allocates 256 columns (128 doubles per thread =
+// 128 ring rows >= M + H), so two CTAs = 8 warps are resident per SM instead of ~4.4, and a whole
+// 8-row chunk moves with ONE tcgen05.ld/st (x16) instead of 8 LDS/STS.  Shared memory only holds
+// the TMA landing buffers (PG chunks of RHS rows and forward records) and the backward records.
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const double *v) {
+    unsigned r[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r[2 * i] = (unsigned)__double2loint(v[i]); r[2 * i + 1] = (unsigned)__double2hiint(v[i]); }
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, double *v) {
+    unsigned r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+constexpr int kTmemCols = 256;            // per CTA (power of two); 2 CTAs per SM
+constexpr int kTmemRows = kTmemCols / 2;  // ring rows per lane (one double = two 32-bit columns)
+
+template <int BW, int PG>
+__global__ void __launch_bounds__(128, 2)
+k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
+              double *__restrict__ rhs, int64_t ngroups, int64_t ld, int n, int n_pad_all, int M, int H,
+              const __grid_constant__ CUtensorMap tmap, int nseg, int SEG, int HF,
+              const double *__restrict__ scratch, const __grid_constant__ CUtensorMap tmap_s) {
+    constexpr int TB = 32;
+    constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
+    constexpr int RWT = kTmemRows;                            // TMEM ring rows
+    constexpr int RC = RWT + PG * G;                          // rows of backward records kept in smem
+    // per-warp shared memory (doubles): stage[PG][8][32] | cur[RC][UW] | cfw[PG][8*LW] | mbar[PG]
+    constexpr int WARP_D = ((PG * G * TB + RC * UW + PG * G * LW + PG + 15) / 16) * 16;   // 128-byte multiple
+    extern __shared__ __align__(128) double smem_d[];
+    __shared__ unsigned s_tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_tmem_base);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tbase = s_tmem_base + ((unsigned)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+
+    double *const stage = smem_d + (size_t)warp * WARP_D;
+    double *const cur = stage + PG * G * TB;
+    double *const cfw = cur + RC * UW;
+    const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
+    const unsigned cur_s = (unsigned)__cvta_generic_to_shared(cur);
+    const unsigned cfw_s = (unsigned)__cvta_generic_to_shared(cfw);
+    const unsigned barA_s = cfw_s + (unsigned)(PG * G * LW * 8);
+    const int hb = H / M;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < PG; ++i) mbar_init(barA_s + 8 * i, 1);
+        fence_proxy_async();
+    }
+    __syncwarp();
+    unsigned issA = 0, conA = 0;
+
+    const int64_t nwork = ngroups * nseg;
+    for (int64_t w = (int64_t)blockIdx.x * 4 + warp; w < nwork; w += (int64_t)gridDim.x * 4) {
+        const int64_t g = w / nseg;
+        const int seg = (int)(w - g * nseg);
+        const int k0 = seg * SEG, k1 = min(n_pad_all, k0 + SEG);
+        const int f0 = max(0, k0 - HF);
+        const int n_pad = min(n_pad_all, k1 + H) - f0;
+        const int nloc = min(n, f0 + n_pad) - f0;
+        const int kl0 = k0 - f0, kl1 = k1 - f0;
+        const int nblk = (n_pad + M - 1) / M;
+        double *const p = rhs + (int64_t)f0 * ld + g * TB + lane;
+        const double *const lrec_l = lrec + (size_t)f0 * LW;
+        const double *const urec_l = urec + (size_t)f0 * UW;
+
+        int pf_row = 0, pf_cslot = 0;                         // next row to prefetch, its slot in `cur`
+        auto issue_fwd = [&]() {
+            const unsigned i = issA % PG;
+            const unsigned bar = barA_s + 8 * i;
+            __syncwarp();                                    // all lanes are done with this staging slot
+            if (elect_one()) {
+                if (pf_row < n_pad) {
+                    fence_proxy_async();
+                    const int ra = f0 + pf_row;
+                    const bool halo = (nseg > 1) && (ra < k0 || ra >= k1);
+                    const int srow = halo ? ((ra < k0 ? seg - 1 : seg) * (HF + H) + ra - ((ra < k0 ? k0 : k1) - HF)) : 0;
+                    mbar_expect_tx(bar, (unsigned)(G * TB * 8 + G * (LW + UW) * 8));
+                    if (halo) tma_load_2d(stage_s + i * (G * TB * 8), &tmap_s, (int)(g * TB), srow, bar);
+                    else tma_load_2d(stage_s + i * (G * TB * 8), &tmap, (int)(g * TB), ra, bar);
+                    bulk_g2s(cfw_s + i * (G * LW * 8), lrec_l + (size_t)pf_row * LW, G * LW * 8, bar);
+                    bulk_g2s(cur_s + (unsigned)(pf_cslot * UW * 8), urec_l + (size_t)pf_row * UW, G * UW * 8, bar);
+                } else {
+                    mbar_arrive(bar);
+                }
+            }
+            ++issA;
+            pf_row += G;
+            pf_cslot += G;
+            if (pf_cslot == RC) pf_cslot = 0;
+        };
+#pragma unroll 1
+        for (int gg = 0; gg < PG; ++gg) issue_fwd();
+
+        int f_slot = 0;                                      // TMEM ring slot of the next forward row
+        double tf[BW > 0 ? BW : 1];
+        {
+            mbar_wait(barA_s + 8 * (conA % PG), (conA / PG) & 1);
+            const double *const ys = stage + (conA % PG) * (G * TB) + lane;
+            ++conA;
+#pragma unroll
+            for (int j = 0; j < BW; ++j) tf[j] = ys[j * TB];
+        }
+        for (int b = 0; b < nblk + hb; ++b) {
+            if (b < nblk) {
+                const int r1 = min(n_pad, (b + 1) * M);
+#pragma unroll 1
+                for (int r0 = b * M; r0 < r1; r0 += G) {
+                    const unsigned i = (conA - 1) % PG;
+                    const unsigned inext = conA % PG;
+                    mbar_wait(barA_s + 8 * inext, (conA / PG) & 1);
+                    ++conA;
+                    const double *const ys = stage + i * (G * TB) + lane;
+                    const double *const yn = stage + inext * (G * TB) + lane;
+                    const double *const lr = cfw + i * (G * LW);
+                    double t[G + BW];
+#pragma unroll
+                    for (int j = 0; j < BW; ++j) t[j] = tf[j];
+#pragma unroll
+                    for (int q = BW; q < G; ++q) t[q] = ys[q * TB];
+                    if (r0 + G < n_pad) {
+#pragma unroll
+                        for (int j = 0; j < BW; ++j) t[G + j] = yn[j * TB];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BW; ++j) t[G + j] = 0.0;
+                    }
+                    double rec[G][LW];
+#pragma unroll
+                    for (int q = 0; q < G; ++q) load_rec_s<LW>(lr + q * LW, rec[q]);
+                    double zs[G];
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        const double z = t[q];
+#pragma unroll
+                        for (int j = 1; j <= BW; ++j) t[q + j] = fma(-z, rec[q][j - 1], t[q + j]);
+                        zs[q] = z * rec[q][BW];
+                    }
+                    tmem_st8(tbase + (unsigned)(f_slot * 2), zs);
+#pragma unroll
+                    for (int j = 0; j < BW; ++j) tf[j] = t[G + j];
+                    f_slot += G;
+                    if (f_slot == RWT) f_slot = 0;
+                    issue_fwd();
+                }
+            }
+            const int bb = b - hb;
+            if (bb >= 0 && bb * M >= kl0 && bb * M < kl1) {
+                const int keep_lo = bb * M;
+                const int keep_hi = min(n_pad, (bb + 1) * M);
+                const int r_top = min(n_pad, (bb + 1) * M + H);
+                double tb[BW > 0 ? BW : 1];
+                int slot = r_top % RWT;
+                slot = (slot == 0 ? RWT : slot) - G;
+                int cslot = r_top % RC;
+                cslot = (cslot == 0 ? RC : cslot) - G;
+                double *dst = p + (int64_t)(keep_hi - 1) * ld;
+                tmem_wait_st();                              // forward results are in TMEM
+#pragma unroll 1
+                for (int rc = r_top - G; rc >= keep_lo; rc -= G) {
+                    const double *const ur = cur + cslot * UW;
+                    const int p_slot = (slot == 0 ? RWT : slot) - G;
+                    double t[G], tl[G];
+                    double la[BW > 0 ? BW : 1];
+                    tmem_ld8(tbase + (unsigned)(slot * 2), t);
+                    if (rc != r_top - G) {
+#pragma unroll
+                        for (int j = 0; j < BW; ++j) t[G - 1 - j] = tb[j];
+                    }
+                    if (rc > keep_lo) {
+                        tmem_ld8(tbase + (unsigned)(p_slot * 2), tl);
+#pragma unroll
+                        for (int j = 0; j < BW; ++j) la[j] = tl[G - 1 - j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BW; ++j) la[j] = 0.0;
+                    }
+                    double rec[G][UW];
+#pragma unroll
+                    for (int q = 0; q < G; ++q) load_rec_s<UW>(ur + q * UW, rec[q]);
+#pragma unroll
+                    for (int q = G - 1; q >= 0; --q) {
+                        const double xq = t[q];
+#pragma unroll
+                        for (int j = 1; j <= BW; ++j) {
+                            if (q - j >= 0) t[q - j] = fma(-xq, rec[q][j - 1], t[q - j]);
+                            else la[j - q - 1] = fma(-xq, rec[q][j - 1], la[j - q - 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < BW; ++j) tb[j] = la[j];
+                    if (rc < keep_hi) {
+#pragma unroll
+                        for (int q = G - 1; q >= 0; --q) {
+                            if (rc + q < nloc) *dst = t[q];
+                            dst -= ld;
+                        }
+                    }
+                    slot = p_slot;
+                    cslot = (cslot == 0 ? RC : cslot) - G;
+                }
+            }
+        }
+        while (conA < issA) { mbar_wait(barA_s + 8 * (conA % PG), (conA / PG) & 1); ++conA; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(s_tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
 template <int BW>
 bsk_status prepare_t(bsk_banded *h) {
     constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
@@ -413,9 +649,12 @@ bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t 
     // Row segments: only when there are too few column groups to fill the machine and the forward
     // recurrence decays too (halo_f > 0).  Redundant work per segment: (HF + H) rows.
     int nseg = 1, SEG = h->n_pad, HF = 0;
-    if (h->halo_f > 0 && ngroups < slots && getenv("BSK_NO_SEGMENTS") == nullptr) {
+    const bool tmem_ok = M + H <= kTmemRows && getenv("BSK_NO_TMEM") == nullptr && get_encoder() != nullptr;
+    const int64_t fill = tmem_ok ? (int64_t)sm_count(h->device) * 8 * 4 / 5     // 8 warps/SM, >= 80 % of them busy
+                                 : (slots * 3 + 1) / 2;
+    if (h->halo_f > 0 && ngroups < fill && getenv("BSK_NO_SEGMENTS") == nullptr) {
         HF = ((h->halo_f + M - 1) / M) * M;
-        int want = (int)((3 * slots / 2 + ngroups - 1) / ngroups);
+        int want = (int)((fill + ngroups - 1) / ngroups);
         int most = std::max(1, h->n_pad / (6 * (HF + H)));          // keep redundancy below ~1/6
         nseg = std::max(1, std::min(want, most));
         if (const char *env = getenv("BSK_WINDOW_NSEG")) nseg = std::max(1, atoi(env));
@@ -455,8 +694,22 @@ bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t 
         }
         if (use_tmap && !make_rhs_tensor_map(&tmap_s, scratch, ngroups * 32, ld, (int64_t)(nseg - 1) * HS)) use_tmap = 0;
     }
-    kern<<<grid, 32, smem, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap, use_tmap,
-                                 nseg, SEG, HF, scratch, tmap_s);
+    if (use_tmap && tmem_ok) {
+        // TMEM-resident ring: 2 CTAs x 4 warps per SM
+        constexpr int RC = kTmemRows + PG * G;
+        const size_t smem_t = (size_t)4 * (((PG * G * 32 + RC * UW + PG * G * LW + PG + 15) / 16) * 16) * sizeof(double);
+        auto kt = k_banded_tmem<BW, PG>;
+        BSK_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        const int64_t wslots = (int64_t)sm_count(h->device) * 8;
+        const int64_t wr = (nwork + wslots - 1) / wslots;
+        const int64_t nwarps = (nwork + wr - 1) / wr;
+        const int gridt = (int)std::max<int64_t>(1, (nwarps + 3) / 4);
+        kt<<<gridt, 128, smem_t, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap,
+                                       nseg, SEG, HF, scratch, tmap_s);
+    } else {
+        kern<<<grid, 32, smem, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap, use_tmap,
+                                     nseg, SEG, HF, scratch, tmap_s);
+    }
     cudaError_t le = cudaGetLastError();
     if (scratch) cudaFreeAsync(scratch, st);
     BSK_CUDA(le);
