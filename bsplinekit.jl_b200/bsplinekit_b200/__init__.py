@@ -9,5 +9,5 @@ from ._lib import (ArgumentError, DimensionMismatch, ZeroPivotException, CudaErr
 from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, period,
                   BSplineBasis, PeriodicBSplineBasis, RecombinedBSplineBasis, augment_knots,
                   knots, order, boundaries, find_knot_interval, evaluate_all,
-                  Spline, collocation_points, greville_points, collocation_matrix, CollocationMatrix,
+                  Spline, SplineBatch, collocation_points, greville_points, collocation_matrix, CollocationMatrix,
                   CyclicTridiagonalMatrix, lu, ldiv, make_knots, SplineInterpolation, interpolate)

@@ -586,6 +586,30 @@ class Spline:
         return self.evaluate(x, (0,), algo)[0]
 
 
+class SplineBatch:
+    """M splines sharing one basis: Spline(B, coefs) with eltype(coefs) <: SVector{M}
+    (Splines/spline.jl:180-184).  coefs: (length(B), M) CUDA tensor, M fastest — exactly what a
+    batched interpolate! leaves on the device.  Calling it returns an (n, M) tensor."""
+
+    def __init__(self, B, coefs):
+        if isinstance(B, RecombinedBSplineBasis):
+            raise _lib.UnsupportedError("vector-valued evaluation needs a plain or periodic basis")
+        if not (isinstance(coefs, torch.Tensor) and coefs.is_cuda):
+            coefs = torch.as_tensor(np.ascontiguousarray(coefs, dtype=_NP[B._dt])).cuda()
+        if coefs.dim() != 2 or coefs.shape[0] != len(B) or coefs.dtype != _TORCH[B._dt]:
+            raise DimensionMismatch("wrong number of coefficients")
+        self.basis, self.coefs = B, coefs.contiguous()
+
+    def __call__(self, x):
+        xd, on_dev = _to_device(x, self.basis._dt)
+        xd = xd.reshape(-1)
+        M = self.coefs.shape[1]
+        out = torch.empty((xd.numel(), M), dtype=self.coefs.dtype, device=xd.device)
+        check(lib.bsk_spline_eval_multi(self.basis._handle, _ptr(self.coefs), self.coefs.shape[0], M,
+                                        _ptr(xd), xd.numel(), _ptr(out), _stream()))
+        return out if on_dev else out.cpu().numpy()
+
+
 # ---- collocation ----------------------------------------------------------------------------------
 
 def greville_points(k, t, N, cl=0, force_ends=True):
@@ -907,6 +931,8 @@ class SplineInterpolation:
             self.spline = Spline(self.basis, Y.cpu().numpy())
         else:
             self.spline = None
+        self.splines = (SplineBatch(self.basis, Y) if Y.dim() == 2 and not isinstance(self.basis, RecombinedBSplineBasis)
+                        else None)
         return self
 
     def spline_of(self, column=0):

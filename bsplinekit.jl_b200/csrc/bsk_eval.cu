@@ -684,6 +684,9 @@ bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout,
         set_error("local-polynomial path needs full end-knot multiplicity");
         return BSK_ERR_UNSUPPORTED;
     }
+    // lazily built state (tables, derivative splines) is created under the handle's mutex; the
+    // kernels themselves only read it
+    std::unique_lock<std::mutex> lock(const_cast<bsk_spline *>(s)->mu);
     if (try_pp) {
         bsk_spline *sm = const_cast<bsk_spline *>(s);
         if (!s->pp_valid) {

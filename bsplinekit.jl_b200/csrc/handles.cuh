@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -93,6 +94,7 @@ struct bsk_spline {
     size_t cell_smem;
     bool cell_valid;
     std::vector<bsk_spline *> derivs;   // cached Derivative(n) * S, index n (0 unused)
+    std::mutex mu;        // guards the lazily built tables / derivative cache (evaluation is otherwise read-only)
 };
 
 struct bsk_banded {

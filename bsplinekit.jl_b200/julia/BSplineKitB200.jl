@@ -213,6 +213,17 @@ function evaluate(S::Spline{T}, xs::Vector{T}, derivs::NTuple{N, Int} = (0,); al
     outs
 end
 
+# Vector-valued splines: coefficients SVector{M,T} held as an M x N DeviceMatrix (M fastest),
+# e.g. the result of a batched interpolate!.  Returns an M x n DeviceMatrix (column p = S(xs[p])).
+function evaluate(B::AbstractBSplineBasis, C::DeviceMatrix{T}, xs::DeviceVector{T}) where {T}
+    C.N == length(B) || throw(DimensionMismatch("wrong number of coefficients"))
+    out = DeviceVector{T}(undef, C.M * length(xs))
+    check(ccall((:bsk_spline_eval_multi, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+        handle(B).ptr, C.data.ptr, C.N, C.M, xs.ptr, length(xs), out.ptr, C_NULL))
+    DeviceMatrix{T}(out, C.M, length(xs))
+end
+
 # ---- collocation + banded LU / solve ------------------------------------------------------------
 """Device-resident CollocationMatrix (band store (2k-3) x n) and its LU; `<: Factorization` so that
 `SplineInterpolation` accepts it exactly like `CyclicLUWrapper` (SplineInterpolations.jl:56-88)."""

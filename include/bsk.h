@@ -155,6 +155,13 @@ bsk_status bsk_spline_eval(const bsk_spline *s, const void *d_x, int64_t n, int3
 bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n, int32_t nout,
                                 const int32_t *derivs, void *const *h_outs, int32_t algo);
 
+/* Vector-valued splines: M splines sharing one basis, coefficients eltype SVector{M,T}
+ * (Splines/spline.jl:180-184; test/periodic.jl:8-23, test/interpolation.jl:57).  d_coefs is
+ * [ncoef][M] with M fastest — the layout of Vector{SVector{M,T}} and of bsk_banded_solve's result —
+ * d_out is [n][M].  Plain and periodic bases; zero outside the knot domain of a plain basis. */
+bsk_status bsk_spline_eval_multi(const bsk_basis *b, const void *d_coefs, int64_t ncoef, int64_t M,
+                                 const void *d_x, int64_t n, void *d_out, void *stream);
+
 /* ---- collocation --------------------------------------------------------------------
  * collocation_matrix!(C, B, x, Derivative(deriv); clip_threshold) —
  * Collocation/Collocation.jl:209-251 into CollocationMatrix band storage

@@ -622,3 +622,137 @@ def test_periodic_linear_interpolation_is_identity(bk, oracle, synth):
     tp = oracle.make_knots_periodic(xp, 2, 2.0)
     xs = -3.0 + 6.0 * synth.u_numpy(4, 0, 1000)
     assert np.array_equal(itp.spline(xs, algo=bk.EVAL_DEBOOR), oracle.spline_eval(1, 2, tp, yp, xs))
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases: empty / ragged inputs, odd sizes, non-decaying factors
+# ------------------------------------------------------------------------------------------------
+def test_empty_and_tiny_inputs(bk, oracle, synth):
+    import torch
+    B = bk.BSplineBasis(4, synth.breakpoints(3, 50))
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    empty = torch.empty(0, dtype=torch.float64, device="cuda")
+    assert S.evaluate(empty, (0, 1))[0].numel() == 0
+    i, z = bk.find_knot_interval(B, empty)
+    assert i.numel() == 0 and z.numel() == 0
+    i, bs = bk.evaluate_all(B, empty)
+    assert i.numel() == 0 and tuple(bs.shape) == (0, 4)
+    assert S(np.empty(0)).size == 0
+    for n in (1, 2, 3, 5, 7, 33):
+        x = synth.u_numpy(5, 0, n)
+        ref = oracle.spline_eval(0, 4, B.knots(), c, x)
+        assert relerr(S(x), ref) < TOL64
+        assert np.array_equal(S(x, algo=bk.EVAL_DEBOOR), ref)
+        xd = torch.from_numpy(x).cuda()
+        assert relerr(S.evaluate(xd, (0,))[0].cpu().numpy(), ref) < TOL64
+
+
+@pytest.mark.parametrize("k,n,nrhs", [(6, 4099, 2081), (4, 1001, 2050), (6, 777, 2048)])
+def test_banded_solve_ragged_sizes(bk, oracle, synth, k, n, nrhs):
+    """n not a multiple of the 8-row chunk, RHS count not a multiple of 32 (tail columns take the
+    BANSLV-order kernels), unaligned sub-blocks."""
+    import torch
+    xdata, t, B, Cm, ref = _interp_system(bk, oracle, synth, n, k)
+    lu_ref = ref.copy(order="F")
+    oracle.banded_lu(lu_ref)
+    Cm.lu_()
+    Y = (2 * synth.u_numpy(7, 0, n * nrhs) - 1).reshape(n, nrhs)
+    Yref = oracle.banded_solve(lu_ref, Y.copy())
+    Yd = torch.from_numpy(Y).cuda()
+    Cm.ldiv_(Yd)                                            # AUTO
+    assert relerr(Yd.cpu().numpy(), Yref) < TOL64
+    if nrhs % 2 == 0:
+        Yd = torch.from_numpy(Y).cuda()
+        Cm.ldiv_(Yd, algo=bk.SOLVE_WINDOWED)
+        assert relerr(Yd.cpu().numpy(), Yref) < TOL64
+    Yh = Y.copy()
+    Cm.ldiv_(Yh)                                            # host path (chunked, pipelined)
+    assert relerr(Yh, Yref) < TOL64
+
+
+def test_banded_solve_without_decay_falls_back(bk, oracle, synth):
+    """A factorisation whose backward recurrence does not decay: the windowed solve must refuse,
+    AUTO must take the exact BANSLV-order kernels."""
+    import torch
+    n, nrhs = 600, 2048
+    band = np.zeros((3, n), order="F")
+    band[1, :] = 1.0                 # diagonal
+    band[0, 1:] = 2.0                # super-diagonal: |x_r| grows like 2^r going up
+    Cm = bk.CollocationMatrix(band).lu_()
+    assert Cm.halo == 0
+    lu = band.copy(order="F")
+    assert oracle.banded_lu(lu) == 0
+    Y = np.zeros((n, nrhs))
+    Y[-40:] = (2 * synth.u_numpy(7, 0, 40 * nrhs) - 1).reshape(40, nrhs)
+    ref = oracle.banded_solve(lu, Y.copy())
+    Yd = torch.from_numpy(Y).cuda()
+    Cm.ldiv_(Yd)
+    assert np.array_equal(Yd.cpu().numpy()[-60:], ref[-60:])
+    with pytest.raises(bk.UnsupportedError):
+        Cm.ldiv_(torch.from_numpy(Y).cuda(), algo=bk.SOLVE_WINDOWED)
+
+
+def test_concurrent_streams(bk, oracle, synth):
+    """Kernels are enqueued on the caller's stream: two torch streams, same handles."""
+    import torch
+    B = bk.BSplineBasis(4, synth.breakpoints(3, 1000))
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    xs = [synth.u_torch(5, i << 22, 1 << 22) for i in range(2)]
+    S.evaluate(xs[0], (0,))           # build the tables once
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    outs = []
+    for st, x in zip(streams, xs):
+        with torch.cuda.stream(st):
+            outs.append(S.evaluate(x, (0, 1)))
+    torch.cuda.synchronize()
+    for x, (v, dv) in zip(xs, outs):
+        ref = oracle.spline_eval(0, 4, B.knots(), c, x[:4096].cpu().numpy())
+        assert relerr(v[:4096].cpu().numpy(), ref) < TOL64
+
+
+# ------------------------------------------------------------------------------------------------
+# vector-valued splines (SURVEY §8f N2): M splines sharing one basis
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,k,M", [("plain", 4, 7), ("plain", 6, 300), ("periodic", 4, 2), ("periodic", 3, 65)])
+def test_spline_eval_multi(bk, oracle, synth, kind, k, M):
+    import torch
+    if kind == "plain":
+        B = bk.BSplineBasis(k, synth.breakpoints(3, 120))
+        okind, t = 0, B.knots()
+        x = _points(synth, 30, 5000, -0.05, 1.05, extra=list(t))
+    else:
+        br = 2.0 * synth.breakpoints(8, 121) - 1.0
+        B = bk.PeriodicBSplineBasis(k, br)
+        okind, t = 1, br
+        x = _points(synth, 30, 5000, -4.0, 5.0, extra=list(br))
+    C = (2 * synth.u_numpy(31, 0, len(B) * M) - 1).reshape(len(B), M)
+    SB = bk.SplineBatch(B, C)
+    got = SB(x)
+    assert got.shape == (x.size, M)
+    for m in sorted(set([0, M // 2, M - 1])):
+        ref = oracle.spline_eval(okind, k, t, C[:, m].copy(), x)
+        assert relerr(got[:, m], ref) < TOL64
+    xs = np.sort(x)                                        # sorted points: cached-coefficient path
+    got_s = SB(torch.from_numpy(xs).cuda()).cpu().numpy()
+    assert relerr(got_s[:, M - 1], oracle.spline_eval(okind, k, t, C[:, M - 1].copy(), xs)) < TOL64
+    with pytest.raises(bk.DimensionMismatch):
+        bk.SplineBatch(B, C[:-1])
+
+
+def test_batched_interpolation_then_multi_eval(bk, oracle, synth):
+    """interpolate! on a batch, then evaluate all data sets at once from the device coefficients:
+    closed parametric curve S(a) == S(b) and I.(xs) ≈ ys  (test/periodic.jl:8-23, 176-180)."""
+    import torch
+    n, M = 400, 128
+    xp = 2.0 * synth.breakpoints(8, n + 1)[:-1] - 1.0
+    B = bk.PeriodicBSplineBasis(4, bk.make_knots(xp, 4, bk.Periodic(2.0)))
+    itp = bk.SplineInterpolation(B, xp)
+    Y = (2 * synth.u_numpy(7, 0, n * M) - 1).reshape(n, M)
+    itp.interpolate_(torch.from_numpy(Y).cuda())
+    vals = itp.splines(xp)
+    assert np.max(np.abs(vals - Y)) < 1e-12
+    ends = itp.splines(np.array([-1.0, 1.0]))
+    assert np.max(np.abs(ends[0] - ends[1])) < 1e-13

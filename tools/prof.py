@@ -101,3 +101,14 @@ elif args.what == "cyclic":
             tot += e0.elapsed_time(e1)
     ms = tot / args.reps
     print("cyclic: %.3f ms  %.2f M RHS/s  %.1f GB/s (16 B/elem)" % (ms, nrhs / ms / 1e3, 16 * n * nrhs / ms / 1e6))
+if args.what == "multi":
+    n, k, M = 4096, 6, args.nrhs
+    xdata = synth.breakpoints(6, n)
+    Bi = bk.BSplineBasis(k, bk.make_knots(xdata, k), augment=False)
+    Cc = (2 * synth.u_torch(7, 0, n * M) - 1).reshape(n, M)
+    SB = bk.SplineBatch(Bi, Cc)
+    for label, xs in (("sorted", torch.from_numpy(np.sort(synth.u_numpy(5, 0, 4096))).cuda()),
+                      ("random", synth.u_torch(5, 0, 4096))):
+        ms = timed(lambda: SB(xs), args.reps)
+        print("multi %s: %d splines x %d points: %.3f ms  %.1f GB/s (out + coefs once)" % (
+            label, M, xs.numel(), ms, (8.0 * xs.numel() * M + 8.0 * n * M) / ms / 1e6))
