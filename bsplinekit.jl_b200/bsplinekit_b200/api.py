@@ -711,6 +711,19 @@ class CollocationMatrix:
                 A[i, j] = w[u + i - j, j]
         return A
 
+    def mul(self, X):
+        """C * X for an (n, nrhs) block (RHS index fastest): mul!(Y, C, X) (matrix.jl:91-94).
+        Only before lu_() (which factorises in place, like lu!)."""
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            Xd, on_dev = X.contiguous(), True
+        else:
+            Xd, on_dev = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).cuda(), False
+        if Xd.dtype != torch.float64 or Xd.shape[0] != self.n:
+            raise DimensionMismatch("vectors `x` and `y` must have length %d" % self.n)
+        Y = torch.empty_like(Xd)
+        check(lib.bsk_banded_matvec(self._handle, _ptr(Xd), _ptr(Y), Xd.numel() // self.n, _stream()))
+        return Y if on_dev else Y.cpu().numpy()
+
     def lu_(self):
         """lu!(C) (Collocation/matrix.jl:132-201)."""
         info = C.c_int64(0)

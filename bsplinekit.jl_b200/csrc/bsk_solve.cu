@@ -643,3 +643,81 @@ bsk_status bsk_cyclic_destroy(bsk_cyclic *h) {
 }
 
 }  // extern "C"
+
+// ---- batched banded mat-vec: Y = C * X for interleaved right-hand sides ---------------------------
+// Replaces mul!(y, C::CollocationMatrix, x) (src/Collocation/matrix.jl:91-94, which goes through
+// BandedMatrices' gbmv) for many vectors at once; used e.g. for residuals ||C c - y|| and for the
+// "RHS per time step" pattern  du = A \ (L * u)  (examples/heat.jl:314-328).
+namespace {
+
+template <int BW, int U>
+__global__ void __launch_bounds__(kThreads)
+k_banded_matvec(const double *__restrict__ w, const double *__restrict__ x, double *__restrict__ y,
+                int64_t nrhs, int n) {
+    constexpr int NB = 2 * BW + 1;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const double *px = x + c;
+        double *py = y + c;
+        double win[NB];                      // win[d + BW] = x[r + d]
+#pragma unroll
+        for (int d = 0; d < NB; ++d) win[d] = 0.0;
+#pragma unroll
+        for (int d = 0; d < BW; ++d) win[BW + 1 + d] = (d < n) ? px[(int64_t)d * nrhs] : 0.0;   // x[0..BW-1] -> slots for r = -1
+        for (int r0 = 0; r0 < n; r0 += U) {
+            double nx[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) nx[q] = (r0 + q + BW < n) ? px[(int64_t)(r0 + q + BW) * nrhs] : 0.0;
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int r = r0 + q;
+                if (r < n) {
+#pragma unroll
+                    for (int d = 0; d < NB - 1; ++d) win[d] = win[d + 1];
+                    win[NB - 1] = nx[q];
+                    double acc = 0.0;
+#pragma unroll
+                    for (int d = -BW; d <= BW; ++d) {
+                        const int col = r + d;
+                        const double a = (col >= 0 && col < n) ? __ldg(w + (BW - d) + (size_t)col * NB) : 0.0;
+                        acc = fma(a, win[d + BW], acc);
+                    }
+                    py[(int64_t)r * nrhs] = acc;
+                }
+            }
+        }
+    }
+}
+
+template <int BW>
+bsk_status matvec_t(const bsk_banded *h, const double *d_x, double *d_y, int64_t nrhs, cudaStream_t st) {
+    const int bs = nrhs >= 148 * 2 * 256 ? 128 : 64;
+    int grid = (int)std::max<int64_t>(1, (nrhs + bs - 1) / bs);
+    k_banded_matvec<BW, 8><<<grid, bs, 0, st>>>(h->d_w, d_x, d_y, nrhs, (int)h->n);
+    BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+}  // namespace
+
+extern "C" bsk_status bsk_banded_matvec(const bsk_banded *h, const double *d_x, double *d_y, int64_t nrhs,
+                                        void *stream) {
+    BSK_REQUIRE(h && (nrhs == 0 || (d_x && d_y)), BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(!h->factored, BSK_ERR_ARGUMENT,
+                "the band data now holds the LU factors (lu! works in place): apply C before factorising, or keep a copy");
+    BSK_REQUIRE(d_x != d_y, BSK_ERR_ARGUMENT, "x and y must not alias");
+    if (nrhs == 0) return BSK_OK;
+    BSK_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->l) {
+        case 0: return matvec_t<0>(h, d_x, d_y, nrhs, st);
+        case 1: return matvec_t<1>(h, d_x, d_y, nrhs, st);
+        case 2: return matvec_t<2>(h, d_x, d_y, nrhs, st);
+        case 3: return matvec_t<3>(h, d_x, d_y, nrhs, st);
+        case 4: return matvec_t<4>(h, d_x, d_y, nrhs, st);
+        case 5: return matvec_t<5>(h, d_x, d_y, nrhs, st);
+        case 6: return matvec_t<6>(h, d_x, d_y, nrhs, st);
+    }
+    set_error("unsupported bandwidth %d", h->l);
+    return BSK_ERR_UNSUPPORTED;
+}

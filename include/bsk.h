@@ -197,6 +197,9 @@ bsk_status bsk_banded_halo(const bsk_banded *h, int32_t *halo);
 bsk_status bsk_banded_solve(const bsk_banded *h, double *d_rhs, int64_t nrhs, int32_t algo,
                             void *stream);
 bsk_status bsk_banded_solve_host(const bsk_banded *h, double *h_rhs, int64_t nrhs, int32_t algo);
+/* mul!(Y, C, X) for nrhs interleaved vectors — Collocation/matrix.jl:91-94 (BandedMatrices gbmv in the
+ * reference).  Only before bsk_banded_lu (which overwrites the band data, like lu!).  X and Y must not alias. */
+bsk_status bsk_banded_matvec(const bsk_banded *h, const double *d_x, double *d_y, int64_t nrhs, void *stream);
 bsk_status bsk_banded_destroy(bsk_banded *h);
 
 /* ---- cyclic tridiagonal (periodic cubic interpolation) -------------------------------

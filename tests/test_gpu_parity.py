@@ -756,3 +756,19 @@ def test_batched_interpolation_then_multi_eval(bk, oracle, synth):
     assert np.max(np.abs(vals - Y)) < 1e-12
     ends = itp.splines(np.array([-1.0, 1.0]))
     assert np.max(np.abs(ends[0] - ends[1])) < 1e-13
+
+
+@pytest.mark.parametrize("k,n,nrhs", [(4, 300, 37), (6, 4096, 1024), (8, 500, 3), (2, 64, 5)])
+def test_banded_matvec(bk, oracle, synth, k, n, nrhs):
+    """mul!(Y, C, X) on batches (src/Collocation/matrix.jl:91-94) and C * (F \\ y) ≈ y (test/splines.jl:170-187)."""
+    xdata, t, B, Cm, ref = _interp_system(bk, oracle, synth, n, k)
+    X = (2 * synth.u_numpy(17, 0, n * nrhs) - 1).reshape(n, nrhs)
+    Y = Cm.mul(X)
+    Yref = oracle.banded_matvec(ref, X)
+    assert relerr(Y, Yref) < TOL64
+    Cm2 = bk.CollocationMatrix(ref.copy(order="F")).lu_()
+    Z = Y.copy()
+    Cm2.ldiv_(Z, algo=bk.SOLVE_TWOPASS)
+    assert np.max(np.abs(Z - X)) < 1e-11
+    with pytest.raises(bk.ArgumentError):
+        Cm2.mul(X)
