@@ -498,9 +498,11 @@ bsk_status build_pp(bsk_spline *s) {
     {
         const int RECV = ((k + VPA - 1) / VPA) * VPA;
         const int NCH = RECV / VPA;
+        const int XI = (k == 1) ? 1 : 0;
         const size_t budget = 214 * 1024;
         const int nbp = (int)nrec - 1;                         // interior breakpoints
         const double a = plo[0], bb = phi[nrec - 1];
+        // raw-bit helpers: flag = LSB of the last coefficient; flagged: last slot = (index << 1) | 1
         auto setflag = [](T v, int f) {
             if (sizeof(T) == 8) {
                 uint64_t u; double d = (double)v; memcpy(&u, &d, 8);
@@ -509,14 +511,22 @@ bsk_status build_pp(bsk_spline *s) {
             uint32_t u; float g = (float)v; memcpy(&u, &g, 4);
             u = (u & ~1u) | (uint32_t)f; memcpy(&g, &u, 4); return (T)g;
         };
-        // first guess: one side entry per interior breakpoint; shrink if the build overflows
-        int64_t nc = (int64_t)((budget - std::min<size_t>(budget, (size_t)(nbp + 8) * (RECV + 1) * sizeof(T))) /
-                               (RECV * sizeof(T) + 2));
+        auto index_bits = [](uint32_t idx) {
+            const uint32_t raw = (idx << 1) | 1u;
+            T out;
+            if (sizeof(T) == 8) { uint64_t u = raw; double d; memcpy(&d, &u, 8); out = (T)d; }
+            else { float g; memcpy(&g, &raw, 4); out = (T)g; }
+            return out;
+        };
+        const uint32_t kMulti = 0x7FFFFFFFu;
+        // first guess: one side entry (two pieces) per interior breakpoint; shrink if it overflows
+        int64_t nc = (int64_t)((budget - std::min<size_t>(budget, (size_t)(nbp + 8) * 2 * RECV * sizeof(T))) /
+                               (RECV * sizeof(T)));
         nc = std::min<int64_t>(nc, 16 * nrec);
         nc = std::min<int64_t>(nc, 60000);
         // Too many intervals for shared memory: keep the same tables in global memory (L2-resident,
-        // ~4.5 cells per interval); the side index is 16-bit, hence the cap on the interval count.
-        const bool in_global = nc < 3 * nrec && nrec <= 30000 && getenv("BSK_NO_GLOBAL_CELL") == nullptr;
+        // ~4.5 cells per interval).
+        const bool in_global = nc < 3 * nrec && nrec <= 400000 && getenv("BSK_NO_GLOBAL_CELL") == nullptr;
         if (in_global) nc = (nrec * 9) / 2;
         for (int attempt = 0; attempt < 6 && nc >= 3 * nrec && nc >= 8; ++attempt, nc = nc * 9 / 10) {
             const T x0 = (T)a;
@@ -524,8 +534,7 @@ bsk_status build_pp(bsk_spline *s) {
             const T scT = (T)((double)nc / (bb - a));
             const double cw = (double)cwT;
             const double margin = (sizeof(T) == 4 ? 0.02 : 1e-6) * cw;
-            std::vector<T> crec((size_t)nc * RECV, (T)0), rcv, xs;     // cell-major while building
-            std::vector<uint16_t> sidx(nc, 0);
+            std::vector<T> crec((size_t)nc * RECV, (T)0), side_l, side_r;     // cell-major while building
             int nmulti = 0;
             for (int64_t c = 0; c < nc; ++c) {
                 const double e0 = a + (double)c * cw, e1 = a + (double)(c + 1) * cw;
@@ -537,44 +546,47 @@ bsk_status build_pp(bsk_spline *s) {
                 if (c == nc - 1) nb = (int)nrec - 1 - pl;        // everything up to the right end
                 double cf[BSK_MAXK];
                 taylor(pid[pl], (double)centerT, cf);
-                for (int m = 0; m < k; ++m) crec[c * RECV + m] = (T)cf[m];
-                crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], nb > 0 ? 1 : 0);
-                if (nb == 1 && xs.size() < 65000) {
-                    sidx[c] = (uint16_t)xs.size();
-                    xs.push_back((T)plo[pl + 1]);
+                if (nb == 0) {
+                    for (int m = 0; m < k; ++m) crec[c * RECV + m] = (T)cf[m];
+                    crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 0);
+                } else if (nb == 1) {
+                    const uint32_t j = (uint32_t)(side_l.size() / RECV);
+                    crec[c * RECV + XI] = (T)plo[pl + 1];
+                    crec[c * RECV + k - 1] = index_bits(j);
+                    size_t base = side_l.size();
+                    side_l.resize(base + RECV, (T)0);
+                    side_r.resize(base + RECV, (T)0);
+                    for (int m = 0; m < k; ++m) side_l[base + m] = (T)cf[m];
                     taylor(pid[pl + 1], (double)centerT, cf);
-                    size_t base = rcv.size();
-                    rcv.resize(base + RECV, (T)0);
-                    for (int m = 0; m < k; ++m) rcv[base + m] = (T)cf[m];
-                } else if (nb >= 1) {
-                    sidx[c] = 0xFFFF;
+                    for (int m = 0; m < k; ++m) side_r[base + m] = (T)cf[m];
+                } else {
+                    crec[c * RECV + k - 1] = index_bits(kMulti);
                     ++nmulti;
                 }
             }
-            if (xs.empty()) { xs.push_back((T)0); rcv.resize(RECV, (T)0); }
-            const int nside = (int)xs.size();
-            const size_t smem = (size_t)nc * RECV * sizeof(T) + (size_t)nside * RECV * sizeof(T) +
-                                (size_t)((nside + VPA - 1) / VPA) * VPA * sizeof(T) + (size_t)nc * 2 + 16;
+            if (side_l.empty()) { side_l.resize(RECV, (T)0); side_r.resize(RECV, (T)0); }
+            const int nside = (int)(side_l.size() / RECV);
+            const size_t smem = ((size_t)nc + 2 * (size_t)nside) * RECV * sizeof(T) + 16;
             if (!in_global && smem > 226 * 1024) continue;      // retry with fewer cells
             if (nmulti * 50 > nc) break;                        // clustered knots: not worth it
             // chunk-major device layout (see CellView in bsk_eval_cell.cu)
-            std::vector<T> crec_cm(crec.size()), rc_cm(rcv.size());
+            std::vector<T> crec_cm(crec.size()), rc_cm(2 * side_l.size());
             for (int64_t c = 0; c < nc; ++c)
                 for (int w = 0; w < NCH; ++w)
                     for (int e = 0; e < VPA; ++e) crec_cm[((size_t)w * nc + c) * VPA + e] = crec[c * RECV + w * VPA + e];
-            for (int64_t j = 0; j < nside; ++j)
-                for (int w = 0; w < NCH; ++w)
-                    for (int e = 0; e < VPA; ++e) rc_cm[((size_t)w * nside + j) * VPA + e] = rcv[j * RECV + w * VPA + e];
-            for (void **p : {&s->d_cell_rec, &s->d_cell_rc, &s->d_cell_xi, (void **)&s->d_cell_idx})
+            for (int side = 0; side < 2; ++side) {
+                const std::vector<T> &src = side ? side_r : side_l;
+                for (int64_t j = 0; j < nside; ++j)
+                    for (int w = 0; w < NCH; ++w)
+                        for (int e = 0; e < VPA; ++e)
+                            rc_cm[(((size_t)side * NCH + w) * nside + j) * VPA + e] = src[j * RECV + w * VPA + e];
+            }
+            for (void **p : {&s->d_cell_rec, &s->d_cell_rc})
                 if (*p) { cudaFree(*p); *p = nullptr; }
             BSK_CUDA(cudaMalloc(&s->d_cell_rec, crec_cm.size() * sizeof(T)));
             BSK_CUDA(cudaMemcpy(s->d_cell_rec, crec_cm.data(), crec_cm.size() * sizeof(T), cudaMemcpyHostToDevice));
             BSK_CUDA(cudaMalloc(&s->d_cell_rc, rc_cm.size() * sizeof(T)));
             BSK_CUDA(cudaMemcpy(s->d_cell_rc, rc_cm.data(), rc_cm.size() * sizeof(T), cudaMemcpyHostToDevice));
-            BSK_CUDA(cudaMalloc(&s->d_cell_xi, xs.size() * sizeof(T)));
-            BSK_CUDA(cudaMemcpy(s->d_cell_xi, xs.data(), xs.size() * sizeof(T), cudaMemcpyHostToDevice));
-            BSK_CUDA(cudaMalloc((void **)&s->d_cell_idx, sidx.size() * 2));
-            BSK_CUDA(cudaMemcpy(s->d_cell_idx, sidx.data(), sidx.size() * 2, cudaMemcpyHostToDevice));
             s->cell_ncell = (int)nc;
             s->cell_nside = nside;
             s->cell_x0 = (double)x0;
@@ -866,7 +878,7 @@ bsk_status bsk_spline_create(const bsk_basis *b, const void *h_coefs, int64_t nc
     bsk_spline *s = new bsk_spline();
     s->basis = nullptr; s->d_coefs = nullptr; s->owns_coefs = true; s->d_pp = nullptr;
     s->d_pp_lut = nullptr; s->pp_valid = false; s->pp_nrec = 0; s->pp_ncell = 0; s->pp_scale = 0; s->pp_rec = 0;
-    s->d_cell_rec = s->d_cell_rc = s->d_cell_xi = nullptr; s->d_cell_idx = nullptr; s->cell_valid = false;
+    s->d_cell_rec = s->d_cell_rc = nullptr; s->cell_valid = false;
     int ekind = b->kind == BSK_BASIS_PERIODIC ? BSK_BASIS_PERIODIC : BSK_BASIS_PLAIN;
     bsk_status rc = clone_basis(b, ekind, b->k, b->h_knots, &s->basis);
     if (rc != BSK_OK) { delete s; return rc; }
@@ -914,8 +926,6 @@ bsk_status bsk_spline_destroy(bsk_spline *s) {
     if (s->d_pp_lut) cudaFree(s->d_pp_lut);
     if (s->d_cell_rec) cudaFree(s->d_cell_rec);
     if (s->d_cell_rc) cudaFree(s->d_cell_rc);
-    if (s->d_cell_xi) cudaFree(s->d_cell_xi);
-    if (s->d_cell_idx) cudaFree(s->d_cell_idx);
     if (s->basis) bsk_basis_destroy(s->basis);
     delete s;
     return BSK_OK;
@@ -965,7 +975,7 @@ bsk_status bsk_spline_derivative(const bsk_spline *s, int32_t nd, bsk_spline **o
     bsk_spline *d = new bsk_spline();
     d->basis = nullptr; d->d_coefs = nullptr; d->owns_coefs = true; d->d_pp = nullptr;
     d->d_pp_lut = nullptr; d->pp_valid = false; d->pp_nrec = 0; d->pp_ncell = 0; d->pp_scale = 0; d->pp_rec = 0;
-    d->d_cell_rec = d->d_cell_rc = d->d_cell_xi = nullptr; d->d_cell_idx = nullptr; d->cell_valid = false;
+    d->d_cell_rec = d->d_cell_rc = nullptr; d->cell_valid = false;
     bsk_status rc = clone_basis(b, kind ? BSK_BASIS_PERIODIC : BSK_BASIS_PLAIN, b->k - nd, tk, &d->basis);
     if (rc != BSK_OK) { delete d; return rc; }
     d->ncoef = (int64_t)dc.size();

@@ -30,10 +30,14 @@ constexpr int kCellThreads = 1024;
 template <typename T> struct Bits;
 template <> struct Bits<double> {
     static __device__ __forceinline__ int flag(double v) { return __double2loint(v) & 1; }
+    // flagged cells: last slot = (side index << 1) | 1 as raw bits
+    static __device__ __forceinline__ unsigned index(double v) { return ((unsigned)__double2loint(v)) >> 1; }
 };
 template <> struct Bits<float> {
     static __device__ __forceinline__ int flag(float v) { return __float_as_int(v) & 1; }
+    static __device__ __forceinline__ unsigned index(float v) { return ((unsigned)__float_as_int(v)) >> 1; }
 };
+constexpr unsigned kMultiKnotCell = 0x7FFFFFFFu;     // cell with two or more knots -> interval table
 
 template <int K, typename T> struct CellRec {
     static constexpr int VPA = 16 / (int)sizeof(T);
@@ -45,10 +49,11 @@ struct CellView {
     // Both tables are stored CHUNK-MAJOR: the w-th 16-byte chunk of record c sits at
     // [(w * count + c) * VEC], so that one LDS.128 of a warp spreads over all eight 16-byte
     // bank groups (a 32-byte record stride would only ever touch every other group).
+    // Unflagged cell: record = Taylor coefficients about the cell centre.  Flagged cell (a knot
+    // inside): slot XI = the knot, last slot = (side index << 1) | 1; the two polynomial pieces
+    // (left / right of the knot, both about the cell centre) are side[0][j] and side[1][j].
     const T *rec;             // (RECV/VEC) x ncell x VEC
-    const T *rc;              // (RECV/VEC) x nside x VEC   right-hand pieces of flagged cells
-    const T *xi;              // nside          the knot inside the flagged cell
-    const uint16_t *sideidx;  // ncell          0xFFFF: two or more knots -> fallback
+    const T *rc;              // 2 x (RECV/VEC) x nside x VEC
     int ncell, nside;
     T x0, scale, cw;
     T a, b;                   // domain
@@ -113,8 +118,6 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
     //      in place from global memory through L1/L2 by the very same code (STAGE = 0) ----------
     T *const d_rec = (T *)smem;
     T *const d_rc = d_rec + (size_t)cv.ncell * RECV;
-    T *const d_xi = d_rc + (size_t)cv.nside * RECV;
-    uint16_t *const d_idx = (uint16_t *)(d_xi + ((cv.nside + VEC - 1) / VEC) * VEC);
     if (STAGE) {
         const int4 *src = (const int4 *)cv.rec;
         int4 *dst = (int4 *)d_rec;
@@ -122,16 +125,13 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
         for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
         src = (const int4 *)cv.rc;
         dst = (int4 *)d_rc;
-        const int m16 = cv.nside * RECV / VEC;
+        const int m16 = 2 * cv.nside * RECV / VEC;
         for (int i = threadIdx.x; i < m16; i += blockDim.x) dst[i] = src[i];
-        for (int i = threadIdx.x; i < cv.nside; i += blockDim.x) d_xi[i] = cv.xi[i];
-        for (int i = threadIdx.x; i < cv.ncell; i += blockDim.x) d_idx[i] = cv.sideidx[i];
         __syncthreads();
     }
     const T *const s_rec = STAGE ? d_rec : cv.rec;
     const T *const s_rc = STAGE ? d_rc : cv.rc;
-    const T *const s_xi = STAGE ? d_xi : cv.xi;
-    const uint16_t *const s_idx = STAGE ? d_idx : cv.sideidx;
+    constexpr int XI = (K == 1) ? 1 : 0;                 // slot of the knot in a flagged record
 
     const T xa = cv.a, xb = cv.b, x0 = cv.x0, scale = cv.scale, cw = cv.cw;
     const int ncell1 = cv.ncell - 1;
@@ -157,6 +157,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
             int c = (int)((xs - x0) * scale);
             c = c < 0 ? 0 : (c > ncell1 ? ncell1 : c);
             T cm[K];
+            T xi_k1 = (T)0;
             {
                 T buf[RECV];
                 const int4 *R4 = (const int4 *)s_rec + c;
@@ -167,19 +168,22 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
                 }
 #pragma unroll
                 for (int m = 0; m < K; ++m) cm[m] = buf[m];
+                if (K == 1) xi_k1 = buf[1];
             }
             T u = xs - fma((T)c + (T)0.5, cw, x0);
             if (Bits<T>::flag(cm[K - 1])) {
-                const int j = s_idx[c];
-                if (j == 0xFFFF) {
+                const unsigned j = Bits<T>::index(cm[K - 1]);
+                if (j == kMultiKnotCell) {
                     T cm2[K], u2;              // separate locals: keep cm[] itself in registers
                     fallback_interval<K, T>(pv, xs, cm2, &u2);
 #pragma unroll
                     for (int m = 0; m < K; ++m) cm[m] = cm2[m];
                     u = u2;
-                } else if (!(xs < s_xi[j])) {
+                } else {
+                    const T xik = (K == 1) ? xi_k1 : cm[XI];
+                    const int right = (xs < xik) ? 0 : 1;
                     T buf[RECV];
-                    const int4 *R4 = (const int4 *)s_rc + j;
+                    const int4 *R4 = (const int4 *)s_rc + (size_t)right * (RECV / VEC) * cv.nside + j;
 #pragma unroll
                     for (int w = 0; w < RECV / VEC; ++w) {
                         int4 r = R4[w * cv.nside];
@@ -250,8 +254,6 @@ bsk_status launch_cell_k(const bsk_spline *s, const KnotView<T> &kv, const T *d_
     CellView<T> cv;
     cv.rec = (const T *)s->d_cell_rec;
     cv.rc = (const T *)s->d_cell_rc;
-    cv.xi = (const T *)s->d_cell_xi;
-    cv.sideidx = s->d_cell_idx;
     cv.ncell = s->cell_ncell;
     cv.nside = s->cell_nside;
     cv.x0 = (T)s->cell_x0;

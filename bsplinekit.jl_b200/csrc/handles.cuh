@@ -87,8 +87,7 @@ struct bsk_spline {
     int pp_rec;
     bool pp_valid;
     // uniform-cell table (bsk_eval_cell.cu)
-    void *d_cell_rec, *d_cell_rc, *d_cell_xi;
-    uint16_t *d_cell_idx;
+    void *d_cell_rec, *d_cell_rc;
     int cell_ncell, cell_nside;
     double cell_x0, cell_b, cell_scale, cell_cw;
     size_t cell_smem;
