@@ -524,10 +524,16 @@ bsk_status build_pp(bsk_spline *s) {
                                (RECV * sizeof(T)));
         nc = std::min<int64_t>(nc, 16 * nrec);
         nc = std::min<int64_t>(nc, 60000);
-        // Too many intervals for shared memory: keep the same tables in global memory (L2-resident,
-        // ~4.5 cells per interval).
+        // Too many intervals for shared memory: keep the same tables in global memory, record-major
+        // (one 32-byte L2 sector per cubic F64 / order-8 F32 record) and L2-resident.
         const bool in_global = nc < 3 * nrec && nrec <= 400000 && getenv("BSK_NO_GLOBAL_CELL") == nullptr;
-        if (in_global) nc = (nrec * 9) / 2;
+        if (in_global) {
+            const char *e = getenv("BSK_GLOBAL_CELL_MULT2");        // cells per interval, x2
+            const int m2 = e ? std::max(6, atoi(e)) : 32;
+            nc = (nrec * m2) / 2;                                   // 16 cells per interval ...
+            const int64_t cap = (32ll << 20) / (int64_t)(RECV * sizeof(T));   // ... within 32 MB (L2-resident)
+            nc = std::max<int64_t>(std::min(nc, cap), 3 * nrec);
+        }
         for (int attempt = 0; attempt < 6 && nc >= 3 * nrec && nc >= 8; ++attempt, nc = nc * 9 / 10) {
             const T x0 = (T)a;
             const T cwT = (T)((bb - a) / (double)nc);
@@ -569,17 +575,20 @@ bsk_status build_pp(bsk_spline *s) {
             const size_t smem = ((size_t)nc + 2 * (size_t)nside) * RECV * sizeof(T) + 16;
             if (!in_global && smem > 226 * 1024) continue;      // retry with fewer cells
             if (nmulti * 50 > nc) break;                        // clustered knots: not worth it
-            // chunk-major device layout (see CellView in bsk_eval_cell.cu)
+            // device layout: chunk-major for shared memory, record-major for global (CellView)
             std::vector<T> crec_cm(crec.size()), rc_cm(2 * side_l.size());
             for (int64_t c = 0; c < nc; ++c)
                 for (int w = 0; w < NCH; ++w)
-                    for (int e = 0; e < VPA; ++e) crec_cm[((size_t)w * nc + c) * VPA + e] = crec[c * RECV + w * VPA + e];
+                    for (int e = 0; e < VPA; ++e)
+                        crec_cm[in_global ? (size_t)c * RECV + w * VPA + e : ((size_t)w * nc + c) * VPA + e] =
+                            crec[c * RECV + w * VPA + e];
             for (int side = 0; side < 2; ++side) {
                 const std::vector<T> &src = side ? side_r : side_l;
                 for (int64_t j = 0; j < nside; ++j)
                     for (int w = 0; w < NCH; ++w)
                         for (int e = 0; e < VPA; ++e)
-                            rc_cm[(((size_t)side * NCH + w) * nside + j) * VPA + e] = src[j * RECV + w * VPA + e];
+                            rc_cm[in_global ? ((size_t)side * nside + j) * RECV + w * VPA + e
+                                            : (((size_t)side * NCH + w) * nside + j) * VPA + e] = src[j * RECV + w * VPA + e];
             }
             for (void **p : {&s->d_cell_rec, &s->d_cell_rc})
                 if (*p) { cudaFree(*p); *p = nullptr; }

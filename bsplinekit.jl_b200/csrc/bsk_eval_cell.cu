@@ -7,8 +7,8 @@
 // covers the cell's left edge.  The cell index is ONE multiply-add and a float->int conversion:
 // the O(1) arithmetic lookup of the uniform-grid case, extended to non-uniform knots.
 // Cells that contain a knot carry a flag (the least significant mantissa bit of the last
-// coefficient) and an entry in a side table {knot, right-hand piece}; the knot is then compared
-// exactly, so the selected knot interval is exactly the one `searchsortedlast` finds
+// slot), the knot itself and the index of a side-table entry {left piece, right piece}; the
+// knot is then compared exactly, so the selected knot interval is exactly the one `searchsortedlast` finds
 // (src/BSplines/evaluate_all.jl:102-119) whatever the rounding of the cell index.  Cells with
 // two or more knots (clustered knots) fall back to the per-interval table in global memory.
 //
@@ -46,9 +46,10 @@ template <int K, typename T> struct CellRec {
 
 template <typename T>
 struct CellView {
-    // Both tables are stored CHUNK-MAJOR: the w-th 16-byte chunk of record c sits at
+    // Shared-memory tables are stored CHUNK-MAJOR: the w-th 16-byte chunk of record c sits at
     // [(w * count + c) * VEC], so that one LDS.128 of a warp spreads over all eight 16-byte
-    // bank groups (a 32-byte record stride would only ever touch every other group).
+    // bank groups (a 32-byte record stride would only ever touch every other group).  Tables
+    // that stay in global memory are RECORD-MAJOR instead: a 32-byte record is one L2 sector.
     // Unflagged cell: record = Taylor coefficients about the cell centre.  Flagged cell (a knot
     // inside): slot XI = the knot, last slot = (side index << 1) | 1; the two polynomial pieces
     // (left / right of the knot, both about the cell centre) are side[0][j] and side[1][j].
@@ -146,52 +147,71 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
         T xv[VEC];
         memcpy(xv, &raw, 16);
         T res[NOUT][VEC];
+        // phase 1: all cell-record gathers of this vector are issued before any of them is used
+        T xs_[VEC], rec_[VEC][RECV];
+        int c_[VEC];
+        bool out_[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
             const T xq = xv[q];
-            const bool isnan_ = !(xq == xq);
             bool outside;                  // plain: zone != 0; periodic: outside the main period
             if (KIND == 1) outside = !(xq >= xa && xq < xb);
             else outside = !(xq >= xa && xq <= xb);
             const T xs = outside ? xa : xq;
             int c = (int)((xs - x0) * scale);
             c = c < 0 ? 0 : (c > ncell1 ? ncell1 : c);
-            T cm[K];
-            T xi_k1 = (T)0;
-            {
-                T buf[RECV];
-                const int4 *R4 = (const int4 *)s_rec + c;
+            xs_[q] = xs;
+            c_[q] = c;
+            out_[q] = outside;
+            // STAGE: chunk-major (bank spread); global: record-major (one 32-byte sector)
+            const int4 *R4 = (const int4 *)s_rec + (STAGE ? (size_t)c : (size_t)c * (RECV / VEC));
+            const int cs = STAGE ? cv.ncell : 1;
 #pragma unroll
-                for (int w = 0; w < RECV / VEC; ++w) {
-                    int4 r = R4[w * cv.ncell];
-                    memcpy(&buf[w * VEC], &r, 16);
-                }
-#pragma unroll
-                for (int m = 0; m < K; ++m) cm[m] = buf[m];
-                if (K == 1) xi_k1 = buf[1];
+            for (int w = 0; w < RECV / VEC; ++w) {
+                int4 r = R4[w * cs];
+                memcpy(&rec_[q][w * VEC], &r, 16);
             }
-            T u = xs - fma((T)c + (T)0.5, cw, x0);
-            if (Bits<T>::flag(cm[K - 1])) {
-                const unsigned j = Bits<T>::index(cm[K - 1]);
-                if (j == kMultiKnotCell) {
-                    T cm2[K], u2;              // separate locals: keep cm[] itself in registers
-                    fallback_interval<K, T>(pv, xs, cm2, &u2);
+        }
+        // phase 2: cells holding a knot -> exact comparison with the knot, gather of the piece on
+        // the right side of it (again all gathers of the vector in flight together)
+        bool multi_[VEC];
 #pragma unroll
-                    for (int m = 0; m < K; ++m) cm[m] = cm2[m];
-                    u = u2;
+        for (int q = 0; q < VEC; ++q) {
+            const T last = rec_[q][K - 1];
+            multi_[q] = false;
+            if (Bits<T>::flag(last)) {
+                const unsigned j = Bits<T>::index(last);
+                if (j == kMultiKnotCell) {
+                    multi_[q] = true;
                 } else {
-                    const T xik = (K == 1) ? xi_k1 : cm[XI];
-                    const int right = (xs < xik) ? 0 : 1;
-                    T buf[RECV];
-                    const int4 *R4 = (const int4 *)s_rc + (size_t)right * (RECV / VEC) * cv.nside + j;
+                    const int right = (xs_[q] < rec_[q][XI]) ? 0 : 1;
+                    const int4 *R4 = (const int4 *)s_rc + (size_t)right * (RECV / VEC) * cv.nside +
+                                     (STAGE ? (size_t)j : (size_t)j * (RECV / VEC));
+                    const int cs = STAGE ? cv.nside : 1;
 #pragma unroll
                     for (int w = 0; w < RECV / VEC; ++w) {
-                        int4 r = R4[w * cv.nside];
-                        memcpy(&buf[w * VEC], &r, 16);
+                        int4 r = R4[w * cs];
+                        memcpy(&rec_[q][w * VEC], &r, 16);
                     }
-#pragma unroll
-                    for (int m = 0; m < K; ++m) cm[m] = buf[m];
                 }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            const T xq = xv[q];
+            const bool isnan_ = !(xq == xq);
+            const bool outside = out_[q];
+            const T xs = xs_[q];
+            T cm[K];
+#pragma unroll
+            for (int m = 0; m < K; ++m) cm[m] = rec_[q][m];
+            T u = xs - fma((T)c_[q] + (T)0.5, cw, x0);
+            if (multi_[q]) {
+                T cm2[K], u2;              // separate locals: keep cm[] itself in registers
+                fallback_interval<K, T>(pv, xs, cm2, &u2);
+#pragma unroll
+                for (int m = 0; m < K; ++m) cm[m] = cm2[m];
+                u = u2;
             }
             T r1[NOUT];
             horner_outputs<K, T, DMASK>(cm, u, outs, r1);
