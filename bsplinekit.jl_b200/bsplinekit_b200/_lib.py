@@ -94,6 +94,7 @@ SIGNATURES = {
     "bsk_banded_solve": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "bsk_banded_solve_host": (_i32, [_vp, _vp, _i64, _i32]),
     "bsk_banded_matvec": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "bsk_banded_matvec_solve": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "bsk_banded_destroy": (_i32, [_vp]),
     "bsk_cyclic_create": (_i32, [_vp, _vp, _vp, _i64, _i32, _pp]),
     "bsk_cyclic_create_device": (_i32, [_vp, _vp, _vp, _i64, _i32, _pp]),

@@ -756,6 +756,22 @@ class CollocationMatrix:
         check(lib.bsk_banded_solve_host(self._handle, Y.ctypes.data_as(C.c_void_p), Y.size // self.n, algo))
         return Y
 
+    def ldiv_mul(self, L, U, out=None):
+        """out = F \\ (L * U) in one pass: the `mul!(y, L, u); ldiv!(du, F, y)` pair of a collocation
+        time step (examples/heat.jl:314-328).  `self` is factorised, `L` is not; U is an (n, nrhs)
+        float64 CUDA block (RHS index fastest) and is left untouched."""
+        if not (isinstance(U, torch.Tensor) and U.is_cuda and U.dtype == torch.float64 and U.is_contiguous()):
+            raise ArgumentError("U must be a contiguous float64 CUDA tensor")
+        if U.shape[0] != self.n or L.n != self.n:
+            raise DimensionMismatch("vectors `x` and `y` must have length %d" % self.n)
+        if out is None:
+            out = torch.empty_like(U)
+        elif not (out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.shape == U.shape):
+            raise ArgumentError("out must be a contiguous float64 CUDA tensor of the shape of U")
+        nrhs = U.numel() // self.n if self.n else 0
+        check(lib.bsk_banded_matvec_solve(self._handle, L._handle, _ptr(U), _ptr(out), nrhs, _stream()))
+        return out
+
 
 class CyclicTridiagonalMatrix:
     """CyclicTridiagonalMatrix(a, b, c) + ldiv! (Collocation/cyclic.jl:21-33,112-197),

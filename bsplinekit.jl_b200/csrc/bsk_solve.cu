@@ -413,6 +413,7 @@ static bsk_status banded_alloc(int64_t n, int32_t l, int32_t u, int32_t device, 
     BSK_CUDA(cudaSetDevice(device));
     bsk_banded *h = new bsk_banded();
     h->device = device; h->n = n; h->l = l; h->u = u; h->factored = false; h->halo = 0; h->halo_f = 0;
+    h->d_mrec = nullptr; h->mrec_bw = -1; h->mrec_npad = 0;
     h->d_w = h->d_lrow = h->d_urow = h->d_dinv = h->d_diag = h->d_urow_s = h->d_lrec = h->d_urec = nullptr;
     h->n_pad = 0;
     size_t nw = (size_t)(l + u + 1) * n, nb = (size_t)std::max(1, l) * n;
@@ -528,6 +529,45 @@ bsk_status bsk_banded_solve(const bsk_banded *h, double *d_rhs, int64_t nrhs, in
     return BSK_ERR_UNSUPPORTED;
 }
 
+// du = F \ (Lm * u) in one pass (the mul! + ldiv! pair of a collocation time step,
+// examples/heat.jl:314-328).  Falls back to bsk_banded_matvec + bsk_banded_solve when the fused
+// kernel does not apply (bandwidth > 4, odd shapes, no validated halo).
+bsk_status bsk_banded_matvec_solve(const bsk_banded *lu, const bsk_banded *Lm, const double *d_u, double *d_out,
+                                   int64_t nrhs, void *stream) {
+    BSK_REQUIRE(lu && Lm && (nrhs == 0 || (d_u && d_out)), BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(lu->factored, BSK_ERR_ARGUMENT, "matrix is not factorised: call bsk_banded_lu first");
+    BSK_REQUIRE(!Lm->factored, BSK_ERR_ARGUMENT, "the matrix to apply holds LU factors (lu! works in place)");
+    BSK_REQUIRE(lu->n == Lm->n, BSK_ERR_DIMENSION, "matrices have different sizes (%lld, %lld)", (long long)lu->n,
+                (long long)Lm->n);
+    BSK_REQUIRE(lu->device == Lm->device, BSK_ERR_ARGUMENT, "matrices live on different devices");
+    BSK_REQUIRE(d_u != d_out, BSK_ERR_ARGUMENT, "u and du must not alias");
+    if (nrhs == 0) return BSK_OK;
+    BSK_CUDA(cudaSetDevice(lu->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool shape_ok = lu->halo > 0 && lu->l <= 4 && Lm->l <= lu->l && nrhs % 32 == 0 && nrhs >= 2048 &&
+                          (((uintptr_t)d_u) & 127) == 0 && (((uintptr_t)d_out) & 15) == 0 &&
+                          getenv("BSK_NO_FUSED") == nullptr;
+    if (shape_ok) {
+        bsk_banded *L = const_cast<bsk_banded *>(Lm);
+        static std::mutex mu;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (!L->d_mrec || L->mrec_bw != lu->l || L->mrec_npad != lu->n_pad) {
+                if (L->d_mrec) { cudaFree(L->d_mrec); L->d_mrec = nullptr; }
+                bsk_status rc = windowed_matrec(L, lu->l, lu->n_pad, &L->d_mrec);
+                if (rc != BSK_OK) return rc;
+                L->mrec_bw = lu->l;
+                L->mrec_npad = lu->n_pad;
+            }
+        }
+        bsk_status rc = windowed_solve_fused(lu, L->d_mrec, d_u, d_out, nrhs / 32, nrhs, st);
+        if (rc != BSK_ERR_UNSUPPORTED) return rc;
+    }
+    bsk_status rc = bsk_banded_matvec(Lm, d_u, d_out, nrhs, stream);
+    if (rc != BSK_OK) return rc;
+    return bsk_banded_solve(lu, d_out, nrhs, BSK_SOLVE_AUTO, stream);
+}
+
 bsk_status bsk_banded_destroy(bsk_banded *h) {
     if (!h) return BSK_OK;
     cudaSetDevice(h->device);
@@ -539,6 +579,7 @@ bsk_status bsk_banded_destroy(bsk_banded *h) {
     if (h->d_urec) cudaFree(h->d_urec);
     if (h->d_dinv) cudaFree(h->d_dinv);
     if (h->d_diag) cudaFree(h->d_diag);
+    if (h->d_mrec) cudaFree(h->d_mrec);
     delete h;
     return BSK_OK;
 }

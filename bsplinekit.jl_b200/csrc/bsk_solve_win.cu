@@ -25,6 +25,7 @@
 // with conflict-free broadcast loads.
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include <cuda.h>            // CUtensorMap (types only; the encoder is fetched at run time)
 
@@ -378,18 +379,26 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 constexpr int kTmemCols = 256;            // per CTA (power of two); 2 CTAs per SM
 constexpr int kTmemRows = kTmemCols / 2;  // ring rows per lane (one double = two 32-bit columns)
 
-template <int BW, int PG>
+// FUSED = 1: the right-hand side is produced on the fly as  y = Lm * u  (Lm: a second banded matrix
+// with at most BW sub/super-diagonals, row records `mrec`; u read through `tmap`, never modified)
+// and the solution goes to `rhs` (a different buffer): the `mul!` + `ldiv!` pair of a collocation
+// time step (examples/heat.jl:314-328) in one pass over HBM.  Needs 2 BW <= 8 so that the u rows
+// one 8-row chunk of y depends on are exactly the chunk being eliminated and the next one.
+template <int BW, int PG, int FUSED>
 __global__ void __launch_bounds__(128, 2)
 k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
               double *__restrict__ rhs, int64_t ngroups, int64_t ld, int n, int n_pad_all, int M, int H,
               const __grid_constant__ CUtensorMap tmap, int nseg, int SEG, int HF,
-              const double *__restrict__ scratch, const __grid_constant__ CUtensorMap tmap_s) {
+              const double *__restrict__ scratch, const __grid_constant__ CUtensorMap tmap_s,
+              const double *__restrict__ mrec, const double *__restrict__ uin) {
     constexpr int TB = 32;
     constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
+    constexpr int MW = 2 * BW + 2;                            // {Lm(r,r-BW) .. Lm(r,r+BW), pad}
+    constexpr int MWS = FUSED ? PG * G * MW : 0;
     constexpr int RWT = kTmemRows;                            // TMEM ring rows
     constexpr int RC = RWT + PG * G;                          // rows of backward records kept in smem
-    // per-warp shared memory (doubles): stage[PG][8][32] | cur[RC][UW] | cfw[PG][8*LW] | mbar[PG]
-    constexpr int WARP_D = ((PG * G * TB + RC * UW + PG * G * LW + PG + 15) / 16) * 16;   // 128-byte multiple
+    // per-warp shared memory (doubles): stage[PG][8][32] | cur[RC][UW] | cfw[PG][8*LW] | cmv[PG][8*MW] | mbar[PG]
+    constexpr int WARP_D = ((PG * G * TB + RC * UW + PG * G * LW + MWS + PG + 15) / 16) * 16;   // 128-byte multiple
     extern __shared__ __align__(128) double smem_d[];
     __shared__ unsigned s_tmem_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -406,10 +415,12 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
     double *const stage = smem_d + (size_t)warp * WARP_D;
     double *const cur = stage + PG * G * TB;
     double *const cfw = cur + RC * UW;
+    double *const cmv = cfw + PG * G * LW;
     const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
     const unsigned cur_s = (unsigned)__cvta_generic_to_shared(cur);
     const unsigned cfw_s = (unsigned)__cvta_generic_to_shared(cfw);
-    const unsigned barA_s = cfw_s + (unsigned)(PG * G * LW * 8);
+    const unsigned cmv_s = (unsigned)__cvta_generic_to_shared(cmv);
+    const unsigned barA_s = cmv_s + (unsigned)(MWS * 8);
     const int hb = H / M;
     if (lane == 0) {
 #pragma unroll
@@ -432,6 +443,7 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
         double *const p = rhs + (int64_t)f0 * ld + g * TB + lane;
         const double *const lrec_l = lrec + (size_t)f0 * LW;
         const double *const urec_l = urec + (size_t)f0 * UW;
+        const double *const mrec_l = FUSED ? mrec + (size_t)f0 * MW : nullptr;
 
         int pf_row = 0, pf_cslot = 0;                         // next row to prefetch, its slot in `cur`
         auto issue_fwd = [&]() {
@@ -442,13 +454,20 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
                 if (pf_row < n_pad) {
                     fence_proxy_async();
                     const int ra = f0 + pf_row;
-                    const bool halo = (nseg > 1) && (ra < k0 || ra >= k1);
+                    const bool halo = !FUSED && (nseg > 1) && (ra < k0 || ra >= k1);
                     const int srow = halo ? ((ra < k0 ? seg - 1 : seg) * (HF + H) + ra - ((ra < k0 ? k0 : k1) - HF)) : 0;
-                    mbar_expect_tx(bar, (unsigned)(G * TB * 8 + G * (LW + UW) * 8));
+                    mbar_expect_tx(bar, (unsigned)(G * TB * 8 + G * (LW + UW) * 8 + (FUSED ? G * MW * 8 : 0)));
                     if (halo) tma_load_2d(stage_s + i * (G * TB * 8), &tmap_s, (int)(g * TB), srow, bar);
                     else tma_load_2d(stage_s + i * (G * TB * 8), &tmap, (int)(g * TB), ra, bar);
                     bulk_g2s(cfw_s + i * (G * LW * 8), lrec_l + (size_t)pf_row * LW, G * LW * 8, bar);
                     bulk_g2s(cur_s + (unsigned)(pf_cslot * UW * 8), urec_l + (size_t)pf_row * UW, G * UW * 8, bar);
+                    // records of the y rows this chunk brings into the window: rows pf_row + BW ...
+                    if (FUSED) bulk_g2s(cmv_s + i * (G * MW * 8), mrec_l + (size_t)(pf_row + BW) * MW, G * MW * 8, bar);
+                } else if (FUSED && pf_row < n_pad + G) {
+                    // one chunk of u past the window: the last y rows of the window depend on it
+                    fence_proxy_async();
+                    mbar_expect_tx(bar, (unsigned)(G * TB * 8));
+                    tma_load_2d(stage_s + i * (G * TB * 8), &tmap, (int)(g * TB), f0 + pf_row, bar);
                 } else {
                     mbar_arrive(bar);
                 }
@@ -467,8 +486,23 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
             mbar_wait(barA_s + 8 * (conA % PG), (conA / PG) & 1);
             const double *const ys = stage + (conA % PG) * (G * TB) + lane;
             ++conA;
+            if (FUSED) {
+                // y rows f0 .. f0+BW-1 also need the u rows just above the window: read them directly
+                const double *const ug = uin + g * TB + lane;
 #pragma unroll
-            for (int j = 0; j < BW; ++j) tf[j] = ys[j * TB];
+                for (int j = 0; j < BW; ++j) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = 0; m <= 2 * BW; ++m) {
+                        const int row = f0 + j + m - BW;
+                        if (row >= 0 && row < n) acc = fma(mrec_l[(size_t)j * MW + m], ug[(int64_t)row * ld], acc);
+                    }
+                    tf[j] = acc;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < BW; ++j) tf[j] = ys[j * TB];
+            }
         }
         for (int b = 0; b < nblk + hb; ++b) {
             if (b < nblk) {
@@ -485,14 +519,33 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
                     double t[G + BW];
 #pragma unroll
                     for (int j = 0; j < BW; ++j) t[j] = tf[j];
+                    if (FUSED) {
+                        // y(r0+BW+q) = sum_m Lm(r, r-BW+m) u(r0+q+m), u rows r0 .. r0+15 = this chunk + next
+                        double uu[2 * G];
 #pragma unroll
-                    for (int q = BW; q < G; ++q) t[q] = ys[q * TB];
-                    if (r0 + G < n_pad) {
+                        for (int q = 0; q < G; ++q) uu[q] = ys[q * TB];
 #pragma unroll
-                        for (int j = 0; j < BW; ++j) t[G + j] = yn[j * TB];
+                        for (int q = 0; q < G; ++q) uu[G + q] = yn[q * TB];
+                        const double *const mr = cmv + i * (G * MW);
+#pragma unroll
+                        for (int q = 0; q < G; ++q) {
+                            double mrow[MW];
+                            load_rec_s<MW>(mr + q * MW, mrow);
+                            double acc = 0.0;
+#pragma unroll
+                            for (int m = 0; m <= 2 * BW; ++m) acc = fma(mrow[m], uu[q + m], acc);
+                            t[BW + q] = acc;
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BW; ++j) t[G + j] = 0.0;
+                        for (int q = BW; q < G; ++q) t[q] = ys[q * TB];
+                        if (r0 + G < n_pad) {
+#pragma unroll
+                            for (int j = 0; j < BW; ++j) t[G + j] = yn[j * TB];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BW; ++j) t[G + j] = 0.0;
+                        }
                     }
                     double rec[G][LW];
 #pragma unroll
@@ -626,8 +679,11 @@ bool make_rhs_tensor_map(CUtensorMap *tm, double *d_rhs, int64_t ncols, int64_t 
     return r == CUDA_SUCCESS;
 }
 
+// mrec / d_u non-null: fused  d_rhs = (LU)^{-1} (Lm * d_u)  (d_u is only read).
 template <int BW>
-bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st) {
+bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st,
+                   const double *mrec = nullptr, const double *d_u = nullptr) {
+    const bool fused = mrec != nullptr;
     constexpr int PG = 4;                                     // 4 chunks x 8 rows in flight
     constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
     // halo validated at factor time (multiple of 8); the kernel restarts every M rows and needs
@@ -668,9 +724,13 @@ bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t 
     CUtensorMap tmap, tmap_s;
     memset(&tmap, 0, sizeof(tmap));
     memset(&tmap_s, 0, sizeof(tmap_s));
-    int use_tmap = make_rhs_tensor_map(&tmap, d_rhs, ngroups * 32, ld, h->n) ? 1 : 0;
+    int use_tmap = make_rhs_tensor_map(&tmap, fused ? const_cast<double *>(d_u) : d_rhs, ngroups * 32, ld, h->n) ? 1 : 0;
     double *scratch = nullptr;
-    if (nseg > 1) {
+    if (fused && !(use_tmap && tmem_ok && 2 * BW <= G)) {
+        set_error("fused mat-vec + solve unavailable for this shape");
+        return BSK_ERR_UNSUPPORTED;
+    }
+    if (nseg > 1 && !fused) {
         // copy of the rows around every segment boundary (contiguous in memory: full rows)
         const int HS = HF + H;
         static bool pool_set[64] = {false};
@@ -698,14 +758,25 @@ bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t 
         // TMEM-resident ring: 2 CTAs x 4 warps per SM
         constexpr int RC = kTmemRows + PG * G;
         const size_t smem_t = (size_t)4 * (((PG * G * 32 + RC * UW + PG * G * LW + PG + 15) / 16) * 16) * sizeof(double);
-        auto kt = k_banded_tmem<BW, PG>;
-        BSK_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
         const int64_t wslots = (int64_t)sm_count(h->device) * 8;
         const int64_t wr = (nwork + wslots - 1) / wslots;
         const int64_t nwarps = (nwork + wr - 1) / wr;
         const int gridt = (int)std::max<int64_t>(1, (nwarps + 3) / 4);
-        kt<<<gridt, 128, smem_t, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap,
-                                       nseg, SEG, HF, scratch, tmap_s);
+        if (fused) {
+            if constexpr (2 * BW <= G) {
+                constexpr int MW = 2 * BW + 2;
+                const size_t smem_f = (size_t)4 * (((PG * G * 32 + RC * UW + PG * G * LW + PG * G * MW + PG + 15) / 16) * 16) * sizeof(double);
+                auto kf = k_banded_tmem<BW, PG, 1>;
+                BSK_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+                kf<<<gridt, 128, smem_f, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap,
+                                               nseg, SEG, HF, nullptr, tmap_s, mrec, d_u);
+            }
+        } else {
+            auto kt = k_banded_tmem<BW, PG, 0>;
+            BSK_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+            kt<<<gridt, 128, smem_t, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap,
+                                           nseg, SEG, HF, scratch, tmap_s, nullptr, nullptr);
+        }
     } else {
         kern<<<grid, 32, smem, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap, use_tmap,
                                      nseg, SEG, HF, scratch, tmap_s);
@@ -719,6 +790,41 @@ bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t 
 }  // namespace
 
 namespace bsk {
+
+// Row records of a second banded matrix Lm for the fused kernel: (n_pad + G) rows of
+// { Lm(r, r-bw) .. Lm(r, r+bw), pad }, zero outside Lm's own band, outside the matrix and for r > n.
+// Band store (Collocation/Collocation.jl:165-198): element (i, j) at w[(u + i - j) + (j-1) (l+u+1)].
+bsk_status windowed_matrec(const bsk_banded *Lm, int bw, int n_pad, double **out) {
+    const int n = (int)Lm->n, lm = Lm->l, um = Lm->u, MW = 2 * bw + 2;
+    const size_t rows = (size_t)n_pad + G;
+    std::vector<double> w((size_t)(lm + um + 1) * n), rec(rows * MW, 0.0);
+    BSK_CUDA(cudaSetDevice(Lm->device));
+    BSK_CUDA(cudaMemcpy(w.data(), Lm->d_w, w.size() * 8, cudaMemcpyDeviceToHost));
+    for (int i = 1; i <= n; ++i)
+        for (int m = 0; m <= 2 * bw; ++m) {
+            const int j = i - bw + m;
+            if (j < 1 || j > n || i - j > lm || j - i > um) continue;
+            rec[(size_t)(i - 1) * MW + m] = w[(size_t)(um + i - j) + (size_t)(j - 1) * (lm + um + 1)];
+        }
+    double *d = nullptr;
+    BSK_CUDA(cudaMalloc((void **)&d, rec.size() * 8));
+    BSK_CUDA(cudaMemcpy(d, rec.data(), rec.size() * 8, cudaMemcpyHostToDevice));
+    *out = d;
+    return BSK_OK;
+}
+
+bsk_status windowed_solve_fused(const bsk_banded *h, const double *mrec, const double *d_u, double *d_out,
+                                int64_t ngroups, int64_t ld, cudaStream_t st) {
+    switch (h->l) {
+        case 0: return solve_t<0>(h, d_out, ngroups, ld, st, mrec, d_u);
+        case 1: return solve_t<1>(h, d_out, ngroups, ld, st, mrec, d_u);
+        case 2: return solve_t<2>(h, d_out, ngroups, ld, st, mrec, d_u);
+        case 3: return solve_t<3>(h, d_out, ngroups, ld, st, mrec, d_u);
+        case 4: return solve_t<4>(h, d_out, ngroups, ld, st, mrec, d_u);
+    }
+    set_error("fused mat-vec + solve needs at most 4 sub-diagonals");
+    return BSK_ERR_UNSUPPORTED;
+}
 
 bsk_status windowed_prepare(bsk_banded *h) {
     switch (h->l) {

@@ -112,11 +112,17 @@ struct bsk_banded {
     int n_pad;
     int halo_f;           // decay halo of the forward recurrence (row-segmented windowed solve)
     int halo;             // decay halo (rows) validated for the windowed solve, 0 = not usable
+    // unfactored matrices used as the Lm of bsk_banded_matvec_solve: cached row records
+    double *d_mrec;
+    int mrec_bw, mrec_npad;
 };
 
 namespace bsk {
 bsk_status windowed_prepare(bsk_banded *h);
 bsk_status windowed_solve(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st);
+bsk_status windowed_matrec(const bsk_banded *Lm, int bw, int n_pad, double **out);
+bsk_status windowed_solve_fused(const bsk_banded *h, const double *mrec, const double *d_u, double *d_out,
+                                int64_t ngroups, int64_t ld, cudaStream_t st);
 }  // namespace bsk
 
 struct bsk_cyclic {

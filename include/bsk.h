@@ -200,6 +200,12 @@ bsk_status bsk_banded_solve_host(const bsk_banded *h, double *h_rhs, int64_t nrh
 /* mul!(Y, C, X) for nrhs interleaved vectors — Collocation/matrix.jl:91-94 (BandedMatrices gbmv in the
  * reference).  Only before bsk_banded_lu (which overwrites the band data, like lu!).  X and Y must not alias. */
 bsk_status bsk_banded_matvec(const bsk_banded *h, const double *d_x, double *d_y, int64_t nrhs, void *stream);
+/* du = F \ (Lm * u): `mul!(y, Lm, u); ldiv!(du, F, y)` of a collocation time step
+ * (examples/heat.jl:314-328; Collocation/matrix.jl:91-94 + :218-271) in ONE pass over HBM (16 B per
+ * element instead of 32).  lu: factorised; Lm: NOT factorised, same size; d_u is only read, d_out must
+ * not alias it.  Shapes the fused kernel does not cover run bsk_banded_matvec + bsk_banded_solve. */
+bsk_status bsk_banded_matvec_solve(const bsk_banded *lu, const bsk_banded *Lm, const double *d_u,
+                                   double *d_out, int64_t nrhs, void *stream);
 bsk_status bsk_banded_destroy(bsk_banded *h);
 
 /* ---- cyclic tridiagonal (periodic cubic interpolation) -------------------------------

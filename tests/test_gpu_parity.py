@@ -772,3 +772,34 @@ def test_banded_matvec(bk, oracle, synth, k, n, nrhs):
     assert np.max(np.abs(Z - X)) < 1e-11
     with pytest.raises(bk.ArgumentError):
         Cm2.mul(X)
+
+
+@pytest.mark.parametrize("k,n,nrhs,nd", [(3, 1000, 4096, 1), (4, 4096, 2048, 2), (5, 777, 4096, 2),
+                                         (6, 4096, 4096, 2), (6, 520, 2048, 0), (8, 600, 2048, 2),
+                                         (6, 300, 37, 2), (4, 64, 2048, 1)])
+def test_banded_matvec_solve_fused(bk, oracle, synth, k, n, nrhs, nd):
+    """du = F \\ (L u): `mul!` then `ldiv!` of a collocation time step (examples/heat.jl:314-328) in one
+    pass.  Checked against the oracle's mat-vec followed by its BANSLV (1e-13), on shapes that take the
+    fused kernel (with and without row segments) and shapes that fall back (k = 8, 37 columns)."""
+    import torch
+    xdata, t, B, Cm, ref = _interp_system(bk, oracle, synth, n, k)
+    Lm = bk.collocation_matrix(B, xdata, bk.Derivative(nd))
+    Lref, _ = oracle.collocation_matrix(0, k, t, xdata, nd)
+    assert np.array_equal(Lm.data(), Lref)
+    lu_ref = ref.copy(order="F")
+    assert oracle.banded_lu(lu_ref) == 0
+    Cm.lu_()
+    U = (2 * synth.u_numpy(21, 0, n * nrhs) - 1).reshape(n, nrhs)
+    want = oracle.banded_matvec(Lref, U)
+    oracle.banded_solve(lu_ref, want)
+    Ud = torch.from_numpy(U).cuda()
+    out = Cm.ldiv_mul(Lm, Ud)
+    torch.cuda.synchronize()
+    assert torch.equal(Ud.cpu(), torch.from_numpy(U))           # u is only read
+    assert relerr(out.cpu().numpy(), want) < TOL64
+    if nd == 0:                                                  # F \ (C u) == u
+        assert np.max(np.abs(out.cpu().numpy() - U)) < 1e-11
+    with pytest.raises(bk.ArgumentError):
+        Cm.ldiv_mul(Lm, Ud, out=Ud)
+    with pytest.raises(bk.ArgumentError):
+        Lm.ldiv_mul(Cm, Ud)                                      # roles swapped: Lm is not factorised

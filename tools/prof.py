@@ -112,3 +112,19 @@ if args.what == "multi":
         ms = timed(lambda: SB(xs), args.reps)
         print("multi %s: %d splines x %d points: %.3f ms  %.1f GB/s (out + coefs once)" % (
             label, M, xs.numel(), ms, (8.0 * xs.numel() * M + 8.0 * n * M) / ms / 1e6))
+if args.what == "fused":
+    # du = F \ (L u): C3-shaped collocation time step, fused vs mul! + ldiv!
+    n, k = 4096, 6
+    xdata = synth.breakpoints(6, n)
+    Bi = bk.BSplineBasis(k, bk.make_knots(xdata, k), augment=False)
+    F = bk.collocation_matrix(Bi, xdata).lu_()
+    L = bk.collocation_matrix(Bi, xdata, bk.Derivative(2))
+    U = (2 * synth.u_torch(7, 0, n * args.nrhs) - 1).reshape(n, args.nrhs)
+    out = torch.empty_like(U)
+    ms = timed(lambda: F.ldiv_mul(L, U, out=out), args.reps)
+    print("fused mat-vec + solve: %.3f ms  %.2f M RHS/s  %.1f GB/s (16 B/elem)" % (
+        ms, args.nrhs / ms / 1e3, 16 * n * args.nrhs / ms / 1e6))
+    os.environ["BSK_NO_FUSED"] = "1"
+    out2 = torch.empty_like(U)
+    ms2 = timed(lambda: F.ldiv_mul(L, U, out=out2), args.reps)
+    print("mul! then ldiv!:       %.3f ms  (max |diff| vs fused %.2e)" % (ms2, (out - out2).abs().max().item()))
