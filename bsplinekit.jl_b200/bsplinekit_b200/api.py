@@ -592,20 +592,32 @@ class SplineBatch:
     batched interpolate! leaves on the device.  Calling it returns an (n, M) tensor."""
 
     def __init__(self, B, coefs):
-        if isinstance(B, RecombinedBSplineBasis):
-            raise _lib.UnsupportedError("vector-valued evaluation needs a plain or periodic basis")
         if not (isinstance(coefs, torch.Tensor) and coefs.is_cuda):
             coefs = torch.as_tensor(np.ascontiguousarray(coefs, dtype=_NP[B._dt])).cuda()
         if coefs.dim() != 2 or coefs.shape[0] != len(B) or coefs.dtype != _TORCH[B._dt]:
             raise DimensionMismatch("wrong number of coefficients")
         self.basis, self.coefs = B, coefs.contiguous()
+        self._eval_basis = B
+        if isinstance(B, RecombinedBSplineBasis):
+            # parent_coefficients (Recombinations/splines.jl:32-65): corner blocks + shifted identity
+            Mr, P = len(B), B.parent
+            par = torch.zeros((len(P), coefs.shape[1]), dtype=coefs.dtype, device=coefs.device)
+            ul = torch.as_tensor(B.ul, dtype=coefs.dtype, device=coefs.device)
+            lr = torch.as_tensor(B.lr, dtype=coefs.dtype, device=coefs.device)
+            par[:ul.shape[0]] = ul @ self.coefs[:B.nl]
+            par[B.nl + B.cl:Mr - B.nr + B.cl] = self.coefs[B.nl:Mr - B.nr]
+            h = Mr - B.nr + B.cl
+            par[h:h + lr.shape[0]] += lr @ self.coefs[Mr - B.nr:]
+            self._eval_basis, self._eval_coefs = P, par
+        else:
+            self._eval_coefs = self.coefs
 
     def __call__(self, x):
         xd, on_dev = _to_device(x, self.basis._dt)
         xd = xd.reshape(-1)
         M = self.coefs.shape[1]
         out = torch.empty((xd.numel(), M), dtype=self.coefs.dtype, device=xd.device)
-        check(lib.bsk_spline_eval_multi(self.basis._handle, _ptr(self.coefs), self.coefs.shape[0], M,
+        check(lib.bsk_spline_eval_multi(self._eval_basis._handle, _ptr(self._eval_coefs), self._eval_coefs.shape[0], M,
                                         _ptr(xd), xd.numel(), _ptr(out), _stream()))
         return out if on_dev else out.cpu().numpy()
 
@@ -996,3 +1008,186 @@ def interpolate(x, y, order, bc=None):
         raise ArgumentError("unknown boundary condition")
     itp = SplineInterpolation(B, xf)
     return itp.interpolate_(y)
+
+
+# ---- approximation (SplineApproximations) ----------------------------------------------------------
+
+class VariationDiminishing:
+    """VariationDiminishing() (SplineApproximations/variation_diminishing.jl:1-44): c_i = f(Greville site i)."""
+
+
+class ApproxByInterpolation:
+    """ApproxByInterpolation(xs) / ApproxByInterpolation(B) (SplineApproximations/by_interpolation.jl:3-38)."""
+
+    def __init__(self, xs_or_basis):
+        if isinstance(xs_or_basis, AbstractBSplineBasis):
+            self.xs = collocation_points(xs_or_basis)
+        else:
+            self.xs = np.asarray(xs_or_basis)
+
+
+class MinimiseL2Error:
+    """MinimiseL2Error() needs the Galerkin mass matrix and quadratures (SplineApproximations/minimiseL2.jl),
+    which are outside the evaluation / interpolation path built here."""
+
+
+class SplineApproximation:
+    """SplineApproximation (SplineApproximations.jl:24-48): the spline plus what is needed to approximate
+    another function in the same basis without refactorising (approximate!)."""
+
+    def __init__(self, method, basis, data):
+        self.method, self.basis, self.data = method, basis, data
+        self.spline = None
+
+    def __call__(self, x, **kw):
+        return self.spline(x, **kw)
+
+    def coefficients(self):
+        return self.spline.coefficients()
+
+
+def _apply(f, xs):
+    """f.(xs) for a Python callable: vectorised call if f accepts arrays, else point by point."""
+    try:
+        ys = np.asarray(f(xs), dtype=np.float64)
+        if ys.shape == xs.shape:
+            return ys
+    except Exception:
+        pass
+    return np.array([f(float(x)) for x in xs], dtype=np.float64)
+
+
+def approximate_(f, A):
+    """approximate!(f, A) (SplineApproximations.jl:121-130)."""
+    if isinstance(A.method, VariationDiminishing):
+        B = A.basis                                          # variation_diminishing.jl:35-44 (Greville sites)
+        A.spline = Spline(B, _apply(f, np.asarray(collocation_points(B), dtype=np.float64)))
+        return A
+    itp = A.data                                             # by_interpolation.jl:47-71 -> interpolate!
+    itp.interpolate_(_apply(f, np.asarray(A.method.xs, dtype=np.float64)))
+    A.spline = itp.spline
+    return A
+
+
+def approximate(f, B, method=None):
+    """approximate(f, B, [method = ApproxByInterpolation(B)]) (SplineApproximations.jl:50-119)."""
+    if method is None:
+        method = ApproxByInterpolation(B)
+    if isinstance(method, MinimiseL2Error):
+        raise _lib.UnsupportedError("MinimiseL2Error needs the Galerkin module (out of scope of this library)")
+    if isinstance(method, VariationDiminishing):
+        return approximate_(f, SplineApproximation(method, B, None))
+    if not isinstance(method, ApproxByInterpolation):
+        raise ArgumentError("unknown approximation method")
+    itp = SplineInterpolation(B, np.asarray(method.xs, dtype=np.float64))
+    return approximate_(f, SplineApproximation(method, B, itp))
+
+
+# ---- cubic smoothing splines (SplineInterpolations/smoothing.jl) ------------------------------------
+
+class DomainError(ValueError):
+    """Julia DomainError (smoothing.jl:49)."""
+
+
+def _band_to_sparse(w, l, u):
+    """Band store data[u + i - j, j] (Collocation.jl:165-198) -> scipy CSR."""
+    import scipy.sparse as sp
+    n = w.shape[1]
+    diags, offs = [], []
+    for d in range(-l, u + 1):                               # diagonal d holds A[i, i + d]
+        js = np.arange(max(0, d), min(n, n + d))
+        diags.append(w[u - d, js])
+        offs.append(d)
+    return sp.diags(diags, offs, shape=(n, n), format="csr")
+
+
+def _sparse_to_band(M, bw):
+    n = M.shape[0]
+    w = np.zeros((2 * bw + 1, n), dtype=np.float64, order="F")
+    Mc = M.tocoo()
+    keep = np.abs(Mc.row - Mc.col) <= bw
+    np.add.at(w, (bw + Mc.row[keep] - Mc.col[keep], Mc.col[keep]), Mc.data[keep])
+    return w
+
+
+def _sparse_bandwidth(M):
+    Mc = M.tocoo()
+    nz = Mc.data != 0
+    return int(np.max(np.abs(Mc.row[nz] - Mc.col[nz]))) if nz.any() else 0
+
+
+class SmoothingSpline:
+    """What fit() factorised: the natural cubic basis, the LU of the 7-band normal matrix and the
+    3-band matrix 2 A' W of the right-hand side.  `fit_(Y)` fits further data sets on the same points
+    (the reference rebuilds everything per call)."""
+
+    def __init__(self, R, F, L, xs):
+        self.basis, self.F, self.L, self.xs = R, F, L, xs
+
+    def fit_(self, ys):
+        n = len(self.xs)
+        if isinstance(ys, torch.Tensor) and ys.is_cuda:
+            if ys.dtype != torch.float64 or ys.shape[0] != n:
+                raise DimensionMismatch("x and y vectors must have the same length")
+            Y = ys.contiguous().reshape(n, -1)
+            cs = self.F.ldiv_mul(self.L, Y)                  # 2 A' W y, then M \ . : one pass over HBM
+            return SplineBatch(self.basis, cs) if ys.dim() > 1 else Spline(self.basis, cs[:, 0].cpu().numpy())
+        ys = np.asarray(ys, dtype=np.float64)
+        if ys.shape[0] != n:
+            raise DimensionMismatch("x and y vectors must have the same length")
+        Y = torch.from_numpy(np.ascontiguousarray(ys.reshape(n, -1))).cuda()
+        cs = self.F.ldiv_mul(self.L, Y)
+        if ys.ndim == 1:
+            return Spline(self.basis, cs[:, 0].cpu().numpy())
+        return SplineBatch(self.basis, cs)
+
+
+def fit(order, xs, ys=None, lam=0.0, bc=None, weights=None):
+    """fit(BSplineOrder(4), xs, ys, λ, [bc = Natural()]; weights) — cubic smoothing spline minimising
+    sum_i w_i |y_i - S(x_i)|^2 + λ ∫ S''^2 (SplineInterpolations/smoothing.jl:1-124).
+
+    ys: (N,) array -> Spline; (N, M) array or CUDA tensor (M data sets, data-set index fastest) ->
+    SplineBatch.  ys=None returns the factorised SmoothingSpline for repeated fit_(ys) calls."""
+    import scipy.sparse as sp
+    k = _order(order)
+    if k != 4:
+        raise ArgumentError("only cubic splines (BSplineOrder(4)) are currently supported")
+    if not lam >= 0:
+        raise DomainError("the smoothing parameter λ must be non-negative (got %r)" % (lam,))    # smoothing.jl:49
+    if bc is None:
+        bc = Natural()
+    if isinstance(bc, Periodic):
+        raise _lib.UnsupportedError("periodic smoothing splines need a cyclic banded solve (not built)")
+    if not isinstance(bc, Natural):
+        raise ArgumentError("the boundary condition must be Natural() or Periodic(L)")
+    xs = np.ascontiguousarray(np.asarray(xs, dtype=np.float64))
+    N = xs.size
+    if ys is not None and np.shape(ys)[0] != N:
+        raise DimensionMismatch("x and y vectors must have the same length")               # smoothing.jl:50
+    if weights is not None:
+        weights = np.asarray(weights, dtype=np.float64)
+        if weights.shape != (N,):
+            raise DimensionMismatch("the `weights` vector must have the same length as the data")   # :110
+    # natural cubic basis with knots = data points (smoothing.jl:56-58)
+    R = RecombinedBSplineBasis(BSplineBasis(4, xs.copy()), Natural())
+    Ab = collocation_matrix(R, xs)                           # smoothing.jl:61-64 (3 bands are populated)
+    Db = collocation_matrix(R, xs, Derivative(2))
+    l, u = Ab.bandwidths
+    A = _band_to_sparse(Ab.data(), l, u)
+    D = _band_to_sparse(Db.data(), l, u)
+    # grid-step matrix Δ (symmetric, rows 2..N-1 populated; smoothing.jl:66-74)
+    dlt = sp.lil_matrix((N, N))
+    for i in range(1, N - 1):
+        dlt[i, i] = 2 * (xs[i + 1] - xs[i - 1])
+        dlt[i, i + 1] = xs[i + 1] - xs[i]
+    dlt = dlt.tocsr()
+    dlt = dlt + sp.triu(dlt, 1).T                            # Hermitian(Δ_upper)
+    H = dlt @ D
+    Bm = H.T @ D
+    W = sp.diags(weights) if weights is not None else sp.identity(N)
+    M = (Bm + Bm.T) * (lam / 6) + 2 * (A.T @ W @ A)          # smoothing.jl:79-92
+    bw = max(1, _sparse_bandwidth(M))
+    F = CollocationMatrix(_sparse_to_band(M, bw)).lu_()
+    L = CollocationMatrix(_sparse_to_band((2 * (A.T @ W)).tocsr(), 1))          # z = 2 A' W y (smoothing.jl:113-114)
+    sm = SmoothingSpline(R, F, L, xs)
+    return sm if ys is None else sm.fit_(ys)

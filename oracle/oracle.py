@@ -209,3 +209,75 @@ def augment_knots(breaks, k):
     """augment_knots! (knots.jl:68-84): pad both ends to multiplicity k."""
     b = np.asarray(breaks)
     return np.concatenate([np.repeat(b[:1], k - 1), b, np.repeat(b[-1:], k - 1)])
+
+
+def natural_corners(k, t):
+    """Natural boundary conditions: corner blocks of the recombination matrix
+    (src/Recombinations/natural.jl:9-134).  For each side: the derivatives D^2..D^h (h = k/2) of the
+    h+1 boundary B-splines at the boundary, two (h+1)x(h+1) systems (rows: sum = h, normalised
+    derivative rows = 0, last row picks b_{h+1} resp. b_1), near-zeros removed."""
+    t = _np(t, np.float64)
+    assert k % 2 == 0
+    h = k // 2
+    N = t.size - k
+    blocks = []
+    for side in ("left", "right"):
+        x = t[k - 1] if side == "left" else t[N]
+        js = list(range(1, h + 2)) if side == "left" else list(range(N - h, N + 1))
+        D = np.zeros((h - 1, h + 1))
+        for i in range(1, h):                                # natural.jl:66-97: evaluate_all(B, x, Derivative(i+1))
+            idx, bs = evaluate_all(0, k, t, [x], nderiv=i + 1)
+            jlast = int(idx[0])
+            for n, j in enumerate(js):
+                dj = jlast + 1 - j
+                if 1 <= dj <= k:
+                    D[i - 1, n] = bs[0, dj - 1]
+        rhs = np.zeros(h + 1)
+        rhs[0] = h
+        cols = []
+        for which in (1, 2):                                 # natural.jl:103-134
+            M = np.zeros((h + 1, h + 1))
+            M[0, :] = 1.0
+            for i in range(2, h + 1):
+                M[i - 1, :] = D[i - 2] / np.max(np.abs(D[i - 2]))
+            M[h, h if which == 1 else 0] = 1.0
+            v = np.linalg.solve(M, rhs)
+            v[np.abs(v) < 10 * np.finfo(np.float64).eps * np.max(np.abs(v))] = 0.0      # natural.jl:44-48
+            cols.append(v)
+        blocks.append(np.stack(cols, axis=1))
+    return Recomb(h - 1, h - 1, 2, 2, blocks[0], blocks[1])
+
+
+def band_to_dense(band):
+    """Band store data[u + i - j, j] (Collocation.jl:165-198) -> dense matrix."""
+    nb, n = band.shape
+    u = (nb - 1) // 2
+    A = np.zeros((n, n))
+    for j in range(n):
+        for i in range(max(0, j - u), min(n, j + u + 1)):
+            A[i, j] = band[u + i - j, j]
+    return A
+
+
+def fit_smoothing(xs, ys, lam, weights=None):
+    """fit(BSplineOrder(4), xs, ys, λ, Natural(); weights) restated with dense numpy algebra
+    (src/SplineInterpolations/smoothing.jl:43-124): returns the coefficients in the natural
+    recombined basis.  ys: (N,) or (N, M).  Small N only (dense N x N matrices)."""
+    xs = _np(xs, np.float64)
+    N = xs.size
+    t = augment_knots(xs, 4)                                 # BSplineBasis(order, copy(xs)), smoothing.jl:57
+    rc = natural_corners(4, t)                               # RecombinedBSplineBasis(B, Natural()), :58
+    A = band_to_dense(collocation_matrix(KIND_RECOMBINED, 4, t, xs, 0, recomb=rc)[0])   # :61-64
+    D = band_to_dense(collocation_matrix(KIND_RECOMBINED, 4, t, xs, 2, recomb=rc)[0])
+    dl = np.zeros((N, N))                                    # :66-74
+    for i in range(1, N - 1):
+        dl[i, i] = 2 * (xs[i + 1] - xs[i - 1])
+        dl[i, i + 1] = xs[i + 1] - xs[i]
+    dl = dl + np.triu(dl, 1).T                               # Hermitian(Δ_upper)
+    H = dl @ D                                               # :77
+    Bm = H.T @ D                                             # :83
+    W = np.diag(np.asarray(weights, dtype=np.float64)) if weights is not None else np.eye(N)
+    M = (Bm + Bm.T) * (lam / 6) + 2 * (A.T @ W @ A)          # :84-92
+    Lc = np.linalg.cholesky((M + M.T) / 2)                   # cholesky!(Hermitian(M)), :93
+    z = 2 * (A.T @ (W @ np.asarray(ys, dtype=np.float64)))   # :113-114
+    return np.linalg.solve(Lc.T, np.linalg.solve(Lc, z)), t, rc

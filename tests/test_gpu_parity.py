@@ -803,3 +803,82 @@ def test_banded_matvec_solve_fused(bk, oracle, synth, k, n, nrhs, nd):
         Cm.ldiv_mul(Lm, Ud, out=Ud)
     with pytest.raises(bk.ArgumentError):
         Lm.ldiv_mul(Cm, Ud)                                      # roles swapped: Lm is not factorised
+
+
+# ---- approximation and smoothing (callers of the interpolation path) ------------
+
+def _goldens():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "docstring_goldens.json")) as f:
+        return json.load(f)
+
+
+def test_approximate_goldens(bk):
+    """approximate(f, B, [method]) against the reference's docstring values
+    (SplineApproximations.jl:78-119, README.md:50-63)."""
+    g = _goldens()["class_C"]["approximate_k3"]
+    B = bk.BSplineBasis(g["k"], dec_range(g["breaks"]["a"], g["breaks"]["b"], g["breaks"]["n"]))
+    A = bk.approximate(np.sin, B)
+    assert np.allclose(A.method.xs, g["interp_points"], atol=1e-15)
+    assert np.allclose(A.coefficients(), g["sin_coefs_6digits"], rtol=6e-6, atol=1e-15)
+    assert A(0.3) == pytest.approx(g["sin_S(0.3)"], abs=2e-15)
+    bk.approximate_(np.exp, A)                                      # approximate!(exp, S_interp)
+    assert np.allclose(A.coefficients(), g["exp_coefs_6digits"], rtol=6e-6)
+    assert A(0.3) == pytest.approx(g["exp_S(0.3)"], abs=4e-15)
+    assert A(0.34) == pytest.approx(g["exp_S_interp(0.34)"], abs=4e-15)
+    V = bk.approximate(np.exp, B, bk.VariationDiminishing())
+    assert np.allclose(V.coefficients(), g["exp_vd_coefs_6digits"], rtol=6e-6)
+    assert V(0.34) == pytest.approx(g["exp_S_vd(0.34)"], abs=4e-15)
+    with pytest.raises(bk.UnsupportedError):
+        bk.approximate(np.exp, B, bk.MinimiseL2Error())
+    r = _goldens()["class_C"]["readme_approximate_k6"]
+    B6 = bk.BSplineBasis(bk.BSplineOrder(6), np.log2(np.arange(1, 17)))
+    fa = bk.approximate(lambda x: np.exp(-x) * np.sin(x), B6)
+    assert fa(2.3) == pytest.approx(r["fapprox(2.3)"], abs=1e-14)
+
+
+def test_fit_smoothing_golden_and_oracle(bk, oracle, synth):
+    """fit(BSplineOrder(4), xs, ys, λ; weights): docstring coefficients (smoothing.jl:30-42), the oracle's
+    dense Cholesky restatement, weights, λ = 0 == natural interpolation, argument errors."""
+    import torch
+    g = _goldens()["class_C"]["smoothing_fit"]
+    xs = dec_range(0.0, 1.0, 101) ** 2
+    ys = np.cos(2 * np.pi * xs) + 0.1 * np.sin(200 * np.pi * xs)
+    S = bk.fit(bk.BSplineOrder(4), xs, ys, g["lambda"])
+    # coefficients() returns the parent-basis coefficients; compare through values and the oracle
+    cs_ref, t, rc = oracle.fit_smoothing(xs, ys, g["lambda"])
+    assert np.allclose(cs_ref[:10], g["coefs_head_6digits"], rtol=6e-6)
+    xq = np.linspace(0, 1, 777)
+    idx, bs = oracle.evaluate_all(2, 4, t, xq, recomb=rc)
+    ref_vals = np.array([sum(bs[p, d] * cs_ref[idx[p] - d - 1] for d in range(4) if 0 <= idx[p] - d - 1 < cs_ref.size)
+                         for p in range(xq.size)])
+    # cond(M) = 9e8 on this grid (steps 1e-4 .. 2e-2): LU and Cholesky of the same matrix already differ
+    # by 2e-9 in numpy; the tolerance is 100 eps cond(M)
+    assert relerr(S(xq), ref_vals) < 2e-8
+    # batch of data sets on the device + weights: one factorisation, fused 2 A' W y + solve
+    n, M = 300, 2048
+    xb = synth.breakpoints(31, n)
+    w = 0.5 + synth.u_numpy(32, 0, n)
+    Y = (2 * synth.u_numpy(33, 0, n * M) - 1).reshape(n, M)
+    sm = bk.fit(bk.BSplineOrder(4), xb, None, 1e-6, weights=w)
+    SB = sm.fit_(torch.from_numpy(Y).cuda())
+    for m in (0, 1000, M - 1):
+        cm, tb, rcb = oracle.fit_smoothing(xb, Y[:, m], 1e-6, weights=w)
+        assert relerr(SB.coefs[:, m].cpu().numpy(), cm) < 1e-8      # ill-conditioned normal equations, see above
+    S0 = bk.fit(bk.BSplineOrder(4), xs, ys, 0.0)                    # λ = 0: passes through the data
+    assert np.max(np.abs(S0(xs) - ys)) < 1e-9
+    # vector-valued evaluation in the recombined (natural) basis == column-by-column evaluation
+    vals = SB(xq)
+    Sm = bk.Spline(sm.basis, SB.coefs[:, 5].cpu().numpy())
+    assert relerr(vals[:, 5], Sm(xq)) < TOL64
+    d2 = Sm.evaluate(np.array([0.0, 1.0]), (2,))[0]                 # natural: S''(a) = S''(b) = 0
+    assert np.max(np.abs(d2)) < 1e-7 * np.max(np.abs(SB.coefs[:, 5].cpu().numpy())) * n * n
+    with pytest.raises(bk.DomainError):
+        bk.fit(bk.BSplineOrder(4), xs, ys, -1.0)
+    with pytest.raises(bk.DimensionMismatch):
+        bk.fit(bk.BSplineOrder(4), xs, ys[:-1], 0.1)
+    with pytest.raises(bk.DimensionMismatch):
+        bk.fit(bk.BSplineOrder(4), xs, ys, 0.1, weights=np.ones(3))
+    with pytest.raises(bk.ArgumentError):
+        bk.fit(bk.BSplineOrder(6), xs, ys, 0.1)

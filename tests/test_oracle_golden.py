@@ -263,3 +263,50 @@ def test_greville_kahan_and_make_knots(oracle):
         assert np.all(np.diff(t) >= 0)
         kinv = 1.0 / (k - 1)
         assert t[k] == sum(x[1:k].tolist(), 0.0) * kinv or t[k] == pytest.approx(np.sum(x[1:k]) * kinv, rel=1e-15)
+
+
+def _interp_coefs(oracle, k, t, xs, ys):
+    band, nout = oracle.collocation_matrix(0, k, t, xs)
+    assert nout == 0 and oracle.banded_lu(band) == 0
+    return oracle.banded_solve(band, np.array(ys, dtype=np.float64).reshape(-1, 1)).ravel()
+
+
+def test_class_c_approximate(oracle):
+    """approximate(f, B) = interpolation at collocation_points(B); VariationDiminishing = f at the
+    Greville sites (SplineApproximations.jl:78-119, by_interpolation.jl:40-71, variation_diminishing.jl:35-44)."""
+    g = GOLD["class_C"]["approximate_k3"]
+    k = g["k"]
+    t = oracle.augment_knots(dec_range(g["breaks"]["a"], g["breaks"]["b"], g["breaks"]["n"]), k)
+    xs = oracle.greville(0, k, t)
+    assert np.allclose(xs, g["interp_points"], atol=1e-15)
+    cs = _interp_coefs(oracle, k, t, xs, np.sin(xs))
+    assert np.allclose(cs, g["sin_coefs_6digits"], rtol=6e-6, atol=1e-15)
+    assert oracle.spline_eval(0, k, t, cs, [0.3])[0] == pytest.approx(g["sin_S(0.3)"], abs=1e-15)
+    ce = _interp_coefs(oracle, k, t, xs, np.exp(xs))
+    assert np.allclose(ce, g["exp_coefs_6digits"], rtol=6e-6)
+    assert oracle.spline_eval(0, k, t, ce, [0.3])[0] == pytest.approx(g["exp_S(0.3)"], abs=2e-15)
+    assert oracle.spline_eval(0, k, t, ce, [0.34])[0] == pytest.approx(g["exp_S_interp(0.34)"], abs=2e-15)
+    cv = np.exp(xs)
+    assert np.allclose(cv, g["exp_vd_coefs_6digits"], rtol=6e-6)
+    assert oracle.spline_eval(0, k, t, cv, [0.34])[0] == pytest.approx(g["exp_S_vd(0.34)"], abs=2e-15)
+    r = GOLD["class_C"]["readme_approximate_k6"]
+    t6 = oracle.augment_knots(np.log2(np.arange(1, 17)), 6)
+    x6 = oracle.greville(0, 6, t6)
+    c6 = _interp_coefs(oracle, 6, t6, x6, np.exp(-x6) * np.sin(x6))
+    assert oracle.spline_eval(0, 6, t6, c6, [2.3])[0] == pytest.approx(r["fapprox(2.3)"], abs=1e-14)
+
+
+def test_class_c_smoothing_fit(oracle):
+    """fit(BSplineOrder(4), xs, ys, λ) docstring coefficients (smoothing.jl:30-42)."""
+    g = GOLD["class_C"]["smoothing_fit"]
+    xs = dec_range(0.0, 1.0, 101) ** 2
+    ys = np.cos(2 * np.pi * xs) + 0.1 * np.sin(200 * np.pi * xs)
+    cs, t, rc = oracle.fit_smoothing(xs, ys, g["lambda"])
+    assert np.allclose(cs[:10], g["coefs_head_6digits"], rtol=6e-6)
+    assert np.allclose(cs[-10:], g["coefs_tail_6digits"], rtol=6e-6)
+    # λ = 0: the natural interpolating spline (smoothing.jl:7-8)
+    c0, _, _ = oracle.fit_smoothing(xs, ys, 0.0)
+    idx, bs = oracle.evaluate_all(2, 4, t, xs, recomb=rc)
+    vals = np.array([sum(bs[p, d] * c0[idx[p] - d - 1] for d in range(4) if 0 <= idx[p] - d - 1 < c0.size)
+                     for p in range(xs.size)])
+    assert np.max(np.abs(vals - ys)) < 1e-9
