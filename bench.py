@@ -311,6 +311,28 @@ def run_ours(args):
                                       "value": best["rhs_per_s"], "unit": "RHS/s",
                                       "roofline_frac": best["frac"], "algos": res,
                                       "factor_once_ms": factor_ms, "halo_rows": itp.C.halo}}
+        # du = F \ (L u), mul! + ldiv! of a collocation time step in one pass
+        Lm = bk.collocation_matrix(Bi, xdata, bk.Derivative(2))
+        tot = 0.0
+        for it in range(args.warmup + args.solve_steps):
+            barrier()
+            s0 = torch.cuda.Event(enable_timing=True)
+            s1 = torch.cuda.Event(enable_timing=True)
+            s0.record()
+            itp.C.ldiv_mul(Lm, Y0, out=Y)
+            s1.record()
+            torch.cuda.synchronize()
+            if it >= args.warmup:
+                tot += s0.elapsed_time(s1)
+        ms = max_over_ranks(tot / args.solve_steps)
+        if rank == 0:
+            yref = O.banded_matvec(O.collocation_matrix(0, kk, Bi.knots(), xdata, 2)[0], Y0[:, :256].cpu().numpy())
+            O.banded_solve(band, yref)
+            chk["fused_matvec_solve_relerr"] = float(np.max(np.abs(Y[:, :256].cpu().numpy() - yref)) / np.max(np.abs(yref)))
+        extra["n1_fused_matvec_solve"] = {"metric": "RHS/s, du = F \\ (D2 u) (n=4096, k=6, %d columns per GPU)" % nrhs,
+                                          "ms": ms, "value": world * nrhs / (ms * 1e-3), "unit": "RHS/s",
+                                          "roofline_frac": SOLVE_BYTES_PER_ELEM * n * nrhs / (ms * 1e-3) / 1e9 / peak}
+        del Lm
 
     # ---- extra: configs[3] (periodic cubic) and configs[4] (Robin k = 8 + Float32 sweep) ------------
     if not args.no_extra_configs:

@@ -10,6 +10,6 @@ from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, p
                   BSplineBasis, PeriodicBSplineBasis, RecombinedBSplineBasis, augment_knots,
                   knots, order, boundaries, find_knot_interval, evaluate_all,
                   Spline, SplineBatch, collocation_points, greville_points, collocation_matrix, CollocationMatrix,
-                  CyclicTridiagonalMatrix, lu, ldiv, make_knots, SplineInterpolation, interpolate,
+                  CyclicTridiagonalMatrix, CyclicBandedMatrix, lu, ldiv, make_knots, SplineInterpolation, interpolate,
                   approximate, approximate_, ApproxByInterpolation, VariationDiminishing, MinimiseL2Error,
                   SplineApproximation, fit, SmoothingSpline, DomainError)

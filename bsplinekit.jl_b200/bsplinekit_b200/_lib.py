@@ -100,6 +100,9 @@ SIGNATURES = {
     "bsk_cyclic_create_device": (_i32, [_vp, _vp, _vp, _i64, _i32, _pp]),
     "bsk_cyclic_solve": (_i32, [_vp, _vp, _i64, _vp]),
     "bsk_cyclic_destroy": (_i32, [_vp]),
+    "bsk_cyclic_banded_create": (_i32, [_vp, _i64, _i32, _i32, _i32, _pp]),
+    "bsk_cyclic_banded_solve": (_i32, [_vp, _vp, _i64, _vp]),
+    "bsk_cyclic_banded_destroy": (_i32, [_vp]),
     "bsk_event_create": (_i32, [_i32, _pp]),
     "bsk_event_record": (_i32, [_vp, _vp]),
     "bsk_event_elapsed_ms": (_i32, [_vp, _vp, C.POINTER(C.c_float)]),

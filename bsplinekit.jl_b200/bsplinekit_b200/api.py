@@ -659,13 +659,58 @@ def greville_points(k, t, N, cl=0, force_ends=True):
     return x
 
 
+def _periodic_knot(data, k, i):
+    """getindex(::PeriodicKnots, i), 1-based (BSplines/periodic.jl:102-115)."""
+    T = data.dtype.type
+    N = data.size - 1
+    L = data[-1] - data[0]
+    x = T(0)
+    i -= k // 2
+    while i < 1:
+        x = x - L
+        i += N
+    while i > N + 1:
+        x = x + L
+        i -= N
+    return x + data[i - 1]
+
+
+def _greville_raw(k, t, N):
+    """GrevilleSiteIterator without end forcing / clamping (Collocation/points.jl:56-104)."""
+    T = t.dtype.type
+    x = np.empty(N, dtype=t.dtype)
+    tsum = T(0)
+    comp = T(0)
+    for i in range(N):
+        if i == 0:
+            tsum = T(0)
+            for j in range(2, k + 1):
+                tsum = tsum + t[i + j - 1]
+        else:
+            prev = tsum
+            y = t[i + k - 1] - comp
+            tsum = prev + y
+            comp = (tsum - prev) - y
+            prev = tsum
+            y = -t[i] - comp
+            tsum = prev + y
+            comp = (tsum - prev) - y
+        x[i] = T(tsum / T(k - 1))
+    return x
+
+
 def collocation_points(B):
     """collocation_points(B) (Collocation/points.jl:46-126,164-225): Greville sites; periodic
     bases of even order -> the knots themselves (SameAsKnots)."""
     if isinstance(B, PeriodicBSplineBasis):
         if B.k % 2 == 0:
-            return B.t[:-1].copy()                                      # points.jl:176
-        raise _lib.UnsupportedError("AvgKnots for odd-order periodic bases is not implemented")
+            return B.t[:-1].copy()                                      # points.jl:176 (SameAsKnots)
+        # AvgKnots on the periodic knot vector t[i] = xi[i - k/2] (+- L), BSplines/periodic.jl:102-115
+        N, k = len(B), B.k
+        tp = np.array([_periodic_knot(B.t, k, i) for i in range(1, N + k + 1)], dtype=B.t.dtype)
+        a, b = B.t[0], B.t[-1]
+        # clamp(x, boundaries(B)...), points.jl:100-102
+        return np.minimum(np.maximum(_greville_raw(k, tp, N), a), b)
     cl = B.cl if isinstance(B, RecombinedBSplineBasis) else 0
     return greville_points(B.k, B.t, len(B), cl, isinstance(B, BSplineBasis))
 
@@ -853,9 +898,7 @@ def collocation_matrix(B, x, deriv=None, clip_threshold=None, return_outside=Fal
     nout = C.c_int64(0)
     if isinstance(B, PeriodicBSplineBasis):
         if B.k != 4:
-            raise _lib.UnsupportedError(
-                "periodic collocation is implemented for cubic splines only (the reference uses "
-                "SparseMatrixCSC + UMFPACK for other orders)")
+            return _periodic_collocation_general(B, xd, nd, clip, return_outside)
         n = len(B)
         a = torch.empty(n, dtype=torch.float64, device="cuda")
         b = torch.empty_like(a)
@@ -876,6 +919,84 @@ def collocation_matrix(B, x, deriv=None, clip_threshold=None, return_outside=Fal
         warnings.warn("Non-zero value outside of matrix bands (%d entries)" % nout.value)   # :239-244
     M = CollocationMatrix(band)
     return (M, nout.value) if return_outside else M
+
+
+class CyclicBandedMatrix:
+    """Collocation matrix of a periodic basis of order k != 4: banded with wrap-around corners.  The
+    reference uses SparseMatrixCSC + UMFPACK (Collocation/Collocation.jl:141-142); here a banded LU of
+    the non-wrapped part + Woodbury correction of the corners, factored once at construction.
+    cband: (2 bw + 1, n) array, A[i, j] with cyclic offset d = i - j in [shift - bw, shift + bw] at
+    cband[bw + d - shift, j]; shift = offset of the band centre (odd orders: 1)."""
+
+    def __init__(self, cband, shift=0):
+        cb = np.asfortranarray(np.asarray(cband, dtype=np.float64))
+        if cb.shape[0] % 2 != 1:
+            raise ArgumentError("odd number of bands expected")
+        self.cband = cb
+        self.n = cb.shape[1]
+        self.bw = (cb.shape[0] - 1) // 2
+        self.shift = int(shift)
+        out = C.c_void_p()
+        check(lib.bsk_cyclic_banded_create(cb.ctypes.data_as(C.c_void_p), self.n, self.bw, self.shift, _device(),
+                                           C.byref(out)))
+        self._handle = out
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None:
+            try:
+                lib.bsk_cyclic_banded_destroy(h)
+            except Exception:
+                pass
+
+    def dense(self):
+        n, bw = self.n, self.bw
+        A = np.zeros((n, n))
+        for j in range(n):
+            for d in range(-bw, bw + 1):
+                A[(j + d + self.shift) % n, j] += self.cband[bw + d, j]
+        return A
+
+    def ldiv_(self, Y):
+        if isinstance(Y, torch.Tensor) and Y.is_cuda:
+            if Y.dtype != torch.float64 or not Y.is_contiguous() or Y.shape[0] != self.n:
+                raise DimensionMismatch("all vectors must have length %d" % self.n)
+            check(lib.bsk_cyclic_banded_solve(self._handle, _ptr(Y), Y.numel() // self.n, _stream()))
+            return Y
+        Yh = np.asarray(Y, dtype=np.float64)
+        if Yh.shape[0] != self.n:
+            raise DimensionMismatch("all vectors must have length %d" % self.n)
+        d = torch.from_numpy(np.ascontiguousarray(Yh)).cuda()
+        check(lib.bsk_cyclic_banded_solve(self._handle, _ptr(d), d.numel() // self.n, _stream()))
+        Y[...] = d.cpu().numpy()
+        return Y
+
+
+def _periodic_collocation_general(B, xd, nd, clip, return_outside):
+    """collocation_matrix!(C, B::PeriodicBSplineBasis, x, Derivative(nd)) for k != 4
+    (Collocation/Collocation.jl:209-251 with basis_to_array_index, BSplines/periodic.jl:245-253): the
+    rows come from the device evaluate_all (K2); the scatter into the cyclic band store is host work
+    done once per interpolation object."""
+    n, k = len(B), B.k
+    idx, bs = evaluate_all(B, xd, Derivative(nd))
+    idx = idx.cpu().numpy() if isinstance(idx, torch.Tensor) else np.asarray(idx)
+    bs = bs.cpu().numpy() if isinstance(bs, torch.Tensor) else np.asarray(bs)
+    rows = np.repeat(np.arange(n), k)
+    cols = (idx[:, None] - np.arange(k)[None, :] - 1) % n          # j = jlast + 1 - dj, wrapped, 0-based
+    vals = bs.reshape(n, k)
+    keep = (np.abs(vals) > clip).ravel()                           # Collocation.jl:231-234
+    rows, cols, vals = rows[keep], cols.ravel()[keep], vals.ravel()[keep]
+    d = (rows - cols + n // 2) % n - n // 2                        # cyclic offset
+    # centre the band: odd orders have b_j peaking at x_{j+1} (offsets 0..k-1 for k = 3)
+    shift = (int(d.min()) + int(d.max())) // 2 if d.size else 0
+    d = d - shift
+    bw = max(1, int(np.max(np.abs(d)))) if d.size else 1
+    if bw > 6 or n < 4 * bw + 1:
+        raise _lib.UnsupportedError("periodic collocation matrix with %d cyclic bands on %d points" % (2 * bw + 1, n))
+    cband = np.zeros((2 * bw + 1, n), order="F")
+    np.add.at(cband, (bw + d, cols), vals)
+    M = CyclicBandedMatrix(cband, shift)
+    return (M, 0) if return_outside else M
 
 
 def lu(C_):
@@ -943,7 +1064,7 @@ class SplineInterpolation:
             self.C = None
         else:
             Cm = collocation_matrix(B, x)
-            self.C = Cm if isinstance(Cm, CyclicTridiagonalMatrix) else Cm.lu_()
+            self.C = Cm if isinstance(Cm, (CyclicTridiagonalMatrix, CyclicBandedMatrix)) else Cm.lu_()
         self.spline = None
         self.coefs = None
 
@@ -963,7 +1084,7 @@ class SplineInterpolation:
             Y = torch.from_numpy(np.ascontiguousarray(yh, dtype=np.float64)).cuda()
         if self.C is None:
             pass                                                        # identity
-        elif isinstance(self.C, CyclicTridiagonalMatrix):
+        elif isinstance(self.C, (CyclicTridiagonalMatrix, CyclicBandedMatrix)):
             self.C.ldiv_(Y)
         else:
             self.C.ldiv_(Y, algo=algo)
@@ -972,8 +1093,7 @@ class SplineInterpolation:
             self.spline = Spline(self.basis, Y.cpu().numpy())
         else:
             self.spline = None
-        self.splines = (SplineBatch(self.basis, Y) if Y.dim() == 2 and not isinstance(self.basis, RecombinedBSplineBasis)
-                        else None)
+        self.splines = SplineBatch(self.basis, Y) if Y.dim() == 2 else None
         return self
 
     def spline_of(self, column=0):

@@ -297,7 +297,9 @@ int decay_halo(const std::vector<double> &urow, const std::vector<double> &dinv,
             if (mx <= tol) { ok = true; break; }
         }
         if (!ok && h >= hmax) return 0;          // no decay within hmax rows
-        if (ok) need = std::max(need, h);        // (running off row 0 first is harmless)
+        // ok: decayed after h rows.  !ok: ran off row 0 after h = s + 1 rows without decaying — a halo
+        // of s + 1 rows makes this restart keep no rows at all, anything shorter would keep polluted ones.
+        need = std::max(need, h);
     }
     int H = ((need + step - 1) / step) * step;
     if (H == 0) H = step;

@@ -71,6 +71,7 @@ typedef struct bsk_basis bsk_basis;
 typedef struct bsk_spline bsk_spline;
 typedef struct bsk_banded bsk_banded;
 typedef struct bsk_cyclic bsk_cyclic;
+typedef struct bsk_cyclic_banded bsk_cyclic_banded;
 
 /* Corner blocks of a RecombineMatrix (Recombinations/matrices.jl:70-110):
  * ul is ul_rows x nl, lr is lr_rows x nr, column-major doubles. */
@@ -219,6 +220,20 @@ bsk_status bsk_cyclic_create_device(const double *d_a, const double *d_b, const 
 /* d_rhs interleaved [n][nrhs], solved in place. */
 bsk_status bsk_cyclic_solve(const bsk_cyclic *h, double *d_rhs, int64_t nrhs, void *stream);
 bsk_status bsk_cyclic_destroy(bsk_cyclic *h);
+
+/* ---- cyclic banded (periodic interpolation, any order but k = 4) ---------------------
+ * The reference builds a SparseMatrixCSC and factorises it with UMFPACK
+ * (Collocation/Collocation.jl:141-142, SplineInterpolations.jl:109).  Here: banded LU of the
+ * non-wrapped part, once, + Woodbury correction of the two bw x bw corners.
+ * h_cband: (2 bw + 1) x n column-major, A(i, j) with cyclic offset d = i - j (mod n) in
+ * [shift - bw, shift + bw] at h_cband[(bw + d - shift) + (j - 1) (2 bw + 1)] (1-based i, j); `shift` =
+ * offset of the band centre (0 for even orders; odd orders have b_j peaking at x_{j+1}: shift = 1).
+ * Needs n >= 4 bw + 1. */
+bsk_status bsk_cyclic_banded_create(const double *h_cband, int64_t n, int32_t bw, int32_t shift,
+                                    int32_t device, bsk_cyclic_banded **out);
+/* In place on nrhs interleaved right-hand sides d_rhs[(i-1)*nrhs + c]. */
+bsk_status bsk_cyclic_banded_solve(const bsk_cyclic_banded *h, double *d_rhs, int64_t nrhs, void *stream);
+bsk_status bsk_cyclic_banded_destroy(bsk_cyclic_banded *h);
 
 /* ---- timing helper (CUDA events on `stream`) ----------------------------------------- */
 bsk_status bsk_event_create(int32_t device, void **event);

@@ -281,3 +281,68 @@ def fit_smoothing(xs, ys, lam, weights=None):
     Lc = np.linalg.cholesky((M + M.T) / 2)                   # cholesky!(Hermitian(M)), :93
     z = 2 * (A.T @ (W @ np.asarray(ys, dtype=np.float64)))   # :113-114
     return np.linalg.solve(Lc.T, np.linalg.solve(Lc, z)), t, rc
+
+
+def periodic_knots(data, k):
+    """Materialised PeriodicKnots t[1..N+k] (src/BSplines/periodic.jl:62,102-115): t[i] = xi[i - k/2] +- L."""
+    data = _np(data, np.float64)
+    N = data.size - 1
+    L = data[-1] - data[0]
+    out = np.empty(N + k)
+    for i in range(1, N + k + 1):
+        x = 0.0
+        j = i - k // 2
+        while j < 1:
+            x -= L
+            j += N
+        while j > N + 1:
+            x += L
+            j -= N
+        out[i - 1] = x + data[j - 1]
+    return out
+
+
+def collocation_points_periodic(k, data):
+    """collocation_points(::PeriodicBSplineBasis): even k -> the knots (SameAsKnots), odd k -> Greville
+    averages of the periodic knots clamped to the period (src/Collocation/points.jl:56-104,164-225)."""
+    data = _np(data, np.float64)
+    N = data.size - 1
+    if k % 2 == 0:
+        return data[:-1].copy()
+    t = periodic_knots(data, k)
+    x = np.empty(N)
+    tsum = comp = 0.0
+    for i in range(N):
+        if i == 0:
+            tsum = 0.0
+            for j in range(2, k + 1):
+                tsum += t[i + j - 1]
+        else:
+            prev = tsum
+            y = t[i + k - 1] - comp
+            tsum = prev + y
+            comp = (tsum - prev) - y
+            prev = tsum
+            y = -t[i] - comp
+            tsum = prev + y
+            comp = (tsum - prev) - y
+        x[i] = min(max(tsum / (k - 1), data[0]), data[-1])
+    return x
+
+
+def periodic_collocation_dense(k, data, x, nderiv=0, clip=np.finfo(np.float64).eps):
+    """collocation_matrix!(C, B::PeriodicBSplineBasis, x, Derivative(n)) as a dense N x N matrix
+    (src/Collocation/Collocation.jl:209-251; column wrap = basis_to_array_index,
+    src/BSplines/periodic.jl:245-253).  The reference stores it sparse and factorises with UMFPACK
+    (Collocation.jl:141-142); a dense pivoted solve of this matrix is the oracle for those orders."""
+    data = _np(data, np.float64); x = _np(x, np.float64)
+    N = data.size - 1
+    idx, bs = evaluate_all(KIND_PERIODIC, k, data, x, nderiv=nderiv)
+    A = np.zeros((x.size, N))
+    for i in range(x.size):
+        for d in range(1, k + 1):
+            v = bs[i, d - 1]
+            if abs(v) <= clip:
+                continue
+            A[i, (int(idx[i]) - d) % N] = v                  # j = jlast + 1 - d (1-based), wrapped
+    return A

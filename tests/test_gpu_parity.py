@@ -882,3 +882,36 @@ def test_fit_smoothing_golden_and_oracle(bk, oracle, synth):
         bk.fit(bk.BSplineOrder(4), xs, ys, 0.1, weights=np.ones(3))
     with pytest.raises(bk.ArgumentError):
         bk.fit(bk.BSplineOrder(6), xs, ys, 0.1)
+
+
+@pytest.mark.parametrize("k,N", [(3, 64), (5, 300), (6, 1000), (7, 50), (8, 4096)])
+def test_periodic_interpolation_general_order(bk, oracle, synth, k, N):
+    """interpolate(x, y, BSplineOrder(k), Periodic(L)) for k not in {2, 4}: the reference factorises a
+    SparseMatrixCSC with UMFPACK (Collocation.jl:141-142); here banded LU + Woodbury corners.  Checked
+    against a dense pivoted solve of the oracle's collocation matrix and I.(xs) ≈ ys (test/periodic.jl:159-180)."""
+    import torch
+    L = 2.0
+    x = -1.0 + L * synth.breakpoints(41, N + 1)[:-1]
+    data = bk.make_knots(x, k, bk.Periodic(L))
+    assert np.array_equal(data, oracle.make_knots_periodic(x, k, L))
+    B = bk.PeriodicBSplineBasis(k, data)
+    assert np.array_equal(bk.collocation_points(B), oracle.collocation_points_periodic(k, data))
+    Cm = bk.collocation_matrix(B, x)
+    A = oracle.periodic_collocation_dense(k, data, x)
+    assert np.array_equal(Cm.dense(), A)                             # K2 rows are bit-exact
+    D1 = bk.collocation_matrix(B, x, bk.Derivative(1))
+    assert np.array_equal(D1.dense(), oracle.periodic_collocation_dense(k, data, x, 1))
+    M = 2048 if N <= 1000 else 256
+    Y = (2 * synth.u_numpy(43, 0, N * M) - 1).reshape(N, M)
+    itp = bk.SplineInterpolation(B, x)
+    itp.interpolate_(torch.from_numpy(Y).cuda())
+    cs = itp.coefs.cpu().numpy()
+    ref = np.linalg.solve(A, Y[:, :64])
+    assert relerr(cs[:, :64], ref) < 1e-12
+    vals = itp.splines(x)                                            # all data sets at the data points
+    assert np.max(np.abs(np.asarray(vals) - Y)) < 1e-11
+    S = bk.interpolate(x, Y[:, 3].copy(), bk.BSplineOrder(k), bk.Periodic(L))      # single data set
+    assert np.max(np.abs(S(x) - Y[:, 3])) < 1e-11
+    xs = np.linspace(-1, 1, 57)
+    assert np.max(np.abs(S(xs) - S(xs + L))) < 1e-11
+    assert relerr(S(xs), oracle.spline_eval(1, k, data, ref[:, 3].copy(), xs)) < 1e-11

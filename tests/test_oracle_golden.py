@@ -310,3 +310,27 @@ def test_class_c_smoothing_fit(oracle):
     vals = np.array([sum(bs[p, d] * c0[idx[p] - d - 1] for d in range(4) if 0 <= idx[p] - d - 1 < c0.size)
                      for p in range(xs.size)])
     assert np.max(np.abs(vals - ys)) < 1e-9
+
+
+@pytest.mark.parametrize("k", [3, 5, 6, 8])
+def test_periodic_interpolation_general_order(oracle, k):
+    """Periodic interpolation for k not in {2, 4}: I.(xs) ≈ ys (test/periodic.jl:159-180); collocation
+    points: even k = knots, odd k = knot averages inside the period."""
+    rng = np.random.default_rng(5)
+    N, L = 40, 2.0
+    x = np.sort(-1.0 + L * (np.arange(N) + 0.6 * (rng.random(N) - 0.5)) / N)
+    data = oracle.make_knots_periodic(x, k, L)
+    xc = oracle.collocation_points_periodic(k, data)
+    if k % 2 == 0:
+        assert np.array_equal(xc, x)                    # SameAsKnots: make_knots put the knots on the data
+    else:
+        assert xc.size == N and np.all(np.diff(xc) > 0) and xc[0] >= data[0] and xc[-1] <= data[-1]
+    A = oracle.periodic_collocation_dense(k, data, x)
+    assert np.allclose(A.sum(axis=1), 1.0, atol=1e-14)  # partition of unity
+    y = np.cos(np.pi * x) + 0.3 * np.sin(3 * np.pi * x)
+    c = np.linalg.solve(A, y)
+    vals = oracle.spline_eval(1, k, data, c, x)
+    assert np.max(np.abs(vals - y)) < 1e-12
+    # periodicity of the interpolant
+    xs = np.linspace(-1, 1, 33)
+    assert np.max(np.abs(oracle.spline_eval(1, k, data, c, xs) - oracle.spline_eval(1, k, data, c, xs + L))) < 1e-12
