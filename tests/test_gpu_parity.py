@@ -915,3 +915,42 @@ def test_periodic_interpolation_general_order(bk, oracle, synth, k, N):
     xs = np.linspace(-1, 1, 57)
     assert np.max(np.abs(S(xs) - S(xs + L))) < 1e-11
     assert relerr(S(xs), oracle.spline_eval(1, k, data, ref[:, 3].copy(), xs)) < 1e-11
+
+
+@pytest.mark.parametrize("bw", [1, 2, 3, 4, 5, 6])
+def test_windowed_solve_halo_is_sufficient(bk, oracle, bw):
+    """The single-pass solve restarts its backward (and, with row segments, forward) recurrence from a
+    zero state `halo` rows away; the halo validated at factor time must make that exact to rounding
+    for ANY matrix it accepts: short matrices (n < halo), slowly decaying factors (weak diagonal
+    dominance), few columns (row segments).  Reference: ldiv! (Collocation/matrix.jl:218-271)."""
+    import torch
+    rng = np.random.default_rng(100 + bw)
+    for n in (4 * bw + 1, 33, 50, 130, 1000, 4096):
+        for alpha in (0.3, 0.9, 0.99):
+            band = np.zeros((2 * bw + 1, n), order="F")
+            band[bw, :] = 1.0
+            off = rng.uniform(-1, 1, size=(2 * bw, n)) * alpha / (2 * bw)
+            band[:bw, :] = off[:bw]
+            band[bw + 1:, :] = off[bw:]
+            for j in range(n):                       # entries outside the matrix
+                for r in range(2 * bw + 1):
+                    i = j + r - bw
+                    if i < 0 or i >= n:
+                        band[r, j] = 0.0
+            lu_ref = band.copy(order="F")
+            assert oracle.banded_lu(lu_ref) == 0
+            F = bk.CollocationMatrix(band.copy(order="F")).lu_()
+            if F.halo == 0:
+                continue                             # windowed unavailable: AUTO uses the two-pass kernels
+            for M in (2048, 4096 if n <= 1000 else 2048):
+                Y = rng.uniform(-1, 1, size=(n, M))
+                want = Y[:, :48].copy()
+                oracle.banded_solve(lu_ref, want)
+                Z = torch.from_numpy(Y).cuda()
+                F.ldiv_(Z, algo=bk.SOLVE_WINDOWED)
+                got = Z[:, :48].cpu().numpy()
+                assert relerr(got, want) < 1e-13, (bw, n, alpha, M, F.halo)
+                # all columns agree with the bit-faithful two-pass kernels
+                Z2 = torch.from_numpy(Y).cuda()
+                F.ldiv_(Z2, algo=bk.SOLVE_TWOPASS)
+                assert float((Z - Z2).abs().max() / Z2.abs().max()) < 1e-13, (bw, n, alpha, M, F.halo)
