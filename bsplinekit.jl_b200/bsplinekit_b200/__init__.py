@@ -5,6 +5,7 @@ has not been built (no CPU fallback).
 """
 from ._lib import (ArgumentError, DimensionMismatch, ZeroPivotException, CudaError, UnsupportedError,
                    EVAL_AUTO, EVAL_DEBOOR, EVAL_PP, SOLVE_AUTO, SOLVE_TWOPASS, SOLVE_WINDOWED,
+                   EXTRAP_NONE, EXTRAP_FLAT, EXTRAP_LINEAR, EXTRAP_SMOOTH,
                    LIB_PATH, device_count, version)
 from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, period,
                   BSplineBasis, PeriodicBSplineBasis, RecombinedBSplineBasis, augment_knots,
@@ -12,4 +13,5 @@ from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, p
                   Spline, SplineBatch, collocation_points, greville_points, collocation_matrix, CollocationMatrix,
                   CyclicTridiagonalMatrix, CyclicBandedMatrix, lu, ldiv, make_knots, SplineInterpolation, interpolate,
                   approximate, approximate_, ApproxByInterpolation, VariationDiminishing, MinimiseL2Error,
-                  SplineApproximation, fit, SmoothingSpline, DomainError)
+                  SplineApproximation, fit, SmoothingSpline, DomainError,
+                  Flat, Linear, Smooth, SplineExtrapolation, extrapolate)

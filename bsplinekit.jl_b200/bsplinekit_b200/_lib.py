@@ -15,6 +15,7 @@ BSK_F32, BSK_F64 = 0, 1
 BASIS_PLAIN, BASIS_PERIODIC, BASIS_RECOMBINED = 0, 1, 2
 EVAL_AUTO, EVAL_DEBOOR, EVAL_PP = 0, 1, 2
 SOLVE_AUTO, SOLVE_TWOPASS, SOLVE_WINDOWED = 0, 1, 2
+EXTRAP_NONE, EXTRAP_FLAT, EXTRAP_LINEAR, EXTRAP_SMOOTH = 0, 1, 2, 3
 
 
 class ArgumentError(ValueError):
@@ -82,6 +83,7 @@ SIGNATURES = {
     "bsk_spline_knots": (_i32, [_vp, _vp, _i64]),
     "bsk_spline_derivative": (_i32, [_vp, _i32, _pp]),
     "bsk_spline_eval": (_i32, [_vp, _vp, _i64, _i32, C.POINTER(_i32), _pp, _i32, _vp]),
+    "bsk_spline_eval_extrap": (_i32, [_vp, _vp, _i64, _i32, C.POINTER(_i32), _pp, _i32, _i32, _vp]),
     "bsk_spline_eval_host": (_i32, [_vp, _vp, _i64, _i32, C.POINTER(_i32), _pp, _i32]),
     "bsk_spline_eval_multi": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "bsk_collocation_matrix": (_i32, [_vp, _vp, _i64, _i32, _dbl, _vp, C.POINTER(_i64), _vp]),

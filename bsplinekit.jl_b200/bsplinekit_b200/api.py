@@ -557,20 +557,26 @@ class Spline:
         check(lib.bsk_spline_derivative(self._handle, int(n), C.byref(out)))
         return Spline(self.basis, _handle=out, _basis_info=(self._dt, self.k - n))
 
-    def evaluate(self, x, derivs=(0,), algo=EVAL_AUTO, out=None):
+    def evaluate(self, x, derivs=(0,), algo=EVAL_AUTO, out=None, extrap=0):
         """Evaluate D^d S for every d in `derivs` at all points, in one pass over x.
-        x: scalar, numpy array (host path, pipelined H2D/kernel/D2H) or CUDA tensor."""
+        x: scalar, numpy array (host path, pipelined H2D/kernel/D2H) or CUDA tensor.
+        extrap: _lib.EXTRAP_* (see SplineExtrapolation)."""
         derivs = [int(d) for d in derivs]
         nout = len(derivs)
         dv = (C.c_int32 * nout)(*derivs)
         scalar = np.isscalar(x)
+        if extrap and not (isinstance(x, torch.Tensor) and x.is_cuda):
+            xt = torch.as_tensor(np.atleast_1d(np.asarray(x, dtype=_NP[self._dt]))).cuda()
+            res = [o.cpu().numpy() for o in self.evaluate(xt, derivs, algo, None, extrap)]
+            return [o[0] for o in res] if scalar else res
         if isinstance(x, torch.Tensor) and x.is_cuda:
             if x.dtype != _TORCH[self._dt]:
                 raise ArgumentError("device vector has dtype %s, expected %s" % (x.dtype, _TORCH[self._dt]))
             xd = x.contiguous().reshape(-1)
             outs = out if out is not None else [torch.empty_like(xd) for _ in derivs]
             ptrs = (C.c_void_p * nout)(*[o.data_ptr() for o in outs])
-            check(lib.bsk_spline_eval(self._handle, _ptr(xd), xd.numel(), nout, dv, ptrs, algo, _stream()))
+            check(lib.bsk_spline_eval_extrap(self._handle, _ptr(xd), xd.numel(), nout, dv, ptrs, algo, int(extrap),
+                                             _stream()))
             return [o.reshape(x.shape) for o in outs]
         xh = np.ascontiguousarray(np.atleast_1d(np.asarray(x, dtype=_NP[self._dt])))
         outs = out if out is not None else [np.empty_like(xh) for _ in derivs]
@@ -1128,6 +1134,49 @@ def interpolate(x, y, order, bc=None):
         raise ArgumentError("unknown boundary condition")
     itp = SplineInterpolation(B, xf)
     return itp.interpolate_(y)
+
+
+# ---- extrapolation (SplineExtrapolations) ----------------------------------------------------------
+
+class Flat:
+    """Flat() (SplineExtrapolations.jl:22-33): boundary values extended to the left and right."""
+    code = _lib.EXTRAP_FLAT
+
+
+class Linear:
+    """Linear() (SplineExtrapolations.jl:35-52): linear continuation with the boundary slope."""
+    code = _lib.EXTRAP_LINEAR
+
+
+class Smooth:
+    """Smooth() (SplineExtrapolations.jl:54-71): the boundary polynomial pieces continued, derivatives
+    up to order k - 2 stay continuous."""
+    code = _lib.EXTRAP_SMOOTH
+
+
+class SplineExtrapolation:
+    """SplineExtrapolation(S, method) (SplineExtrapolations.jl:73-101); the method rides along in the
+    evaluation kernel (bsk_spline_eval_extrap), no extra pass over the points."""
+
+    def __init__(self, sp, method):
+        if isinstance(sp, (SplineInterpolation, SplineApproximation, SplineExtrapolation)):
+            sp = sp.spline                                     # SplineWrapper, SplineExtrapolations.jl:90
+        if not isinstance(sp, Spline):
+            raise ArgumentError("expected a Spline or a spline wrapper")
+        if not isinstance(method, (Flat, Linear, Smooth)):
+            raise ArgumentError("unknown extrapolation method")
+        self.spline, self.method = sp, method
+
+    def evaluate(self, x, derivs=(0,), algo=EVAL_AUTO, out=None):
+        return self.spline.evaluate(x, derivs, algo, out, extrap=self.method.code)
+
+    def __call__(self, x, algo=EVAL_AUTO):
+        return self.evaluate(x, (0,), algo)[0]
+
+
+def extrapolate(sp, method):
+    """extrapolate(S, method) (SplineExtrapolations.jl:103-111)."""
+    return SplineExtrapolation(sp, method)
 
 
 # ---- approximation (SplineApproximations) ----------------------------------------------------------

@@ -116,7 +116,7 @@ k_evaluate_all(KnotView<KT> kv, RecombView rv, const KT *__restrict__ x, int64_t
 template <int K, int KIND, typename T>
 __global__ void __launch_bounds__(kThreads)
 k_spline_deboor(KnotView<T> kv, const T *__restrict__ coefs, int ncoef, const T *__restrict__ x,
-                int64_t n, T *__restrict__ out, int stage) {
+                int64_t n, T *__restrict__ out, int stage, int extrap) {
     extern __shared__ __align__(16) unsigned char smem[];
     size_t off = 0;
     const T *t = stage_knots(kv, smem, stage, off);
@@ -130,8 +130,14 @@ k_spline_deboor(KnotView<T> kv, const T *__restrict__ coefs, int ncoef, const T 
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
          p += (int64_t)gridDim.x * blockDim.x) {
         T xv = x[p];
+        if (extrap == BSK_EXTRAP_FLAT)                     // S(clamp(x, a, b)), SplineExtrapolations.jl:29-33
+            xv = xv < kv.a ? kv.a : (xv > kv.b ? kv.b : xv);
         int z;
         int i = find_interval<KIND>(kv, t, xv, z);
+        if (KIND == 0 && extrap == BSK_EXTRAP_SMOOTH && z != 0) {   // interval clamped, SplineExtrapolations.jl:60-71
+            i = i < K ? K : (i > ncoef ? ncoef : i);
+            z = 0;
+        }
         T r = (T)0;
         // i < K can only happen for knot vectors without full end multiplicity, where the
         // reference reads coefficients out of bounds; we return 0 there.
@@ -163,6 +169,7 @@ k_spline_pp(KnotView<T> kv, int ncoef, PPView<T> pv, const T *__restrict__ x, in
     }
     __syncthreads();
     const T xa = kv.a, xb = kv.b;
+    const int E = outs.extrap;
 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * PTS;
     for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PTS; base < n; base += stride) {
@@ -178,15 +185,18 @@ k_spline_pp(KnotView<T> kv, int ncoef, PPView<T> pv, const T *__restrict__ x, in
         T res[kMaxOut][PTS];
 #pragma unroll
         for (int q = 0; q < PTS; ++q) {
+            if (KIND == 1 && E == BSK_EXTRAP_FLAT)
+                xv[q] = xv[q] < xa ? xa : (xv[q] > xb ? xb : xv[q]);
             const T xq = xv[q];
             const bool isnan_ = !(xq == xq);
             bool outside;
             if (KIND == 1) outside = !(xq >= xa && xq < xb);
             else outside = !(xq >= xa && xq <= xb);
-            const T xs = outside ? xa : xq;
+            const T xs = outside ? ((KIND == 0 && E != 0 && xq > xa) ? xb : xa) : xq;
             T cm[K];
             T u;
             pp_lookup<K, T>(pv, xs, cm, &u);
+            if (KIND == 0 && E == BSK_EXTRAP_SMOOTH && outside) u += xq - xs;
 #pragma unroll
             for (int o = 0; o < kMaxOut; ++o) {
                 if (o < outs.nout) {
@@ -195,7 +205,15 @@ k_spline_pp(KnotView<T> kv, int ncoef, PPView<T> pv, const T *__restrict__ x, in
 #pragma unroll
                     for (int m = K - 1; m >= 0; --m)
                         if (m >= d) acc = fma(acc, u, d == 0 ? cm[m] : cm[m] * falling<T>(m, d));
-                    if (KIND == 0 && outside) acc = (T)0;       // Splines/spline.jl:164-168
+                    if (KIND == 0 && outside) {
+                        if (E == 0) acc = (T)0;                 // Splines/spline.jl:164-168
+                        else if (E == BSK_EXTRAP_LINEAR) {
+                            T cml[K];                       // separate copy: cm[] itself stays in registers
+#pragma unroll
+                            for (int m = 0; m < K; ++m) cml[m] = cm[m];
+                            acc += extrap_linear_term<K, T>(cml, u, d, xq - xs);
+                        }
+                    }
                     if (isnan_) acc = xq;
                     res[o][q] = acc;
                 }
@@ -624,7 +642,7 @@ bsk_status get_derivative(const bsk_spline *s_const, int nd, bsk_spline **out) {
 }
 
 template <int K, int KIND, typename T>
-bsk_status launch_deboor(const bsk_spline *s, const T *d_x, int64_t n, T *d_out, cudaStream_t st) {
+bsk_status launch_deboor(const bsk_spline *s, const T *d_x, int64_t n, T *d_out, int extrap, cudaStream_t st) {
     const bsk_basis *b = s->basis;
     KnotView<T> kv = make_view<T>(b);
     size_t smem = knots_smem_bytes<T>(b) + (size_t)s->ncoef * sizeof(T);
@@ -634,19 +652,19 @@ bsk_status launch_deboor(const bsk_spline *s, const T *d_x, int64_t n, T *d_out,
     BSK_CUDA(set_smem(kern, smem));
     int ctas = stage ? std::max<int>(1, (int)std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem, 1))) : 8;
     int grid = grid_for(n, b->device, ctas);
-    kern<<<grid, kThreads, smem, st>>>(kv, (const T *)s->d_coefs, (int)s->ncoef, d_x, n, d_out, stage);
+    kern<<<grid, kThreads, smem, st>>>(kv, (const T *)s->d_coefs, (int)s->ncoef, d_x, n, d_out, stage, extrap);
     BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }
 
 template <typename T>
-bsk_status eval_deboor_t(const bsk_spline *s, const T *d_x, int64_t n, T *d_out, cudaStream_t st) {
+bsk_status eval_deboor_t(const bsk_spline *s, const T *d_x, int64_t n, T *d_out, int extrap, cudaStream_t st) {
     const bsk_basis *b = s->basis;
     bsk_status rc = BSK_ERR_UNSUPPORTED;
     if (b->kind == BSK_BASIS_PERIODIC) {
-        BSK_DISPATCH_K(b->k, rc = (launch_deboor<K, 1, T>(s, d_x, n, d_out, st)))
+        BSK_DISPATCH_K(b->k, rc = (launch_deboor<K, 1, T>(s, d_x, n, d_out, extrap, st)))
     } else {
-        BSK_DISPATCH_K(b->k, rc = (launch_deboor<K, 0, T>(s, d_x, n, d_out, st)))
+        BSK_DISPATCH_K(b->k, rc = (launch_deboor<K, 0, T>(s, d_x, n, d_out, extrap, st)))
     }
     if (rc == BSK_ERR_UNSUPPORTED) set_error("unsupported order %d", b->k);
     return rc;
@@ -698,8 +716,15 @@ bsk_status dispatch_pp(const bsk_spline *s, const T *d_x, int64_t n, const EvalO
 
 template <typename T>
 bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout, const int32_t *derivs,
-                         void *const *d_outs, int algo, cudaStream_t st) {
+                         void *const *d_outs, int algo, int extrap, cudaStream_t st) {
     const bsk_basis *b = s->basis;
+    if (b->kind == BSK_BASIS_PERIODIC) {
+        if (extrap == BSK_EXTRAP_SMOOTH) extrap = BSK_EXTRAP_NONE;      // zone is always 0: nothing to do
+        if (extrap == BSK_EXTRAP_LINEAR) {
+            set_error("Linear extrapolation of a periodic spline is not supported");
+            return BSK_ERR_UNSUPPORTED;
+        }
+    }
     bool try_pp = (algo == BSK_EVAL_AUTO || algo == BSK_EVAL_PP) && pp_eligible(s);
     if (algo == BSK_EVAL_PP && !try_pp) {
         set_error("local-polynomial path needs full end-knot multiplicity");
@@ -718,6 +743,7 @@ bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout,
         EvalOuts outs;
         memset(&outs, 0, sizeof(outs));
         outs.nout = nout;
+        outs.extrap = extrap;
         for (int o = 0; o < nout; ++o) {
             outs.out[o] = d_outs[o];
             outs.deriv[o] = derivs[o];
@@ -771,6 +797,11 @@ bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout,
         if (used) return BSK_OK;
     }
     // de Boor in the reference's operation order, one pass per requested derivative
+    if (extrap == BSK_EXTRAP_LINEAR) {
+        set_error("Linear extrapolation needs the local-polynomial path (BSK_EVAL_AUTO / BSK_EVAL_PP on a "
+                  "basis with full end-knot multiplicity)");
+        return BSK_ERR_UNSUPPORTED;
+    }
     for (int o = 0; o < nout; ++o) {
         const bsk_spline *ds = s;
         if (derivs[o] > 0) {
@@ -779,7 +810,7 @@ bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout,
             if (rc != BSK_OK) return rc;
             ds = tmp;
         }
-        bsk_status rc = eval_deboor_t<T>(ds, d_x, n, (T *)d_outs[o], st);
+        bsk_status rc = eval_deboor_t<T>(ds, d_x, n, (T *)d_outs[o], extrap, st);
         if (rc != BSK_OK) return rc;
     }
     return BSK_OK;
@@ -1000,7 +1031,14 @@ bsk_status bsk_spline_derivative(const bsk_spline *s, int32_t nd, bsk_spline **o
 
 bsk_status bsk_spline_eval(const bsk_spline *s, const void *d_x, int64_t n, int32_t nout, const int32_t *derivs,
                            void *const *d_outs, int32_t algo, void *stream) {
+    return bsk_spline_eval_extrap(s, d_x, n, nout, derivs, d_outs, algo, BSK_EXTRAP_NONE, stream);
+}
+
+bsk_status bsk_spline_eval_extrap(const bsk_spline *s, const void *d_x, int64_t n, int32_t nout,
+                                  const int32_t *derivs, void *const *d_outs, int32_t algo, int32_t extrap,
+                                  void *stream) {
     BSK_REQUIRE(s && derivs && d_outs, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(extrap >= 0 && extrap <= 3, BSK_ERR_ARGUMENT, "unknown extrapolation method %d", extrap);
     BSK_REQUIRE(nout >= 1 && nout <= kMaxOut, BSK_ERR_ARGUMENT, "nout must be in 1..%d", kMaxOut);
     BSK_REQUIRE(algo >= 0 && algo <= 2, BSK_ERR_ARGUMENT, "unknown algo %d", algo);
     for (int o = 0; o < nout; ++o) {
@@ -1013,8 +1051,9 @@ bsk_status bsk_spline_eval(const bsk_spline *s, const void *d_x, int64_t n, int3
     BSK_REQUIRE(d_x, BSK_ERR_ARGUMENT, "NULL points");
     BSK_CUDA(cudaSetDevice(s->basis->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (s->basis->dtype == BSK_F64) return spline_eval_t<double>(s, (const double *)d_x, n, nout, derivs, d_outs, algo, st);
-    return spline_eval_t<float>(s, (const float *)d_x, n, nout, derivs, d_outs, algo, st);
+    if (s->basis->dtype == BSK_F64)
+        return spline_eval_t<double>(s, (const double *)d_x, n, nout, derivs, d_outs, algo, extrap, st);
+    return spline_eval_t<float>(s, (const float *)d_x, n, nout, derivs, d_outs, algo, extrap, st);
 }
 
 }  // extern "C"

@@ -107,7 +107,9 @@ __device__ __noinline__ void fallback_interval(const PPView<T> pv, T xs, T *cm, 
     pp_lookup<K, T>(pv, xs, cm, u);
 }
 
-template <int K, int KIND, typename T, int DMASK, int STAGE>
+// EX = 1: extrapolation methods compiled in (SplineExtrapolations.jl:22-71); the plain kernels carry
+// none of that code.
+template <int K, int KIND, typename T, int DMASK, int STAGE, int EX>
 __global__ void __launch_bounds__(kCellThreads, 1)
 k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *__restrict__ x,
               int64_t nvec, EvalOuts outs) {
@@ -135,6 +137,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
     constexpr int XI = (K == 1) ? 1 : 0;                 // slot of the knot in a flagged record
 
     const T xa = cv.a, xb = cv.b, x0 = cv.x0, scale = cv.scale, cw = cv.cw;
+    const int E = EX ? outs.extrap : 0;
     const int ncell1 = cv.ncell - 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,11 +156,15 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
         bool out_[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
+            if (KIND == 1 && E == BSK_EXTRAP_FLAT)      // periodic + Flat: clamp(x, a, b), then as usual
+                xv[q] = xv[q] < xa ? xa : (xv[q] > xb ? xb : xv[q]);
             const T xq = xv[q];
             bool outside;                  // plain: zone != 0; periodic: outside the main period
             if (KIND == 1) outside = !(xq >= xa && xq < xb);
             else outside = !(xq >= xa && xq <= xb);
-            const T xs = outside ? xa : xq;
+            // outside: evaluate at a (no extrapolation: the result is discarded), or at the nearer
+            // boundary (Flat / Linear / Smooth, SplineExtrapolations.jl:22-71)
+            const T xs = outside ? ((KIND == 0 && E != 0 && xq > xa) ? xb : xa) : xq;
             int c = (int)((xs - x0) * scale);
             c = c < 0 ? 0 : (c > ncell1 ? ncell1 : c);
             xs_[q] = xs;
@@ -213,12 +220,21 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
                 for (int m = 0; m < K; ++m) cm[m] = cm2[m];
                 u = u2;
             }
+            if (KIND == 0 && E == BSK_EXTRAP_SMOOTH && outside) u += xq - xs;   // boundary piece continued
             T r1[NOUT];
             horner_outputs<K, T, DMASK>(cm, u, outs, r1);
 #pragma unroll
             for (int o = 0; o < NOUT; ++o) {
                 T val = r1[o];
-                if (KIND == 0 && outside) val = (T)0;       // Splines/spline.jl:164-168
+                if (KIND == 0 && outside) {
+                    if (E == 0) val = (T)0;                 // Splines/spline.jl:164-168
+                    else if (E == BSK_EXTRAP_LINEAR && (DMASK != 0 || o < outs.nout)) {
+                        T cml[K];                           // separate copy: cm[] itself stays in registers
+#pragma unroll
+                        for (int m = 0; m < K; ++m) cml[m] = cm[m];
+                        val += extrap_linear_term<K, T>(cml, u, outs.deriv[o], xq - xs);
+                    }
+                }
                 if (isnan_) val = xq;
                 res[o][q] = val;
             }
@@ -248,7 +264,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
     }
 }
 
-template <int K, int KIND, typename T, int DMASK>
+template <int K, int KIND, typename T, int DMASK, int EX = 0>
 bsk_status launch_cell_mask(const bsk_spline *s, const CellView<T> &cv, const PPView<T> &pv,
                             const KnotView<T> &kv, const T *d_x, int64_t nvec, const EvalOuts &outs,
                             cudaStream_t st) {
@@ -256,11 +272,11 @@ bsk_status launch_cell_mask(const bsk_spline *s, const CellView<T> &cv, const PP
     const int sms = sm_count(s->basis->device);
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nvec + kCellThreads - 1) / kCellThreads, sms));
     if (smem > 0) {
-        auto kern = k_spline_cell<K, KIND, T, DMASK, 1>;
+        auto kern = k_spline_cell<K, KIND, T, DMASK, 1, EX>;
         BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kCellThreads, smem, st>>>(cv, pv, kv, (int)s->ncoef, d_x, nvec, outs);
     } else {
-        auto kern = k_spline_cell<K, KIND, T, DMASK, 0>;
+        auto kern = k_spline_cell<K, KIND, T, DMASK, 0, EX>;
         kern<<<grid, kCellThreads, 0, st>>>(cv, pv, kv, (int)s->ncoef, d_x, nvec, outs);
     }
     BSK_CUDA(cudaGetLastError());
@@ -290,6 +306,7 @@ bsk_status launch_cell_k(const bsk_spline *s, const KnotView<T> &kv, const T *d_
         if (o > 0 && outs.deriv[o] <= outs.deriv[o - 1]) increasing = false;
         mask |= 1 << outs.deriv[o];
     }
+    if (outs.extrap != 0) return launch_cell_mask<K, KIND, T, 0, 1>(s, cv, pv, kv, d_x, nvec, outs, st);
     if (increasing && mask == 1) return launch_cell_mask<K, KIND, T, 1>(s, cv, pv, kv, d_x, nvec, outs, st);
     if (increasing && mask == 3 && K >= 2) return launch_cell_mask<K, KIND, T, (K >= 2 ? 3 : 1)>(s, cv, pv, kv, d_x, nvec, outs, st);
     return launch_cell_mask<K, KIND, T, 0>(s, cv, pv, kv, d_x, nvec, outs, st);

@@ -13,6 +13,7 @@ struct EvalOuts {
     const void *dcoefs[kMaxOut];   // coefficients of Derivative(deriv) * S (periodic slow path)
     int deriv[kMaxOut];
     int nout;
+    int extrap;                    // BSK_EXTRAP_*: what to return outside the domain
 };
 
 template <int K, typename T> struct PPRec {
@@ -47,6 +48,17 @@ __host__ __device__ __forceinline__ T falling(int m, int d) {
     for (int q = 0; q < BSK_MAXK; ++q)
         if (q < d) ff *= (T)(m - q);
     return ff;
+}
+
+// Rare path of Linear extrapolation (SplineExtrapolations.jl:40-52): slope of D^d S at the boundary
+// from the boundary polynomial piece, times the distance to the boundary.
+template <int K, typename T>
+__device__ __noinline__ T extrap_linear_term(const T *cm, T u, int d, T dx) {
+    T acc = (T)0;
+#pragma unroll
+    for (int m = K - 1; m >= 0; --m)
+        if (m >= d + 1) acc = fma(acc, u, cm[m] * falling<T>(m, d + 1));
+    return acc * dx;
 }
 
 // Locate the record of xs (which must lie inside the domain) and return its coefficients

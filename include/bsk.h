@@ -60,6 +60,14 @@ enum {
     BSK_EVAL_PP = 2       /* per-interval local-polynomial table staged in shared memory    */
 };
 
+/* extrapolation method of bsk_spline_eval_extrap (SplineExtrapolations.jl:22-71) */
+enum {
+    BSK_EXTRAP_NONE = 0,    /* 0 outside the domain (Splines/spline.jl:164-168)              */
+    BSK_EXTRAP_FLAT = 1,    /* Flat():   S(clamp(x, a, b))                                   */
+    BSK_EXTRAP_LINEAR = 2,  /* Linear(): S(a) + S'(a) (x - a), S(b) + S'(b) (x - b)           */
+    BSK_EXTRAP_SMOOTH = 3   /* Smooth(): the boundary polynomial pieces continued           */
+};
+
 /* banded multi-RHS solve algorithm selector */
 enum {
     BSK_SOLVE_AUTO = 0,
@@ -152,6 +160,14 @@ bsk_status bsk_spline_derivative(const bsk_spline *s, int32_t n, bsk_spline **ou
 bsk_status bsk_spline_eval(const bsk_spline *s, const void *d_x, int64_t n, int32_t nout,
                            const int32_t *derivs, void *const *d_outs, int32_t algo,
                            void *stream);
+/* extrapolate(S, method).(x) — SplineExtrapolation (src/SplineExtrapolations/SplineExtrapolations.jl:29-71),
+ * fused into the same evaluation pass.  Every requested output D^d S is extrapolated as its own spline
+ * (Linear uses D^{d+1} S at the boundary).  extrap: BSK_EXTRAP_*.  Periodic bases: Smooth is the
+ * identity, Flat clamps to one period, Linear is not supported.  Linear needs the table path
+ * (BSK_EVAL_AUTO / BSK_EVAL_PP). */
+bsk_status bsk_spline_eval_extrap(const bsk_spline *s, const void *d_x, int64_t n, int32_t nout,
+                                  const int32_t *derivs, void *const *d_outs, int32_t algo,
+                                  int32_t extrap, void *stream);
 /* Same through HOST buffers (H2D, kernel, D2H, synchronise). */
 bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n, int32_t nout,
                                 const int32_t *derivs, void *const *h_outs, int32_t algo);

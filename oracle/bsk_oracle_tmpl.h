@@ -309,6 +309,20 @@ void FN(orc_spline_eval)(int kind, int k, const KT *t, int64_t nt, const VT *c, 
     for (int64_t p = 0; p < n; ++p) out[p] = FN(spline_eval1)(&ts, c, ncoef, x[p], k);
 }
 
+/* extrapolate(S, Smooth()) (src/SplineExtrapolations/SplineExtrapolations.jl:60-71): the usual
+ * evaluation with the knot interval clamped to [k, N + k] whatever the zone. */
+void FN(orc_spline_eval_smooth)(int k, const KT *t, int64_t nt, const VT *c, int64_t ncoef,
+                                const KT *x, int64_t n, VT *out) {
+    FN(oknots) ts = FN(make_knots_view)(0, k, t, nt);
+    for (int64_t p = 0; p < n; ++p) {
+        int zone;
+        int64_t i = FN(find_knot_interval)(&ts, x[p], &zone);
+        if (i < k) i = k;
+        if (i > ncoef + k) i = ncoef + k;
+        out[p] = FN(spline_kernel)(&ts, c, ncoef, i, x[p], k);
+    }
+}
+
 /* Derivative(n) * S: _derivative (spline.jl:293-330; periodic: Splines/periodic.jl:76-117).
  * plain:    du_out has ncoef - nd entries (view du[1+nd : N]); new knots = t[1+nd : end-nd].
  * periodic: du_out has ncoef entries; new basis = same breakpoints, order k - nd. */

@@ -346,3 +346,27 @@ def periodic_collocation_dense(k, data, x, nderiv=0, clip=np.finfo(np.float64).e
                 continue
             A[i, (int(idx[i]) - d) % N] = v                  # j = jlast + 1 - d (1-based), wrapped
     return A
+
+
+def spline_extrapolate(method, k, t, coefs, x):
+    """extrapolate(S, method)(x) for a plain basis, method in {"flat", "linear", "smooth"}
+    (src/SplineExtrapolations/SplineExtrapolations.jl:22-71).  Linear: the slope is the value of
+    Derivative(1) * S at the boundary (the reference differentiates S with ForwardDiff, the same
+    number up to rounding)."""
+    t = _np(t, np.float64); c = _np(coefs, np.float64); x = _np(x, np.float64)
+    N = c.size
+    a, b = t[k - 1], t[N]
+    if method == "flat":
+        return spline_eval(0, k, t, c, np.clip(x, a, b))
+    if method == "smooth":
+        out = np.empty_like(x)
+        lib().orc_spline_eval_smooth_dd(C.c_int(k), _p(t), C.c_int64(t.size), _p(c), C.c_int64(N), _p(x),
+                                        C.c_int64(x.size), _p(out))
+        return out
+    assert method == "linear"
+    k1, t1, c1 = spline_derivative(0, k, t, c, 1)
+    va, vb = spline_eval(0, k, t, c, [a, b])
+    sa, sb = spline_eval(0, k1, t1, c1, [a, b])
+    out = spline_eval(0, k, t, c, np.clip(x, a, b))
+    out = np.where(x < a, va + sa * (x - a), out)
+    return np.where(x > b, vb + sb * (x - b), out)

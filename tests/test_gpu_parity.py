@@ -954,3 +954,56 @@ def test_windowed_solve_halo_is_sufficient(bk, oracle, bw):
                 Z2 = torch.from_numpy(Y).cuda()
                 F.ldiv_(Z2, algo=bk.SOLVE_TWOPASS)
                 assert float((Z - Z2).abs().max() / Z2.abs().max()) < 1e-13, (bw, n, alpha, M, F.halo)
+
+
+@pytest.mark.parametrize("k", [2, 4, 5, 8])
+def test_spline_extrapolation(bk, oracle, synth, k):
+    """extrapolate(S, Flat() / Linear() / Smooth()) (src/SplineExtrapolations/SplineExtrapolations.jl:22-71)
+    fused into the evaluation kernels; inside the domain nothing changes."""
+    import torch
+    breaks = synth.breakpoints(51, 40)
+    B = bk.BSplineBasis(k, breaks)
+    c = 2 * synth.u_numpy(52, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    t = B.knots()
+    n = 20001
+    x = np.concatenate([-0.7 + 2.4 * synth.u_numpy(53, 0, n), [0.0, 1.0, -1e-300, 1 + 1e-15, -3.0, 4.0, np.nan]])
+    xd = torch.from_numpy(x).cuda()
+    inside = (x >= 0) & (x <= 1)
+    plain = S(x)
+    for name, meth in (("flat", bk.Flat()), ("linear", bk.Linear()), ("smooth", bk.Smooth())):
+        E = bk.extrapolate(S, meth)
+        ref = oracle.spline_extrapolate(name, k, t, c, x[:-1])
+        for algo in (bk.EVAL_AUTO, bk.EVAL_PP, bk.EVAL_DEBOOR):
+            if name == "linear" and algo == bk.EVAL_DEBOOR:
+                with pytest.raises(bk.UnsupportedError):
+                    E(xd, algo=algo)
+                continue
+            got = E(xd, algo=algo).cpu().numpy()
+            assert np.isnan(got[-1])
+            if algo == bk.EVAL_DEBOOR:                          # reference operation order: bit-exact
+                assert np.array_equal(got[:-1], ref)
+            else:
+                assert relerr(got[:-1], ref) < TOL64
+            assert np.array_equal(got[inside], S(xd, algo=algo).cpu().numpy()[inside])
+        assert relerr(E(x[:-1]), ref) < TOL64                   # host arrays
+        assert np.array_equal(plain[~inside & ~np.isnan(x)], np.zeros(np.sum(~inside & ~np.isnan(x))))
+    # derivative outputs are extrapolated as their own splines
+    if k >= 4:
+        E = bk.extrapolate(S, bk.Linear())
+        v, d1 = E.evaluate(xd, (0, 1))
+        k1, t1, c1 = oracle.spline_derivative(0, k, t, c, 1)
+        assert relerr(d1.cpu().numpy()[:-1], oracle.spline_extrapolate("linear", k1, t1, c1, x[:-1])) < 1e-12
+        assert relerr(v.cpu().numpy()[:-1], oracle.spline_extrapolate("linear", k, t, c, x[:-1])) < TOL64
+    # wrappers: extrapolate(interpolation)
+    itp = bk.interpolate(breaks, np.cos(3 * breaks), bk.BSplineOrder(k))
+    Ef = bk.extrapolate(itp, bk.Flat())
+    assert Ef(-5.0) == itp(0.0) and Ef(7.0) == itp(1.0)
+    # periodic: Smooth is the identity, Flat clamps to one period
+    Bp = bk.PeriodicBSplineBasis(4, breaks)
+    Sp = bk.Spline(Bp, c[:len(Bp)])
+    xs = torch.from_numpy(-2 + 5 * synth.u_numpy(54, 0, 999)).cuda()
+    assert torch.equal(bk.extrapolate(Sp, bk.Smooth())(xs), Sp(xs))
+    assert relerr(bk.extrapolate(Sp, bk.Flat())(xs).cpu().numpy(), Sp(xs.clamp(0.0, 1.0)).cpu().numpy()) < TOL64
+    with pytest.raises(bk.UnsupportedError):
+        bk.extrapolate(Sp, bk.Linear())(xs)
