@@ -18,6 +18,41 @@ void set_error(const char *fmt, ...) {
 
 using namespace bsk;
 
+namespace bsk {
+
+void ensure_pool(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = 1ull << 30;     // keep up to 1 GiB of freed blocks instead of returning them at every sync
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[device] = true;
+}
+
+cudaError_t dev_malloc(void **p, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    ensure_pool(dev);
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t)0);
+    if (e == cudaSuccess) return cudaStreamSynchronize((cudaStream_t)0);   // usable from any stream from here on
+    cudaGetLastError();
+    return cudaMalloc(p, bytes ? bytes : 1);
+}
+
+cudaError_t dev_free(void *p) {
+    if (!p) return cudaSuccess;
+    cudaError_t e = cudaDeviceSynchronize();      // like cudaFree: nothing in flight may still use the block
+    if (e != cudaSuccess) return e;
+    e = cudaFreeAsync(p, (cudaStream_t)0);
+    if (e == cudaSuccess) return e;
+    cudaGetLastError();
+    return cudaFree(p);
+}
+
+}  // namespace bsk
+
 extern "C" {
 
 const char *bsk_version(void) { return "bsplinekit_b200 0.1.0 (sm_100a)"; }
@@ -215,21 +250,21 @@ bsk_status bsk_basis_create(int32_t kind, int32_t k, int32_t dtype, const void *
 
     cudaError_t e = cudaSetDevice(device);
     size_t es = dtype == BSK_F64 ? 8 : 4;
-    if (e == cudaSuccess) e = cudaMalloc(&b->d_knots, es * nknots);
+    if (e == cudaSuccess) e = bsk::dev_malloc(&b->d_knots, es * nknots);
     if (e == cudaSuccess) e = cudaMemcpy(b->d_knots, h_knots, es * nknots, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         std::vector<uint32_t> lut;
         build_lut(b->h_knots, dtype, lut, b->ncell, b->lut_scale);
         if (b->ncell > 0) {
-            e = cudaMalloc((void **)&b->d_lut, sizeof(uint32_t) * lut.size());
+            e = bsk::dev_malloc((void **)&b->d_lut, sizeof(uint32_t) * lut.size());
             if (e == cudaSuccess)
                 e = cudaMemcpy(b->d_lut, lut.data(), sizeof(uint32_t) * lut.size(), cudaMemcpyHostToDevice);
         }
     }
     if (e != cudaSuccess) {
         set_error("basis upload failed: %s", cudaGetErrorString(e));
-        if (b->d_knots) cudaFree(b->d_knots);
-        if (b->d_lut) cudaFree(b->d_lut);
+        if (b->d_knots) bsk::dev_free(b->d_knots);
+        if (b->d_lut) bsk::dev_free(b->d_lut);
         delete b;
         return BSK_ERR_CUDA;
     }
@@ -240,8 +275,8 @@ bsk_status bsk_basis_create(int32_t kind, int32_t k, int32_t dtype, const void *
 bsk_status bsk_basis_destroy(bsk_basis *b) {
     if (!b) return BSK_OK;
     cudaSetDevice(b->device);
-    if (b->d_knots) cudaFree(b->d_knots);
-    if (b->d_lut) cudaFree(b->d_lut);
+    if (b->d_knots) bsk::dev_free(b->d_knots);
+    if (b->d_lut) bsk::dev_free(b->d_lut);
     delete b;
     return BSK_OK;
 }

@@ -212,7 +212,7 @@ bsk_status bsk_cyclic_banded_create(const double *h_cband, int64_t n, int32_t bw
     BSK_CUDA(cudaSetDevice(device));
     bsk_cyclic_banded *h = new bsk_cyclic_banded();
     h->device = device; h->n = n; h->bw = bw; h->ntop = (int)ntop; h->nbot = (int)nbot; h->B = B; h->shift = shift; h->d_K = nullptr;
-    cudaError_t e = cudaMalloc((void **)&h->d_K, Kz.size() * 8);
+    cudaError_t e = bsk::dev_malloc((void **)&h->d_K, Kz.size() * 8);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_K, Kz.data(), Kz.size() * 8, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         set_error("cyclic banded upload failed: %s", cudaGetErrorString(e));
@@ -253,7 +253,7 @@ bsk_status bsk_cyclic_banded_solve(const bsk_cyclic_banded *h, double *d_rhs, in
 bsk_status bsk_cyclic_banded_destroy(bsk_cyclic_banded *h) {
     if (!h) return BSK_OK;
     cudaSetDevice(h->device);
-    if (h->d_K) cudaFree(h->d_K);
+    if (h->d_K) bsk::dev_free(h->d_K);
     if (h->B) bsk_banded_destroy(h->B);
     delete h;
     return BSK_OK;

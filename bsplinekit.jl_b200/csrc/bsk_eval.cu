@@ -333,7 +333,7 @@ bsk_status upload_coefs(bsk_spline *s) {
     const bsk_basis *b = s->basis;
     size_t es = b->dtype == BSK_F64 ? 8 : 4;
     BSK_CUDA(cudaSetDevice(b->device));
-    if (!s->d_coefs) BSK_CUDA(cudaMalloc(&s->d_coefs, es * std::max<int64_t>(1, s->ncoef)));
+    if (!s->d_coefs) BSK_CUDA(bsk::dev_malloc(&s->d_coefs, es * std::max<int64_t>(1, s->ncoef)));
     if (b->dtype == BSK_F64) {
         BSK_CUDA(cudaMemcpy(s->d_coefs, s->h_coefs.data(), es * s->ncoef, cudaMemcpyHostToDevice));
     } else {
@@ -499,11 +499,11 @@ bsk_status build_pp(bsk_spline *s) {
         scale = sc;
     }
     BSK_CUDA(cudaSetDevice(b->device));
-    if (s->d_pp) { cudaFree(s->d_pp); s->d_pp = nullptr; }
-    if (s->d_pp_lut) { cudaFree(s->d_pp_lut); s->d_pp_lut = nullptr; }
-    BSK_CUDA(cudaMalloc(&s->d_pp, recs.size() * sizeof(T)));
+    if (s->d_pp) { bsk::dev_free(s->d_pp); s->d_pp = nullptr; }
+    if (s->d_pp_lut) { bsk::dev_free(s->d_pp_lut); s->d_pp_lut = nullptr; }
+    BSK_CUDA(bsk::dev_malloc(&s->d_pp, recs.size() * sizeof(T)));
     BSK_CUDA(cudaMemcpy(s->d_pp, recs.data(), recs.size() * sizeof(T), cudaMemcpyHostToDevice));
-    BSK_CUDA(cudaMalloc((void **)&s->d_pp_lut, lut.size() * 4));
+    BSK_CUDA(bsk::dev_malloc((void **)&s->d_pp_lut, lut.size() * 4));
     BSK_CUDA(cudaMemcpy(s->d_pp_lut, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice));
     s->pp_nrec = nrec;
     s->pp_ncell = ncell;
@@ -609,10 +609,10 @@ bsk_status build_pp(bsk_spline *s) {
                                             : (((size_t)side * NCH + w) * nside + j) * VPA + e] = src[j * RECV + w * VPA + e];
             }
             for (void **p : {&s->d_cell_rec, &s->d_cell_rc})
-                if (*p) { cudaFree(*p); *p = nullptr; }
-            BSK_CUDA(cudaMalloc(&s->d_cell_rec, crec_cm.size() * sizeof(T)));
+                if (*p) { bsk::dev_free(*p); *p = nullptr; }
+            BSK_CUDA(bsk::dev_malloc(&s->d_cell_rec, crec_cm.size() * sizeof(T)));
             BSK_CUDA(cudaMemcpy(s->d_cell_rec, crec_cm.data(), crec_cm.size() * sizeof(T), cudaMemcpyHostToDevice));
-            BSK_CUDA(cudaMalloc(&s->d_cell_rc, rc_cm.size() * sizeof(T)));
+            BSK_CUDA(bsk::dev_malloc(&s->d_cell_rc, rc_cm.size() * sizeof(T)));
             BSK_CUDA(cudaMemcpy(s->d_cell_rc, rc_cm.data(), rc_cm.size() * sizeof(T), cudaMemcpyHostToDevice));
             s->cell_ncell = (int)nc;
             s->cell_nside = nside;
@@ -961,11 +961,11 @@ bsk_status bsk_spline_destroy(bsk_spline *s) {
     if (s->basis) cudaSetDevice(s->basis->device);
     for (bsk_spline *d : s->derivs)
         if (d) bsk_spline_destroy(d);
-    if (s->d_coefs && s->owns_coefs) cudaFree(s->d_coefs);
-    if (s->d_pp) cudaFree(s->d_pp);
-    if (s->d_pp_lut) cudaFree(s->d_pp_lut);
-    if (s->d_cell_rec) cudaFree(s->d_cell_rec);
-    if (s->d_cell_rc) cudaFree(s->d_cell_rc);
+    if (s->d_coefs && s->owns_coefs) bsk::dev_free(s->d_coefs);
+    if (s->d_pp) bsk::dev_free(s->d_pp);
+    if (s->d_pp_lut) bsk::dev_free(s->d_pp_lut);
+    if (s->d_cell_rec) bsk::dev_free(s->d_cell_rec);
+    if (s->d_cell_rc) bsk::dev_free(s->d_cell_rc);
     if (s->basis) bsk_basis_destroy(s->basis);
     delete s;
     return BSK_OK;

@@ -26,10 +26,10 @@ std::mutex g_pool_mu[kMaxDev];
 
 cudaError_t pool_get(Pool &p, int slot, int b, size_t bytes, void **out) {
     if (p.cap[slot][b] < bytes) {
-        if (p.buf[slot][b]) cudaFree(p.buf[slot][b]);
+        if (p.buf[slot][b]) bsk::dev_free(p.buf[slot][b]);
         p.buf[slot][b] = nullptr;
         p.cap[slot][b] = 0;
-        cudaError_t e = cudaMalloc(&p.buf[slot][b], bytes);
+        cudaError_t e = bsk::dev_malloc(&p.buf[slot][b], bytes);
         if (e != cudaSuccess) return e;
         p.cap[slot][b] = bytes;
     }

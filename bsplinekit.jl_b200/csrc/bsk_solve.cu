@@ -354,7 +354,7 @@ bsk_status bsk_collocation_matrix(const bsk_basis *b, const double *d_x, int64_t
     const int nroww = 2 * (b->k - 2) + 1;
     BSK_CUDA(cudaMemsetAsync(d_band, 0, sizeof(double) * (size_t)nroww * (size_t)b->len, st));
     unsigned long long *d_cnt = nullptr;
-    BSK_CUDA(cudaMalloc((void **)&d_cnt, 8));
+    BSK_CUDA(bsk::dev_malloc((void **)&d_cnt, 8));
     BSK_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
     KnotView<double> kv = make_view_s<double>(b);
     const double dom_a = b->h_knots[b->k - 1], dom_b = b->h_knots[b->N];   // boundaries (basis.jl:217-222)
@@ -387,7 +387,7 @@ bsk_status bsk_collocation_cyclic(const bsk_basis *b, const double *d_x, int64_t
     BSK_CUDA(cudaMemsetAsync(d_b, 0, 8 * (size_t)nx, st));
     BSK_CUDA(cudaMemsetAsync(d_c, 0, 8 * (size_t)nx, st));
     unsigned long long *d_cnt = nullptr;
-    BSK_CUDA(cudaMalloc((void **)&d_cnt, 8));
+    BSK_CUDA(bsk::dev_malloc((void **)&d_cnt, 8));
     BSK_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
     KnotView<double> kv = make_view_s<double>(b);
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nx + kThreads - 1) / kThreads, 148 * 8));
@@ -419,12 +419,12 @@ static bsk_status banded_alloc(int64_t n, int32_t l, int32_t u, int32_t device, 
     h->d_w = h->d_lrow = h->d_urow = h->d_dinv = h->d_diag = h->d_urow_s = h->d_lrec = h->d_urec = nullptr;
     h->n_pad = 0;
     size_t nw = (size_t)(l + u + 1) * n, nb = (size_t)std::max(1, l) * n;
-    cudaError_t e = cudaMalloc((void **)&h->d_w, 8 * nw);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_lrow, 8 * nb);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_urow, 8 * nb);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_urow_s, 8 * nb);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_dinv, 8 * n);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_diag, 8 * n);
+    cudaError_t e = bsk::dev_malloc((void **)&h->d_w, 8 * nw);
+    if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_lrow, 8 * nb);
+    if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_urow, 8 * nb);
+    if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_urow_s, 8 * nb);
+    if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_dinv, 8 * n);
+    if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_diag, 8 * n);
     if (e != cudaSuccess) {
         set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
         bsk_banded_destroy(h);
@@ -457,12 +457,12 @@ bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot) {
     BSK_REQUIRE(!h->factored, BSK_ERR_ARGUMENT, "matrix is already factorised");
     BSK_CUDA(cudaSetDevice(h->device));
     long long *d_info = nullptr;
-    BSK_CUDA(cudaMalloc((void **)&d_info, 8));
+    BSK_CUDA(bsk::dev_malloc((void **)&d_info, 8));
     k_banded_lu<<<1, 1>>>(h->d_w, h->l, h->u, (int)h->n, d_info);
     long long info = 0;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(&info, d_info, 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_info);
+    bsk::dev_free(d_info);
     if (e != cudaSuccess) { set_error("banded LU failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
     if (info_pivot) *info_pivot = info;
     if (info != 0) {
@@ -555,7 +555,7 @@ bsk_status bsk_banded_matvec_solve(const bsk_banded *lu, const bsk_banded *Lm, c
         {
             std::lock_guard<std::mutex> lock(mu);
             if (!L->d_mrec || L->mrec_bw != lu->l || L->mrec_npad != lu->n_pad) {
-                if (L->d_mrec) { cudaFree(L->d_mrec); L->d_mrec = nullptr; }
+                if (L->d_mrec) { bsk::dev_free(L->d_mrec); L->d_mrec = nullptr; }
                 bsk_status rc = windowed_matrec(L, lu->l, lu->n_pad, &L->d_mrec);
                 if (rc != BSK_OK) return rc;
                 L->mrec_bw = lu->l;
@@ -573,15 +573,15 @@ bsk_status bsk_banded_matvec_solve(const bsk_banded *lu, const bsk_banded *Lm, c
 bsk_status bsk_banded_destroy(bsk_banded *h) {
     if (!h) return BSK_OK;
     cudaSetDevice(h->device);
-    if (h->d_w) cudaFree(h->d_w);
-    if (h->d_lrow) cudaFree(h->d_lrow);
-    if (h->d_urow) cudaFree(h->d_urow);
-    if (h->d_urow_s) cudaFree(h->d_urow_s);
-    if (h->d_lrec) cudaFree(h->d_lrec);
-    if (h->d_urec) cudaFree(h->d_urec);
-    if (h->d_dinv) cudaFree(h->d_dinv);
-    if (h->d_diag) cudaFree(h->d_diag);
-    if (h->d_mrec) cudaFree(h->d_mrec);
+    if (h->d_w) bsk::dev_free(h->d_w);
+    if (h->d_lrow) bsk::dev_free(h->d_lrow);
+    if (h->d_urow) bsk::dev_free(h->d_urow);
+    if (h->d_urow_s) bsk::dev_free(h->d_urow_s);
+    if (h->d_lrec) bsk::dev_free(h->d_lrec);
+    if (h->d_urec) bsk::dev_free(h->d_urec);
+    if (h->d_dinv) bsk::dev_free(h->d_dinv);
+    if (h->d_diag) bsk::dev_free(h->d_diag);
+    if (h->d_mrec) bsk::dev_free(h->d_mrec);
     delete h;
     return BSK_OK;
 }
@@ -629,7 +629,7 @@ static bsk_status cyclic_build(const std::vector<double> &a, const std::vector<d
     BSK_CUDA(cudaSetDevice(device));
     bsk_cyclic *h = new bsk_cyclic();
     h->device = device; h->n = n; h->vn = vn; h->denom = denom; h->tri = tri; h->zone = zone; h->d_q = nullptr;
-    cudaError_t e = cudaMalloc((void **)&h->d_q, 8 * (size_t)n);
+    cudaError_t e = bsk::dev_malloc((void **)&h->d_q, 8 * (size_t)n);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_q, q.data(), 8 * (size_t)n, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         set_error("cyclic upload failed: %s", cudaGetErrorString(e));
@@ -679,7 +679,7 @@ bsk_status bsk_cyclic_solve(const bsk_cyclic *h, double *d_rhs, int64_t nrhs, vo
 bsk_status bsk_cyclic_destroy(bsk_cyclic *h) {
     if (!h) return BSK_OK;
     cudaSetDevice(h->device);
-    if (h->d_q) cudaFree(h->d_q);
+    if (h->d_q) bsk::dev_free(h->d_q);
     if (h->tri) bsk_banded_destroy(h->tri);
     delete h;
     return BSK_OK;

@@ -638,8 +638,8 @@ bsk_status prepare_t(bsk_banded *h) {
     const int n = (int)h->n;
     const int n_pad = ((n + G - 1) / G) * G;
     h->n_pad = n_pad;
-    BSK_CUDA(cudaMalloc((void **)&h->d_lrec, sizeof(double) * (size_t)n_pad * LW));
-    BSK_CUDA(cudaMalloc((void **)&h->d_urec, sizeof(double) * (size_t)n_pad * UW));
+    BSK_CUDA(bsk::dev_malloc((void **)&h->d_lrec, sizeof(double) * (size_t)n_pad * LW));
+    BSK_CUDA(bsk::dev_malloc((void **)&h->d_urec, sizeof(double) * (size_t)n_pad * UW));
     int grid = std::max(1, std::min((n_pad + 255) / 256, 148 * 4));
     k_win_repack<BW><<<grid, 256>>>(h->d_w, n, n_pad, h->d_lrec, h->d_urec);
     BSK_CUDA(cudaGetLastError());
@@ -733,17 +733,9 @@ bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t 
     if (nseg > 1 && !fused) {
         // copy of the rows around every segment boundary (contiguous in memory: full rows)
         const int HS = HF + H;
-        static bool pool_set[64] = {false};
-        if (h->device >= 0 && h->device < 64 && !pool_set[h->device]) {
-            // keep freed scratch blocks cached in the stream-ordered pool (default: returned to the
-            // OS at every synchronisation, which makes the next cudaMallocAsync cost ~1 ms)
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
-                uint64_t thr = UINT64_MAX;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-            }
-            pool_set[h->device] = true;
-        }
+        // freed scratch blocks stay cached in the stream-ordered pool (default: returned to the OS at
+        // every synchronisation, which makes the next cudaMallocAsync cost ~1 ms)
+        ensure_pool(h->device);
         BSK_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * (size_t)(nseg - 1) * HS * ld, st));
         for (int b = 0; b + 1 < nseg; ++b) {
             const int64_t kb = (int64_t)(b + 1) * SEG;
@@ -807,7 +799,7 @@ bsk_status windowed_matrec(const bsk_banded *Lm, int bw, int n_pad, double **out
             rec[(size_t)(i - 1) * MW + m] = w[(size_t)(um + i - j) + (size_t)(j - 1) * (lm + um + 1)];
         }
     double *d = nullptr;
-    BSK_CUDA(cudaMalloc((void **)&d, rec.size() * 8));
+    BSK_CUDA(bsk::dev_malloc((void **)&d, rec.size() * 8));
     BSK_CUDA(cudaMemcpy(d, rec.data(), rec.size() * 8, cudaMemcpyHostToDevice));
     *out = d;
     return BSK_OK;

@@ -15,6 +15,14 @@
 namespace bsk {
 
 void set_error(const char *fmt, ...);
+// Device memory of the handles comes from the stream-ordered pool of the current device: plain
+// cudaMalloc / cudaFree cost tens of milliseconds each once the process maps many GB (measured:
+// 60 ms per band handle next to a 17 GB torch cache, 1 ms alone); pool allocations are served from
+// memory the pool retains (release threshold 1 GiB).
+void ensure_pool(int device);
+cudaError_t dev_malloc(void **p, size_t bytes);
+cudaError_t dev_free(void *p);
+template <typename P> inline cudaError_t dev_malloc(P **p, size_t bytes) { return dev_malloc((void **)p, bytes); }
 
 #define BSK_CUDA(call)                                                                       \
     do {                                                                                     \

@@ -128,3 +128,31 @@ if args.what == "fused":
     out2 = torch.empty_like(U)
     ms2 = timed(lambda: F.ldiv_mul(L, U, out=out2), args.reps)
     print("mul! then ldiv!:       %.3f ms  (max |diff| vs fused %.2e)" % (ms2, (out - out2).abs().max().item()))
+if args.what == "colloc":
+    import time
+    import ctypes as C
+    from bsplinekit_b200 import _lib
+    B5 = bk.BSplineBasis(8, synth.breakpoints(10, 99996))
+    R5 = bk.RecombinedBSplineBasis(B5, bk.Derivative(0) + 3 * bk.Derivative(1))
+    x5 = torch.from_numpy(bk.collocation_points(R5)).cuda()
+    if os.environ.get("PRE") == "cyclic":        # same process state as bench.py: a row-segmented solve first
+        n = 10000
+        Bc = bk.PeriodicBSplineBasis(4, synth.breakpoints(8, n + 1))
+        Mc = bk.collocation_matrix(Bc, bk.collocation_points(Bc))
+        Yc = (2 * synth.u_torch(9, 0, n * 16384) - 1).reshape(n, 16384)
+        Mc.ldiv_(Yc); torch.cuda.synchronize()
+        del Yc
+    if os.environ.get("PRE") == "big":
+        big = torch.empty(1 << 31, dtype=torch.float64, device="cuda"); del big
+    for it in range(4):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        band = torch.empty((len(R5), 13), dtype=torch.float64, device="cuda")
+        nout = C.c_int64(0)
+        _lib.check(_lib.lib.bsk_collocation_matrix(R5._handle, x5.data_ptr(), x5.numel(), 2, 2.2e-16, band.data_ptr(),
+                                                   C.byref(nout), None))
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        M = bk.CollocationMatrix(band)
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        del M
+        torch.cuda.synchronize(); t3 = time.perf_counter()
+        print("assembly %.2f ms, band handle %.2f ms, destroy %.2f ms" % (1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)))
