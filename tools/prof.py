@@ -156,3 +156,16 @@ if args.what == "colloc":
         del M
         torch.cuda.synchronize(); t3 = time.perf_counter()
         print("assembly %.2f ms, band handle %.2f ms, destroy %.2f ms" % (1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)))
+if args.what == "factor":
+    import time
+    for (n, k) in ((4096, 6), (100000, 8), (11, 4)):
+        xdata = synth.breakpoints(6, n)
+        Bi = bk.BSplineBasis(k, bk.make_knots(xdata, k), augment=False)
+        for it in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            Cm = bk.collocation_matrix(Bi, xdata)
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            Cm.lu_()
+            torch.cuda.synchronize(); t2 = time.perf_counter()
+        print("n=%d k=%d: assemble %.2f ms, lu! (BANFAC + repack + halo analysis) %.2f ms, halo %d" % (
+            n, k, 1e3 * (t1 - t0), 1e3 * (t2 - t1), Cm.halo))
