@@ -17,7 +17,7 @@
 module BSplineKitB200
 
 using BSplineKit
-using BSplineKit: BSplines, Splines, Collocation, SplineInterpolations, Recombinations
+using BSplineKit: BSplines, Splines, Collocation, SplineInterpolations, Recombinations, SplineExtrapolations
 using BSplineKit.BSplines: BSplineBasis, PeriodicBSplineBasis, AbstractBSplineBasis, knots, order
 using BSplineKit.Recombinations: RecombinedBSplineBasis, recombination_matrix, num_constraints,
     num_recombined, submatrices
@@ -265,6 +265,72 @@ function LinearAlgebra.ldiv!(F::DeviceBandedLU, Y::DeviceMatrix{Float64}; algo =
     check(ccall((:bsk_banded_solve, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Cvoid}),
                 F.ptr, Y.data.ptr, Y.M, algo, C_NULL))
     Y
+end
+
+# mul!(Y, L, X) on batches (Collocation/matrix.jl:91-94) — L must not be factorised
+function LinearAlgebra.mul!(Y::DeviceMatrix{Float64}, L::DeviceBandedLU, X::DeviceMatrix{Float64})
+    (X.N == L.n && Y.N == L.n && X.M == Y.M) || throw(DimensionMismatch("vectors `x` and `y` must have length $(L.n)"))
+    check(ccall((:bsk_banded_matvec, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Cvoid}),
+                L.ptr, X.data.ptr, Y.data.ptr, X.M, C_NULL))
+    Y
+end
+
+"""
+    ldiv_mul!(dU, F, L, U)
+
+`mul!(Y, L, U); ldiv!(dU, F, Y)` — the right-hand side of a collocation time step
+(examples/heat.jl:314-328) — in one pass over device memory.  `F` factorised, `L` not; `U` is only read.
+"""
+function ldiv_mul!(dU::DeviceMatrix{Float64}, F::DeviceBandedLU, L::DeviceBandedLU, U::DeviceMatrix{Float64})
+    (U.N == F.n && dU.N == F.n && U.M == dU.M) || throw(DimensionMismatch("vectors `x` and `y` must have length $(F.n)"))
+    check(ccall((:bsk_banded_matvec_solve, lib), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Cvoid}),
+                F.ptr, L.ptr, U.data.ptr, dU.data.ptr, U.M, C_NULL))
+    dU
+end
+
+# ---- periodic bases of order k ∉ {2, 4}: cyclic banded factorisation ---------------------------------
+"""Stands where the reference puts `lu(::SparseMatrixCSC)` (UMFPACK) for periodic bases
+(Collocation/Collocation.jl:141-142, SplineInterpolations.jl:107-109).  `cband` is the host-assembled
+(2bw+1) x N cyclic band store; `shift` the offset of the band centre (1 for odd orders)."""
+mutable struct DeviceCyclicBandedLU{T} <: Factorization{T}
+    ptr::Ptr{Cvoid}
+    n::Int
+end
+Base.size(F::DeviceCyclicBandedLU) = (F.n, F.n)
+
+function DeviceCyclicBandedLU(cband::Matrix{Float64}, shift::Integer = 0; device = Int32(0))
+    nb, N = size(cband)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:bsk_cyclic_banded_create, lib), Int32,
+                (Ptr{Float64}, Int64, Int32, Int32, Int32, Ptr{Ptr{Cvoid}}),
+                cband, N, (nb - 1) ÷ 2, shift, device, out))
+    F = DeviceCyclicBandedLU{Float64}(out[], N)
+    finalizer(f -> ccall((:bsk_cyclic_banded_destroy, lib), Int32, (Ptr{Cvoid},), f.ptr), F)
+end
+
+function LinearAlgebra.ldiv!(F::DeviceCyclicBandedLU, Y::DeviceMatrix{Float64})
+    Y.N == F.n || throw(DimensionMismatch("all vectors must have length $(F.n)"))
+    check(ccall((:bsk_cyclic_banded_solve, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Cvoid}),
+                F.ptr, Y.data.ptr, Y.M, C_NULL))
+    Y
+end
+
+# ---- extrapolation -------------------------------------------------------------------------------------
+extrap_code(::SplineExtrapolations.Flat) = Int32(1)
+extrap_code(::SplineExtrapolations.Linear) = Int32(2)
+extrap_code(::SplineExtrapolations.Smooth) = Int32(3)
+
+# (f::SplineExtrapolation)(xs) on device points   (SplineExtrapolations.jl:22-101)
+function (f::SplineExtrapolations.SplineExtrapolation)(xs::DeviceVector{T}) where {T}
+    S = SplineExtrapolations.spline(f)
+    out = DeviceVector{T}(undef, length(xs))
+    ptrs = Ptr{Cvoid}[out.ptr]
+    ds = Int32[0]
+    GC.@preserve ptrs ds check(ccall((:bsk_spline_eval_extrap, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Int32, Int32, Ptr{Cvoid}),
+        device_spline(S).ptr, xs.ptr, length(xs), 1, ds, ptrs, 0, extrap_code(SplineExtrapolations.method(f)), C_NULL))
+    out
 end
 
 """
