@@ -14,4 +14,5 @@ from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, p
                   CyclicTridiagonalMatrix, CyclicBandedMatrix, lu, ldiv, make_knots, SplineInterpolation, interpolate,
                   approximate, approximate_, ApproxByInterpolation, VariationDiminishing, MinimiseL2Error,
                   SplineApproximation, fit, SmoothingSpline, DomainError,
-                  Flat, Linear, Smooth, SplineExtrapolation, extrapolate)
+                  Flat, Linear, Smooth, SplineExtrapolation, extrapolate,
+                  galerkin_matrix, galerkin_projection)

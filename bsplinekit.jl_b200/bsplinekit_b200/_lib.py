@@ -105,6 +105,9 @@ SIGNATURES = {
     "bsk_cyclic_banded_create": (_i32, [_vp, _i64, _i32, _i32, _i32, _pp]),
     "bsk_cyclic_banded_solve": (_i32, [_vp, _vp, _i64, _vp]),
     "bsk_cyclic_banded_destroy": (_i32, [_vp]),
+    "bsk_galerkin_nodes": (_i32, [_vp, _vp, _i32, _vp, _i64, C.POINTER(_i64)]),
+    "bsk_galerkin_matrix": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "bsk_galerkin_projection": (_i32, [_vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "bsk_event_create": (_i32, [_i32, _pp]),
     "bsk_event_record": (_i32, [_vp, _vp]),
     "bsk_event_elapsed_ms": (_i32, [_vp, _vp, C.POINTER(C.c_float)]),

@@ -1179,6 +1179,46 @@ def extrapolate(sp, method):
     return SplineExtrapolation(sp, method)
 
 
+# ---- Galerkin (src/Galerkin) -------------------------------------------------------------------------
+
+def _gauss_legendre(n):
+    """Nodes and weights on [-1, 1] (the reference takes them from FastGaussQuadrature, quadratures.jl:35-49)."""
+    x, w = np.polynomial.legendre.leggauss(int(n))
+    return np.ascontiguousarray(x), np.ascontiguousarray(w)
+
+
+def galerkin_matrix(B, derivs=None, quadrature=None, as_band=False):
+    """galerkin_matrix(B, (Derivative(m), Derivative(n))) (Galerkin/linear.jl:60-311): banded matrix of the
+    integrals of D^m b_i D^n b_j, k Gauss-Legendre nodes per knot segment (exact for B-spline products).
+    Returns a CollocationMatrix handle (band store with k - 1 sub / super-diagonals), or the band store
+    itself as a CUDA tensor when as_band=True (needed for k = 8: 15 bands exceed the solver's 13)."""
+    d1, d2 = (0, 0) if derivs is None else (derivs[0].n, derivs[1].n)
+    if isinstance(B, PeriodicBSplineBasis):
+        raise _lib.UnsupportedError("Galerkin matrices of periodic bases are not built")
+    qx, qw = _gauss_legendre(B.k) if quadrature is None else quadrature
+    nb = 2 * (B.k - 1) + 1
+    band = torch.empty((len(B), nb), dtype=torch.float64, device="cuda")      # == (nb, n) column-major
+    check(lib.bsk_galerkin_matrix(B._handle, d1, d2, qx.ctypes.data_as(C.c_void_p), qw.ctypes.data_as(C.c_void_p),
+                                  qx.size, _ptr(band), _stream()))
+    return band if as_band else CollocationMatrix(band)
+
+
+def galerkin_projection(f, B, deriv=None):
+    """galerkin_projection(f, B, [Derivative(n)]) (Galerkin/projection.jl:1-99): phi_i = <f, D^n b_i>."""
+    nd = 0 if deriv is None else deriv.n
+    qx, qw = _gauss_legendre(B.k)
+    npts = C.c_int64(0)
+    check(lib.bsk_galerkin_nodes(B._handle, qx.ctypes.data_as(C.c_void_p), qx.size, None, 0, C.byref(npts)))
+    xs = np.empty(npts.value)
+    check(lib.bsk_galerkin_nodes(B._handle, qx.ctypes.data_as(C.c_void_p), qx.size, xs.ctypes.data_as(C.c_void_p),
+                                 xs.size, C.byref(npts)))
+    fx = torch.from_numpy(_apply(f, xs)).cuda()
+    phi = torch.empty(len(B), dtype=torch.float64, device="cuda")
+    check(lib.bsk_galerkin_projection(B._handle, nd, qx.ctypes.data_as(C.c_void_p), qw.ctypes.data_as(C.c_void_p),
+                                      qx.size, _ptr(fx), fx.numel(), _ptr(phi), _stream()))
+    return phi.cpu().numpy()
+
+
 # ---- approximation (SplineApproximations) ----------------------------------------------------------
 
 class VariationDiminishing:
@@ -1196,8 +1236,8 @@ class ApproxByInterpolation:
 
 
 class MinimiseL2Error:
-    """MinimiseL2Error() needs the Galerkin mass matrix and quadratures (SplineApproximations/minimiseL2.jl),
-    which are outside the evaluation / interpolation path built here."""
+    """MinimiseL2Error() (SplineApproximations/minimiseL2.jl:10-77): solve M c = phi with the Galerkin mass
+    matrix M and the projection phi_i = <b_i, f>."""
 
 
 class SplineApproximation:
@@ -1228,6 +1268,11 @@ def _apply(f, xs):
 
 def approximate_(f, A):
     """approximate!(f, A) (SplineApproximations.jl:121-130)."""
+    if isinstance(A.method, MinimiseL2Error):
+        phi = galerkin_projection(f, A.basis)                # minimiseL2.jl:68-76
+        A.data.ldiv_(phi.reshape(-1, 1))
+        A.spline = Spline(A.basis, phi)
+        return A
     if isinstance(A.method, VariationDiminishing):
         B = A.basis                                          # variation_diminishing.jl:35-44 (Greville sites)
         A.spline = Spline(B, _apply(f, np.asarray(collocation_points(B), dtype=np.float64)))
@@ -1243,7 +1288,10 @@ def approximate(f, B, method=None):
     if method is None:
         method = ApproxByInterpolation(B)
     if isinstance(method, MinimiseL2Error):
-        raise _lib.UnsupportedError("MinimiseL2Error needs the Galerkin module (out of scope of this library)")
+        if isinstance(B, PeriodicBSplineBasis):
+            raise _lib.UnsupportedError("MinimiseL2Error on periodic bases is not built")
+        Mfact = galerkin_matrix(B).lu_()                     # cholesky!(M) in the reference; M is SPD
+        return approximate_(f, SplineApproximation(method, B, Mfact))
     if isinstance(method, VariationDiminishing):
         return approximate_(f, SplineApproximation(method, B, None))
     if not isinstance(method, ApproxByInterpolation):

@@ -1,0 +1,210 @@
+// bsk_galerkin.cu — K10: Galerkin matrices and projections.
+//
+// galerkin_matrix!(M, B, (Derivative(m), Derivative(n)))  — src/Galerkin/linear.jl:220-311
+// galerkin_projection!(f, phi, B, Derivative(n))          — src/Galerkin/projection.jl:44-99
+//
+// The reference loops over the knot segments, evaluates all k non-zero B-splines at the k
+// Gauss-Legendre nodes of each segment (evaluate_all with a known `ileft`) and accumulates the outer
+// products into the banded matrix.  Here the nodes of ALL segments go through one batched
+// evaluate_all (K2, bit-exact), and a gather kernel with one thread per matrix entry adds the
+// contributions of the segments in the reference's own order (segment by segment, node by node, the
+// products formed left to right, no FMA contraction) — same result as the sequential loop, no atomics.
+#include <algorithm>
+
+#include "handles.cuh"
+
+using namespace bsk;
+
+namespace {
+
+struct Segments {
+    std::vector<double> x, y;          // nodes, alpha * w        (nseg * nq)
+    std::vector<int64_t> ileft;        // n - cl per node
+    std::vector<int32_t> seg_of_n;     // knot index n (1-based) -> segment slot or -1
+    int64_t nseg = 0;
+};
+
+// Knot segments inside the domain and their quadrature nodes (linear.jl:268-286, quadratures.jl:52-65).
+bsk_status build_segments(const bsk_basis *b, const double *qx, const double *qw, int nq, Segments &sg) {
+    BSK_REQUIRE(b->kind != BSK_BASIS_PERIODIC, BSK_ERR_UNSUPPORTED, "Galerkin matrices of periodic bases are not built");
+    BSK_REQUIRE(b->dtype == BSK_F64, BSK_ERR_UNSUPPORTED, "Galerkin assembly needs a Float64 basis");
+    const int k = b->k;
+    const int64_t nt = b->nt, N = b->N;
+    const std::vector<double> &t = b->h_knots;
+    const double xa = t[k - 1], xb = t[N];                 // boundaries(B)
+    const int off = b->rv.enabled ? b->rv.cl : 0;
+    sg.seg_of_n.assign((size_t)nt + 1, -1);
+    for (int64_t n = 1; n < nt; ++n) {
+        const double tn = t[n - 1], tn1 = t[n];
+        if (tn1 == tn) continue;
+        if (tn1 <= xa || tn >= xb) continue;
+        const double alpha = (tn1 - tn) / 2, beta = (tn + tn1) / 2;
+        sg.seg_of_n[n] = (int32_t)sg.nseg++;
+        for (int q = 0; q < nq; ++q) {
+            sg.x.push_back(alpha * qx[q] + beta);
+            sg.y.push_back(alpha * qw[q]);
+            sg.ileft.push_back(n - off);
+        }
+    }
+    return BSK_OK;
+}
+
+template <typename V>
+bsk_status upload(void **d, const std::vector<V> &h) {
+    BSK_CUDA(bsk::dev_malloc(d, std::max<size_t>(1, h.size()) * sizeof(V)));
+    BSK_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice));
+    return BSK_OK;
+}
+
+// One thread per band entry.  Band store data[bw + i - j, j], bw = k - 1.
+__global__ void __launch_bounds__(128)
+k_galerkin_gather(const double *__restrict__ bs1, const double *__restrict__ bs2, const int32_t *__restrict__ seg_of_n,
+                  const double *__restrict__ y, int nq, int k, int off, int64_t nt, int64_t N,
+                  double *__restrict__ band) {
+    const int bw = k - 1, nb = 2 * bw + 1;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N * nb; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = e / nb;
+        const int r = (int)(e - j * nb);
+        const int64_t i = j + r - bw;
+        double acc = 0.0;
+        if (i >= 0 && i < N) {
+            const int64_t i1 = i + 1, j1 = j + 1;
+            const int64_t lo = i1 > j1 ? i1 : j1, hi = (i1 < j1 ? i1 : j1) + k - 1;
+            for (int64_t ilast = lo; ilast <= hi; ++ilast) {          // segments in increasing order
+                const int64_t n = ilast + off;
+                if (n < 1 || n >= nt) continue;
+                const int s = seg_of_n[n];
+                if (s < 0) continue;
+                const int di = (int)(ilast + 1 - i1), dj = (int)(ilast + 1 - j1);
+                for (int q = 0; q < nq; ++q) {
+                    const int64_t p = (int64_t)s * nq + q;
+                    const double bi = bs1[p * k + di - 1], bj = bs2[p * k + dj - 1];
+                    acc = xadd(acc, xmul(xmul(y[p], bi), bj));         // A[i, j] += y * bi * bj   (linear.jl:305)
+                }
+            }
+        }
+        band[e] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_galerkin_project(const double *__restrict__ bs, const int32_t *__restrict__ seg_of_n, const double *__restrict__ y,
+                   const double *__restrict__ fx, int nq, int k, int off, int64_t nt, int64_t N,
+                   double *__restrict__ phi) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i1 = i + 1;
+        double acc = 0.0;
+        for (int64_t ilast = i1; ilast <= i1 + k - 1; ++ilast) {
+            const int64_t n = ilast + off;
+            if (n < 1 || n >= nt) continue;
+            const int s = seg_of_n[n];
+            if (s < 0) continue;
+            const int di = (int)(ilast + 1 - i1);
+            for (int q = 0; q < nq; ++q) {
+                const int64_t p = (int64_t)s * nq + q;
+                acc = xadd(acc, xmul(xmul(y[p], fx[p]), bs[p * k + di - 1]));   // y = alpha * w * f(x); phi[i] += y * bi
+            }
+        }
+        phi[i] = acc;
+    }
+}
+
+struct DevBufs {
+    void *x = nullptr, *y = nullptr, *il = nullptr, *seg = nullptr, *idx = nullptr, *bs1 = nullptr, *bs2 = nullptr;
+    ~DevBufs() {
+        for (void *p : {x, y, il, seg, idx, bs1, bs2})
+            if (p) bsk::dev_free(p);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// Number of quadrature points (nseg * nq) and, if h_x != NULL, their abscissae in the reference's
+// order (segment by segment) — where the caller evaluates f for bsk_galerkin_projection.
+bsk_status bsk_galerkin_nodes(const bsk_basis *b, const double *h_qx, int32_t nq, double *h_x, int64_t capacity,
+                              int64_t *npts) {
+    BSK_REQUIRE(b && h_qx && npts && nq >= 1, BSK_ERR_ARGUMENT, "NULL argument");
+    Segments sg;
+    std::vector<double> w(nq, 0.0);
+    bsk_status rc = build_segments(b, h_qx, w.data(), nq, sg);
+    if (rc != BSK_OK) return rc;
+    *npts = (int64_t)sg.x.size();
+    if (h_x) {
+        BSK_REQUIRE(capacity >= *npts, BSK_ERR_DIMENSION, "node buffer too small (%lld < %lld)", (long long)capacity,
+                    (long long)*npts);
+        std::copy(sg.x.begin(), sg.x.end(), h_x);
+    }
+    return BSK_OK;
+}
+
+// d_band: (2 (k - 1) + 1) x length(B) column-major band store, data[(k - 1) + i - j, j], fully overwritten.
+bsk_status bsk_galerkin_matrix(const bsk_basis *b, int32_t deriv1, int32_t deriv2, const double *h_qx,
+                               const double *h_qw, int32_t nq, double *d_band, void *stream) {
+    BSK_REQUIRE(b && h_qx && h_qw && d_band && nq >= 1, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(deriv1 >= 0 && deriv2 >= 0, BSK_ERR_ARGUMENT, "derivative order must be >= 0");
+    Segments sg;
+    bsk_status rc = build_segments(b, h_qx, h_qw, nq, sg);
+    if (rc != BSK_OK) return rc;
+    BSK_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k = b->k;
+    const int64_t npts = (int64_t)sg.x.size();
+    DevBufs d;
+    if ((rc = upload(&d.x, sg.x)) != BSK_OK || (rc = upload(&d.y, sg.y)) != BSK_OK ||
+        (rc = upload(&d.il, sg.ileft)) != BSK_OK || (rc = upload(&d.seg, sg.seg_of_n)) != BSK_OK)
+        return rc;
+    BSK_CUDA(bsk::dev_malloc(&d.idx, std::max<int64_t>(1, npts) * 8));
+    BSK_CUDA(bsk::dev_malloc(&d.bs1, std::max<int64_t>(1, npts) * k * 8));
+    rc = bsk_evaluate_all(b, d.x, npts, deriv1, BSK_F64, (const int64_t *)d.il, (int64_t *)d.idx, d.bs1, stream);
+    if (rc != BSK_OK) return rc;
+    const double *bs2 = (const double *)d.bs1;
+    if (deriv2 != deriv1) {
+        BSK_CUDA(bsk::dev_malloc(&d.bs2, std::max<int64_t>(1, npts) * k * 8));
+        rc = bsk_evaluate_all(b, d.x, npts, deriv2, BSK_F64, (const int64_t *)d.il, (int64_t *)d.idx, d.bs2, stream);
+        if (rc != BSK_OK) return rc;
+        bs2 = (const double *)d.bs2;
+    }
+    const int off = b->rv.enabled ? b->rv.cl : 0;
+    const int64_t nent = b->len * (2 * (k - 1) + 1);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nent + 127) / 128, 148 * 16));
+    k_galerkin_gather<<<grid, 128, 0, st>>>((const double *)d.bs1, bs2, (const int32_t *)d.seg, (const double *)d.y, nq, k, off,
+                                            b->nt, b->len, d_band);
+    BSK_CUDA(cudaGetLastError());
+    BSK_CUDA(cudaStreamSynchronize(st));                     // temporaries are released on return
+    return BSK_OK;
+}
+
+// phi[i] = sum over segments and nodes of (alpha w f(x)) b_i(x); d_fx = f at the nodes of bsk_galerkin_nodes.
+bsk_status bsk_galerkin_projection(const bsk_basis *b, int32_t deriv, const double *h_qx, const double *h_qw, int32_t nq,
+                                   const double *d_fx, int64_t nfx, double *d_phi, void *stream) {
+    BSK_REQUIRE(b && h_qx && h_qw && d_fx && d_phi && nq >= 1, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(deriv >= 0, BSK_ERR_ARGUMENT, "derivative order must be >= 0");
+    Segments sg;
+    bsk_status rc = build_segments(b, h_qx, h_qw, nq, sg);
+    if (rc != BSK_OK) return rc;
+    const int64_t npts = (int64_t)sg.x.size();
+    BSK_REQUIRE(nfx == npts, BSK_ERR_DIMENSION, "expected f at %lld quadrature nodes, got %lld", (long long)npts,
+                (long long)nfx);
+    BSK_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k = b->k;
+    DevBufs d;
+    if ((rc = upload(&d.x, sg.x)) != BSK_OK || (rc = upload(&d.y, sg.y)) != BSK_OK ||
+        (rc = upload(&d.il, sg.ileft)) != BSK_OK || (rc = upload(&d.seg, sg.seg_of_n)) != BSK_OK)
+        return rc;
+    BSK_CUDA(bsk::dev_malloc(&d.idx, std::max<int64_t>(1, npts) * 8));
+    BSK_CUDA(bsk::dev_malloc(&d.bs1, std::max<int64_t>(1, npts) * k * 8));
+    rc = bsk_evaluate_all(b, d.x, npts, deriv, BSK_F64, (const int64_t *)d.il, (int64_t *)d.idx, d.bs1, stream);
+    if (rc != BSK_OK) return rc;
+    const int off = b->rv.enabled ? b->rv.cl : 0;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((b->len + 127) / 128, 148 * 16));
+    k_galerkin_project<<<grid, 128, 0, st>>>((const double *)d.bs1, (const int32_t *)d.seg, (const double *)d.y, d_fx, nq, k,
+                                             off, b->nt, b->len, d_phi);
+    BSK_CUDA(cudaGetLastError());
+    BSK_CUDA(cudaStreamSynchronize(st));
+    return BSK_OK;
+}
+
+}  // extern "C"

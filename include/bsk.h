@@ -251,6 +251,23 @@ bsk_status bsk_cyclic_banded_create(const double *h_cband, int64_t n, int32_t bw
 bsk_status bsk_cyclic_banded_solve(const bsk_cyclic_banded *h, double *d_rhs, int64_t nrhs, void *stream);
 bsk_status bsk_cyclic_banded_destroy(bsk_cyclic_banded *h);
 
+/* ---- Galerkin matrices and projections (plain and recombined Float64 bases) ------------
+ * galerkin_matrix!(M, B, (Derivative(deriv1), Derivative(deriv2)))  — src/Galerkin/linear.jl:220-311:
+ *   M[i, j] = integral of D^deriv1 b_i * D^deriv2 b_j, Gauss-Legendre with the caller's nodes / weights on
+ *   [-1, 1] (h_qx, h_qw, nq; the reference uses nq = k, quadratures.jl:23-33) on every knot segment.
+ *   d_band: (2 (k - 1) + 1) x length(B) column-major band store data[(k - 1) + i - j, j], overwritten.
+ *   Contributions are added in the reference's order (segment by segment, node by node).
+ * galerkin_projection!(f, phi, B, Derivative(deriv))  — src/Galerkin/projection.jl:44-99:
+ *   phi[i] = integral of f * D^deriv b_i.  f is the caller's: bsk_galerkin_nodes returns the abscissae
+ *   (host, reference order), d_fx holds f there. */
+bsk_status bsk_galerkin_nodes(const bsk_basis *b, const double *h_qx, int32_t nq, double *h_x,
+                              int64_t capacity, int64_t *npts);
+bsk_status bsk_galerkin_matrix(const bsk_basis *b, int32_t deriv1, int32_t deriv2, const double *h_qx,
+                               const double *h_qw, int32_t nq, double *d_band, void *stream);
+bsk_status bsk_galerkin_projection(const bsk_basis *b, int32_t deriv, const double *h_qx,
+                                   const double *h_qw, int32_t nq, const double *d_fx, int64_t nfx,
+                                   double *d_phi, void *stream);
+
 /* ---- timing helper (CUDA events on `stream`) ----------------------------------------- */
 bsk_status bsk_event_create(int32_t device, void **event);
 bsk_status bsk_event_record(void *event, void *stream);

@@ -370,3 +370,66 @@ def spline_extrapolate(method, k, t, coefs, x):
     out = spline_eval(0, k, t, c, np.clip(x, a, b))
     out = np.where(x < a, va + sa * (x - a), out)
     return np.where(x > b, vb + sb * (x - b), out)
+
+
+def galerkin_matrix(k, t, d1=0, d2=0, recomb=None):
+    """galerkin_matrix!(M, B, (Derivative(d1), Derivative(d2))) as a dense matrix, the reference's own
+    loop (src/Galerkin/linear.jl:268-311): knot segments in order, k Gauss-Legendre nodes each
+    (quadratures.jl:23-65), evaluate_all with ileft, A[i, j] += y * bi * bj."""
+    t = _np(t, np.float64)
+    kind = KIND_RECOMBINED if recomb is not None else KIND_PLAIN
+    off = recomb.cl if recomb is not None else 0
+    Np = t.size - k
+    N = Np - (recomb.cl + recomb.cr if recomb is not None else 0)
+    xa, xb = t[k - 1], t[Np]
+    qx, qw = np.polynomial.legendre.leggauss(k)
+    A = np.zeros((N, N))
+    for n in range(1, t.size):
+        tn, tn1 = t[n - 1], t[n]
+        if tn1 == tn or tn1 <= xa or tn >= xb:
+            continue
+        alpha, beta = (tn1 - tn) / 2, (tn + tn1) / 2
+        xs = alpha * qx + beta
+        il = np.full(k, n - off, dtype=np.int64)
+        _, b1 = evaluate_all(kind, k, t, xs, nderiv=d1, ileft=il, recomb=recomb)
+        b2 = b1 if d2 == d1 else evaluate_all(kind, k, t, xs, nderiv=d2, ileft=il, recomb=recomb)[1]
+        ilast = n - off
+        for q in range(k):
+            y = alpha * qw[q]
+            for dj in range(1, k + 1):
+                j = ilast + 1 - dj
+                if not 1 <= j <= N:
+                    continue
+                for di in range(1, k + 1):
+                    i = ilast + 1 - di
+                    if not 1 <= i <= N:
+                        continue
+                    A[i - 1, j - 1] += y * b1[q, di - 1] * b2[q, dj - 1]
+    return A
+
+
+def galerkin_projection(f, k, t, nderiv=0, recomb=None):
+    """galerkin_projection!(f, phi, B, Derivative(n)) (src/Galerkin/projection.jl:60-99)."""
+    t = _np(t, np.float64)
+    kind = KIND_RECOMBINED if recomb is not None else KIND_PLAIN
+    off = recomb.cl if recomb is not None else 0
+    Np = t.size - k
+    N = Np - (recomb.cl + recomb.cr if recomb is not None else 0)
+    qx, qw = np.polynomial.legendre.leggauss(k)
+    phi = np.zeros(N)
+    for n in range(1, t.size):
+        tn, tn1 = t[n - 1], t[n]
+        if tn1 == tn:
+            continue
+        alpha, beta = (tn1 - tn) / 2, (tn + tn1) / 2
+        xs = alpha * qx + beta
+        il = np.full(k, n - off, dtype=np.int64)
+        _, bs = evaluate_all(kind, k, t, xs, nderiv=nderiv, ileft=il, recomb=recomb)
+        ilast = n - off
+        for q in range(k):
+            y = alpha * qw[q] * f(xs[q])
+            for di in range(1, k + 1):
+                i = ilast + 1 - di
+                if 1 <= i <= N:
+                    phi[i - 1] += y * bs[q, di - 1]
+    return phi

@@ -830,8 +830,6 @@ def test_approximate_goldens(bk):
     V = bk.approximate(np.exp, B, bk.VariationDiminishing())
     assert np.allclose(V.coefficients(), g["exp_vd_coefs_6digits"], rtol=6e-6)
     assert V(0.34) == pytest.approx(g["exp_S_vd(0.34)"], abs=4e-15)
-    with pytest.raises(bk.UnsupportedError):
-        bk.approximate(np.exp, B, bk.MinimiseL2Error())
     r = _goldens()["class_C"]["readme_approximate_k6"]
     B6 = bk.BSplineBasis(bk.BSplineOrder(6), np.log2(np.arange(1, 17)))
     fa = bk.approximate(lambda x: np.exp(-x) * np.sin(x), B6)
@@ -1007,3 +1005,55 @@ def test_spline_extrapolation(bk, oracle, synth, k):
     assert relerr(bk.extrapolate(Sp, bk.Flat())(xs).cpu().numpy(), Sp(xs.clamp(0.0, 1.0)).cpu().numpy()) < TOL64
     with pytest.raises(bk.UnsupportedError):
         bk.extrapolate(Sp, bk.Linear())(xs)
+
+
+@pytest.mark.parametrize("k,nbreaks", [(3, 6), (4, 60), (6, 300), (8, 40)])
+def test_galerkin_matrix_and_projection(bk, oracle, synth, k, nbreaks):
+    """galerkin_matrix / galerkin_projection (src/Galerkin/linear.jl:220-311, projection.jl:44-99): batched
+    evaluate_all at all quadrature nodes + one gather thread per entry adding the segments in the reference's
+    order — bit-exact against the oracle's sequential loop; plain and recombined bases, derivative pairs."""
+    breaks = synth.breakpoints(61, nbreaks) if nbreaks > 6 else dec_range(-1.0, 1.0, 6)
+    B = bk.BSplineBasis(k, breaks)
+    t = B.knots()
+    N = len(B)
+
+    def dense(band):
+        w = band.cpu().numpy().T                        # (nb, N) band store
+        bw = (w.shape[0] - 1) // 2
+        A = np.zeros((N, N))
+        for j in range(N):
+            for i in range(max(0, j - bw), min(N, j + bw + 1)):
+                A[i, j] = w[bw + i - j, j]
+        return A
+
+    for d1, d2 in ((0, 0), (1, 1), (0, min(2, k - 1))):
+        got = dense(bk.galerkin_matrix(B, (bk.Derivative(d1), bk.Derivative(d2)), as_band=True))
+        assert np.array_equal(got, oracle.galerkin_matrix(k, t, d1, d2)), (d1, d2)
+    f = lambda x: np.exp(-x) * np.sin(3 * x)
+    phi = bk.galerkin_projection(f, B)
+    assert np.array_equal(phi, oracle.galerkin_projection(f, k, t))
+    if k <= 6:                                            # recombined basis (Dirichlet + Neumann mix)
+        R = bk.RecombinedBSplineBasis(B, bk.Derivative(0), bk.Derivative(1))
+        rc = oracle.Recomb(R.cl, R.cr, R.nl, R.nr, R.ul, R.lr)
+        Rb = bk.galerkin_matrix(R, as_band=True).cpu().numpy().T
+        ref = oracle.galerkin_matrix(k, t, 0, 0, recomb=rc)
+        bw = k - 1
+        for j in range(len(R)):
+            for i in range(max(0, j - bw), min(len(R), j + bw + 1)):
+                assert Rb[bw + i - j, j] == ref[i, j]
+        assert np.array_equal(bk.galerkin_projection(f, R), oracle.galerkin_projection(f, k, t, recomb=rc))
+
+
+def test_approximate_minimise_l2_golden(bk):
+    """approximate(exp, B, MinimiseL2Error()) docstring values (SplineApproximations.jl:104-119)."""
+    g = _goldens()["class_C"]["approximate_k3"]
+    B = bk.BSplineBasis(g["k"], dec_range(g["breaks"]["a"], g["breaks"]["b"], g["breaks"]["n"]))
+    A = bk.approximate(np.exp, B, bk.MinimiseL2Error())
+    assert np.allclose(A.coefficients(), g["exp_l2_coefs_6digits"], rtol=6e-6)
+    assert A(0.34) == pytest.approx(g["exp_S_opt(0.34)"], abs=5e-15)
+    bk.approximate_(np.sin, A)                                  # approximate! reuses the factorisation
+    xs = np.linspace(-1, 1, 101)
+    assert np.max(np.abs(A(xs) - np.sin(xs))) < 2e-2
+    # polynomials of degree k - 1 are reproduced exactly (test/approximation.jl:38-49)
+    P = bk.approximate(lambda x: 1 - 2 * x + 3 * x * x, B, bk.MinimiseL2Error())
+    assert np.max(np.abs(P(xs) - (1 - 2 * xs + 3 * xs * xs))) < 1e-13

@@ -334,3 +334,19 @@ def test_periodic_interpolation_general_order(oracle, k):
     # periodicity of the interpolant
     xs = np.linspace(-1, 1, 33)
     assert np.max(np.abs(oracle.spline_eval(1, k, data, c, xs) - oracle.spline_eval(1, k, data, c, xs + L))) < 1e-12
+
+
+def test_class_c_minimise_l2(oracle):
+    """approximate(exp, B, MinimiseL2Error()): Galerkin mass matrix + projection
+    (SplineApproximations.jl:104-119, minimiseL2.jl:52-77, Galerkin/linear.jl:268-311, projection.jl:60-99)."""
+    g = GOLD["class_C"]["approximate_k3"]
+    k = g["k"]
+    t = oracle.augment_knots(dec_range(g["breaks"]["a"], g["breaks"]["b"], g["breaks"]["n"]), k)
+    M = oracle.galerkin_matrix(k, t)
+    assert np.max(np.abs(M - M.T)) < 1e-16 and M.sum() == pytest.approx(2.0, abs=1e-14)   # sum_ij <b_i, b_j> = b - a
+    c = np.linalg.solve(M, oracle.galerkin_projection(np.exp, k, t))
+    assert np.allclose(c, g["exp_l2_coefs_6digits"], rtol=6e-6)
+    assert oracle.spline_eval(0, k, t, c, [0.34])[0] == pytest.approx(g["exp_S_opt(0.34)"], abs=5e-15)
+    # stiffness matrix of the derivative: rows sum to zero (constants are in the kernel)
+    K1 = oracle.galerkin_matrix(k, t, 1, 1)
+    assert np.max(np.abs(K1.sum(axis=1))) < 1e-12
