@@ -333,6 +333,31 @@ def run_ours(args):
                                           "ms": ms, "value": world * nrhs / (ms * 1e-3), "unit": "RHS/s",
                                           "roofline_frac": SOLVE_BYTES_PER_ELEM * n * nrhs / (ms * 1e-3) / 1e9 / peak}
         del Lm
+        # all `nrhs` interpolants (coefficient block left by the solve) at 4096 points
+        SBn = bk.SplineBatch(Bi, Y)
+        xsn = synth.u_torch(5, 0, 4096)
+        outn = None
+        tot = 0.0
+        for it in range(args.warmup + args.solve_steps):
+            barrier()
+            s0 = torch.cuda.Event(enable_timing=True)
+            s1 = torch.cuda.Event(enable_timing=True)
+            s0.record()
+            outn = SBn(xsn)
+            s1.record()
+            torch.cuda.synchronize()
+            if it >= args.warmup:
+                tot += s0.elapsed_time(s1)
+        ms = max_over_ranks(tot / args.solve_steps)
+        if rank == 0:
+            cn = Y[:, 7].cpu().numpy().copy()
+            refn = O.spline_eval(0, kk, Bi.knots(), cn, xsn.cpu().numpy())
+            chk["vector_eval_relerr"] = float(np.max(np.abs(outn[:, 7].cpu().numpy() - refn)) / np.max(np.abs(refn)))
+        nb_ = 8.0 * 4096 * nrhs + 8.0 * n * nrhs                # values written + coefficient block read once
+        extra["n2_vector_valued_eval"] = {"metric": "spline values/s, %d splines sharing one basis x 4096 points" % nrhs,
+                                          "ms": ms, "value": world * 4096.0 * nrhs / (ms * 1e-3), "unit": "values/s",
+                                          "roofline_frac": nb_ / (ms * 1e-3) / 1e9 / peak}
+        del SBn, outn
 
     # ---- extra: configs[3] (periodic cubic) and configs[4] (Robin k = 8 + Float32 sweep) ------------
     if not args.no_extra_configs:

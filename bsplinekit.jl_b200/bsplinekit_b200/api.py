@@ -1333,6 +1333,69 @@ def _sparse_bandwidth(M):
     return int(np.max(np.abs(Mc.row[nz] - Mc.col[nz]))) if nz.any() else 0
 
 
+def _cyclic_sparse(B, xs, nd):
+    """Periodic cubic collocation matrix (cyclic tridiagonal, Collocation/cyclic.jl:21-33) as scipy CSR."""
+    import scipy.sparse as sp
+    n = len(B)
+    xd = torch.from_numpy(xs).cuda()
+    a = torch.empty(n, dtype=torch.float64, device="cuda")
+    b, c = torch.empty_like(a), torch.empty_like(a)
+    nout = C.c_int64(0)
+    check(lib.bsk_collocation_cyclic(B._handle, _ptr(xd), n, nd, float(np.finfo(np.float64).eps), _ptr(a), _ptr(b),
+                                     _ptr(c), C.byref(nout), _stream()))
+    a, b, c = (v.cpu().numpy() for v in (a, b, c))
+    i = np.arange(n)
+    return sp.csr_matrix((np.concatenate([a, b, c]), (np.concatenate([i, i, i]),
+                                                      np.concatenate([(i - 1) % n, i, (i + 1) % n]))), shape=(n, n))
+
+
+class _PeriodicSmoothing:
+    """fit(...; Periodic(L)) factorised (smoothing.jl:126-213): cyclic 7-band normal matrix (K7b)."""
+
+    def __init__(self, B, F, At2W, xs):
+        self.basis, self.F, self.At2W, self.xs = B, F, At2W, xs
+
+    def fit_(self, ys):
+        n = len(self.xs)
+        on_dev = isinstance(ys, torch.Tensor) and ys.is_cuda
+        yh = ys.cpu().numpy() if on_dev else np.asarray(ys, dtype=np.float64)
+        if yh.shape[0] != n:
+            raise DimensionMismatch("x and y vectors must have the same length")
+        z = np.ascontiguousarray(self.At2W @ yh.reshape(n, -1))      # 2 A' W y (smoothing.jl:196-199), once per fit
+        Z = torch.from_numpy(z).cuda()
+        self.F.ldiv_(Z)
+        if yh.ndim == 1:
+            return Spline(self.basis, Z[:, 0].cpu().numpy())
+        return SplineBatch(self.basis, Z)
+
+
+def _fit_periodic(xs, lam, bc, weights):
+    import scipy.sparse as sp
+    N = xs.size
+    ts = make_knots(xs, 4, bc)                               # smoothing.jl:137-138
+    B = PeriodicBSplineBasis(4, ts)
+    A = _cyclic_sparse(B, xs, 0)                             # smoothing.jl:141-144
+    D = _cyclic_sparse(B, xs, 2)
+    L = float(bc.L)
+    xm, xp = np.roll(xs, 1).copy(), np.roll(xs, -1).copy()   # x_{i-1}, x_{i+1} with the period (ts[i + h] == xs[i])
+    xm[0] -= L
+    xp[-1] += L
+    i = np.arange(N)
+    dl = sp.csr_matrix((np.concatenate([xs - xm, 2 * (xp - xm), xp - xs]),
+                        (np.concatenate([i, i, i]), np.concatenate([(i - 1) % N, i, (i + 1) % N]))), shape=(N, N))
+    H = dl @ D                                               # smoothing.jl:170
+    Bm = H.T @ D
+    W = sp.diags(weights) if weights is not None else sp.identity(N)
+    M = ((Bm + Bm.T) * (lam / 6) + 2 * (A.T @ W @ A)).tocoo()
+    d = (M.row - M.col + N // 2) % N - N // 2                # cyclic offsets
+    keep = M.data != 0
+    bw = max(1, int(np.max(np.abs(d[keep])))) if keep.any() else 1
+    cband = np.zeros((2 * bw + 1, N), order="F")
+    np.add.at(cband, (bw + d[keep], M.col[keep]), M.data[keep])
+    F = CyclicBandedMatrix(cband, 0)
+    return _PeriodicSmoothing(B, F, (2 * (A.T @ W)).tocsr(), xs)
+
+
 class SmoothingSpline:
     """What fit() factorised: the natural cubic basis, the LU of the 7-band normal matrix and the
     3-band matrix 2 A' W of the right-hand side.  `fit_(Y)` fits further data sets on the same points
@@ -1373,9 +1436,7 @@ def fit(order, xs, ys=None, lam=0.0, bc=None, weights=None):
         raise DomainError("the smoothing parameter λ must be non-negative (got %r)" % (lam,))    # smoothing.jl:49
     if bc is None:
         bc = Natural()
-    if isinstance(bc, Periodic):
-        raise _lib.UnsupportedError("periodic smoothing splines need a cyclic banded solve (not built)")
-    if not isinstance(bc, Natural):
+    if not isinstance(bc, (Natural, Periodic)):
         raise ArgumentError("the boundary condition must be Natural() or Periodic(L)")
     xs = np.ascontiguousarray(np.asarray(xs, dtype=np.float64))
     N = xs.size
@@ -1385,6 +1446,9 @@ def fit(order, xs, ys=None, lam=0.0, bc=None, weights=None):
         weights = np.asarray(weights, dtype=np.float64)
         if weights.shape != (N,):
             raise DimensionMismatch("the `weights` vector must have the same length as the data")   # :110
+    if isinstance(bc, Periodic):
+        sm = _fit_periodic(xs, lam, bc, weights)
+        return sm if ys is None else sm.fit_(ys)
     # natural cubic basis with knots = data points (smoothing.jl:56-58)
     R = RecombinedBSplineBasis(BSplineBasis(4, xs.copy()), Natural())
     Ab = collocation_matrix(R, xs)                           # smoothing.jl:61-64 (3 bands are populated)

@@ -433,3 +433,26 @@ def galerkin_projection(f, k, t, nderiv=0, recomb=None):
                 if 1 <= i <= N:
                     phi[i - 1] += y * bs[q, di - 1]
     return phi
+
+
+def fit_smoothing_periodic(xs, ys, lam, L, weights=None):
+    """fit(BSplineOrder(4), xs, ys, λ, Periodic(L); weights) with dense numpy algebra
+    (src/SplineInterpolations/smoothing.jl:126-213).  Returns (coefficients, breakpoints)."""
+    xs = _np(xs, np.float64)
+    N = xs.size
+    data = make_knots_periodic(xs, 4, L)
+    A = periodic_collocation_dense(4, data, xs, 0)
+    D = periodic_collocation_dense(4, data, xs, 2)
+    dl = np.zeros((N, N))                                    # :149-167 (ts[i + h] == xs[i])
+    for i in range(N):
+        xm = xs[i - 1] - (L if i == 0 else 0.0)
+        xp = xs[(i + 1) % N] + (L if i == N - 1 else 0.0)
+        dl[i, (i - 1) % N] += xs[i] - xm
+        dl[i, i] += 2 * (xp - xm)
+        dl[i, (i + 1) % N] += xp - xs[i]
+    H = dl @ D
+    Bm = H.T @ D
+    W = np.diag(np.asarray(weights, dtype=np.float64)) if weights is not None else np.eye(N)
+    M = (Bm + Bm.T) * (lam / 6) + 2 * (A.T @ W @ A)
+    z = 2 * (A.T @ (W @ np.asarray(ys, dtype=np.float64)))
+    return np.linalg.solve(M, z), data

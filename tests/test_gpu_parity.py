@@ -1057,3 +1057,26 @@ def test_approximate_minimise_l2_golden(bk):
     # polynomials of degree k - 1 are reproduced exactly (test/approximation.jl:38-49)
     P = bk.approximate(lambda x: 1 - 2 * x + 3 * x * x, B, bk.MinimiseL2Error())
     assert np.max(np.abs(P(xs) - (1 - 2 * xs + 3 * xs * xs))) < 1e-13
+
+
+def test_fit_smoothing_periodic(bk, oracle, synth):
+    """fit(BSplineOrder(4), xs, ys, λ, Periodic(L); weights) (smoothing.jl:126-213): cyclic 7-band normal
+    matrix through the cyclic banded solve; against the oracle's dense restatement, λ = 0 == periodic
+    interpolation, periodicity of the result, a batch of data sets."""
+    import torch
+    N, L = 200, 2.0
+    xs = -1.0 + L * synth.breakpoints(71, N + 1)[:-1]
+    ys = np.cos(np.pi * xs) + 0.1 * np.sin(40 * np.pi * xs)
+    w = 0.5 + synth.u_numpy(72, 0, N)
+    for lam, wt in ((1e-4, None), (1e-6, w), (0.0, None)):
+        S = bk.fit(bk.BSplineOrder(4), xs, ys, lam, bk.Periodic(L), weights=wt)
+        cref, data = oracle.fit_smoothing_periodic(xs, ys, lam, L, weights=wt)
+        xq = np.linspace(-1, 1, 301)[:-1]
+        ref = oracle.spline_eval(1, 4, data, cref, xq)
+        assert relerr(S(xq), ref) < 1e-9, lam                      # normal equations: cond up to ~1e6 here
+        assert np.max(np.abs(S(xq) - S(xq + L))) < 1e-12
+    assert np.max(np.abs(S(xs) - ys)) < 1e-10                       # λ = 0 interpolates
+    Y = np.stack([ys, 2 * ys, np.sin(np.pi * xs)], axis=1)
+    SB = bk.fit(bk.BSplineOrder(4), xs, torch.from_numpy(Y).cuda(), 1e-4, bk.Periodic(L))
+    c0, _ = oracle.fit_smoothing_periodic(xs, Y[:, 2], 1e-4, L)
+    assert relerr(SB.coefs[:, 2].cpu().numpy(), c0) < 1e-9
