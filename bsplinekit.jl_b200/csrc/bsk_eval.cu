@@ -547,8 +547,8 @@ bsk_status build_pp(bsk_spline *s) {
         const bool in_global = nc < 3 * nrec && nrec <= 400000 && getenv("BSK_NO_GLOBAL_CELL") == nullptr;
         if (in_global) {
             const char *e = getenv("BSK_GLOBAL_CELL_MULT2");        // cells per interval, x2
-            const int m2 = e ? std::max(6, atoi(e)) : 32;
-            nc = (nrec * m2) / 2;                                   // 16 cells per interval ...
+            const int m2 = e ? std::max(6, atoi(e)) : 64;
+            nc = (nrec * m2) / 2;                                   // 32 cells per interval ...
             const int64_t cap = (32ll << 20) / (int64_t)(RECV * sizeof(T));   // ... within 32 MB (L2-resident)
             nc = std::max<int64_t>(std::min(nc, cap), 3 * nrec);
         }

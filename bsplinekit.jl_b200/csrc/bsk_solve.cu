@@ -239,8 +239,7 @@ k_banded_lu_stream(double *__restrict__ w, int nrow, long long *info) {
 // Repack the factors row-wise for the solve kernels:
 //   lrow[r][j-1] = L(r, r-j) = w[mid + j, r - j],  urow[r][j-1] = U(r, r+j) = w[mid - j, r + j]
 __global__ void k_repack(const double *__restrict__ w, int bw, int n, double *__restrict__ lrow,
-                         double *__restrict__ urow, double *__restrict__ diag, double *__restrict__ dinv,
-                         double *__restrict__ urow_s) {
+                         double *__restrict__ urow, double *__restrict__ diag, double *__restrict__ dinv) {
     const int nroww = 2 * bw + 1, middle = bw + 1;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x + 1; r <= n; r += gridDim.x * blockDim.x) {
         for (int j = 1; j <= bw; ++j) {
@@ -250,8 +249,6 @@ __global__ void k_repack(const double *__restrict__ w, int bw, int n, double *__
         const double d = w[(middle - 1) + (size_t)(r - 1) * nroww];
         diag[r - 1] = d;
         dinv[r - 1] = 1.0 / d;
-        for (int j = 1; j <= bw; ++j)      // rows pre-scaled by 1/U(r,r) for the single-FMA backward chain
-            urow_s[(size_t)(r - 1) * bw + j - 1] = urow[(size_t)(r - 1) * bw + j - 1] * (1.0 / d);
     }
 }
 
@@ -350,12 +347,6 @@ k_cyclic_correct(const double *__restrict__ q, double *__restrict__ rhs, int64_t
             for (int r = n - zone; r < n; ++r) p[(int64_t)r * nrhs] -= alpha * __ldg(q + r);
         }
     }
-}
-
-inline int grid_cols(int64_t ncols, int device, int per_sm) {
-    int64_t want = (ncols + kThreads - 1) / kThreads;
-    int64_t cap = (int64_t)sm_count(device) * per_sm;
-    return (int)std::max<int64_t>(1, std::min(want, cap));
 }
 
 // Decay of the backward recurrence.  A backward sweep restarted at row s with a wrong state
@@ -605,13 +596,12 @@ static bsk_status banded_alloc(int64_t n, int32_t l, int32_t u, int32_t device, 
     bsk_banded *h = new bsk_banded();
     h->device = device; h->n = n; h->l = l; h->u = u; h->factored = false; h->halo = 0; h->halo_f = 0;
     h->d_mrec = nullptr; h->mrec_bw = -1; h->mrec_npad = 0;
-    h->d_w = h->d_lrow = h->d_urow = h->d_dinv = h->d_diag = h->d_urow_s = h->d_lrec = h->d_urec = nullptr;
+    h->d_w = h->d_lrow = h->d_urow = h->d_dinv = h->d_diag = h->d_lrec = h->d_urec = nullptr;
     h->n_pad = 0;
     size_t nw = (size_t)(l + u + 1) * n, nb = (size_t)std::max(1, l) * n;
     cudaError_t e = bsk::dev_malloc((void **)&h->d_w, 8 * nw);
     if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_lrow, 8 * nb);
     if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_urow, 8 * nb);
-    if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_urow_s, 8 * nb);
     if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_dinv, 8 * n);
     if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_diag, 8 * n);
     if (e != cudaSuccess) {
@@ -676,7 +666,7 @@ bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot) {
     }
     const int n = (int)h->n, bw = h->l;
     int grid = std::max(1, std::min((n + kThreads - 1) / kThreads, 148 * 4));
-    k_repack<<<grid, kThreads>>>(h->d_w, bw, n, h->d_lrow, h->d_urow, h->d_diag, h->d_dinv, h->d_urow_s);
+    k_repack<<<grid, kThreads>>>(h->d_w, bw, n, h->d_lrow, h->d_urow, h->d_diag, h->d_dinv);
     BSK_CUDA(cudaGetLastError());
     // decay bound for the windowed solve
     const double t_pack = now();
@@ -795,7 +785,6 @@ bsk_status bsk_banded_destroy(bsk_banded *h) {
     if (h->d_w) bsk::dev_free(h->d_w);
     if (h->d_lrow) bsk::dev_free(h->d_lrow);
     if (h->d_urow) bsk::dev_free(h->d_urow);
-    if (h->d_urow_s) bsk::dev_free(h->d_urow_s);
     if (h->d_lrec) bsk::dev_free(h->d_lrec);
     if (h->d_urec) bsk::dev_free(h->d_urec);
     if (h->d_dinv) bsk::dev_free(h->d_dinv);

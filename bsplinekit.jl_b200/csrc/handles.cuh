@@ -113,7 +113,6 @@ struct bsk_banded {
     // solve-ready repack (built by bsk_banded_lu): row-major per-row multipliers
     double *d_lrow;       // n x l : lrow[i][j-1] = L(i, i-j)      (multiplier of x[i-j] in row i)
     double *d_urow;       // n x u : urow[i][j-1] = U(i, i+j)
-    double *d_urow_s;     // n x u : urow scaled by 1/U(i,i) (windowed solve)
     double *d_dinv;       // n     : 1 / U(i,i)
     double *d_diag;       // n     : U(i,i)
     double *d_lrec, *d_urec;   // padded per-row records of the windowed solve (bsk_solve_win.cu)
