@@ -30,6 +30,7 @@
 #include <cuda.h>            // CUtensorMap (types only; the encoder is fetched at run time)
 
 #include "handles.cuh"
+#include "tma.cuh"
 
 using namespace bsk;
 
@@ -66,60 +67,8 @@ __global__ void k_win_repack(const double *__restrict__ w, int n, int n_pad, dou
     }
 }
 
-// ---- TMA (bulk async copy) + mbarrier plumbing ----------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void *gsrc, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
-                 "l"(gsrc), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-// 2-D tiled TMA load (box = 8 rows x 32 columns of the RHS block), SASS: UTMALDG.  Rows beyond the
-// end of the matrix are zero-filled by the hardware and still counted in the transaction bytes.
-__device__ __forceinline__ void tma_load_2d(unsigned smem_dst, const CUtensorMap *tmap, int c0, int r0, unsigned bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_dst),
-        "l"((unsigned long long)tmap), "r"(c0), "r"(r0), "r"(bar)
-        : "memory");
-}
-
 // (A TMA tile store of the results from the ring was tried and measured slower than direct
 // coalesced STG on B200: 1.28 ms vs 1.22 ms on C3.)
-
-// One lane of the (converged) warp; ptxas then knows the TMA operands are warp-uniform and emits
-// plain UBLKCP instead of a per-value election loop.
-__device__ __forceinline__ bool elect_one() {
-    unsigned pred;
-    asm volatile(
-        "{\n"
-        ".reg .pred P;\n"
-        "elect.sync _|P, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, P;\n"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
 
 template <int W>
 __device__ __forceinline__ void load_rec_s(const double *p, double *out) {      // shared memory, 16-B aligned
