@@ -412,6 +412,36 @@ def run_ours(args):
                                     "roofline_frac": 8.0 * npts / (ms * 1e-3) / 1e9 / peak}
         del x5f, o5
 
+    # ---- extra: configs[0] (the reference's own CPU-runnable case), in full, host arrays in and out --
+    if not args.no_extra_configs and rank == 0:
+        xdata1 = (np.arange(11.0)) ** 2
+        ydata1 = synth.u_numpy(1, 0, 11)
+        xs1 = 100.0 * synth.u_numpy(2, 0, 1000000)
+        t0 = time.perf_counter()
+        itp1 = bk.interpolate(xdata1, ydata1, bk.BSplineOrder(4))
+        v1 = itp1(xs1)                                   # first call builds the tables
+        torch.cuda.synchronize()
+        first_ms = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            itp1.interpolate_(ydata1)
+            v1 = itp1(xs1)
+        torch.cuda.synchronize()
+        rep_ms = 1e3 * (time.perf_counter() - t0) / 5
+        from oracle import oracle as O1
+        t1k = O1.make_knots(xdata1, 4)
+        band1, _ = O1.collocation_matrix(0, 4, t1k, xdata1)
+        O1.banded_lu(band1)
+        c1 = O1.banded_solve(band1, ydata1.copy().reshape(-1, 1)).ravel()
+        omp_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        ref1 = O1.spline_eval(0, 4, t1k, c1, xs1)
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        chk["c1_relerr"] = float(np.max(np.abs(v1 - ref1)) / np.max(np.abs(ref1)))
+        extra["c1_interpolate_eval_1e6"] = {"metric": "ms, interpolate((0:10).^2, y, k=4) + S.(xs) at 10^6 host points "
+                                                      "(H2D + kernel + D2H)", "first_call_ms": first_ms, "ms": rep_ms,
+                                            "cpu_port_eval_ms": cpu_ms}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
