@@ -1080,3 +1080,83 @@ def test_fit_smoothing_periodic(bk, oracle, synth):
     SB = bk.fit(bk.BSplineOrder(4), xs, torch.from_numpy(Y).cuda(), 1e-4, bk.Periodic(L))
     c0, _ = oracle.fit_smoothing_periodic(xs, Y[:, 2], 1e-4, L)
     assert relerr(SB.coefs[:, 2].cpu().numpy(), c0) < 1e-9
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 6, 8])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_eval_awkward_knot_vectors(bk, oracle, synth, k, dtype):
+    """Repeated interior knots (up to multiplicity k: discontinuous splines), clusters of nearly equal
+    knots, shifted / scaled domains: the table paths must pick exactly searchsortedlast's interval
+    (src/BSplines/evaluate_all.jl:102-119) and stay within tolerance; de Boor stays bit-exact."""
+    import torch
+    T = np.float64 if dtype == "f64" else np.float32
+    tol = TOL64 if dtype == "f64" else TOL32
+    rng = np.random.default_rng(1000 + k)
+    for case, (a, b) in enumerate(((0.0, 1.0), (1.0e3, 1.0e3 + 2.0), (-3.0e-3, 5.0e-3))):
+        base = np.sort(rng.random(40))
+        base[0], base[-1] = 0.0, 1.0
+        pieces = [base]
+        for j in rng.choice(np.arange(1, 39), size=6, replace=False):        # repeated knots
+            pieces.append(np.repeat(base[j], rng.integers(1, k)))
+        if dtype == "f64":
+            for j in rng.choice(np.arange(1, 39), size=4, replace=False):    # clusters
+                pieces.append(base[j] + 1e-9 * np.arange(1, 4))
+        br = np.sort(np.concatenate(pieces))
+        br = (a + (b - a) * br).astype(T)
+        br[0], br[-1] = T(a), T(b)
+        br = np.sort(br)
+        t = oracle.augment_knots(br, k).astype(T)
+        B = bk.BSplineBasis(k, t, augment=False)
+        c = (2 * rng.random(len(B)) - 1).astype(T)
+        S = bk.Spline(B, c)
+        x = np.concatenate([a + (b - a) * rng.random(20000), br.astype(np.float64),
+                            np.nextafter(br, T(-np.inf)).astype(np.float64), np.nextafter(br, T(np.inf)).astype(np.float64),
+                            [a - 1.0, b + 1.0]]).astype(T)
+        xd = torch.from_numpy(x).cuda()
+        kt = dtype
+        ref = oracle.spline_eval(0, k, t, c, x, kt=kt)
+        assert np.array_equal(S(xd, algo=bk.EVAL_DEBOOR).cpu().numpy(), ref), (case,)
+        scale = np.max(np.abs(ref))
+        for algo in (bk.EVAL_AUTO, bk.EVAL_PP):
+            got = S(xd, algo=algo).cpu().numpy()
+            bad = np.abs(got.astype(np.float64) - ref.astype(np.float64)) > tol * scale
+            # a point may only differ beyond rounding if it sits on a discontinuity side that the
+            # reference resolves the same way: there must be none
+            assert not bad.any(), (case, algo, x[bad][:5], got[bad][:5], ref[bad][:5])
+        if k >= 3:
+            k1, t1, c1 = oracle.spline_derivative(0, k, t, c, 1, kt=kt)
+            refd = oracle.spline_eval(0, k1, t1, c1, x, kt=kt)
+            gotd = S.evaluate(xd, (1,))[0].cpu().numpy()
+            # first derivative: 1e-10 relative (clustered knots amplify rounding of the derivative)
+            sc = np.max(np.abs(refd))
+            badd = np.abs(gotd.astype(np.float64) - refd.astype(np.float64)) > (1e-9 if dtype == "f64" else 1e-3) * sc
+            assert not badd.any(), (case, x[badd][:5], gotd[badd][:5], refd[badd][:5])
+
+
+@pytest.mark.parametrize("k", [2, 4, 5, 8])
+def test_knot_search_and_basis_awkward_knot_vectors(bk, oracle, k):
+    """find_knot_interval / evaluate_all on knot vectors with repeated and clustered interior knots:
+    indices, zones and all k basis values bit-exact (src/BSplines/evaluate_all.jl:102-204)."""
+    import torch
+    rng = np.random.default_rng(2000 + k)
+    base = np.sort(rng.random(60))
+    base[0], base[-1] = 0.0, 1.0
+    pieces = [base]
+    for j in rng.choice(np.arange(1, 59), size=10, replace=False):
+        pieces.append(np.repeat(base[j], rng.integers(1, k)))
+    for j in rng.choice(np.arange(1, 59), size=6, replace=False):
+        pieces.append(base[j] + 1e-12 * np.arange(1, 5))
+    br = np.sort(np.concatenate(pieces))
+    t = oracle.augment_knots(br, k)
+    B = bk.BSplineBasis(k, t, augment=False)
+    x = np.concatenate([rng.random(5000), br, np.nextafter(br, -np.inf), np.nextafter(br, np.inf), [-0.5, 1.5, np.nan]])
+    xd = torch.from_numpy(x).cuda()
+    idx, zone = bk.find_knot_interval(B, xd)
+    ridx, rzone = oracle.find_knot_interval(0, k, t, x)
+    assert np.array_equal(idx.cpu().numpy(), ridx) and np.array_equal(zone.cpu().numpy(), rzone)
+    xin = x[:-3]                                               # inside the domain
+    for nd in range(0, min(3, k)):
+        i, bs = bk.evaluate_all(B, torch.from_numpy(xin).cuda(), bk.Derivative(nd))
+        ri, rbs = oracle.evaluate_all(0, k, t, xin, nderiv=nd)
+        assert np.array_equal(i.cpu().numpy(), ri)
+        assert np.array_equal(bs.cpu().numpy(), rbs, equal_nan=True), nd
