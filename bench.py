@@ -112,6 +112,27 @@ def omp_threads(nthreads):
         return nthreads
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs next to its GPU (NVML's ideal affinity) so that its pinned host buffers
+    are allocated on the NUMA node of the GPU's PCIe root — matters for the host-buffer (e2e) leg when
+    several ranks stream over PCIe at once.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < ncpu}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_rate(npts_sample, nthreads):
     """The reference algorithm on the host cores: de Boor value + derivative spline, OpenMP over
     points (oracle/bsk_oracle.c).  Returns (Gpoints/s, seconds)."""
@@ -173,6 +194,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
