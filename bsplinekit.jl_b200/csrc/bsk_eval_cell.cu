@@ -44,6 +44,15 @@ template <int K, typename T> struct CellRec {
     static constexpr int RECV = ((K + VPA - 1) / VPA) * VPA;      // values per cell record
 };
 
+// One 32-byte record of a table that stays in global memory = one L2 sector = ONE 256-bit load
+// (SASS LDG.E.ENL2.256, sm_100+): a gather of 32 random records costs the L1 pipe 32 wavefronts
+// instead of the 64 of two 128-bit loads, and that pipe is what bounds the global-table kernels.
+__device__ __forceinline__ void ldg256(const void *p, int4 &lo, int4 &hi) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+
 template <typename T>
 struct CellView {
     // Shared-memory tables are stored CHUNK-MAJOR: the w-th 16-byte chunk of record c sits at
@@ -116,6 +125,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
     constexpr int RECV = CellRec<K, T>::RECV;
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int NOUT = DMASK ? MaskCount<DMASK>::value : kMaxOut;
+    constexpr bool WIDE = !STAGE && (RECV * sizeof(T)) % 32 == 0;     // 256-bit record gathers
     extern __shared__ __align__(16) unsigned char smem[];
     // ---- tables: staged in shared memory (STAGE = 1), or, when they are too large for it, read
     //      in place from global memory through L1/L2 by the very same code (STAGE = 0) ----------
@@ -173,10 +183,20 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
             // STAGE: chunk-major (bank spread); global: record-major (one 32-byte sector)
             const int4 *R4 = (const int4 *)s_rec + (STAGE ? (size_t)c : (size_t)c * (RECV / VEC));
             const int cs = STAGE ? cv.ncell : 1;
+            if (WIDE) {
 #pragma unroll
-            for (int w = 0; w < RECV / VEC; ++w) {
-                int4 r = R4[w * cs];
-                memcpy(&rec_[q][w * VEC], &r, 16);
+                for (int w = 0; w < RECV / VEC; w += 2) {
+                    int4 lo, hi;
+                    ldg256(R4 + w, lo, hi);
+                    memcpy(&rec_[q][w * VEC], &lo, 16);
+                    memcpy(&rec_[q][(w + 1) * VEC], &hi, 16);
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < RECV / VEC; ++w) {
+                    int4 r = R4[w * cs];
+                    memcpy(&rec_[q][w * VEC], &r, 16);
+                }
             }
         }
         // phase 2: cells holding a knot -> exact comparison with the knot, gather of the piece on
@@ -195,10 +215,20 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
                     const int4 *R4 = (const int4 *)s_rc + (size_t)right * (RECV / VEC) * cv.nside +
                                      (STAGE ? (size_t)j : (size_t)j * (RECV / VEC));
                     const int cs = STAGE ? cv.nside : 1;
+                    if (WIDE) {
 #pragma unroll
-                    for (int w = 0; w < RECV / VEC; ++w) {
-                        int4 r = R4[w * cs];
-                        memcpy(&rec_[q][w * VEC], &r, 16);
+                        for (int w = 0; w < RECV / VEC; w += 2) {
+                            int4 lo, hi;
+                            ldg256(R4 + w, lo, hi);
+                            memcpy(&rec_[q][w * VEC], &lo, 16);
+                            memcpy(&rec_[q][(w + 1) * VEC], &hi, 16);
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < RECV / VEC; ++w) {
+                            int4 r = R4[w * cs];
+                            memcpy(&rec_[q][w * VEC], &r, 16);
+                        }
                     }
                 }
             }
