@@ -105,6 +105,17 @@ SIGNATURES = {
     "bsk_cyclic_banded_create": (_i32, [_vp, _i64, _i32, _i32, _i32, _pp]),
     "bsk_cyclic_banded_solve": (_i32, [_vp, _vp, _i64, _vp]),
     "bsk_cyclic_banded_destroy": (_i32, [_vp]),
+    "bsk_collocation_matrix_f32": (_i32, [_vp, _vp, _i64, _i32, C.c_float, _vp, C.POINTER(_i64), _vp]),
+    "bsk_collocation_cyclic_f32": (_i32, [_vp, _vp, _i64, _i32, C.c_float, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
+    "bsk_banded_f32_create": (_i32, [_vp, _i64, _i32, _i32, _i32, _pp]),
+    "bsk_banded_f32_create_host": (_i32, [_vp, _i64, _i32, _i32, _i32, _pp]),
+    "bsk_banded_f32_lu": (_i32, [_vp, C.POINTER(_i64)]),
+    "bsk_banded_f32_data": (_i32, [_vp, _vp]),
+    "bsk_banded_f32_solve": (_i32, [_vp, _vp, _i64, _vp]),
+    "bsk_banded_f32_destroy": (_i32, [_vp]),
+    "bsk_cyclic_f32_create": (_i32, [_vp, _vp, _vp, _i64, _i32, _pp]),
+    "bsk_cyclic_f32_solve": (_i32, [_vp, _vp, _i64, _vp]),
+    "bsk_cyclic_f32_destroy": (_i32, [_vp]),
     "bsk_galerkin_nodes": (_i32, [_vp, _vp, _i32, _vp, _i64, C.POINTER(_i64)]),
     "bsk_galerkin_matrix": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "bsk_galerkin_projection": (_i32, [_vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),

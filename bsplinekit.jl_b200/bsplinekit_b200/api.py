@@ -728,21 +728,26 @@ class CollocationMatrix:
     def __init__(self, band, _handle=None):
         self._handle = _handle
         self.factored = False
+        self.f32 = False           # CollocationMatrix{Float32}: the *_f32 entry points (bsk_solve_f32.cu)
         if band is None:
             return
         if isinstance(band, torch.Tensor) and band.is_cuda:
             # torch tensor of shape (n, nbands) row-major == (nbands, n) column-major
             nb, n = band.shape[1], band.shape[0]
+            self.f32 = band.dtype == torch.float32
             out = C.c_void_p()
-            check(lib.bsk_banded_create(_ptr(band), n, (nb - 1) // 2, (nb - 1) // 2, _device(), C.byref(out)))
+            create = lib.bsk_banded_f32_create if self.f32 else lib.bsk_banded_create
+            check(create(_ptr(band.contiguous()), n, (nb - 1) // 2, (nb - 1) // 2, _device(), C.byref(out)))
         else:
-            bh = np.asfortranarray(np.asarray(band, dtype=np.float64))
+            band = np.asarray(band)
+            self.f32 = band.dtype == np.float32
+            bh = np.asfortranarray(band, dtype=np.float32 if self.f32 else np.float64)
             if bh.shape[0] % 2 != 1:
                 raise ArgumentError("odd number of bands expected")
             nb, n = bh.shape
             out = C.c_void_p()
-            check(lib.bsk_banded_create_host(bh.ctypes.data_as(C.c_void_p), n, (nb - 1) // 2, (nb - 1) // 2,
-                                             _device(), C.byref(out)))
+            create = lib.bsk_banded_f32_create_host if self.f32 else lib.bsk_banded_create_host
+            check(create(bh.ctypes.data_as(C.c_void_p), n, (nb - 1) // 2, (nb - 1) // 2, _device(), C.byref(out)))
         self._handle = out
         self.n, self.nbands = n, nb
 
@@ -750,7 +755,7 @@ class CollocationMatrix:
         h, self._handle = getattr(self, "_handle", None), None
         if h is not None:
             try:
-                lib.bsk_banded_destroy(h)
+                (lib.bsk_banded_f32_destroy if self.f32 else lib.bsk_banded_destroy)(h)
             except Exception:
                 pass
 
@@ -761,14 +766,14 @@ class CollocationMatrix:
 
     def data(self):
         """(nbands, n) Fortran-ordered copy of the band store (factors after lu!)."""
-        out = np.empty((self.nbands, self.n), dtype=np.float64, order="F")
-        check(lib.bsk_banded_data(self._handle, out.ctypes.data_as(C.c_void_p)))
+        out = np.empty((self.nbands, self.n), dtype=np.float32 if self.f32 else np.float64, order="F")
+        check((lib.bsk_banded_f32_data if self.f32 else lib.bsk_banded_data)(self._handle, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def dense(self):
         w = self.data()
         l, u = self.bandwidths
-        A = np.zeros((self.n, self.n))
+        A = np.zeros((self.n, self.n), dtype=w.dtype)
         for j in range(self.n):
             for i in range(max(0, j - u), min(self.n, j + l + 1)):
                 A[i, j] = w[u + i - j, j]
@@ -777,6 +782,8 @@ class CollocationMatrix:
     def mul(self, X):
         """C * X for an (n, nrhs) block (RHS index fastest): mul!(Y, C, X) (matrix.jl:91-94).
         Only before lu_() (which factorises in place, like lu!)."""
+        if self.f32:
+            raise _lib.UnsupportedError("mul! is implemented for Float64 collocation matrices")
         if isinstance(X, torch.Tensor) and X.is_cuda:
             Xd, on_dev = X.contiguous(), True
         else:
@@ -790,19 +797,37 @@ class CollocationMatrix:
     def lu_(self):
         """lu!(C) (Collocation/matrix.jl:132-201)."""
         info = C.c_int64(0)
-        st = lib.bsk_banded_lu(self._handle, C.byref(info))
+        st = (lib.bsk_banded_f32_lu if self.f32 else lib.bsk_banded_lu)(self._handle, C.byref(info))
         check(st, info.value)
         self.factored = True
         return self
 
     @property
     def halo(self):
+        if self.f32:
+            return 0
         h = C.c_int32(0)
         check(lib.bsk_banded_halo(self._handle, C.byref(h)))
         return h.value
 
     def ldiv_(self, Y, algo=SOLVE_AUTO):
         """ldiv!(F, Y) in place; Y is (n, nrhs) with the RHS index fastest (matrix.jl:218-271)."""
+        if self.f32:
+            on_dev = isinstance(Y, torch.Tensor) and Y.is_cuda
+            if on_dev:
+                if Y.dtype != torch.float32 or not Y.is_contiguous():
+                    raise ArgumentError("Y must be a contiguous float32 CUDA tensor")
+                Yd = Y
+            else:
+                if not (isinstance(Y, np.ndarray) and Y.dtype == np.float32 and Y.flags.c_contiguous):
+                    raise ArgumentError("Y must be a C-contiguous float32 array (solved in place)")
+                Yd = torch.from_numpy(Y).cuda()
+            if Yd.shape[0] != self.n:
+                raise DimensionMismatch("vectors `x` and `y` must have length %d" % self.n)
+            check(lib.bsk_banded_f32_solve(self._handle, _ptr(Yd), Yd.numel() // self.n if self.n else 0, _stream()))
+            if not on_dev:
+                Y[...] = Yd.cpu().numpy()
+            return Y
         if isinstance(Y, torch.Tensor) and Y.is_cuda:
             if Y.dtype != torch.float64 or not Y.is_contiguous():
                 raise ArgumentError("Y must be a contiguous float64 CUDA tensor")
@@ -823,6 +848,8 @@ class CollocationMatrix:
         """out = F \\ (L * U) in one pass: the `mul!(y, L, u); ldiv!(du, F, y)` pair of a collocation
         time step (examples/heat.jl:314-328).  `self` is factorised, `L` is not; U is an (n, nrhs)
         float64 CUDA block (RHS index fastest) and is left untouched."""
+        if self.f32 or L.f32:
+            raise _lib.UnsupportedError("the fused mat-vec + solve is implemented for Float64 matrices")
         if not (isinstance(U, torch.Tensor) and U.is_cuda and U.dtype == torch.float64 and U.is_contiguous()):
             raise ArgumentError("U must be a contiguous float64 CUDA tensor")
         if U.shape[0] != self.n or L.n != self.n:
@@ -841,7 +868,18 @@ class CyclicTridiagonalMatrix:
     factored once."""
 
     def __init__(self, a, b, c):
-        if isinstance(a, torch.Tensor) and a.is_cuda:
+        self.f32 = (a.dtype == torch.float32) if isinstance(a, torch.Tensor) else (np.asarray(a).dtype == np.float32)
+        if self.f32:
+            a, b, c = (np.ascontiguousarray(v.cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
+                       for v in (a, b, c))
+            if not (a.size == b.size == c.size):
+                raise DimensionMismatch("all diagonals must have the same length")
+            self.n = a.size
+            out = C.c_void_p()
+            check(lib.bsk_cyclic_f32_create(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                            c.ctypes.data_as(C.c_void_p), self.n, _device(), C.byref(out)))
+            self.a, self.b, self.c = a, b, c
+        elif isinstance(a, torch.Tensor) and a.is_cuda:
             self.n = a.numel()
             out = C.c_void_p()
             check(lib.bsk_cyclic_create_device(_ptr(a), _ptr(b), _ptr(c), self.n, _device(), C.byref(out)))
@@ -861,7 +899,7 @@ class CyclicTridiagonalMatrix:
         h, self._handle = getattr(self, "_handle", None), None
         if h is not None:
             try:
-                lib.bsk_cyclic_destroy(h)
+                (lib.bsk_cyclic_f32_destroy if self.f32 else lib.bsk_cyclic_destroy)(h)
             except Exception:
                 pass
 
@@ -875,6 +913,15 @@ class CyclicTridiagonalMatrix:
         return A
 
     def ldiv_(self, Y):
+        if self.f32:
+            on_dev = isinstance(Y, torch.Tensor) and Y.is_cuda
+            Yd = Y if on_dev else torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float32)).cuda()
+            if Yd.dtype != torch.float32 or not Yd.is_contiguous() or Yd.shape[0] != self.n:
+                raise DimensionMismatch("all vectors must have length %d" % self.n)
+            check(lib.bsk_cyclic_f32_solve(self._handle, _ptr(Yd), Yd.numel() // self.n, _stream()))
+            if not on_dev:
+                Y[...] = Yd.cpu().numpy()
+            return Y
         if isinstance(Y, torch.Tensor) and Y.is_cuda:
             if Y.dtype != torch.float64 or not Y.is_contiguous() or Y.shape[0] != self.n:
                 raise DimensionMismatch("all vectors must have length %d" % self.n)
@@ -894,9 +941,9 @@ def collocation_matrix(B, x, deriv=None, clip_threshold=None, return_outside=Fal
     (Collocation/Collocation.jl:111-120,209-251).  Periodic cubic bases give a
     CyclicTridiagonalMatrix (Collocation.jl:138-146)."""
     nd = 0 if deriv is None else deriv.n
+    if B._dt == BSK_F32:
+        return _collocation_matrix_f32(B, x, nd, clip_threshold, return_outside)
     clip = float(np.finfo(np.float64).eps) if clip_threshold is None else float(clip_threshold)
-    if B._dt != BSK_F64:
-        raise _lib.UnsupportedError("collocation assembly needs a Float64 basis")
     xd, _ = _to_device(x, BSK_F64)
     xd = xd.reshape(-1)
     if xd.numel() != len(B):
@@ -920,6 +967,39 @@ def collocation_matrix(B, x, deriv=None, clip_threshold=None, return_outside=Fal
     band = torch.empty((len(B), nb), dtype=torch.float64, device="cuda")   # == (nb, n) column-major
     check(lib.bsk_collocation_matrix(B._handle, _ptr(xd), xd.numel(), nd, clip, _ptr(band),
                                      C.byref(nout), _stream()))
+    if nout.value:
+        import warnings
+        warnings.warn("Non-zero value outside of matrix bands (%d entries)" % nout.value)   # :239-244
+    M = CollocationMatrix(band)
+    return (M, nout.value) if return_outside else M
+
+
+def _collocation_matrix_f32(B, x, nd, clip_threshold, return_outside):
+    """CollocationMatrix{Float32} / CyclicTridiagonalMatrix{Float32}: T = eltype of the basis' knots
+    (Collocation.jl:111-120: `T = eltype(x)` default, clip_threshold = eps(T))."""
+    clip = float(np.finfo(np.float32).eps) if clip_threshold is None else float(clip_threshold)
+    xd, _ = _to_device(x, BSK_F32)
+    xd = xd.reshape(-1)
+    if xd.numel() != len(B):
+        raise ArgumentError("wrong dimensions of collocation matrix")   # Collocation.jl:214-216
+    nout = C.c_int64(0)
+    if isinstance(B, PeriodicBSplineBasis):
+        if B.k != 4:
+            raise _lib.UnsupportedError("Float32 periodic interpolation is implemented for cubic splines")
+        n = len(B)
+        a = torch.empty(n, dtype=torch.float32, device="cuda")
+        b = torch.empty_like(a)
+        c = torch.empty_like(a)
+        check(lib.bsk_collocation_cyclic_f32(B._handle, _ptr(xd), n, nd, clip, _ptr(a), _ptr(b), _ptr(c),
+                                             C.byref(nout), _stream()))
+        if nout.value:
+            raise ArgumentError("DomainError: %d entries outside of the matrix bands" % nout.value)
+        M = CyclicTridiagonalMatrix(a, b, c)
+        return (M, nout.value) if return_outside else M
+    nb = 2 * B.k - 3
+    band = torch.empty((len(B), nb), dtype=torch.float32, device="cuda")   # == (nb, n) column-major
+    check(lib.bsk_collocation_matrix_f32(B._handle, _ptr(xd), xd.numel(), nd, clip, _ptr(band),
+                                         C.byref(nout), _stream()))
     if nout.value:
         import warnings
         warnings.warn("Non-zero value outside of matrix bands (%d entries)" % nout.value)   # :239-244
@@ -1082,16 +1162,20 @@ class SplineInterpolation:
         if isinstance(y, torch.Tensor) and y.is_cuda:
             if y.shape[0] != N:
                 raise DimensionMismatch("input data has incorrect length")
+            if y.dtype != _TORCH[self.basis._dt]:
+                raise ArgumentError("data has dtype %s, the basis is %s" % (y.dtype, _TORCH[self.basis._dt]))
             Y = y
         else:
             yh = np.asarray(y)
             if yh.shape[0] != N:
                 raise DimensionMismatch("input data has incorrect length")
-            Y = torch.from_numpy(np.ascontiguousarray(yh, dtype=np.float64)).cuda()
+            Y = torch.from_numpy(np.ascontiguousarray(yh, dtype=_NP[self.basis._dt])).cuda()
         if self.C is None:
             pass                                                        # identity
         elif isinstance(self.C, (CyclicTridiagonalMatrix, CyclicBandedMatrix)):
             self.C.ldiv_(Y)
+        elif self.C.f32:
+            self.C.ldiv_(Y)                                             # BANSLV order, Float32
         else:
             self.C.ldiv_(Y, algo=algo)
         self.coefs = Y

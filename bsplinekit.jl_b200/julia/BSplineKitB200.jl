@@ -252,7 +252,7 @@ function Collocation.collocation_matrix(B::AbstractBSplineBasis, xs::DeviceVecto
     finalizer(f -> ccall((:bsk_banded_destroy, lib), Int32, (Ptr{Cvoid},), f.ptr), F)
 end
 
-function LinearAlgebra.lu!(F::DeviceBandedLU)                       # Collocation/matrix.jl:132-201
+function LinearAlgebra.lu!(F::DeviceBandedLU{Float64})              # Collocation/matrix.jl:132-201
     info = Ref{Int64}(0)
     st = ccall((:bsk_banded_lu, lib), Int32, (Ptr{Cvoid}, Ptr{Int64}), F.ptr, info)
     check(st, info[])
@@ -260,7 +260,7 @@ function LinearAlgebra.lu!(F::DeviceBandedLU)                       # Collocatio
 end
 
 # ldiv!(F, Y): Y is M x N (M data sets interleaved), solved in place   (Collocation/matrix.jl:218-271)
-function LinearAlgebra.ldiv!(F::DeviceBandedLU, Y::DeviceMatrix{Float64}; algo = 0)
+function LinearAlgebra.ldiv!(F::DeviceBandedLU{Float64}, Y::DeviceMatrix{Float64}; algo = 0)
     Y.N == F.n || throw(DimensionMismatch("vectors `x` and `y` must have length $(F.n)"))
     check(ccall((:bsk_banded_solve, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ptr{Cvoid}),
                 F.ptr, Y.data.ptr, Y.M, algo, C_NULL))
@@ -287,6 +287,42 @@ function ldiv_mul!(dU::DeviceMatrix{Float64}, F::DeviceBandedLU, L::DeviceBanded
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Cvoid}),
                 F.ptr, L.ptr, U.data.ptr, dU.data.ptr, U.M, C_NULL))
     dU
+end
+
+# ---- the same path in Float32 (the reference methods are generic in T) ------------------------------
+# CollocationMatrix{Float32} / lu! / ldiv! in Float32 (Collocation/Collocation.jl:165-198,
+# Collocation/matrix.jl:132-271): the `_f32` entry points, same layouts and status codes.
+function Collocation.collocation_matrix(B::AbstractBSplineBasis, xs::DeviceVector{Float32},
+                                        deriv::Derivative{n} = Derivative(0);
+                                        clip_threshold = eps(Float32)) where {n}
+    k = order(B)
+    N = length(B)
+    length(xs) == N || throw(ArgumentError("wrong dimensions of collocation matrix"))
+    band = DeviceVector{Float32}(undef, (2k - 3) * N)
+    nout = Ref{Int64}(0)
+    check(ccall((:bsk_collocation_matrix_f32, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float32}, Int64, Int32, Float32, Ptr{Float32}, Ptr{Int64}, Ptr{Cvoid}),
+        handle(B).ptr, xs.ptr, N, n, Float32(clip_threshold), band.ptr, nout, C_NULL))
+    nout[] > 0 && @warn "Non-zero value outside of matrix bands ($(nout[]) entries)"
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:bsk_banded_f32_create, lib), Int32, (Ptr{Float32}, Int64, Int32, Int32, Int32, Ptr{Ptr{Cvoid}}),
+                band.ptr, N, k - 2, k - 2, xs.device, out))
+    F = DeviceBandedLU{Float32}(out[], N)
+    finalizer(f -> ccall((:bsk_banded_f32_destroy, lib), Int32, (Ptr{Cvoid},), f.ptr), F)
+end
+
+function LinearAlgebra.lu!(F::DeviceBandedLU{Float32})
+    info = Ref{Int64}(0)
+    st = ccall((:bsk_banded_f32_lu, lib), Int32, (Ptr{Cvoid}, Ptr{Int64}), F.ptr, info)
+    check(st, info[])
+    F
+end
+
+function LinearAlgebra.ldiv!(F::DeviceBandedLU{Float32}, Y::DeviceMatrix{Float32})
+    Y.N == F.n || throw(DimensionMismatch("vectors `x` and `y` must have length $(F.n)"))
+    check(ccall((:bsk_banded_f32_solve, lib), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int64, Ptr{Cvoid}),
+                F.ptr, Y.data.ptr, Y.M, C_NULL))
+    Y
 end
 
 # ---- periodic bases of order k ∉ {2, 4}: cyclic banded factorisation ---------------------------------
@@ -340,10 +376,10 @@ Batched `interpolate` (SplineInterpolations.jl:260-273): knots from `make_knots`
 collocation assembly + LU on the device, then every data set of `Y` is solved in place; column
 `j` of the result holds the B-spline coefficients of data set `j`.
 """
-function SplineInterpolations.interpolate(x::AbstractVector, Y::DeviceMatrix{Float64}, ord::BSplineOrder{k}) where {k}
-    t = SplineInterpolations.make_knots(x, ord, nothing)            # :302-326, stays host code
+function SplineInterpolations.interpolate(x::AbstractVector, Y::DeviceMatrix{T}, ord::BSplineOrder{k}) where {k, T <: Union{Float32, Float64}}
+    t = SplineInterpolations.make_knots(collect(T, x), ord, nothing)   # :302-326, stays host code
     B = BSplineBasis(ord, t; augment = Val(false))
-    xs = DeviceVector(collect(Float64, x))
+    xs = DeviceVector(collect(T, x))
     F = lu!(Collocation.collocation_matrix(B, xs))
     ldiv!(F, Y)
     B, F, Y

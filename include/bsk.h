@@ -80,6 +80,8 @@ typedef struct bsk_spline bsk_spline;
 typedef struct bsk_banded bsk_banded;
 typedef struct bsk_cyclic bsk_cyclic;
 typedef struct bsk_cyclic_banded bsk_cyclic_banded;
+typedef struct bsk_banded_f32 bsk_banded_f32;
+typedef struct bsk_cyclic_f32 bsk_cyclic_f32;
 
 /* Corner blocks of a RecombineMatrix (Recombinations/matrices.jl:70-110):
  * ul is ul_rows x nl, lr is lr_rows x nr, column-major doubles. */
@@ -250,6 +252,33 @@ bsk_status bsk_cyclic_banded_create(const double *h_cband, int64_t n, int32_t bw
 /* In place on nrhs interleaved right-hand sides d_rhs[(i-1)*nrhs + c]. */
 bsk_status bsk_cyclic_banded_solve(const bsk_cyclic_banded *h, double *d_rhs, int64_t nrhs, void *stream);
 bsk_status bsk_cyclic_banded_destroy(bsk_cyclic_banded *h);
+
+/* ---- the interpolation path in Float32 ------------------------------------------------
+ * The reference code is generic in the element type: interpolate(x::Vector{Float32}, y, ...) builds a
+ * CollocationMatrix{Float32} (Collocation/Collocation.jl:165-198) and runs lu! / ldiv!
+ * (Collocation/matrix.jl:132-201,218-271) in Float32; periodic cubic bases use
+ * CyclicTridiagonalMatrix{Float32} (Collocation/cyclic.jl:112-197).  Same layouts, argument meaning
+ * and status codes as the Float64 entry points above; the basis must have been created with
+ * BSK_F32 knots.  Assembly, factors and solutions keep the reference's operation order in Float32
+ * (bit-identical to a Float32 CPU restatement, see tests/); the cyclic solve is factored once. */
+bsk_status bsk_collocation_matrix_f32(const bsk_basis *b, const float *d_x, int64_t nx, int32_t deriv,
+                                      float clip_threshold, float *d_band, int64_t *h_n_outside,
+                                      void *stream);
+bsk_status bsk_collocation_cyclic_f32(const bsk_basis *b, const float *d_x, int64_t nx, int32_t deriv,
+                                      float clip_threshold, float *d_a, float *d_b, float *d_c,
+                                      int64_t *h_n_outside, void *stream);
+bsk_status bsk_banded_f32_create(const float *d_band, int64_t n, int32_t l, int32_t u, int32_t device,
+                                 bsk_banded_f32 **out);
+bsk_status bsk_banded_f32_create_host(const float *h_band, int64_t n, int32_t l, int32_t u,
+                                      int32_t device, bsk_banded_f32 **out);
+bsk_status bsk_banded_f32_lu(bsk_banded_f32 *h, int64_t *info_pivot);
+bsk_status bsk_banded_f32_data(const bsk_banded_f32 *h, float *h_out);
+bsk_status bsk_banded_f32_solve(const bsk_banded_f32 *h, float *d_rhs, int64_t nrhs, void *stream);
+bsk_status bsk_banded_f32_destroy(bsk_banded_f32 *h);
+bsk_status bsk_cyclic_f32_create(const float *h_a, const float *h_b, const float *h_c, int64_t n,
+                                 int32_t device, bsk_cyclic_f32 **out);
+bsk_status bsk_cyclic_f32_solve(const bsk_cyclic_f32 *h, float *d_rhs, int64_t nrhs, void *stream);
+bsk_status bsk_cyclic_f32_destroy(bsk_cyclic_f32 *h);
 
 /* ---- Galerkin matrices and projections (plain and recombined Float64 bases) ------------
  * galerkin_matrix!(M, B, (Derivative(deriv1), Derivative(deriv2)))  — src/Galerkin/linear.jl:220-311:

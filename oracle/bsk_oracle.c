@@ -48,6 +48,15 @@
 #undef SFX
 #undef KT_IS_WIDER
 
+/* ---- Float32 collocation / BANFAC / BANSLV / cyclic (the reference code is generic in T) ---- */
+#define RT float
+#define RSFX f32
+#define EFN(name) name##_ff
+#include "bsk_oracle_band_tmpl.h"
+#undef RT
+#undef RSFX
+#undef EFN
+
 /* ================================================================================
  * Single basis function, recursive Cox-de Boor (src/BSplines/basis_function.jl)
  * ================================================================================ */

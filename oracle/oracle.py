@@ -24,7 +24,7 @@ def lib():
     if _LIB is None:
         path = os.path.join(_HERE, "libbsk_oracle.so")
         src_m = max(os.path.getmtime(os.path.join(_HERE, f))
-                    for f in ("bsk_oracle.c", "bsk_oracle_tmpl.h"))
+                    for f in ("bsk_oracle.c", "bsk_oracle_tmpl.h", "bsk_oracle_band_tmpl.h"))
         if not os.path.exists(path) or os.path.getmtime(path) < src_m:
             build()
         _LIB = C.CDLL(path)
@@ -32,6 +32,9 @@ def lib():
         _LIB.orc_collocation_matrix.restype = C.c_int64
         _LIB.orc_collocation_cyclic.restype = C.c_int64
         _LIB.orc_banded_lu.restype = C.c_int64
+        _LIB.orc_collocation_matrix_f32.restype = C.c_int64
+        _LIB.orc_collocation_cyclic_f32.restype = C.c_int64
+        _LIB.orc_banded_lu_f32.restype = C.c_int64
     return _LIB
 
 
@@ -135,19 +138,50 @@ def collocation_cyclic(k, data, x, nderiv=0, clip=np.finfo(np.float64).eps):
     return a, b, c, int(nout)
 
 
+def collocation_matrix_f32(kind, k, t, x, nderiv=0, clip=np.finfo(np.float32).eps, recomb=None):
+    """Float32 basis and points: CollocationMatrix{Float32} (Collocation.jl:165-198)."""
+    t = _np(t, np.float32); x = _np(x, np.float32)
+    r = recomb if recomb is not None else Recomb(0, 0, 0, 0, np.zeros((0, 0)), np.zeros((0, 0)))
+    ncols = t.size - k - r.cl - r.cr
+    band = np.zeros((2 * k - 3, ncols), np.float32, order="F")
+    nout = lib().orc_collocation_matrix_f32(
+        C.c_int(kind), C.c_int(k), _p(t), C.c_int64(t.size), C.c_int(r.cl), C.c_int(r.cr),
+        C.c_int(r.nl), C.c_int(r.nr), C.c_int(r.ul.shape[0]), _p(r.ul), C.c_int(r.lr.shape[0]),
+        _p(r.lr), _p(x), C.c_int64(x.size), C.c_int(nderiv), C.c_float(clip), _p(band),
+        C.c_int64(ncols))
+    return band, int(nout)
+
+
+def collocation_cyclic_f32(k, data, x, nderiv=0, clip=np.finfo(np.float32).eps):
+    data = _np(data, np.float32); x = _np(x, np.float32)
+    n = data.size - 1
+    a = np.empty(n, np.float32); b = np.empty(n, np.float32); c = np.empty(n, np.float32)
+    nout = lib().orc_collocation_cyclic_f32(C.c_int(k), _p(data), C.c_int64(data.size), _p(x),
+                                            C.c_int64(x.size), C.c_int(nderiv), C.c_float(clip),
+                                            _p(a), _p(b), _p(c))
+    return a, b, c, int(nout)
+
+
 def banded_lu(band):
     """In place on a Fortran-ordered (l+u+1, n) array, l == u. Returns info (0 = ok)."""
-    assert band.flags.f_contiguous and band.dtype == np.float64
+    assert band.flags.f_contiguous and band.dtype in (np.float64, np.float32)
     h = (band.shape[0] - 1) // 2
+    if band.dtype == np.float32:
+        return int(lib().orc_banded_lu_f32(_p(band), C.c_int(h), C.c_int(h), C.c_int64(band.shape[1])))
     return int(lib().orc_banded_lu(_p(band), C.c_int(h), C.c_int(h), C.c_int64(band.shape[1])))
 
 
 def banded_solve(band_lu, rhs):
     """rhs: C-ordered (n, nrhs) array (rhs index fastest), solved in place."""
-    assert band_lu.flags.f_contiguous and rhs.flags.c_contiguous and rhs.dtype == np.float64
+    assert band_lu.flags.f_contiguous and rhs.flags.c_contiguous and rhs.dtype == band_lu.dtype
     h = (band_lu.shape[0] - 1) // 2
     n = band_lu.shape[1]
     r2 = rhs.reshape(n, -1)
+    if rhs.dtype == np.float32:
+        lib().orc_banded_solve_f32(_p(band_lu), C.c_int(h), C.c_int(h), C.c_int64(n), _p(r2),
+                                   C.c_int64(r2.shape[1]))
+        return rhs
+    assert rhs.dtype == np.float64
     lib().orc_banded_solve(_p(band_lu), C.c_int(h), C.c_int(h), C.c_int64(n), _p(r2),
                            C.c_int64(r2.shape[1]))
     return rhs
@@ -161,6 +195,15 @@ def banded_matvec(band, x):
     lib().orc_banded_matvec(_p(band), C.c_int(h), C.c_int(h), C.c_int64(n), _p(x2), _p(y),
                             C.c_int64(x2.shape[1]))
     return y.reshape(np.shape(x))
+
+
+def cyclic_solve_f32(a, b, c, d):
+    a = _np(a, np.float32); b = _np(b, np.float32); c = _np(c, np.float32)
+    n = a.size
+    d2 = np.array(d, dtype=np.float32, order="C").reshape(n, -1)
+    x = np.empty_like(d2)
+    lib().orc_cyclic_solve_f32(_p(a), _p(b), _p(c), C.c_int64(n), _p(d2), _p(x), C.c_int64(d2.shape[1]))
+    return x.reshape(np.shape(d))
 
 
 def cyclic_solve(a, b, c, d):

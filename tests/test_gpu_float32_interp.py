@@ -1,0 +1,181 @@
+"""GPU parity tests of the Float32 interpolation path (bsk_solve_f32.cu) through the C ABI.
+
+The reference is generic in the element type: Float32 `x` gives a Float32 basis, a
+CollocationMatrix{Float32} and Float32 lu! / ldiv! (Collocation/Collocation.jl:165-198,
+Collocation/matrix.jl:132-271).  Bar: bit-exact against the Float32 restatement in oracle/ for
+assembly, factors and BANSLV solutions; within 1e-5 relative of the Float64 results
+(BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-5
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from bsplinekit_b200 import synth as s
+    return s
+
+
+def _system(bk, oracle, synth, n, k, seed=6):
+    xdata = synth.breakpoints(seed, n).astype(np.float32)
+    t = bk.make_knots(xdata, k)
+    assert t.dtype == np.float32
+    B = bk.BSplineBasis(k, t, augment=False)
+    Cm = bk.collocation_matrix(B, xdata)
+    ref, nout = oracle.collocation_matrix_f32(0, k, t, xdata)
+    assert nout == 0
+    return xdata, t, B, Cm, ref
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 8])
+def test_collocation_lu_solve_f32_bitexact(bk, oracle, synth, k):
+    n, nrhs = 301, 77
+    xdata, t, B, Cm, ref = _system(bk, oracle, synth, n, k)
+    assert Cm.f32 and Cm.data().dtype == np.float32
+    assert np.array_equal(Cm.data(), ref)
+    D = Cm.dense()
+    assert np.allclose(D.sum(axis=1), 1.0, atol=1e-5)                 # partition of unity
+    lu_ref = ref.copy(order="F")
+    assert oracle.banded_lu(lu_ref) == 0
+    Cm.lu_()
+    assert np.array_equal(Cm.data(), lu_ref)
+    Y = (2 * synth.u_numpy(7, 0, n * nrhs) - 1).reshape(n, nrhs).astype(np.float32)
+    Yref = oracle.banded_solve(lu_ref, Y.copy())
+    import torch
+    Yd = torch.from_numpy(Y).cuda()
+    Cm.ldiv_(Yd)
+    assert np.array_equal(Yd.cpu().numpy(), Yref)
+    Yh = Y.copy()
+    Cm.ldiv_(Yh)                                                      # host array, solved in place
+    assert np.array_equal(Yh, Yref)
+    # against the Float64 solve of the same data
+    xd64 = xdata.astype(np.float64)
+    t64 = oracle.make_knots(xd64, k)
+    band64, _ = oracle.collocation_matrix(0, k, t64, xd64)
+    oracle.banded_lu(band64)
+    Y64 = oracle.banded_solve(band64, Y.astype(np.float64))
+    cond_slack = 50.0                                                 # Float32 rounding x conditioning of the system
+    assert relerr(Yref, Y64) < cond_slack * TOL32
+
+
+def test_collocation_f32_derivative_and_recombined(bk, oracle, synth):
+    k = 6
+    br = synth.breakpoints(10, 400).astype(np.float32)
+    B = bk.BSplineBasis(k, br)
+    R = bk.RecombinedBSplineBasis(B, bk.Derivative(0) + 3 * bk.Derivative(1))
+    rc = oracle.Recomb(R.cl, R.cr, R.nl, R.nr, R.ul, R.lr)
+    x = bk.collocation_points(R).astype(np.float32)
+    for nd in (0, 1, 2):
+        ref, nout_ref = oracle.collocation_matrix_f32(2, k, B.knots(), x, nderiv=nd, recomb=rc)
+        Cm, nout = bk.collocation_matrix(R, x, bk.Derivative(nd), return_outside=True)
+        assert nout == nout_ref
+        assert np.array_equal(Cm.data(), ref)
+    with pytest.raises(bk.ArgumentError):
+        bk.collocation_matrix(R, x[:-1])
+
+
+def test_interpolate_f32_end_to_end(bk, oracle, synth):
+    """interpolate(x::Vector{Float32}, y, BSplineOrder(k)): S.(xs) ≈ ys (test/interpolation.jl:61-66)
+    and agreement with the Float64 interpolation of the same data."""
+    n = 200
+    x = synth.breakpoints(6, n).astype(np.float32)
+    y = np.sin(6 * x.astype(np.float64)).astype(np.float32)
+    for k in (4, 6):
+        itp = bk.interpolate(x, y, bk.BSplineOrder(k))
+        S = itp.spline
+        assert S.coefficients().dtype == np.float32
+        got = S(x)
+        assert np.allclose(got, y, atol=2e-5)
+        itp64 = bk.interpolate(x.astype(np.float64), y.astype(np.float64), bk.BSplineOrder(k))
+        xs = synth.u_numpy(12, 0, 5000)
+        v64 = itp64.spline(xs)
+        v32 = S(xs.astype(np.float32))
+        assert relerr(v32, v64) < 20 * TOL32
+    # a batch of data sets stays on the device
+    import torch
+    M = 130
+    Y = torch.from_numpy((2 * synth.u_numpy(7, 0, n * M) - 1).reshape(n, M).astype(np.float32)).cuda()
+    Y0 = Y.cpu().numpy().copy()
+    t = bk.make_knots(x, 4)
+    Bi = bk.BSplineBasis(4, t, augment=False)
+    itp = bk.SplineInterpolation(Bi, x)
+    itp.interpolate_(Y)
+    band, _ = oracle.collocation_matrix_f32(0, 4, t, x)
+    oracle.banded_lu(band)
+    assert np.array_equal(Y.cpu().numpy(), oracle.banded_solve(band, Y0))
+    with pytest.raises(bk.ArgumentError):
+        itp.interpolate_(Y.double())
+    with pytest.raises(bk.DimensionMismatch):
+        itp.interpolate_(Y[:-1])
+
+
+def test_banded_f32_special_cases(bk):
+    """test/collocation.jl:4-53 in Float32: 1x1, zero pivots, wrong dimensions."""
+    C1 = bk.CollocationMatrix(np.array([[2.0]], dtype=np.float32))
+    C1.lu_()
+    y = np.array([[3.0]], dtype=np.float32)
+    C1.ldiv_(y)
+    assert y[0, 0] == 1.5
+    with pytest.raises(bk.ZeroPivotException) as ei:
+        bk.CollocationMatrix(np.array([[0.0]], dtype=np.float32)).lu_()
+    assert ei.value.info == 1
+    band = np.zeros((3, 4), dtype=np.float32, order="F")
+    band[1, :] = [1.0, 2.0, 0.0, 4.0]
+    with pytest.raises(bk.ZeroPivotException) as ei:
+        bk.CollocationMatrix(band).lu_()
+    assert ei.value.info == 3
+    band[1, 2] = 3.0
+    Cm = bk.CollocationMatrix(band).lu_()
+    with pytest.raises(bk.DimensionMismatch):
+        Cm.ldiv_(np.zeros((5, 2), dtype=np.float32))
+    with pytest.raises(bk.ArgumentError):
+        Cm.ldiv_(np.zeros((4, 2)))                                    # Float64 data on a Float32 matrix
+    y = np.ones((4, 3), dtype=np.float32)
+    Cm.ldiv_(y)
+    assert np.allclose(y[:, 0], [1.0, 0.5, 1 / 3, 0.25], rtol=1e-6)
+    # long matrix: the factorisation streams several chunks of columns through shared memory
+    n, bw = 2000, 2
+    rng = np.random.default_rng(5)
+    big = (0.1 * rng.standard_normal((2 * bw + 1, n))).astype(np.float32)
+    big[bw] = 2.0 + rng.random(n).astype(np.float32)
+    big = np.asfortranarray(big)
+    Cb = bk.CollocationMatrix(big.copy(order="F")).lu_()
+    from oracle import oracle as O
+    ref = big.copy(order="F")
+    assert O.banded_lu(ref) == 0
+    assert np.array_equal(Cb.data(), ref)
+
+
+def test_periodic_cubic_f32(bk, oracle, synth):
+    n, M = 500, 90
+    br = synth.breakpoints(8, n + 1).astype(np.float32)
+    B = bk.PeriodicBSplineBasis(4, br)
+    x = bk.collocation_points(B).astype(np.float32)
+    a, b, c, nout = oracle.collocation_cyclic_f32(4, br, x)
+    Mx = bk.collocation_matrix(B, x)
+    assert nout == 0 and Mx.f32
+    assert np.array_equal(Mx.a, a) and np.array_equal(Mx.b, b) and np.array_equal(Mx.c, c)
+    Y = (2 * synth.u_numpy(7, 0, n * M) - 1).reshape(n, M).astype(np.float32)
+    ref32 = oracle.cyclic_solve_f32(a, b, c, Y.copy())
+    ref64 = np.linalg.solve(Mx.dense().astype(np.float64), Y.astype(np.float64))
+    import torch
+    Yd = torch.from_numpy(Y.copy()).cuda()
+    Mx.ldiv_(Yd)
+    got = Yd.cpu().numpy()
+    assert relerr(got, ref64) < TOL32
+    assert relerr(got, ref32) < TOL32
+    # interpolate(x, y, BSplineOrder(4), Periodic(L)) in Float32: S.(xs) ≈ ys (test/periodic.jl:176-180)
+    xs = br[:-1]
+    ys = np.cos(2 * np.pi * xs.astype(np.float64)).astype(np.float32)
+    itp = bk.interpolate(xs, ys, bk.BSplineOrder(4), bk.Periodic(np.float32(br[-1] - br[0])))
+    assert np.allclose(itp.spline(xs), ys, atol=2e-5)

@@ -350,3 +350,65 @@ def test_class_c_minimise_l2(oracle):
     # stiffness matrix of the derivative: rows sum to zero (constants are in the kernel)
     K1 = oracle.galerkin_matrix(k, t, 1, 1)
     assert np.max(np.abs(K1.sum(axis=1))) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# Float32 restatement of the interpolation path (oracle/bsk_oracle_band_tmpl.h)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [2, 4, 6, 8])
+def test_float32_interpolation_chain(oracle, k):
+    """CollocationMatrix{Float32} + lu! + ldiv! in Float32: properties the reference tests state for
+    any element type (test/collocation.jl:4-53,112-121; test/interpolation.jl:61-66) and agreement with
+    the Float64 chain at Float32 accuracy."""
+    rng = np.random.default_rng(3 + k)
+    n = 120
+    x = np.sort(rng.random(n)); x[0], x[-1] = 0.0, 1.0
+    x32 = x.astype(np.float32)
+    x64 = x32.astype(np.float64)
+    t64 = oracle.make_knots(x64, k)
+    t32 = t64.astype(np.float32)
+    band32, nout = oracle.collocation_matrix_f32(0, k, t32, x32)
+    assert nout == 0 and band32.dtype == np.float32
+    A32 = oracle.band_to_dense(band32.astype(np.float64))
+    assert np.allclose(A32.sum(axis=1), 1.0, atol=2e-6)              # partition of unity
+    band64, _ = oracle.collocation_matrix(0, k, t64, x64)
+    assert np.max(np.abs(band32 - band64)) < 2e-4                     # knots rounded to Float32
+    lu32 = band32.copy(order="F")
+    assert oracle.banded_lu(lu32) == 0
+    # L * U == A in Float32 accuracy
+    h = k - 2
+    L = np.eye(n); U = np.zeros((n, n))
+    D = oracle.band_to_dense(lu32.astype(np.float64))
+    for i in range(n):
+        for j in range(max(0, i - h), min(n, i + h + 1)):
+            if j < i:
+                L[i, j] = D[i, j]
+            else:
+                U[i, j] = D[i, j]
+    assert np.max(np.abs(L @ U - A32)) < 1e-5
+    Y = (2 * rng.random((n, 9)) - 1).astype(np.float32)
+    C32 = oracle.banded_solve(lu32, Y.copy())
+    assert C32.dtype == np.float32
+    ref = np.linalg.solve(A32, Y.astype(np.float64))
+    assert np.max(np.abs(C32 - ref)) / np.max(np.abs(ref)) < 5e-4     # Float32 rounding x conditioning
+    res = np.max(np.abs(A32 @ C32.astype(np.float64) - Y))            # backward error of the solve
+    assert res < 1e-6 * k * max(1.0, float(np.max(np.abs(C32))))
+    # zero pivot is reported with its row (ZeroPivotException(i))
+    z = np.zeros((3, 4), dtype=np.float32, order="F"); z[1] = [1, 2, 0, 4]
+    assert oracle.banded_lu(z) == 3
+
+
+def test_float32_cyclic_chain(oracle):
+    n = 64
+    rng = np.random.default_rng(11)
+    br = np.concatenate([[0.0], np.sort(rng.random(n - 1)), [1.0]]).astype(np.float32)
+    a, b, c, nout = oracle.collocation_cyclic_f32(4, br, br[:-1])
+    assert nout == 0
+    A = np.zeros((n, n))
+    for i in range(n):
+        A[i, i] = b[i]; A[i, (i - 1) % n] = a[i]; A[i, (i + 1) % n] = c[i]
+    assert np.allclose(A.sum(axis=1), 1.0, atol=2e-6)
+    Y = (2 * rng.random((n, 5)) - 1).astype(np.float32)
+    X = oracle.cyclic_solve_f32(a, b, c, Y.copy())
+    ref = np.linalg.solve(A, Y.astype(np.float64))
+    assert np.max(np.abs(X - ref)) / np.max(np.abs(ref)) < 1e-4
