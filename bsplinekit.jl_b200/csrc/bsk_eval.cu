@@ -537,14 +537,37 @@ bsk_status build_pp(bsk_spline *s) {
             return out;
         };
         const uint32_t kMulti = 0x7FFFFFFFu;
-        // first guess: one side entry (two pieces) per interior breakpoint; shrink if it overflows
-        int64_t nc = (int64_t)((budget - std::min<size_t>(budget, (size_t)(nbp + 8) * 2 * RECV * sizeof(T))) /
+        // "Jump" scheme (shared-memory tables, Float64, k >= 4; cell_jump_scheme in handles.cuh): a cell
+        // with one SIMPLE knot xi keeps the Taylor coefficients of the piece LEFT of the knot in its
+        // record, and the piece right of it is  P_L + J (x - xi)^(k-1)  (the spline is C^(k-2) at a
+        // simple knot: only the leading coefficient jumps).  The side entry is just {xi, J} (16 bytes
+        // instead of two full pieces), its index sits in bits 1..3 of the first four coefficients
+        // (<= 8 ulp of each), so a flagged lane needs ONE extra 16-byte gather instead of two and the
+        // smaller side table leaves room for ~40 % more cells (fewer flagged lanes).
+        const bool jump_ok = bsk::cell_jump_scheme((int)sizeof(T), k);
+        const uint32_t kJumpMulti = 4095u;
+        const size_t side_bytes = jump_ok ? 16 : (size_t)2 * RECV * sizeof(T);
+        // first guess: one side entry per interior breakpoint; shrink if it overflows
+        int64_t nc = (int64_t)((budget - std::min<size_t>(budget, (size_t)(nbp + 8) * side_bytes)) /
                                (RECV * sizeof(T)));
         nc = std::min<int64_t>(nc, 16 * nrec);
         nc = std::min<int64_t>(nc, 60000);
         // Too many intervals for shared memory: keep the same tables in global memory, record-major
         // (one 32-byte L2 sector per cubic F64 / order-8 F32 record) and L2-resident.
         const bool in_global = nc < 3 * nrec && nrec <= 400000 && getenv("BSK_NO_GLOBAL_CELL") == nullptr;
+        const bool jump = jump_ok && !in_global;
+        double dscale[BSK_MAXK];                               // magnitude of D^d S: max |coefficient|
+        for (int d = 0; d < k; ++d) {
+            dscale[d] = 0.0;
+            for (double v : taylor.dc[d]) dscale[d] = std::max(dscale[d], std::fabs(v));
+        }
+        auto put_index_bits = [](T *rec, uint32_t idx) {      // bits 1..3 of c_0 .. c_3
+            for (int m = 0; m < 4; ++m) {
+                uint64_t u; double d = (double)rec[m]; memcpy(&u, &d, 8);
+                u = (u & ~0xEull) | ((uint64_t)((idx >> (3 * m)) & 7u) << 1);
+                memcpy(&d, &u, 8); rec[m] = (T)d;
+            }
+        };
         if (in_global) {
             const char *e = getenv("BSK_GLOBAL_CELL_MULT2");        // cells per interval, x2
             const int m2 = e ? std::max(6, atoi(e)) : 64;
@@ -573,6 +596,50 @@ bsk_status build_pp(bsk_spline *s) {
                 if (nb == 0) {
                     for (int m = 0; m < k; ++m) crec[c * RECV + m] = (T)cf[m];
                     crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 0);
+                } else if (nb == 1 && jump) {
+                    // simple knot <=> the two pieces are consecutive knot intervals; the first and the
+                    // last cell are kept unflagged-or-multi (boundary pieces feed the extrapolations)
+                    const bool simple = pid[pl + 1] == pid[pl] + 1 && c != 0 && c != nc - 1;
+                    const uint32_t j = (uint32_t)(side_l.size() / 2);
+                    for (int m = 0; m < k; ++m) crec[c * RECV + m] = (T)cf[m];
+                    double cr[BSK_MAXK];
+                    bool accurate = simple;
+                    if (simple) {
+                        // Right of the knot the kernel forms P_L + J dx^(k-1) with P_L continued beyond its
+                        // own interval.  With very uneven neighbouring intervals the two terms can be much
+                        // larger than the spline and cancel: accept the cell only if the sum of the absolute
+                        // terms stays within 16x the magnitude of D^d S for every derivative order (rounding
+                        // error <= ~4e-15 of the output scale); otherwise the cell takes the interval table.
+                        taylor(pid[pl + 1], (double)centerT, cr);
+                        const double jmp = cr[k - 1] - cf[k - 1];
+                        const double h = e1 - (double)centerT, dxm = e1 - plo[pl + 1];
+                        for (int d = 0; d < k && accurate; ++d) {
+                            double sum = 0.0, hp = 1.0;
+                            for (int m = d; m < k; ++m) {
+                                double ff = 1.0;
+                                for (int q = 0; q < d; ++q) ff *= (double)(m - q);
+                                sum += std::fabs(cf[m]) * ff * hp;
+                                hp *= std::fabs(h);
+                            }
+                            double ffj = 1.0;
+                            for (int q = 0; q < d; ++q) ffj *= (double)(k - 1 - q);
+                            sum += std::fabs(jmp) * ffj * std::pow(std::fabs(dxm), k - 1 - d);
+                            if (!(sum <= 16.0 * dscale[d] + 1e-300)) accurate = false;
+                        }
+                    }
+                    if (accurate && j < kJumpMulti) {
+                        side_l.push_back((T)plo[pl + 1]);
+                        side_l.push_back((T)(cr[k - 1] - cf[k - 1]));
+                        put_index_bits(&crec[c * RECV], j);
+                    } else {
+                        put_index_bits(&crec[c * RECV], kJumpMulti);
+                        ++nmulti;
+                    }
+                    crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 1);
+                } else if (nb >= 2 && jump) {
+                    put_index_bits(&crec[c * RECV], kJumpMulti);
+                    crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 1);
+                    ++nmulti;
                 } else if (nb == 1) {
                     const uint32_t j = (uint32_t)(side_l.size() / RECV);
                     crec[c * RECV + XI] = (T)plo[pl + 1];
@@ -588,19 +655,22 @@ bsk_status build_pp(bsk_spline *s) {
                     ++nmulti;
                 }
             }
+            if (jump && side_l.empty()) side_l.resize(2, (T)0);
             if (side_l.empty()) { side_l.resize(RECV, (T)0); side_r.resize(RECV, (T)0); }
-            const int nside = (int)(side_l.size() / RECV);
-            const size_t smem = ((size_t)nc + 2 * (size_t)nside) * RECV * sizeof(T) + 16;
+            const int nside = jump ? (int)(side_l.size() / 2) : (int)(side_l.size() / RECV);
+            const size_t smem = jump ? ((size_t)nc * RECV + 2 * (size_t)nside) * sizeof(T) + 16
+                                     : ((size_t)nc + 2 * (size_t)nside) * RECV * sizeof(T) + 16;
             if (!in_global && smem > 226 * 1024) continue;      // retry with fewer cells
             if (nmulti * 50 > nc) break;                        // clustered knots: not worth it
             // device layout: chunk-major for shared memory, record-major for global (CellView)
-            std::vector<T> crec_cm(crec.size()), rc_cm(2 * side_l.size());
+            std::vector<T> crec_cm(crec.size()), rc_cm(jump ? side_l.size() : 2 * side_l.size());
+            if (jump) rc_cm = side_l;                           // {knot, jump} pairs, 16 bytes each
             for (int64_t c = 0; c < nc; ++c)
                 for (int w = 0; w < NCH; ++w)
                     for (int e = 0; e < VPA; ++e)
                         crec_cm[in_global ? (size_t)c * RECV + w * VPA + e : ((size_t)w * nc + c) * VPA + e] =
                             crec[c * RECV + w * VPA + e];
-            for (int side = 0; side < 2; ++side) {
+            for (int side = 0; side < 2 && !jump; ++side) {
                 const std::vector<T> &src = side ? side_r : side_l;
                 for (int64_t j = 0; j < nside; ++j)
                     for (int w = 0; w < NCH; ++w)

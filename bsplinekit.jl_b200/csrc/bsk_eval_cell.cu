@@ -11,6 +11,10 @@
 // knot is then compared exactly, so the selected knot interval is exactly the one `searchsortedlast` finds
 // (src/BSplines/evaluate_all.jl:102-119) whatever the rounding of the cell index.  Cells with
 // two or more knots (clustered knots) fall back to the per-interval table in global memory.
+// Float64 splines of order >= 4 staged in shared memory use the "jump" encoding instead: the
+// flagged record keeps the piece left of the (simple) knot xi, the side entry is {xi, J} and the
+// piece right of the knot is  P_L + J (x - xi)^(k-1)  — one 16-byte gather on the slow path instead
+// of two, and a 4x smaller side table (more cells, fewer flagged lanes).
 //
 // Replaces the body of (S::Spline)(x) broadcast over many points
 // (src/Splines/spline.jl:144-209) and of (Derivative(n) * S).(x) (spline.jl:272-330) fused in
@@ -38,6 +42,25 @@ template <> struct Bits<float> {
     static __device__ __forceinline__ unsigned index(float v) { return ((unsigned)__float_as_int(v)) >> 1; }
 };
 constexpr unsigned kMultiKnotCell = 0x7FFFFFFFu;     // cell with two or more knots -> interval table
+constexpr unsigned kJumpMultiCell = 4095u;           // same, "jump" encoding (12 index bits)
+
+// "jump" encoding: side index = bits 1..3 of the first four coefficients of the record
+__device__ __forceinline__ unsigned jump_index(const double *rec) {
+    return ((unsigned)(__double2loint(rec[0]) >> 1) & 7u) | (((unsigned)(__double2loint(rec[1]) >> 1) & 7u) << 3) |
+           (((unsigned)(__double2loint(rec[2]) >> 1) & 7u) << 6) | (((unsigned)(__double2loint(rec[3]) >> 1) & 7u) << 9);
+}
+__device__ __forceinline__ unsigned jump_index(const float *) { return kJumpMultiCell; }   // never used
+
+// acc + D^d of  J dx^(K-1)  =  acc + J (K-1)!/(K-1-d)! dx^(K-1-d).  Explicitly rounded products and
+// one explicit fma, so that the compile-time (DMASK) and run-time derivative lists give the same bits.
+template <int K, typename T>
+__device__ __forceinline__ T add_jump_term(T acc, T jump, T dx, int d) {
+    T pw = jump;
+#pragma unroll
+    for (int q = 0; q < K - 1; ++q)
+        if (q < K - 1 - d) pw = xmul(pw, dx);
+    return d > K - 1 ? acc : fma(pw, falling<T>(K - 1, d), acc);
+}
 
 template <int K, typename T> struct CellRec {
     static constexpr int VPA = 16 / (int)sizeof(T);
@@ -126,6 +149,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int NOUT = DMASK ? MaskCount<DMASK>::value : kMaxOut;
     constexpr bool WIDE = !STAGE && (RECV * sizeof(T)) % 32 == 0;     // 256-bit record gathers
+    constexpr bool JUMP = STAGE && bsk::cell_jump_scheme((int)sizeof(T), K);
     extern __shared__ __align__(16) unsigned char smem[];
     // ---- tables: staged in shared memory (STAGE = 1), or, when they are too large for it, read
     //      in place from global memory through L1/L2 by the very same code (STAGE = 0) ----------
@@ -138,7 +162,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
         for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
         src = (const int4 *)cv.rc;
         dst = (int4 *)d_rc;
-        const int m16 = 2 * cv.nside * RECV / VEC;
+        const int m16 = JUMP ? cv.nside : 2 * cv.nside * RECV / VEC;
         for (int i = threadIdx.x; i < m16; i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
@@ -202,11 +226,29 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
         // phase 2: cells holding a knot -> exact comparison with the knot, gather of the piece on
         // the right side of it (again all gathers of the vector in flight together)
         bool multi_[VEC];
+        T jump_[VEC], dxk_[VEC];           // "jump" encoding: J and x - knot right of the knot, else 0
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
             const T last = rec_[q][K - 1];
             multi_[q] = false;
-            if (Bits<T>::flag(last)) {
+            jump_[q] = (T)0;
+            dxk_[q] = (T)0;
+            if (JUMP) {
+                if (Bits<T>::flag(last)) {
+                    const unsigned j = jump_index(rec_[q]);
+                    if (j == kJumpMultiCell) {
+                        multi_[q] = true;
+                    } else {
+                        const int4 r = ((const int4 *)s_rc)[j];
+                        T kj[VEC];
+                        memcpy(kj, &r, 16);
+                        if (!(xs_[q] < kj[0])) {            // at or right of the knot: searchsortedlast
+                            jump_[q] = kj[1];
+                            dxk_[q] = xs_[q] - kj[0];
+                        }
+                    }
+                }
+            } else if (Bits<T>::flag(last)) {
                 const unsigned j = Bits<T>::index(last);
                 if (j == kMultiKnotCell) {
                     multi_[q] = true;
@@ -253,6 +295,18 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
             if (KIND == 0 && E == BSK_EXTRAP_SMOOTH && outside) u += xq - xs;   // boundary piece continued
             T r1[NOUT];
             horner_outputs<K, T, DMASK>(cm, u, outs, r1);
+            if (JUMP) {
+                if (DMASK != 0) {
+                    int o = 0;
+#pragma unroll
+                    for (int d = 0; d < K; ++d)
+                        if (DMASK & (1 << d)) { r1[o] = add_jump_term<K, T>(r1[o], jump_[q], dxk_[q], d); ++o; }
+                } else {
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o)
+                        if (o < outs.nout) r1[o] = add_jump_term<K, T>(r1[o], jump_[q], dxk_[q], outs.deriv[o]);
+                }
+            }
 #pragma unroll
             for (int o = 0; o < NOUT; ++o) {
                 T val = r1[o];

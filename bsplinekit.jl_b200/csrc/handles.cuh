@@ -42,6 +42,10 @@ template <typename P> inline cudaError_t dev_malloc(P **p, size_t bytes) { retur
         }                                 \
     } while (0)
 
+// Uniform-cell tables staged in shared memory use the "jump" encoding of cells that contain a knot
+// (bsk_eval.cu: build, bsk_eval_cell.cu: kernel) for Float64 splines of order >= 4.
+__host__ __device__ constexpr bool cell_jump_scheme(int elt_bytes, int k) { return elt_bytes == 8 && k >= 4; }
+
 inline int sm_count(int device) {
     static int cached[64] = {0};
     if (device < 0 || device >= 64) return 148;

@@ -1160,3 +1160,40 @@ def test_knot_search_and_basis_awkward_knot_vectors(bk, oracle, k):
         ri, rbs = oracle.evaluate_all(0, k, t, xin, nderiv=nd)
         assert np.array_equal(i.cpu().numpy(), ri)
         assert np.array_equal(bs.cpu().numpy(), rbs, equal_nan=True), nd
+
+
+@pytest.mark.parametrize("k", [4, 5, 6, 7, 8])
+@pytest.mark.parametrize("uneven", [False, True])
+def test_eval_cell_jump_encoding(bk, oracle, synth, k, uneven):
+    """Shared-memory cell tables of Float64 splines of order >= 4 keep, for a cell holding one simple
+    knot xi, the piece left of it plus {xi, J}: right of the knot the kernel evaluates
+    P_L + J (x - xi)^(k-1).  Values and every derivative order, at the knots themselves, one ulp either
+    side of them and at random points, against the oracle (src/Splines/spline.jl:144-209,272-330);
+    very uneven neighbouring intervals must be caught by the accuracy guard of the table builder."""
+    import torch
+    nb = 1000 if k <= 6 else 600
+    br = synth.breakpoints(3, nb)
+    if uneven:
+        rng = np.random.default_rng(77 + k)
+        extra = []
+        for j in rng.choice(np.arange(5, nb - 5), size=60, replace=False):   # tiny intervals next to long ones
+            extra.append(br[j] + (br[j + 1] - br[j]) * 10.0 ** (-rng.integers(2, 7)))
+        br = np.sort(np.concatenate([br, extra]))
+    B = bk.BSplineBasis(k, br)
+    t = B.knots()
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    x = np.concatenate([synth.u_numpy(5, 0, 300000), br, np.nextafter(br, -np.inf), np.nextafter(br, np.inf)])
+    xd = torch.from_numpy(x).cuda()
+    for derivs in ((0, 1), tuple(range(2, min(k, 6))), tuple(range(6, k))):
+        if not derivs:
+            continue
+        outs = S.evaluate(xd, derivs)
+        for d, got in zip(derivs, outs):
+            kd, td, cd = (k, t, c) if d == 0 else oracle.spline_derivative(0, k, t, c, d)
+            ref = oracle.spline_eval(0, kd, td, cd, x)
+            assert relerr(got.cpu().numpy(), ref) < TOL64, (d,)
+    # single-output launches (compile-time derivative mask) and the run-time list agree bit for bit
+    v0 = S.evaluate(xd, (0,))[0]
+    v02 = S.evaluate(xd, (0, 2))[0]
+    assert torch.equal(v0, v02)
