@@ -439,6 +439,29 @@ def run_ours(args):
                                     "value": world * npts / (ms * 1e-3) / 1e9, "unit": "Gpoints/s",
                                     "roofline_frac": 8.0 * npts / (ms * 1e-3) / 1e9 / peak}
         del x5f, o5
+        # Float32 batched interpolation (C3 shape in Float32; BANSLV order, two passes: 16 B/element moved,
+        # 8 B/element algorithmic) and evaluation of an order-6 Float64 spline (shared-memory cell table
+        # with the jump encoding of knot cells)
+        xd32 = synth.breakpoints(6, 4096).astype(np.float32)
+        B32 = bk.BSplineBasis(6, bk.make_knots(xd32, 6), augment=False)
+        itp32 = bk.SplineInterpolation(B32, xd32)
+        nr32 = 65536
+        Y32 = (2 * synth.u_torch(7, rank * 4096 * nr32, 4096 * nr32, dtype=torch.float32) - 1).reshape(4096, nr32)
+        W32 = torch.empty_like(Y32)
+        ms = timed(lambda: itp32.C.ldiv_(W32), 5, setup=lambda: W32.copy_(Y32))
+        extra["float32_batched_solve"] = {"metric": "RHS/s (n=4096, k=6, 65536 RHS per GPU, Float32, BANSLV order)",
+                                          "ms": ms, "value": world * nr32 / (ms * 1e-3), "unit": "RHS/s",
+                                          "roofline_frac": 8.0 * 4096 * nr32 / (ms * 1e-3) / 1e9 / peak}
+        del Y32, W32, itp32
+        B6 = bk.BSplineBasis(6, synth.breakpoints(3, 1000))
+        S6 = bk.Spline(B6, 2 * synth.u_numpy(4, 0, len(B6)) - 1)
+        x6 = synth.u_torch(5, rank * npts, npts)
+        o6 = [torch.empty_like(x6), torch.empty_like(x6)]
+        ms = timed(lambda: S6.evaluate(x6, (0, 1), out=o6), 5)
+        extra["order6_eval"] = {"metric": "Gpoints/s (k=6, 1000 breakpoints, value + 1st derivative, 2^28 F64 points)",
+                                "ms": ms, "value": world * npts / (ms * 1e-3) / 1e9, "unit": "Gpoints/s",
+                                "roofline_frac": 24.0 * npts / (ms * 1e-3) / 1e9 / peak}
+        del x6, o6
 
     # ---- extra: configs[0] (the reference's own CPU-runnable case), in full, host arrays in and out --
     if not args.no_extra_configs and rank == 0:
