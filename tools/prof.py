@@ -170,3 +170,20 @@ if args.what == "factor":
             torch.cuda.synchronize(); t2 = time.perf_counter()
         print("n=%d k=%d: assemble %.2f ms, lu! (BANFAC + repack + halo analysis) %.2f ms, halo %d" % (
             n, k, 1e3 * (t1 - t0), 1e3 * (t2 - t1), Cm.halo))
+if args.what == "solve32":
+    xd32 = synth.breakpoints(6, 4096).astype(np.float32)
+    B32 = bk.BSplineBasis(args.order if args.order != 4 else 6, bk.make_knots(xd32, args.order if args.order != 4 else 6), augment=False)
+    itp32 = bk.SplineInterpolation(B32, xd32)
+    Y32 = (2 * synth.u_torch(7, 0, 4096 * args.nrhs, dtype=torch.float32) - 1).reshape(4096, args.nrhs)
+    W32 = torch.empty_like(Y32)
+    tot = 0.0
+    for it in range(args.reps + 1):
+        W32.copy_(Y32)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); itp32.C.ldiv_(W32); e1.record()
+        torch.cuda.synchronize()
+        if it:
+            tot += e0.elapsed_time(e1)
+    ms = tot / args.reps
+    print("solve32: %.3f ms  %.1f M RHS/s  %.1f GB/s (8 B/element)" % (ms, args.nrhs / ms / 1e3, 8 * 4096 * args.nrhs / ms / 1e6))
