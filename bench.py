@@ -302,6 +302,11 @@ def run_ours(args):
         t_f0 = time.perf_counter()
         itp = bk.SplineInterpolation(Bi, xdata)          # assemble + LU, once
         torch.cuda.synchronize()
+        factor_first_ms = 1e3 * (time.perf_counter() - t_f0)   # first call in the process: + lazy kernel loading
+        del itp
+        t_f0 = time.perf_counter()
+        itp = bk.SplineInterpolation(Bi, xdata)
+        torch.cuda.synchronize()
         factor_ms = 1e3 * (time.perf_counter() - t_f0)
         Y0 = (2 * synth.u_torch(7, rank * n * nrhs, n * nrhs) - 1).reshape(n, nrhs)
         Y = torch.empty_like(Y0)
@@ -338,7 +343,8 @@ def run_ours(args):
         extra = {"c3_batched_solve": {"metric": "RHS/s (n=4096, k=6, %d RHS per GPU, Float64)" % nrhs,
                                       "value": best["rhs_per_s"], "unit": "RHS/s",
                                       "roofline_frac": best["frac"], "algos": res,
-                                      "factor_once_ms": factor_ms, "halo_rows": itp.C.halo}}
+                                      "factor_once_ms": factor_ms, "factor_first_call_ms": factor_first_ms,
+                                      "halo_rows": itp.C.halo}}
         # du = F \ (L u), mul! + ldiv! of a collocation time step in one pass
         Lm = bk.collocation_matrix(Bi, xdata, bk.Derivative(2))
         tot = 0.0

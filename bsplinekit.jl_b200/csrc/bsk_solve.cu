@@ -141,8 +141,8 @@ __global__ void k_banded_lu(double *__restrict__ w, int nbandl, int nbandu, int 
 
 // Same recurrence, same operations in the same order (bit-identical factors), but the band streams
 // through shared memory: all threads load / store chunks of columns with coalesced accesses while
-// thread 0 eliminates from a window of kLuChunk + nbandu columns, so the serial chain runs at
-// shared-memory latency (~100 cycles per column) instead of DRAM latency (6.5 ms -> 0.3 ms at n = 4096).
+// warp 0 eliminates from a window of kLuChunk + nbandu columns (one band row per lane), so the serial
+// chain runs at register / shuffle latency instead of DRAM latency.
 constexpr int kLuChunk = 256;
 
 template <int BW>
@@ -164,55 +164,53 @@ k_banded_lu_stream(double *__restrict__ w, int nrow, long long *info) {
 #define SW(r, idx) sw[((r) - 1) + (size_t)(idx) * nroww]
     for (int c0 = 0; c0 < nrow; c0 += kLuChunk) {
         const int ndo = min(kLuChunk, nrow - c0);           // columns eliminated in this round
-        if (tid == 0) {
-            // register window: column idx and the BW columns it updates (static indexing only)
-            double win[BW + 1][nroww];
+        if (tid < 32) {
+            // Warp 0 eliminates.  Lane r (< nroww) owns band row r of a register window of BW + 1 columns:
+            // column idx and the BW columns it updates.  The bw x bw rank-one update of a column step is
+            // spread over the lanes (pivot, multipliers and factors travel by shuffle), so the serial
+            // chain per column is  shuffle -> 1/pivot -> multiply -> shuffle -> multiply, subtract
+            // instead of ~bw^2 dependent operations in one thread.  Same operations on the same values
+            // as BANFAC: bit-identical factors.
+            const int r = tid;
+            const unsigned full = 0xffffffffu;
+            double win[BW + 1];
 #pragma unroll
-            for (int c = 0; c <= BW; ++c)
-#pragma unroll
-                for (int r = 0; r < nroww; ++r) win[c][r] = (c0 + c < nrow) ? sw[r + (size_t)c * nroww] : 0.0;
-            for (int idx = 0; idx < ndo; ++idx) {
+            for (int c = 0; c <= BW; ++c) win[c] = (r < nroww && c0 + c < nrow) ? sw[r + (size_t)c * nroww] : 0.0;
+            bool stop = false;
+            int idx = 0;
+            for (; idx < ndo; ++idx) {
                 const int i = c0 + idx + 1;                 // 1-based column
                 if (i <= nrow - 1) {
-                    const double pivot = win[0][middle - 1];
-                    if (pivot == 0.0) { s_info = i; break; }
+                    const double pivot = __shfl_sync(full, win[0], middle - 1);
+                    if (pivot == 0.0) { if (r == 0) s_info = i; stop = true; break; }
                     const double ipiv = xdiv(1.0, pivot);
                     const int jmax = min(nbandl, nrow - i);
-#pragma unroll
-                    for (int j = 1; j <= BW; ++j)
-                        if (j <= jmax) win[0][middle + j - 1] = xmul(win[0][middle + j - 1], ipiv);
+                    if (r >= middle && r - (middle - 1) <= jmax) win[0] = xmul(win[0], ipiv);
 #pragma unroll
                     for (int kk = 1; kk <= BW; ++kk) {
-                        if (kk <= jmax) {                   // kmax == jmax (nbandl == nbandu)
-                            const double factor = win[kk][middle - kk - 1];
-#pragma unroll
-                            for (int j = 1; j <= BW; ++j)
-                                if (j <= jmax)
-                                    win[kk][middle - kk + j - 1] = xsub(win[kk][middle - kk + j - 1], xmul(factor, win[0][middle + j - 1]));
-                        }
+                        // column i + kk: W(middle - kk + j, i + kk) -= W(middle - kk, i + kk) * W(middle + j, i)
+                        const double factor = __shfl_sync(full, win[kk], middle - kk - 1);
+                        const double lj = __shfl_down_sync(full, win[0], kk);
+                        const int j = r - (middle - kk - 1);
+                        if (kk <= jmax && j >= 1 && j <= jmax) win[kk] = xsub(win[kk], xmul(factor, lj));
                     }
                 }
                 // retire column idx, shift the window, bring in column idx + BW + 1
+                if (r < nroww) sw[r + (size_t)idx * nroww] = win[0];
 #pragma unroll
-                for (int r = 0; r < nroww; ++r) sw[r + (size_t)idx * nroww] = win[0][r];
-#pragma unroll
-                for (int c = 0; c < BW; ++c)
-#pragma unroll
-                    for (int r = 0; r < nroww; ++r) win[c][r] = win[c + 1][r];
+                for (int c = 0; c < BW; ++c) win[c] = win[c + 1];
                 const bool have = (idx + BW + 1 < kLuChunk + BW) && (c0 + idx + BW + 1 < nrow);
-#pragma unroll
-                for (int r = 0; r < nroww; ++r) win[BW][r] = have ? sw[r + (size_t)(idx + BW + 1) * nroww] : 0.0;
+                win[BW] = (have && r < nroww) ? sw[r + (size_t)(idx + BW + 1) * nroww] : 0.0;
             }
-            if (s_info == 0) {
+            if (!stop) {
                 // the BW columns after the last eliminated one carry partial updates: back to the window
-                const int idx = ndo;
 #pragma unroll
                 for (int c = 0; c < BW; ++c)
-                    if (c0 + idx + c < nrow && idx + c < kLuChunk + BW)
-#pragma unroll
-                        for (int r = 0; r < nroww; ++r) sw[r + (size_t)(idx + c) * nroww] = win[c][r];
+                    if (r < nroww && c0 + ndo + c < nrow && ndo + c < kLuChunk + BW)
+                        sw[r + (size_t)(ndo + c) * nroww] = win[c];
+                __syncwarp();
+                if (r == 0 && c0 + ndo >= nrow && SW(middle, nrow - 1 - c0) == 0.0) s_info = nrow;
             }
-            if (s_info == 0 && c0 + ndo >= nrow && SW(middle, nrow - 1 - c0) == 0.0) s_info = nrow;
         }
         __syncthreads();
         // write the finished columns back
