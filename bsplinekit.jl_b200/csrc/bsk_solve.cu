@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdlib>
 
+#include "banfac.cuh"
 #include "handles.cuh"
 
 using namespace bsk;
@@ -107,131 +108,6 @@ k_collocation_cyclic(KnotView<double> kv, const double *__restrict__ x, int nx, 
             else atomicAdd(n_outside, 1ull);                  // reference: DomainError
         }
     }
-}
-
-// ---- K5: BANFAC (matrix.jl:132-201), a strictly serial recurrence: one thread -----------
-__global__ void k_banded_lu(double *__restrict__ w, int nbandl, int nbandu, int nrow, long long *info) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    const int nroww = nbandl + nbandu + 1;
-    const int middle = nbandu + 1;
-#define W(r, c) w[((r) - 1) + (size_t)((c) - 1) * nroww]
-    *info = 0;
-    if (nrow == 1) { if (W(middle, 1) == 0.0) *info = 1; return; }
-    if (nbandl == 0) {
-        for (int i = 1; i <= nrow; ++i)
-            if (W(middle, i) == 0.0) { *info = i; return; }
-        return;
-    }
-    for (int i = 1; i <= nrow - 1; ++i) {
-        const double pivot = W(middle, i);
-        if (pivot == 0.0) { *info = i; return; }
-        const double ipiv = xdiv(1.0, pivot);
-        const int jmax = min(nbandl, nrow - i);
-        for (int j = 1; j <= jmax; ++j) W(middle + j, i) = xmul(W(middle + j, i), ipiv);
-        const int kmax = min(nbandu, nrow - i);
-        for (int kk = 1; kk <= kmax; ++kk) {
-            const double factor = W(middle - kk, i + kk);
-            for (int j = 1; j <= jmax; ++j)
-                W(middle - kk + j, i + kk) = xsub(W(middle - kk + j, i + kk), xmul(factor, W(middle + j, i)));
-        }
-    }
-    if (W(middle, nrow) == 0.0) *info = nrow;
-#undef W
-}
-
-// Same recurrence, same operations in the same order (bit-identical factors), but the band streams
-// through shared memory: all threads load / store chunks of columns with coalesced accesses while
-// warp 0 eliminates from a window of kLuChunk + nbandu columns (one band row per lane), so the serial
-// chain runs at register / shuffle latency instead of DRAM latency.
-constexpr int kLuChunk = 256;
-
-template <int BW>
-__global__ void __launch_bounds__(128)
-k_banded_lu_stream(double *__restrict__ w, int nrow, long long *info) {
-    extern __shared__ double sw[];                          // (kLuChunk + nbandu) columns x nroww
-    __shared__ long long s_info;
-    constexpr int nbandl = BW, nbandu = BW;
-    constexpr int nroww = nbandl + nbandu + 1;
-    constexpr int middle = nbandu + 1;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) s_info = 0;
-    // initial window: columns 1 .. min(nrow, kLuChunk + nbandu)
-    {
-        const int ncol = min(nrow, kLuChunk + nbandu);
-        for (int e = tid; e < ncol * nroww; e += nt) sw[e] = w[e];
-    }
-    __syncthreads();
-#define SW(r, idx) sw[((r) - 1) + (size_t)(idx) * nroww]
-    for (int c0 = 0; c0 < nrow; c0 += kLuChunk) {
-        const int ndo = min(kLuChunk, nrow - c0);           // columns eliminated in this round
-        if (tid < 32) {
-            // Warp 0 eliminates.  Lane r (< nroww) owns band row r of a register window of BW + 1 columns:
-            // column idx and the BW columns it updates.  The bw x bw rank-one update of a column step is
-            // spread over the lanes (pivot, multipliers and factors travel by shuffle), so the serial
-            // chain per column is  shuffle -> 1/pivot -> multiply -> shuffle -> multiply, subtract
-            // instead of ~bw^2 dependent operations in one thread.  Same operations on the same values
-            // as BANFAC: bit-identical factors.
-            const int r = tid;
-            const unsigned full = 0xffffffffu;
-            double win[BW + 1];
-#pragma unroll
-            for (int c = 0; c <= BW; ++c) win[c] = (r < nroww && c0 + c < nrow) ? sw[r + (size_t)c * nroww] : 0.0;
-            bool stop = false;
-            int idx = 0;
-            for (; idx < ndo; ++idx) {
-                const int i = c0 + idx + 1;                 // 1-based column
-                if (i <= nrow - 1) {
-                    const double pivot = __shfl_sync(full, win[0], middle - 1);
-                    if (pivot == 0.0) { if (r == 0) s_info = i; stop = true; break; }
-                    const double ipiv = xdiv(1.0, pivot);
-                    const int jmax = min(nbandl, nrow - i);
-                    if (r >= middle && r - (middle - 1) <= jmax) win[0] = xmul(win[0], ipiv);
-#pragma unroll
-                    for (int kk = 1; kk <= BW; ++kk) {
-                        // column i + kk: W(middle - kk + j, i + kk) -= W(middle - kk, i + kk) * W(middle + j, i)
-                        const double factor = __shfl_sync(full, win[kk], middle - kk - 1);
-                        const double lj = __shfl_down_sync(full, win[0], kk);
-                        const int j = r - (middle - kk - 1);
-                        if (kk <= jmax && j >= 1 && j <= jmax) win[kk] = xsub(win[kk], xmul(factor, lj));
-                    }
-                }
-                // retire column idx, shift the window, bring in column idx + BW + 1
-                if (r < nroww) sw[r + (size_t)idx * nroww] = win[0];
-#pragma unroll
-                for (int c = 0; c < BW; ++c) win[c] = win[c + 1];
-                const bool have = (idx + BW + 1 < kLuChunk + BW) && (c0 + idx + BW + 1 < nrow);
-                win[BW] = (have && r < nroww) ? sw[r + (size_t)(idx + BW + 1) * nroww] : 0.0;
-            }
-            if (!stop) {
-                // the BW columns after the last eliminated one carry partial updates: back to the window
-#pragma unroll
-                for (int c = 0; c < BW; ++c)
-                    if (r < nroww && c0 + ndo + c < nrow && ndo + c < kLuChunk + BW)
-                        sw[r + (size_t)(ndo + c) * nroww] = win[c];
-                __syncwarp();
-                if (r == 0 && c0 + ndo >= nrow && SW(middle, nrow - 1 - c0) == 0.0) s_info = nrow;
-            }
-        }
-        __syncthreads();
-        // write the finished columns back
-        for (int e = tid; e < ndo * nroww; e += nt) w[(size_t)c0 * nroww + e] = sw[e];
-        if (s_info != 0) break;
-        __syncthreads();
-        // carry the nbandu partially updated columns over, then load the next ones
-        const int carry = min(nbandu, nrow - (c0 + ndo));
-        if (carry <= 0) break;
-        for (int e = tid; e < carry * nroww; e += nt) {
-            const double v = sw[(size_t)kLuChunk * nroww + e];
-            sw[e] = v;                                      // kLuChunk >= nbandu: source and target do not overlap
-        }
-        __syncthreads();                                    // the loads below overwrite the carried columns' old slots
-        const int first = c0 + kLuChunk + nbandu;           // 0-based global column of window slot `nbandu`
-        const int nnew = min(kLuChunk, nrow - first);
-        for (int e = tid; e < nnew * nroww; e += nt) sw[(size_t)nbandu * nroww + e] = w[(size_t)first * nroww + e];
-        __syncthreads();
-    }
-#undef SW
-    if (tid == 0) *info = s_info;
 }
 
 // Repack the factors row-wise for the solve kernels:
@@ -665,21 +541,8 @@ bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot) {
     const double t_start = now();
     long long *d_info = nullptr;
     BSK_CUDA(bsk::dev_malloc((void **)&d_info, 8));
-    if (h->n == 1 || h->l == 0 || getenv("BSK_LU_SERIAL"))
-        k_banded_lu<<<1, 1>>>(h->d_w, h->l, h->u, (int)h->n, d_info);
-    else {
-        const size_t smem = sizeof(double) * (size_t)(kLuChunk + h->u) * (h->l + h->u + 1);
-        switch (h->l) {
-            case 1: k_banded_lu_stream<1><<<1, 128, smem>>>(h->d_w, (int)h->n, d_info); break;
-            case 2: k_banded_lu_stream<2><<<1, 128, smem>>>(h->d_w, (int)h->n, d_info); break;
-            case 3: k_banded_lu_stream<3><<<1, 128, smem>>>(h->d_w, (int)h->n, d_info); break;
-            case 4: k_banded_lu_stream<4><<<1, 128, smem>>>(h->d_w, (int)h->n, d_info); break;
-            case 5: k_banded_lu_stream<5><<<1, 128, smem>>>(h->d_w, (int)h->n, d_info); break;
-            default: k_banded_lu_stream<6><<<1, 128, smem>>>(h->d_w, (int)h->n, d_info); break;
-        }
-    }
+    cudaError_t e = bsk::launch_banfac<double>(h->d_w, h->l, h->u, (int)h->n, d_info, getenv("BSK_LU_SERIAL") != nullptr);
     long long info = 0;
-    cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(&info, d_info, 8, cudaMemcpyDeviceToHost);
     bsk::dev_free(d_info);
     if (e != cudaSuccess) { set_error("banded LU failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }

@@ -6,12 +6,13 @@
 // lu! / ldiv! statements in Float32 (src/Collocation/matrix.jl:132-201,218-271); periodic cubic
 // bases go through CyclicTridiagonalMatrix{Float32} (src/Collocation/cyclic.jl:112-197).  The
 // kernels here keep that operation order with non-contracting Float32 arithmetic, so assembly,
-// factors and solutions are bit-identical to the Float32 restatement of those statements (checked in tests/).
+// factors (the BANFAC kernels of banfac.cuh, shared with Float64) and solutions are bit-identical to the Float32 restatement of those statements (checked in tests/).
 // The Float64 path has its own, more elaborate kernels (bsk_solve.cu, bsk_solve_win.cu).
 #include <algorithm>
 #include <cmath>
 #include <vector>
 
+#include "banfac.cuh"
 #include "handles.cuh"
 
 using namespace bsk;
@@ -128,52 +129,6 @@ k_collocation_cyclic_f32(KnotView<float> kv, const float *__restrict__ x, int nx
             else atomicAdd(n_outside, 1ull);
         }
     }
-}
-
-// BANFAC (matrix.jl:132-201): a serial recurrence.  The CTA stages chunks of kChunk columns in
-// shared memory with coalesced accesses; thread 0 eliminates inside the staged window.
-constexpr int kChunk = 512;
-
-__global__ void __launch_bounds__(128)
-k_banded_lu_f32(float *__restrict__ w, int nbandl, int nbandu, int nrow, long long *info) {
-    extern __shared__ float sw[];                          // nroww x (kChunk + nbandu) columns
-    const int nroww = nbandl + nbandu + 1;
-    const int middle = nbandu + 1;
-    __shared__ long long s_info;
-    if (threadIdx.x == 0) s_info = 0;
-    __syncthreads();
-#define W(r, c) sw[((r) - 1) + (size_t)((c) - c0) * nroww]
-    // columns [c0, c0 + ncol) are staged; eliminating column i touches columns i .. i + nbandu
-    for (int c0 = 1; c0 <= nrow && s_info == 0; c0 += kChunk) {
-        const int ncol = min(kChunk + nbandu, nrow - c0 + 1);
-        for (int e = threadIdx.x; e < ncol * nroww; e += blockDim.x) sw[e] = w[(size_t)(c0 - 1) * nroww + e];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int iend = min(c0 + kChunk - 1, nrow);
-            for (int i = c0; i <= iend; ++i) {
-                const float pivot = W(middle, i);
-                if (i == nrow || nbandl == 0) {
-                    if (pivot == 0.0f) { s_info = i; break; }
-                    continue;
-                }
-                if (pivot == 0.0f) { s_info = i; break; }
-                const float ipiv = xdiv(1.0f, pivot);
-                const int jmax = min(nbandl, nrow - i);
-                for (int j = 1; j <= jmax; ++j) W(middle + j, i) = xmul(W(middle + j, i), ipiv);
-                const int kmax = min(nbandu, nrow - i);
-                for (int kk = 1; kk <= kmax; ++kk) {
-                    const float factor = W(middle - kk, i + kk);
-                    for (int j = 1; j <= jmax; ++j)
-                        W(middle - kk + j, i + kk) = xsub(W(middle - kk + j, i + kk), xmul(factor, W(middle + j, i)));
-                }
-            }
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < ncol * nroww; e += blockDim.x) w[(size_t)(c0 - 1) * nroww + e] = sw[e];
-        __syncthreads();
-    }
-#undef W
-    if (threadIdx.x == 0) *info = s_info;
 }
 
 __global__ void k_repack_f32(const float *__restrict__ w, int bw, int n, float *__restrict__ lrow,
@@ -425,10 +380,8 @@ bsk_status bsk_banded_f32_lu(bsk_banded_f32 *h, int64_t *info_pivot) {
     BSK_CUDA(cudaSetDevice(h->device));
     long long *d_info = nullptr;
     BSK_CUDA(bsk::dev_malloc((void **)&d_info, 8));
-    const size_t smem = sizeof(float) * (size_t)(kChunk + h->u) * (h->l + h->u + 1);
-    k_banded_lu_f32<<<1, 128, smem>>>(h->d_w, h->l, h->u, (int)h->n, d_info);
     long long info = 0;
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = bsk::launch_banfac<float>(h->d_w, h->l, h->u, (int)h->n, d_info, false);
     if (e == cudaSuccess) e = cudaMemcpy(&info, d_info, 8, cudaMemcpyDeviceToHost);
     bsk::dev_free(d_info);
     if (e != cudaSuccess) { set_error("banded LU failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
