@@ -179,3 +179,27 @@ def test_periodic_cubic_f32(bk, oracle, synth):
     ys = np.cos(2 * np.pi * xs.astype(np.float64)).astype(np.float32)
     itp = bk.interpolate(xs, ys, bk.BSplineOrder(4), bk.Periodic(np.float32(br[-1] - br[0])))
     assert np.allclose(itp.spline(xs), ys, atol=2e-5)
+
+
+def test_interpolate_f32_natural_and_derivative_rows(bk, synth):
+    """Natural() interpolation in Float32 (SplineInterpolations.jl:275-285, test/natural.jl): the
+    interpolant reproduces the data and its second derivative vanishes at both ends; collocation rows of
+    Derivative(1) in Float32 agree with the Float64 rows."""
+    n = 64
+    x = synth.breakpoints(6, n).astype(np.float32)
+    y = np.cos(5 * x.astype(np.float64)).astype(np.float32)
+    itp = bk.interpolate(x, y, bk.BSplineOrder(4), bk.Natural())
+    S = itp.spline
+    assert np.allclose(S(x), y, atol=3e-5)
+    d2 = (bk.Derivative(2) * S)(np.array([x[0], x[-1]], dtype=np.float32))
+    scale = float(np.max(np.abs((bk.Derivative(2) * S)(x))))
+    assert np.all(np.abs(d2) < 2e-3 * scale)
+    itp64 = bk.interpolate(x.astype(np.float64), y.astype(np.float64), bk.BSplineOrder(4), bk.Natural())
+    xs = synth.u_numpy(13, 0, 2000)
+    assert relerr(S(xs.astype(np.float32)), itp64.spline(xs)) < 50 * TOL32
+    B32 = bk.BSplineBasis(5, x)
+    B64 = bk.BSplineBasis(5, x.astype(np.float64))
+    xc = bk.collocation_points(B32).astype(np.float32)
+    C32 = bk.collocation_matrix(B32, xc, bk.Derivative(1)).dense()
+    C64 = bk.collocation_matrix(B64, xc.astype(np.float64), bk.Derivative(1)).dense()
+    assert relerr(C32, C64) < 20 * TOL32
