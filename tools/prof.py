@@ -187,3 +187,16 @@ if args.what == "solve32":
             tot += e0.elapsed_time(e1)
     ms = tot / args.reps
     print("solve32: %.3f ms  %.1f M RHS/s  %.1f GB/s (8 B/element)" % (ms, args.nrhs / ms / 1e3, 8 * 4096 * args.nrhs / ms / 1e6))
+if args.what == "sweep":
+    # evaluation rate over (dtype, order, number of breakpoints): which table variant serves which shape
+    for dt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+        for k in (2, 3, 4, 6, 8):
+            for nb in (100, 1000, 1700, 3000, 30000):
+                br = synth.breakpoints(3, nb).astype(dt)
+                B = bk.BSplineBasis(k, br)
+                S = bk.Spline(B, (2 * synth.u_numpy(4, 0, len(B)) - 1).astype(dt))
+                xd = synth.u_torch(5, 0, args.points, dtype=tdt)
+                outs = [torch.empty_like(xd)]
+                ms = timed(lambda: S.evaluate(xd, (0,), out=outs), args.reps)
+                print("%s k=%d breaks=%6d: %.3f ms  %.1f Gpt/s" % (np.dtype(dt).name, k, nb, ms, args.points / ms / 1e6), flush=True)
+                del xd, outs
