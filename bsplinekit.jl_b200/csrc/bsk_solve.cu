@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "banfac.cuh"
+#include "banslv.cuh"
 #include "handles.cuh"
 
 using namespace bsk;
@@ -126,79 +127,7 @@ __global__ void k_repack(const double *__restrict__ w, int bw, int n, double *__
     }
 }
 
-// ---- K6a: BANSLV order, two passes over HBM, one thread per right-hand side ----------------
-// rhs is interleaved: rhs[r * nrhs + c].  Bit-faithful to matrix.jl:218-271 (mul, then sub,
-// true division by the pivot).
-template <int BW, int U>
-__global__ void __launch_bounds__(kThreads)
-k_banded_forward(const double *__restrict__ lrow, double *__restrict__ rhs, int64_t nrhs, int64_t ld, int n) {
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
-         c += (int64_t)gridDim.x * blockDim.x) {
-        double zw[BW > 0 ? BW : 1];
-#pragma unroll
-        for (int j = 0; j < BW; ++j) zw[j] = 0.0;
-        double *p = rhs + c;
-        double cur[U], nxt[U];
-#pragma unroll
-        for (int q = 0; q < U; ++q) cur[q] = q < n ? p[(int64_t)q * ld] : 0.0;
-        for (int r = 0; r < n; r += U) {
-            // prefetch the next batch of rows while this one is being eliminated
-#pragma unroll
-            for (int q = 0; q < U; ++q) nxt[q] = (r + U + q < n) ? p[(int64_t)(r + U + q) * ld] : 0.0;
-#pragma unroll
-            for (int q = 0; q < U; ++q) {
-                if (r + q < n) {
-                    double z = cur[q];
-                    const double *lr = lrow + (size_t)(r + q) * BW;
-#pragma unroll
-                    for (int j = BW; j >= 1; --j) z = xsub(z, xmul(zw[j - 1], __ldg(lr + j - 1)));
-#pragma unroll
-                    for (int j = BW - 1; j >= 1; --j) zw[j] = zw[j - 1];
-                    if (BW > 0) zw[0] = z;
-                    p[(int64_t)(r + q) * ld] = z;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < U; ++q) cur[q] = nxt[q];
-        }
-    }
-}
-
-template <int BW, int U>
-__global__ void __launch_bounds__(kThreads)
-k_banded_backward(const double *__restrict__ urow, const double *__restrict__ diag,
-                  double *__restrict__ rhs, int64_t nrhs, int64_t ld, int n) {
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs;
-         c += (int64_t)gridDim.x * blockDim.x) {
-        double xw[BW > 0 ? BW : 1];
-#pragma unroll
-        for (int j = 0; j < BW; ++j) xw[j] = 0.0;
-        double *p = rhs + c;
-        double cur[U], nxt[U];
-#pragma unroll
-        for (int q = 0; q < U; ++q) cur[q] = (n - 1 - q >= 0) ? p[(int64_t)(n - 1 - q) * ld] : 0.0;
-        for (int r = n - 1; r >= 0; r -= U) {
-#pragma unroll
-            for (int q = 0; q < U; ++q) nxt[q] = (r - U - q >= 0) ? p[(int64_t)(r - U - q) * ld] : 0.0;
-#pragma unroll
-            for (int q = 0; q < U; ++q) {
-                if (r - q >= 0) {
-                    double acc = cur[q];
-                    const double *ur = urow + (size_t)(r - q) * BW;
-#pragma unroll
-                    for (int j = BW; j >= 1; --j) acc = xsub(acc, xmul(xw[j - 1], __ldg(ur + j - 1)));
-                    const double xr = xdiv(acc, __ldg(diag + (r - q)));
-#pragma unroll
-                    for (int j = BW - 1; j >= 1; --j) xw[j] = xw[j - 1];
-                    if (BW > 0) xw[0] = xr;
-                    p[(int64_t)(r - q) * ld] = xr;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < U; ++q) cur[q] = nxt[q];
-        }
-    }
-}
+// ---- K6a (BANSLV order, two passes over HBM, one thread per right-hand side): banslv.cuh -------
 
 // ---- K6b (single-pass windowed solve) lives in bsk_solve_win.cu --------------------------------
 
@@ -409,9 +338,9 @@ bsk_status solve_dispatch(const bsk_banded *h, double *d_rhs, int64_t nrhs, int 
     } else if (rest > 0) {                                    // BANSLV-order two-pass
         const int bs = rest >= 148 * 2 * 256 ? 128 : 64;
         int grid = (int)std::max<int64_t>(1, (rest + bs - 1) / bs);
-        k_banded_forward<BW, 16><<<grid, bs, 0, st>>>(h->d_lrow, d_rhs + done, rest, nrhs, n);
+        if (BW > 0) k_banslv_sweep<BW, 16, +1, double><<<grid, bs, 0, st>>>(h->d_lrow, h->d_diag, d_rhs + done, rest, nrhs, n);
         BSK_CUDA(cudaGetLastError());
-        k_banded_backward<BW, 16><<<grid, bs, 0, st>>>(h->d_urow, h->d_diag, d_rhs + done, rest, nrhs, n);
+        k_banslv_sweep<BW, 16, -1, double><<<grid, bs, 0, st>>>(h->d_urow, h->d_diag, d_rhs + done, rest, nrhs, n);
         BSK_CUDA(cudaGetLastError());
     }
     return BSK_OK;

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "banfac.cuh"
+#include "banslv.cuh"
 #include "handles.cuh"
 
 using namespace bsk;
@@ -143,89 +144,6 @@ __global__ void k_repack_f32(const float *__restrict__ w, int bw, int n, float *
     }
 }
 
-// BANSLV (matrix.jl:218-271), one thread per right-hand side, rhs[r * nrhs + c].  The reference
-// updates x[i+j] -= x[i] * w[middle+j, i] for j = 1..bw right after x[i] is final; per element that
-// is the sequence of subtractions below, in the same order (oldest multiplier first).  One routine
-// serves both sweeps: DIR = +1 walks the rows downwards with the rows of L (unit diagonal), DIR = -1
-// upwards with the rows of U and a true division by the pivot.  Rows are prefetched U at a time into
-// registers; addresses advance by pointer increments and full batches run without predication (the
-// per-row instruction count is what bounds a single thread walking all n rows).
-template <int BW>
-__device__ __forceinline__ void load_rec(const float *rp, float (&l)[BW > 0 ? BW : 1]) {
-    if (BW == 4) {
-        const float4 v = __ldg((const float4 *)rp);
-        l[0] = v.x; l[1 % (BW > 0 ? BW : 1)] = v.y; l[2 % (BW > 0 ? BW : 1)] = v.z; l[3 % (BW > 0 ? BW : 1)] = v.w;
-    } else if (BW == 2) {
-        const float2 v = __ldg((const float2 *)rp);
-        l[0] = v.x; l[1 % (BW > 0 ? BW : 1)] = v.y;
-    } else {
-#pragma unroll
-        for (int j = 0; j < BW; ++j) l[j] = __ldg(rp + j);
-    }
-}
-
-template <int BW, int DIR>
-__device__ __forceinline__ float row_step(float v, float (&st)[BW > 0 ? BW : 1], const float *rp, const float *dp) {
-    float l[BW > 0 ? BW : 1];
-    load_rec<BW>(rp, l);
-#pragma unroll
-    for (int j = BW; j >= 1; --j) v = xsub(v, xmul(st[j - 1], l[j - 1]));
-    if (DIR < 0) v = xdiv(v, __ldg(dp));
-#pragma unroll
-    for (int j = BW - 1; j >= 1; --j) st[j] = st[j - 1];
-    if (BW > 0) st[0] = v;
-    return v;
-}
-
-template <int BW, int U, int DIR>
-__global__ void __launch_bounds__(kThreads)
-k_sweep_f32(const float *__restrict__ rec, const float *__restrict__ diag, float *__restrict__ rhs, int64_t nrhs,
-            int n) {
-    const int64_t sd = DIR > 0 ? nrhs : -nrhs;              // element stride between consecutive steps
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nrhs; c += (int64_t)gridDim.x * blockDim.x) {
-        float st[BW > 0 ? BW : 1];
-#pragma unroll
-        for (int j = 0; j < (BW > 0 ? BW : 1); ++j) st[j] = 0.0f;
-        const int64_t first = DIR > 0 ? 0 : (int64_t)(n - 1);
-        float *ps = rhs + c + first * nrhs;                  // element of the current step
-        const float *pl = ps;                                // element of the next step to load
-        const float *rp = rec + first * BW;
-        const float *dp = diag + first;
-        float cur[U], nxt[U];
-#pragma unroll
-        for (int q = 0; q < U; ++q) {
-            cur[q] = q < n ? *pl : 0.0f;
-            pl += sd;
-        }
-        for (int s0 = 0; s0 < n; s0 += U) {
-            if (s0 + 2 * U <= n) {                           // next batch complete: no predication
-#pragma unroll
-                for (int q = 0; q < U; ++q) { nxt[q] = *pl; pl += sd; }
-            } else {
-#pragma unroll
-                for (int q = 0; q < U; ++q) { nxt[q] = (s0 + U + q < n) ? *pl : 0.0f; pl += sd; }
-            }
-            if (s0 + U <= n) {
-#pragma unroll
-                for (int q = 0; q < U; ++q) {
-                    *ps = row_step<BW, DIR>(cur[q], st, rp, dp);
-                    ps += sd; rp += DIR * BW; dp += DIR;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < U; ++q) {
-                    if (s0 + q < n) {
-                        *ps = row_step<BW, DIR>(cur[q], st, rp, dp);
-                        ps += sd; rp += DIR * BW; dp += DIR;
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < U; ++q) cur[q] = nxt[q];
-        }
-    }
-}
-
 template <int BW>
 bsk_status solve_f32(const bsk_banded_f32 *h, float *d_rhs, int64_t nrhs, cudaStream_t st) {
     // one thread per column walks all n rows: small CTAs spread the columns evenly over the SMs
@@ -233,8 +151,8 @@ bsk_status solve_f32(const bsk_banded_f32 *h, float *d_rhs, int64_t nrhs, cudaSt
     // enough 128-byte requests in flight per warp
     constexpr int kBlock = 64;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nrhs + kBlock - 1) / kBlock, 148 * 32));
-    if (BW > 0) k_sweep_f32<BW, 32, +1><<<grid, kBlock, 0, st>>>(h->d_lrow, h->d_diag, d_rhs, nrhs, (int)h->n);
-    k_sweep_f32<BW, 32, -1><<<grid, kBlock, 0, st>>>(h->d_urow, h->d_diag, d_rhs, nrhs, (int)h->n);
+    if (BW > 0) k_banslv_sweep<BW, 32, +1, float><<<grid, kBlock, 0, st>>>(h->d_lrow, h->d_diag, d_rhs, nrhs, nrhs, (int)h->n);
+    k_banslv_sweep<BW, 32, -1, float><<<grid, kBlock, 0, st>>>(h->d_urow, h->d_diag, d_rhs, nrhs, nrhs, (int)h->n);
     BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }
