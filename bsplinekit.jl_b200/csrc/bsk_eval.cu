@@ -556,6 +556,7 @@ bsk_status build_pp(bsk_spline *s) {
         // (one 32-byte L2 sector per cubic F64 / order-8 F32 record) and L2-resident.
         const bool in_global = nc < 3 * nrec && nrec <= 400000 && getenv("BSK_NO_GLOBAL_CELL") == nullptr;
         const bool jump = jump_ok && !in_global;
+        const bool jpad = jump && bsk::cell_jump_pad(k);      // odd order: flag + index in the spare slot
         double dscale[BSK_MAXK];                               // magnitude of D^d S: max |coefficient|
         for (int d = 0; d < k; ++d) {
             dscale[d] = 0.0;
@@ -595,7 +596,7 @@ bsk_status build_pp(bsk_spline *s) {
                 taylor(pid[pl], (double)centerT, cf);
                 if (nb == 0) {
                     for (int m = 0; m < k; ++m) crec[c * RECV + m] = (T)cf[m];
-                    crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 0);
+                    if (!jpad) crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 0);
                 } else if (nb == 1 && jump) {
                     // simple knot <=> the two pieces are consecutive knot intervals; the first and the
                     // last cell are kept unflagged-or-multi (boundary pieces feed the extrapolations)
@@ -627,18 +628,23 @@ bsk_status build_pp(bsk_spline *s) {
                             if (!(sum <= 16.0 * dscale[d] + 1e-300)) accurate = false;
                         }
                     }
-                    if (accurate && j < kJumpMulti) {
+                    if (accurate && (jpad || j < kJumpMulti)) {
                         side_l.push_back((T)plo[pl + 1]);
                         side_l.push_back((T)(cr[k - 1] - cf[k - 1]));
-                        put_index_bits(&crec[c * RECV], j);
+                        if (jpad) crec[c * RECV + RECV - 1] = index_bits(j);
+                        else put_index_bits(&crec[c * RECV], j);
                     } else {
-                        put_index_bits(&crec[c * RECV], kJumpMulti);
+                        if (jpad) crec[c * RECV + RECV - 1] = index_bits(kMulti);
+                        else put_index_bits(&crec[c * RECV], kJumpMulti);
                         ++nmulti;
                     }
-                    crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 1);
+                    if (!jpad) crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 1);
                 } else if (nb >= 2 && jump) {
-                    put_index_bits(&crec[c * RECV], kJumpMulti);
-                    crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 1);
+                    if (jpad) crec[c * RECV + RECV - 1] = index_bits(kMulti);
+                    else {
+                        put_index_bits(&crec[c * RECV], kJumpMulti);
+                        crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 1);
+                    }
                     ++nmulti;
                 } else if (nb == 1) {
                     const uint32_t j = (uint32_t)(side_l.size() / RECV);

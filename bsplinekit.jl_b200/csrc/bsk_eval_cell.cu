@@ -11,10 +11,12 @@
 // knot is then compared exactly, so the selected knot interval is exactly the one `searchsortedlast` finds
 // (src/BSplines/evaluate_all.jl:102-119) whatever the rounding of the cell index.  Cells with
 // two or more knots (clustered knots) fall back to the per-interval table in global memory.
-// Float64 splines of order >= 4 staged in shared memory use the "jump" encoding instead: the
+// Float64 splines of order >= 3 staged in shared memory use the "jump" encoding instead: the
 // flagged record keeps the piece left of the (simple) knot xi, the side entry is {xi, J} and the
 // piece right of the knot is  P_L + J (x - xi)^(k-1)  — one 16-byte gather on the slow path instead
-// of two, and a 4x smaller side table (more cells, fewer flagged lanes).
+// of two, and a 4x smaller side table (more cells, fewer flagged lanes).  Odd orders carry the flag
+// and the side index in the spare slot of the padded record (coefficients untouched), even orders in
+// bits 1..3 of the first four coefficients.
 //
 // Replaces the body of (S::Spline)(x) broadcast over many points
 // (src/Splines/spline.jl:144-209) and of (Derivative(n) * S).(x) (spline.jl:272-330) fused in
@@ -150,6 +152,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
     constexpr int NOUT = DMASK ? MaskCount<DMASK>::value : kMaxOut;
     constexpr bool WIDE = !STAGE && (RECV * sizeof(T)) % 32 == 0;     // 256-bit record gathers
     constexpr bool JUMP = STAGE && bsk::cell_jump_scheme((int)sizeof(T), K);
+    constexpr bool JPAD = JUMP && bsk::cell_jump_pad(K);            // flag + side index in the spare slot
     extern __shared__ __align__(16) unsigned char smem[];
     // ---- tables: staged in shared memory (STAGE = 1), or, when they are too large for it, read
     //      in place from global memory through L1/L2 by the very same code (STAGE = 0) ----------
@@ -229,14 +232,14 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
         T jump_[VEC], dxk_[VEC];           // "jump" encoding: J and x - knot right of the knot, else 0
 #pragma unroll
         for (int q = 0; q < VEC; ++q) {
-            const T last = rec_[q][K - 1];
+            const T last = rec_[q][JPAD ? RECV - 1 : K - 1];
             multi_[q] = false;
             jump_[q] = (T)0;
             dxk_[q] = (T)0;
             if (JUMP) {
                 if (Bits<T>::flag(last)) {
-                    const unsigned j = jump_index(rec_[q]);
-                    if (j == kJumpMultiCell) {
+                    const unsigned j = JPAD ? Bits<T>::index(last) : jump_index(rec_[q]);
+                    if (j == (JPAD ? kMultiKnotCell : kJumpMultiCell)) {
                         multi_[q] = true;
                     } else {
                         const int4 r = ((const int4 *)s_rc)[j];

@@ -43,8 +43,11 @@ template <typename P> inline cudaError_t dev_malloc(P **p, size_t bytes) { retur
     } while (0)
 
 // Uniform-cell tables staged in shared memory use the "jump" encoding of cells that contain a knot
-// (bsk_eval.cu: build, bsk_eval_cell.cu: kernel) for Float64 splines of order >= 4.
-__host__ __device__ constexpr bool cell_jump_scheme(int elt_bytes, int k) { return elt_bytes == 8 && k >= 4; }
+// (bsk_eval.cu: build, bsk_eval_cell.cu: kernel) for Float64 splines of order >= 3.  Odd orders have a
+// spare slot in the 16-byte-padded record, which carries the flag and the side index; even orders
+// (>= 4) carry them in low mantissa bits of the coefficients.
+__host__ __device__ constexpr bool cell_jump_scheme(int elt_bytes, int k) { return elt_bytes == 8 && k >= 3; }
+__host__ __device__ constexpr bool cell_jump_pad(int k) { return (k & 1) != 0; }     // RECV = k + 1 for doubles
 
 inline int sm_count(int device) {
     static int cached[64] = {0};

@@ -1162,16 +1162,16 @@ def test_knot_search_and_basis_awkward_knot_vectors(bk, oracle, k):
         assert np.array_equal(bs.cpu().numpy(), rbs, equal_nan=True), nd
 
 
-@pytest.mark.parametrize("k", [4, 5, 6, 7, 8])
+@pytest.mark.parametrize("k", [3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("uneven", [False, True])
 def test_eval_cell_jump_encoding(bk, oracle, synth, k, uneven):
-    """Shared-memory cell tables of Float64 splines of order >= 4 keep, for a cell holding one simple
+    """Shared-memory cell tables of Float64 splines of order >= 3 keep, for a cell holding one simple
     knot xi, the piece left of it plus {xi, J}: right of the knot the kernel evaluates
     P_L + J (x - xi)^(k-1).  Values and every derivative order, at the knots themselves, one ulp either
     side of them and at random points, against the oracle (src/Splines/spline.jl:144-209,272-330);
     very uneven neighbouring intervals must be caught by the accuracy guard of the table builder."""
     import torch
-    nb = 1000 if k <= 6 else 600
+    nb = 1500 if k == 3 else (1000 if k <= 6 else 600)
     br = synth.breakpoints(3, nb)
     if uneven:
         rng = np.random.default_rng(77 + k)
