@@ -62,5 +62,16 @@ Bg = bk.BSplineBasis(5, synth.breakpoints(61, 70))
 bk.galerkin_matrix(Bg, (bk.Derivative(1), bk.Derivative(0)))
 bk.approximate(np.exp, Bg, bk.MinimiseL2Error())
 bk.galerkin_matrix(bk.RecombinedBSplineBasis(Bg, bk.Derivative(0)), as_band=True)
+# jump-encoded knot cells (odd / even orders), Float32 interpolation path (plain, recombined, periodic cubic)
+for k in (3, 5, 6, 7):
+    Bj = bk.BSplineBasis(k, synth.breakpoints(3, 900))
+    Sj = bk.Spline(Bj, 2 * synth.u_numpy(4, 0, len(Bj)) - 1)
+    Sj.evaluate(torch.from_numpy(synth.u_numpy(5, 0, 20011)).cuda(), (0, 1, 2))
+x32 = synth.breakpoints(6, 333).astype(np.float32)
+for k in (2, 4, 6, 8):
+    itp = bk.interpolate(x32, np.sin(6 * x32), bk.BSplineOrder(k))
+    itp.interpolate_((2 * synth.u_torch(7, 0, 333 * 130, dtype=torch.float32) - 1).reshape(333, 130))
+bk.interpolate(x32, np.sin(6 * x32), bk.BSplineOrder(4), bk.Natural())
+bk.interpolate(x32[:-1], np.sin(2 * np.pi * x32[:-1]), bk.BSplineOrder(4), bk.Periodic(np.float32(1.0)))
 torch.cuda.synchronize()
 print("DONE")
