@@ -458,6 +458,12 @@ def run_ours(args):
         extra["float32_batched_solve"] = {"metric": "RHS/s (n=4096, k=6, 65536 RHS per GPU, Float32, BANSLV order)",
                                           "ms": ms, "value": world * nr32 / (ms * 1e-3), "unit": "RHS/s",
                                           "roofline_frac": 8.0 * 4096 * nr32 / (ms * 1e-3) / 1e9 / peak}
+        if rank == 0:
+            from oracle import oracle as O32
+            band32, _ = O32.collocation_matrix_f32(0, 6, B32.knots(), xd32)
+            O32.banded_lu(band32)
+            ref32 = O32.banded_solve(band32, Y32[:, :128].cpu().numpy().copy())
+            chk["float32_solve_bitexact"] = bool(np.array_equal(W32[:, :128].cpu().numpy(), ref32))
         del Y32, W32, itp32
         B6 = bk.BSplineBasis(6, synth.breakpoints(3, 1000))
         S6 = bk.Spline(B6, 2 * synth.u_numpy(4, 0, len(B6)) - 1)
@@ -467,6 +473,12 @@ def run_ours(args):
         extra["order6_eval"] = {"metric": "Gpoints/s (k=6, 1000 breakpoints, value + 1st derivative, 2^28 F64 points)",
                                 "ms": ms, "value": world * npts / (ms * 1e-3) / 1e9, "unit": "Gpoints/s",
                                 "roofline_frac": 24.0 * npts / (ms * 1e-3) / 1e9 / peak}
+        if rank == 0:
+            from oracle import oracle as O6
+            x6h = x6[:1 << 16].cpu().numpy()
+            c6 = 2 * synth.u_numpy(4, 0, len(B6)) - 1
+            r6 = O6.spline_eval(0, 6, B6.knots(), c6, x6h)
+            chk["order6_value_relerr"] = float(np.max(np.abs(o6[0][:1 << 16].cpu().numpy() - r6)) / np.max(np.abs(r6)))
         del x6, o6
 
     # ---- extra: configs[0] (the reference's own CPU-runnable case), in full, host arrays in and out --
