@@ -174,3 +174,49 @@ def test_c5_recombined_robin_full(bk, oracle, synth):
     ref32 = oracle.spline_eval(0, k, Bf.knots(), cf, xs, kt="f32")
     assert np.array_equal(Sf.evaluate(xd[idx].contiguous(), (0,), algo=bk.EVAL_DEBOOR)[0].cpu().numpy(), ref32)
     assert v.abs().max().item() <= 1.0 + 1e-5
+
+
+def test_c3_shape_float32_solve(bk, oracle, synth):
+    """C3's shape in Float32 (n = 4096, k = 6, 65 536 data sets): BANSLV-order solve, bit-exact against the
+    Float32 restatement on columns sampled over the whole block; identical columns give identical bits
+    wherever they sit in the block; small backward error."""
+    import torch
+    n, k, M = 4096, 6, 65536
+    x32 = synth.breakpoints(6, n).astype(np.float32)
+    B = bk.BSplineBasis(k, bk.make_knots(x32, k), augment=False)
+    itp = bk.SplineInterpolation(B, x32)
+    Y = (2 * synth.u_torch(7, 0, n * M, dtype=torch.float32) - 1).reshape(n, M)
+    Y[:, M - 3] = Y[:, 5]                      # the same data set in two far-apart columns
+    Y[:, 40001] = Y[:, 5]
+    cols = torch.arange(0, M, 509, device="cuda")
+    Y0 = Y[:, cols].cpu().numpy().copy()
+    itp.interpolate_(Y)
+    band, _ = oracle.collocation_matrix_f32(0, k, B.knots(), x32)
+    assert oracle.banded_lu(band) == 0
+    ref = oracle.banded_solve(band, Y0.copy())
+    assert np.array_equal(Y[:, cols].cpu().numpy(), ref)
+    assert torch.equal(Y[:, 5], Y[:, M - 3]) and torch.equal(Y[:, 5], Y[:, 40001])
+    # backward error of the Float32 solve, measured in Float64 against the Float32 matrix itself (with 4096
+    # points on [0, 1] the Float32 knots carry ~1e-4 of a knot interval, so the Float64 interpolant of the
+    # same data is a different, equally valid, answer; the reference behaves the same way)
+    A32, _ = oracle.collocation_matrix_f32(0, k, B.knots(), x32)
+    res = oracle.banded_matvec(A32.astype(np.float64), ref[:, :16].astype(np.float64)) - Y0[:, :16]
+    assert np.max(np.abs(res)) < 1e-5 * max(1.0, float(np.max(np.abs(ref[:, :16]))))
+
+
+def test_order6_full_size_eval(bk, oracle, synth):
+    """Order 6 at 2^28 points: shared-memory cell table with jump-encoded knot cells (value + derivative)."""
+    import torch
+    n, k = 1 << 28, 6
+    B = bk.BSplineBasis(k, synth.breakpoints(3, 1000))
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    xd = synth.u_torch(5, 0, n)
+    v, d = S.evaluate(xd, (0, 1))
+    idx = torch.arange(0, n, 4099, device="cuda")
+    xs = xd[idx].cpu().numpy()
+    assert relerr(v[idx].cpu().numpy(), oracle.spline_eval(0, k, B.knots(), c, xs)) < TOL64
+    kd, td, cd = oracle.spline_derivative(0, k, B.knots(), c, 1)
+    assert relerr(d[idx].cpu().numpy(), oracle.spline_eval(0, kd, td, cd, xs)) < TOL64
+    assert v.abs().max().item() <= np.abs(c).max() * (1 + 1e-14)
+    assert torch.equal(S.evaluate(xd, (0,))[0], v)
