@@ -573,7 +573,7 @@ bsk_status build_pp(bsk_spline *s) {
             const char *e = getenv("BSK_GLOBAL_CELL_MULT2");        // cells per interval, x2
             const int m2 = e ? std::max(6, atoi(e)) : 64;
             nc = (nrec * m2) / 2;                                   // 32 cells per interval ...
-            const int64_t cap = (32ll << 20) / (int64_t)(RECV * sizeof(T));   // ... within 32 MB (L2-resident)
+            const int64_t cap = (32ll << 20) / (int64_t)(bsk::cell_global_stride((int)sizeof(T), RECV) * sizeof(T));   // ... within 32 MB (L2-resident)
             nc = std::max<int64_t>(std::min(nc, cap), 3 * nrec);
         }
         for (int attempt = 0; attempt < 6 && nc >= 3 * nrec && nc >= 8; ++attempt, nc = nc * 9 / 10) {
@@ -669,19 +669,20 @@ bsk_status build_pp(bsk_spline *s) {
             if (!in_global && smem > 226 * 1024) continue;      // retry with fewer cells
             if (nmulti * 50 > nc) break;                        // clustered knots: not worth it
             // device layout: chunk-major for shared memory, record-major for global (CellView)
-            std::vector<T> crec_cm(crec.size()), rc_cm(jump ? side_l.size() : 2 * side_l.size());
+            const int RS = in_global ? bsk::cell_global_stride((int)sizeof(T), RECV) : RECV;   // record stride on the device
+            std::vector<T> crec_cm((size_t)nc * RS, (T)0), rc_cm(jump ? side_l.size() : 2 * (size_t)nside * RS, (T)0);
             if (jump) rc_cm = side_l;                           // {knot, jump} pairs, 16 bytes each
             for (int64_t c = 0; c < nc; ++c)
                 for (int w = 0; w < NCH; ++w)
                     for (int e = 0; e < VPA; ++e)
-                        crec_cm[in_global ? (size_t)c * RECV + w * VPA + e : ((size_t)w * nc + c) * VPA + e] =
+                        crec_cm[in_global ? (size_t)c * RS + w * VPA + e : ((size_t)w * nc + c) * VPA + e] =
                             crec[c * RECV + w * VPA + e];
             for (int side = 0; side < 2 && !jump; ++side) {
                 const std::vector<T> &src = side ? side_r : side_l;
                 for (int64_t j = 0; j < nside; ++j)
                     for (int w = 0; w < NCH; ++w)
                         for (int e = 0; e < VPA; ++e)
-                            rc_cm[in_global ? ((size_t)side * nside + j) * RECV + w * VPA + e
+                            rc_cm[in_global ? ((size_t)side * nside + j) * RS + w * VPA + e
                                             : (((size_t)side * NCH + w) * nside + j) * VPA + e] = src[j * RECV + w * VPA + e];
             }
             for (void **p : {&s->d_cell_rec, &s->d_cell_rc})

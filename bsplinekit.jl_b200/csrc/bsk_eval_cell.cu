@@ -150,7 +150,9 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
     constexpr int RECV = CellRec<K, T>::RECV;
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int NOUT = DMASK ? MaskCount<DMASK>::value : kMaxOut;
-    constexpr bool WIDE = !STAGE && (RECV * sizeof(T)) % 32 == 0;     // 256-bit record gathers
+    // global-memory tables: record stride RS (records longer than a sector are padded to 64 bytes)
+    constexpr int RS = STAGE ? RECV : bsk::cell_global_stride((int)sizeof(T), RECV);
+    constexpr bool WIDE = !STAGE && (RS * sizeof(T)) % 32 == 0;       // 256-bit record gathers
     constexpr bool JUMP = STAGE && bsk::cell_jump_scheme((int)sizeof(T), K);
     constexpr bool JPAD = JUMP && bsk::cell_jump_pad(K);            // flag + side index in the spare slot
     extern __shared__ __align__(16) unsigned char smem[];
@@ -188,7 +190,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
         memcpy(xv, &raw, 16);
         T res[NOUT][VEC];
         // phase 1: all cell-record gathers of this vector are issued before any of them is used
-        T xs_[VEC], rec_[VEC][RECV];
+        T xs_[VEC], rec_[VEC][RS];
         int c_[VEC];
         bool out_[VEC];
 #pragma unroll
@@ -208,11 +210,11 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
             c_[q] = c;
             out_[q] = outside;
             // STAGE: chunk-major (bank spread); global: record-major (one 32-byte sector)
-            const int4 *R4 = (const int4 *)s_rec + (STAGE ? (size_t)c : (size_t)c * (RECV / VEC));
+            const int4 *R4 = (const int4 *)s_rec + (STAGE ? (size_t)c : (size_t)c * (RS / VEC));
             const int cs = STAGE ? cv.ncell : 1;
             if (WIDE) {
 #pragma unroll
-                for (int w = 0; w < RECV / VEC; w += 2) {
+                for (int w = 0; w < RS / VEC; w += 2) {
                     int4 lo, hi;
                     ldg256(R4 + w, lo, hi);
                     memcpy(&rec_[q][w * VEC], &lo, 16);
@@ -257,12 +259,12 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
                     multi_[q] = true;
                 } else {
                     const int right = (xs_[q] < rec_[q][XI]) ? 0 : 1;
-                    const int4 *R4 = (const int4 *)s_rc + (size_t)right * (RECV / VEC) * cv.nside +
-                                     (STAGE ? (size_t)j : (size_t)j * (RECV / VEC));
+                    const int4 *R4 = (const int4 *)s_rc + (size_t)right * (RS / VEC) * cv.nside +
+                                     (STAGE ? (size_t)j : (size_t)j * (RS / VEC));
                     const int cs = STAGE ? cv.nside : 1;
                     if (WIDE) {
 #pragma unroll
-                        for (int w = 0; w < RECV / VEC; w += 2) {
+                        for (int w = 0; w < RS / VEC; w += 2) {
                             int4 lo, hi;
                             ldg256(R4 + w, lo, hi);
                             memcpy(&rec_[q][w * VEC], &lo, 16);

@@ -49,6 +49,13 @@ template <typename P> inline cudaError_t dev_malloc(P **p, size_t bytes) { retur
 __host__ __device__ constexpr bool cell_jump_scheme(int elt_bytes, int k) { return elt_bytes == 8 && k >= 3; }
 __host__ __device__ constexpr bool cell_jump_pad(int k) { return (k & 1) != 0; }     // RECV = k + 1 for doubles
 
+// Record stride (in elements) of a cell table that stays in global memory: records longer than one
+// 32-byte sector are padded to 64 bytes, so that a record is two whole sectors of one 128-byte line,
+// fetched by two 256-bit loads (bsk_eval_cell.cu).
+__host__ __device__ constexpr int cell_global_stride(int elt_bytes, int recv) {
+    return (recv * elt_bytes > 32 && (recv * elt_bytes) % 64 != 0) ? ((recv * elt_bytes + 63) / 64) * 64 / elt_bytes : recv;
+}
+
 inline int sm_count(int device) {
     static int cached[64] = {0};
     if (device < 0 || device >= 64) return 148;

@@ -1197,3 +1197,33 @@ def test_eval_cell_jump_encoding(bk, oracle, synth, k, uneven):
     v0 = S.evaluate(xd, (0,))[0]
     v02 = S.evaluate(xd, (0, 2))[0]
     assert torch.equal(v0, v02)
+
+
+@pytest.mark.parametrize("k", [5, 6, 7, 8])
+def test_eval_cell_global_wide_records(bk, oracle, synth, k):
+    """Float64 orders 5..8 on thousands of intervals: cell tables in global memory with 64-byte records that
+    lane pairs fetch half by half (full warps) or each lane alone (ragged last warp, unaligned slices).
+    Values and derivatives against the oracle, at knots, one ulp either side of them and at random points."""
+    import torch
+    br = synth.breakpoints(3, 4000)
+    B = bk.BSplineBasis(k, br)
+    t = B.knots()
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    x = np.concatenate([synth.u_numpy(5, 0, 200003), br, np.nextafter(br, -np.inf), np.nextafter(br, np.inf),
+                        [-0.5, 1.5, np.nan]])
+    xd = torch.from_numpy(x).cuda()
+    refs = {}
+    for d in (0, 1, 2):
+        kd, td, cd = (k, t, c) if d == 0 else oracle.spline_derivative(0, k, t, c, d)
+        refs[d] = oracle.spline_eval(0, kd, td, cd, x[:-1])
+    for derivs in ((0,), (0, 1), (0, 1, 2)):
+        outs = S.evaluate(xd, derivs)
+        for d, got in zip(derivs, outs):
+            g = got.cpu().numpy()
+            assert np.isnan(g[-1])
+            assert relerr(g[:-1], refs[d]) < TOL64, (derivs, d)
+    # short and unaligned streams: the last warp is ragged, head / tail elements take the scalar path
+    for lo, hi in ((0, 37), (1, 1000), (3, 65)):
+        got = S.evaluate(xd[lo:hi], (0,))[0].cpu().numpy()
+        assert relerr(got, refs[0][lo:hi]) < TOL64

@@ -24,6 +24,7 @@ ap.add_argument("--nrhs", type=int, default=65536)
 ap.add_argument("--algo", default="auto")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--order", type=int, default=4)
+ap.add_argument("--breaks", type=int, default=1000)
 args = ap.parse_args()
 
 
@@ -40,7 +41,7 @@ def timed(fn, reps):
 
 
 if args.what == "eval":
-    B = bk.BSplineBasis(args.order, synth.breakpoints(3, 1000))
+    B = bk.BSplineBasis(args.order, synth.breakpoints(3, args.breaks))
     S = bk.Spline(B, 2 * synth.u_numpy(4, 0, len(B)) - 1)
     xd = synth.u_torch(5, 0, args.points)
     outs = [torch.empty_like(xd), torch.empty_like(xd)]
