@@ -257,6 +257,30 @@ def run_ours(args):
     except Exception:
         pass
 
+    # the same access mix without the table lookups (n doubles in, 2 n out, same launch shape): what HBM
+    # gives a 1 : 2 read : write stream on this GPU, measured the same way beside the kernel
+    stream_mix = None
+    try:
+        import ctypes
+        from bsplinekit_b200 import _lib as _bl
+        sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        w0 = torch.empty_like(v); w1 = torch.empty_like(dv)      # scratch: the results stay intact
+        probe = lambda: _bl.check(_bl.lib.bsk_probe_stream_1r2w(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(w0.data_ptr()),
+                                                                ctypes.c_void_p(w1.data_ptr()), npts, sp))
+        for _ in range(3):
+            probe()
+        p0 = torch.cuda.Event(enable_timing=True)
+        p1 = torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(10):
+            probe()
+        p1.record()
+        torch.cuda.synchronize()
+        stream_mix = BYTES_PER_POINT * npts / (p0.elapsed_time(p1) / 10 * 1e-3) / 1e9
+        del w0, w1
+    except Exception as exc:                 # the probe is informative only
+        print("stream probe skipped: %r" % (exc,), file=sys.stderr)
+
     # parity spot check on what was just computed (not timed)
     chk = {}
     if rank == 0:
@@ -533,6 +557,8 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "stream_1r2w_gbs": stream_mix,
+                         "frac_of_stream_1r2w": (achieved / stream_mix) if stream_mix else None,
                          "kernel": "k_spline_cell<4,0,double,3>" if args.algo != "deboor" else "k_spline_deboor<4,0,double>",
                          "algorithmic_bytes_per_launch": BYTES_PER_POINT * npts},
             "e2e": e2e, "cpu_baseline": cpu, "parity": chk, "extra": extra,

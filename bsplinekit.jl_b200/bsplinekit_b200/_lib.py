@@ -63,6 +63,7 @@ SIGNATURES = {
     "bsk_version": (C.c_char_p, []),
     "bsk_last_error": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "bsk_device_count": (_i32, [C.POINTER(_i32)]),
+    "bsk_probe_stream_1r2w": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "bsk_malloc": (_i32, [_i32, C.c_size_t, _pp]),
     "bsk_free": (_i32, [_i32, _vp]),
     "bsk_memcpy_h2d": (_i32, [_i32, _vp, _vp, C.c_size_t, _vp]),

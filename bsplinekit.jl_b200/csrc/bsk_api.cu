@@ -53,6 +53,22 @@ cudaError_t dev_free(void *p) {
 
 }  // namespace bsk
 
+// 1 read : 2 writes per element, 16-byte vectors, one CTA of 1024 threads per SM, next vector prefetched:
+// the memory behaviour of the fused value + derivative evaluation without its table lookups.
+__global__ void __launch_bounds__(1024, 1)
+k_probe_stream_1r2w(const double2 *__restrict__ in, double2 *__restrict__ o0, double2 *__restrict__ o1, int64_t nvec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double2 nxt = make_double2(0.0, 0.0);
+    if (v < nvec) nxt = in[v];
+    for (; v < nvec; v += stride) {
+        const double2 x = nxt;
+        if (v + stride < nvec) nxt = in[v + stride];
+        o0[v] = make_double2(x.x + 1.0, x.y + 1.0);
+        o1[v] = make_double2(x.x * 0.5, x.y * 0.5);
+    }
+}
+
 extern "C" {
 
 const char *bsk_version(void) { return "bsplinekit_b200 0.1.0 (sm_100a)"; }
@@ -77,6 +93,20 @@ bsk_status bsk_device_count(int32_t *count) {
         return BSK_ERR_CUDA;
     }
     *count = n;
+    return BSK_OK;
+}
+
+bsk_status bsk_probe_stream_1r2w(const double *d_in, double *d_out0, double *d_out1, int64_t n, void *stream) {
+    BSK_REQUIRE(d_in && d_out0 && d_out1, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(n >= 0 && n % 2 == 0, BSK_ERR_ARGUMENT, "n must be even");
+    BSK_REQUIRE((((uintptr_t)d_in | (uintptr_t)d_out0 | (uintptr_t)d_out1) & 15) == 0, BSK_ERR_ARGUMENT,
+                "pointers must be 16-byte aligned");
+    if (n == 0) return BSK_OK;
+    int dev = 0;
+    BSK_CUDA(cudaGetDevice(&dev));
+    k_probe_stream_1r2w<<<bsk::sm_count(dev), 1024, 0, (cudaStream_t)stream>>>((const double2 *)d_in, (double2 *)d_out0,
+                                                                              (double2 *)d_out1, n / 2);
+    BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }
 

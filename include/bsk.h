@@ -96,6 +96,10 @@ typedef struct {
 const char *bsk_version(void);
 size_t bsk_last_error(char *buf, size_t buflen);
 bsk_status bsk_device_count(int32_t *count);
+/* Measurement aid (no reference counterpart): a pure streaming kernel with the access mix of the fused
+ * value + derivative evaluation — n doubles read, 2 n doubles written, 16-byte vectors, same launch shape —
+ * so that the HBM roofline of that 1 : 2 read : write stream can be measured beside the evaluation kernel. */
+bsk_status bsk_probe_stream_1r2w(const double *d_in, double *d_out0, double *d_out1, int64_t n, void *stream);
 bsk_status bsk_malloc(int32_t device, size_t nbytes, void **d_ptr);
 bsk_status bsk_free(int32_t device, void *d_ptr);
 bsk_status bsk_memcpy_h2d(int32_t device, void *d_dst, const void *h_src, size_t nbytes, void *stream);
