@@ -85,6 +85,7 @@ SIGNATURES = {
     "bsk_spline_derivative": (_i32, [_vp, _i32, _pp]),
     "bsk_spline_eval": (_i32, [_vp, _vp, _i64, _i32, C.POINTER(_i32), _pp, _i32, _vp]),
     "bsk_spline_eval_extrap": (_i32, [_vp, _vp, _i64, _i32, C.POINTER(_i32), _pp, _i32, _i32, _vp]),
+    "bsk_spline_table_info": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_dbl)]),
     "bsk_spline_eval_host": (_i32, [_vp, _vp, _i64, _i32, C.POINTER(_i32), _pp, _i32]),
     "bsk_spline_eval_multi": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "bsk_collocation_matrix": (_i32, [_vp, _vp, _i64, _i32, _dbl, _vp, C.POINTER(_i64), _vp]),

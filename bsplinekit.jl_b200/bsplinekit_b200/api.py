@@ -557,6 +557,18 @@ class Spline:
         check(lib.bsk_spline_derivative(self._handle, int(n), C.byref(out)))
         return Spline(self.basis, _handle=out, _basis_info=(self._dt, self.k - n))
 
+    def table_info(self):
+        """Diagnostics of the evaluation tables of the default path (bsk_spline_table_info): how many cells /
+        interval records there are and how many of them could not be certified to the tolerance."""
+        info = (C.c_int64 * 8)()
+        geom = (C.c_double * 4)()
+        check(lib.bsk_spline_table_info(self._handle, info, geom))
+        names = ("intervals", "intervals_deboor", "cells", "knot_cells", "cells_interval_table", "cells_in_global",
+                 "smem_bytes", "auto_uses_cells")
+        d = dict(zip(names, [int(v) for v in info]))
+        d.update(x0=geom[0], b=geom[1], cell_width=geom[2], scale=geom[3])
+        return d
+
     def evaluate(self, x, derivs=(0,), algo=EVAL_AUTO, out=None, extrap=0):
         """Evaluate D^d S for every d in `derivs` at all points, in one pass over x.
         x: scalar, numpy array (host path, pipelined H2D/kernel/D2H) or CUDA tensor.

@@ -13,7 +13,7 @@ for f in bsk_api bsk_eval bsk_solve bsk_host bsk_eval_cell bsk_eval_cell_f32 bsk
   extra=""
   if [ "$f" = "bsk_eval_cell_f32" ]; then src="$HERE/csrc/bsk_eval_cell.cu"; extra="-DBSK_CELL_F32"; fi
   obj="$OBJ/$f.o"
-  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/csrc/core.cuh" -nt "$obj" ] || [ "$HERE/csrc/handles.cuh" -nt "$obj" ] || [ "$HERE/csrc/pp.cuh" -nt "$obj" ] || [ "$HERE/csrc/tma.cuh" -nt "$obj" ] || [ "$HERE/csrc/banfac.cuh" -nt "$obj" ] || [ "$HERE/csrc/banslv.cuh" -nt "$obj" ] || [ "$HERE/../include/bsk.h" -nt "$obj" ]; then
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/csrc/core.cuh" -nt "$obj" ] || [ "$HERE/csrc/handles.cuh" -nt "$obj" ] || [ "$HERE/csrc/pp.cuh" -nt "$obj" ] || [ "$HERE/csrc/tma.cuh" -nt "$obj" ] || [ "$HERE/csrc/banfac.cuh" -nt "$obj" ] || [ "$HERE/csrc/banslv.cuh" -nt "$obj" ] || [ "$HERE/csrc/pptable.h" -nt "$obj" ] || [ "$HERE/csrc/dd.h" -nt "$obj" ] || [ "$HERE/../include/bsk.h" -nt "$obj" ]; then
     ( $NVCC $FLAGS $extra -c "$src" -o "$obj" > "$OBJ/$f.log" 2>&1 || { cat "$OBJ/$f.log" | grep -v "^ptxas info" | head -60; exit 1; } ) &
     pids+=($!)
   fi

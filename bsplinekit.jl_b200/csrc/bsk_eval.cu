@@ -12,6 +12,7 @@
 
 #include "handles.cuh"
 #include "pp.cuh"
+#include "pptable.h"
 
 using namespace bsk;
 
@@ -195,7 +196,7 @@ k_spline_pp(KnotView<T> kv, int ncoef, PPView<T> pv, const T *__restrict__ x, in
             const T xs = outside ? ((KIND == 0 && E != 0 && xq > xa) ? xb : xa) : xq;
             T cm[K];
             T u;
-            pp_lookup<K, T>(pv, xs, cm, &u);
+            const bool exact = pp_lookup<K, T>(pv, xs, cm, &u);      // record not certified -> de Boor
             if (KIND == 0 && E == BSK_EXTRAP_SMOOTH && outside) u += xq - xs;
 #pragma unroll
             for (int o = 0; o < kMaxOut; ++o) {
@@ -205,14 +206,15 @@ k_spline_pp(KnotView<T> kv, int ncoef, PPView<T> pv, const T *__restrict__ x, in
 #pragma unroll
                     for (int m = K - 1; m >= 0; --m)
                         if (m >= d) acc = fma(acc, u, d == 0 ? cm[m] : cm[m] * falling<T>(m, d));
+                    if (exact)
+                        acc = deboor_exact<KIND, T>(kv, K, d, (const T *)outs.dcoefs[o], ncoef, xs,
+                                                    (KIND == 0 && E == BSK_EXTRAP_SMOOTH && outside) ? xq : xs);
                     if (KIND == 0 && outside) {
+                        const int side = xq > xa ? 1 : 0;
                         if (E == 0) acc = (T)0;                 // Splines/spline.jl:164-168
-                        else if (E == BSK_EXTRAP_LINEAR) {
-                            T cml[K];                       // separate copy: cm[] itself stays in registers
-#pragma unroll
-                            for (int m = 0; m < K; ++m) cml[m] = cm[m];
-                            acc += extrap_linear_term<K, T>(cml, u, d, xq - xs);
-                        }
+                        else if (E == BSK_EXTRAP_FLAT) acc = (T)outs.bval[o][side];
+                        else if (E == BSK_EXTRAP_LINEAR)        // S(a) + S'(a) (x - a), SplineExtrapolations.jl:40-52
+                            acc = xadd((T)outs.bval[o][side], xmul((T)outs.bslope[o][side], xsub(xq, xs)));
                     }
                     if (isnan_) acc = xq;
                     res[o][q] = acc;
@@ -272,53 +274,6 @@ template <typename F>
 cudaError_t set_smem(F func, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
     return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-
-// Derivative coefficients, _derivative (Splines/spline.jl:293-330; periodic: Splines/periodic.jl:76-117)
-// computed in T (the reference differentiates in the coefficient type).  t = stored knots
-// (plain: full vector; periodic: breakpoints incl. endpoint).  Output: plain ncoef - nd, periodic ncoef.
-template <typename T>
-void derivative_coefs(int kind, int k, const std::vector<double> &tk, const std::vector<double> &c,
-                      int nd, std::vector<double> &out) {
-    const int64_t n = (int64_t)c.size();
-    std::vector<T> du(n);
-    if (kind == 0) {
-        for (int64_t i = 0; i < n; ++i) du[i] = (T)c[i];
-        for (int m = 1; m <= nd; ++m)
-            for (int64_t i = n; i >= 1; --i) {
-                T dt = (T)tk[i + k - m - 1] - (T)tk[i - 1];
-                if (dt == (T)0 || i == 1) du[i - 1] = (T)0;
-                else du[i - 1] = (T)(k - m) * (du[i - 1] - du[i - 2]) / dt;
-            }
-        out.resize(n - nd);
-        for (int64_t i = 0; i < n - nd; ++i) out[i] = (double)du[i + nd];
-    } else {
-        // knots(B') : same breakpoints, order k - nd (BSplines/periodic.jl:255-260)
-        std::vector<T> tt(tk.size());
-        for (size_t i = 0; i < tk.size(); ++i) tt[i] = (T)tk[i];
-        KnotView<T> kd;
-        kd.t = tt.data(); kd.nt = (int)tt.size(); kd.N = (int)tt.size() - 1; kd.k = k - nd; kd.kind = 1;
-        kd.ilast = 0; kd.a = tt.front(); kd.b = tt.back(); kd.period = tt.back() - tt.front();
-        kd.lut = nullptr; kd.ncell = 0; kd.lut_scale = 0;
-        const int64_t N = n;
-        const int delta = k / 2 - (k - nd) / 2;
-        for (int64_t i = 1; i <= N; ++i) {
-            int64_t j = i - delta;
-            while (j < 1) j += N;
-            while (j > N) j -= N;
-            du[j - 1] = (T)c[i - 1];
-        }
-        for (int m = 1; m <= nd; ++m) {
-            T du0 = du[N - 1];
-            for (int64_t i = N; i >= 1; --i) {
-                T dt = knot_at<1>(kd, kd.t, (int)(i + k - m)) - knot_at<1>(kd, kd.t, (int)i);
-                T prev = (i == 1) ? du0 : du[i - 2];
-                du[i - 1] = (T)(k - m) * (du[i - 1] - prev) / dt;
-            }
-        }
-        out.resize(N);
-        for (int64_t i = 0; i < N; ++i) out[i] = (double)du[i];
-    }
 }
 
 bsk_status clone_basis(const bsk_basis *b, int kind, int k, const std::vector<double> &knots,
@@ -394,315 +349,94 @@ bsk_status set_host_coefs(bsk_spline *s, const bsk_basis *user_basis, const std:
 // ---- local-polynomial table ------------------------------------------------------------------
 bool pp_eligible(const bsk_spline *s) {
     const bsk_basis *b = s->basis;
-    if (b->kind == BSK_BASIS_PERIODIC) return b->N >= 1;
+    if (b->kind == BSK_BASIS_PERIODIC) return b->N >= 1 && b->N < (1ll << 24);
     // plain: need full multiplicity k at both ends so that [t1, tend] == [t_k, t_{N+1}]
     const auto &t = b->h_knots;
-    return t[0] == t[b->k - 1] && t[b->N] == t[b->nt - 1] && t[0] < t[b->nt - 1];
+    return t[0] == t[b->k - 1] && t[b->N] == t[b->nt - 1] && t[0] < t[b->nt - 1] && b->N < (1ll << 24);
 }
 
-// Taylor coefficients of one polynomial piece of the spline about an arbitrary point, from the
-// de Boor evaluation of the coefficient-differenced derivative splines (all in double).
-struct PieceTaylor {
-    const bsk_basis *b;
-    int k, kind;
-    std::vector<std::vector<double>> dc;     // dc[m] = coefficients of D^m S
-    explicit PieceTaylor(const bsk_spline *s) : b(s->basis), k(s->basis->k),
-                                                kind(s->basis->kind == BSK_BASIS_PERIODIC ? 1 : 0), dc(s->basis->k) {
-        dc[0] = s->h_coefs;
-        for (int m = 1; m < k; ++m) derivative_coefs<double>(kind, k, b->h_knots, s->h_coefs, m, dc[m]);
-    }
-    // piece = 1-based knot-interval index i (plain) or breakpoint index s (periodic)
-    void operator()(int piece, double xpt, double *c) const {
-        double fact = 1.0;
-        for (int m = 0; m < k; ++m) {
-            if (m > 0) fact *= (double)m;
-            KnotView<double> kd;
-            kd.kind = kind; kd.k = k - m; kd.lut = nullptr; kd.ncell = 0; kd.lut_scale = 0; kd.ilast = 0;
-            double val;
-            if (kind == 0) {
-                // knots of the D^m basis: t[1+m : end-m]; interval index i - m (basis.jl:104-111)
-                kd.t = b->h_knots.data() + m; kd.nt = (int)b->nt - 2 * m; kd.N = kd.nt - kd.k;
-                kd.a = kd.t[0]; kd.b = kd.t[kd.nt - 1]; kd.period = 0;
-                val = deboor_generic<0, double>(kd, kd.t, dc[m].data(), (int)dc[m].size(), 1, kd.k, piece - m, xpt);
-            } else {
-                kd.t = b->h_knots.data(); kd.nt = (int)b->nt; kd.N = (int)b->N;
-                kd.a = kd.t[0]; kd.b = kd.t[kd.nt - 1]; kd.period = kd.b - kd.a;
-                val = deboor_generic<1, double>(kd, kd.t, dc[m].data(), (int)dc[m].size(), 1, kd.k,
-                                                piece + kd.k / 2, xpt);
-            }
-            c[m] = val / fact;
-        }
-    }
-};
-
-// non-empty polynomial pieces of the spline: left ends, right ends, piece ids
-void list_pieces(const bsk_basis *b, std::vector<double> &lo, std::vector<double> &hi, std::vector<int> &id) {
-    const auto &t = b->h_knots;
-    if (b->kind != BSK_BASIS_PERIODIC) {
-        for (int64_t i = b->k; i <= b->N; ++i)
-            if (t[i - 1] < t[i]) { lo.push_back(t[i - 1]); hi.push_back(t[i]); id.push_back((int)i); }
-    } else {
-        for (int64_t sidx = 1; sidx <= b->N; ++sidx)
-            if (t[sidx - 1] < t[sidx]) { lo.push_back(t[sidx - 1]); hi.push_back(t[sidx]); id.push_back((int)sidx); }
-    }
-}
-
+// Upload the evaluation tables built on the host by pptable.h (per-interval records for K3b,
+// uniform-cell records for K3c) and the boundary constants of the Flat / Linear extrapolations.
 template <typename T>
 bsk_status build_pp(bsk_spline *s) {
     bsk_basis *b = s->basis;
-    const int k = b->k;
-    const int VPA = 16 / (int)sizeof(T);
-    const int REC = ((k + 2 + VPA - 1) / VPA) * VPA;
-    PieceTaylor taylor(s);
-    std::vector<double> plo, phi;
-    std::vector<int> pid;
-    list_pieces(b, plo, phi, pid);
-    const int64_t nrec = (int64_t)plo.size();
-    BSK_REQUIRE(nrec >= 1, BSK_ERR_ARGUMENT, "spline has no non-empty knot interval");
-    std::vector<T> recs((size_t)nrec * REC, (T)0);
-    std::vector<double> xi(nrec + 1);   // record left ends + right end of the domain
-    for (int64_t r = 0; r < nrec; ++r) {
-        T tlo = (T)plo[r], thi = (T)phi[r];
-        T midT = (T)0.5 * (tlo + thi);
-        double c[BSK_MAXK];
-        taylor(pid[r], (double)midT, c);
-        recs[r * REC] = tlo; recs[r * REC + 1] = thi;
-        for (int m = 0; m < k; ++m) recs[r * REC + 2 + m] = (T)c[m];
-        xi[r] = (double)tlo;
+    TableInput in;
+    in.kind = b->kind == BSK_BASIS_PERIODIC ? 1 : 0;
+    in.k = b->k;
+    in.N = b->N;
+    in.knots = &b->h_knots;
+    in.coefs = &s->h_coefs;
+    in.allow_global_cell = getenv("BSK_NO_GLOBAL_CELL") == nullptr;
+    const char *e = getenv("BSK_GLOBAL_CELL_MULT2");        // cells per interval, x2
+    in.global_cells_x2 = e ? atoi(e) : 64;
+    EvalTables<T> tb;
+    std::string err;
+    if (!build_eval_tables<T>(in, tb, &err)) {
+        set_error("%s", err.c_str());
+        return BSK_ERR_ARGUMENT;
     }
-    xi[nrec] = b->h_knots[b->nt - 1];
-    // LUT over the record left ends (same bracket construction as the knot LUT, bsk_api.cu)
-    std::vector<uint32_t> lut;
-    int ncell = 0;
-    double scale = 0;
-    {
-        const int n = (int)xi.size();
-        double range = xi[n - 1] - xi[0];
-        int nc = 64;
-        while (nc < 4 * n && nc < 65536) nc <<= 1;
-        double sc = (double)nc / range;
-        if (sizeof(T) == 4) sc = (double)(float)sc;
-        const double margin = sizeof(T) == 4 ? 0.05 : 1e-6;
-        lut.resize(nc);
-        for (int c = 0; c < nc; ++c) {
-            double e_lo = xi[0] + ((double)c - margin) / sc;
-            double e_hi = xi[0] + ((double)c + 1.0 + margin) / sc;
-            int lo = (int)(std::lower_bound(xi.begin(), xi.end(), e_lo) - xi.begin());
-            int hi = (int)(std::upper_bound(xi.begin(), xi.end(), e_hi) - xi.begin());
-            if (c == 0) lo = 0;
-            if (c == nc - 1) hi = n;
-            int w = hi - lo;
-            if (w > 254) w = 255;
-            lut[c] = (uint32_t)lo | ((uint32_t)w << 24);
-        }
-        ncell = nc;
-        scale = sc;
-    }
+    BSK_REQUIRE(tb.nrec < (1ll << 24), BSK_ERR_UNSUPPORTED, "too many knot intervals for the interval-table LUT");
     BSK_CUDA(cudaSetDevice(b->device));
-    if (s->d_pp) { bsk::dev_free(s->d_pp); s->d_pp = nullptr; }
-    if (s->d_pp_lut) { bsk::dev_free(s->d_pp_lut); s->d_pp_lut = nullptr; }
-    BSK_CUDA(bsk::dev_malloc(&s->d_pp, recs.size() * sizeof(T)));
-    BSK_CUDA(cudaMemcpy(s->d_pp, recs.data(), recs.size() * sizeof(T), cudaMemcpyHostToDevice));
-    BSK_CUDA(bsk::dev_malloc((void **)&s->d_pp_lut, lut.size() * 4));
-    BSK_CUDA(cudaMemcpy(s->d_pp_lut, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice));
-    s->pp_nrec = nrec;
-    s->pp_ncell = ncell;
-    s->pp_scale = scale;
-    s->pp_rec = REC;
-    s->pp_valid = true;
-
-    // ---- uniform-cell table (bsk_eval_cell.cu) -------------------------------------------------
+    for (void **p : {&s->d_pp, (void **)&s->d_pp_lut, &s->d_cell_rec, &s->d_cell_rc})
+        if (*p) { bsk::dev_free(*p); *p = nullptr; }
+    BSK_CUDA(bsk::dev_malloc(&s->d_pp, tb.recs.size() * sizeof(T)));
+    BSK_CUDA(cudaMemcpy(s->d_pp, tb.recs.data(), tb.recs.size() * sizeof(T), cudaMemcpyHostToDevice));
+    BSK_CUDA(bsk::dev_malloc((void **)&s->d_pp_lut, tb.lut.size() * 4));
+    BSK_CUDA(cudaMemcpy(s->d_pp_lut, tb.lut.data(), tb.lut.size() * 4, cudaMemcpyHostToDevice));
+    s->pp_nrec = tb.nrec;
+    s->pp_ncell = tb.lut_ncell;
+    s->pp_scale = tb.lut_scale;
+    s->pp_rec = tb.rec;
+    s->pp_uncertified = tb.n_uncertified;
     s->cell_valid = false;
-    {
-        const int RECV = ((k + VPA - 1) / VPA) * VPA;
-        const int NCH = RECV / VPA;
-        const int XI = (k == 1) ? 1 : 0;
-        const size_t budget = 214 * 1024;
-        const int nbp = (int)nrec - 1;                         // interior breakpoints
-        const double a = plo[0], bb = phi[nrec - 1];
-        // raw-bit helpers: flag = LSB of the last coefficient; flagged: last slot = (index << 1) | 1
-        auto setflag = [](T v, int f) {
-            if (sizeof(T) == 8) {
-                uint64_t u; double d = (double)v; memcpy(&u, &d, 8);
-                u = (u & ~1ull) | (uint64_t)f; memcpy(&d, &u, 8); return (T)d;
-            }
-            uint32_t u; float g = (float)v; memcpy(&u, &g, 4);
-            u = (u & ~1u) | (uint32_t)f; memcpy(&g, &u, 4); return (T)g;
-        };
-        auto index_bits = [](uint32_t idx) {
-            const uint32_t raw = (idx << 1) | 1u;
-            T out;
-            if (sizeof(T) == 8) { uint64_t u = raw; double d; memcpy(&d, &u, 8); out = (T)d; }
-            else { float g; memcpy(&g, &raw, 4); out = (T)g; }
-            return out;
-        };
-        const uint32_t kMulti = 0x7FFFFFFFu;
-        // "Jump" scheme (shared-memory tables, Float64, k >= 4; cell_jump_scheme in handles.cuh): a cell
-        // with one SIMPLE knot xi keeps the Taylor coefficients of the piece LEFT of the knot in its
-        // record, and the piece right of it is  P_L + J (x - xi)^(k-1)  (the spline is C^(k-2) at a
-        // simple knot: only the leading coefficient jumps).  The side entry is just {xi, J} (16 bytes
-        // instead of two full pieces), its index sits in bits 1..3 of the first four coefficients
-        // (<= 8 ulp of each), so a flagged lane needs ONE extra 16-byte gather instead of two and the
-        // smaller side table leaves room for ~40 % more cells (fewer flagged lanes).
-        const bool jump_ok = bsk::cell_jump_scheme((int)sizeof(T), k);
-        const uint32_t kJumpMulti = 4095u;
-        const size_t side_bytes = jump_ok ? 16 : (size_t)2 * RECV * sizeof(T);
-        // first guess: one side entry per interior breakpoint; shrink if it overflows
-        int64_t nc = (int64_t)((budget - std::min<size_t>(budget, (size_t)(nbp + 8) * side_bytes)) /
-                               (RECV * sizeof(T)));
-        nc = std::min<int64_t>(nc, 16 * nrec);
-        nc = std::min<int64_t>(nc, 60000);
-        // Too many intervals for shared memory: keep the same tables in global memory, record-major
-        // (one 32-byte L2 sector per cubic F64 / order-8 F32 record) and L2-resident.
-        const bool in_global = nc < 3 * nrec && nrec <= 400000 && getenv("BSK_NO_GLOBAL_CELL") == nullptr;
-        const bool jump = jump_ok && !in_global;
-        const bool jpad = jump && bsk::cell_jump_pad(k);      // odd order: flag + index in the spare slot
-        double dscale[BSK_MAXK];                               // magnitude of D^d S: max |coefficient|
-        for (int d = 0; d < k; ++d) {
-            dscale[d] = 0.0;
-            for (double v : taylor.dc[d]) dscale[d] = std::max(dscale[d], std::fabs(v));
-        }
-        auto put_index_bits = [](T *rec, uint32_t idx) {      // bits 1..3 of c_0 .. c_3
-            for (int m = 0; m < 4; ++m) {
-                uint64_t u; double d = (double)rec[m]; memcpy(&u, &d, 8);
-                u = (u & ~0xEull) | ((uint64_t)((idx >> (3 * m)) & 7u) << 1);
-                memcpy(&d, &u, 8); rec[m] = (T)d;
-            }
-        };
-        if (in_global) {
-            const char *e = getenv("BSK_GLOBAL_CELL_MULT2");        // cells per interval, x2
-            const int m2 = e ? std::max(6, atoi(e)) : 64;
-            nc = (nrec * m2) / 2;                                   // 32 cells per interval ...
-            const int64_t cap = (32ll << 20) / (int64_t)(bsk::cell_global_stride((int)sizeof(T), RECV) * sizeof(T));   // ... within 32 MB (L2-resident)
-            nc = std::max<int64_t>(std::min(nc, cap), 3 * nrec);
-        }
-        for (int attempt = 0; attempt < 6 && nc >= 3 * nrec && nc >= 8; ++attempt, nc = nc * 9 / 10) {
-            const T x0 = (T)a;
-            const T cwT = (T)((bb - a) / (double)nc);
-            const T scT = (T)((double)nc / (bb - a));
-            const double cw = (double)cwT;
-            const double margin = (sizeof(T) == 4 ? 0.02 : 1e-6) * cw;
-            std::vector<T> crec((size_t)nc * RECV, (T)0), side_l, side_r;     // cell-major while building
-            int nmulti = 0;
-            for (int64_t c = 0; c < nc; ++c) {
-                const double e0 = a + (double)c * cw, e1 = a + (double)(c + 1) * cw;
-                const T centerT = std::fma((T)c + (T)0.5, cwT, x0);     // exactly the device's formula
-                // piece at the left edge: number of interior breakpoints strictly below e0 - margin
-                int pl = (int)(std::lower_bound(plo.begin() + 1, plo.end(), e0 - margin) - (plo.begin() + 1));
-                int nb = 0;
-                while (pl + 1 + nb < (int)nrec && plo[pl + 1 + nb] <= e1 + margin) ++nb;
-                if (c == nc - 1) nb = (int)nrec - 1 - pl;        // everything up to the right end
-                double cf[BSK_MAXK];
-                taylor(pid[pl], (double)centerT, cf);
-                if (nb == 0) {
-                    for (int m = 0; m < k; ++m) crec[c * RECV + m] = (T)cf[m];
-                    if (!jpad) crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 0);
-                } else if (nb == 1 && jump) {
-                    // simple knot <=> the two pieces are consecutive knot intervals; the first and the
-                    // last cell are kept unflagged-or-multi (boundary pieces feed the extrapolations)
-                    const bool simple = pid[pl + 1] == pid[pl] + 1 && c != 0 && c != nc - 1;
-                    const uint32_t j = (uint32_t)(side_l.size() / 2);
-                    for (int m = 0; m < k; ++m) crec[c * RECV + m] = (T)cf[m];
-                    double cr[BSK_MAXK];
-                    bool accurate = simple;
-                    if (simple) {
-                        // Right of the knot the kernel forms P_L + J dx^(k-1) with P_L continued beyond its
-                        // own interval.  With very uneven neighbouring intervals the two terms can be much
-                        // larger than the spline and cancel: accept the cell only if the sum of the absolute
-                        // terms stays within 16x the magnitude of D^d S for every derivative order (rounding
-                        // error <= ~4e-15 of the output scale); otherwise the cell takes the interval table.
-                        taylor(pid[pl + 1], (double)centerT, cr);
-                        const double jmp = cr[k - 1] - cf[k - 1];
-                        const double h = e1 - (double)centerT, dxm = e1 - plo[pl + 1];
-                        for (int d = 0; d < k && accurate; ++d) {
-                            double sum = 0.0, hp = 1.0;
-                            for (int m = d; m < k; ++m) {
-                                double ff = 1.0;
-                                for (int q = 0; q < d; ++q) ff *= (double)(m - q);
-                                sum += std::fabs(cf[m]) * ff * hp;
-                                hp *= std::fabs(h);
-                            }
-                            double ffj = 1.0;
-                            for (int q = 0; q < d; ++q) ffj *= (double)(k - 1 - q);
-                            sum += std::fabs(jmp) * ffj * std::pow(std::fabs(dxm), k - 1 - d);
-                            if (!(sum <= 16.0 * dscale[d] + 1e-300)) accurate = false;
-                        }
-                    }
-                    if (accurate && (jpad || j < kJumpMulti)) {
-                        side_l.push_back((T)plo[pl + 1]);
-                        side_l.push_back((T)(cr[k - 1] - cf[k - 1]));
-                        if (jpad) crec[c * RECV + RECV - 1] = index_bits(j);
-                        else put_index_bits(&crec[c * RECV], j);
-                    } else {
-                        if (jpad) crec[c * RECV + RECV - 1] = index_bits(kMulti);
-                        else put_index_bits(&crec[c * RECV], kJumpMulti);
-                        ++nmulti;
-                    }
-                    if (!jpad) crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 1);
-                } else if (nb >= 2 && jump) {
-                    if (jpad) crec[c * RECV + RECV - 1] = index_bits(kMulti);
-                    else {
-                        put_index_bits(&crec[c * RECV], kJumpMulti);
-                        crec[c * RECV + k - 1] = setflag(crec[c * RECV + k - 1], 1);
-                    }
-                    ++nmulti;
-                } else if (nb == 1) {
-                    const uint32_t j = (uint32_t)(side_l.size() / RECV);
-                    crec[c * RECV + XI] = (T)plo[pl + 1];
-                    crec[c * RECV + k - 1] = index_bits(j);
-                    size_t base = side_l.size();
-                    side_l.resize(base + RECV, (T)0);
-                    side_r.resize(base + RECV, (T)0);
-                    for (int m = 0; m < k; ++m) side_l[base + m] = (T)cf[m];
-                    taylor(pid[pl + 1], (double)centerT, cf);
-                    for (int m = 0; m < k; ++m) side_r[base + m] = (T)cf[m];
-                } else {
-                    crec[c * RECV + k - 1] = index_bits(kMulti);
-                    ++nmulti;
-                }
-            }
-            if (jump && side_l.empty()) side_l.resize(2, (T)0);
-            if (side_l.empty()) { side_l.resize(RECV, (T)0); side_r.resize(RECV, (T)0); }
-            const int nside = jump ? (int)(side_l.size() / 2) : (int)(side_l.size() / RECV);
-            const size_t smem = jump ? ((size_t)nc * RECV + 2 * (size_t)nside) * sizeof(T) + 16
-                                     : ((size_t)nc + 2 * (size_t)nside) * RECV * sizeof(T) + 16;
-            if (!in_global && smem > 226 * 1024) continue;      // retry with fewer cells
-            if (nmulti * 50 > nc) break;                        // clustered knots: not worth it
-            // device layout: chunk-major for shared memory, record-major for global (CellView)
-            const int RS = in_global ? bsk::cell_global_stride((int)sizeof(T), RECV) : RECV;   // record stride on the device
-            std::vector<T> crec_cm((size_t)nc * RS, (T)0), rc_cm(jump ? side_l.size() : 2 * (size_t)nside * RS, (T)0);
-            if (jump) rc_cm = side_l;                           // {knot, jump} pairs, 16 bytes each
-            for (int64_t c = 0; c < nc; ++c)
-                for (int w = 0; w < NCH; ++w)
-                    for (int e = 0; e < VPA; ++e)
-                        crec_cm[in_global ? (size_t)c * RS + w * VPA + e : ((size_t)w * nc + c) * VPA + e] =
-                            crec[c * RECV + w * VPA + e];
-            for (int side = 0; side < 2 && !jump; ++side) {
-                const std::vector<T> &src = side ? side_r : side_l;
-                for (int64_t j = 0; j < nside; ++j)
-                    for (int w = 0; w < NCH; ++w)
-                        for (int e = 0; e < VPA; ++e)
-                            rc_cm[in_global ? ((size_t)side * nside + j) * RS + w * VPA + e
-                                            : (((size_t)side * NCH + w) * nside + j) * VPA + e] = src[j * RECV + w * VPA + e];
-            }
-            for (void **p : {&s->d_cell_rec, &s->d_cell_rc})
-                if (*p) { bsk::dev_free(*p); *p = nullptr; }
-            BSK_CUDA(bsk::dev_malloc(&s->d_cell_rec, crec_cm.size() * sizeof(T)));
-            BSK_CUDA(cudaMemcpy(s->d_cell_rec, crec_cm.data(), crec_cm.size() * sizeof(T), cudaMemcpyHostToDevice));
-            BSK_CUDA(bsk::dev_malloc(&s->d_cell_rc, rc_cm.size() * sizeof(T)));
-            BSK_CUDA(cudaMemcpy(s->d_cell_rc, rc_cm.data(), rc_cm.size() * sizeof(T), cudaMemcpyHostToDevice));
-            s->cell_ncell = (int)nc;
-            s->cell_nside = nside;
-            s->cell_x0 = (double)x0;
-            s->cell_b = (double)(T)bb;
-            s->cell_scale = (double)scT;
-            s->cell_cw = (double)cwT;
-            s->cell_smem = in_global ? 0 : smem;
-            s->cell_valid = true;
-            break;
+    if (tb.cell_valid) {
+        BSK_CUDA(bsk::dev_malloc(&s->d_cell_rec, tb.cell_rec.size() * sizeof(T)));
+        BSK_CUDA(cudaMemcpy(s->d_cell_rec, tb.cell_rec.data(), tb.cell_rec.size() * sizeof(T), cudaMemcpyHostToDevice));
+        BSK_CUDA(bsk::dev_malloc(&s->d_cell_rc, tb.cell_rc.size() * sizeof(T)));
+        BSK_CUDA(cudaMemcpy(s->d_cell_rc, tb.cell_rc.data(), tb.cell_rc.size() * sizeof(T), cudaMemcpyHostToDevice));
+        s->cell_ncell = tb.ncell;
+        s->cell_nside = tb.nside;
+        s->cell_x0 = tb.x0;
+        s->cell_b = tb.b;
+        s->cell_scale = tb.scale;
+        s->cell_cw = tb.cw;
+        s->cell_smem = tb.smem;
+        s->cell_slow = tb.n_cell_slow;
+        s->cell_valid = true;
+    }
+    s->pp_valid = true;
+    return BSK_OK;
+}
+
+// D^d S and D^(d+1) S at the two boundaries of a plain basis, by the reference's own recurrences in T
+// (coefficient differencing spline.jl:293-330, then de Boor spline.jl:174-209): the constants of the
+// Flat / Linear extrapolations (SplineExtrapolations.jl:29-52).
+template <typename T>
+void boundary_constants(const bsk_spline *s, int d, double *val, double *slope) {
+    const bsk_basis *b = s->basis;
+    const int k = b->k;
+    for (int w = 0; w < 2; ++w) {           // w = 0: D^d S, w = 1: its slope D^(d+1) S
+        const int dd_ = d + w;
+        double *dst = w ? slope : val;
+        dst[0] = dst[1] = 0.0;
+        if (dd_ > k - 1) continue;
+        std::vector<double> dc;
+        if (dd_ == 0) dc = s->h_coefs;
+        else derivative_coefs<T>(0, k, b->h_knots, s->h_coefs, dd_, dc);
+        std::vector<T> tt(b->h_knots.begin() + dd_, b->h_knots.end() - dd_), cc(dc.begin(), dc.end());
+        KnotView<T> kd;
+        kd.t = tt.data(); kd.nt = (int)tt.size(); kd.k = k - dd_; kd.N = kd.nt - kd.k; kd.kind = 0;
+        kd.a = tt.front(); kd.b = tt.back(); kd.period = 0; kd.lut = nullptr; kd.ncell = 0; kd.lut_scale = 0;
+        int il = kd.nt;
+        do { il -= 1; } while (il > 1 && tt[il - 1] == tt.back());
+        kd.ilast = il;
+        for (int side = 0; side < 2; ++side) {
+            const T x = side ? kd.b : kd.a;
+            int z;
+            const int i = find_interval<0>(kd, kd.t, x, z);
+            dst[side] = (double)deboor_generic<0, T>(kd, kd.t, cc.data(), (int)cc.size(), 1, kd.k, i, x);
         }
     }
-    return BSK_OK;
 }
 
 bsk_status get_derivative(const bsk_spline *s_const, int nd, bsk_spline **out) {
@@ -803,6 +537,31 @@ bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout,
         }
     }
     bool try_pp = (algo == BSK_EVAL_AUTO || algo == BSK_EVAL_PP) && pp_eligible(s);
+    // Periodic splines, derivative outputs on the table paths: the reference defines Derivative(d) * S by
+    // differencing the coefficients with the knot differences of the MAIN period (Splines/periodic.jl:76-117);
+    // next to the period boundary, where the evaluation uses knots shifted by +-L (rounded), that is not the
+    // analytic derivative of the value spline to the last bits (1e-12 relative at 10^4 knots).  To stay
+    // faithful, each derivative output is evaluated from the tables of its own derivative spline.
+    if (try_pp && b->kind == BSK_BASIS_PERIODIC) {
+        bool any = false;
+        for (int o = 0; o < nout; ++o) any = any || derivs[o] > 0;
+        if (any) {
+            const int32_t zero = 0;
+            for (int o = 0; o < nout; ++o) {
+                const bsk_spline *ds = s;
+                if (derivs[o] > 0) {
+                    std::unique_lock<std::mutex> lock(const_cast<bsk_spline *>(s)->mu);
+                    bsk_spline *tmp = nullptr;
+                    bsk_status rc = get_derivative(s, derivs[o], &tmp);
+                    if (rc != BSK_OK) return rc;
+                    ds = tmp;
+                }
+                bsk_status rc = spline_eval_t<T>(ds, d_x, n, 1, &zero, &d_outs[o], algo, extrap, st);
+                if (rc != BSK_OK) return rc;
+            }
+            return BSK_OK;
+        }
+    }
     if (algo == BSK_EVAL_PP && !try_pp) {
         set_error("local-polynomial path needs full end-knot multiplicity");
         return BSK_ERR_UNSUPPORTED;
@@ -825,17 +584,23 @@ bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout,
             outs.out[o] = d_outs[o];
             outs.deriv[o] = derivs[o];
             outs.dcoefs[o] = s->d_coefs;
-            if (b->kind == BSK_BASIS_PERIODIC && derivs[o] > 0) {
+            // de Boor routes inside the kernels (periodic points outside the main period, interval
+            // records that are not certified) evaluate Derivative(d) * S from its own coefficients
+            if ((b->kind == BSK_BASIS_PERIODIC || s->pp_uncertified > 0) && derivs[o] > 0) {
                 bsk_spline *ds = nullptr;
                 rc = get_derivative(s, derivs[o], &ds);
                 if (rc != BSK_OK) return rc;
                 outs.dcoefs[o] = ds->d_coefs;
             }
+            if (b->kind != BSK_BASIS_PERIODIC && (extrap == BSK_EXTRAP_FLAT || extrap == BSK_EXTRAP_LINEAR))
+                boundary_constants<T>(s, derivs[o], outs.bval[o], outs.bslope[o]);
         }
         // 1) uniform-cell table in shared memory (bsk_eval_cell.cu): needs every pointer to share
         //    the same 16-byte phase; the unaligned head / tail go through the scalar pp kernel.
         constexpr int VEC = 16 / (int)sizeof(T);
-        const bool want_cell = s->cell_valid && getenv("BSK_NO_CELL") == nullptr;
+        // (splines with interval records that are not certified take the interval-table kernel, which
+        //  carries the de Boor route for those records)
+        const bool want_cell = s->cell_valid && s->pp_uncertified == 0 && getenv("BSK_NO_CELL") == nullptr;
         if (want_cell) {
             const uintptr_t phase = ((uintptr_t)d_x) & 15;
             bool same = (phase % sizeof(T)) == 0;
@@ -994,7 +759,7 @@ bsk_status bsk_spline_create(const bsk_basis *b, const void *h_coefs, int64_t nc
                 (long long)ncoef, (long long)b->len);
     bsk_spline *s = new bsk_spline();
     s->basis = nullptr; s->d_coefs = nullptr; s->owns_coefs = true; s->d_pp = nullptr;
-    s->d_pp_lut = nullptr; s->pp_valid = false; s->pp_nrec = 0; s->pp_ncell = 0; s->pp_scale = 0; s->pp_rec = 0;
+    s->d_pp_lut = nullptr; s->pp_valid = false; s->pp_nrec = 0; s->pp_ncell = 0; s->pp_scale = 0; s->pp_rec = 0; s->pp_uncertified = 0; s->cell_slow = 0;
     s->d_cell_rec = s->d_cell_rc = nullptr; s->cell_valid = false;
     int ekind = b->kind == BSK_BASIS_PERIODIC ? BSK_BASIS_PERIODIC : BSK_BASIS_PLAIN;
     bsk_status rc = clone_basis(b, ekind, b->k, b->h_knots, &s->basis);
@@ -1091,7 +856,7 @@ bsk_status bsk_spline_derivative(const bsk_spline *s, int32_t nd, bsk_spline **o
     else tk = b->h_knots;
     bsk_spline *d = new bsk_spline();
     d->basis = nullptr; d->d_coefs = nullptr; d->owns_coefs = true; d->d_pp = nullptr;
-    d->d_pp_lut = nullptr; d->pp_valid = false; d->pp_nrec = 0; d->pp_ncell = 0; d->pp_scale = 0; d->pp_rec = 0;
+    d->d_pp_lut = nullptr; d->pp_valid = false; d->pp_nrec = 0; d->pp_ncell = 0; d->pp_scale = 0; d->pp_rec = 0; d->pp_uncertified = 0; d->cell_slow = 0;
     d->d_cell_rec = d->d_cell_rc = nullptr; d->cell_valid = false;
     bsk_status rc = clone_basis(b, kind ? BSK_BASIS_PERIODIC : BSK_BASIS_PLAIN, b->k - nd, tk, &d->basis);
     if (rc != BSK_OK) { delete d; return rc; }
@@ -1103,6 +868,31 @@ bsk_status bsk_spline_derivative(const bsk_spline *s, int32_t nd, bsk_spline **o
     rc = upload_coefs(d);
     if (rc != BSK_OK) { bsk_spline_destroy(d); return rc; }
     *out = d;
+    return BSK_OK;
+}
+
+bsk_status bsk_spline_table_info(const bsk_spline *s, int64_t *info, double *geom) {
+    BSK_REQUIRE(s && info, BSK_ERR_ARGUMENT, "NULL argument");
+    for (int i = 0; i < 8; ++i) info[i] = 0;
+    if (geom) geom[0] = geom[1] = geom[2] = geom[3] = 0.0;
+    if (!pp_eligible(s)) return BSK_OK;             // AUTO evaluates this spline with the de Boor kernel
+    bsk_spline *sm = const_cast<bsk_spline *>(s);
+    std::unique_lock<std::mutex> lock(sm->mu);
+    if (!s->pp_valid) {
+        bsk_status rc = s->basis->dtype == BSK_F64 ? build_pp<double>(sm) : build_pp<float>(sm);
+        if (rc != BSK_OK) return rc;
+    }
+    info[0] = s->pp_nrec;
+    info[1] = s->pp_uncertified;
+    if (s->cell_valid) {
+        info[2] = s->cell_ncell;
+        info[3] = s->cell_nside;
+        info[4] = s->cell_slow;
+        info[5] = s->cell_smem == 0;
+        info[6] = (int64_t)s->cell_smem;
+        info[7] = s->pp_uncertified == 0;
+        if (geom) { geom[0] = s->cell_x0; geom[1] = s->cell_b; geom[2] = s->cell_cw; geom[3] = s->cell_scale; }
+    }
     return BSK_OK;
 }
 

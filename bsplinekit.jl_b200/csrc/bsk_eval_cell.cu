@@ -135,7 +135,10 @@ template <int DMASK> struct MaskCount {
                                  ((DMASK >> 4) & 1) + ((DMASK >> 5) & 1) + ((DMASK >> 6) & 1) + ((DMASK >> 7) & 1);
 };
 
-// Rare path, kept out of line: per-interval table in global memory (pp.cuh).
+// Rare path, kept out of line: per-interval table in global memory (pp.cuh).  This kernel is only
+// launched for splines all of whose interval records are certified (bsk_eval.cu: splines with
+// uncertified records go through k_spline_pp, which carries the de Boor route), so the record's flag
+// is not looked at here.
 template <int K, typename T>
 __device__ __noinline__ void fallback_interval(const PPView<T> pv, T xs, T *cm, T *u) {
     pp_lookup<K, T>(pv, xs, cm, u);
@@ -290,6 +293,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
 #pragma unroll
             for (int m = 0; m < K; ++m) cm[m] = rec_[q][m];
             T u = xs - fma((T)c_[q] + (T)0.5, cw, x0);
+            const bool smooth_out = KIND == 0 && E == BSK_EXTRAP_SMOOTH && outside;
             if (multi_[q]) {
                 T cm2[K], u2;              // separate locals: keep cm[] itself in registers
                 fallback_interval<K, T>(pv, xs, cm2, &u2);
@@ -297,7 +301,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
                 for (int m = 0; m < K; ++m) cm[m] = cm2[m];
                 u = u2;
             }
-            if (KIND == 0 && E == BSK_EXTRAP_SMOOTH && outside) u += xq - xs;   // boundary piece continued
+            if (smooth_out) u += xq - xs;                     // boundary piece continued
             T r1[NOUT];
             horner_outputs<K, T, DMASK>(cm, u, outs, r1);
             if (JUMP) {
@@ -316,13 +320,11 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
             for (int o = 0; o < NOUT; ++o) {
                 T val = r1[o];
                 if (KIND == 0 && outside) {
+                    const int side = xq > xa ? 1 : 0;
                     if (E == 0) val = (T)0;                 // Splines/spline.jl:164-168
-                    else if (E == BSK_EXTRAP_LINEAR && (DMASK != 0 || o < outs.nout)) {
-                        T cml[K];                           // separate copy: cm[] itself stays in registers
-#pragma unroll
-                        for (int m = 0; m < K; ++m) cml[m] = cm[m];
-                        val += extrap_linear_term<K, T>(cml, u, outs.deriv[o], xq - xs);
-                    }
+                    else if (E == BSK_EXTRAP_FLAT) val = (T)outs.bval[o][side];
+                    else if (E == BSK_EXTRAP_LINEAR)        // S(a) + S'(a) (x - a), SplineExtrapolations.jl:40-52
+                        val = xadd((T)outs.bval[o][side], xmul((T)outs.bslope[o][side], xsub(xq, xs)));
                 }
                 if (isnan_) val = xq;
                 res[o][q] = val;

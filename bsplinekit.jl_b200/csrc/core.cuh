@@ -11,10 +11,36 @@
 #include <cstdint>
 #include <cmath>
 
+// Also included by plain C++ translation units (the host-side table builder is unit-tested on CPU).
+#ifndef __CUDACC__
+#ifndef __host__
+#define __host__
+#endif
+#ifndef __device__
+#define __device__
+#endif
+#ifndef __forceinline__
+#define __forceinline__ inline
+#endif
+#endif
+
 #define BSK_HD __host__ __device__ __forceinline__
 #define BSK_MAXK 8
 
 namespace bsk {
+
+// ---- layout of the uniform-cell tables (pptable.h builds them, bsk_eval_cell.cu reads them) ----
+// Tables staged in shared memory use the "jump" encoding of cells that contain a knot for Float64
+// splines of order >= 3.  Odd orders have a spare slot in the 16-byte-padded record, which carries the
+// flag and the side index; even orders (>= 4) carry them in low mantissa bits of the coefficients.
+__host__ __device__ constexpr bool cell_jump_scheme(int elt_bytes, int k) { return elt_bytes == 8 && k >= 3; }
+__host__ __device__ constexpr bool cell_jump_pad(int k) { return (k & 1) != 0; }     // RECV = k + 1 for doubles
+// Record stride (in elements) of a cell table that stays in global memory: records longer than one
+// 32-byte sector are padded to 64 bytes, so that a record is two whole sectors of one 128-byte line,
+// fetched by two 256-bit loads (bsk_eval_cell.cu).
+__host__ __device__ constexpr int cell_global_stride(int elt_bytes, int recv) {
+    return (recv * elt_bytes > 32 && (recv * elt_bytes) % 64 != 0) ? ((recv * elt_bytes + 63) / 64) * 64 / elt_bytes : recv;
+}
 
 // ---- non-contracting arithmetic ------------------------------------------------------
 BSK_HD double xadd(double a, double b) {
@@ -125,12 +151,26 @@ BSK_HD int search_last(const KT *v, int n, const uint32_t *lut, int ncell, KT sc
     return count_le(v, lo, hi, x);
 }
 
+// Periodic bases follow the reference's wrap loops (repeated +-L, one rounding per step) for points
+// and knot indices up to kFarPeriods periods away from the main one, so that results there are the
+// reference's bit for bit.  Farther out the reference itself needs that many sequential steps per
+// point; there the shift is formed by ONE multiplication (documented deviation, results then agree
+// with the reference to rounding only), and beyond 2^30 knot indices x is treated like +-Inf.
+#define BSK_FAR_PERIODS 4096
+
 // getindex(ts, i), i 1-based  (periodic: BSplines/periodic.jl:102-115)
 template <int KIND, typename KT>
 BSK_HD KT knot_at(const KnotView<KT> &kv, const KT *t, int i) {
     if (KIND == 0) return t[i - 1];
     KT x = 0;
     i -= kv.k / 2;
+    const long long far = (long long)BSK_FAR_PERIODS * kv.N;
+    if ((long long)i < 1 - far || (long long)i > (long long)kv.nt + far) {
+        int m = (i - 1) / kv.N;                       // floor division
+        if ((i - 1) % kv.N < 0) m -= 1;
+        x = xmul((KT)m, kv.period);
+        i -= m * kv.N;
+    }
     while (i < 1) { x = xsub(x, kv.period); i += kv.N; }
     while (i > kv.nt) { x = xadd(x, kv.period); i -= kv.N; }
     return xadd(x, t[i - 1]);
@@ -146,12 +186,13 @@ BSK_HD int find_interval(const KnotView<KT> &kv, const KT *t, KT x, int &zone) {
             return i + kv.N;
         }
         KT xw = x;
-        // The reference wraps by repeated +-L.  Beyond 64 periods we jump most of the
-        // way first (the remaining steps are still the reference's loop).
-        KT far = (KT)64 * kv.period;
+        // The reference wraps by repeated +-L (periodic.jl:88-97).  Beyond BSK_FAR_PERIODS periods we
+        // jump most of the way first (the remaining steps are still the reference's loop).
+        KT far = (KT)BSK_FAR_PERIODS * kv.period;
         if (xw < kv.a - far || xw > kv.b + far) {
             double m = floor(((double)xw - (double)kv.a) / (double)kv.period);
             double mm = m > 0 ? m - 1 : m + 1;
+            if (!(fabs(mm) * (double)kv.N < 1073741824.0)) return i + kv.N;      // index out of range: like Inf
             xw = (KT)((double)xw - mm * (double)kv.period);
             i += (int)mm * kv.N;
         }
@@ -297,9 +338,10 @@ BSK_HD int recombine_point(const RecombView &A, int ilast, const VT *bs, VT *phi
 // periodic coefficient wrap: PeriodicVector (Splines/periodic.jl:48-62)
 template <int KIND, typename T>
 BSK_HD T coef_at(const T *c, int ncoef, long long stride, int i) {
-    if (KIND == 1) {
-        while (i < 1) i += ncoef;
-        while (i > ncoef) i -= ncoef;
+    if (KIND == 1 && (i < 1 || i > ncoef)) {        // PeriodicVector: wrap into 1..N
+        i = (i - 1) % ncoef;
+        if (i < 0) i += ncoef;
+        i += 1;
     }
     return c[(long long)(i - 1) * stride];
 }

@@ -42,20 +42,6 @@ template <typename P> inline cudaError_t dev_malloc(P **p, size_t bytes) { retur
         }                                 \
     } while (0)
 
-// Uniform-cell tables staged in shared memory use the "jump" encoding of cells that contain a knot
-// (bsk_eval.cu: build, bsk_eval_cell.cu: kernel) for Float64 splines of order >= 3.  Odd orders have a
-// spare slot in the 16-byte-padded record, which carries the flag and the side index; even orders
-// (>= 4) carry them in low mantissa bits of the coefficients.
-__host__ __device__ constexpr bool cell_jump_scheme(int elt_bytes, int k) { return elt_bytes == 8 && k >= 3; }
-__host__ __device__ constexpr bool cell_jump_pad(int k) { return (k & 1) != 0; }     // RECV = k + 1 for doubles
-
-// Record stride (in elements) of a cell table that stays in global memory: records longer than one
-// 32-byte sector are padded to 64 bytes, so that a record is two whole sectors of one 128-byte line,
-// fetched by two 256-bit loads (bsk_eval_cell.cu).
-__host__ __device__ constexpr int cell_global_stride(int elt_bytes, int recv) {
-    return (recv * elt_bytes > 32 && (recv * elt_bytes) % 64 != 0) ? ((recv * elt_bytes + 63) / 64) * 64 / elt_bytes : recv;
-}
-
 inline int sm_count(int device) {
     static int cached[64] = {0};
     if (device < 0 || device >= 64) return 148;
@@ -107,12 +93,14 @@ struct bsk_spline {
     int pp_ncell;
     double pp_scale;
     int pp_rec;
+    int64_t pp_uncertified;   // interval records flagged for the de Boor route (pptable.h)
     bool pp_valid;
     // uniform-cell table (bsk_eval_cell.cu)
     void *d_cell_rec, *d_cell_rc;
     int cell_ncell, cell_nside;
     double cell_x0, cell_b, cell_scale, cell_cw;
     size_t cell_smem;
+    int64_t cell_slow;        // cells routed to the interval table
     bool cell_valid;
     std::vector<bsk_spline *> derivs;   // cached Derivative(n) * S, index n (0 unused)
     std::mutex mu;        // guards the lazily built tables / derivative cache (evaluation is otherwise read-only)

@@ -1,6 +1,9 @@
 // pp.cuh — per-knot-interval local-polynomial ("pp-form") table shared by the evaluation
-// kernels.  Record r (REC values of T, 16-byte aligned): { t_lo, t_hi, c_0 .. c_{K-1}, pad };
-// on [t_lo, t_hi):  S(x) = sum_m c_m u^m,  u = x - (t_lo + t_hi)/2.
+// kernels (built on the host by pptable.h).  Record r (REC values of T, 16-byte aligned):
+// { t_lo, mid, c_0 .. c_{K-1}, pad };  on [t_lo, t_hi):  S(x) = sum_m c_m u^m,  u = x - mid.
+// The least significant mantissa bit of `mid` is a flag: set = the Horner evaluation of this record
+// is NOT certified to the tolerance (pptable.h); such points are evaluated by the bit-faithful
+// de Boor recurrence (deboor_exact below).
 #pragma once
 #include "handles.cuh"
 
@@ -10,10 +13,13 @@ constexpr int kMaxOut = 4;
 
 struct EvalOuts {
     void *out[kMaxOut];
-    const void *dcoefs[kMaxOut];   // coefficients of Derivative(deriv) * S (periodic slow path)
+    const void *dcoefs[kMaxOut];   // coefficients of Derivative(deriv) * S (de Boor routes inside the kernels)
     int deriv[kMaxOut];
     int nout;
     int extrap;                    // BSK_EXTRAP_*: what to return outside the domain
+    // Flat / Linear extrapolation (plain bases): D^deriv S and its slope at the two boundaries, formed on
+    // the host by the reference's own recurrences (de Boor on the differenced coefficients)
+    double bval[kMaxOut][2], bslope[kMaxOut][2];
 };
 
 template <int K, typename T> struct PPRec {
@@ -50,21 +56,36 @@ __host__ __device__ __forceinline__ T falling(int m, int d) {
     return ff;
 }
 
-// Rare path of Linear extrapolation (SplineExtrapolations.jl:40-52): slope of D^d S at the boundary
-// from the boundary polynomial piece, times the distance to the boundary.
-template <int K, typename T>
-__device__ __noinline__ T extrap_linear_term(const T *cm, T u, int d, T dx) {
-    T acc = (T)0;
-#pragma unroll
-    for (int m = K - 1; m >= 0; --m)
-        if (m >= d + 1) acc = fma(acc, u, cm[m] * falling<T>(m, d + 1));
-    return acc * dx;
+template <typename T> __device__ __forceinline__ bool lsb_set(T v);
+template <> __device__ __forceinline__ bool lsb_set<double>(double v) { return (__double2loint(v) & 1) != 0; }
+template <> __device__ __forceinline__ bool lsb_set<float>(float v) { return (__float_as_int(v) & 1) != 0; }
+
+// Rare path: D^d S in the reference's own arithmetic (knot search + de Boor on the coefficients of
+// Derivative(d) * S; src/Splines/spline.jl:155-209, 293-330), for points whose interval record is not
+// certified.  `xs` selects the knot interval, `xq` is where the piece is evaluated (they differ only for
+// Smooth extrapolation).  kv = view of the spline's own basis (order K).
+template <int KIND, typename T>
+__device__ __noinline__ T deboor_exact(KnotView<T> kv, int K, int d, const T *dcoefs, int ncoef, T xs, T xq) {
+    kv.k = K - d;
+    kv.lut = nullptr;
+    kv.ncell = 0;
+    if (KIND == 0) {                 // knots of the derivative basis: t[1+d : end-d] (BSplines/basis.jl:104-111)
+        kv.t += d;
+        kv.nt -= 2 * d;
+        kv.N -= d;
+        kv.ilast -= d;
+        ncoef -= d;
+    }
+    int z;
+    const int i = find_interval<KIND>(kv, kv.t, xs, z);
+    return deboor_generic<KIND, T>(kv, kv.t, dcoefs, ncoef, 1, kv.k, i, xq);
 }
 
 // Locate the record of xs (which must lie inside the domain) and return its coefficients
-// and the local abscissa u.  `rec` / `lut` may point to shared or global memory.
+// and the local abscissa u; the return value is the record's "not certified" flag.
+// `rec` / `lut` may point to shared or global memory.
 template <int K, typename T>
-__device__ __forceinline__ void pp_lookup(const PPView<T> &pv, T xs, T *cm, T *u) {
+__device__ __forceinline__ bool pp_lookup(const PPView<T> &pv, T xs, T *cm, T *u) {
     constexpr int REC = PPRec<K, T>::REC;
     constexpr int VPA = 16 / (int)sizeof(T);
     const T *rec = pv.rec;
@@ -90,7 +111,8 @@ __device__ __forceinline__ void pp_lookup(const PPView<T> &pv, T xs, T *cm, T *u
     }
 #pragma unroll
     for (int m = 0; m < K; ++m) cm[m] = buf[2 + m];
-    *u = xs - (T)0.5 * (buf[0] + buf[1]);
+    *u = xs - buf[1];
+    return lsb_set<T>(buf[1]);
 }
 
 // implemented in bsk_eval_cell.cu (one translation unit per element type)

@@ -174,6 +174,17 @@ bsk_status bsk_spline_eval(const bsk_spline *s, const void *d_x, int64_t n, int3
 bsk_status bsk_spline_eval_extrap(const bsk_spline *s, const void *d_x, int64_t n, int32_t nout,
                                   const int32_t *derivs, void *const *d_outs, int32_t algo,
                                   int32_t extrap, void *stream);
+/* Diagnostics of the tables BSK_EVAL_AUTO / BSK_EVAL_PP use for this spline (built here if they are not yet).
+ * Every table coefficient is formed in double-double arithmetic and rounded once; each uniform cell and each
+ * knot-interval record is CERTIFIED on the host to evaluate D^d S, d = 0 .. k-1, within a quarter of the
+ * tolerance (1e-13 Float64 / 1e-5 Float32 of max |D^d S|); what cannot be certified is evaluated by the
+ * de Boor recurrence in the reference's operation order (Splines/spline.jl:174-209).
+ *   info[0] knot intervals          info[1] interval records routed to de Boor
+ *   info[2] uniform cells (0: none) info[3] cells holding one knot (side entries)
+ *   info[4] cells routed to the interval table             info[5] 1 = cell table stays in global memory
+ *   info[6] shared-memory bytes of the staged cell table   info[7] 1 = BSK_EVAL_AUTO launches the cell kernel
+ *   geom[0..3] (optional) = cell origin, domain end, cell width, 1 / cell width as the kernel uses them */
+bsk_status bsk_spline_table_info(const bsk_spline *s, int64_t *info, double *geom);
 /* Same through HOST buffers (H2D, kernel, D2H, synchronise). */
 bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n, int32_t nout,
                                 const int32_t *derivs, void *const *h_outs, int32_t algo);

@@ -15,6 +15,26 @@ def relerr(a, b):
     return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
 
 
+def per_element(got, ref, floor):
+    """Worst per-element relative error, |got - ref| / max(|ref|, floor): the norm-wise bar cannot see an error
+    next to a zero of S; this one can, down to |S| = floor ("per-element relative check wherever
+    abs(ref) is not tiny").  floor = 2^-5 of the coefficient (or output) magnitude."""
+    got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), floor)))
+
+
+def knot_cell_mask(S, x):
+    """Points whose uniform cell holds a knot: the records that carry a flag (and, for even orders, the side
+    index in bits 1..3 of four coefficients — csrc/bsk_eval_cell.cu)."""
+    ti = S.table_info()
+    assert ti["cells"] > 0
+    t = np.unique(S.knots())[1:-1]
+    has_knot = np.zeros(ti["cells"] + 1, dtype=bool)
+    has_knot[np.clip(np.floor((t - ti["x0"]) / ti["cell_width"]).astype(np.int64), 0, ti["cells"])] = True
+    pc = np.clip(np.floor((x - ti["x0"]) * ti["scale"]).astype(np.int64), 0, ti["cells"] - 1)
+    return has_knot[pc]
+
+
 @pytest.fixture(scope="module")
 def synth():
     from bsplinekit_b200 import synth as s
@@ -40,6 +60,16 @@ def test_c2_full_size_eval(bk, oracle, synth):
     refd = oracle.spline_eval(0, kd, td, cd, xs)
     assert relerr(v1[idx].cpu().numpy(), ref) < TOL64
     assert relerr(d1[idx].cpu().numpy(), refd) < TOL64
+    # per element, and separately for the points in knot cells (bit-encoded records)
+    ti = S1.table_info()
+    assert ti["auto_uses_cells"] == 1 and ti["intervals_deboor"] == 0 and ti["cells_interval_table"] <= 2
+    flagged = knot_cell_mask(S1, xs)
+    assert 0.1 < flagged.mean() < 0.3
+    f0, f1 = np.max(np.abs(c1)) / 32, np.max(np.abs(refd)) / 32
+    assert per_element(v1[idx].cpu().numpy(), ref, f0) < TOL64
+    assert per_element(d1[idx].cpu().numpy(), refd, f1) < TOL64
+    assert per_element(v1[idx].cpu().numpy()[flagged], ref[flagged], f0) < TOL64
+    assert per_element(d1[idx].cpu().numpy()[flagged], refd[flagged], f1) < TOL64
     # linearity over ALL points: S(0.5 c1 - 2 c2) == 0.5 S(c1) - 2 S(c2)
     v2, d2 = S2.evaluate(xd, (0, 1))
     v12, d12 = S12.evaluate(xd, (0, 1))
@@ -128,6 +158,17 @@ def test_c4_periodic_full(bk, oracle, synth):
     idx = torch.arange(0, 1 << 28, 8191, device="cuda")
     ref = oracle.spline_eval(1, 4, br, coefs, xd[idx].cpu().numpy())
     assert relerr(v[idx].cpu().numpy(), ref) < TOL64
+    assert per_element(v[idx].cpu().numpy(), ref, np.max(np.abs(coefs)) / 32) < TOL64
+    ti = S.table_info()
+    assert ti["cells_in_global"] == 1 and ti["intervals_deboor"] == 0
+    # derivative outputs of a periodic spline come from the tables of Derivative(1) * S itself
+    # (Splines/periodic.jl:76-117): same bar, incl. the points next to the period boundary
+    xb = np.concatenate([xd[idx].cpu().numpy()[:20000], 1e-5 * synth.u_numpy(9, 7, 4000), 1 - 1e-5 * synth.u_numpy(9, 8, 4000)])
+    kd, td, cd = oracle.spline_derivative(1, 4, br, coefs, 1)
+    refd = oracle.spline_eval(1, kd, td, cd, xb)
+    gotv, gotd = S.evaluate(torch.from_numpy(xb).cuda(), (0, 1))
+    assert relerr(gotd.cpu().numpy(), refd) < TOL64
+    assert relerr(gotv.cpu().numpy(), oracle.spline_eval(1, 4, br, coefs, xb)) < TOL64
     xw = -2.0 + 5.0 * synth.u_numpy(9, 1 << 41, 1 << 20)
     refw = oracle.spline_eval(1, 4, br, coefs, xw)
     assert relerr(S(xw), refw) < TOL64
@@ -174,6 +215,15 @@ def test_c5_recombined_robin_full(bk, oracle, synth):
     ref32 = oracle.spline_eval(0, k, Bf.knots(), cf, xs, kt="f32")
     assert np.array_equal(Sf.evaluate(xd[idx].contiguous(), (0,), algo=bk.EVAL_DEBOOR)[0].cpu().numpy(), ref32)
     assert v.abs().max().item() <= 1.0 + 1e-5
+    assert relerr(v[idx].cpu().numpy(), ref32) < TOL32
+    # the Float32 cell index slips against the cell edges by ~0.3 cell at the far end of a 10^6-cell table:
+    # points AT the knots and one ulp either side must still take searchsortedlast's piece, for the value and
+    # for a derivative (the jump of D^2 S at a knot would show a wrong piece at once)
+    xk = np.concatenate([brf, np.nextafter(brf, np.float32(-1)), np.nextafter(brf, np.float32(2))])
+    gv, g2 = Sf.evaluate(torch.from_numpy(xk).cuda(), (0, 2))
+    assert relerr(gv.cpu().numpy(), oracle.spline_eval(0, k, Bf.knots(), cf, xk, kt="f32")) < TOL32
+    k2, t2, c2 = oracle.spline_derivative(0, k, Bf.knots(), cf, 2, kt="f32")
+    assert relerr(g2.cpu().numpy(), oracle.spline_eval(0, k2, t2, c2, xk, kt="f32")) < TOL32
 
 
 def test_c3_shape_float32_solve(bk, oracle, synth):
@@ -215,8 +265,15 @@ def test_order6_full_size_eval(bk, oracle, synth):
     v, d = S.evaluate(xd, (0, 1))
     idx = torch.arange(0, n, 4099, device="cuda")
     xs = xd[idx].cpu().numpy()
-    assert relerr(v[idx].cpu().numpy(), oracle.spline_eval(0, k, B.knots(), c, xs)) < TOL64
+    ref = oracle.spline_eval(0, k, B.knots(), c, xs)
+    assert relerr(v[idx].cpu().numpy(), ref) < TOL64
     kd, td, cd = oracle.spline_derivative(0, k, B.knots(), c, 1)
-    assert relerr(d[idx].cpu().numpy(), oracle.spline_eval(0, kd, td, cd, xs)) < TOL64
+    refd = oracle.spline_eval(0, kd, td, cd, xs)
+    assert relerr(d[idx].cpu().numpy(), refd) < TOL64
+    flagged = knot_cell_mask(S, xs)
+    assert flagged.mean() > 0.15
+    assert per_element(v[idx].cpu().numpy(), ref, np.max(np.abs(c)) / 32) < TOL64
+    assert per_element(d[idx].cpu().numpy(), refd, np.max(np.abs(refd)) / 32) < TOL64
+    assert per_element(v[idx].cpu().numpy()[flagged], ref[flagged], np.max(np.abs(c)) / 32) < TOL64
     assert v.abs().max().item() <= np.abs(c).max() * (1 + 1e-14)
     assert torch.equal(S.evaluate(xd, (0,))[0], v)
