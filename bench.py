@@ -1,18 +1,25 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the spline-evaluation hot path (BASELINE.json configs[1]):
 k = 4 spline on 1,000 non-uniform breakpoints, value + first derivative at 2^28 random Float64
-points per GPU, one process per GPU.  One JSON line on stdout (rank 0).
+points, one process per GPU.  One JSON line on stdout (rank 0).
 
   python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the reference
 
-A "step" is one fused pass (S(x) and S'(x)) over the 2^28 device-resident points.  `value`
-is whole-job Gpoints/s with inputs resident in HBM; `e2e` is the same metric through the
-host-buffer C-ABI call (pinned host arrays, H2D and D2H inside the timed region).
-The batched-interpolation solve (configs[2]) is timed in the same run and reported under
-"extra" with its own roofline fraction.
+A "step" is one fused pass (S(x) and S'(x)) over the device-resident points.  `value` is whole-job
+Gpoints/s with inputs resident in HBM; `e2e` is the same metric through the host-buffer C-ABI call
+(pinned host arrays, H2D and D2H inside the timed region), with a copy-only probe of the same pipeline
+beside it.
+
+Scaling.  BASELINE.json names ONE problem — 2^28 points — "at 1/2/4/8 B200": with N > 1 ranks the
+default is therefore STRONG scaling, every rank evaluating its contiguous slice of 2^28 / N points
+(SURVEY.md §8e).  `--scaling weak` gives every rank its own 2^28 points instead.
+
+The batched-interpolation solve (configs[2]) is timed in the same run; its numbers are top-level
+scalars (`solve_*`), the other configs are under "extra".
 """
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -27,6 +34,17 @@ METRIC = "Gpoints/s spline eval (k=4, 2^28 pts, value + 1st derivative, Float64)
 UNIT = "Gpoints/s"
 BYTES_PER_POINT = 24.0          # 8 B read + 2 x 8 B written
 SOLVE_BYTES_PER_ELEM = 16.0     # read y + write c
+WORKLOAD = "C2: k=4 spline, 1000 non-uniform breakpoints, value + 1st derivative at 2^28 random Float64 points"
+
+
+def load_synth():
+    """The deterministic input generator, loaded BY PATH: importing the package would dlopen the CUDA
+    library, which the CPU reference arm must not touch."""
+    spec = importlib.util.spec_from_file_location(
+        "bsk_synth", os.path.join(ROOT, "bsplinekit.jl_b200", "bsplinekit_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def measured_peak():
@@ -36,6 +54,14 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profile_numbers():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -90,15 +116,6 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def workload_c2(bk, synth):
-    import numpy as np
-    k = 4
-    br = synth.breakpoints(3, 1000)
-    B = bk.BSplineBasis(k, br)
-    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
-    return k, B, c
-
-
 def omp_threads(nthreads):
     """Use all host cores for the CPU arm (torchrun exports OMP_NUM_THREADS=1); must run before
     the oracle library is first loaded.  Returns the thread count OpenMP will actually use."""
@@ -114,8 +131,7 @@ def omp_threads(nthreads):
 
 def bind_to_gpu_numa_node(index):
     """Run this rank on the CPUs next to its GPU (NVML's ideal affinity) so that its pinned host buffers
-    are allocated on the NUMA node of the GPU's PCIe root — matters for the host-buffer (e2e) leg when
-    several ranks stream over PCIe at once.  Best effort."""
+    are allocated on the NUMA node of the GPU's PCIe root.  Best effort; a no-op on single-node-NUMA boxes."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -136,12 +152,10 @@ def bind_to_gpu_numa_node(index):
 _CPU_POINTS = {}
 
 
-def cpu_reference_rate(npts_sample, nthreads):
+def cpu_reference_rate(synth, npts_sample, nthreads):
     """The reference algorithm on the host cores: de Boor value + derivative spline, OpenMP over
     points (oracle/bsk_oracle.c).  Returns (Gpoints/s, seconds)."""
-    import numpy as np
     from oracle import oracle as O
-    from bsplinekit_b200 import synth
     k = 4
     br = synth.breakpoints(3, 1000)
     t = O.augment_knots(br, k)
@@ -160,39 +174,52 @@ def cpu_reference_rate(npts_sample, nthreads):
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of BSplineKit's algorithm (oracle/, "port": the reference is a
+    Julia package and there is no Julia toolchain) on all host cores, rank 0 only, on the SAME workload as the
+    CUDA arm: all 2^28 points per step.  Nothing of the product is imported or loaded here."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    synth = load_synth()
     cores = omp_threads(os.cpu_count() or 1)
-    sample = 1 << 26
+    sample = args.points
     rates, times = [], []
-    for _ in range(args.warmup):
-        cpu_reference_rate(1 << 20, cores)
+    for _ in range(min(args.warmup, 2)):
+        cpu_reference_rate(synth, 1 << 22, cores)
+    cpu_reference_rate(synth, sample, cores)        # untimed: generates the points, touches the pages
     for _ in range(args.steps):
-        r, dt = cpu_reference_rate(sample, cores)
+        r, dt = cpu_reference_rate(synth, sample, cores)
         rates.append(r)
         times.append(dt)
     tot = sum(times)
     value = sample * len(times) / tot / 1e9
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": scaling_mode(args, world), "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "C2 cubic eval value+derivative, k=4, 1000 non-uniform breakpoints",
-                   "points_per_step": sample, "note": "bounded sample of the 2^28-point workload"},
+        "config": {"workload": WORKLOAD, "points_per_step": sample, "points_total": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "2^26 points per step, OpenMP over points, all host cores"},
+                         "sample": "all %d points per step, value + derivative, OpenMP over points, all host cores" % sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def scaling_mode(args, world):
+    if args.scaling != "auto":
+        return args.scaling
+    return "strong" if world > 1 else "weak"
+
+
 def run_ours(args):
+    import ctypes
     import numpy as np
     import torch
     import bsplinekit_b200 as bk
     from bsplinekit_b200 import synth
+    from bsplinekit_b200 import _lib as _bl
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,15 +245,41 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    npts = args.points
-    k, B, c = workload_c2(bk, synth)
+    def sp():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def timed(fn, reps, setup=None, warm=1):
+        tot = 0.0
+        for it in range(reps + warm):
+            if setup is not None:
+                setup()
+            torch.cuda.synchronize()
+            a = torch.cuda.Event(enable_timing=True)
+            b_ = torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b_.record()
+            torch.cuda.synchronize()
+            if it >= warm:
+                tot += a.elapsed_time(b_)
+        return max_over_ranks(tot / reps)
+
+    launches = [0]                      # kernels of ours launched inside the headline timed region
+    mode = scaling_mode(args, world)
+    total_pts = args.points if mode == "strong" else args.points * world
+    npts = (args.points // world) // 2 * 2 if mode == "strong" else args.points     # this rank's slice
+    first = rank * npts
+    peak, peak_src = measured_peak()
+    prof = profile_numbers()
+
+    k = 4
+    B = bk.BSplineBasis(k, synth.breakpoints(3, 1000))
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
     S = bk.Spline(B, c)
-    # each rank generates its own slice of the point stream on its device
-    xd = synth.u_torch(5, rank * npts, npts)
+    xd = synth.u_torch(5, first, npts)          # each rank generates its own slice on its device
     v = torch.empty_like(xd)
     dv = torch.empty_like(xd)
     outs = [v, dv]
     algo = {"auto": bk.EVAL_AUTO, "pp": bk.EVAL_PP, "deboor": bk.EVAL_DEBOOR}[args.algo]
+    launches_per_step = 1 if args.algo != "deboor" else 2
 
     for _ in range(args.warmup):
         S.evaluate(xd, (0, 1), algo=algo, out=outs)
@@ -238,6 +291,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         S.evaluate(xd, (0, 1), algo=algo, out=outs)
+        launches[0] += launches_per_step
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -245,53 +299,80 @@ def run_ours(args):
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
     value = world * npts / (ms_step * 1e-3) / 1e9
-    launches_per_step = 1 if args.algo != "deboor" else 2
-    peak, peak_src = measured_peak()
     achieved = BYTES_PER_POINT * npts / (ms_step * 1e-3) / 1e9      # per GPU, GB/s
     traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get("k_spline_cell_bytes_per_launch")
-            if t is not None and args.algo != "deboor":
-                traffic = t * (npts / float(1 << 28))      # captured on 2^28 points
-    except Exception:
-        pass
+    t_ = prof.get("k_spline_cell_bytes_per_launch")
+    if t_ is not None and args.algo != "deboor":
+        traffic = t_ * (npts / float(1 << 28))      # captured on 2^28 points
 
-    # the same access mix without the table lookups (n doubles in, 2 n out, same launch shape): what HBM
-    # gives a 1 : 2 read : write stream on this GPU, measured the same way beside the kernel
-    stream_mix = None
+    # ---- the same access mix without the table lookups (n doubles in, 2 n out): what HBM gives a 1 : 2
+    #      read : write stream on this GPU — with 128-bit LDG / STG, and moved by TMA bulk copies ------------
+    stream_mix = stream_tma = None
     try:
-        import ctypes
-        from bsplinekit_b200 import _lib as _bl
-        sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         w0 = torch.empty_like(v); w1 = torch.empty_like(dv)      # scratch: the results stay intact
-        probe = lambda: _bl.check(_bl.lib.bsk_probe_stream_1r2w(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(w0.data_ptr()),
-                                                                ctypes.c_void_p(w1.data_ptr()), npts, sp))
-        for _ in range(3):
-            probe()
-        p0 = torch.cuda.Event(enable_timing=True)
-        p1 = torch.cuda.Event(enable_timing=True)
-        p0.record()
-        for _ in range(10):
-            probe()
-        p1.record()
-        torch.cuda.synchronize()
-        stream_mix = BYTES_PER_POINT * npts / (p0.elapsed_time(p1) / 10 * 1e-3) / 1e9
+        nprobe = npts // 2048 * 2048
+        for name in ("bsk_probe_stream_1r2w", "bsk_probe_stream_1r2w_tma"):
+            fn = getattr(_bl.lib, name)
+            call = lambda: _bl.check(fn(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(w0.data_ptr()),
+                                        ctypes.c_void_p(w1.data_ptr()), nprobe, sp()))
+            ms = timed(lambda: [call() for _ in range(10)], 1, warm=1) / 10
+            gbs = BYTES_PER_POINT * nprobe / (ms * 1e-3) / 1e9
+            if name.endswith("tma"):
+                stream_tma = gbs
+                ok = bool(torch.equal(w0[:nprobe:4097], xd[:nprobe:4097] + 1.0) and torch.equal(w1[:nprobe:4097], xd[:nprobe:4097] * 0.5))
+                if not ok:
+                    stream_tma = None
+                    print("TMA stream probe produced wrong data", file=sys.stderr)
+            else:
+                stream_mix = gbs
         del w0, w1
-    except Exception as exc:                 # the probe is informative only
+    except Exception as exc:                 # the probes are informative only
         print("stream probe skipped: %r" % (exc,), file=sys.stderr)
 
-    # parity spot check on what was just computed (not timed)
+    # ---- FMA pipe peaks (denominators of the pipe fractions below) ---------------------------------------
+    pipes = {}
+    try:
+        scratch = torch.zeros(16, dtype=torch.float64, device="cuda")
+        for name, dt_ in (("fp64", 1), ("fp32", 0)):
+            cnt = ctypes.c_double(0)
+            iters = 1 << 14 if name == "fp64" else 1 << 15
+            call = lambda: _bl.check(_bl.lib.bsk_probe_fma(dt_, iters, ctypes.c_void_p(scratch.data_ptr()), ctypes.byref(cnt), sp()))
+            ms = timed(call, 3, warm=1)
+            pipes[name + "_fma_per_s"] = cnt.value / (ms * 1e-3)
+            pipes[name + "_tflops"] = 2 * cnt.value / (ms * 1e-3) / 1e12
+    except Exception as exc:
+        print("fma probe skipped: %r" % (exc,), file=sys.stderr)
+
+    def pipe_frac(kernel_key, pipe, n_points, ms):
+        """Fraction of the measured FMA-pipe peak: thread-level pipe instructions per point (from the ncu
+        capture recorded in profiles/traffic.json) x points / time / probe rate."""
+        per_pt = prof.get(kernel_key)
+        rate = pipes.get(pipe + "_fma_per_s")
+        if per_pt is None or not rate:
+            return None
+        return per_pt * n_points / (ms * 1e-3) / rate
+
+    # ---- parity spot check on what was just computed (not timed) ------------------------------------------
     chk = {}
     if rank == 0:
         from oracle import oracle as O
-        m = 1 << 16
+        m = min(npts, 1 << 18)
         xh = xd[:m].cpu().numpy()
         ref = O.spline_eval(0, k, B.knots(), c, xh)
         kd, td, cd = O.spline_derivative(0, k, B.knots(), c, 1)
         refd = O.spline_eval(0, kd, td, cd, xh)
-        chk = {"value_relerr": float(np.max(np.abs(v[:m].cpu().numpy() - ref)) / np.max(np.abs(ref))),
-               "deriv_relerr": float(np.max(np.abs(dv[:m].cpu().numpy() - refd)) / np.max(np.abs(refd)))}
+        gv, gd = v[:m].cpu().numpy(), dv[:m].cpu().numpy()
+        chk = {"value_relerr": float(np.max(np.abs(gv - ref)) / np.max(np.abs(ref))),
+               "deriv_relerr": float(np.max(np.abs(gd - refd)) / np.max(np.abs(refd))),
+               # per element: |got - ref| / max(|ref|, 2^-5 scale); scale = ||c||_inf resp. max |S'|
+               "value_per_element": float(np.max(np.abs(gv - ref) / np.maximum(np.abs(ref), np.max(np.abs(c)) / 32))),
+               "deriv_per_element": float(np.max(np.abs(gd - refd) / np.maximum(np.abs(refd), np.max(np.abs(refd)) / 32))),
+               "checked_points": int(m)}
+        try:
+            ti = S.table_info()
+            chk["table"] = {kk: ti[kk] for kk in ("cells", "knot_cells", "cells_interval_table", "intervals_deboor")}
+        except Exception:
+            pass
 
     # ---- e2e: host buffers through the C-ABI host call (H2D + kernel + D2H, pipelined) ----------
     e2e = None
@@ -301,10 +382,22 @@ def run_ours(args):
         xh.copy_(xd[:ne])
         oh = [torch.empty(ne, dtype=torch.float64, pin_memory=True) for _ in range(2)]
         xnp, onp = xh.numpy(), [o.numpy() for o in oh]
-        S.evaluate(xnp, (0, 1), algo=algo, out=onp)       # warm-up
+        ptrs = (ctypes.c_void_p * 2)(*[o.ctypes.data for o in onp])
+        ke = max(1, args.e2e_steps)
+        # copy-only twin first: same chunks, same streams, no kernel — what PCIe / host memory give
+        copy_call = lambda: _bl.check(_bl.lib.bsk_probe_copy_host(S._handle, ctypes.c_void_p(xnp.ctypes.data), ne, 2, ptrs))
+        for _ in range(2):
+            copy_call()
         barrier()
         t0 = time.perf_counter()
-        ke = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(ke):
+            copy_call()
+        torch.cuda.synchronize()
+        dt_copy = max_over_ranks(time.perf_counter() - t0) / ke
+        for _ in range(2):
+            S.evaluate(xnp, (0, 1), algo=algo, out=onp)       # warm-up
+        barrier()
+        t0 = time.perf_counter()
         for _ in range(ke):
             S.evaluate(xnp, (0, 1), algo=algo, out=onp)
         torch.cuda.synchronize()
@@ -312,15 +405,20 @@ def run_ours(args):
         assert np.array_equal(onp[0][:1024], v[:1024].cpu().numpy())
         e2e = {"value": world * ne / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8 * ne,
                "d2h_bytes_per_step": 16 * ne, "points_per_step": ne, "steps": ke,
-               "ms_per_step": 1e3 * dt}
+               "ms_per_step": 1e3 * dt, "copy_only_ms_per_step": 1e3 * dt_copy,
+               "copy_only_gbs_per_gpu": 24.0 * ne / dt_copy / 1e9,
+               "frac_of_copy_only": dt_copy / dt}
         del xh, oh
 
-    # ---- extra: batched interpolation solve, configs[2] -------------------------------------------
+    # ---- batched interpolation solve, configs[2]: top-level scalars ----------------------------------------
     extra = {}
+    solve = {}
     if not args.no_solve:
         del xd, v, dv
         torch.cuda.empty_cache()
-        n, kk, nrhs = 4096, 6, args.nrhs
+        n, kk = 4096, 6
+        nrhs_total = args.nrhs if mode == "strong" else args.nrhs * world
+        nrhs = (args.nrhs // world) // 32 * 32 if mode == "strong" else args.nrhs
         xdata = synth.breakpoints(6, n)
         Bi = bk.BSplineBasis(kk, bk.make_knots(xdata, kk), augment=False)
         t_f0 = time.perf_counter()
@@ -335,24 +433,12 @@ def run_ours(args):
         Y0 = (2 * synth.u_torch(7, rank * n * nrhs, n * nrhs) - 1).reshape(n, nrhs)
         Y = torch.empty_like(Y0)
         res = {}
+        keep = None
         for name, salgo in (("windowed", bk.SOLVE_WINDOWED), ("twopass", bk.SOLVE_TWOPASS)):
             if name == "windowed" and itp.C.halo == 0:
                 continue
-            tot = 0.0
-            for it in range(args.warmup + args.solve_steps):
-                Y.copy_(Y0)
-                barrier()
-                s0 = torch.cuda.Event(enable_timing=True)
-                s1 = torch.cuda.Event(enable_timing=True)
-                s0.record()
-                itp.C.ldiv_(Y, algo=salgo)
-                s1.record()
-                torch.cuda.synchronize()
-                if it >= args.warmup:
-                    tot += s0.elapsed_time(s1)
-            ms = max_over_ranks(tot / args.solve_steps)
+            ms = timed(lambda: itp.C.ldiv_(Y, algo=salgo), args.solve_steps, setup=lambda: Y.copy_(Y0), warm=args.warmup)
             res[name] = {"ms": ms, "rhs_per_s": world * nrhs / (ms * 1e-3),
-                         "achieved_gbs": SOLVE_BYTES_PER_ELEM * n * nrhs / (ms * 1e-3) / 1e9,
                          "frac": SOLVE_BYTES_PER_ELEM * n * nrhs / (ms * 1e-3) / 1e9 / peak}
             if rank == 0 and name == "windowed":
                 keep = Y[:, :256].cpu().numpy()
@@ -361,149 +447,168 @@ def run_ours(args):
             band, _ = O.collocation_matrix(0, kk, Bi.knots(), xdata)
             O.banded_lu(band)
             ref = O.banded_solve(band, Y0[:, :256].cpu().numpy().copy())
-            got = keep if "windowed" in res else Y[:, :256].cpu().numpy()
+            got = keep if keep is not None else Y[:, :256].cpu().numpy()
             chk["solve_relerr"] = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
-        best = min(res.values(), key=lambda r: r["ms"])
-        extra = {"c3_batched_solve": {"metric": "RHS/s (n=4096, k=6, %d RHS per GPU, Float64)" % nrhs,
-                                      "value": best["rhs_per_s"], "unit": "RHS/s",
-                                      "roofline_frac": best["frac"], "algos": res,
-                                      "factor_once_ms": factor_ms, "factor_first_call_ms": factor_first_ms,
-                                      "halo_rows": itp.C.halo}}
-        # du = F \ (L u), mul! + ldiv! of a collocation time step in one pass
-        Lm = bk.collocation_matrix(Bi, xdata, bk.Derivative(2))
-        tot = 0.0
-        for it in range(args.warmup + args.solve_steps):
-            barrier()
-            s0 = torch.cuda.Event(enable_timing=True)
-            s1 = torch.cuda.Event(enable_timing=True)
-            s0.record()
-            itp.C.ldiv_mul(Lm, Y0, out=Y)
-            s1.record()
-            torch.cuda.synchronize()
-            if it >= args.warmup:
-                tot += s0.elapsed_time(s1)
-        ms = max_over_ranks(tot / args.solve_steps)
-        if rank == 0:
-            yref = O.banded_matvec(O.collocation_matrix(0, kk, Bi.knots(), xdata, 2)[0], Y0[:, :256].cpu().numpy())
-            O.banded_solve(band, yref)
-            chk["fused_matvec_solve_relerr"] = float(np.max(np.abs(Y[:, :256].cpu().numpy() - yref)) / np.max(np.abs(yref)))
-        extra["n1_fused_matvec_solve"] = {"metric": "RHS/s, du = F \\ (D2 u) (n=4096, k=6, %d columns per GPU)" % nrhs,
-                                          "ms": ms, "value": world * nrhs / (ms * 1e-3), "unit": "RHS/s",
-                                          "roofline_frac": SOLVE_BYTES_PER_ELEM * n * nrhs / (ms * 1e-3) / 1e9 / peak}
-        del Lm
-        # all `nrhs` interpolants (coefficient block left by the solve) at 4096 points
-        SBn = bk.SplineBatch(Bi, Y)
-        xsn = synth.u_torch(5, 0, 4096)
-        outn = None
-        tot = 0.0
-        for it in range(args.warmup + args.solve_steps):
-            barrier()
-            s0 = torch.cuda.Event(enable_timing=True)
-            s1 = torch.cuda.Event(enable_timing=True)
-            s0.record()
-            outn = SBn(xsn)
-            s1.record()
-            torch.cuda.synchronize()
-            if it >= args.warmup:
-                tot += s0.elapsed_time(s1)
-        ms = max_over_ranks(tot / args.solve_steps)
-        if rank == 0:
-            cn = Y[:, 7].cpu().numpy().copy()
-            refn = O.spline_eval(0, kk, Bi.knots(), cn, xsn.cpu().numpy())
-            chk["vector_eval_relerr"] = float(np.max(np.abs(outn[:, 7].cpu().numpy() - refn)) / np.max(np.abs(refn)))
-        nb_ = 8.0 * 4096 * nrhs + 8.0 * n * nrhs                # values written + coefficient block read once
-        extra["n2_vector_valued_eval"] = {"metric": "spline values/s, %d splines sharing one basis x 4096 points" % nrhs,
-                                          "ms": ms, "value": world * 4096.0 * nrhs / (ms * 1e-3), "unit": "values/s",
-                                          "roofline_frac": nb_ / (ms * 1e-3) / 1e9 / peak}
-        del SBn, outn
+        best_name = min(res, key=lambda r: res[r]["ms"])
+        best = res[best_name]
+        st_ = prof.get("k_banded_tmem_bytes_per_launch")
+        solve = {"solve_metric": "RHS/s batched interpolation solve (n=4096, k=6, %d RHS total, Float64, one LU)" % nrhs_total,
+                 "solve_rhs_per_s": best["rhs_per_s"], "solve_ms": best["ms"], "solve_roofline_frac": best["frac"],
+                 "solve_traffic": (st_ * nrhs / 65536.0) if st_ else None, "solve_algo": best_name,
+                 "solve_twopass_ms": res["twopass"]["ms"], "solve_factor_once_ms": factor_ms,
+                 "solve_factor_first_call_ms": factor_first_ms, "solve_halo_rows": itp.C.halo,
+                 "solve_rhs_per_gpu": nrhs}
+        if not args.no_extra_configs:
+            # du = F \ (L u), mul! + ldiv! of a collocation time step in one pass
+            Lm = bk.collocation_matrix(Bi, xdata, bk.Derivative(2))
+            ms = timed(lambda: itp.C.ldiv_mul(Lm, Y0, out=Y), args.solve_steps, warm=args.warmup)
+            if rank == 0:
+                yref = O.banded_matvec(O.collocation_matrix(0, kk, Bi.knots(), xdata, 2)[0], Y0[:, :256].cpu().numpy())
+                O.banded_solve(band, yref)
+                chk["fused_matvec_solve_relerr"] = float(np.max(np.abs(Y[:, :256].cpu().numpy() - yref)) / np.max(np.abs(yref)))
+            extra["n1_fused_matvec_solve"] = {"ms": ms, "rhs_per_s": world * nrhs / (ms * 1e-3),
+                                              "roofline_frac": SOLVE_BYTES_PER_ELEM * n * nrhs / (ms * 1e-3) / 1e9 / peak}
+            del Lm
+            # all interpolants (coefficient block left by the solve) at 4096 points
+            itp.C.ldiv_(Y.copy_(Y0))
+            SBn = bk.SplineBatch(Bi, Y)
+            xsn = synth.u_torch(5, 0, 4096)
+            outn = [None]
+            def _n2():
+                outn[0] = SBn(xsn)
+            ms = timed(_n2, args.solve_steps, warm=args.warmup)
+            if rank == 0:
+                cn = Y[:, 7].cpu().numpy().copy()
+                refn = O.spline_eval(0, kk, Bi.knots(), cn, xsn.cpu().numpy())
+                chk["vector_eval_relerr"] = float(np.max(np.abs(outn[0][:, 7].cpu().numpy() - refn)) / np.max(np.abs(refn)))
+            nb_ = 8.0 * 4096 * nrhs + 8.0 * n * nrhs                # values written + coefficient block read once
+            extra["n2_vector_valued_eval"] = {"ms": ms, "values_per_s": world * 4096.0 * nrhs / (ms * 1e-3),
+                                              "roofline_frac": nb_ / (ms * 1e-3) / 1e9 / peak}
+            del SBn, outn
+        del Y, Y0, itp
 
-    # ---- extra: configs[3] (periodic cubic) and configs[4] (Robin k = 8 + Float32 sweep) ------------
+    # ---- extra: K1 / K2 at scale, configs[3] (periodic cubic), configs[4] (Robin k = 8 + Float32 sweep) -----
     if not args.no_extra_configs:
-        def timed(fn, reps, setup=None):
-            tot = 0.0
-            for it in range(reps + 1):
-                if setup is not None:
-                    setup()
-                torch.cuda.synchronize()
-                a = torch.cuda.Event(enable_timing=True)
-                b_ = torch.cuda.Event(enable_timing=True)
-                a.record(); fn(); b_.record()
-                torch.cuda.synchronize()
-                if it > 0:
-                    tot += a.elapsed_time(b_)
-            return max_over_ranks(tot / reps)
-
         torch.cuda.empty_cache()
+        nk = min(npts, 1 << 27)
+        xk = synth.u_torch(5, first, nk)
+        # K1: find_knot_interval, 8 B in + 8 B index + 1 B zone per point
+        idx = torch.empty(nk, dtype=torch.int64, device="cuda")
+        zone = torch.empty(nk, dtype=torch.int8, device="cuda")
+        call = lambda: _bl.check(_bl.lib.bsk_find_knot_interval(B._handle, ctypes.c_void_p(xk.data_ptr()), nk,
+                                                                ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(zone.data_ptr()), sp()))
+        ms = timed(call, 5)
+        extra["find_knot_interval"] = {"points": nk, "ms": ms, "gpoints_per_s": world * nk / (ms * 1e-3) / 1e9,
+                                       "bytes_per_point": 17, "roofline_frac": 17.0 * nk / (ms * 1e-3) / 1e9 / peak}
+        if rank == 0:
+            i_ref, z_ref = O.find_knot_interval(0, k, B.knots(), xk[:1 << 16].cpu().numpy())
+            chk["find_knot_interval_bitexact"] = bool(np.array_equal(idx[:1 << 16].cpu().numpy(), i_ref) and
+                                                      np.array_equal(zone[:1 << 16].cpu().numpy(), z_ref))
+        del zone
+        # K2: evaluate_all, 8 B in + 8 B index + 8 k B of basis values per point (bit-exact path)
+        for kk2 in (4, 8):
+            Bk = B if kk2 == 4 else bk.BSplineBasis(kk2, synth.breakpoints(3, 1000))
+            bs = torch.empty(nk * kk2, dtype=torch.float64, device="cuda")
+            call = lambda: _bl.check(_bl.lib.bsk_evaluate_all(Bk._handle, ctypes.c_void_p(xk.data_ptr()), nk, 0, 1, None,
+                                                              ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(bs.data_ptr()), sp()))
+            ms = timed(call, 5)
+            bpp = 16 + 8 * kk2
+            ent = {"points": nk, "ms": ms, "gpoints_per_s": world * nk / (ms * 1e-3) / 1e9, "bytes_per_point": bpp,
+                   "roofline_frac": bpp * nk / (ms * 1e-3) / 1e9 / peak,
+                   "fp64_pipe_frac": pipe_frac("k_evaluate_all_k%d_fp64_inst_per_point" % kk2, "fp64", nk, ms)}
+            if rank == 0:
+                i_ref, bs_ref = O.evaluate_all(0, kk2, Bk.knots(), xk[:1 << 16].cpu().numpy())
+                ent["bitexact"] = bool(np.array_equal(idx[:1 << 16].cpu().numpy(), i_ref) and
+                                       np.array_equal(bs[:(1 << 16) * kk2].cpu().numpy().reshape(-1, kk2), bs_ref))
+            extra["evaluate_all_k%d" % kk2] = ent
+            del bs
+        del xk, idx
+        torch.cuda.empty_cache()
+
         n4 = 10000
         br4 = synth.breakpoints(8, n4 + 1)
         B4 = bk.PeriodicBSplineBasis(4, br4)
         M4 = bk.collocation_matrix(B4, bk.collocation_points(B4))
-        nrhs4 = 16384
+        nrhs4 = 16384 if mode != "strong" else max(32, (16384 // world) // 32 * 32)
         D0 = (2 * synth.u_torch(9, rank * n4 * nrhs4, n4 * nrhs4) - 1).reshape(n4, nrhs4)
         D = torch.empty_like(D0)
         ms = timed(lambda: M4.ldiv_(D), 5, setup=lambda: D.copy_(D0))
-        extra["c4_cyclic_solve"] = {"metric": "RHS/s (periodic cubic, n=10^4, 16384 RHS per GPU)", "ms": ms,
-                                    "value": world * nrhs4 / (ms * 1e-3), "unit": "RHS/s",
+        extra["c4_cyclic_solve"] = {"ms": ms, "rhs_per_s": world * nrhs4 / (ms * 1e-3), "rhs_per_gpu": nrhs4,
                                     "roofline_frac": 16.0 * n4 * nrhs4 / (ms * 1e-3) / 1e9 / peak}
         S4 = bk.Spline(B4, D[:, 0].cpu().numpy())
         del D, D0
-        x4 = synth.u_torch(9, (1 << 40) + rank * npts, npts)
+        x4 = synth.u_torch(9, (1 << 40) + first, npts)
         o4 = [torch.empty_like(x4)]
         ms = timed(lambda: S4.evaluate(x4, (0,), out=o4), 5)
-        extra["c4_periodic_eval"] = {"metric": "Gpoints/s (periodic cubic, 10^4 knots, 2^28 F64 points)", "ms": ms,
-                                     "value": world * npts / (ms * 1e-3) / 1e9, "unit": "Gpoints/s",
+        extra["c4_periodic_eval"] = {"ms": ms, "gpoints_per_s": world * npts / (ms * 1e-3) / 1e9,
                                      "roofline_frac": 16.0 * npts / (ms * 1e-3) / 1e9 / peak}
+        if rank == 0:
+            x4h = x4[:1 << 16].cpu().numpy()
+            r4 = O.spline_eval(1, 4, br4, S4.coefficients(), x4h)
+            chk["c4_eval_relerr"] = float(np.max(np.abs(o4[0][:1 << 16].cpu().numpy() - r4)) / np.max(np.abs(r4)))
         del x4, o4
         B5 = bk.BSplineBasis(8, synth.breakpoints(10, 99996))
         R5 = bk.RecombinedBSplineBasis(B5, bk.Derivative(0) + 3 * bk.Derivative(1))
         x5 = torch.from_numpy(bk.collocation_points(R5)).cuda()
         ms = timed(lambda: bk.collocation_matrix(R5, x5, bk.Derivative(2)), 5)
-        extra["c5_collocation_assembly"] = {"metric": "ms per collocation_matrix(R, x, Derivative(2)), 10^5 x k=8 "
-                                                      "(assembly + band handle; launch-bound)", "ms": ms}
+        extra["c5_collocation_assembly"] = {"ms": ms, "note": "10^5 x k=8, Derivative(2): assembly + band handle, launch-bound"}
         B5f = bk.BSplineBasis(8, synth.breakpoints(10, 99996).astype(np.float32))
-        S5f = bk.Spline(B5f, (2 * synth.u_numpy(4, 0, len(B5f)) - 1).astype(np.float32))
-        x5f = synth.u_torch(11, rank * npts, npts, dtype=torch.float32)
+        c5f = (2 * synth.u_numpy(4, 0, len(B5f)) - 1).astype(np.float32)
+        S5f = bk.Spline(B5f, c5f)
+        x5f = synth.u_torch(11, first, npts, dtype=torch.float32)
         o5 = [torch.empty_like(x5f)]
         ms = timed(lambda: S5f.evaluate(x5f, (0,), out=o5), 5)
-        extra["c5_float32_eval"] = {"metric": "Gpoints/s (k=8, 10^5 knots, 2^28 F32 points)", "ms": ms,
-                                    "value": world * npts / (ms * 1e-3) / 1e9, "unit": "Gpoints/s",
-                                    "roofline_frac": 8.0 * npts / (ms * 1e-3) / 1e9 / peak}
+        extra["c5_float32_eval"] = {"ms": ms, "gpoints_per_s": world * npts / (ms * 1e-3) / 1e9,
+                                    "roofline_frac": 8.0 * npts / (ms * 1e-3) / 1e9 / peak,
+                                    "fp32_pipe_frac": pipe_frac("k_spline_cell_f32k8_fma_inst_per_point", "fp32", npts, ms)}
+        if rank == 0:
+            x5h = x5f[:1 << 16].cpu().numpy()
+            r5 = O.spline_eval(0, 8, B5f.knots(), c5f, x5h, kt="f32")
+            chk["c5_f32_eval_relerr"] = float(np.max(np.abs(o5[0][:1 << 16].cpu().numpy().astype(np.float64) - r5)) / np.max(np.abs(r5)))
         del x5f, o5
-        # Float32 batched interpolation (C3 shape in Float32; BANSLV order, two passes: 16 B/element moved,
-        # 8 B/element algorithmic) and evaluation of an order-6 Float64 spline (shared-memory cell table
-        # with the jump encoding of knot cells)
+        # Float32 batched interpolation (C3's shape in Float32: 8 B/element algorithmic)
         xd32 = synth.breakpoints(6, 4096).astype(np.float32)
         B32 = bk.BSplineBasis(6, bk.make_knots(xd32, 6), augment=False)
         itp32 = bk.SplineInterpolation(B32, xd32)
-        nr32 = 65536
+        nr32 = 65536 if mode != "strong" else (65536 // world) // 32 * 32
         Y32 = (2 * synth.u_torch(7, rank * 4096 * nr32, 4096 * nr32, dtype=torch.float32) - 1).reshape(4096, nr32)
         W32 = torch.empty_like(Y32)
-        ms = timed(lambda: itp32.C.ldiv_(W32), 5, setup=lambda: W32.copy_(Y32))
-        extra["float32_batched_solve"] = {"metric": "RHS/s (n=4096, k=6, 65536 RHS per GPU, Float32, BANSLV order)",
-                                          "ms": ms, "value": world * nr32 / (ms * 1e-3), "unit": "RHS/s",
-                                          "roofline_frac": 8.0 * 4096 * nr32 / (ms * 1e-3) / 1e9 / peak}
-        if rank == 0:
-            from oracle import oracle as O32
-            band32, _ = O32.collocation_matrix_f32(0, 6, B32.knots(), xd32)
-            O32.banded_lu(band32)
-            ref32 = O32.banded_solve(band32, Y32[:, :128].cpu().numpy().copy())
-            chk["float32_solve_bitexact"] = bool(np.array_equal(W32[:, :128].cpu().numpy(), ref32))
+        f32res = {}
+        for name, salgo in (("auto", bk.SOLVE_AUTO), ("twopass", bk.SOLVE_TWOPASS)):
+            try:
+                ms = timed(lambda: itp32.C.ldiv_(W32, algo=salgo), 5, setup=lambda: W32.copy_(Y32))
+            except TypeError:
+                if name != "auto":
+                    continue
+                ms = timed(lambda: itp32.C.ldiv_(W32), 5, setup=lambda: W32.copy_(Y32))
+            f32res[name] = {"ms": ms, "rhs_per_s": world * nr32 / (ms * 1e-3),
+                            "roofline_frac": 8.0 * 4096 * nr32 / (ms * 1e-3) / 1e9 / peak}
+            if rank == 0:
+                from oracle import oracle as O32
+                band32, _ = O32.collocation_matrix_f32(0, 6, B32.knots(), xd32)
+                O32.banded_lu(band32)
+                ref32 = O32.banded_solve(band32, Y32[:, :128].cpu().numpy().copy())
+                g32 = W32[:, :128].cpu().numpy()
+                f32res[name]["bitexact"] = bool(np.array_equal(g32, ref32))
+                f32res[name]["relerr"] = float(np.max(np.abs(g32.astype(np.float64) - ref32)) / np.max(np.abs(ref32)))
+        extra["float32_batched_solve"] = f32res
         del Y32, W32, itp32
-        B6 = bk.BSplineBasis(6, synth.breakpoints(3, 1000))
-        S6 = bk.Spline(B6, 2 * synth.u_numpy(4, 0, len(B6)) - 1)
-        x6 = synth.u_torch(5, rank * npts, npts)
-        o6 = [torch.empty_like(x6), torch.empty_like(x6)]
-        ms = timed(lambda: S6.evaluate(x6, (0, 1), out=o6), 5)
-        extra["order6_eval"] = {"metric": "Gpoints/s (k=6, 1000 breakpoints, value + 1st derivative, 2^28 F64 points)",
-                                "ms": ms, "value": world * npts / (ms * 1e-3) / 1e9, "unit": "Gpoints/s",
-                                "roofline_frac": 24.0 * npts / (ms * 1e-3) / 1e9 / peak}
-        if rank == 0:
-            from oracle import oracle as O6
-            x6h = x6[:1 << 16].cpu().numpy()
+        for kk6 in (6, 8):
+            B6 = bk.BSplineBasis(kk6, synth.breakpoints(3, 1000))
             c6 = 2 * synth.u_numpy(4, 0, len(B6)) - 1
-            r6 = O6.spline_eval(0, 6, B6.knots(), c6, x6h)
-            chk["order6_value_relerr"] = float(np.max(np.abs(o6[0][:1 << 16].cpu().numpy() - r6)) / np.max(np.abs(r6)))
-        del x6, o6
+            S6 = bk.Spline(B6, c6)
+            x6 = synth.u_torch(5, first, npts)
+            o6 = [torch.empty_like(x6), torch.empty_like(x6)]
+            ms = timed(lambda: S6.evaluate(x6, (0, 1), out=o6), 5)
+            ent = {"ms": ms, "gpoints_per_s": world * npts / (ms * 1e-3) / 1e9,
+                   "roofline_frac": 24.0 * npts / (ms * 1e-3) / 1e9 / peak,
+                   "fp64_pipe_frac": pipe_frac("k_spline_cell_k%d_fp64_inst_per_point" % kk6, "fp64", npts, ms)}
+            if rank == 0:
+                x6h = x6[:1 << 16].cpu().numpy()
+                r6 = O.spline_eval(0, kk6, B6.knots(), c6, x6h)
+                ent["value_relerr"] = float(np.max(np.abs(o6[0][:1 << 16].cpu().numpy() - r6)) / np.max(np.abs(r6)))
+            extra["order%d_eval" % kk6] = ent
+            del x6, o6
 
     # ---- extra: configs[0] (the reference's own CPU-runnable case), in full, host arrays in and out --
     if not args.no_extra_configs and rank == 0:
@@ -531,38 +636,39 @@ def run_ours(args):
         ref1 = O1.spline_eval(0, 4, t1k, c1, xs1)
         cpu_ms = 1e3 * (time.perf_counter() - t0)
         chk["c1_relerr"] = float(np.max(np.abs(v1 - ref1)) / np.max(np.abs(ref1)))
-        extra["c1_interpolate_eval_1e6"] = {"metric": "ms, interpolate((0:10).^2, y, k=4) + S.(xs) at 10^6 host points "
-                                                      "(H2D + kernel + D2H)", "first_call_ms": first_ms, "ms": rep_ms,
-                                            "cpu_port_eval_ms": cpu_ms}
+        extra["c1_interpolate_eval_1e6"] = {"first_call_ms": first_ms, "ms": rep_ms, "cpu_port_eval_ms": cpu_ms,
+                                            "note": "10^6 host points: copy / launch bound, no speed-up claimed"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = omp_threads(os.cpu_count() or 1)
         sample = 1 << 27
-        r, dt = cpu_reference_rate(sample, cores)
+        r, dt = cpu_reference_rate(synth, sample, cores)
         cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "2^27 of the 2^28 points, value + derivative, OpenMP over points (%.1f s)" % dt}
 
     if rank == 0:
+        extra["pipe_peaks"] = pipes
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2: k=4 spline, 1000 non-uniform breakpoints, value + 1st derivative "
-                                   "at %d random Float64 points per GPU" % npts,
-                       "points_per_gpu": npts, "algo": args.algo,
-                       "l2": "inputs (%.2f GB per step) larger than the 126 MB L2" % (8e-9 * npts),
-                       "parallelism": "points sharded, basis replicated, no collective"},
-            "clocks": clocks, "gpu_launches": args.steps * launches_per_step,
+            "scaling": mode, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points_total": total_pts, "points_per_gpu": npts, "algo": args.algo,
+                       "l2": "inputs (%.2f GB per GPU per step) larger than the 126 MB L2" % (8e-9 * npts),
+                       "parallelism": "points sharded contiguously (%s scaling), basis replicated, no collective" % mode},
+            "clocks": clocks, "gpu_launches": launches[0],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "stream_1r2w_gbs": stream_mix,
+                         "stream_1r2w_gbs": stream_mix, "stream_1r2w_tma_gbs": stream_tma,
                          "frac_of_stream_1r2w": (achieved / stream_mix) if stream_mix else None,
                          "kernel": "k_spline_cell<4,0,double,3>" if args.algo != "deboor" else "k_spline_deboor<4,0,double>",
                          "algorithmic_bytes_per_launch": BYTES_PER_POINT * npts},
-            "e2e": e2e, "cpu_baseline": cpu, "parity": chk, "extra": extra,
+            "e2e": e2e, "cpu_baseline": cpu,
         }
+        line.update(solve)
+        line["parity"] = chk
+        line["extra"] = extra
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -574,12 +680,14 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=int, default=1 << 28)
+    ap.add_argument("--points", type=int, default=1 << 28, help="points of the problem (strong) / per GPU (weak)")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
+                    help="auto = strong under torchrun (2^28 points in total), single process otherwise")
     ap.add_argument("--algo", default="auto", choices=["auto", "pp", "deboor"])
     ap.add_argument("--nrhs", type=int, default=65536)
     ap.add_argument("--solve-steps", type=int, default=10)
     ap.add_argument("--e2e-points", type=int, default=1 << 28)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

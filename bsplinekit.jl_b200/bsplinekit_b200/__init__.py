@@ -4,7 +4,7 @@ See api.py.  Importing this package loads the CUDA shared library and fails loud
 has not been built (no CPU fallback).
 """
 from ._lib import (ArgumentError, DimensionMismatch, ZeroPivotException, CudaError, UnsupportedError,
-                   EVAL_AUTO, EVAL_DEBOOR, EVAL_PP, SOLVE_AUTO, SOLVE_TWOPASS, SOLVE_WINDOWED,
+                   EVAL_AUTO, EVAL_DEBOOR, EVAL_PP, SOLVE_AUTO, SOLVE_TWOPASS, SOLVE_WINDOWED, LU_EXACT, LU_FAST,
                    EXTRAP_NONE, EXTRAP_FLAT, EXTRAP_LINEAR, EXTRAP_SMOOTH,
                    LIB_PATH, device_count, version)
 from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, period,

@@ -15,6 +15,7 @@ BSK_F32, BSK_F64 = 0, 1
 BASIS_PLAIN, BASIS_PERIODIC, BASIS_RECOMBINED = 0, 1, 2
 EVAL_AUTO, EVAL_DEBOOR, EVAL_PP = 0, 1, 2
 SOLVE_AUTO, SOLVE_TWOPASS, SOLVE_WINDOWED = 0, 1, 2
+LU_EXACT, LU_FAST = 0, 1
 EXTRAP_NONE, EXTRAP_FLAT, EXTRAP_LINEAR, EXTRAP_SMOOTH = 0, 1, 2, 3
 
 
@@ -64,6 +65,9 @@ SIGNATURES = {
     "bsk_last_error": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "bsk_device_count": (_i32, [C.POINTER(_i32)]),
     "bsk_probe_stream_1r2w": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "bsk_probe_stream_1r2w_tma": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "bsk_probe_fma": (_i32, [_i32, _i64, _vp, C.POINTER(_dbl), _vp]),
+    "bsk_probe_copy_host": (_i32, [_vp, _vp, _i64, _i32, _pp]),
     "bsk_malloc": (_i32, [_i32, C.c_size_t, _pp]),
     "bsk_free": (_i32, [_i32, _vp]),
     "bsk_memcpy_h2d": (_i32, [_i32, _vp, _vp, C.c_size_t, _vp]),
@@ -93,6 +97,7 @@ SIGNATURES = {
     "bsk_banded_create": (_i32, [_vp, _i64, _i32, _i32, _i32, _pp]),
     "bsk_banded_create_host": (_i32, [_vp, _i64, _i32, _i32, _i32, _pp]),
     "bsk_banded_lu": (_i32, [_vp, C.POINTER(_i64)]),
+    "bsk_banded_lu_mode": (_i32, [_vp, _i32, C.POINTER(_i64)]),
     "bsk_banded_data": (_i32, [_vp, _vp]),
     "bsk_banded_halo": (_i32, [_vp, C.POINTER(_i32)]),
     "bsk_banded_solve": (_i32, [_vp, _vp, _i64, _i32, _vp]),
@@ -113,7 +118,8 @@ SIGNATURES = {
     "bsk_banded_f32_create_host": (_i32, [_vp, _i64, _i32, _i32, _i32, _pp]),
     "bsk_banded_f32_lu": (_i32, [_vp, C.POINTER(_i64)]),
     "bsk_banded_f32_data": (_i32, [_vp, _vp]),
-    "bsk_banded_f32_solve": (_i32, [_vp, _vp, _i64, _vp]),
+    "bsk_banded_f32_halo": (_i32, [_vp, C.POINTER(_i32)]),
+    "bsk_banded_f32_solve": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "bsk_banded_f32_destroy": (_i32, [_vp]),
     "bsk_cyclic_f32_create": (_i32, [_vp, _vp, _vp, _i64, _i32, _pp]),
     "bsk_cyclic_f32_solve": (_i32, [_vp, _vp, _i64, _vp]),

@@ -806,20 +806,23 @@ class CollocationMatrix:
         check(lib.bsk_banded_matvec(self._handle, _ptr(Xd), _ptr(Y), Xd.numel() // self.n, _stream()))
         return Y if on_dev else Y.cpu().numpy()
 
-    def lu_(self):
-        """lu!(C) (Collocation/matrix.jl:132-201)."""
+    def lu_(self, mode=_lib.LU_EXACT):
+        """lu!(C) (Collocation/matrix.jl:132-201).  mode LU_EXACT: BANFAC's statements in BANFAC's order
+        (bit-identical factors); LU_FAST: partitioned elimination with validated overlap (Float64, n >= 1024),
+        factors within ~1e-16 relative of BANFAC's."""
         info = C.c_int64(0)
-        st = (lib.bsk_banded_f32_lu if self.f32 else lib.bsk_banded_lu)(self._handle, C.byref(info))
+        if self.f32:
+            st = lib.bsk_banded_f32_lu(self._handle, C.byref(info))
+        else:
+            st = lib.bsk_banded_lu_mode(self._handle, int(mode), C.byref(info))
         check(st, info.value)
         self.factored = True
         return self
 
     @property
     def halo(self):
-        if self.f32:
-            return 0
         h = C.c_int32(0)
-        check(lib.bsk_banded_halo(self._handle, C.byref(h)))
+        check((lib.bsk_banded_f32_halo if self.f32 else lib.bsk_banded_halo)(self._handle, C.byref(h)))
         return h.value
 
     def ldiv_(self, Y, algo=SOLVE_AUTO):
@@ -836,7 +839,7 @@ class CollocationMatrix:
                 Yd = torch.from_numpy(Y).cuda()
             if Yd.shape[0] != self.n:
                 raise DimensionMismatch("vectors `x` and `y` must have length %d" % self.n)
-            check(lib.bsk_banded_f32_solve(self._handle, _ptr(Yd), Yd.numel() // self.n if self.n else 0, _stream()))
+            check(lib.bsk_banded_f32_solve(self._handle, _ptr(Yd), Yd.numel() // self.n if self.n else 0, algo, _stream()))
             if not on_dev:
                 Y[...] = Yd.cpu().numpy()
             return Y
@@ -1148,7 +1151,9 @@ class SplineInterpolation:
     """SplineInterpolation (SplineInterpolations.jl:56-119): basis + factorised collocation
     matrix, reusable for many data sets on the same x through interpolate_ (= interpolate!)."""
 
-    def __init__(self, B, x):
+    def __init__(self, B, x, lu_mode=_lib.LU_FAST):
+        """lu_mode: LU_FAST (default: partitioned factorisation from 1024 points on, within 1e-13 like the default
+        solve) or LU_EXACT (BANFAC order: with algo=SOLVE_TWOPASS the coefficients are then the reference's bits)."""
         N = len(B)
         x = np.asarray(x)
         if x.size != N:
@@ -1162,7 +1167,7 @@ class SplineInterpolation:
             self.C = None
         else:
             Cm = collocation_matrix(B, x)
-            self.C = Cm if isinstance(Cm, (CyclicTridiagonalMatrix, CyclicBandedMatrix)) else Cm.lu_()
+            self.C = Cm if isinstance(Cm, (CyclicTridiagonalMatrix, CyclicBandedMatrix)) else Cm.lu_(lu_mode)
         self.spline = None
         self.coefs = None
 
@@ -1186,8 +1191,6 @@ class SplineInterpolation:
             pass                                                        # identity
         elif isinstance(self.C, (CyclicTridiagonalMatrix, CyclicBandedMatrix)):
             self.C.ldiv_(Y)
-        elif self.C.f32:
-            self.C.ldiv_(Y)                                             # BANSLV order, Float32
         else:
             self.C.ldiv_(Y, algo=algo)
         self.coefs = Y

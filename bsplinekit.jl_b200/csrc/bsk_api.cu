@@ -69,6 +69,96 @@ k_probe_stream_1r2w(const double2 *__restrict__ in, double2 *__restrict__ o0, do
     }
 }
 
+// The same stream through TMA: one elected thread per CTA issues cp.async.bulk global -> shared for the
+// next tile of points (mbarrier completion), the tile is transformed in shared memory and leaves through
+// cp.async.bulk shared -> global.  Answers whether a bulk-copy write path gives the 1 : 2 stream more
+// HBM bandwidth than 128-bit LDG / STG (bsk_probe_stream_1r2w).
+namespace {
+constexpr int kTmaTile = 2048;              // doubles per tile: 16 KB in, 2 x 16 KB out, two stages
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+}  // namespace
+
+__global__ void __launch_bounds__(1024, 1)
+k_probe_stream_1r2w_tma(const double *__restrict__ in, double *__restrict__ o0, double *__restrict__ o1, int64_t ntiles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double *sin = (double *)smem;                                  // [2][kTmaTile]
+    double *so0 = sin + 2 * kTmaTile;                              // [2][kTmaTile]
+    double *so1 = so0 + 2 * kTmaTile;
+    __shared__ uint64_t full[2];
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    int64_t tile = blockIdx.x;
+    if (threadIdx.x == 0 && tile < ntiles) {
+        mbar_expect_tx(&full[0], kTmaTile * 8);
+        bulk_g2s(sin, in + tile * kTmaTile, kTmaTile * 8, &full[0]);
+    }
+    uint32_t phase[2] = {0, 0};
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const int64_t nxt = tile + gridDim.x;
+        if (threadIdx.x == 0) {
+            // the stage we are about to refill / rewrite must have been drained by its bulk stores
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (nxt < ntiles) {
+                mbar_expect_tx(&full[st ^ 1], kTmaTile * 8);
+                bulk_g2s(sin + (st ^ 1) * kTmaTile, in + nxt * kTmaTile, kTmaTile * 8, &full[st ^ 1]);
+            }
+        }
+        __syncthreads();                                           // stage st: outputs of two tiles ago are out
+        mbar_wait(&full[st], phase[st]);
+        phase[st] ^= 1;
+        const double2 x = ((const double2 *)(sin + st * kTmaTile))[threadIdx.x];
+        ((double2 *)(so0 + st * kTmaTile))[threadIdx.x] = make_double2(x.x + 1.0, x.y + 1.0);
+        ((double2 *)(so1 + st * kTmaTile))[threadIdx.x] = make_double2(x.x * 0.5, x.y * 0.5);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(o0 + tile * kTmaTile, so0 + st * kTmaTile, kTmaTile * 8);
+            bulk_s2g(o1 + tile * kTmaTile, so1 + st * kTmaTile, kTmaTile * 8);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// Peak rate of the FP64 / FP32 FMA pipes: 8 independent fused multiply-add chains per thread, full
+// occupancy, nothing else in the loop.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_probe_fma(T *out, int iters, T a, T b) {
+    T v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (T)(threadIdx.x + j);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fma(v[j], a, b);
+    }
+    T s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+    if (s == (T)-1.2345) out[0] = s;        // never true: keeps the chains alive
+}
+
 extern "C" {
 
 const char *bsk_version(void) { return "bsplinekit_b200 0.1.0 (sm_100a)"; }
@@ -107,6 +197,34 @@ bsk_status bsk_probe_stream_1r2w(const double *d_in, double *d_out0, double *d_o
     k_probe_stream_1r2w<<<bsk::sm_count(dev), 1024, 0, (cudaStream_t)stream>>>((const double2 *)d_in, (double2 *)d_out0,
                                                                               (double2 *)d_out1, n / 2);
     BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+bsk_status bsk_probe_stream_1r2w_tma(const double *d_in, double *d_out0, double *d_out1, int64_t n, void *stream) {
+    BSK_REQUIRE(d_in && d_out0 && d_out1, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(n >= 0 && n % kTmaTile == 0, BSK_ERR_ARGUMENT, "n must be a multiple of %d", kTmaTile);
+    BSK_REQUIRE((((uintptr_t)d_in | (uintptr_t)d_out0 | (uintptr_t)d_out1) & 15) == 0, BSK_ERR_ARGUMENT,
+                "pointers must be 16-byte aligned");
+    if (n == 0) return BSK_OK;
+    int dev = 0;
+    BSK_CUDA(cudaGetDevice(&dev));
+    const int smem = 6 * kTmaTile * 8;
+    BSK_CUDA(cudaFuncSetAttribute(k_probe_stream_1r2w_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_probe_stream_1r2w_tma<<<bsk::sm_count(dev), 1024, smem, (cudaStream_t)stream>>>(d_in, d_out0, d_out1, n / kTmaTile);
+    BSK_CUDA(cudaGetLastError());
+    return BSK_OK;
+}
+
+bsk_status bsk_probe_fma(int32_t dtype, int64_t iters, void *d_scratch, double *fma_count, void *stream) {
+    BSK_REQUIRE(d_scratch && iters > 0 && iters < (1ll << 31), BSK_ERR_ARGUMENT, "bad argument");
+    BSK_REQUIRE(dtype == BSK_F32 || dtype == BSK_F64, BSK_ERR_ARGUMENT, "bad dtype");
+    int dev = 0;
+    BSK_CUDA(cudaGetDevice(&dev));
+    const int grid = bsk::sm_count(dev) * 8;
+    if (dtype == BSK_F64) k_probe_fma<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double *)d_scratch, (int)iters, 0.999999, 1e-7);
+    else k_probe_fma<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float *)d_scratch, (int)iters, 0.99999f, 1e-4f);
+    BSK_CUDA(cudaGetLastError());
+    if (fma_count) *fma_count = 8.0 * (double)iters * 256.0 * (double)grid;
     return BSK_OK;
 }
 

@@ -86,7 +86,11 @@ k_find_interval(KnotView<KT> kv, const KT *__restrict__ x, int64_t n, int64_t *_
 }
 
 // ---- K2 ---------------------------------------------------------------------------------
-template <int K, int KIND, typename KT, typename VT>
+// One thread per point; the K values of a point are a row of K * sizeof(VT) bytes of the [n][K] output.
+// WIDE = 1: the 32 rows of a warp (one contiguous block of the output) are staged in shared memory and
+// leave as 16-byte vectors, each store instruction of the warp covering 512 contiguous bytes; the
+// strided per-lane stores of the plain variant touch every 32-byte sector K / 4 times over.
+template <int K, int KIND, typename KT, typename VT, int WIDE>
 __global__ void __launch_bounds__(kThreads)
 k_evaluate_all(KnotView<KT> kv, RecombView rv, const KT *__restrict__ x, int64_t n, int deriv,
                const int64_t *__restrict__ ileft, int64_t *__restrict__ idx, VT *__restrict__ bs,
@@ -94,22 +98,67 @@ k_evaluate_all(KnotView<KT> kv, RecombView rv, const KT *__restrict__ x, int64_t
     extern __shared__ __align__(16) unsigned char smem[];
     size_t off = 0;
     const KT *t = stage_knots(kv, smem, stage, off);
+    off = (off + 15) & ~(size_t)15;
+    VT *const rows = (VT *)(smem + off) + (threadIdx.x >> 5) * (32 * K);     // this warp's 32 rows
+    const int lane = threadIdx.x & 31;
     __syncthreads();
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p - lane < n;
          p += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = p < n;
         VT bq[K];
-        long long il = ileft ? ileft[p] : 0;
-        if (rv.enabled && il != 0) il += rv.cl;          // bases.jl:393-395
-        int i = eval_all_point<K, KIND, KT, VT>(kv, t, x[p], deriv, il, bq);
-        if (rv.enabled) {
-            VT ph[K];
-            i = recombine_point<K, KT, VT>(rv, i, bq, ph);
+        int i = 1;
+        if (live) {
+            long long il = ileft ? ileft[p] : 0;
+            if (rv.enabled && il != 0) il += rv.cl;          // bases.jl:393-395
+            i = eval_all_point<K, KIND, KT, VT>(kv, t, x[p], deriv, il, bq);
+            if (rv.enabled) {
+                VT ph[K];
+                i = recombine_point<K, KT, VT>(rv, i, bq, ph);
 #pragma unroll
-            for (int j = 0; j < K; ++j) bq[j] = ph[j];
+                for (int j = 0; j < K; ++j) bq[j] = ph[j];
+            }
+            idx[p] = i;
         }
-        idx[p] = i;
+        const int64_t p0 = p - lane;
+        if (WIDE && p0 + 32 <= n) {
+            // 16-byte vectors of the warp's block; a lane's row is NVL of them.  Lanes of one shared-memory phase
+            // are NVL vectors apart, which for NVL = 2, 4 lands them on the same bank groups: the vector index is
+            // XOR-swizzled by its 128-byte line number (writes and reads alike), conflict-free both ways.
+            constexpr int RB = K * (int)sizeof(VT);
+            constexpr int NV = 32 * RB / 16;
+            if constexpr (RB % 16 == 0) {
+                constexpr int NVL = RB / 16;
+                constexpr int SW = (NVL == 2 || NVL == 4) ? NVL - 1 : 0;
+                int4 *const rows4 = (int4 *)rows;
 #pragma unroll
-        for (int j = 0; j < K; ++j) bs[p * K + j] = bq[j];
+                for (int jj = 0; jj < NVL; ++jj) {
+                    int4 raw;
+                    memcpy(&raw, &bq[jj * (16 / (int)sizeof(VT))], 16);
+                    const int v = lane * NVL + jj;
+                    rows4[v ^ ((v >> 3) & SW)] = raw;
+                }
+                __syncwarp();
+                int4 *dst = (int4 *)(bs + p0 * K);
+#pragma unroll
+                for (int it = 0; it < NV / 32; ++it) {
+                    const int v = it * 32 + lane;
+                    dst[v] = rows4[v ^ ((v >> 3) & SW)];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; ++j) rows[lane * K + j] = bq[j];
+                __syncwarp();
+                const int4 *src = (const int4 *)rows;
+                int4 *dst = (int4 *)(bs + p0 * K);
+#pragma unroll
+                for (int v = 0; v < (NV + 31) / 32; ++v)
+                    if (v * 32 + lane < NV) dst[v * 32 + lane] = src[v * 32 + lane];
+            }
+            __syncwarp();
+        } else if (live) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) bs[p * K + j] = bq[j];
+        }
     }
 }
 
@@ -712,10 +761,18 @@ bsk_status launch_eval_all(const bsk_basis *b, const KT *d_x, int64_t n, int der
     size_t smem = knots_smem_bytes<KT>(b);
     int stage = smem <= kSmemStageLimit;
     if (!stage) smem = 0;
-    auto kern = k_evaluate_all<K, KIND, KT, VT>;
-    BSK_CUDA(set_smem(kern, smem));
-    int grid = grid_for(n, b->device, 4);
-    kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs, stage);
+    smem = ((smem + 15) & ~(size_t)15) + (size_t)kThreads * K * sizeof(VT);      // + the row staging of WIDE
+    const bool wide = (((uintptr_t)d_bs) & 15) == 0 && getenv("BSK_EVALALL_NARROW") == nullptr;
+    int grid = grid_for(n, b->device, 8);
+    if (wide) {
+        auto kern = k_evaluate_all<K, KIND, KT, VT, 1>;
+        BSK_CUDA(set_smem(kern, smem));
+        kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs, stage);
+    } else {
+        auto kern = k_evaluate_all<K, KIND, KT, VT, 0>;
+        BSK_CUDA(set_smem(kern, smem));
+        kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs, stage);
+    }
     BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }

@@ -4,6 +4,7 @@
 // "e2e" leg of bench.py.  Staging buffers and streams are cached per device (grow-only) so that
 // repeated calls do not pay cudaMalloc / cudaFree (which synchronises the device).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "handles.cuh"
@@ -48,11 +49,9 @@ cudaError_t pool_stream(Pool &p, int slot, cudaStream_t *out) {
 
 }  // namespace
 
-extern "C" {
-
-bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n, int32_t nout,
-                                const int32_t *derivs, void *const *h_outs, int32_t algo) {
-    BSK_REQUIRE(s && derivs && h_outs, BSK_ERR_ARGUMENT, "NULL argument");
+static bsk_status eval_host_impl(const bsk_spline *s, const void *h_x, int64_t n, int32_t nout,
+                                 const int32_t *derivs, void *const *h_outs, int32_t algo, bool copy_only) {
+    BSK_REQUIRE(s && (derivs || copy_only) && h_outs, BSK_ERR_ARGUMENT, "NULL argument");
     BSK_REQUIRE(nout >= 1 && nout <= 4, BSK_ERR_ARGUMENT, "nout must be in 1..4");
     if (n == 0) return BSK_OK;
     BSK_REQUIRE(h_x, BSK_ERR_ARGUMENT, "NULL points");
@@ -62,7 +61,9 @@ bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n,
     BSK_CUDA(cudaSetDevice(device));
     std::lock_guard<std::mutex> lock(g_pool_mu[device]);
     Pool &pool = g_pool[device];
-    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 23);
+    int chunk_log2 = 23;                              // 2^23 points per chunk (64 MB of Float64 points)
+    if (const char *ev = getenv("BSK_HOST_CHUNK_LOG2")) chunk_log2 = std::max(16, std::min(27, atoi(ev)));
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << chunk_log2);
     const int nslots = (int)std::min<int64_t>(kSlots, (n + chunk - 1) / chunk);
     cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
     void *dx[kSlots] = {nullptr, nullptr, nullptr};
@@ -82,7 +83,7 @@ bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n,
             // stream order on the slot guarantees the previous use of its buffers is finished
             e = cudaMemcpyAsync(dx[slot], (const char *)h_x + es * off, es * m, cudaMemcpyHostToDevice, st[slot]);
             if (e != cudaSuccess) break;
-            rc = bsk_spline_eval(s, dx[slot], m, nout, derivs, dout[slot], algo, (void *)st[slot]);
+            if (!copy_only) rc = bsk_spline_eval(s, dx[slot], m, nout, derivs, dout[slot], algo, (void *)st[slot]);
             if (rc != BSK_OK) break;
             for (int o = 0; o < nout && e == cudaSuccess; ++o)
                 e = cudaMemcpyAsync((char *)h_outs[o] + es * off, dout[slot][o], es * m, cudaMemcpyDeviceToHost, st[slot]);
@@ -97,6 +98,17 @@ bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n,
     if (rc != BSK_OK) return rc;
     if (e != cudaSuccess) { set_error("bsk_spline_eval_host failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
     return BSK_OK;
+}
+
+extern "C" {
+
+bsk_status bsk_spline_eval_host(const bsk_spline *s, const void *h_x, int64_t n, int32_t nout,
+                                const int32_t *derivs, void *const *h_outs, int32_t algo) {
+    return eval_host_impl(s, h_x, n, nout, derivs, h_outs, algo, false);
+}
+
+bsk_status bsk_probe_copy_host(const bsk_spline *s, const void *h_x, int64_t n, int32_t nout, void *const *h_outs) {
+    return eval_host_impl(s, h_x, n, nout, nullptr, h_outs, 0, true);
 }
 
 bsk_status bsk_banded_solve_host(const bsk_banded *h, double *h_rhs, int64_t nrhs, int32_t algo) {

@@ -9,6 +9,9 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
+#include <utility>
+#include <vector>
 
 #include "banfac.cuh"
 #include "banslv.cuh"
@@ -213,37 +216,44 @@ k_decay_need(const double *__restrict__ rec, const double *__restrict__ scale, i
     }
 }
 
-template <int BW>
-int decay_halo_device_t(const double *d_rec, const double *d_scale, int n, int reversed, double tol, int step,
-                        int hmax, int phase) {
-    if (n <= 2 * step) return 0;
-    int *d_res = nullptr;
-    if (bsk::dev_malloc((void **)&d_res, 8) != cudaSuccess) return 0;
-    cudaMemset(d_res, 0, 8);
+// Launch the analysis on the default stream; d_res = {need, fail} (zeroed by the caller).
+void decay_halo_launch(const double *d_rec, const double *d_scale, int n, int bw, int reversed, double tol, int step,
+                       int hmax, int phase, int *d_res) {
+    if (bw == 0 || n <= 2 * step) return;
     const int ncand = (n - 1 + step) / step + 1;
-    k_decay_need<BW><<<std::max(1, std::min((ncand + 127) / 128, 148 * 8)), 128>>>(d_rec, d_scale, n, reversed, tol, step,
-                                                                                  hmax, phase, d_res, d_res + 1);
-    int res[2] = {0, 1};
-    cudaError_t e = cudaMemcpy(res, d_res, 8, cudaMemcpyDeviceToHost);
-    bsk::dev_free(d_res);
-    if (e != cudaSuccess || res[1] != 0) return 0;
-    int H = ((res[0] + step - 1) / step) * step;
+    const int grid = std::max(1, std::min((ncand + 127) / 128, 148 * 8));
+    switch (bw) {
+        case 1: k_decay_need<1><<<grid, 128>>>(d_rec, d_scale, n, reversed, tol, step, hmax, phase, d_res, d_res + 1); break;
+        case 2: k_decay_need<2><<<grid, 128>>>(d_rec, d_scale, n, reversed, tol, step, hmax, phase, d_res, d_res + 1); break;
+        case 3: k_decay_need<3><<<grid, 128>>>(d_rec, d_scale, n, reversed, tol, step, hmax, phase, d_res, d_res + 1); break;
+        case 4: k_decay_need<4><<<grid, 128>>>(d_rec, d_scale, n, reversed, tol, step, hmax, phase, d_res, d_res + 1); break;
+        case 5: k_decay_need<5><<<grid, 128>>>(d_rec, d_scale, n, reversed, tol, step, hmax, phase, d_res, d_res + 1); break;
+        case 6: k_decay_need<6><<<grid, 128>>>(d_rec, d_scale, n, reversed, tol, step, hmax, phase, d_res, d_res + 1); break;
+        default: break;
+    }
+}
+// ... and turn {need, fail} (copied back to the host) into the halo
+int decay_halo_finish(int need, int fail, int n, int bw, int step, int hmax) {
+    if (bw == 0) return step;
+    if (n <= 2 * step || bw > 6 || fail != 0) return 0;
+    int H = ((need + step - 1) / step) * step;
     if (H == 0) H = step;
     return H <= hmax ? H : 0;
 }
 
-int decay_halo_device(const double *d_rec, const double *d_scale, int n, int bw, int reversed, double tol, int step,
-                      int hmax, int phase) {
-    switch (bw) {
-        case 0: return step;
-        case 1: return decay_halo_device_t<1>(d_rec, d_scale, n, reversed, tol, step, hmax, phase);
-        case 2: return decay_halo_device_t<2>(d_rec, d_scale, n, reversed, tol, step, hmax, phase);
-        case 3: return decay_halo_device_t<3>(d_rec, d_scale, n, reversed, tol, step, hmax, phase);
-        case 4: return decay_halo_device_t<4>(d_rec, d_scale, n, reversed, tol, step, hmax, phase);
-        case 5: return decay_halo_device_t<5>(d_rec, d_scale, n, reversed, tol, step, hmax, phase);
-        case 6: return decay_halo_device_t<6>(d_rec, d_scale, n, reversed, tol, step, hmax, phase);
-    }
-    return 0;
+int decay_halo_device_impl(const double *d_rec, const double *d_scale, int n, int bw, int reversed, double tol, int step,
+                           int hmax, int phase) {
+    if (bw == 0) return step;
+    if (n <= 2 * step) return 0;
+    int *d_res = nullptr;
+    if (bsk::dev_malloc((void **)&d_res, 8) != cudaSuccess) return 0;
+    cudaMemset(d_res, 0, 8);
+    decay_halo_launch(d_rec, d_scale, n, bw, reversed, tol, step, hmax, phase, d_res);
+    int res[2] = {0, 1};
+    cudaError_t e = cudaMemcpy(res, d_res, 8, cudaMemcpyDeviceToHost);
+    bsk::dev_free(d_res);
+    if (e != cudaSuccess) return 0;
+    return decay_halo_finish(res[0], res[1], n, bw, step, hmax);
 }
 
 // Host version of the same analysis (kept as the readable statement of the bound; BSK_HALO_HOST=1).
@@ -348,6 +358,13 @@ bsk_status solve_dispatch(const bsk_banded *h, double *d_rhs, int64_t nrhs, int 
 
 }  // namespace
 
+namespace bsk {
+int decay_halo_device(const double *d_rec, const double *d_scale, int n, int bw, int reversed, double tol, int step,
+                      int hmax, int phase) {
+    return decay_halo_device_impl(d_rec, d_scale, n, bw, reversed, tol, step, hmax, phase);
+}
+}  // namespace bsk
+
 extern "C" {
 
 bsk_status bsk_collocation_matrix(const bsk_basis *b, const double *d_x, int64_t nx, int32_t deriv,
@@ -415,6 +432,11 @@ bsk_status bsk_collocation_cyclic(const bsk_basis *b, const double *d_x, int64_t
     return BSK_OK;
 }
 
+// Partitioned factorisation (banfac.cuh): used from this many rows on; partition length and warm-up columns
+constexpr int kPartMinRows = 1024;
+constexpr int kPartWarmup = 128;
+inline int part_length(int64_t n) { return (int)std::max<int64_t>(256, (n + 148 * 2 - 1) / (148 * 2)); }
+
 static bsk_status banded_alloc(int64_t n, int32_t l, int32_t u, int32_t device, bsk_banded **out) {
     BSK_REQUIRE(out, BSK_ERR_ARGUMENT, "out is NULL");
     *out = nullptr;
@@ -427,18 +449,33 @@ static bsk_status banded_alloc(int64_t n, int32_t l, int32_t u, int32_t device, 
     h->device = device; h->n = n; h->l = l; h->u = u; h->factored = false; h->halo = 0; h->halo_f = 0;
     h->d_mrec = nullptr; h->mrec_bw = -1; h->mrec_npad = 0;
     h->d_w = h->d_lrow = h->d_urow = h->d_dinv = h->d_diag = h->d_lrec = h->d_urec = nullptr;
-    h->n_pad = 0;
-    size_t nw = (size_t)(l + u + 1) * n, nb = (size_t)std::max(1, l) * n;
-    cudaError_t e = bsk::dev_malloc((void **)&h->d_w, 8 * nw);
-    if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_lrow, 8 * nb);
-    if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_urow, 8 * nb);
-    if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_dinv, 8 * n);
-    if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_diag, 8 * n);
+    h->arena = nullptr; h->d_w2 = h->d_ver = nullptr; h->d_status = nullptr;
+    h->n_pad = (int)((n + 7) / 8 * 8);
+    // ONE device allocation for everything the handle will ever hold (every allocation synchronises)
+    const bool part = l >= 1 && n >= kPartMinRows;
+    const size_t nw = (size_t)(l + u + 1) * n, nb = (size_t)std::max(1, l) * n;
+    const size_t nparts = part ? (size_t)bsk::banfac_part_count((int)n, part_length(n)) : 0;
+    const size_t sizes[10] = {nw, part ? nw : 0, nb, nb, (size_t)n, (size_t)n, (size_t)h->n_pad * bsk::win_lw(l),
+                              (size_t)h->n_pad * bsk::win_uw(l), nparts * (l + 1) * (2 * l + 1), 16};
+    size_t offs[10], total = 0;
+    for (int i = 0; i < 10; ++i) { offs[i] = total; total += (sizes[i] * 8 + 255) / 256 * 256; }
+    cudaError_t e = bsk::dev_malloc(&h->arena, total);
     if (e != cudaSuccess) {
         set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
-        bsk_banded_destroy(h);
+        delete h;
         return BSK_ERR_ALLOC;
     }
+    char *base = (char *)h->arena;
+    h->d_w = (double *)(base + offs[0]);
+    h->d_w2 = part ? (double *)(base + offs[1]) : nullptr;
+    h->d_lrow = (double *)(base + offs[2]);
+    h->d_urow = (double *)(base + offs[3]);
+    h->d_dinv = (double *)(base + offs[4]);
+    h->d_diag = (double *)(base + offs[5]);
+    h->d_lrec = (double *)(base + offs[6]);
+    h->d_urec = (double *)(base + offs[7]);
+    h->d_ver = part ? (double *)(base + offs[8]) : nullptr;
+    h->d_status = (int *)(base + offs[9]);
     *out = h;
     return BSK_OK;
 }
@@ -448,7 +485,12 @@ bsk_status bsk_banded_create(const double *d_band, int64_t n, int32_t l, int32_t
     BSK_REQUIRE(d_band, BSK_ERR_ARGUMENT, "NULL band data");
     bsk_status rc = banded_alloc(n, l, u, device, out);
     if (rc != BSK_OK) return rc;
-    BSK_CUDA(cudaMemcpy((*out)->d_w, d_band, 8 * (size_t)(l + u + 1) * n, cudaMemcpyDeviceToDevice));
+    const cudaError_t ce = cudaMemcpy((*out)->d_w, d_band, 8 * (size_t)(l + u + 1) * n, cudaMemcpyDeviceToDevice);
+    if (ce != cudaSuccess) {
+        bsk_banded_destroy(*out);
+        *out = nullptr;
+        BSK_CUDA(ce);
+    }
     return BSK_OK;
 }
 
@@ -457,70 +499,102 @@ bsk_status bsk_banded_create_host(const double *h_band, int64_t n, int32_t l, in
     BSK_REQUIRE(h_band, BSK_ERR_ARGUMENT, "NULL band data");
     bsk_status rc = banded_alloc(n, l, u, device, out);
     if (rc != BSK_OK) return rc;
-    BSK_CUDA(cudaMemcpy((*out)->d_w, h_band, 8 * (size_t)(l + u + 1) * n, cudaMemcpyHostToDevice));
+    const cudaError_t ce = cudaMemcpy((*out)->d_w, h_band, 8 * (size_t)(l + u + 1) * n, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) {
+        bsk_banded_destroy(*out);
+        *out = nullptr;
+        BSK_CUDA(ce);
+    }
     return BSK_OK;
 }
 
-bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot) {
+// lu!(C).  mode BSK_LU_EXACT: BANFAC's own statements, serial in the column index (bit-identical factors).
+// mode BSK_LU_FAST: from kPartMinRows rows on, the partitioned factorisation of banfac.cuh (factors within
+// ~1e-16 relative of BANFAC's, certified at every partition boundary); anything it cannot certify — and every
+// zero pivot — goes through the serial kernel, which reports the pivot row.  Everything after the elimination
+// (row repack, decay analysis for the single-pass solve, solve records) is enqueued behind it and ONE small
+// device-to-host copy fetches all the results.
+static bsk_status banded_lu_impl(bsk_banded *h, int64_t *info_pivot, bool fast) {
     BSK_REQUIRE(h, BSK_ERR_ARGUMENT, "NULL handle");
     BSK_REQUIRE(!h->factored, BSK_ERR_ARGUMENT, "matrix is already factorised");
     BSK_CUDA(cudaSetDevice(h->device));
     const bool timing = getenv("BSK_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = now();
-    long long *d_info = nullptr;
-    BSK_CUDA(bsk::dev_malloc((void **)&d_info, 8));
-    cudaError_t e = bsk::launch_banfac<double>(h->d_w, h->l, h->u, (int)h->n, d_info, getenv("BSK_LU_SERIAL") != nullptr);
-    long long info = 0;
-    if (e == cudaSuccess) e = cudaMemcpy(&info, d_info, 8, cudaMemcpyDeviceToHost);
-    bsk::dev_free(d_info);
-    if (e != cudaSuccess) { set_error("banded LU failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
+    const int n = (int)h->n, bw = h->l;
+    // status words: [0] partition failure, [1..2] backward halo {need, fail}, [3..4] forward halo, [8..9] BANFAC info
+    int st[16];
+    bool used_part = fast && h->d_w2 != nullptr && getenv("BSK_LU_SERIAL") == nullptr && getenv("BSK_LU_NO_PART") == nullptr;
+    const bool halo_host = getenv("BSK_HALO_HOST") != nullptr;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        BSK_CUDA(cudaMemsetAsync(h->d_status, 0, 64, 0));
+        const double *wf = h->d_w;
+        cudaError_t e;
+        if (used_part) {
+            e = bsk::launch_banfac_part<double>(h->d_w, h->d_w2, h->d_ver, bw, n, part_length(n), kPartWarmup, 1e-14,
+                                                h->d_status, 0);
+            wf = h->d_w2;
+        } else {
+            e = bsk::launch_banfac<double>(h->d_w, h->l, h->u, n, (long long *)(h->d_status + 8), getenv("BSK_LU_SERIAL") != nullptr);
+        }
+        if (e != cudaSuccess) { set_error("banded LU failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
+        int grid = std::max(1, std::min((n + kThreads - 1) / kThreads, 148 * 4));
+        k_repack<<<grid, kThreads>>>(wf, bw, n, h->d_lrow, h->d_urow, h->d_diag, h->d_dinv);
+        BSK_CUDA(cudaGetLastError());
+        if (!halo_host) {
+            // decay bounds for the windowed solve: backward recurrence of U, and the forward recurrence of the
+            // unit-diagonal L walked bottom-up (forward sweeps start at rows f0 = 0 mod 8)
+            decay_halo_launch(h->d_urow, h->d_dinv, n, bw, 0, 1e-17, 8, 448, 0, h->d_status + 1);
+            decay_halo_launch(h->d_lrow, nullptr, n, bw, 1, 1e-17, 8, 448, n % 8, h->d_status + 3);
+            BSK_CUDA(cudaGetLastError());
+        }
+        bsk_status rc = windowed_prepare(h, wf);
+        if (rc != BSK_OK) return rc;
+        BSK_CUDA(cudaMemcpy(st, h->d_status, 64, cudaMemcpyDeviceToHost));
+        if (used_part && st[0] != 0) { used_part = false; continue; }   // not certified: serial kernel on the intact original
+        break;
+    }
     const double t_lu = now();
+    long long info = 0;
+    memcpy(&info, &st[8], 8);
+    if (used_part) info = 0;
     if (info_pivot) *info_pivot = info;
     if (info != 0) {
         set_error("ZeroPivotException(%lld)", info);
         return BSK_ERR_ZERO_PIVOT;
     }
-    const int n = (int)h->n, bw = h->l;
-    int grid = std::max(1, std::min((n + kThreads - 1) / kThreads, 148 * 4));
-    k_repack<<<grid, kThreads>>>(h->d_w, bw, n, h->d_lrow, h->d_urow, h->d_diag, h->d_dinv);
-    BSK_CUDA(cudaGetLastError());
-    // decay bound for the windowed solve
-    const double t_pack = now();
-    const bool halo_host = getenv("BSK_HALO_HOST") != nullptr;
+    if (used_part) std::swap(h->d_w, h->d_w2);                 // the factors live in the second buffer
     h->halo_f = 0;
     if (!halo_host) {
-        h->halo = decay_halo_device(h->d_urow, h->d_dinv, n, bw, 0, 1e-17, 8, 448, 0);
-        // forward recurrence (unit-diagonal L) walked bottom-up; forward sweeps start at rows f0 = 0 mod 8
-        if (h->halo > 0) h->halo_f = decay_halo_device(h->d_lrow, nullptr, n, bw, 1, 1e-17, 8, 448, n % 8);
+        h->halo = decay_halo_finish(st[1], st[2], n, bw, 8, 448);
+        if (h->halo > 0) h->halo_f = decay_halo_finish(st[3], st[4], n, bw, 8, 448);
     } else {
         std::vector<double> urow((size_t)std::max(1, bw) * n), dinv(n);
         BSK_CUDA(cudaMemcpy(urow.data(), h->d_urow, 8 * (size_t)std::max(1, bw) * n, cudaMemcpyDeviceToHost));
         BSK_CUDA(cudaMemcpy(dinv.data(), h->d_dinv, 8 * (size_t)n, cudaMemcpyDeviceToHost));
         h->halo = decay_halo(urow, dinv, n, bw, 1e-17, 8, 448);
+        if (h->halo > 0 && bw > 0) {
+            // same bound for the forward recurrence (unit-diagonal L), by reversing the row order
+            std::vector<double> lrow((size_t)bw * n), lrev((size_t)bw * n), ones(n, 1.0);
+            BSK_CUDA(cudaMemcpy(lrow.data(), h->d_lrow, 8 * (size_t)bw * n, cudaMemcpyDeviceToHost));
+            for (int r = 0; r < n; ++r)
+                for (int j = 0; j < bw; ++j) lrev[(size_t)(n - 1 - r) * bw + j] = lrow[(size_t)r * bw + j];
+            h->halo_f = decay_halo(lrev, ones, n, bw, 1e-17, 8, 448, n % 8);
+        }
     }
-    if (halo_host && h->halo > 0 && bw > 0) {
-        // same bound for the forward recurrence (unit-diagonal L), by reversing the row order
-        std::vector<double> lrow((size_t)bw * n), lrev((size_t)bw * n), ones(n, 1.0);
-        BSK_CUDA(cudaMemcpy(lrow.data(), h->d_lrow, 8 * (size_t)bw * n, cudaMemcpyDeviceToHost));
-        for (int r = 0; r < n; ++r)
-            for (int j = 0; j < bw; ++j) lrev[(size_t)(n - 1 - r) * bw + j] = lrow[(size_t)r * bw + j];
-        h->halo_f = decay_halo(lrev, ones, n, bw, 1e-17, 8, 448, n % 8);   // forward sweeps start at rows f0 = 0 mod 8
-    } else if (bw == 0) {
-        h->halo_f = 8;
-    }
-    const double t_halo = now();
-    if (h->halo > 0) {
-        bsk_status rc = windowed_prepare(h);
-        if (rc != BSK_OK) return rc;
-    }
-    if (timing) {
-        cudaDeviceSynchronize();
-        fprintf(stderr, "bsk_banded_lu n=%d bw=%d: BANFAC %.2f ms, repack + copies %.2f ms, halo analysis %.2f ms, records %.2f ms\n",
-                n, bw, t_lu - t_start, t_pack - t_lu, t_halo - t_pack, now() - t_halo);
-    }
+    if (bw == 0) h->halo_f = 8;
+    if (timing)
+        fprintf(stderr, "bsk_banded_lu n=%d bw=%d %s: elimination + repack + decay analysis + records %.3f ms, halo %d / %d\n",
+                n, bw, used_part ? "partitioned" : "serial", t_lu - t_start, h->halo, h->halo_f);
     h->factored = true;
     return BSK_OK;
+}
+
+bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot) { return banded_lu_impl(h, info_pivot, false); }
+
+bsk_status bsk_banded_lu_mode(bsk_banded *h, int32_t mode, int64_t *info_pivot) {
+    BSK_REQUIRE(mode == BSK_LU_EXACT || mode == BSK_LU_FAST, BSK_ERR_ARGUMENT, "unknown LU mode %d", mode);
+    return banded_lu_impl(h, info_pivot, mode == BSK_LU_FAST);
 }
 
 bsk_status bsk_banded_data(const bsk_banded *h, double *h_out) {
@@ -599,13 +673,7 @@ bsk_status bsk_banded_matvec_solve(const bsk_banded *lu, const bsk_banded *Lm, c
 bsk_status bsk_banded_destroy(bsk_banded *h) {
     if (!h) return BSK_OK;
     cudaSetDevice(h->device);
-    if (h->d_w) bsk::dev_free(h->d_w);
-    if (h->d_lrow) bsk::dev_free(h->d_lrow);
-    if (h->d_urow) bsk::dev_free(h->d_urow);
-    if (h->d_lrec) bsk::dev_free(h->d_lrec);
-    if (h->d_urec) bsk::dev_free(h->d_urec);
-    if (h->d_dinv) bsk::dev_free(h->d_dinv);
-    if (h->d_diag) bsk::dev_free(h->d_diag);
+    if (h->arena) bsk::dev_free(h->arena);                    // every array of the handle lives in it
     if (h->d_mrec) bsk::dev_free(h->d_mrec);
     delete h;
     return BSK_OK;

@@ -10,6 +10,7 @@
 // The Float64 path has its own, more elaborate kernels (bsk_solve.cu, bsk_solve_win.cu).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "banfac.cuh"
@@ -17,17 +18,6 @@
 #include "handles.cuh"
 
 using namespace bsk;
-
-struct bsk_banded_f32 {
-    int device;
-    int64_t n;
-    int l, u;
-    float *d_w;           // (l+u+1) x n column-major: matrix, LU factors after bsk_banded_f32_lu
-    float *d_lrow;        // n x l: lrow[i][j-1] = L(i, i-j)
-    float *d_urow;        // n x u: urow[i][j-1] = U(i, i+j)
-    float *d_diag;        // n:     U(i, i)
-    bool factored;
-};
 
 struct bsk_cyclic_f32 {
     int device;
@@ -144,6 +134,12 @@ __global__ void k_repack_f32(const float *__restrict__ w, int bw, int n, float *
     }
 }
 
+// float factors -> double copies for the decay analysis (shared with the Float64 path)
+__global__ void k_f32_to_f64(const float *__restrict__ in, double *__restrict__ out, int64_t n, int invert) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = invert ? 1.0 / (double)in[i] : (double)in[i];
+}
+
 template <int BW>
 bsk_status solve_f32(const bsk_banded_f32 *h, float *d_rhs, int64_t nrhs, cudaStream_t st) {
     // one thread per column walks all n rows: small CTAs spread the columns evenly over the SMs
@@ -256,6 +252,8 @@ bsk_status bsk_banded_f32_destroy(bsk_banded_f32 *h) {
     cudaSetDevice(h->device);
     for (float *p : {h->d_w, h->d_lrow, h->d_urow, h->d_diag})
         if (p) bsk::dev_free(p);
+    if (h->d_lrec) bsk::dev_free(h->d_lrec);
+    if (h->d_urec) bsk::dev_free(h->d_urec);
     delete h;
     return BSK_OK;
 }
@@ -272,6 +270,7 @@ static bsk_status banded_f32_alloc(int64_t n, int32_t l, int32_t u, int32_t devi
     bsk_banded_f32 *h = new bsk_banded_f32();
     h->device = device; h->n = n; h->l = l; h->u = u; h->factored = false;
     h->d_w = h->d_lrow = h->d_urow = h->d_diag = nullptr;
+    h->d_lrec = h->d_urec = nullptr; h->n_pad = 0; h->halo = 0; h->halo_f = 0;
     const size_t nw = (size_t)(l + u + 1) * n, nb = (size_t)std::max(1, l) * n;
     cudaError_t e = bsk::dev_malloc((void **)&h->d_w, 4 * nw);
     if (e == cudaSuccess) e = bsk::dev_malloc((void **)&h->d_lrow, 4 * nb);
@@ -324,8 +323,41 @@ bsk_status bsk_banded_f32_lu(bsk_banded_f32 *h, int64_t *info_pivot) {
     const int grid = std::max(1, std::min((n + kThreads - 1) / kThreads, 148 * 4));
     k_repack_f32<<<grid, kThreads>>>(h->d_w, h->l, n, h->d_lrow, h->d_urow, h->d_diag);
     BSK_CUDA(cudaGetLastError());
+    // Decay halos for the single-pass solve (same analysis as the Float64 path, on double copies of the
+    // Float32 factors).  Tolerance: the start-state error of a restarted recurrence must stay below
+    // 2^-34 (6e-11) of the solution's magnitude, i.e. 2^-10 of a Float32 ulp.
+    h->halo = h->halo_f = 0;
+    const int bw = h->l;
+    if (bw == 0) {
+        h->halo = h->halo_f = 8;
+    } else if (getenv("BSK_F32_NO_WINDOWED") == nullptr) {
+        double *d_u = nullptr, *d_l = nullptr, *d_dinv = nullptr;
+        cudaError_t ce = bsk::dev_malloc((void **)&d_u, 8 * (size_t)bw * n);
+        if (ce == cudaSuccess) ce = bsk::dev_malloc((void **)&d_l, 8 * (size_t)bw * n);
+        if (ce == cudaSuccess) ce = bsk::dev_malloc((void **)&d_dinv, 8 * (size_t)n);
+        if (ce == cudaSuccess) {
+            const int g2 = std::max(1, std::min((bw * n + kThreads - 1) / kThreads, 148 * 8));
+            k_f32_to_f64<<<g2, kThreads>>>(h->d_urow, d_u, (int64_t)bw * n, 0);
+            k_f32_to_f64<<<g2, kThreads>>>(h->d_lrow, d_l, (int64_t)bw * n, 0);
+            k_f32_to_f64<<<g2, kThreads>>>(h->d_diag, d_dinv, (int64_t)n, 1);
+            h->halo = bsk::decay_halo_device(d_u, d_dinv, n, bw, 0, 6e-11, 8, 448, 0);
+            if (h->halo > 0) h->halo_f = bsk::decay_halo_device(d_l, nullptr, n, bw, 1, 6e-11, 8, 448, n % 8);
+        }
+        for (double *p : {d_u, d_l, d_dinv})
+            if (p) bsk::dev_free(p);
+    }
+    if (h->halo > 0) {
+        bsk_status rc = bsk::windowed_prepare_f32(h);
+        if (rc != BSK_OK) return rc;
+    }
     BSK_CUDA(cudaDeviceSynchronize());
     h->factored = true;
+    return BSK_OK;
+}
+
+bsk_status bsk_banded_f32_halo(const bsk_banded_f32 *h, int32_t *halo) {
+    BSK_REQUIRE(h && halo, BSK_ERR_ARGUMENT, "NULL argument");
+    *halo = h->halo;
     return BSK_OK;
 }
 
@@ -336,13 +368,45 @@ bsk_status bsk_banded_f32_data(const bsk_banded_f32 *h, float *h_out) {
     return BSK_OK;
 }
 
-bsk_status bsk_banded_f32_solve(const bsk_banded_f32 *h, float *d_rhs, int64_t nrhs, void *stream) {
+bsk_status bsk_banded_f32_solve(const bsk_banded_f32 *h, float *d_rhs, int64_t nrhs, int32_t algo, void *stream) {
     BSK_REQUIRE(h && (nrhs == 0 || d_rhs), BSK_ERR_ARGUMENT, "NULL argument");
     BSK_REQUIRE(h->factored, BSK_ERR_ARGUMENT, "matrix is not factorised: call bsk_banded_f32_lu first");
+    BSK_REQUIRE(algo >= 0 && algo <= 2, BSK_ERR_ARGUMENT, "unknown algo %d", algo);
     BSK_REQUIRE(nrhs >= 0, BSK_ERR_DIMENSION, "negative number of right-hand sides");
     if (nrhs == 0) return BSK_OK;
     BSK_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (algo == BSK_SOLVE_WINDOWED && h->halo == 0) {
+        set_error("windowed solve unavailable: the decay bound of U^{-1} was not met for this matrix");
+        return BSK_ERR_UNSUPPORTED;
+    }
+    // Single pass (AUTO when the halo was validated): column PAIRS per lane, 64 columns per warp; the
+    // block must be 128-byte aligned with rows a multiple of 16 bytes apart (TMA tiles: nrhs % 4 == 0); columns
+    // beyond the last full group of 64 go through the BANSLV-order kernels below.
+    if ((algo == BSK_SOLVE_WINDOWED || (algo == BSK_SOLVE_AUTO && h->halo > 0)) && nrhs >= 64 && nrhs % 4 == 0 &&
+        (((uintptr_t)d_rhs) & 127) == 0) {
+        const int64_t ngroups = nrhs / 64;
+        bsk_status rc = bsk::windowed_solve_f32(h, d_rhs, ngroups, nrhs / 2, st);
+        if (rc == BSK_OK) {
+            const int64_t done = ngroups * 64, rest = nrhs - done;
+            if (rest == 0) return BSK_OK;
+            constexpr int kBlock = 64;
+            const int grid = (int)((rest + kBlock - 1) / kBlock);
+#define BSK_F32_REST(BWV)                                                                                                      \
+    case BWV:                                                                                                                  \
+        if (BWV > 0) k_banslv_sweep<BWV, 32, +1, float><<<grid, kBlock, 0, st>>>(h->d_lrow, h->d_diag, d_rhs + done, rest, nrhs, (int)h->n); \
+        k_banslv_sweep<BWV, 32, -1, float><<<grid, kBlock, 0, st>>>(h->d_urow, h->d_diag, d_rhs + done, rest, nrhs, (int)h->n); \
+        break;
+            switch (h->l) { BSK_F32_REST(0) BSK_F32_REST(1) BSK_F32_REST(2) BSK_F32_REST(3) BSK_F32_REST(4) BSK_F32_REST(5) BSK_F32_REST(6) }
+#undef BSK_F32_REST
+            BSK_CUDA(cudaGetLastError());
+            return BSK_OK;
+        }
+        if (algo == BSK_SOLVE_WINDOWED || rc != BSK_ERR_UNSUPPORTED) return rc;
+    } else if (algo == BSK_SOLVE_WINDOWED) {
+        set_error("windowed Float32 solve needs >= 64 columns, a column count that is a multiple of 4 and a 128-byte aligned block");
+        return BSK_ERR_UNSUPPORTED;
+    }
     switch (h->l) {
         case 0: return solve_f32<0>(h, d_rhs, nrhs, st);
         case 1: return solve_f32<1>(h, d_rhs, nrhs, st);

@@ -25,6 +25,7 @@
 // with conflict-free broadcast loads.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include <cuda.h>            // CUtensorMap (types only; the encoder is fetched at run time)
@@ -39,8 +40,8 @@ namespace {
 constexpr int G = 8;   // rows per chunk
 
 template <int BW> struct RecW {
-    static constexpr int LW = ((BW + 1 + 1) / 2) * 2;           // {l_BW .. l_1, dinv} padded to even
-    static constexpr int UW = BW == 0 ? 2 : ((BW + 1) / 2) * 2;  // {u'_BW .. u'_1} padded to even
+    static constexpr int LW = bsk::win_lw(BW);                  // {l_BW .. l_1, dinv} padded to even
+    static constexpr int UW = bsk::win_uw(BW);                  // {u'_BW .. u'_1} padded to even
 };
 
 // Column-oriented ("right-looking", exactly BANSLV's own loop order, matrix.jl:246-266) records:
@@ -325,16 +326,44 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, double *v) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
-constexpr int kTmemCols = 256;            // per CTA (power of two); 2 CTAs per SM
-constexpr int kTmemRows = kTmemCols / 2;  // ring rows per lane (one double = two 32-bit columns)
+// Arithmetic on the 8-byte lane elements of the ring.  ArF64: one double per lane.  ArF32x2: TWO
+// Float32 right-hand sides per lane, packed in the 64 bits of a `double` register and updated with the
+// packed fma.rn.f32x2 / mul.rn.f32x2 of sm_100 — data movement (TMA tiles of 32 x 8-byte elements, TMEM
+// x16 transfers, 8-byte stores) is bit-for-bit the Float64 kernel's, each instruction now serves two
+// columns.  The packed FMA has no operand negation, so the Float32 records hold the multipliers NEGATED
+// (and duplicated in both halves).
+struct ArF64 {
+    static __device__ __forceinline__ double fnma(double z, double r, double t) { return fma(-z, r, t); }   // t - z r
+    static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+};
+struct ArF32x2 {
+    static __device__ __forceinline__ double fnma(double z, double nr, double t) {                          // t + z (-r)
+        unsigned long long o;
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(o) : "l"(__double_as_longlong(z)), "l"(__double_as_longlong(nr)),
+                                               "l"(__double_as_longlong(t)));
+        return __longlong_as_double((long long)o);
+    }
+    static __device__ __forceinline__ double mul(double a, double b) {
+        unsigned long long o;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(o) : "l"(__double_as_longlong(a)), "l"(__double_as_longlong(b)));
+        return __longlong_as_double((long long)o);
+    }
+};
+
+// TMEM columns per CTA = 512 / OCC (OCC resident CTAs of 4 warps per SM); ring rows per lane = half of that
+// (one 8-byte element = two 32-bit columns).
+template <int OCC> struct TmemCfg {
+    static constexpr int kCols = 512 / OCC;
+    static constexpr int kRows = kCols / 2;
+};
 
 // FUSED = 1: the right-hand side is produced on the fly as  y = Lm * u  (Lm: a second banded matrix
 // with at most BW sub/super-diagonals, row records `mrec`; u read through `tmap`, never modified)
 // and the solution goes to `rhs` (a different buffer): the `mul!` + `ldiv!` pair of a collocation
 // time step (examples/heat.jl:314-328) in one pass over HBM.  Needs 2 BW <= 8 so that the u rows
 // one 8-row chunk of y depends on are exactly the chunk being eliminated and the next one.
-template <int BW, int PG, int FUSED>
-__global__ void __launch_bounds__(128, 2)
+template <int BW, int PG, int FUSED, typename AR, int OCC>
+__global__ void __launch_bounds__(128, OCC)
 k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
               double *__restrict__ rhs, int64_t ngroups, int64_t ld, int n, int n_pad_all, int M, int H,
               const __grid_constant__ CUtensorMap tmap, int nseg, int SEG, int HF,
@@ -344,7 +373,8 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
     constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
     constexpr int MW = 2 * BW + 2;                            // {Lm(r,r-BW) .. Lm(r,r+BW), pad}
     constexpr int MWS = FUSED ? PG * G * MW : 0;
-    constexpr int RWT = kTmemRows;                            // TMEM ring rows
+    constexpr int kTmemCols = TmemCfg<OCC>::kCols;
+    constexpr int RWT = TmemCfg<OCC>::kRows;                  // TMEM ring rows
     constexpr int RC = RWT + PG * G;                          // rows of backward records kept in smem
     // per-warp shared memory (doubles): stage[PG][8][32] | cur[RC][UW] | cfw[PG][8*LW] | cmv[PG][8*MW] | mbar[PG]
     constexpr int WARP_D = ((PG * G * TB + RC * UW + PG * G * LW + MWS + PG + 15) / 16) * 16;   // 128-byte multiple
@@ -504,8 +534,8 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
                     for (int q = 0; q < G; ++q) {
                         const double z = t[q];
 #pragma unroll
-                        for (int j = 1; j <= BW; ++j) t[q + j] = fma(-z, rec[q][j - 1], t[q + j]);
-                        zs[q] = z * rec[q][BW];
+                        for (int j = 1; j <= BW; ++j) t[q + j] = AR::fnma(z, rec[q][j - 1], t[q + j]);
+                        zs[q] = AR::mul(z, rec[q][BW]);
                     }
                     tmem_st8(tbase + (unsigned)(f_slot * 2), zs);
 #pragma unroll
@@ -554,8 +584,8 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
                         const double xq = t[q];
 #pragma unroll
                         for (int j = 1; j <= BW; ++j) {
-                            if (q - j >= 0) t[q - j] = fma(-xq, rec[q][j - 1], t[q - j]);
-                            else la[j - q - 1] = fma(-xq, rec[q][j - 1], la[j - q - 1]);
+                            if (q - j >= 0) t[q - j] = AR::fnma(xq, rec[q][j - 1], t[q - j]);
+                            else la[j - q - 1] = AR::fnma(xq, rec[q][j - 1], la[j - q - 1]);
                         }
                     }
 #pragma unroll
@@ -582,15 +612,15 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
 }
 
 template <int BW>
-bsk_status prepare_t(bsk_banded *h) {
+bsk_status prepare_t(bsk_banded *h, const double *w) {
     constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
     const int n = (int)h->n;
     const int n_pad = ((n + G - 1) / G) * G;
     h->n_pad = n_pad;
-    BSK_CUDA(bsk::dev_malloc((void **)&h->d_lrec, sizeof(double) * (size_t)n_pad * LW));
-    BSK_CUDA(bsk::dev_malloc((void **)&h->d_urec, sizeof(double) * (size_t)n_pad * UW));
+    if (!h->d_lrec) BSK_CUDA(bsk::dev_malloc((void **)&h->d_lrec, sizeof(double) * (size_t)n_pad * LW));
+    if (!h->d_urec) BSK_CUDA(bsk::dev_malloc((void **)&h->d_urec, sizeof(double) * (size_t)n_pad * UW));
     int grid = std::max(1, std::min((n_pad + 255) / 256, 148 * 4));
-    k_win_repack<BW><<<grid, 256>>>(h->d_w, n, n_pad, h->d_lrec, h->d_urec);
+    k_win_repack<BW><<<grid, 256>>>(w, n, n_pad, h->d_lrec, h->d_urec);
     BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }
@@ -628,11 +658,56 @@ bool make_rhs_tensor_map(CUtensorMap *tm, double *d_rhs, int64_t ncols, int64_t 
     return r == CUDA_SUCCESS;
 }
 
+// What the solve kernels need to know about a factorised matrix (Float64 handle or Float32 handle).
+struct WinMat {
+    int device;
+    int n, n_pad;
+    int halo, halo_f;
+    const double *lrec, *urec;       // 8-byte records (Float32: two packed, negated floats per entry)
+};
+
+template <int BW, typename AR, int OCC>
+bsk_status launch_tmem(const WinMat &h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st, int M, int H,
+                       const CUtensorMap &tmap, int nseg, int SEG, int HF, const double *scratch,
+                       const CUtensorMap &tmap_s, const double *mrec, const double *d_u) {
+    constexpr int PG = 4;
+    constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
+    constexpr int RC = TmemCfg<OCC>::kRows + PG * G;
+    const int64_t nwork = ngroups * nseg;
+    const int64_t wslots = (int64_t)sm_count(h.device) * 4 * OCC;
+    const int64_t wr = (nwork + wslots - 1) / wslots;
+    const int64_t nwarps = (nwork + wr - 1) / wr;
+    const int gridt = (int)std::max<int64_t>(1, (nwarps + 3) / 4);
+    if (mrec != nullptr) {
+        if constexpr (2 * BW <= G && OCC == 2 && std::is_same<AR, ArF64>::value) {
+            constexpr int MW = 2 * BW + 2;
+            const size_t smem_f = (size_t)4 * (((PG * G * 32 + RC * UW + PG * G * LW + PG * G * MW + PG + 15) / 16) * 16) * sizeof(double);
+            auto kf = k_banded_tmem<BW, PG, 1, AR, OCC>;
+            BSK_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+            kf<<<gridt, 128, smem_f, st>>>(h.lrec, h.urec, d_rhs, ngroups, ld, h.n, h.n_pad, M, H, tmap, nseg, SEG, HF,
+                                           nullptr, tmap_s, mrec, d_u);
+        } else {
+            set_error("fused mat-vec + solve unavailable for this shape");
+            return BSK_ERR_UNSUPPORTED;
+        }
+    } else {
+        const size_t smem_t = (size_t)4 * (((PG * G * 32 + RC * UW + PG * G * LW + PG + 15) / 16) * 16) * sizeof(double);
+        auto kt = k_banded_tmem<BW, PG, 0, AR, OCC>;
+        BSK_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        kt<<<gridt, 128, smem_t, st>>>(h.lrec, h.urec, d_rhs, ngroups, ld, h.n, h.n_pad, M, H, tmap, nseg, SEG, HF,
+                                       scratch, tmap_s, nullptr, nullptr);
+    }
+    return BSK_OK;
+}
+
 // mrec / d_u non-null: fused  d_rhs = (LU)^{-1} (Lm * d_u)  (d_u is only read).
-template <int BW>
-bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st,
+// `d_rhs`, `ld`, `ngroups` are in 8-byte lane elements: doubles, or PAIRS of Float32 columns (AR = ArF32x2).
+template <int BW, typename AR>
+bsk_status solve_t(const WinMat &hm, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st,
                    const double *mrec = nullptr, const double *d_u = nullptr) {
+    const WinMat *h = &hm;
     const bool fused = mrec != nullptr;
+    constexpr bool kF64 = std::is_same<AR, ArF64>::value;
     constexpr int PG = 4;                                     // 4 chunks x 8 rows in flight
     constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
     // halo validated at factor time (multiple of 8); the kernel restarts every M rows and needs
@@ -646,16 +721,16 @@ bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t 
     if (const char *env = getenv("BSK_WINDOW_CTAS")) per_sm_cap = std::max(1, atoi(env));
     const int H = ((h->halo + M - 1) / M) * M;
     const size_t smem = ((size_t)(M + H + PG * G) * (32 + UW) + (size_t)PG * G * LW + PG) * sizeof(double);
-    auto kern = k_banded_windowed<BW, PG>;
-    if (smem > 48 * 1024)
-        BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(per_sm_cap, (226 * 1024) / (smem + 1024)));
     const int64_t slots = (int64_t)sm_count(h->device) * per_sm;
+    // TMEM ring: 4 resident CTAs per SM (16 warps, 64 ring rows per lane) when the window fits, else 2 (128 rows)
+    int occ = (M + H <= TmemCfg<4>::kRows && !fused) ? 4 : 2;
+    if (const char *env = getenv("BSK_TMEM_OCC")) { if (atoi(env) == 2) occ = 2; }
+    const bool tmem_ok = M + H <= TmemCfg<2>::kRows && getenv("BSK_NO_TMEM") == nullptr && get_encoder() != nullptr;
     // Row segments: only when there are too few column groups to fill the machine and the forward
     // recurrence decays too (halo_f > 0).  Redundant work per segment: (HF + H) rows.
     int nseg = 1, SEG = h->n_pad, HF = 0;
-    const bool tmem_ok = M + H <= kTmemRows && getenv("BSK_NO_TMEM") == nullptr && get_encoder() != nullptr;
-    const int64_t fill = tmem_ok ? (int64_t)sm_count(h->device) * 8 * 4 / 5     // 8 warps/SM, >= 80 % of them busy
+    const int64_t fill = tmem_ok ? (int64_t)sm_count(h->device) * 4 * occ * 4 / 5     // >= 80 % of the warp slots busy
                                  : (slots * 3 + 1) / 2;
     if (h->halo_f > 0 && ngroups < fill && getenv("BSK_NO_SEGMENTS") == nullptr) {
         HF = ((h->halo_f + M - 1) / M) * M;
@@ -675,8 +750,9 @@ bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t 
     memset(&tmap_s, 0, sizeof(tmap_s));
     int use_tmap = make_rhs_tensor_map(&tmap, fused ? const_cast<double *>(d_u) : d_rhs, ngroups * 32, ld, h->n) ? 1 : 0;
     double *scratch = nullptr;
-    if (fused && !(use_tmap && tmem_ok && 2 * BW <= G)) {
-        set_error("fused mat-vec + solve unavailable for this shape");
+    if ((fused || !kF64) && !(use_tmap && tmem_ok && (!fused || 2 * BW <= G))) {
+        set_error(fused ? "fused mat-vec + solve unavailable for this shape"
+                        : "single-pass Float32 solve unavailable for this shape");
         return BSK_ERR_UNSUPPORTED;
     }
     if (nseg > 1 && !fused) {
@@ -686,45 +762,94 @@ bsk_status solve_t(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t 
         // every synchronisation, which makes the next cudaMallocAsync cost ~1 ms)
         ensure_pool(h->device);
         BSK_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * (size_t)(nseg - 1) * HS * ld, st));
-        for (int b = 0; b + 1 < nseg; ++b) {
+        cudaError_t ce = cudaSuccess;
+        for (int b = 0; b + 1 < nseg && ce == cudaSuccess; ++b) {
             const int64_t kb = (int64_t)(b + 1) * SEG;
             const int64_t r0 = kb - HF, r1 = std::min<int64_t>(h->n, kb + H);
             if (r1 > r0)
-                BSK_CUDA(cudaMemcpyAsync(scratch + (size_t)b * HS * ld, d_rhs + r0 * ld, sizeof(double) * (size_t)(r1 - r0) * ld,
-                                         cudaMemcpyDeviceToDevice, st));
+                ce = cudaMemcpyAsync(scratch + (size_t)b * HS * ld, d_rhs + r0 * ld, sizeof(double) * (size_t)(r1 - r0) * ld,
+                                     cudaMemcpyDeviceToDevice, st);
+        }
+        if (ce != cudaSuccess) {                      // do not leak the scratch block on a failed copy
+            cudaFreeAsync(scratch, st);
+            BSK_CUDA(ce);
         }
         if (use_tmap && !make_rhs_tensor_map(&tmap_s, scratch, ngroups * 32, ld, (int64_t)(nseg - 1) * HS)) use_tmap = 0;
     }
+    bsk_status rc = BSK_OK;
     if (use_tmap && tmem_ok) {
-        // TMEM-resident ring: 2 CTAs x 4 warps per SM
-        constexpr int RC = kTmemRows + PG * G;
-        const size_t smem_t = (size_t)4 * (((PG * G * 32 + RC * UW + PG * G * LW + PG + 15) / 16) * 16) * sizeof(double);
-        const int64_t wslots = (int64_t)sm_count(h->device) * 8;
-        const int64_t wr = (nwork + wslots - 1) / wslots;
-        const int64_t nwarps = (nwork + wr - 1) / wr;
-        const int gridt = (int)std::max<int64_t>(1, (nwarps + 3) / 4);
-        if (fused) {
-            if constexpr (2 * BW <= G) {
-                constexpr int MW = 2 * BW + 2;
-                const size_t smem_f = (size_t)4 * (((PG * G * 32 + RC * UW + PG * G * LW + PG * G * MW + PG + 15) / 16) * 16) * sizeof(double);
-                auto kf = k_banded_tmem<BW, PG, 1>;
-                BSK_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-                kf<<<gridt, 128, smem_f, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap,
-                                               nseg, SEG, HF, nullptr, tmap_s, mrec, d_u);
-            }
-        } else {
-            auto kt = k_banded_tmem<BW, PG, 0>;
-            BSK_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-            kt<<<gridt, 128, smem_t, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap,
-                                           nseg, SEG, HF, scratch, tmap_s, nullptr, nullptr);
-        }
+        if (occ == 4) rc = launch_tmem<BW, AR, 4>(*h, d_rhs, ngroups, ld, st, M, H, tmap, nseg, SEG, HF, scratch, tmap_s, mrec, d_u);
+        else rc = launch_tmem<BW, AR, 2>(*h, d_rhs, ngroups, ld, st, M, H, tmap, nseg, SEG, HF, scratch, tmap_s, mrec, d_u);
+    } else if constexpr (kF64) {
+        auto kern = k_banded_windowed<BW, PG>;
+        if (smem > 48 * 1024)
+            rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess ? BSK_OK : BSK_ERR_CUDA;
+        if (rc == BSK_OK)
+            kern<<<grid, 32, smem, st>>>(h->lrec, h->urec, d_rhs, ngroups, ld, h->n, h->n_pad, M, H, tmap, use_tmap,
+                                         nseg, SEG, HF, scratch, tmap_s);
     } else {
-        kern<<<grid, 32, smem, st>>>(h->d_lrec, h->d_urec, d_rhs, ngroups, ld, (int)h->n, h->n_pad, M, H, tmap, use_tmap,
-                                     nseg, SEG, HF, scratch, tmap_s);
+        set_error("single-pass Float32 solve needs the TMEM kernel");
+        rc = BSK_ERR_UNSUPPORTED;
     }
     cudaError_t le = cudaGetLastError();
     if (scratch) cudaFreeAsync(scratch, st);
+    if (rc != BSK_OK) return rc;
     BSK_CUDA(le);
+    return BSK_OK;
+}
+
+inline WinMat winmat(const bsk_banded *h) {
+    WinMat m;
+    m.device = h->device; m.n = (int)h->n; m.n_pad = h->n_pad; m.halo = h->halo; m.halo_f = h->halo_f;
+    m.lrec = h->d_lrec; m.urec = h->d_urec;
+    return m;
+}
+inline WinMat winmat(const bsk_banded_f32 *h) {
+    WinMat m;
+    m.device = h->device; m.n = (int)h->n; m.n_pad = h->n_pad; m.halo = h->halo; m.halo_f = h->halo_f;
+    m.lrec = h->d_lrec; m.urec = h->d_urec;
+    return m;
+}
+
+// Float32 factors -> records of the single-pass kernel: every entry is a pair of identical floats, the
+// multipliers NEGATED (see ArF32x2); same column-oriented layout as k_win_repack.
+template <int BW>
+__global__ void k_win_repack_f32(const float *__restrict__ w, int n, int n_pad, float2 *__restrict__ lrec,
+                                 float2 *__restrict__ urec) {
+    constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
+    const int nroww = 2 * BW + 1, middle = BW + 1;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x + 1; r <= n_pad; r += gridDim.x * blockDim.x) {
+        float2 *lr = lrec + (size_t)(r - 1) * LW;
+        float2 *ur = urec + (size_t)(r - 1) * UW;
+        for (int j = 0; j < LW; ++j) lr[j] = make_float2(0.0f, 0.0f);
+        for (int j = 0; j < UW; ++j) ur[j] = make_float2(0.0f, 0.0f);
+        if (r > n) { lr[BW] = make_float2(1.0f, 1.0f); continue; }
+        const float dinv = 1.0f / w[(middle - 1) + (size_t)(r - 1) * nroww];
+        lr[BW] = make_float2(dinv, dinv);
+        for (int j = 1; j <= BW; ++j) {
+            if (r + j <= n) {
+                const float v = -w[(middle + j - 1) + (size_t)(r - 1) * nroww];
+                lr[j - 1] = make_float2(v, v);
+            }
+            if (r - j >= 1) {
+                const float v = -(w[(middle - j - 1) + (size_t)(r - 1) * nroww] / w[(middle - 1) + (size_t)(r - j - 1) * nroww]);
+                ur[j - 1] = make_float2(v, v);
+            }
+        }
+    }
+}
+
+template <int BW>
+bsk_status prepare_f32_t(bsk_banded_f32 *h) {
+    constexpr int LW = RecW<BW>::LW, UW = RecW<BW>::UW;
+    const int n = (int)h->n;
+    const int n_pad = ((n + G - 1) / G) * G;
+    h->n_pad = n_pad;
+    BSK_CUDA(bsk::dev_malloc((void **)&h->d_lrec, sizeof(double) * (size_t)n_pad * LW));
+    BSK_CUDA(bsk::dev_malloc((void **)&h->d_urec, sizeof(double) * (size_t)n_pad * UW));
+    int grid = std::max(1, std::min((n_pad + 255) / 256, 148 * 4));
+    k_win_repack_f32<BW><<<grid, 256>>>(h->d_w, n, n_pad, (float2 *)h->d_lrec, (float2 *)h->d_urec);
+    BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }
 
@@ -757,25 +882,26 @@ bsk_status windowed_matrec(const bsk_banded *Lm, int bw, int n_pad, double **out
 bsk_status windowed_solve_fused(const bsk_banded *h, const double *mrec, const double *d_u, double *d_out,
                                 int64_t ngroups, int64_t ld, cudaStream_t st) {
     switch (h->l) {
-        case 0: return solve_t<0>(h, d_out, ngroups, ld, st, mrec, d_u);
-        case 1: return solve_t<1>(h, d_out, ngroups, ld, st, mrec, d_u);
-        case 2: return solve_t<2>(h, d_out, ngroups, ld, st, mrec, d_u);
-        case 3: return solve_t<3>(h, d_out, ngroups, ld, st, mrec, d_u);
-        case 4: return solve_t<4>(h, d_out, ngroups, ld, st, mrec, d_u);
+        case 0: return solve_t<0, ArF64>(winmat(h), d_out, ngroups, ld, st, mrec, d_u);
+        case 1: return solve_t<1, ArF64>(winmat(h), d_out, ngroups, ld, st, mrec, d_u);
+        case 2: return solve_t<2, ArF64>(winmat(h), d_out, ngroups, ld, st, mrec, d_u);
+        case 3: return solve_t<3, ArF64>(winmat(h), d_out, ngroups, ld, st, mrec, d_u);
+        case 4: return solve_t<4, ArF64>(winmat(h), d_out, ngroups, ld, st, mrec, d_u);
     }
     set_error("fused mat-vec + solve needs at most 4 sub-diagonals");
     return BSK_ERR_UNSUPPORTED;
 }
 
-bsk_status windowed_prepare(bsk_banded *h) {
+// `w`: the factors to repack (h->d_w, or the second band buffer of the partitioned factorisation)
+bsk_status windowed_prepare(bsk_banded *h, const double *w) {
     switch (h->l) {
-        case 0: return prepare_t<0>(h);
-        case 1: return prepare_t<1>(h);
-        case 2: return prepare_t<2>(h);
-        case 3: return prepare_t<3>(h);
-        case 4: return prepare_t<4>(h);
-        case 5: return prepare_t<5>(h);
-        case 6: return prepare_t<6>(h);
+        case 0: return prepare_t<0>(h, w);
+        case 1: return prepare_t<1>(h, w);
+        case 2: return prepare_t<2>(h, w);
+        case 3: return prepare_t<3>(h, w);
+        case 4: return prepare_t<4>(h, w);
+        case 5: return prepare_t<5>(h, w);
+        case 6: return prepare_t<6>(h, w);
     }
     return BSK_ERR_UNSUPPORTED;
 }
@@ -784,13 +910,43 @@ bsk_status windowed_prepare(bsk_banded *h) {
 // elements apart.  Requires 16-byte aligned rows (d_rhs 16-byte aligned, ld even).
 bsk_status windowed_solve(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st) {
     switch (h->l) {
-        case 0: return solve_t<0>(h, d_rhs, ngroups, ld, st);
-        case 1: return solve_t<1>(h, d_rhs, ngroups, ld, st);
-        case 2: return solve_t<2>(h, d_rhs, ngroups, ld, st);
-        case 3: return solve_t<3>(h, d_rhs, ngroups, ld, st);
-        case 4: return solve_t<4>(h, d_rhs, ngroups, ld, st);
-        case 5: return solve_t<5>(h, d_rhs, ngroups, ld, st);
-        case 6: return solve_t<6>(h, d_rhs, ngroups, ld, st);
+        case 0: return solve_t<0, ArF64>(winmat(h), d_rhs, ngroups, ld, st);
+        case 1: return solve_t<1, ArF64>(winmat(h), d_rhs, ngroups, ld, st);
+        case 2: return solve_t<2, ArF64>(winmat(h), d_rhs, ngroups, ld, st);
+        case 3: return solve_t<3, ArF64>(winmat(h), d_rhs, ngroups, ld, st);
+        case 4: return solve_t<4, ArF64>(winmat(h), d_rhs, ngroups, ld, st);
+        case 5: return solve_t<5, ArF64>(winmat(h), d_rhs, ngroups, ld, st);
+        case 6: return solve_t<6, ArF64>(winmat(h), d_rhs, ngroups, ld, st);
+    }
+    return BSK_ERR_UNSUPPORTED;
+}
+
+// ---- Float32: two right-hand sides per lane -------------------------------------------------------
+bsk_status windowed_prepare_f32(bsk_banded_f32 *h) {
+    switch (h->l) {
+        case 0: return prepare_f32_t<0>(h);
+        case 1: return prepare_f32_t<1>(h);
+        case 2: return prepare_f32_t<2>(h);
+        case 3: return prepare_f32_t<3>(h);
+        case 4: return prepare_f32_t<4>(h);
+        case 5: return prepare_f32_t<5>(h);
+        case 6: return prepare_f32_t<6>(h);
+    }
+    return BSK_ERR_UNSUPPORTED;
+}
+
+// Solves the first 64 * ngroups columns of an interleaved Float32 RHS block whose rows are `ld_pairs`
+// column PAIRS apart (nrhs even, block 128-byte aligned).
+bsk_status windowed_solve_f32(const bsk_banded_f32 *h, float *d_rhs, int64_t ngroups, int64_t ld_pairs, cudaStream_t st) {
+    double *p = (double *)d_rhs;
+    switch (h->l) {
+        case 0: return solve_t<0, ArF32x2>(winmat(h), p, ngroups, ld_pairs, st);
+        case 1: return solve_t<1, ArF32x2>(winmat(h), p, ngroups, ld_pairs, st);
+        case 2: return solve_t<2, ArF32x2>(winmat(h), p, ngroups, ld_pairs, st);
+        case 3: return solve_t<3, ArF32x2>(winmat(h), p, ngroups, ld_pairs, st);
+        case 4: return solve_t<4, ArF32x2>(winmat(h), p, ngroups, ld_pairs, st);
+        case 5: return solve_t<5, ArF32x2>(winmat(h), p, ngroups, ld_pairs, st);
+        case 6: return solve_t<6, ArF32x2>(winmat(h), p, ngroups, ld_pairs, st);
     }
     return BSK_ERR_UNSUPPORTED;
 }

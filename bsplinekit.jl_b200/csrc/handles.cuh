@@ -119,6 +119,11 @@ struct bsk_banded {
     double *d_diag;       // n     : U(i,i)
     double *d_lrec, *d_urec;   // padded per-row records of the windowed solve (bsk_solve_win.cu)
     int n_pad;
+    // one device allocation holds every array above (created once in bsk_banded_create*), plus the second
+    // band buffer, the boundary columns and the status words of the partitioned factorisation (banfac.cuh)
+    void *arena;
+    double *d_w2, *d_ver;
+    int *d_status;
     int halo_f;           // decay halo of the forward recurrence (row-segmented windowed solve)
     int halo;             // decay halo (rows) validated for the windowed solve, 0 = not usable
     // unfactored matrices used as the Lm of bsk_banded_matvec_solve: cached row records
@@ -126,8 +131,31 @@ struct bsk_banded {
     int mrec_bw, mrec_npad;
 };
 
+struct bsk_banded_f32 {
+    int device;
+    int64_t n;
+    int l, u;
+    float *d_w;           // (l+u+1) x n column-major: matrix, LU factors after bsk_banded_f32_lu
+    float *d_lrow;        // n x l: lrow[i][j-1] = L(i, i-j)
+    float *d_urow;        // n x u: urow[i][j-1] = U(i, i+j)
+    float *d_diag;        // n:     U(i, i)
+    bool factored;
+    // single-pass (TMEM) solve, two right-hand sides per lane (bsk_solve_win.cu)
+    double *d_lrec, *d_urec;   // records of packed, negated float pairs
+    int n_pad;
+    int halo, halo_f;     // decay halos validated at factor time (0 = single pass unavailable)
+};
+
 namespace bsk {
-bsk_status windowed_prepare(bsk_banded *h);
+// record widths of the single-pass solve (bsk_solve_win.cu: RecW)
+constexpr int win_lw(int bw) { return ((bw + 2) / 2) * 2; }
+constexpr int win_uw(int bw) { return bw == 0 ? 2 : ((bw + 1) / 2) * 2; }
+// decay bound of a triangular recurrence (bsk_solve.cu): rows rec[r][j-1] * scale[r]
+int decay_halo_device(const double *d_rec, const double *d_scale, int n, int bw, int reversed, double tol, int step,
+                      int hmax, int phase);
+bsk_status windowed_prepare_f32(bsk_banded_f32 *h);
+bsk_status windowed_solve_f32(const bsk_banded_f32 *h, float *d_rhs, int64_t ngroups, int64_t ld_pairs, cudaStream_t st);
+bsk_status windowed_prepare(bsk_banded *h, const double *w);
 bsk_status windowed_solve(const bsk_banded *h, double *d_rhs, int64_t ngroups, int64_t ld, cudaStream_t st);
 bsk_status windowed_matrec(const bsk_banded *Lm, int bw, int n_pad, double **out);
 bsk_status windowed_solve_fused(const bsk_banded *h, const double *mrec, const double *d_u, double *d_out,

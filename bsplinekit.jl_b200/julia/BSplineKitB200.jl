@@ -320,8 +320,8 @@ end
 
 function LinearAlgebra.ldiv!(F::DeviceBandedLU{Float32}, Y::DeviceMatrix{Float32})
     Y.N == F.n || throw(DimensionMismatch("vectors `x` and `y` must have length $(F.n)"))
-    check(ccall((:bsk_banded_f32_solve, lib), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int64, Ptr{Cvoid}),
-                F.ptr, Y.data.ptr, Y.M, C_NULL))
+    check(ccall((:bsk_banded_f32_solve, lib), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int64, Int32, Ptr{Cvoid}),
+                F.ptr, Y.data.ptr, Y.M, Int32(0), C_NULL))
     Y
 end
 

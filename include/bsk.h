@@ -68,6 +68,13 @@ enum {
     BSK_EXTRAP_SMOOTH = 3   /* Smooth(): the boundary polynomial pieces continued           */
 };
 
+/* banded LU mode selector for bsk_banded_lu_mode */
+enum {
+    BSK_LU_EXACT = 0,  /* BANFAC's statements in BANFAC's order, serial in the column index: bit-identical factors */
+    BSK_LU_FAST = 1    /* partitioned elimination with validated overlap (n >= 1024), factors within ~1e-16
+                          relative of BANFAC's; falls back to EXACT when a boundary check or a pivot fails  */
+};
+
 /* banded multi-RHS solve algorithm selector */
 enum {
     BSK_SOLVE_AUTO = 0,
@@ -100,6 +107,17 @@ bsk_status bsk_device_count(int32_t *count);
  * value + derivative evaluation — n doubles read, 2 n doubles written, 16-byte vectors, same launch shape —
  * so that the HBM roofline of that 1 : 2 read : write stream can be measured beside the evaluation kernel. */
 bsk_status bsk_probe_stream_1r2w(const double *d_in, double *d_out0, double *d_out1, int64_t n, void *stream);
+/* The same stream moved by TMA: cp.async.bulk global -> shared for the point tiles, cp.async.bulk shared ->
+ * global for the two result tiles (n a multiple of 2048).  Measures what a bulk-copy write path would give. */
+bsk_status bsk_probe_stream_1r2w_tma(const double *d_in, double *d_out0, double *d_out1, int64_t n, void *stream);
+/* Peak rate of the FP64 (dtype BSK_F64) or FP32 FMA pipe: `iters` x 8 independent fused multiply-adds per
+ * thread at full occupancy; *fma_count = fused multiply-adds executed by the launch (time it with events).
+ * The denominators of the pipe fractions bench.py reports beside the HBM fractions. */
+bsk_status bsk_probe_fma(int32_t dtype, int64_t iters, void *d_scratch, double *fma_count, void *stream);
+/* Copy-only twin of bsk_spline_eval_host: the same chunks on the same streams, host -> device copy of the
+ * points and device -> host copy of nout result buffers, NO kernel — what the platform (PCIe, host memory)
+ * gives the host-buffer call.  h_outs are overwritten with whatever the staging buffers hold. */
+bsk_status bsk_probe_copy_host(const bsk_spline *s, const void *h_x, int64_t n, int32_t nout, void *const *h_outs);
 bsk_status bsk_malloc(int32_t device, size_t nbytes, void **d_ptr);
 bsk_status bsk_free(int32_t device, void *d_ptr);
 bsk_status bsk_memcpy_h2d(int32_t device, void *d_dst, const void *h_src, size_t nbytes, void *stream);
@@ -222,6 +240,11 @@ bsk_status bsk_banded_create_host(const double *h_band, int64_t n, int32_t l, in
 /* lu!(C): BANFAC without pivoting, in place in the handle.  On a zero pivot returns
  * BSK_ERR_ZERO_PIVOT and *info_pivot = 1-based row (ZeroPivotException(i)). */
 bsk_status bsk_banded_lu(bsk_banded *h, int64_t *info_pivot);
+/* The same with a mode (BSK_LU_*): BSK_LU_FAST factors partitions of the matrix in parallel — the recurrence
+ * forgets its start state, every partition starts 128 columns early and the state it hands to the next one is
+ * checked against what that partition computed itself (1e-14 relative).  lu! of C3 (n = 4096) in ~0.1 ms
+ * instead of 1.1 ms, n = 10^5 in ~0.15 ms instead of 30 ms; ZeroPivotException(i) is still reported. */
+bsk_status bsk_banded_lu_mode(bsk_banded *h, int32_t mode, int64_t *info_pivot);
 bsk_status bsk_banded_data(const bsk_banded *h, double *h_out); /* (l+u+1) x n copy */
 /* Rows of halo validated at factor time for BSK_SOLVE_WINDOWED (0 = windowed unavailable). */
 bsk_status bsk_banded_halo(const bsk_banded *h, int32_t *halo);
@@ -274,8 +297,8 @@ bsk_status bsk_cyclic_banded_destroy(bsk_cyclic_banded *h);
  * (Collocation/matrix.jl:132-201,218-271) in Float32; periodic cubic bases use
  * CyclicTridiagonalMatrix{Float32} (Collocation/cyclic.jl:112-197).  Same layouts, argument meaning
  * and status codes as the Float64 entry points above; the basis must have been created with
- * BSK_F32 knots.  Assembly, factors and solutions keep the reference's operation order in Float32
- * (bit-identical to a Float32 CPU restatement, see tests/); the cyclic solve is factored once. */
+ * BSK_F32 knots.  Assembly, factors and BSK_SOLVE_TWOPASS solutions keep the reference's operation order in
+ * Float32 (bit-identical to a Float32 CPU restatement, see tests/); the cyclic solve is factored once. */
 bsk_status bsk_collocation_matrix_f32(const bsk_basis *b, const float *d_x, int64_t nx, int32_t deriv,
                                       float clip_threshold, float *d_band, int64_t *h_n_outside,
                                       void *stream);
@@ -288,7 +311,13 @@ bsk_status bsk_banded_f32_create_host(const float *h_band, int64_t n, int32_t l,
                                       int32_t device, bsk_banded_f32 **out);
 bsk_status bsk_banded_f32_lu(bsk_banded_f32 *h, int64_t *info_pivot);
 bsk_status bsk_banded_f32_data(const bsk_banded_f32 *h, float *h_out);
-bsk_status bsk_banded_f32_solve(const bsk_banded_f32 *h, float *d_rhs, int64_t nrhs, void *stream);
+/* Rows of halo validated at factor time for the single-pass solve (0 = unavailable). */
+bsk_status bsk_banded_f32_halo(const bsk_banded_f32 *h, int32_t *halo);
+/* algo: BSK_SOLVE_TWOPASS = BANSLV order, bit-identical to the Float32 restatement of ldiv!;
+ * BSK_SOLVE_WINDOWED = single pass over HBM (8 B per element), two right-hand sides per lane with packed
+ * Float32 FMAs, within 1e-5 of the BANSLV result; BSK_SOLVE_AUTO = single pass when the matrix has a
+ * validated halo and the block has >= 64 columns. */
+bsk_status bsk_banded_f32_solve(const bsk_banded_f32 *h, float *d_rhs, int64_t nrhs, int32_t algo, void *stream);
 bsk_status bsk_banded_f32_destroy(bsk_banded_f32 *h);
 bsk_status bsk_cyclic_f32_create(const float *h_a, const float *h_b, const float *h_c, int64_t n,
                                  int32_t device, bsk_cyclic_f32 **out);

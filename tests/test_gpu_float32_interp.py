@@ -109,10 +109,14 @@ def test_interpolate_f32_end_to_end(bk, oracle, synth):
     t = bk.make_knots(x, 4)
     Bi = bk.BSplineBasis(4, t, augment=False)
     itp = bk.SplineInterpolation(Bi, x)
-    itp.interpolate_(Y)
+    itp.interpolate_(Y, algo=bk.SOLVE_TWOPASS)                       # BANSLV order: the restatement's bits
     band, _ = oracle.collocation_matrix_f32(0, 4, t, x)
     oracle.banded_lu(band)
-    assert np.array_equal(Y.cpu().numpy(), oracle.banded_solve(band, Y0))
+    ref = oracle.banded_solve(band, Y0.copy())
+    assert np.array_equal(Y.cpu().numpy(), ref)
+    Y2 = torch.from_numpy(Y0).cuda()
+    itp.interpolate_(Y2)                                             # default: single pass where available
+    assert relerr(Y2.cpu().numpy(), ref) < TOL32
     with pytest.raises(bk.ArgumentError):
         itp.interpolate_(Y.double())
     with pytest.raises(bk.DimensionMismatch):
@@ -203,3 +207,49 @@ def test_interpolate_f32_natural_and_derivative_rows(bk, synth):
     C32 = bk.collocation_matrix(B32, xc, bk.Derivative(1)).dense()
     C64 = bk.collocation_matrix(B64, xc.astype(np.float64), bk.Derivative(1)).dense()
     assert relerr(C32, C64) < 20 * TOL32
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 8])
+def test_single_pass_solve_f32(bk, oracle, synth, k):
+    """ldiv! on Float32 data in ONE pass over HBM (k_banded_tmem with two right-hand sides per lane, packed
+    Float32 FMAs, ring in Tensor Memory): within 1e-5 of the BANSLV-order Float32 restatement of
+    src/Collocation/matrix.jl:218-271 for every bandwidth, with and without row segments, ragged column counts
+    (the columns past the last group of 64 take the BANSLV kernels), and against the Float64 solve."""
+    import torch
+    for n, nrhs in ((1000, 64), (4096, 4096 + 68), (4096, 132), (257, 192)):
+        xdata, t, B, Cm, ref = _system(bk, oracle, synth, n, k, seed=6 + k)
+        lu_ref = ref.copy(order="F")
+        assert oracle.banded_lu(lu_ref) == 0
+        Cm.lu_()
+        assert np.array_equal(Cm.data(), lu_ref)
+        Y = (2 * synth.u_numpy(7, 0, n * nrhs) - 1).reshape(n, nrhs).astype(np.float32)
+        cols = np.r_[0:40, nrhs - 70:nrhs]
+        Yref = oracle.banded_solve(lu_ref, np.ascontiguousarray(Y[:, cols]))
+        if Cm.halo == 0:
+            with pytest.raises(bk.UnsupportedError):
+                Cm.ldiv_(torch.from_numpy(Y).cuda(), algo=bk.SOLVE_WINDOWED)
+            continue
+        Yd = torch.from_numpy(Y).cuda()
+        Cm.ldiv_(Yd, algo=bk.SOLVE_WINDOWED)
+        got = Yd[:, torch.from_numpy(cols).cuda()].cpu().numpy()
+        assert relerr(got, Yref) < TOL32, (n, nrhs)
+        # per column too
+        assert np.max(np.max(np.abs(got - Yref), axis=0) / np.max(np.abs(Yref), axis=0)) < TOL32
+        Ya = torch.from_numpy(Y).cuda()
+        Cm.ldiv_(Ya)                                                  # AUTO == single pass here
+        assert torch.equal(Ya, Yd)
+        Yt = torch.from_numpy(Y).cuda()
+        Cm.ldiv_(Yt, algo=bk.SOLVE_TWOPASS)
+        assert np.array_equal(Yt[:, torch.from_numpy(cols).cuda()].cpu().numpy(), Yref)
+        # the Float64 solve of the same (Float32) matrix and data
+        C64 = bk.CollocationMatrix(ref.astype(np.float64)).lu_()
+        Z = torch.from_numpy(Y[:, :64].astype(np.float64)).cuda()
+        C64.ldiv_(Z)
+        assert relerr(Yd[:, :64].cpu().numpy(), Z.cpu().numpy()) < 20 * TOL32
+    # column counts that are not a multiple of 4 (rows not 16-byte multiples apart): WINDOWED refuses, AUTO falls
+    # back to BANSLV order
+    Yo = torch.from_numpy(Y[:, :77].copy()).cuda()
+    with pytest.raises(bk.UnsupportedError):
+        Cm.ldiv_(Yo, algo=bk.SOLVE_WINDOWED)
+    Cm.ldiv_(Yo)
+    assert np.array_equal(Yo.cpu().numpy(), oracle.banded_solve(lu_ref, np.ascontiguousarray(Y[:, :77])))

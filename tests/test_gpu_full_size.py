@@ -95,8 +95,9 @@ def test_c3_full_size_batched_solve(bk, oracle, synth):
     xdata = synth.breakpoints(6, n)
     t = bk.make_knots(xdata, k)
     B = bk.BSplineBasis(k, t, augment=False)
-    itp = bk.SplineInterpolation(B, xdata)
-    assert itp.C.halo > 0
+    itp = bk.SplineInterpolation(B, xdata)                       # default: partitioned lu! (within 1e-13)
+    itp_exact = bk.SplineInterpolation(B, xdata, lu_mode=bk.LU_EXACT)     # BANFAC order: the reference's bits
+    assert itp.C.halo > 0 and itp_exact.C.halo == itp.C.halo
     Y0 = (2 * synth.u_torch(7, 0, n * nrhs) - 1).reshape(n, nrhs)
     band, nout = oracle.collocation_matrix(0, k, t, xdata)
     assert nout == 0
@@ -106,9 +107,12 @@ def test_c3_full_size_batched_solve(bk, oracle, synth):
     ref = oracle.banded_solve(lu, np.ascontiguousarray(Y0[:, cols].cpu().numpy()))
     bw = k - 2
     bd = torch.from_numpy(np.ascontiguousarray(band)).cuda()       # (2bw+1, n): band[u+i-j, j]
+    assert np.array_equal(itp_exact.C.data(), lu)
+    f_fast = itp.C.data()
+    assert np.max(np.abs(f_fast - lu) / np.max(np.abs(lu), axis=0)) < 1e-13
     for algo, exact in ((bk.SOLVE_WINDOWED, False), (bk.SOLVE_TWOPASS, True), (bk.SOLVE_AUTO, False)):
         Y = Y0.clone()
-        itp.C.ldiv_(Y, algo=algo)
+        (itp_exact if exact else itp).C.ldiv_(Y, algo=algo)
         got = Y[:, cols].cpu().numpy()
         if exact:
             assert np.array_equal(got, ref)
@@ -240,12 +244,20 @@ def test_c3_shape_float32_solve(bk, oracle, synth):
     Y[:, 40001] = Y[:, 5]
     cols = torch.arange(0, M, 509, device="cuda")
     Y0 = Y[:, cols].cpu().numpy().copy()
-    itp.interpolate_(Y)
+    Ysp = Y.clone()
+    itp.interpolate_(Y, algo=bk.SOLVE_TWOPASS)
     band, _ = oracle.collocation_matrix_f32(0, k, B.knots(), x32)
     assert oracle.banded_lu(band) == 0
     ref = oracle.banded_solve(band, Y0.copy())
     assert np.array_equal(Y[:, cols].cpu().numpy(), ref)
     assert torch.equal(Y[:, 5], Y[:, M - 3]) and torch.equal(Y[:, 5], Y[:, 40001])
+    # default: single pass (two columns per lane, packed Float32 FMAs): within 1e-5 of the BANSLV bits on the
+    # sampled columns and on every column against the two-pass result; identical columns -> identical bits
+    assert itp.C.halo > 0
+    itp.interpolate_(Ysp)
+    assert relerr(Ysp[:, cols].cpu().numpy(), ref) < TOL32
+    assert float((Ysp - Y).abs().max() / Y.abs().max()) < TOL32
+    assert torch.equal(Ysp[:, 5], Ysp[:, M - 3]) and torch.equal(Ysp[:, 5], Ysp[:, 40001])
     # backward error of the Float32 solve, measured in Float64 against the Float32 matrix itself (with 4096
     # points on [0, 1] the Float32 knots carry ~1e-4 of a knot interval, so the Float64 interpolant of the
     # same data is a different, equally valid, answer; the reference behaves the same way)

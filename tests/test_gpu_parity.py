@@ -1330,3 +1330,62 @@ def test_float32_large_tables_pick_the_right_piece(bk, oracle, synth, k, nb):
         sc = np.max(np.abs(ref))
         bad = np.abs(g.cpu().numpy().astype(np.float64) - ref.astype(np.float64)) > TOL32 * sc
         assert not bad.any(), (d, int(bad.sum()), x[bad][:3])
+
+
+@pytest.mark.parametrize("k,n", [(3, 1024), (4, 3000), (6, 4096), (8, 100000), (5, 20011)])
+def test_partitioned_lu(bk, oracle, synth, k, n):
+    """lu! by partitions (BSK_LU_FAST, csrc/banfac.cuh): every partition is eliminated from the original matrix
+    starting 128 columns early and hands a checked elimination state to the next one.  Factors within 1e-13 of
+    BANFAC's (src/Collocation/matrix.jl:132-201) column by column, the validated halos and the solutions of the
+    solve are those of the exact factorisation."""
+    import torch
+    xdata = synth.breakpoints(6 + k, n)
+    t = bk.make_knots(xdata, k)
+    B = bk.BSplineBasis(k, t, augment=False)
+    band, nout = oracle.collocation_matrix(0, k, t, xdata)
+    assert nout == 0
+    lu = band.copy(order="F")
+    assert oracle.banded_lu(lu) == 0
+    Ce = bk.CollocationMatrix(band.copy(order="F")).lu_(bk.LU_EXACT)
+    assert np.array_equal(Ce.data(), lu)
+    Cf = bk.CollocationMatrix(band.copy(order="F")).lu_(bk.LU_FAST)
+    f = Cf.data()
+    assert not np.array_equal(f, band)                       # it did factorise
+    err = np.max(np.abs(f - lu), axis=0) / np.max(np.abs(lu), axis=0)
+    assert err.max() < 1e-13, (err.max(), int(np.argmax(err)))
+    assert Cf.halo == Ce.halo
+    Y = (2 * synth.u_numpy(7, 0, n * 64) - 1).reshape(n, 64)
+    ref = oracle.banded_solve(lu, Y.copy())
+    for Cm in (Ce, Cf):
+        Z = torch.from_numpy(Y).cuda()
+        Cm.ldiv_(Z)
+        assert relerr(Z.cpu().numpy(), ref) < TOL64
+
+
+def test_partitioned_lu_zero_pivot_and_fallback(bk, oracle):
+    """A zero pivot deep inside a large matrix: BSK_LU_FAST must still raise ZeroPivotException(i) with BANFAC's
+    row (the partition that meets it gives up, the serial kernel reports it).  A matrix whose elimination does
+    not forget its start state (no diagonal dominance) must fall back to the exact factors."""
+    n, bw = 5000, 2
+    rng = np.random.default_rng(5)
+    band = np.zeros((2 * bw + 1, n), order="F")
+    band[bw, :] = 4.0 + rng.random(n)
+    band[:bw, :] = rng.random((bw, n)) - 0.5
+    band[bw + 1:, :] = rng.random((bw, n)) - 0.5
+    sing = band.copy(order="F")
+    sing[:, 3210] = 0.0                                    # column 3211 of the matrix is zero
+    ref = sing.copy(order="F")
+    info = oracle.banded_lu(ref)
+    assert info > 0
+    with pytest.raises(bk.ZeroPivotException) as ei:
+        bk.CollocationMatrix(sing).lu_(bk.LU_FAST)
+    assert ei.value.info == info
+    # slowly decaying recurrence: off-diagonals as large as the diagonal
+    slow = np.zeros((3, n), order="F")
+    slow[1, :] = 2.0
+    slow[0, 1:] = -0.999999
+    slow[2, :-1] = -0.999999
+    ref = slow.copy(order="F")
+    assert oracle.banded_lu(ref) == 0
+    got = bk.CollocationMatrix(slow.copy(order="F")).lu_(bk.LU_FAST).data()
+    assert np.max(np.abs(got - ref) / np.max(np.abs(ref), axis=0)) < 1e-13

@@ -103,6 +103,51 @@ elif args.what == "cyclic":
             tot += e0.elapsed_time(e1)
     ms = tot / args.reps
     print("cyclic: %.3f ms  %.2f M RHS/s  %.1f GB/s (16 B/elem)" % (ms, nrhs / ms / 1e3, 16 * n * nrhs / ms / 1e6))
+if args.what == "evalall":
+    import ctypes as C
+    from bsplinekit_b200 import _lib
+    k = args.order
+    B = bk.BSplineBasis(k, synth.breakpoints(3, args.breaks))
+    xd = synth.u_torch(5, 0, args.points)
+    idx = torch.empty(args.points, dtype=torch.int64, device="cuda")
+    bs = torch.empty(args.points * k, dtype=torch.float64, device="cuda")
+    call = lambda: _lib.check(_lib.lib.bsk_evaluate_all(B._handle, C.c_void_p(xd.data_ptr()), args.points, 0, 1, None,
+                                                        C.c_void_p(idx.data_ptr()), C.c_void_p(bs.data_ptr()), None))
+    ms = timed(call, args.reps)
+    print("evaluate_all k=%d: %.3f ms  %.1f Gpt/s  %.1f GB/s (%d B/pt)" % (k, ms, args.points / ms / 1e6,
+                                                                          (16 + 8 * k) * args.points / ms / 1e6, 16 + 8 * k))
+if args.what == "probefma":
+    import ctypes as C
+    from bsplinekit_b200 import _lib
+    scratch = torch.zeros(16, dtype=torch.float64, device="cuda")
+    for name, dt_ in (("fp64", 1), ("fp32", 0)):
+        cnt = C.c_double(0)
+        call = lambda: _lib.check(_lib.lib.bsk_probe_fma(dt_, 1 << 14, C.c_void_p(scratch.data_ptr()), C.byref(cnt), None))
+        ms = timed(call, args.reps)
+        print("%s FMA probe: %.3f ms, %.2f TFLOP/s" % (name, ms, 2 * cnt.value / ms / 1e9))
+if args.what == "solve32w":
+    xd32 = synth.breakpoints(6, 4096).astype(np.float32)
+    B32 = bk.BSplineBasis(6, bk.make_knots(xd32, 6), augment=False)
+    itp32 = bk.SplineInterpolation(B32, xd32)
+    Y32 = (2 * synth.u_torch(7, 0, 4096 * args.nrhs, dtype=torch.float32) - 1).reshape(4096, args.nrhs)
+    W32 = torch.empty_like(Y32)
+    for name, al in (("windowed", bk.SOLVE_WINDOWED), ("twopass", bk.SOLVE_TWOPASS)):
+        tot = 0.0
+        for it in range(args.reps + 1):
+            W32.copy_(Y32)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); itp32.C.ldiv_(W32, algo=al); e1.record()
+            torch.cuda.synchronize()
+            if it:
+                tot += e0.elapsed_time(e1)
+        ms = tot / args.reps
+        print("solve32 %s halo=%d: %.3f ms  %.1f M RHS/s  %.1f GB/s (8 B/element)" % (name, itp32.C.halo, ms, args.nrhs / ms / 1e3, 8 * 4096 * args.nrhs / ms / 1e6))
+if args.what == "knot":
+    B = bk.BSplineBasis(args.order, synth.breakpoints(3, args.breaks))
+    xd = synth.u_torch(5, 0, args.points)
+    ms = timed(lambda: bk.find_knot_interval(B, xd), args.reps)
+    print("find_knot_interval: %.3f ms (incl. output allocation)  %.1f Gpt/s" % (ms, args.points / ms / 1e6))
 if args.what == "multi":
     n, k, M = 4096, 6, args.nrhs
     xdata = synth.breakpoints(6, n)
@@ -163,14 +208,23 @@ if args.what == "factor":
     for (n, k) in ((4096, 6), (100000, 8), (11, 4)):
         xdata = synth.breakpoints(6, n)
         Bi = bk.BSplineBasis(k, bk.make_knots(xdata, k), augment=False)
-        for it in range(3):
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            Cm = bk.collocation_matrix(Bi, xdata)
-            torch.cuda.synchronize(); t1 = time.perf_counter()
-            Cm.lu_()
-            torch.cuda.synchronize(); t2 = time.perf_counter()
-        print("n=%d k=%d: assemble %.2f ms, lu! (BANFAC + repack + halo analysis) %.2f ms, halo %d" % (
-            n, k, 1e3 * (t1 - t0), 1e3 * (t2 - t1), Cm.halo))
+        for mode, name in ((bk.LU_EXACT, "exact"), (bk.LU_FAST, "fast")):
+            best = [1e9, 1e9, 1e9]
+            for it in range(5):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                Cm = bk.collocation_matrix(Bi, xdata)
+                torch.cuda.synchronize(); t1 = time.perf_counter()
+                Cm.lu_(mode)
+                torch.cuda.synchronize(); t2 = time.perf_counter()
+                del Cm
+                torch.cuda.synchronize(); t3 = time.perf_counter()
+                itp = bk.SplineInterpolation(Bi, xdata, lu_mode=mode)
+                torch.cuda.synchronize(); t4 = time.perf_counter()
+                halo = itp.C.halo
+                del itp
+                best = [min(best[0], t1 - t0), min(best[1], t2 - t1), min(best[2], t4 - t3)]
+            print("n=%d k=%d %s: assemble %.3f ms, lu! (elimination + repack + halo analysis + records) %.3f ms, "
+                  "SplineInterpolation(B, x) %.3f ms, halo %d" % (n, k, name, 1e3 * best[0], 1e3 * best[1], 1e3 * best[2], halo))
 if args.what == "solve32":
     xd32 = synth.breakpoints(6, 4096).astype(np.float32)
     B32 = bk.BSplineBasis(args.order if args.order != 4 else 6, bk.make_knots(xd32, args.order if args.order != 4 else 6), augment=False)
