@@ -10,7 +10,7 @@ from ._lib import (ArgumentError, DimensionMismatch, ZeroPivotException, CudaErr
 from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, period,
                   BSplineBasis, PeriodicBSplineBasis, RecombinedBSplineBasis, augment_knots,
                   knots, order, boundaries, find_knot_interval, evaluate_all,
-                  Spline, SplineBatch, collocation_points, greville_points, collocation_matrix, CollocationMatrix,
+                  Spline, SplineBatch, ComplexSpline, integral, collocation_points, greville_points, collocation_matrix, collocation_rows, CollocationMatrix,
                   CyclicTridiagonalMatrix, CyclicBandedMatrix, lu, ldiv, make_knots, SplineInterpolation, interpolate,
                   approximate, approximate_, ApproxByInterpolation, VariationDiminishing, MinimiseL2Error,
                   SplineApproximation, fit, SmoothingSpline, DomainError,

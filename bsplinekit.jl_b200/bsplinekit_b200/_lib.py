@@ -93,6 +93,7 @@ SIGNATURES = {
     "bsk_spline_eval_host": (_i32, [_vp, _vp, _i64, _i32, C.POINTER(_i32), _pp, _i32]),
     "bsk_spline_eval_multi": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "bsk_collocation_matrix": (_i32, [_vp, _vp, _i64, _i32, _dbl, _vp, C.POINTER(_i64), _vp]),
+    "bsk_collocation_rows": (_i32, [_vp, _vp, _i64, _i32, _dbl, _vp, _vp, _vp, _vp]),
     "bsk_collocation_cyclic": (_i32, [_vp, _vp, _i64, _i32, _dbl, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
     "bsk_banded_create": (_i32, [_vp, _i64, _i32, _i32, _i32, _pp]),
     "bsk_banded_create_host": (_i32, [_vp, _i64, _i32, _i32, _i32, _pp]),

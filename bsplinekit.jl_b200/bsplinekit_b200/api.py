@@ -604,6 +604,79 @@ class Spline:
         return self.evaluate(x, (0,), algo)[0]
 
 
+class ComplexSpline:
+    """Spline with complex coefficients (eltype ComplexF32 / ComplexF64 in the reference: the de Boor recurrence
+    is linear in the coefficients, Splines/spline.jl:180-184): real and imaginary part are two splines sharing
+    one basis, evaluated together by the vector-valued kernel (M = 2)."""
+
+    def __init__(self, B, coefs):
+        self.basis = B
+        self.coefs = coefs                                   # (N,) complex CUDA tensor
+        self._batch = SplineBatch(B, torch.view_as_real(coefs).contiguous())
+
+    def coefficients(self):
+        return self.coefs.cpu().numpy()
+
+    def __call__(self, x):
+        on_dev = isinstance(x, torch.Tensor) and x.is_cuda
+        xd = x if on_dev else torch.from_numpy(np.ascontiguousarray(np.atleast_1d(x), dtype=_NP[self.basis._dt])).cuda()
+        out = torch.view_as_complex(self._batch(xd.reshape(-1)).contiguous()).reshape(xd.shape)
+        if on_dev:
+            return out
+        out = out.cpu().numpy()
+        return out[0] if np.isscalar(x) else out
+
+
+def _periodic_knot(data, k, i):
+    """getindex(::PeriodicKnots, i), i 1-based (BSplines/periodic.jl:102-115): repeated +-L, in the knot type."""
+    T = data.dtype.type
+    N = data.size - 1
+    L = T(data[-1] - data[0])
+    x = T(0)
+    i -= k // 2
+    while i < 1:
+        x = T(x - L)
+        i += N
+    while i > N + 1:
+        x = T(x + L)
+        i -= N
+    return T(x + data[i - 1])
+
+
+def integral(S):
+    """integral(S) (Splines/spline.jl:354-374; periodic: Splines/periodic.jl:122-140): an antiderivative of S as a
+    spline of order k + 1 on basis_integral(B) (BSplines/basis.jl:113-122, periodic.jl:264-276), zero at the left
+    boundary.  O(N) host code like Derivative(n) * S, same operation order as the reference; the result is a
+    device spline like any other.  Periodic splines give a non-periodic spline over one period plus k knots."""
+    k = S.k
+    if k + 1 > 8:
+        raise _lib.UnsupportedError("integral of an order-8 spline has order 9 (orders 1..8 are supported)")
+    T = _NP[S._dt]
+    u = S.coefficients()                     # evaluation-basis coefficients (parent basis for recombined splines)
+    t = S.knots()
+    periodic = u.size == t.size - 1          # stored knots of a periodic spline: N + 1 breakpoints
+    if not periodic:
+        beta = np.zeros(u.size + 1, dtype=T)
+        np.cumsum(u * (t[k:] - t[:-k]) / T(k), out=beta[1:])       # beta[i+1] = beta[i] + u[i] (t[i+k] - t[i]) / k
+        t_int = np.concatenate([t[:1], t, t[-1:]])
+        return Spline(BSplineBasis(k + 1, t_int, augment=False), beta)
+    N = u.size
+    off = k // 2
+    t_int = np.array([_periodic_knot(t, k, i) for i in range(1 + off - k, 1 + off + N + k + 1)], dtype=T)
+    Np = t_int.size - (k + 1)
+    delta = off - k + 1
+    beta = np.zeros(Np, dtype=T)
+    for i in range(1, Np):
+        j = i + delta
+        uj = u[(j - 1) % N]
+        beta[i] = T(beta[i - 1] + T(T(uj * T(_periodic_knot(t, k, j + k) - _periodic_knot(t, k, j))) / T(k)))
+    Bp = BSplineBasis(k + 1, t_int, augment=False)
+    Sp = Spline(Bp, beta)
+    xleft = t_int[k]                         # boundaries(B')[1] = t[k + 1]
+    beta = (beta - T(Sp(np.array([xleft], dtype=T), algo=EVAL_DEBOOR)[0])).astype(T)
+    return Spline(Bp, beta)
+
+
 class SplineBatch:
     """M splines sharing one basis: Spline(B, coefs) with eltype(coefs) <: SVector{M}
     (Splines/spline.jl:180-184).  coefs: (length(B), M) CUDA tensor, M fastest — exactly what a
@@ -675,6 +748,29 @@ def greville_points(k, t, N, cl=0, force_ends=True):
                 xi = b
         x[i] = min(max(xi, a), b)
     return x
+
+
+class ComplexSpline:
+    """Spline with complex coefficients (eltype ComplexF32 / ComplexF64 in the reference: the de Boor recurrence
+    is linear in the coefficients, Splines/spline.jl:180-184): real and imaginary part are two splines sharing
+    one basis, evaluated together by the vector-valued kernel (M = 2)."""
+
+    def __init__(self, B, coefs):
+        self.basis = B
+        self.coefs = coefs                                   # (N,) complex CUDA tensor
+        self._batch = SplineBatch(B, torch.view_as_real(coefs).contiguous())
+
+    def coefficients(self):
+        return self.coefs.cpu().numpy()
+
+    def __call__(self, x):
+        on_dev = isinstance(x, torch.Tensor) and x.is_cuda
+        xd = x if on_dev else torch.from_numpy(np.ascontiguousarray(np.atleast_1d(x), dtype=_NP[self.basis._dt])).cuda()
+        out = torch.view_as_complex(self._batch(xd.reshape(-1)).contiguous()).reshape(xd.shape)
+        if on_dev:
+            return out
+        out = out.cpu().numpy()
+        return out[0] if np.isscalar(x) else out
 
 
 def _periodic_knot(data, k, i):
@@ -989,6 +1085,26 @@ def collocation_matrix(B, x, deriv=None, clip_threshold=None, return_outside=Fal
     return (M, nout.value) if return_outside else M
 
 
+def collocation_rows(B, x, deriv=None, clip_threshold=None, dense=False):
+    """collocation_matrix(B, x, deriv, SparseMatrixCSC{T} / Matrix{T}) for ANY number of points
+    (Collocation/Collocation.jl:82-106,162-193,209-251): returns (col, val) — (nx, k) int64 / float64 CUDA tensors,
+    col 1-based, 0 = no entry — or, with dense=True, the (nx, length(B)) matrix itself (column-major on the
+    device, returned as a torch tensor of that shape)."""
+    nd = 0 if deriv is None else deriv.n
+    clip = float(np.finfo(np.float64).eps) if clip_threshold is None else float(clip_threshold)
+    xd, _ = _to_device(x, BSK_F64)
+    xd = xd.reshape(-1)
+    nx, k = xd.numel(), B.k
+    if dense:
+        Ct = torch.empty((len(B), nx), dtype=torch.float64, device="cuda")      # == nx x len(B) column-major
+        check(lib.bsk_collocation_rows(B._handle, _ptr(xd), nx, nd, clip, None, None, _ptr(Ct), _stream()))
+        return Ct.t()
+    col = torch.empty((nx, k), dtype=torch.int64, device="cuda")
+    val = torch.empty((nx, k), dtype=torch.float64, device="cuda")
+    check(lib.bsk_collocation_rows(B._handle, _ptr(xd), nx, nd, clip, _ptr(col), _ptr(val), None, _stream()))
+    return col, val
+
+
 def _collocation_matrix_f32(B, x, nd, clip_threshold, return_outside):
     """CollocationMatrix{Float32} / CyclicTridiagonalMatrix{Float32}: T = eltype of the basis' knots
     (Collocation.jl:111-120: `T = eltype(x)` default, clip_threshold = eps(T))."""
@@ -1176,6 +1292,23 @@ class SplineInterpolation:
         (N, M) batch with the data-set index fastest (== Vector{SVector{M}}); CUDA tensors are
         solved in place and stay on the device."""
         N = len(self.basis)
+        # Complex data (test/interpolation.jl:57: ComplexF32): ldiv! is linear with a real matrix, so a complex
+        # right-hand side is two interleaved real ones — exactly the memory layout of a complex array.  The
+        # coefficients come back with the data's own complex type; integer data is converted to the basis'
+        # float type (T = float(eltype(y)), SplineInterpolations.jl:268-270).
+        is_cplx = (isinstance(y, torch.Tensor) and y.is_complex()) or (not isinstance(y, torch.Tensor) and np.iscomplexobj(y))
+        if is_cplx:
+            ctype = torch.complex128 if self.basis._dt == BSK_F64 else torch.complex64
+            yc = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
+            if yc.shape[0] != N:
+                raise DimensionMismatch("input data has incorrect length")
+            src_dtype = yc.dtype
+            Yc = yc.cuda().to(ctype).contiguous()
+            self.interpolate_(torch.view_as_real(Yc).reshape(N, -1), algo=algo)
+            self.coefs = Yc.to(src_dtype)
+            self.spline = ComplexSpline(self.basis, Yc) if Yc.dim() == 1 else None
+            self.splines = None
+            return self
         if isinstance(y, torch.Tensor) and y.is_cuda:
             if y.shape[0] != N:
                 raise DimensionMismatch("input data has incorrect length")

@@ -256,8 +256,12 @@ bsk_status bsk_memcpy_d2h(int32_t device, void *h_dst, const void *d_src, size_t
 bsk_status bsk_stream_create(int32_t device, void **stream) {
     BSK_REQUIRE(stream, BSK_ERR_ARGUMENT, "stream is NULL");
     BSK_CUDA(cudaSetDevice(device));
+    // A BLOCKING stream: the handle-building entry points (bsk_banded_create / _lu, bsk_spline_create,
+    // bsk_spline_set_coefs_device, table builds) run on the legacy default stream, and a blocking stream
+    // orders against it in both directions — work enqueued here before such a call is finished when the
+    // call reads it, and the call's results are complete before later work on this stream starts.
     cudaStream_t s;
-    BSK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    BSK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamDefault));
     *stream = (void *)s;
     return BSK_OK;
 }

@@ -91,7 +91,7 @@ k_find_interval(KnotView<KT> kv, const KT *__restrict__ x, int64_t n, int64_t *_
 // leave as 16-byte vectors, each store instruction of the warp covering 512 contiguous bytes; the
 // strided per-lane stores of the plain variant touch every 32-byte sector K / 4 times over.
 template <int K, int KIND, typename KT, typename VT, int WIDE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads)          // (forcing 6 CTAs / SM for K <= 4 spills: 48 instead of 75 Gpt/s)
 k_evaluate_all(KnotView<KT> kv, RecombView rv, const KT *__restrict__ x, int64_t n, int deriv,
                const int64_t *__restrict__ ileft, int64_t *__restrict__ idx, VT *__restrict__ bs,
                int stage) {
@@ -102,15 +102,23 @@ k_evaluate_all(KnotView<KT> kv, RecombView rv, const KT *__restrict__ x, int64_t
     VT *const rows = (VT *)(smem + off) + (threadIdx.x >> 5) * (32 * K);     // this warp's 32 rows
     const int lane = threadIdx.x & 31;
     __syncthreads();
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p - lane < n;
-         p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    KT x_next = p < n ? x[p] : (KT)0;
+    long long il_next = (ileft && p < n) ? ileft[p] : 0;
+    for (; p - lane < n; p += stride) {
         const bool live = p < n;
+        const KT xp = x_next;
+        long long il = il_next;
+        if (p + stride < n) {                               // software prefetch: the next point's load is in
+            x_next = x[p + stride];                         // flight while this one goes through the triangle
+            if (ileft) il_next = ileft[p + stride];
+        }
         VT bq[K];
         int i = 1;
         if (live) {
-            long long il = ileft ? ileft[p] : 0;
             if (rv.enabled && il != 0) il += rv.cl;          // bases.jl:393-395
-            i = eval_all_point<K, KIND, KT, VT>(kv, t, x[p], deriv, il, bq);
+            i = eval_all_point<K, KIND, KT, VT>(kv, t, xp, deriv, il, bq);
             if (rv.enabled) {
                 VT ph[K];
                 i = recombine_point<K, KT, VT>(rv, i, bq, ph);
@@ -840,6 +848,7 @@ bsk_status bsk_spline_set_coefs_device(bsk_spline *s, const void *d_coefs, int64
     BSK_REQUIRE(ncoef == s->user_len, BSK_ERR_DIMENSION, "wrong number of coefficients: got %lld, expected %lld",
                 (long long)ncoef, (long long)s->user_len);
     BSK_REQUIRE(stride >= 1, BSK_ERR_ARGUMENT, "stride must be >= 1");
+    std::unique_lock<std::mutex> lock(s->mu);             // tables / derivative cache are rebuilt: no concurrent evaluation
     const bsk_basis *b = s->basis;
     size_t es = b->dtype == BSK_F64 ? 8 : 4;
     BSK_CUDA(cudaSetDevice(b->device));

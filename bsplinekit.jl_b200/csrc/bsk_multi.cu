@@ -237,14 +237,17 @@ bsk_status spline_multi_t(const bsk_basis *b, const T *d_coefs, int64_t ncoef, i
     T *d_bs = nullptr;
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_idx, d_idx_s, d_perm, d_perm_s, (int)n, 0, 40, st);
-    BSK_CUDA(cudaMallocAsync((void **)&d_idx, sizeof(int64_t) * n, st));
-    BSK_CUDA(cudaMallocAsync((void **)&d_idx_s, sizeof(int64_t) * n, st));
-    BSK_CUDA(cudaMallocAsync((void **)&d_perm, sizeof(int32_t) * n, st));
-    BSK_CUDA(cudaMallocAsync((void **)&d_perm_s, sizeof(int32_t) * n, st));
-    BSK_CUDA(cudaMallocAsync((void **)&d_bs, sizeof(T) * n * b->k, st));
-    BSK_CUDA(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 16, st));
-    bsk_status rc = bsk_evaluate_all(b, d_x, n, 0, b->dtype, nullptr, d_idx, d_bs, (void *)st);
+    cudaError_t ae = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_idx, d_idx_s, d_perm, d_perm_s, (int)n, 0, 40, st);
+    // every block is released at the common exit below, also when a later allocation fails
+    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&d_idx, sizeof(int64_t) * n, st);
+    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&d_idx_s, sizeof(int64_t) * n, st);
+    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&d_perm, sizeof(int32_t) * n, st);
+    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&d_perm_s, sizeof(int32_t) * n, st);
+    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&d_bs, sizeof(T) * n * b->k, st);
+    if (ae == cudaSuccess) ae = cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 16, st);
+    bsk_status rc = BSK_OK;
+    if (ae != cudaSuccess) { set_error("vector-valued evaluation: scratch allocation failed: %s", cudaGetErrorString(ae)); rc = BSK_ERR_ALLOC; }
+    if (rc == BSK_OK) rc = bsk_evaluate_all(b, d_x, n, 0, b->dtype, nullptr, d_idx, d_bs, (void *)st);
     if (rc == BSK_OK) {
         k_iota<<<(unsigned)std::min<int64_t>(1024, (n + 255) / 256), 256, 0, st>>>(d_perm, n);
         // interval indices fit in 40 bits (periodic indices can be negative: they sort after the
@@ -282,12 +285,8 @@ bsk_status spline_multi_t(const bsk_basis *b, const T *d_coefs, int64_t ncoef, i
         (void)V;
         if (rc == BSK_OK && cudaGetLastError() != cudaSuccess) { set_error("k_spline_multi launch failed"); rc = BSK_ERR_CUDA; }
     }
-    cudaFreeAsync(d_idx, st);
-    cudaFreeAsync(d_idx_s, st);
-    cudaFreeAsync(d_perm, st);
-    cudaFreeAsync(d_perm_s, st);
-    cudaFreeAsync(d_bs, st);
-    cudaFreeAsync(d_tmp, st);
+    for (void *p : {(void *)d_idx, (void *)d_idx_s, (void *)d_perm, (void *)d_perm_s, (void *)d_bs, d_tmp})
+        if (p) cudaFreeAsync(p, st);
     return rc;
 }
 

@@ -88,6 +88,46 @@ k_collocation(KnotView<double> kv, RecombView rv, double dom_a, double dom_b,
     }
 }
 
+// Any number of points (least-squares fitting has more points than basis functions): the matrix row by row,
+// exactly k slots per row — col[i][dj] = 1-based column (0 = entry clipped or row outside the domain),
+// val[i][dj] = D^n b_col(x_i), slots in the reference's order dj = 1..k (column jlast + 1 - dj).  This is the
+// SparseMatrixCSC / Matrix target of collocation_matrix! (Collocation.jl:209-251) with the column mapping of
+// basis_to_array_index (periodic wrap, BSplines/periodic.jl:245-253).  `dense` != nullptr additionally
+// scatters into a zero-filled column-major nx x ncols matrix.
+template <int K, int KIND>
+__global__ void __launch_bounds__(kThreads)
+k_collocation_rows(KnotView<double> kv, RecombView rv, double dom_a, double dom_b, const double *__restrict__ x,
+                   int64_t nx, int deriv, double clip, int64_t *__restrict__ col, double *__restrict__ val,
+                   double *__restrict__ dense, int ncols) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += (int64_t)gridDim.x * blockDim.x) {
+        const double xi = x[i];
+        double bq[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) bq[j] = 0.0;
+        int jlast = 0;
+        const bool in = KIND == 1 || (xi >= dom_a && xi <= dom_b);        // isindomain (basis.jl:229-234)
+        if (in) {
+            jlast = eval_all_point<K, KIND, double, double>(kv, kv.t, xi, deriv, 0, bq);
+            if (rv.enabled) {
+                double ph[K];
+                jlast = recombine_point<K, double, double>(rv, jlast, bq, ph);
+#pragma unroll
+                for (int j = 0; j < K; ++j) bq[j] = ph[j];
+            }
+        }
+#pragma unroll
+        for (int dj = 1; dj <= K; ++dj) {
+            int j = jlast + 1 - dj;
+            if (KIND == 1) { j = (j - 1) % ncols; if (j < 0) j += ncols; j += 1; }
+            const double bj = bq[dj - 1];
+            const bool keep = in && !(fabs(bj) <= clip) && j >= 1 && j <= ncols;
+            if (col) col[i * K + dj - 1] = keep ? j : 0;
+            if (val) val[i * K + dj - 1] = keep ? bj : 0.0;
+            if (dense && keep) dense[i + (int64_t)(j - 1) * nx] = bj;
+        }
+    }
+}
+
 // Periodic cubic: CyclicTridiagonalMatrix (cyclic.jl:21-33, setindex! :77-92)
 template <int K>
 __global__ void __launch_bounds__(kThreads)
@@ -397,6 +437,32 @@ bsk_status bsk_collocation_matrix(const bsk_basis *b, const double *d_x, int64_t
     }
     cudaFreeAsync(d_cnt, st);
     if (e != cudaSuccess) { set_error("collocation kernel failed: %s", cudaGetErrorString(e)); return BSK_ERR_CUDA; }
+    return BSK_OK;
+}
+
+bsk_status bsk_collocation_rows(const bsk_basis *b, const double *d_x, int64_t nx, int32_t deriv, double clip_threshold,
+                                int64_t *d_col, double *d_val, double *d_dense, void *stream) {
+    BSK_REQUIRE(b && (nx == 0 || d_x) && (d_col || d_val || d_dense), BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(b->dtype == BSK_F64, BSK_ERR_UNSUPPORTED, "collocation assembly needs a Float64 basis");
+    BSK_REQUIRE(deriv >= 0, BSK_ERR_ARGUMENT, "derivative order must be >= 0");
+    BSK_REQUIRE(nx >= 0, BSK_ERR_DIMENSION, "negative number of points");
+    if (nx == 0) return BSK_OK;
+    BSK_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_dense) BSK_CUDA(cudaMemsetAsync(d_dense, 0, sizeof(double) * (size_t)nx * (size_t)b->len, st));
+    KnotView<double> kv = make_view_s<double>(b);
+    const bool periodic = b->kind == BSK_BASIS_PERIODIC;
+    const double dom_a = periodic ? b->h_knots.front() : b->h_knots[b->k - 1];
+    const double dom_b = periodic ? b->h_knots.back() : b->h_knots[b->N];
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nx + kThreads - 1) / kThreads, 148 * 8));
+    if (periodic) {
+        BSK_DISPATCH_K(b->k, (k_collocation_rows<K, 1><<<grid, kThreads, 0, st>>>(kv, b->rv, dom_a, dom_b, d_x, nx, deriv, clip_threshold,
+                                                                                 d_col, d_val, d_dense, (int)b->len)))
+    } else {
+        BSK_DISPATCH_K(b->k, (k_collocation_rows<K, 0><<<grid, kThreads, 0, st>>>(kv, b->rv, dom_a, dom_b, d_x, nx, deriv, clip_threshold,
+                                                                                 d_col, d_val, d_dense, (int)b->len)))
+    }
+    BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }
 

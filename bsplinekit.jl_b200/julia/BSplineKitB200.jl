@@ -22,6 +22,7 @@ using BSplineKit.BSplines: BSplineBasis, PeriodicBSplineBasis, AbstractBSplineBa
 using BSplineKit.Recombinations: RecombinedBSplineBasis, recombination_matrix, num_constraints,
     num_recombined, submatrices
 using LinearAlgebra
+using SparseArrays: SparseMatrixCSC, sparse
 
 export DeviceVector, DeviceMatrix, device_spline, evaluate
 
@@ -98,32 +99,36 @@ struct RecombDesc
     ul::Ptr{Float64}; lr::Ptr{Float64}
 end
 
+# One handle per (basis, device): a handle lives on the device it was created for, so a process that
+# drives several GPUs (one host thread per device) gets one handle per device from the same basis object.
 const _basis_cache = IdDict{Any, BasisHandle}()
+const _cache_lock = ReentrantLock()
+_key(obj, device) = (obj, Int32(device))
 
 function handle(B::BSplineBasis{k, T}; device = Int32(0)) where {k, T}
-    get!(_basis_cache, B) do
+    lock(_cache_lock) do; get!(_basis_cache, _key(B, device)) do
         t = collect(T, knots(B))                       # materialises AugmentedKnots (knots.jl:43-48)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         GC.@preserve t check(ccall((:bsk_basis_create, lib), Int32,
             (Int32, Int32, Int32, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}),
             0, k, dtype_code(T), pointer(t), length(t), C_NULL, device, out))
         finalizer(destroy!, BasisHandle(out[]))
-    end
+    end; end
 end
 
 function handle(B::PeriodicBSplineBasis{k, T}; device = Int32(0)) where {k, T}
-    get!(_basis_cache, B) do
+    lock(_cache_lock) do; get!(_basis_cache, _key(B, device)) do
         ξ = collect(T, parent(knots(B)))               # breakpoints incl. endpoint (periodic.jl:37-55)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         GC.@preserve ξ check(ccall((:bsk_basis_create, lib), Int32,
             (Int32, Int32, Int32, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}),
             1, k, dtype_code(T), pointer(ξ), length(ξ), C_NULL, device, out))
         finalizer(destroy!, BasisHandle(out[]))
-    end
+    end; end
 end
 
 function handle(R::RecombinedBSplineBasis{k, T}; device = Int32(0)) where {k, T}
-    get!(_basis_cache, R) do
+    lock(_cache_lock) do; get!(_basis_cache, _key(R, device)) do
         A = recombination_matrix(R)
         ul, lr = map(m -> Matrix{Float64}(m), submatrices(A))      # corner blocks (matrices.jl:70-110)
         cl, cr = num_constraints(A); nl, nr = num_recombined(A)
@@ -136,7 +141,7 @@ function handle(R::RecombinedBSplineBasis{k, T}; device = Int32(0)) where {k, T}
                 2, k, dtype_code(T), pointer(t), length(t), desc, device, out))
         end
         finalizer(destroy!, BasisHandle(out[]))
-    end
+    end; end
 end
 
 # find_knot_interval(ts, xs)  (BSplines/evaluate_all.jl:102-119, periodic.jl:85-100)
@@ -144,7 +149,7 @@ function BSplines.find_knot_interval(B::AbstractBSplineBasis, xs::DeviceVector{T
     is = DeviceVector{Int64}(undef, length(xs)); zs = DeviceVector{Int8}(undef, length(xs))
     check(ccall((:bsk_find_knot_interval, lib), Int32,
         (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int8}, Ptr{Cvoid}),
-        handle(B).ptr, xs.ptr, length(xs), is.ptr, zs.ptr, C_NULL))
+        handle(B; device = xs.device).ptr, xs.ptr, length(xs), is.ptr, zs.ptr, C_NULL))
     is, zs
 end
 
@@ -158,7 +163,7 @@ function BSplines.evaluate_all(B::AbstractBSplineBasis, xs::DeviceVector{Tx},
     bs = DeviceVector{T}(undef, k * length(xs))
     check(ccall((:bsk_evaluate_all, lib), Int32,
         (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Ptr{Cvoid}),
-        handle(B).ptr, xs.ptr, length(xs), n, dtype_code(T),
+        handle(B; device = xs.device).ptr, xs.ptr, length(xs), n, dtype_code(T),
         ileft === nothing ? Ptr{Int64}(C_NULL) : ileft.ptr, is.ptr, bs.ptr, C_NULL))
     is, DeviceMatrix{T}(bs, k, length(xs))
 end
@@ -170,15 +175,15 @@ mutable struct SplineHandle
 end
 const _spline_cache = IdDict{Any, SplineHandle}()
 
-function device_spline(S::Spline{T}) where {T <: Union{Float32, Float64}}
-    get!(_spline_cache, S) do
+function device_spline(S::Spline{T}; device = Int32(0)) where {T <: Union{Float32, Float64}}
+    lock(_cache_lock) do; get!(_spline_cache, _key(S, device)) do
         B = Splines.basis(S)
         c = collect(T, Splines.unwrap_coefficients(S))
         out = Ref{Ptr{Cvoid}}(C_NULL)
         GC.@preserve c check(ccall((:bsk_spline_create, lib), Int32,
-            (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}), handle(B).ptr, pointer(c), length(c), out))
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}), handle(B; device).ptr, pointer(c), length(c), out))
         finalizer(h -> ccall((:bsk_spline_destroy, lib), Int32, (Ptr{Cvoid},), h.ptr), SplineHandle(out[]))
-    end
+    end; end
 end
 
 """
@@ -192,7 +197,7 @@ function evaluate(S::Spline{T}, xs::DeviceVector{T}, derivs::NTuple{N, Int} = (0
     ds = Int32[d for d in derivs]
     GC.@preserve ptrs ds check(ccall((:bsk_spline_eval, lib), Int32,
         (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Int32, Ptr{Cvoid}),
-        device_spline(S).ptr, xs.ptr, length(xs), N, ds, ptrs, algo, C_NULL))
+        device_spline(S; device = xs.device).ptr, xs.ptr, length(xs), N, ds, ptrs, algo, C_NULL))
     outs
 end
 
@@ -203,13 +208,13 @@ Base.Broadcast.broadcasted(S::Spline, xs::DeviceVector) = S(xs)
 # Spline is uploaded on first use by device_spline.
 
 # Host arrays, staged and pipelined inside the library (H2D | kernel | D2H overlapped):
-function evaluate(S::Spline{T}, xs::Vector{T}, derivs::NTuple{N, Int} = (0,); algo = 0) where {T, N}
+function evaluate(S::Spline{T}, xs::Vector{T}, derivs::NTuple{N, Int} = (0,); algo = 0, device = Int32(0)) where {T, N}
     outs = ntuple(_ -> Vector{T}(undef, length(xs)), Val(N))
     ptrs = Ptr{Cvoid}[pointer(o) for o in outs]
     ds = Int32[d for d in derivs]
     GC.@preserve xs outs ptrs ds check(ccall((:bsk_spline_eval_host, lib), Int32,
         (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Int32),
-        device_spline(S).ptr, pointer(xs), length(xs), N, ds, ptrs, algo))
+        device_spline(S; device).ptr, pointer(xs), length(xs), N, ds, ptrs, algo))
     outs
 end
 
@@ -220,7 +225,7 @@ function evaluate(B::AbstractBSplineBasis, C::DeviceMatrix{T}, xs::DeviceVector{
     out = DeviceVector{T}(undef, C.M * length(xs))
     check(ccall((:bsk_spline_eval_multi, lib), Int32,
         (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
-        handle(B).ptr, C.data.ptr, C.N, C.M, xs.ptr, length(xs), out.ptr, C_NULL))
+        handle(B; device = xs.device).ptr, C.data.ptr, C.N, C.M, xs.ptr, length(xs), out.ptr, C_NULL))
     DeviceMatrix{T}(out, C.M, length(xs))
 end
 
@@ -243,7 +248,7 @@ function Collocation.collocation_matrix(B::AbstractBSplineBasis, xs::DeviceVecto
     nout = Ref{Int64}(0)
     check(ccall((:bsk_collocation_matrix, lib), Int32,
         (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Float64, Ptr{Float64}, Ptr{Int64}, Ptr{Cvoid}),
-        handle(B).ptr, xs.ptr, N, n, clip_threshold, band.ptr, nout, C_NULL))
+        handle(B; device = xs.device).ptr, xs.ptr, N, n, clip_threshold, band.ptr, nout, C_NULL))
     nout[] > 0 && @warn "Non-zero value outside of matrix bands ($(nout[]) entries)"    # Collocation.jl:239-244
     out = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:bsk_banded_create, lib), Int32, (Ptr{Float64}, Int64, Int32, Int32, Int32, Ptr{Ptr{Cvoid}}),
@@ -252,9 +257,36 @@ function Collocation.collocation_matrix(B::AbstractBSplineBasis, xs::DeviceVecto
     finalizer(f -> ccall((:bsk_banded_destroy, lib), Int32, (Ptr{Cvoid},), f.ptr), F)
 end
 
-function LinearAlgebra.lu!(F::DeviceBandedLU{Float64})              # Collocation/matrix.jl:132-201
+# fast = false: BANFAC's own order, bit-identical factors; fast = true: partitioned elimination with checked
+# partition boundaries (n >= 1024), factors within ~1e-16 relative, ZeroPivotException(i) still thrown.
+# Rectangular collocation matrices (any number of points; least-squares fitting): the Matrix / SparseMatrixCSC
+# targets of collocation_matrix (Collocation/Collocation.jl:82-106,162-193).
+function Collocation.collocation_matrix(B::AbstractBSplineBasis, xs::DeviceVector{Float64}, deriv::Derivative{n},
+                                        ::Type{Matrix{Float64}}; clip_threshold = eps(Float64)) where {n}
+    nx, N = length(xs), length(B)
+    dense = DeviceVector{Float64}(undef, nx * N)
+    check(ccall((:bsk_collocation_rows, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Float64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+        handle(B; device = xs.device).ptr, xs.ptr, nx, n, clip_threshold, C_NULL, C_NULL, dense.ptr, C_NULL))
+    DeviceMatrix{Float64}(dense, nx, N)
+end
+
+function Collocation.collocation_matrix(B::AbstractBSplineBasis, xs::DeviceVector{Float64}, deriv::Derivative{n},
+                                        ::Type{SparseMatrixCSC{Float64}}; clip_threshold = eps(Float64)) where {n}
+    nx, N, k = length(xs), length(B), order(B)
+    col = DeviceVector{Int64}(undef, nx * k); val = DeviceVector{Float64}(undef, nx * k)
+    check(ccall((:bsk_collocation_rows, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Float64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+        handle(B; device = xs.device).ptr, xs.ptr, nx, n, clip_threshold, col.ptr, val.ptr, C_NULL, C_NULL))
+    J, V = Array(col), Array(val)
+    I = repeat(1:nx; inner = k)
+    keep = J .> 0
+    sparse(I[keep], J[keep], V[keep], nx, N)
+end
+
+function LinearAlgebra.lu!(F::DeviceBandedLU{Float64}; fast::Bool = false)     # Collocation/matrix.jl:132-201
     info = Ref{Int64}(0)
-    st = ccall((:bsk_banded_lu, lib), Int32, (Ptr{Cvoid}, Ptr{Int64}), F.ptr, info)
+    st = ccall((:bsk_banded_lu_mode, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}), F.ptr, Int32(fast), info)
     check(st, info[])
     F
 end
@@ -302,7 +334,7 @@ function Collocation.collocation_matrix(B::AbstractBSplineBasis, xs::DeviceVecto
     nout = Ref{Int64}(0)
     check(ccall((:bsk_collocation_matrix_f32, lib), Int32,
         (Ptr{Cvoid}, Ptr{Float32}, Int64, Int32, Float32, Ptr{Float32}, Ptr{Int64}, Ptr{Cvoid}),
-        handle(B).ptr, xs.ptr, N, n, Float32(clip_threshold), band.ptr, nout, C_NULL))
+        handle(B; device = xs.device).ptr, xs.ptr, N, n, Float32(clip_threshold), band.ptr, nout, C_NULL))
     nout[] > 0 && @warn "Non-zero value outside of matrix bands ($(nout[]) entries)"
     out = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:bsk_banded_f32_create, lib), Int32, (Ptr{Float32}, Int64, Int32, Int32, Int32, Ptr{Ptr{Cvoid}}),
@@ -322,6 +354,34 @@ function LinearAlgebra.ldiv!(F::DeviceBandedLU{Float32}, Y::DeviceMatrix{Float32
     Y.N == F.n || throw(DimensionMismatch("vectors `x` and `y` must have length $(F.n)"))
     check(ccall((:bsk_banded_f32_solve, lib), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int64, Int32, Ptr{Cvoid}),
                 F.ptr, Y.data.ptr, Y.M, Int32(0), C_NULL))
+    Y
+end
+
+# ---- periodic cubic bases: CyclicTridiagonalMatrix (Collocation/cyclic.jl:21-33, 112-197) ----------------
+"""Device factorisation of a `CyclicTridiagonalMatrix` (periodic cubic interpolation; `default_matrix_type`
+picks it for k = 4, Collocation/Collocation.jl:133-149).  The reference re-eliminates the matrix inside every
+`ldiv!` (cyclic.jl:121-197, re-copied from `C_copy` at SplineInterpolations.jl:147-149); here the tridiagonal
+part is factored once and `ldiv!` only streams the right-hand sides."""
+mutable struct DeviceCyclicLU{T} <: Factorization{T}
+    ptr::Ptr{Cvoid}
+    n::Int
+end
+Base.size(F::DeviceCyclicLU) = (F.n, F.n)
+
+function DeviceCyclicLU(A::Collocation.CyclicTridiagonalMatrix{Float64}; device = Int32(0))
+    a, b, c = collect(Float64, A.a), collect(Float64, A.b), collect(Float64, A.c)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve a b c check(ccall((:bsk_cyclic_create, lib), Int32,
+                (Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Ptr{Ptr{Cvoid}}),
+                a, b, c, length(b), device, out))
+    F = DeviceCyclicLU{Float64}(out[], length(b))
+    finalizer(f -> ccall((:bsk_cyclic_destroy, lib), Int32, (Ptr{Cvoid},), f.ptr), F)
+end
+
+function LinearAlgebra.ldiv!(F::DeviceCyclicLU, Y::DeviceMatrix{Float64})        # cyclic.jl:112-161
+    Y.N == F.n || throw(DimensionMismatch("all vectors must have length $(F.n)"))
+    check(ccall((:bsk_cyclic_solve, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Cvoid}),
+                F.ptr, Y.data.ptr, Y.M, C_NULL))
     Y
 end
 
@@ -365,7 +425,7 @@ function (f::SplineExtrapolations.SplineExtrapolation)(xs::DeviceVector{T}) wher
     ds = Int32[0]
     GC.@preserve ptrs ds check(ccall((:bsk_spline_eval_extrap, lib), Int32,
         (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Int32, Int32, Ptr{Cvoid}),
-        device_spline(S).ptr, xs.ptr, length(xs), 1, ds, ptrs, 0, extrap_code(SplineExtrapolations.method(f)), C_NULL))
+        device_spline(S; device = xs.device).ptr, xs.ptr, length(xs), 1, ds, ptrs, 0, extrap_code(SplineExtrapolations.method(f)), C_NULL))
     out
 end
 

@@ -19,6 +19,11 @@
  *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Kernels
  *    are enqueued and the call returns without synchronising, except the *_host
  *    convenience calls, which stage through device memory and synchronise.
+ *  - the handle-building calls (*_create, bsk_banded_lu[_mode], bsk_spline_set_coefs_device and the
+ *    lazy table build inside the first bsk_spline_eval of a spline) take no stream: they run on the
+ *    legacy default stream and return with their device work complete.  Streams from
+ *    bsk_stream_create are BLOCKING streams, which order against the default stream; work a caller
+ *    enqueues on its own non-blocking stream must be synchronised before such a call reads it.
  *  - there is no CPU fallback: with no CUDA device every compute call fails with
  *    BSK_ERR_CUDA.
  */
@@ -159,9 +164,11 @@ bsk_status bsk_evaluate_all(const bsk_basis *b, const void *d_x, int64_t n, int3
 /* ---- splines ----------------------------------------------------------------------
  * Spline(B, coefs) — Splines/spline.jl:41-60.  h_coefs: length(B) values of the basis
  * dtype (for a recombined basis they are converted to parent coefficients once here,
- * Recombinations/splines.jl:32-65).  bsk_spline_set_coefs_device re-points the handle at
- * device-resident coefficients (e.g. one column of a bsk_banded_solve result with
- * element stride `stride`). */
+ * Recombinations/splines.jl:32-65).  bsk_spline_set_coefs_device replaces the coefficients by
+ * device-resident ones (e.g. one column of a bsk_banded_solve result with element stride
+ * `stride`): they are copied (strided, synchronising `stream`), converted to the parent basis for a
+ * recombined spline and re-uploaded; tables and cached derivative splines are rebuilt on the next
+ * evaluation.  Not concurrent with evaluations of the same handle (it takes the handle's lock). */
 bsk_status bsk_spline_create(const bsk_basis *b, const void *h_coefs, int64_t ncoef,
                              bsk_spline **out);
 bsk_status bsk_spline_set_coefs_device(bsk_spline *s, const void *d_coefs, int64_t ncoef,
@@ -218,13 +225,25 @@ bsk_status bsk_spline_eval_multi(const bsk_basis *b, const void *d_coefs, int64_
  * collocation_matrix!(C, B, x, Derivative(deriv); clip_threshold) —
  * Collocation/Collocation.jl:209-251 into CollocationMatrix band storage
  * data[u+1+i-j, j], (2k-3) x length(B) column-major (Collocation/matrix.jl:105-117,
- * Collocation.jl:165-198).  d_x: nx F64 points (nx must equal length(B)).
+ * Collocation.jl:165-198).  d_x: nx F64 points (nx must equal length(B): the band store is square, like the
+ * reference's CollocationMatrix; other shapes: bsk_collocation_rows).
  * *h_n_outside (optional) receives the number of non-clipped entries that fell outside
  * the bands (the reference emits one @warn each, Collocation.jl:239-244).  Synchronises
  * only if h_n_outside != NULL. */
 bsk_status bsk_collocation_matrix(const bsk_basis *b, const double *d_x, int64_t nx,
                                   int32_t deriv, double clip_threshold, double *d_band,
                                   int64_t *h_n_outside, void *stream);
+/* collocation_matrix! for ANY number of points nx (rectangular matrices: least-squares fitting with more data
+ * than basis functions) — the Matrix / SparseMatrixCSC targets of Collocation/Collocation.jl:82-106,162-193,
+ * 209-251.  Row form with exactly k slots per point: d_col[nx][k] = 1-based column index (0: clipped entry, or
+ * point outside the domain of a non-periodic basis), d_val[nx][k] = D^deriv b_col(x_i), slots in the reference's
+ * order (column jlast + 1 - dj, dj = 1..k; periodic columns wrapped, BSplines/periodic.jl:245-253) — the rows of
+ * a CSR / ELL matrix, from which the shim builds SparseMatrixCSC.  d_dense (optional): nx x length(B)
+ * column-major (a Julia Matrix), zero-filled here.  Any of the three outputs may be NULL.  Plain, periodic and
+ * recombined Float64 bases. */
+bsk_status bsk_collocation_rows(const bsk_basis *b, const double *d_x, int64_t nx, int32_t deriv,
+                                double clip_threshold, int64_t *d_col, double *d_val, double *d_dense,
+                                void *stream);
 /* Periodic cubic: CyclicTridiagonalMatrix diagonals a, b, c (Collocation/cyclic.jl:21-33). */
 bsk_status bsk_collocation_cyclic(const bsk_basis *b, const double *d_x, int64_t nx,
                                   int32_t deriv, double clip_threshold, double *d_a, double *d_b,

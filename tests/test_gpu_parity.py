@@ -1389,3 +1389,147 @@ def test_partitioned_lu_zero_pivot_and_fallback(bk, oracle):
     assert oracle.banded_lu(ref) == 0
     got = bk.CollocationMatrix(slow.copy(order="F")).lu_(bk.LU_FAST).data()
     assert np.max(np.abs(got - ref) / np.max(np.abs(ref), axis=0)) < 1e-13
+
+
+@pytest.mark.parametrize("kind", ["plain", "periodic", "robin"])
+def test_collocation_rows_rectangular(bk, oracle, synth, kind):
+    """collocation_matrix(B, x, deriv, Matrix / SparseMatrixCSC) with MORE points than basis functions
+    (src/Collocation/Collocation.jl:82-106,162-193,209-251): row form (k slots per point) and dense form, bit-exact
+    against the entries evaluate_all gives the reference loop; points outside the domain leave empty rows
+    (Collocation.jl:224), entries <= clip_threshold are dropped (:237)."""
+    import torch
+    k = 5
+    br = synth.breakpoints(21, 30)
+    nx = 500
+    if kind == "periodic":
+        B = bk.PeriodicBSplineBasis(k, br)
+        x = -0.7 + 2.4 * synth.u_numpy(22, 0, nx)
+        okind, ot, rc = 1, br, None
+    else:
+        P = bk.BSplineBasis(k, br)
+        ot = P.knots()
+        okind = 0
+        if kind == "robin":
+            B = bk.RecombinedBSplineBasis(P, bk.Derivative(0) + 3 * bk.Derivative(1))
+            rc = oracle.robin_corners(k, ot, [1.0, 3.0])
+        else:
+            B, rc = P, None
+        x = np.concatenate([-0.1 + 1.2 * synth.u_numpy(22, 0, nx - 2), [0.0, 1.0]])
+    N = len(B)
+    eps = np.finfo(np.float64).eps
+    for nd in (0, 2):
+        i_ref, bs_ref = oracle.evaluate_all(okind, k, ot, x, nderiv=nd, recomb=rc)
+        ref = np.zeros((nx, N))
+        inside = np.ones(nx, dtype=bool) if kind == "periodic" else (x >= 0) & (x <= 1)
+        for i in range(nx):
+            if not inside[i]:
+                continue
+            for dj in range(1, k + 1):
+                j = i_ref[i] + 1 - dj
+                if kind == "periodic":
+                    j = (j - 1) % N + 1
+                if 1 <= j <= N and abs(bs_ref[i, dj - 1]) > eps:
+                    ref[i, j - 1] = bs_ref[i, dj - 1]
+        col, val = bk.collocation_rows(B, x, bk.Derivative(nd))
+        col, val = col.cpu().numpy(), val.cpu().numpy()
+        got = np.zeros((nx, N))
+        for dj in range(k):
+            m = col[:, dj] > 0
+            got[np.nonzero(m)[0], col[m, dj] - 1] = val[m, dj]
+        assert np.array_equal(got, ref), (kind, nd)
+        assert np.all(col[~inside] == 0) and np.all(val[col == 0] == 0.0)
+        dense = bk.collocation_rows(B, x, bk.Derivative(nd), dense=True).cpu().numpy()
+        assert dense.shape == (nx, N) and np.array_equal(dense, ref)
+    if kind == "plain":                                       # least squares with the rectangular matrix reproduces a spline
+        c = 2 * synth.u_numpy(23, 0, N) - 1
+        xin = synth.u_numpy(24, 0, 400)
+        A = bk.collocation_rows(B, xin, dense=True).cpu().numpy()
+        y = oracle.spline_eval(0, k, ot, c, xin)
+        assert np.max(np.abs(np.linalg.lstsq(A, y, rcond=None)[0] - c)) < 1e-11
+
+
+@pytest.mark.parametrize("k", [2, 4, 5, 7])
+def test_integral(bk, oracle, synth, k):
+    """integral(S) (src/Splines/spline.jl:354-374): zero at the left boundary (test/splines.jl:62-66), the
+    derivative of the integral is S again (coefficients to rounding), I(b) - I(a) equals a Gauss-Legendre
+    quadrature of S piece by piece; periodic splines (src/Splines/periodic.jl:122-140): differences of the
+    integral agree with those of the equivalent non-periodic spline (test/periodic.jl:153-155)."""
+    br = synth.breakpoints(3, 40)
+    B = bk.BSplineBasis(k, br)
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    I = bk.integral(S)
+    assert I.k == k + 1 and I.knots().size == B.knots().size + 2
+    t = B.knots()
+    ref = np.concatenate([[0.0], np.cumsum(c * (t[k:] - t[:-k]) / k)])
+    assert np.array_equal(I.coefficients(), ref)
+    assert I(np.array([0.0]), algo=bk.EVAL_DEBOOR)[0] == 0.0        # Sint(a) == 0 (test/splines.jl:66), de Boor order
+    assert abs(I(np.array([0.0]))[0]) < 1e-15 * np.max(np.abs(ref))    # default (table) path: to rounding
+    dI = bk.Derivative(1) * I
+    assert np.max(np.abs(dI.coefficients() - c)) < 1e-13
+    xs = synth.u_numpy(5, 0, 2000)
+    assert relerr(dI(xs), S(xs)) < 1e-13
+    # quadrature of S over [0, x1] piece by piece
+    qx, qw = np.polynomial.legendre.leggauss(k)
+    x1 = 0.77
+    edges = np.concatenate([br[br < x1], [x1]])
+    tot = 0.0
+    for a_, b_ in zip(edges[:-1], edges[1:]):
+        xm = 0.5 * (a_ + b_) + 0.5 * (b_ - a_) * qx
+        tot += 0.5 * (b_ - a_) * np.dot(qw, oracle.spline_eval(0, k, t, c, xm))
+    assert abs(I(np.array([x1]))[0] - tot) < 1e-14
+    # periodic
+    if k >= 3:
+        L = 2.0
+        brp = L * synth.breakpoints(8, 31) - 1.0
+        Bp = bk.PeriodicBSplineBasis(k, brp)
+        cp = 2 * synth.u_numpy(9, 0, len(Bp)) - 1
+        Sp = bk.Spline(Bp, cp)
+        Ip = bk.integral(Sp)
+        assert Ip.k == k + 1
+        assert abs(Ip(np.array([brp[0]]))[0]) < 1e-15
+        xa, xb = -0.4, 0.55
+        edges = np.concatenate([[xa], brp[(brp > xa) & (brp < xb)], [xb]])
+        tot = 0.0
+        for a_, b_ in zip(edges[:-1], edges[1:]):
+            xm = 0.5 * (a_ + b_) + 0.5 * (b_ - a_) * qx
+            tot += 0.5 * (b_ - a_) * np.dot(qw, oracle.spline_eval(1, k, brp, cp, xm))
+        got = Ip(np.array([xb]))[0] - Ip(np.array([xa]))[0]
+        assert abs(got - tot) < 1e-13
+    with pytest.raises(bk.UnsupportedError):
+        bk.integral(bk.Spline(bk.BSplineBasis(8, br), np.ones(len(br) + 6)))
+
+
+@pytest.mark.parametrize("dt", ["int32", "complex64", "complex128", "f32x2"])
+def test_interpolate_other_element_types(bk, synth, dt):
+    """test/interpolation.jl:53-60 — data of type Int32, ComplexF32 (and ComplexF64), SVector{2,Float32} on
+    Float64 points: `S.(xs) ≈ ys` with the coefficient type float(eltype(y))."""
+    import torch
+    n, k = 40, 4
+    xs = np.sort(np.random.default_rng(42).standard_normal(n))
+    u = lambda s: 2 * synth.u_numpy(s, 0, n) - 1
+    if dt == "int32":
+        ys = (np.floor(31 * synth.u_numpy(60, 0, n)) - 15).astype(np.int32)
+        S = bk.interpolate(xs, ys, bk.BSplineOrder(k)).spline
+        assert S.coefficients().dtype == np.float64
+        assert np.allclose(S(xs), ys, rtol=1e-12, atol=1e-12)
+    elif dt.startswith("complex"):
+        ys = (u(61) + 1j * u(62)).astype(np.complex64 if dt == "complex64" else np.complex128)
+        itp = bk.interpolate(xs, ys, bk.BSplineOrder(k))
+        S = itp.spline
+        assert itp.coefs.dtype == (torch.complex64 if dt == "complex64" else torch.complex128)
+        got = S(xs)
+        assert np.iscomplexobj(got)
+        assert np.allclose(got, ys, rtol=1e-6 if dt == "complex64" else 1e-12, atol=1e-6 if dt == "complex64" else 1e-12)
+        # linearity: the real part is the interpolant of the real part
+        Sr = bk.interpolate(xs, ys.real.astype(np.float64), bk.BSplineOrder(k)).spline
+        xq = np.linspace(xs[0], xs[-1], 301)
+        assert np.max(np.abs(S(xq).real - Sr(xq))) < 1e-12
+        # natural boundary conditions, complex data (test/interpolation.jl:24-47)
+        Sn = bk.interpolate(xs, ys, bk.BSplineOrder(k), bk.Natural()).spline
+        assert np.allclose(Sn(xs), ys, rtol=1e-6, atol=1e-6)
+    else:
+        ys = np.stack([u(63), u(64)], axis=1).astype(np.float32)
+        itp = bk.interpolate(xs, ys, bk.BSplineOrder(k))
+        got = itp.splines(torch.from_numpy(xs).cuda()).cpu().numpy()
+        assert np.allclose(got, ys, rtol=1e-6, atol=1e-6)
