@@ -542,6 +542,26 @@ def run_ours(args):
         ms = timed(lambda: S4.evaluate(x4, (0,), out=o4), 5)
         extra["c4_periodic_eval"] = {"ms": ms, "gpoints_per_s": world * npts / (ms * 1e-3) / 1e9,
                                      "roofline_frac": 16.0 * npts / (ms * 1e-3) / 1e9 / peak}
+        # what the memory system gives this access pattern by itself (8 B in, ONE random 32-byte sector from an
+        # L2-resident table, 8 B out; bsk_probe_gather): the bound of the global-table kernels (C4, C5)
+        try:
+            tab = synth.u_torch(12, 0, 4 * 320000)
+            ng = npts // 2 * 2
+            best = None
+            for variant in (0, 1, 2, 3):
+                call = lambda: _bl.check(_bl.lib.bsk_probe_gather(ctypes.c_void_p(x4.data_ptr()), ctypes.c_void_p(o4[0].data_ptr()),
+                                                                  ng, ctypes.c_void_p(tab.data_ptr()), 320000, variant, sp()))
+                msg = timed(call, 5)
+                extra["c4_periodic_eval"]["gather_probe_v%d_gpoints_per_s" % variant] = ng / (msg * 1e-3) / 1e9
+                best = msg if best is None else min(best, msg)
+            extra["c4_periodic_eval"]["frac_of_gather_probe"] = best / ms * (npts / ng)
+            extra["c4_periodic_eval"]["note"] = ("table in global memory (10^4 intervals do not fit one SM's shared memory): bound by the "
+                                                 "random-sector rate L2 -> SM; probe variants: 0 LDG points, 1 TMA point rings, 2/3 the same "
+                                                 "with L1::no_allocate gathers")
+            S4.evaluate(x4, (0,), out=o4)          # the probe wrote into the result buffer: restore it for the parity check
+            del tab
+        except Exception as exc:
+            print("gather probe skipped: %r" % (exc,), file=sys.stderr)
         if rank == 0:
             x4h = x4[:1 << 16].cpu().numpy()
             r4 = O.spline_eval(1, 4, br4, S4.coefficients(), x4h)

@@ -67,6 +67,7 @@ SIGNATURES = {
     "bsk_probe_stream_1r2w": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "bsk_probe_stream_1r2w_tma": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "bsk_probe_fma": (_i32, [_i32, _i64, _vp, C.POINTER(_dbl), _vp]),
+    "bsk_probe_gather": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp]),
     "bsk_probe_copy_host": (_i32, [_vp, _vp, _i64, _i32, _pp]),
     "bsk_malloc": (_i32, [_i32, C.c_size_t, _pp]),
     "bsk_free": (_i32, [_i32, _vp]),

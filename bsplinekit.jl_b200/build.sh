@@ -8,7 +8,7 @@ mkdir -p "$OUT" "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -ccbin /usr/bin/g++ -Xcompiler -fPIC,-ffp-contract=off -Xptxas -v"
 pids=()
-for f in bsk_api bsk_eval bsk_solve bsk_host bsk_eval_cell bsk_eval_cell_f32 bsk_solve_win bsk_multi bsk_cyclic_banded bsk_galerkin bsk_solve_f32; do
+for f in bsk_api bsk_eval bsk_solve bsk_host bsk_eval_cell bsk_eval_cell_f32 bsk_solve_win bsk_multi bsk_cyclic_banded bsk_galerkin bsk_solve_f32 bsk_probe; do
   src="$HERE/csrc/$f.cu"
   extra=""
   if [ "$f" = "bsk_eval_cell_f32" ]; then src="$HERE/csrc/bsk_eval_cell.cu"; extra="-DBSK_CELL_F32"; fi
@@ -19,5 +19,5 @@ for f in bsk_api bsk_eval bsk_solve bsk_host bsk_eval_cell bsk_eval_cell_f32 bsk
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o "$OUT/libbsplinekit_b200.so" "$OBJ"/bsk_api.o "$OBJ"/bsk_eval.o "$OBJ"/bsk_solve.o "$OBJ"/bsk_host.o "$OBJ"/bsk_eval_cell.o "$OBJ"/bsk_eval_cell_f32.o "$OBJ"/bsk_solve_win.o "$OBJ"/bsk_multi.o "$OBJ"/bsk_cyclic_banded.o "$OBJ"/bsk_galerkin.o "$OBJ"/bsk_solve_f32.o -lcudart_static -ldl -lrt -lpthread
+$NVCC -shared -o "$OUT/libbsplinekit_b200.so" "$OBJ"/bsk_api.o "$OBJ"/bsk_eval.o "$OBJ"/bsk_solve.o "$OBJ"/bsk_host.o "$OBJ"/bsk_eval_cell.o "$OBJ"/bsk_eval_cell_f32.o "$OBJ"/bsk_solve_win.o "$OBJ"/bsk_multi.o "$OBJ"/bsk_cyclic_banded.o "$OBJ"/bsk_galerkin.o "$OBJ"/bsk_solve_f32.o "$OBJ"/bsk_probe.o -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT/libbsplinekit_b200.so"

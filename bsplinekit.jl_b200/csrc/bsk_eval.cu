@@ -86,6 +86,12 @@ k_find_interval(KnotView<KT> kv, const KT *__restrict__ x, int64_t n, int64_t *_
 }
 
 // ---- K2 ---------------------------------------------------------------------------------
+__device__ __forceinline__ void stg256(void *p, const int4 &lo, const int4 &hi) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
+
 // One thread per point; the K values of a point are a row of K * sizeof(VT) bytes of the [n][K] output.
 // WIDE = 1: the 32 rows of a warp (one contiguous block of the output) are staged in shared memory and
 // leave as 16-byte vectors, each store instruction of the warp covering 512 contiguous bytes; the
@@ -128,7 +134,21 @@ k_evaluate_all(KnotView<KT> kv, RecombView rv, const KT *__restrict__ x, int64_t
             idx[p] = i;
         }
         const int64_t p0 = p - lane;
-        if (WIDE && p0 + 32 <= n) {
+        if constexpr (WIDE == 2) {
+            // rows that are whole 32-byte sectors leave as 256-bit stores (SASS STG.E.ENL2.256, sm_100+): every lane
+            // writes its own row, a warp covers 32 * RB contiguous bytes, no staging at all
+            constexpr int RB = K * (int)sizeof(VT);
+            static_assert(RB % 32 == 0, "WIDE = 2 needs rows of whole sectors");
+            if (live) {
+#pragma unroll
+                for (int w = 0; w < RB / 32; ++w) {
+                    int4 lo, hi;
+                    memcpy(&lo, &bq[w * (32 / (int)sizeof(VT))], 16);
+                    memcpy(&hi, &bq[w * (32 / (int)sizeof(VT)) + 16 / (int)sizeof(VT)], 16);
+                    stg256((char *)(bs + p * K) + 32 * w, lo, hi);
+                }
+            }
+        } else if (WIDE && p0 + 32 <= n) {
             // 16-byte vectors of the warp's block; a lane's row is NVL of them.  Lanes of one shared-memory phase
             // are NVL vectors apart, which for NVL = 2, 4 lands them on the same bank groups: the vector index is
             // XOR-swizzled by its 128-byte line number (writes and reads alike), conflict-free both ways.
@@ -769,9 +789,21 @@ bsk_status launch_eval_all(const bsk_basis *b, const KT *d_x, int64_t n, int der
     size_t smem = knots_smem_bytes<KT>(b);
     int stage = smem <= kSmemStageLimit;
     if (!stage) smem = 0;
-    smem = ((smem + 15) & ~(size_t)15) + (size_t)kThreads * K * sizeof(VT);      // + the row staging of WIDE
+    constexpr bool kSectorRows = (K * sizeof(VT)) % 32 == 0;
     const bool wide = (((uintptr_t)d_bs) & 15) == 0 && getenv("BSK_EVALALL_NARROW") == nullptr;
+    const bool wide256 = kSectorRows && wide && (((uintptr_t)d_bs) & 31) == 0 && getenv("BSK_EVALALL_STAGED") == nullptr;
+    smem = (smem + 15) & ~(size_t)15;
+    if (!wide256) smem += (size_t)kThreads * K * sizeof(VT);      // + the row staging of WIDE = 1
     int grid = grid_for(n, b->device, 8);
+    if constexpr (kSectorRows) {
+        if (wide256) {
+            auto kern = k_evaluate_all<K, KIND, KT, VT, 2>;
+            BSK_CUDA(set_smem(kern, smem));
+            kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs, stage);
+            BSK_CUDA(cudaGetLastError());
+            return BSK_OK;
+        }
+    }
     if (wide) {
         auto kern = k_evaluate_all<K, KIND, KT, VT, 1>;
         BSK_CUDA(set_smem(kern, smem));

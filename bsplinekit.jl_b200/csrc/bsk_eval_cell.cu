@@ -73,7 +73,9 @@ template <int K, typename T> struct CellRec {
 // (SASS LDG.E.ENL2.256, sm_100+): a gather of 32 random records costs the L1 pipe 32 wavefronts
 // instead of the 64 of two 128-bit loads, and that pipe is what bounds the global-table kernels.
 __device__ __forceinline__ void ldg256(const void *p, int4 &lo, int4 &hi) {
-    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    // L1::no_allocate: the table is far larger than L1 (hit rate 0.6 %); not allocating lines for the gathers is
+    // worth 2 % on the bare access pattern (bsk_probe_gather, variants 0 / 2)
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
                  : "l"(p));
 }

@@ -119,6 +119,13 @@ bsk_status bsk_probe_stream_1r2w_tma(const double *d_in, double *d_out0, double 
  * thread at full occupancy; *fma_count = fused multiply-adds executed by the launch (time it with events).
  * The denominators of the pipe fractions bench.py reports beside the HBM fractions. */
 bsk_status bsk_probe_fma(int32_t dtype, int64_t iters, void *d_scratch, double *fma_count, void *stream);
+/* The memory behaviour of the global-table evaluation kernels (C4, C5) and nothing else: n doubles streamed in,
+ * for each ONE 32-byte record gathered from a table of nrec records that lives in L2 (index (int)(x * nrec), x in
+ * [0, 1)), a cubic Horner, n doubles streamed out.  variant 0 = the product kernel's access scheme (LDG.128 point
+ * vectors with software prefetch, 256-bit gathers); the other variants move the point stream by per-warp TMA rings
+ * of several shapes or change cache hints (csrc/bsk_probe.cu).  States the bound of those evaluations. */
+bsk_status bsk_probe_gather(const double *d_x, double *d_out, int64_t n, const double *d_table, int64_t nrec,
+                            int32_t variant, void *stream);
 /* Copy-only twin of bsk_spline_eval_host: the same chunks on the same streams, host -> device copy of the
  * points and device -> host copy of nout result buffers, NO kernel — what the platform (PCIe, host memory)
  * gives the host-buffer call.  h_outs are overwritten with whatever the staging buffers hold. */

@@ -48,6 +48,26 @@ if args.what == "eval":
     algo = {"auto": bk.EVAL_AUTO, "deboor": bk.EVAL_DEBOOR, "pp": bk.EVAL_PP}[args.algo]
     ms = timed(lambda: S.evaluate(xd, (0, 1), algo=algo, out=outs), args.reps)
     print("eval %s: %.3f ms  %.1f Gpt/s  %.1f GB/s" % (args.algo, ms, args.points / ms / 1e6, 24 * args.points / ms / 1e6))
+elif args.what == "gather":
+    # the access pattern of the global-table kernels alone (bsk_probe_gather), every variant
+    import ctypes
+    from bsplinekit_b200 import _lib as _bl
+    xd = synth.u_torch(9, 0, args.points)
+    out = torch.empty_like(xd)
+    for nrec in (320000, 1 << 20):
+        tab = synth.u_torch(12, 0, 4 * nrec)
+        ref = None
+        for variant in [int(v) for v in os.environ.get("VARIANTS", "0,1,2,3,4").split(",")]:
+            call = lambda: _bl.check(_bl.lib.bsk_probe_gather(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                              args.points, ctypes.c_void_p(tab.data_ptr()), nrec, variant, None))
+            out.zero_()
+            ms = timed(call, args.reps)
+            chk = out[::4099].clone()
+            if ref is None:
+                ref = chk
+            print("gather nrec=%d variant %2d: %.3f ms  %.1f Gpt/s  frac of 16 B/pt line %.3f  %s" % (
+                nrec, variant, ms, args.points / ms / 1e6, 16 * args.points / ms / 1e6 / 6547.2,
+                "ok" if torch.equal(chk, ref) else "MISMATCH"), flush=True)
 elif args.what == "evalc4":
     br = synth.breakpoints(8, 10001)
     B = bk.PeriodicBSplineBasis(4, br)
