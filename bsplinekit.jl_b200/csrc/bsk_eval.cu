@@ -46,10 +46,11 @@ inline int grid_for(int64_t n, int device, int ctas_per_sm) {
 }
 
 // Stage knots (+ LUT) into dynamic shared memory; returns the knot pointer to use.
-template <typename KT>
-__device__ __forceinline__ const KT *stage_knots(KnotView<KT> &kv, unsigned char *smem, int stage,
-                                                 size_t &off) {
-    if (!stage) return kv.t;
+// STAGE is a template parameter so that the knot / LUT reads of the staged kernels compile to LDS (a pointer
+// that may be shared OR global makes every one of them a generic LD).
+template <int STAGE, typename KT>
+__device__ __forceinline__ const KT *stage_knots(KnotView<KT> &kv, unsigned char *smem, size_t &off) {
+    if constexpr (!STAGE) return kv.t;
     KT *st = (KT *)(smem + off);
     for (int i = threadIdx.x; i < kv.nt; i += blockDim.x) st[i] = kv.t[i];
     off += ((size_t)kv.nt * sizeof(KT) + 15) & ~(size_t)15;
@@ -68,16 +69,56 @@ size_t knots_smem_bytes(const bsk_basis *b) {
 }
 
 // ---- K1 ---------------------------------------------------------------------------------
-template <int KIND, typename KT>
+template <int KIND, typename KT, int STAGE>
 __global__ void __launch_bounds__(kThreads)
 k_find_interval(KnotView<KT> kv, const KT *__restrict__ x, int64_t n, int64_t *__restrict__ idx,
-                int8_t *__restrict__ zone, int stage) {
+                int8_t *__restrict__ zone) {
     extern __shared__ __align__(16) unsigned char smem[];
     size_t off = 0;
-    const KT *t = stage_knots(kv, smem, stage, off);
+    const KT *t = stage_knots<STAGE>(kv, smem, off);
     __syncthreads();
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n;
-         p += (int64_t)gridDim.x * blockDim.x) {
+    // 16-byte vectors of points (the next one prefetched), 128-bit index stores; the C ABI only promises natural
+    // alignment, so the vector body starts at the first 16-byte boundary of x and needs idx 16-byte aligned there
+    constexpr int VEC = 16 / (int)sizeof(KT);
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t head = (int64_t)((16 - ((uintptr_t)x & 15)) & 15) / (int64_t)sizeof(KT);
+    if (head > n) head = n;
+    const bool vec_ok = (((uintptr_t)(idx + head)) & 15) == 0;
+    const int64_t nvec = vec_ok ? (n - head) / VEC : 0;
+    const int4 *x4 = (const int4 *)(x + head);
+    int64_t v = gtid;
+    int4 raw_next = make_int4(0, 0, 0, 0);
+    if (v < nvec) raw_next = x4[v];
+    for (; v < nvec; v += stride) {
+        const int4 raw = raw_next;
+        if (v + stride < nvec) raw_next = x4[v + stride];
+        KT xv[VEC];
+        memcpy(xv, &raw, 16);
+        long long iv[VEC];
+        int8_t zv[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            int z;
+            iv[q] = find_interval<KIND>(kv, t, xv[q], z);
+            zv[q] = (int8_t)z;
+        }
+        int4 *dst = (int4 *)(idx + head + v * VEC);
+#pragma unroll
+        for (int q = 0; q < VEC; q += 2) {
+            int4 o;
+            memcpy(&o, &iv[q], 16);
+            dst[q / 2] = o;
+        }
+        if (zone) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) zone[head + v * VEC + q] = zv[q];
+        }
+    }
+    // head and tail (or everything, if idx is not aligned like x)
+    const int64_t done_hi = head + nvec * VEC;
+    for (int64_t p = gtid; p < n; p += stride) {
+        if (p >= head && p < done_hi) { p += ((done_hi - p - 1) / stride) * stride; continue; }
         int z;
         int i = find_interval<KIND>(kv, t, x[p], z);
         idx[p] = i;
@@ -96,14 +137,13 @@ __device__ __forceinline__ void stg256(void *p, const int4 &lo, const int4 &hi) 
 // WIDE = 1: the 32 rows of a warp (one contiguous block of the output) are staged in shared memory and
 // leave as 16-byte vectors, each store instruction of the warp covering 512 contiguous bytes; the
 // strided per-lane stores of the plain variant touch every 32-byte sector K / 4 times over.
-template <int K, int KIND, typename KT, typename VT, int WIDE>
+template <int K, int KIND, typename KT, typename VT, int WIDE, int STAGE>
 __global__ void __launch_bounds__(kThreads)          // (forcing 6 CTAs / SM for K <= 4 spills: 48 instead of 75 Gpt/s)
 k_evaluate_all(KnotView<KT> kv, RecombView rv, const KT *__restrict__ x, int64_t n, int deriv,
-               const int64_t *__restrict__ ileft, int64_t *__restrict__ idx, VT *__restrict__ bs,
-               int stage) {
+               const int64_t *__restrict__ ileft, int64_t *__restrict__ idx, VT *__restrict__ bs) {
     extern __shared__ __align__(16) unsigned char smem[];
     size_t off = 0;
-    const KT *t = stage_knots(kv, smem, stage, off);
+    const KT *t = stage_knots<STAGE>(kv, smem, off);
     off = (off + 15) & ~(size_t)15;
     VT *const rows = (VT *)(smem + off) + (threadIdx.x >> 5) * (32 * K);     // this warp's 32 rows
     const int lane = threadIdx.x & 31;
@@ -191,15 +231,15 @@ k_evaluate_all(KnotView<KT> kv, RecombView rv, const KT *__restrict__ x, int64_t
 }
 
 // ---- K3a: de Boor, reference operation order ------------------------------------------------
-template <int K, int KIND, typename T>
+template <int K, int KIND, typename T, int STAGE>
 __global__ void __launch_bounds__(kThreads)
 k_spline_deboor(KnotView<T> kv, const T *__restrict__ coefs, int ncoef, const T *__restrict__ x,
-                int64_t n, T *__restrict__ out, int stage, int extrap) {
+                int64_t n, T *__restrict__ out, int extrap) {
     extern __shared__ __align__(16) unsigned char smem[];
     size_t off = 0;
-    const T *t = stage_knots(kv, smem, stage, off);
+    const T *t = stage_knots<STAGE>(kv, smem, off);
     const T *c = coefs;
-    if (stage) {
+    if constexpr (STAGE) {
         T *sc = (T *)(smem + off);
         for (int i = threadIdx.x; i < ncoef; i += blockDim.x) sc[i] = coefs[i];
         c = sc;
@@ -536,11 +576,16 @@ bsk_status launch_deboor(const bsk_spline *s, const T *d_x, int64_t n, T *d_out,
     size_t smem = knots_smem_bytes<T>(b) + (size_t)s->ncoef * sizeof(T);
     int stage = smem <= kSmemStageLimit ? 1 : 0;
     if (!stage) smem = 0;
-    auto kern = k_spline_deboor<K, KIND, T>;
-    BSK_CUDA(set_smem(kern, smem));
     int ctas = stage ? std::max<int>(1, (int)std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem, 1))) : 8;
     int grid = grid_for(n, b->device, ctas);
-    kern<<<grid, kThreads, smem, st>>>(kv, (const T *)s->d_coefs, (int)s->ncoef, d_x, n, d_out, stage, extrap);
+    if (stage) {
+        auto kern = k_spline_deboor<K, KIND, T, 1>;
+        BSK_CUDA(set_smem(kern, smem));
+        kern<<<grid, kThreads, smem, st>>>(kv, (const T *)s->d_coefs, (int)s->ncoef, d_x, n, d_out, extrap);
+    } else {
+        auto kern = k_spline_deboor<K, KIND, T, 0>;
+        kern<<<grid, kThreads, 0, st>>>(kv, (const T *)s->d_coefs, (int)s->ncoef, d_x, n, d_out, extrap);
+    }
     BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }
@@ -737,6 +782,22 @@ bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout,
 
 }  // namespace
 
+namespace {
+template <int KIND, typename KT>
+bsk_status launch_find(const bsk_basis *b, const KT *d_x, int64_t n, int64_t *d_idx, int8_t *d_zone, cudaStream_t st) {
+    KnotView<KT> kv = make_view<KT>(b);
+    const size_t smem = knots_smem_bytes<KT>(b);
+    const int grid = grid_for(n, b->device, 8);
+    if (smem <= kSmemStageLimit) {
+        BSK_CUDA(set_smem(k_find_interval<KIND, KT, 1>, smem));
+        k_find_interval<KIND, KT, 1><<<grid, kThreads, smem, st>>>(kv, d_x, n, d_idx, d_zone);
+    } else {
+        k_find_interval<KIND, KT, 0><<<grid, kThreads, 0, st>>>(kv, d_x, n, d_idx, d_zone);
+    }
+    return BSK_OK;
+}
+}  // namespace
+
 // ============================================================================================
 extern "C" {
 
@@ -747,33 +808,12 @@ bsk_status bsk_find_knot_interval(const bsk_basis *b, const void *d_x, int64_t n
     BSK_CUDA(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int periodic = b->kind == BSK_BASIS_PERIODIC;
-    if (b->dtype == BSK_F64) {
-        KnotView<double> kv = make_view<double>(b);
-        size_t smem = knots_smem_bytes<double>(b);
-        int stage = smem <= kSmemStageLimit;
-        if (!stage) smem = 0;
-        int grid = grid_for(n, b->device, 8);
-        if (periodic) {
-            BSK_CUDA(set_smem(k_find_interval<1, double>, smem));
-            k_find_interval<1, double><<<grid, kThreads, smem, st>>>(kv, (const double *)d_x, n, d_idx, d_zone, stage);
-        } else {
-            BSK_CUDA(set_smem(k_find_interval<0, double>, smem));
-            k_find_interval<0, double><<<grid, kThreads, smem, st>>>(kv, (const double *)d_x, n, d_idx, d_zone, stage);
-        }
-    } else {
-        KnotView<float> kv = make_view<float>(b);
-        size_t smem = knots_smem_bytes<float>(b);
-        int stage = smem <= kSmemStageLimit;
-        if (!stage) smem = 0;
-        int grid = grid_for(n, b->device, 8);
-        if (periodic) {
-            BSK_CUDA(set_smem(k_find_interval<1, float>, smem));
-            k_find_interval<1, float><<<grid, kThreads, smem, st>>>(kv, (const float *)d_x, n, d_idx, d_zone, stage);
-        } else {
-            BSK_CUDA(set_smem(k_find_interval<0, float>, smem));
-            k_find_interval<0, float><<<grid, kThreads, smem, st>>>(kv, (const float *)d_x, n, d_idx, d_zone, stage);
-        }
-    }
+    bsk_status rc;
+    if (b->dtype == BSK_F64) rc = periodic ? launch_find<1, double>(b, (const double *)d_x, n, d_idx, d_zone, st)
+                                           : launch_find<0, double>(b, (const double *)d_x, n, d_idx, d_zone, st);
+    else rc = periodic ? launch_find<1, float>(b, (const float *)d_x, n, d_idx, d_zone, st)
+                       : launch_find<0, float>(b, (const float *)d_x, n, d_idx, d_zone, st);
+    if (rc != BSK_OK) return rc;
     BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }
@@ -782,13 +822,11 @@ bsk_status bsk_find_knot_interval(const bsk_basis *b, const void *d_x, int64_t n
 
 namespace {
 
-template <int K, int KIND, typename KT, typename VT>
-bsk_status launch_eval_all(const bsk_basis *b, const KT *d_x, int64_t n, int deriv, const int64_t *d_ileft,
-                           int64_t *d_idx, VT *d_bs, cudaStream_t st) {
+template <int K, int KIND, typename KT, typename VT, int STAGE>
+bsk_status launch_eval_all_s(const bsk_basis *b, const KT *d_x, int64_t n, int deriv, const int64_t *d_ileft,
+                             int64_t *d_idx, VT *d_bs, cudaStream_t st) {
     KnotView<KT> kv = make_view<KT>(b);
-    size_t smem = knots_smem_bytes<KT>(b);
-    int stage = smem <= kSmemStageLimit;
-    if (!stage) smem = 0;
+    size_t smem = STAGE ? knots_smem_bytes<KT>(b) : 0;
     constexpr bool kSectorRows = (K * sizeof(VT)) % 32 == 0;
     const bool wide = (((uintptr_t)d_bs) & 15) == 0 && getenv("BSK_EVALALL_NARROW") == nullptr;
     const bool wide256 = kSectorRows && wide && (((uintptr_t)d_bs) & 31) == 0 && getenv("BSK_EVALALL_STAGED") == nullptr;
@@ -797,24 +835,32 @@ bsk_status launch_eval_all(const bsk_basis *b, const KT *d_x, int64_t n, int der
     int grid = grid_for(n, b->device, 8);
     if constexpr (kSectorRows) {
         if (wide256) {
-            auto kern = k_evaluate_all<K, KIND, KT, VT, 2>;
+            auto kern = k_evaluate_all<K, KIND, KT, VT, 2, STAGE>;
             BSK_CUDA(set_smem(kern, smem));
-            kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs, stage);
+            kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs);
             BSK_CUDA(cudaGetLastError());
             return BSK_OK;
         }
     }
     if (wide) {
-        auto kern = k_evaluate_all<K, KIND, KT, VT, 1>;
+        auto kern = k_evaluate_all<K, KIND, KT, VT, 1, STAGE>;
         BSK_CUDA(set_smem(kern, smem));
-        kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs, stage);
+        kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs);
     } else {
-        auto kern = k_evaluate_all<K, KIND, KT, VT, 0>;
+        auto kern = k_evaluate_all<K, KIND, KT, VT, 0, STAGE>;
         BSK_CUDA(set_smem(kern, smem));
-        kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs, stage);
+        kern<<<grid, kThreads, smem, st>>>(kv, b->rv, d_x, n, deriv, d_ileft, d_idx, d_bs);
     }
     BSK_CUDA(cudaGetLastError());
     return BSK_OK;
+}
+
+template <int K, int KIND, typename KT, typename VT>
+bsk_status launch_eval_all(const bsk_basis *b, const KT *d_x, int64_t n, int deriv, const int64_t *d_ileft,
+                           int64_t *d_idx, VT *d_bs, cudaStream_t st) {
+    if (knots_smem_bytes<KT>(b) <= kSmemStageLimit)
+        return launch_eval_all_s<K, KIND, KT, VT, 1>(b, d_x, n, deriv, d_ileft, d_idx, d_bs, st);
+    return launch_eval_all_s<K, KIND, KT, VT, 0>(b, d_x, n, deriv, d_ileft, d_idx, d_bs, st);
 }
 
 template <typename KT, typename VT>

@@ -161,6 +161,10 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
     constexpr bool JUMP = STAGE && bsk::cell_jump_scheme((int)sizeof(T), K);
     constexpr bool JPAD = JUMP && bsk::cell_jump_pad(K);            // flag + side index in the spare slot
     extern __shared__ __align__(16) unsigned char smem[];
+    // Programmatic dependent launch: the next launch on the stream may be scheduled as soon as SMs fall free, so
+    // that ITS table staging overlaps OUR tail; it touches points and results only after griddepcontrol.wait below
+    // (= this grid has completed and its writes are visible).  A no-op for launches without the attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- tables: staged in shared memory (STAGE = 1), or, when they are too large for it, read
     //      in place from global memory through L1/L2 by the very same code (STAGE = 0) ----------
     T *const d_rec = (T *)smem;
@@ -176,6 +180,8 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
         for (int i = threadIdx.x; i < m16; i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
+    // the tables were uploaded by the host long before; everything below depends on the previous kernel
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const T *const s_rec = STAGE ? d_rec : cv.rec;
     const T *const s_rc = STAGE ? d_rc : cv.rc;
     constexpr int XI = (K == 1) ? 1 : 0;                 // slot of the knot in a flagged record
@@ -364,15 +370,27 @@ bsk_status launch_cell_mask(const bsk_spline *s, const CellView<T> &cv, const PP
     const size_t smem = s->cell_smem;                    // 0: tables stay in global memory
     const int sms = sm_count(s->basis->device);
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nvec + kCellThreads - 1) / kCellThreads, sms));
+    // launched with programmatic stream serialization (see the kernel's griddepcontrol pair)
+    static const bool pdl = getenv("BSK_NO_PDL") == nullptr;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kCellThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const int ncoef = (int)s->ncoef;
     if (smem > 0) {
         auto kern = k_spline_cell<K, KIND, T, DMASK, 1, EX>;
         BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kCellThreads, smem, st>>>(cv, pv, kv, (int)s->ncoef, d_x, nvec, outs);
+        BSK_CUDA(cudaLaunchKernelEx(&cfg, kern, cv, pv, kv, ncoef, d_x, nvec, outs));
     } else {
         auto kern = k_spline_cell<K, KIND, T, DMASK, 0, EX>;
-        kern<<<grid, kCellThreads, 0, st>>>(cv, pv, kv, (int)s->ncoef, d_x, nvec, outs);
+        BSK_CUDA(cudaLaunchKernelEx(&cfg, kern, cv, pv, kv, ncoef, d_x, nvec, outs));
     }
-    BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }
 

@@ -67,6 +67,37 @@ def test_find_knot_interval_periodic(bk, oracle, synth, k):
     assert np.all(z == 0)
 
 
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("xoff,ioff", [(0, 0), (1, 0), (1, 1), (0, 1), (3, 1), (2, 2)])
+def test_find_knot_interval_any_alignment(bk, oracle, synth, dt, xoff, ioff):
+    """The vector body of K1 starts at the first 16-byte boundary of x; the C ABI only promises natural alignment
+    of x / idx / zone: every combination of offsets (and lengths shorter than one vector) gives the same integers."""
+    import ctypes
+    import torch
+    from bsplinekit_b200 import _lib as L
+    npdt = np.float64 if dt == "f64" else np.float32
+    tdt = torch.float64 if dt == "f64" else torch.float32
+    br = synth.breakpoints(3, 300).astype(npdt)
+    B = bk.BSplineBasis(4, br)
+    t = B.knots()
+    for n in (0, 1, 2, 3, 5, 1000, 70001):
+        x = _points(synth, 31 + n, n + 8, -0.1, 1.1)[:n].astype(npdt) if n else np.zeros(0, npdt)
+        xd = torch.zeros(n + 8, dtype=tdt, device="cuda")
+        xd[xoff:xoff + n] = torch.from_numpy(x).cuda()
+        idx = torch.full((n + 8,), -7, dtype=torch.int64, device="cuda")
+        zone = torch.full((n + 8,), 5, dtype=torch.int8, device="cuda")
+        es = xd.element_size()
+        L.check(L.lib.bsk_find_knot_interval(B._handle, ctypes.c_void_p(xd.data_ptr() + es * xoff), n,
+                                             ctypes.c_void_p(idx.data_ptr() + 8 * ioff),
+                                             ctypes.c_void_p(zone.data_ptr() + ioff), None))
+        i_ref, z_ref = oracle.find_knot_interval(0, 4, t, x, kt=dt) if n else (np.zeros(0, np.int64), np.zeros(0, np.int8))
+        ih, zh = idx.cpu().numpy(), zone.cpu().numpy()
+        assert np.array_equal(ih[ioff:ioff + n], i_ref) and np.array_equal(zh[ioff:ioff + n], z_ref)
+        # nothing written outside [ioff, ioff + n)
+        assert np.all(ih[:ioff] == -7) and np.all(ih[ioff + n:] == -7)
+        assert np.all(zh[:ioff] == 5) and np.all(zh[ioff + n:] == 5)
+
+
 def test_find_knot_interval_large_no_smem(bk, oracle, synth):
     """10^5 knots: the knot vector does not fit in shared memory (global-memory path)."""
     br = synth.breakpoints(10, 99996)
