@@ -1564,3 +1564,58 @@ def test_interpolate_other_element_types(bk, synth, dt):
         itp = bk.interpolate(xs, ys, bk.BSplineOrder(k))
         got = itp.splines(torch.from_numpy(xs).cuda()).cpu().numpy()
         assert np.allclose(got, ys, rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# stream ordering of the programmatically launched evaluation kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nbreaks,periodic", [(1000, False), (10000, True)])
+def test_back_to_back_launches_see_the_previous_results(bk, oracle, synth, nbreaks, periodic):
+    """The cell-table kernels are launched with programmatic stream serialization (their table staging may overlap
+    the tail of the previous kernel on the stream); points and results are only touched after griddepcontrol.wait.
+    A chain on ONE stream without any host synchronisation — torch kernel writes x, S(x) -> y, torch kernel maps y
+    back into the domain, S(y') -> z, several rounds — must give what the same chain gives step by step."""
+    import torch
+    k = 4
+    if periodic:
+        br = synth.breakpoints(8, nbreaks + 1)
+        B = bk.PeriodicBSplineBasis(k, br)
+        kind, tref = 1, br
+    else:
+        B = bk.BSplineBasis(k, synth.breakpoints(3, nbreaks))
+        kind, tref = 0, B.knots()
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    S = bk.Spline(B, c)
+    n = 1 << 21
+    x0 = synth.u_torch(41, 0, n)
+    S.evaluate(x0, (0,))                                   # tables built, nothing pending
+    torch.cuda.synchronize()
+    x = torch.empty_like(x0)
+    y = [torch.empty_like(x0)]
+    z = [torch.empty_like(x0)]
+    for rnd in range(6):
+        x.copy_(x0).mul_(0.5 + 0.07 * rnd)                 # producer kernels on the same stream
+        S.evaluate(x, (0,), out=y)
+        y[0].abs_().mul_(0.25).clamp_(0.0, 0.999)          # consumer / producer in between
+        S.evaluate(y[0], (0,), out=z)
+        S.evaluate(z[0].abs_().mul_(0.25).clamp_(0.0, 0.999), (0,), out=y)
+    torch.cuda.synchronize()
+    # the same chain on the host with the oracle, last round only (rounds are independent)
+    xh = x0.cpu().numpy()[: 1 << 16] * (0.5 + 0.07 * 5)
+    y1 = oracle.spline_eval(kind, k, tref, c, xh)
+    y1 = np.clip(np.abs(y1) * 0.25, 0.0, 0.999)
+    z1 = oracle.spline_eval(kind, k, tref, c, y1)
+    z1 = np.clip(np.abs(z1) * 0.25, 0.0, 0.999)
+    y2 = oracle.spline_eval(kind, k, tref, c, z1)
+    # each stage amplifies the 1e-15 of the previous one by |S'| ~ 1e3 .. 1e4: compare with that in mind
+    got = y[0].cpu().numpy()[: 1 << 16]
+    assert np.max(np.abs(got - y2)) < 1e-6 * np.max(np.abs(y2))
+    # and exactly reproducible against a fully synchronised replay of the same chain on the device
+    xs = (x0 * (0.5 + 0.07 * 5))
+    torch.cuda.synchronize()
+    a = S.evaluate(xs, (0,))[0]; torch.cuda.synchronize()
+    a = a.abs().mul(0.25).clamp(0.0, 0.999); torch.cuda.synchronize()
+    b = S.evaluate(a, (0,))[0]; torch.cuda.synchronize()
+    b = b.abs().mul(0.25).clamp(0.0, 0.999); torch.cuda.synchronize()
+    cfin = S.evaluate(b, (0,))[0]; torch.cuda.synchronize()
+    assert torch.equal(cfin, y[0])
