@@ -1425,14 +1425,17 @@ def galerkin_matrix(B, derivs=None, quadrature=None, as_band=False):
     Returns a CollocationMatrix handle (band store with k - 1 sub / super-diagonals), or the band store
     itself as a CUDA tensor when as_band=True (needed for k = 8: 15 bands exceed the solver's 13)."""
     d1, d2 = (0, 0) if derivs is None else (derivs[0].n, derivs[1].n)
-    if isinstance(B, PeriodicBSplineBasis):
-        raise _lib.UnsupportedError("Galerkin matrices of periodic bases are not built")
     qx, qw = _gauss_legendre(B.k) if quadrature is None else quadrature
     nb = 2 * (B.k - 1) + 1
     band = torch.empty((len(B), nb), dtype=torch.float64, device="cuda")      # == (nb, n) column-major
     check(lib.bsk_galerkin_matrix(B._handle, d1, d2, qx.ctypes.data_as(C.c_void_p), qw.ctypes.data_as(C.c_void_p),
                                   qx.size, _ptr(band), _stream()))
-    return band if as_band else CollocationMatrix(band)
+    if as_band:
+        return band
+    if isinstance(B, PeriodicBSplineBasis):
+        # SparseMatrixCSC in the reference (linear.jl:50-54,144): band + wrap-around corners = the cyclic band store
+        return CyclicBandedMatrix(band.cpu().numpy().T, shift=0)
+    return CollocationMatrix(band)
 
 
 def galerkin_projection(f, B, deriv=None):
@@ -1520,8 +1523,8 @@ def approximate(f, B, method=None):
     if method is None:
         method = ApproxByInterpolation(B)
     if isinstance(method, MinimiseL2Error):
-        if isinstance(B, PeriodicBSplineBasis):
-            raise _lib.UnsupportedError("MinimiseL2Error on periodic bases is not built")
+        if isinstance(B, PeriodicBSplineBasis):              # test/periodic.jl:75; factored at construction
+            return approximate_(f, SplineApproximation(method, B, galerkin_matrix(B)))
         Mfact = galerkin_matrix(B).lu_()                     # cholesky!(M) in the reference; M is SPD
         return approximate_(f, SplineApproximation(method, B, Mfact))
     if isinstance(method, VariationDiminishing):

@@ -268,13 +268,13 @@ k_spline_deboor(KnotView<T> kv, const T *__restrict__ coefs, int ncoef, const T 
 // ---- K3b: per-interval local-polynomial (pp) table (pp.cuh) -----------------------------------
 // Used when the uniform-cell table (bsk_eval_cell.cu) is not available: staged in shared memory
 // if it fits, otherwise served from global memory through L1/L2.
-template <int K, int KIND, typename T, int PTS>
+template <int K, int KIND, typename T, int PTS, int STAGE>
 __global__ void __launch_bounds__(kThreads)
 k_spline_pp(KnotView<T> kv, int ncoef, PPView<T> pv, const T *__restrict__ x, int64_t n,
-            EvalOuts outs, int stage) {
+            EvalOuts outs) {
     constexpr int REC = PPRec<K, T>::REC;
     extern __shared__ __align__(16) unsigned char smem[];
-    if (stage) {
+    if constexpr (STAGE) {               // (a template parameter: the table reads then compile to LDS)
         T *sr = (T *)smem;
         const int4 *src = (const int4 *)pv.rec;
         int4 *dst = (int4 *)sr;
@@ -521,6 +521,9 @@ bsk_status build_pp(bsk_spline *s) {
         s->cell_slow = tb.n_cell_slow;
         s->cell_valid = true;
     }
+    // the copies above come from pageable memory (they may return while the DMA is still in flight) and the
+    // evaluation kernels read the tables from ANY stream, before their griddepcontrol.wait: be done here
+    BSK_CUDA(cudaDeviceSynchronize());
     s->pp_valid = true;
     return BSK_OK;
 }
@@ -620,17 +623,16 @@ bsk_status launch_pp(const bsk_spline *s, const T *d_x, int64_t n, const EvalOut
     bool aligned = !scalar_only && (((uintptr_t)d_x) & 15) == 0;
     for (int o = 0; o < outs.nout; ++o) aligned = aligned && ((((uintptr_t)outs.out[o]) & 15) == 0);
     int ctas = stage ? std::max<int>(1, (int)std::min<size_t>(4, (220 * 1024) / std::max<size_t>(smem, 1))) : 4;
-    if (aligned) {
-        auto kern = k_spline_pp<K, KIND, T, PTS>;
+    const int grid = aligned ? grid_for((n + PTS - 1) / PTS, b->device, ctas) : grid_for(n, b->device, ctas);
+    auto go = [&](auto kern) -> bsk_status {
         BSK_CUDA(set_smem(kern, smem));
-        int grid = grid_for((n + PTS - 1) / PTS, b->device, ctas);
-        kern<<<grid, kThreads, smem, st>>>(kv, (int)s->ncoef, pv, d_x, n, outs, stage);
-    } else {
-        auto kern = k_spline_pp<K, KIND, T, 1>;
-        BSK_CUDA(set_smem(kern, smem));
-        int grid = grid_for(n, b->device, ctas);
-        kern<<<grid, kThreads, smem, st>>>(kv, (int)s->ncoef, pv, d_x, n, outs, stage);
-    }
+        kern<<<grid, kThreads, smem, st>>>(kv, (int)s->ncoef, pv, d_x, n, outs);
+        return BSK_OK;
+    };
+    bsk_status rc;
+    if (aligned) rc = stage ? go(k_spline_pp<K, KIND, T, PTS, 1>) : go(k_spline_pp<K, KIND, T, PTS, 0>);
+    else rc = stage ? go(k_spline_pp<K, KIND, T, 1, 1>) : go(k_spline_pp<K, KIND, T, 1, 0>);
+    if (rc != BSK_OK) return rc;
     BSK_CUDA(cudaGetLastError());
     return BSK_OK;
 }

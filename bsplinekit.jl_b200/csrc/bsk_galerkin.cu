@@ -24,11 +24,48 @@ struct Segments {
     int64_t nseg = 0;
 };
 
-// Knot segments inside the domain and their quadrature nodes (linear.jl:268-286, quadratures.jl:52-65).
+// PeriodicKnots ts[1 .. N + k] materialised with the reference's own arithmetic (BSplines/periodic.jl:62,102-115):
+// ts[i] = data[i - k / 2] shifted by repeated -+ L.
+std::vector<double> periodic_knot_vector(const bsk_basis *b) {
+    const int k = b->k;
+    const int64_t N = b->N;
+    const std::vector<double> &data = b->h_knots;             // N + 1 breakpoints
+    const double L = data.back() - data.front();
+    std::vector<double> ts((size_t)(N + k));
+    for (int64_t i = 1; i <= N + k; ++i) {
+        double x = 0.0;
+        int64_t j = i - k / 2;
+        while (j < 1) { x -= L; j += N; }
+        while (j > N + 1) { x += L; j -= N; }
+        ts[(size_t)i - 1] = x + data[(size_t)j - 1];
+    }
+    return ts;
+}
+
+// Knot segments and their quadrature nodes (linear.jl:268-286, quadratures.jl:52-65).  Plain / recombined bases:
+// the segments inside the domain.  Periodic bases: ALL segments of ts[1 .. N + k] — the projection loop has no
+// boundary test (projection.jl:72-96), the matrix loop keeps the N segments of the main period (linear.jl:277-279),
+// which the periodic gather kernel selects by index.
 bsk_status build_segments(const bsk_basis *b, const double *qx, const double *qw, int nq, Segments &sg) {
-    BSK_REQUIRE(b->kind != BSK_BASIS_PERIODIC, BSK_ERR_UNSUPPORTED, "Galerkin matrices of periodic bases are not built");
     BSK_REQUIRE(b->dtype == BSK_F64, BSK_ERR_UNSUPPORTED, "Galerkin assembly needs a Float64 basis");
     const int k = b->k;
+    if (b->kind == BSK_BASIS_PERIODIC) {
+        const std::vector<double> ts = periodic_knot_vector(b);
+        const int64_t nt = (int64_t)ts.size();
+        sg.seg_of_n.assign((size_t)nt + 1, -1);
+        for (int64_t n = 1; n < nt; ++n) {
+            const double tn = ts[n - 1], tn1 = ts[n];
+            if (tn1 == tn) continue;
+            const double alpha = (tn1 - tn) / 2, beta = (tn + tn1) / 2;
+            sg.seg_of_n[n] = (int32_t)sg.nseg++;
+            for (int q = 0; q < nq; ++q) {
+                sg.x.push_back(alpha * qx[q] + beta);
+                sg.y.push_back(alpha * qw[q]);
+                sg.ileft.push_back(n);
+            }
+        }
+        return BSK_OK;
+    }
     const int64_t nt = b->nt, N = b->N;
     const std::vector<double> &t = b->h_knots;
     const double xa = t[k - 1], xb = t[N];                 // boundaries(B)
@@ -80,6 +117,46 @@ k_galerkin_gather(const double *__restrict__ bs1, const double *__restrict__ bs2
                     const int64_t p = (int64_t)s * nq + q;
                     const double bi = bs1[p * k + di - 1], bj = bs2[p * k + dj - 1];
                     acc = xadd(acc, xmul(xmul(y[p], bi), bj));         // A[i, j] += y * bi * bj   (linear.jl:305)
+                }
+            }
+        }
+        band[e] = acc;
+    }
+}
+
+// Periodic bases: one thread per entry of the CYCLIC band store, data[bw + d, j] = A[(j + d) mod N, j], |d| <= bw =
+// k - 1 (N >= 2 k - 1, so that the 2 k - 1 offsets are distinct entries).  Entry (I, J) collects, for every pair
+// (delta_i, delta_j) with delta_j - delta_i = d, the main-period segment n in h + 1 .. h + N with n + 1 - delta_j = J
+// (mod N); the reference visits the segments in increasing n (linear.jl:268), hence the wrapped ones first.
+__global__ void __launch_bounds__(128)
+k_galerkin_gather_periodic(const double *__restrict__ bs1, const double *__restrict__ bs2,
+                           const int32_t *__restrict__ seg_of_n, const double *__restrict__ y, int nq, int k, int64_t N,
+                           double *__restrict__ band) {
+    const int bw = k - 1, nb = 2 * bw + 1, h = k / 2;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N * nb; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = e / nb;
+        const int d = (int)(e - j * nb) - bw;                  // i - j (cyclic)
+        const int64_t J = j + 1;
+        const int dj_lo = d > 0 ? 1 + d : 1, dj_hi = d < 0 ? k + d : k;
+        // n(delta_j) = h + 1 + ((J - 1 + delta_j) - (h + 1) mod N): increasing in delta_j up to one wrap
+        auto seg_n = [&](int dj) -> int64_t {
+            int64_t m = (J - 1 + dj - (h + 1)) % N;
+            if (m < 0) m += N;
+            return h + 1 + m;
+        };
+        const int64_t n_first = seg_n(dj_lo);
+        double acc = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int dj = dj_lo; dj <= dj_hi; ++dj) {
+                const int64_t n = seg_n(dj);
+                if ((n < n_first) != (pass == 0)) continue;        // pass 0: the wrapped (smaller) n, pass 1: the rest
+                const int s = seg_of_n[n];
+                if (s < 0) continue;
+                const int di = dj - d;
+                for (int q = 0; q < nq; ++q) {
+                    const int64_t p = (int64_t)s * nq + q;
+                    const double bi = bs1[p * k + di - 1], bj = bs2[p * k + dj - 1];
+                    acc = xadd(acc, xmul(xmul(y[p], bi), bj));
                 }
             }
         }
@@ -140,10 +217,14 @@ bsk_status bsk_galerkin_nodes(const bsk_basis *b, const double *h_qx, int32_t nq
 }
 
 // d_band: (2 (k - 1) + 1) x length(B) column-major band store, data[(k - 1) + i - j, j], fully overwritten.
+// Periodic bases: the same store read cyclically, data[(k - 1) + d, j] = A[(j + d) mod N, j] (the SparseMatrixCSC of
+// linear.jl:144 has exactly these entries).
 bsk_status bsk_galerkin_matrix(const bsk_basis *b, int32_t deriv1, int32_t deriv2, const double *h_qx,
                                const double *h_qw, int32_t nq, double *d_band, void *stream) {
     BSK_REQUIRE(b && h_qx && h_qw && d_band && nq >= 1, BSK_ERR_ARGUMENT, "NULL argument");
     BSK_REQUIRE(deriv1 >= 0 && deriv2 >= 0, BSK_ERR_ARGUMENT, "derivative order must be >= 0");
+    BSK_REQUIRE(b->kind != BSK_BASIS_PERIODIC || b->len >= 2 * b->k - 1, BSK_ERR_UNSUPPORTED,
+                "periodic Galerkin matrix: the cyclic band store needs length(B) >= 2 k - 1");
     Segments sg;
     bsk_status rc = build_segments(b, h_qx, h_qw, nq, sg);
     if (rc != BSK_OK) return rc;
@@ -169,8 +250,12 @@ bsk_status bsk_galerkin_matrix(const bsk_basis *b, int32_t deriv1, int32_t deriv
     const int off = b->rv.enabled ? b->rv.cl : 0;
     const int64_t nent = b->len * (2 * (k - 1) + 1);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nent + 127) / 128, 148 * 16));
-    k_galerkin_gather<<<grid, 128, 0, st>>>((const double *)d.bs1, bs2, (const int32_t *)d.seg, (const double *)d.y, nq, k, off,
-                                            b->nt, b->len, d_band);
+    if (b->kind == BSK_BASIS_PERIODIC)
+        k_galerkin_gather_periodic<<<grid, 128, 0, st>>>((const double *)d.bs1, bs2, (const int32_t *)d.seg,
+                                                         (const double *)d.y, nq, k, b->len, d_band);
+    else
+        k_galerkin_gather<<<grid, 128, 0, st>>>((const double *)d.bs1, bs2, (const int32_t *)d.seg, (const double *)d.y, nq, k, off,
+                                                b->nt, b->len, d_band);
     BSK_CUDA(cudaGetLastError());
     BSK_CUDA(cudaStreamSynchronize(st));                     // temporaries are released on return
     return BSK_OK;
@@ -200,8 +285,9 @@ bsk_status bsk_galerkin_projection(const bsk_basis *b, int32_t deriv, const doub
     if (rc != BSK_OK) return rc;
     const int off = b->rv.enabled ? b->rv.cl : 0;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((b->len + 127) / 128, 148 * 16));
+    const int64_t nt_seg = b->kind == BSK_BASIS_PERIODIC ? b->len + k : b->nt;      // length of the knot vector looped over
     k_galerkin_project<<<grid, 128, 0, st>>>((const double *)d.bs1, (const int32_t *)d.seg, (const double *)d.y, d_fx, nq, k,
-                                             off, b->nt, b->len, d_phi);
+                                             off, nt_seg, b->len, d_phi);
     BSK_CUDA(cudaGetLastError());
     BSK_CUDA(cudaStreamSynchronize(st));
     return BSK_OK;

@@ -478,6 +478,61 @@ def galerkin_projection(f, k, t, nderiv=0, recomb=None):
     return phi
 
 
+def galerkin_matrix_periodic(k, data, d1=0, d2=0):
+    """galerkin_matrix!(M, B::PeriodicBSplineBasis, (Derivative(d1), Derivative(d2))) as a dense matrix: the same
+    loop (src/Galerkin/linear.jl:268-311) over the PeriodicKnots ts[1 .. N+k]; only the segments inside the main
+    period pass the boundary test (:277-279); array indices wrap (basis_to_array_index, BSplines/periodic.jl:245-253)."""
+    data = _np(data, np.float64)
+    N = data.size - 1
+    ts = periodic_knots(data, k)
+    xa, xb = data[0], data[-1]
+    qx, qw = np.polynomial.legendre.leggauss(k)
+    A = np.zeros((N, N))
+    for n in range(1, ts.size):
+        tn, tn1 = ts[n - 1], ts[n]
+        if tn1 == tn or tn1 <= xa or tn >= xb:
+            continue
+        alpha, beta = (tn1 - tn) / 2, (tn + tn1) / 2
+        xs = alpha * qx + beta
+        il = np.full(k, n, dtype=np.int64)
+        _, b1 = evaluate_all(KIND_PERIODIC, k, data, xs, nderiv=d1, ileft=il)
+        b2 = b1 if d2 == d1 else evaluate_all(KIND_PERIODIC, k, data, xs, nderiv=d2, ileft=il)[1]
+        for q in range(k):
+            y = alpha * qw[q]
+            for dj in range(1, k + 1):
+                j = (n + 1 - dj - 1) % N
+                for di in range(1, k + 1):
+                    i = (n + 1 - di - 1) % N
+                    A[i, j] += y * b1[q, di - 1] * b2[q, dj - 1]
+    return A
+
+
+def galerkin_projection_periodic(f, k, data, nderiv=0):
+    """galerkin_projection!(f, phi::Vector, B::PeriodicBSplineBasis) (src/Galerkin/projection.jl:60-99): ALL segments
+    of ts[1 .. N+k] (no boundary test in this loop), indices outside 1..N skipped (:90-92) — every b_i, i = 1..N, is
+    integrated over its own unwrapped support, f being evaluated at the unwrapped nodes."""
+    data = _np(data, np.float64)
+    N = data.size - 1
+    ts = periodic_knots(data, k)
+    qx, qw = np.polynomial.legendre.leggauss(k)
+    phi = np.zeros(N)
+    for n in range(1, ts.size):
+        tn, tn1 = ts[n - 1], ts[n]
+        if tn1 == tn:
+            continue
+        alpha, beta = (tn1 - tn) / 2, (tn + tn1) / 2
+        xs = alpha * qx + beta
+        il = np.full(k, n, dtype=np.int64)
+        _, bs = evaluate_all(KIND_PERIODIC, k, data, xs, nderiv=nderiv, ileft=il)
+        for q in range(k):
+            y = alpha * qw[q] * f(xs[q])
+            for di in range(1, k + 1):
+                i = n + 1 - di
+                if 1 <= i <= N:
+                    phi[i - 1] += y * bs[q, di - 1]
+    return phi
+
+
 def fit_smoothing_periodic(xs, ys, lam, L, weights=None):
     """fit(BSplineOrder(4), xs, ys, λ, Periodic(L); weights) with dense numpy algebra
     (src/SplineInterpolations/smoothing.jl:126-213).  Returns (coefficients, breakpoints)."""

@@ -1144,6 +1144,53 @@ def test_galerkin_matrix_and_projection(bk, oracle, synth, k, nbreaks):
         assert np.array_equal(bk.galerkin_projection(f, R), oracle.galerkin_projection(f, k, t, recomb=rc))
 
 
+@pytest.mark.parametrize("k,N", [(2, 12), (3, 9), (4, 40), (5, 33), (6, 200), (8, 60)])
+def test_galerkin_periodic(bk, oracle, synth, k, N):
+    """Galerkin matrix / projection of a PeriodicBSplineBasis (src/Galerkin/linear.jl:50-54,144,268-311; the
+    reference fills a SparseMatrixCSC): cyclic band store, bit-exact against the oracle's sequential loop, the
+    reference's own assertions (test/periodic.jl:184-196: sum(G) == period, column sums == (t[j+k] - t[j]) / k)
+    and approximate(f, B, MinimiseL2Error()) on a periodic basis (test/periodic.jl:75)."""
+    L = 2.0
+    data = -1.0 + L * synth.breakpoints(63, N + 1)
+    B = bk.PeriodicBSplineBasis(k, data)
+    bw = k - 1
+
+    def dense(band):
+        w = band.cpu().numpy().T                        # (2 bw + 1, N)
+        A = np.zeros((N, N))
+        for j in range(N):
+            for d in range(-bw, bw + 1):
+                A[(j + d) % N, j] = w[bw + d, j]
+        return A
+
+    for d1, d2 in ((0, 0), (1, 1), (0, 1)):
+        if max(d1, d2) > k - 1:
+            continue
+        got = dense(bk.galerkin_matrix(B, (bk.Derivative(d1), bk.Derivative(d2)), as_band=True))
+        assert np.array_equal(got, oracle.galerkin_matrix_periodic(k, data, d1, d2)), (d1, d2)
+    G = dense(bk.galerkin_matrix(B, as_band=True))
+    ts = oracle.periodic_knots(data, k)
+    assert G.sum() == pytest.approx(L, rel=1e-14)
+    assert np.allclose(G.sum(axis=0), (ts[k:k + N] - ts[:N]) / k, rtol=1e-13, atol=0)
+    assert np.max(np.abs(G - G.T)) < 1e-15 * np.max(np.abs(G))      # symmetric up to the order of the additions
+    f = lambda x: np.cos(np.pi * x) + 0.3 * np.sin(3 * np.pi * x)      # period 2
+    assert np.array_equal(bk.galerkin_projection(f, B), oracle.galerkin_projection_periodic(f, k, data))
+    if k <= 7 and N >= 4 * bw + 1:
+        A = bk.approximate(f, B, bk.MinimiseL2Error())
+        cref = np.linalg.solve(oracle.galerkin_matrix_periodic(k, data), oracle.galerkin_projection_periodic(f, k, data))
+        assert relerr(A.coefficients(), cref) < 1e-12
+        xs = np.linspace(-1.0, 1.0, 200, endpoint=False)
+        if N >= 30 and k >= 4:
+            assert np.max(np.abs(A(xs) - f(xs))) < 5e-3
+        assert relerr(A(xs), oracle.spline_eval(1, k, data, cref, xs)) < 1e-12
+
+
+def test_galerkin_periodic_too_small(bk, synth):
+    B = bk.PeriodicBSplineBasis(4, np.linspace(0.0, 1.0, 6))      # N = 5 < 2 k - 1
+    with pytest.raises(bk.UnsupportedError):
+        bk.galerkin_matrix(B, as_band=True)
+
+
 def test_approximate_minimise_l2_golden(bk):
     """approximate(exp, B, MinimiseL2Error()) docstring values (SplineApproximations.jl:104-119)."""
     g = _goldens()["class_C"]["approximate_k3"]
