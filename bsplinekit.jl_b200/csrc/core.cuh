@@ -223,19 +223,32 @@ BSK_HD int knot_zone(const KnotView<KT> &kv, KT x) {   // evaluate_all.jl:126; p
 template <typename KT, typename VT> struct Promote { typedef VT type; };
 template <> struct Promote<double, float> { typedef double type; };
 
+#ifndef BSK_KNOT_WINDOW_MAXK
+#define BSK_KNOT_WINDOW_MAXK 6      // measured: k = 4 +5 %, k = 6 +5 %, k = 7 / 8 -8 % with the window in registers
+#endif
 template <int K, int KIND, typename KT, typename VT>
 BSK_HD void eval_all_core(const KnotView<KT> &kv, const KT *t, KT x, int i, int deriv, VT *bq) {
     typedef typename Promote<KT, VT>::type PT;
     const int m = K - deriv;   // order of the values stage
     VT Ds[BSK_MAXK];
     bq[0] = (VT)1;
+    // The 2 K - 2 knots t[i-K+2 .. i+K-1] every stage below draws from, read ONCE: left in place, each (q, j) pair
+    // re-reads its two knots (K (K - 1) loads instead of 2 K - 2; the compiler does not merge them across the
+    // division sequences), and those bank-conflicted gathers were what kept the L1 / shared pipe at 88 %.
+    // (orders above BSK_KNOT_WINDOW_MAXK keep the per-use reads: 2 K - 2 more live doubles cost them occupancy)
+    constexpr bool PRE = K <= BSK_KNOT_WINDOW_MAXK;
+    KT tw[PRE && 2 * K - 2 > 0 ? 2 * K - 2 : 1];
+    if constexpr (PRE) {
+#pragma unroll
+        for (int w = 0; w < 2 * K - 2; ++w) tw[w] = knot_at<KIND>(kv, t, i - K + 2 + w);
+    }
 #pragma unroll
     for (int q = 2; q <= K; ++q) {
         if (q <= m) {
 #pragma unroll
             for (int j = 1; j <= q - 1; ++j) {
-                KT ti = knot_at<KIND>(kv, t, i - j + 1);
-                KT tj = knot_at<KIND>(kv, t, i - j + q);
+                KT ti = PRE ? tw[PRE ? K - 1 - j : 0] : knot_at<KIND>(kv, t, i - j + 1);        // t[i - j + 1]
+                KT tj = PRE ? tw[PRE ? K - 2 - j + q : 0] : knot_at<KIND>(kv, t, i - j + q);    // t[i - j + q]
                 Ds[j - 1] = (VT)xdiv(xsub(x, ti), xsub(tj, ti));
             }
             VT bp = bq[0];
@@ -258,7 +271,8 @@ BSK_HD void eval_all_core(const KnotView<KT> &kv, const KT *t, KT x, int i, int 
             VT us[BSK_MAXK];
 #pragma unroll
             for (int dj = 1; dj <= p; ++dj) {
-                KT dt = xsub(knot_at<KIND>(kv, t, i + q - dj), knot_at<KIND>(kv, t, i + 1 - dj));
+                KT dt = PRE ? xsub(tw[PRE ? K - 2 + q - dj : 0], tw[PRE ? K - 1 - dj : 0])      // t[i + q - dj] - t[i + 1 - dj]
+                            : xsub(knot_at<KIND>(kv, t, i + q - dj), knot_at<KIND>(kv, t, i + 1 - dj));
                 us[dj - 1] = (VT)xdiv((PT)bq[dj - 1], (PT)dt);
             }
             bq[0] = xmul((VT)p, us[0]);
@@ -352,12 +366,18 @@ BSK_HD T deboor_point(const KnotView<T> &kv, const T *t, const T *c, int ncoef, 
     T d[BSK_MAXK];
 #pragma unroll
     for (int j = 1; j <= K; ++j) d[j - 1] = xadd((T)0, coef_at<KIND>(c, ncoef, cstride, j + n - K));
+    constexpr bool PRE = K <= BSK_KNOT_WINDOW_MAXK;
+    T tw[PRE && 2 * K - 2 > 0 ? 2 * K - 2 : 1];       // t[n-K+2 .. n+K-1], read once (see eval_all_core)
+    if constexpr (PRE) {
+#pragma unroll
+        for (int w = 0; w < 2 * K - 2; ++w) tw[w] = knot_at<KIND>(kv, t, n - K + 2 + w);
+    }
 #pragma unroll
     for (int r = 2; r <= K; ++r) {
 #pragma unroll
         for (int j = K; j >= r; --j) {
-            T ti = knot_at<KIND>(kv, t, j - K + n);
-            T tj = knot_at<KIND>(kv, t, j - r + n + 1);
+            T ti = PRE ? tw[PRE ? j - 2 : 0] : knot_at<KIND>(kv, t, j - K + n);
+            T tj = PRE ? tw[PRE ? j - r + K - 1 : 0] : knot_at<KIND>(kv, t, j - r + n + 1);
             T alpha = xdiv(xsub(x, ti), xsub(tj, ti));
             d[j - 1] = xadd(xmul(xsub((T)1, alpha), d[j - 2]), xmul(alpha, d[j - 1]));
         }
