@@ -24,7 +24,8 @@ using BSplineKit.Recombinations: RecombinedBSplineBasis, recombination_matrix, n
 using LinearAlgebra
 using SparseArrays: SparseMatrixCSC, sparse
 
-export DeviceVector, DeviceMatrix, device_spline, evaluate
+export DeviceVector, DeviceMatrix, device_spline, evaluate,
+    device_galerkin_band, device_galerkin_matrix, device_galerkin_projection
 
 const lib = get(ENV, "BSPLINEKIT_B200_LIB", "libbsplinekit_b200")
 
@@ -410,6 +411,59 @@ function LinearAlgebra.ldiv!(F::DeviceCyclicBandedLU, Y::DeviceMatrix{Float64})
     check(ccall((:bsk_cyclic_banded_solve, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Cvoid}),
                 F.ptr, Y.data.ptr, Y.M, C_NULL))
     Y
+end
+
+# ---- Galerkin matrices and projections (Galerkin/linear.jl:60-311, projection.jl:1-99) -----------------
+"""
+    device_galerkin_band(B, (Derivative(m), Derivative(n))) -> Matrix{Float64}   # (2k-1) x N band store
+
+All quadrature nodes go through one batched `evaluate_all` on the device; entry `[(k-1) + i - j + 1, j]` is
+`A[i, j]` (plain / recombined bases: the `BandedMatrix` of linear.jl:176-199; periodic bases: read cyclically,
+`A[mod1(j + d, N), j]` — the entries of the `SparseMatrixCSC` of linear.jl:144).  Bit-identical to the
+sequential loop of `galerkin_matrix!` (linear.jl:268-311).
+"""
+function device_galerkin_band(B::AbstractBSplineBasis, deriv = (Derivative(0), Derivative(0)); device = Int32(0))
+    k = order(B); N = length(B)
+    qx, qw = BSplineKit.Galerkin.default_quadrature((B, B))
+    qxv = collect(Float64, qx); qwv = collect(Float64, qw)
+    m, n = map(d -> Int32(BSplineKit.DifferentialOps.max_order(d)), deriv)
+    band = DeviceVector{Float64}(undef, (2k - 1) * N; device)
+    GC.@preserve qxv qwv check(ccall((:bsk_galerkin_matrix, lib), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Cvoid}),
+        handle(B; device).ptr, m, n, pointer(qxv), pointer(qwv), Int32(length(qxv)), band.ptr, C_NULL))
+    reshape(Array(band), 2k - 1, N)
+end
+
+# galerkin_matrix(B::PeriodicBSplineBasis) as the reference's SparseMatrixCSC, assembled on the device
+function device_galerkin_matrix(B::PeriodicBSplineBasis, deriv = (Derivative(0), Derivative(0)); device = Int32(0))
+    w = device_galerkin_band(B, deriv; device); k = order(B); N = length(B)
+    I = Int[]; J = Int[]; V = Float64[]
+    for j in 1:N, d in -(k - 1):(k - 1)
+        push!(I, mod1(j + d, N)); push!(J, j); push!(V, w[k + d, j])
+    end
+    sparse(I, J, V, N, N)
+end
+
+# galerkin_projection(f, B, Derivative(n)): f is evaluated on the host at the nodes the library lists
+function device_galerkin_projection(f, B::AbstractBSplineBasis, deriv = Derivative(0); device = Int32(0))
+    k = order(B)
+    qx, qw = BSplineKit.Galerkin.default_quadrature((B, B))
+    qxv = collect(Float64, qx); qwv = collect(Float64, qw)
+    np = Ref{Int64}(0)
+    GC.@preserve qxv check(ccall((:bsk_galerkin_nodes, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Int64}),
+        handle(B; device).ptr, pointer(qxv), Int32(length(qxv)), C_NULL, 0, np))
+    xs = Vector{Float64}(undef, np[])
+    GC.@preserve qxv xs check(ccall((:bsk_galerkin_nodes, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Int64}),
+        handle(B; device).ptr, pointer(qxv), Int32(length(qxv)), pointer(xs), length(xs), np))
+    fx = DeviceVector(Float64.(f.(xs)); device)
+    φ = DeviceVector{Float64}(undef, length(B); device)
+    GC.@preserve qxv qwv check(ccall((:bsk_galerkin_projection, lib), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Cvoid}),
+        handle(B; device).ptr, Int32(BSplineKit.DifferentialOps.max_order(deriv)), pointer(qxv), pointer(qwv),
+        Int32(length(qxv)), fx.ptr, length(xs), φ.ptr, C_NULL))
+    Array(φ)
 end
 
 # ---- extrapolation -------------------------------------------------------------------------------------
