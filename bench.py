@@ -214,6 +214,17 @@ def scaling_mode(args, world):
     return "strong" if world > 1 else "weak"
 
 
+def shard_points(points, mode, world, rank):
+    """This rank's contiguous slice of the point stream: (points of the slice, index of its first point, points of
+    the whole job).  strong: ONE problem of `points` points split evenly (slices of even length: the kernels work
+    on 16-byte vectors); weak: `points` per rank.  No data-path collective either way."""
+    if mode == "strong":
+        npts = (points // world) // 2 * 2
+    else:
+        npts = points // 2 * 2
+    return npts, rank * npts, npts * world
+
+
 def run_ours(args):
     import ctypes
     import numpy as np
@@ -265,9 +276,7 @@ def run_ours(args):
 
     launches = [0]                      # kernels of ours launched inside the headline timed region
     mode = scaling_mode(args, world)
-    total_pts = args.points if mode == "strong" else args.points * world
-    npts = (args.points // world) // 2 * 2 if mode == "strong" else args.points     # this rank's slice
-    first = rank * npts
+    npts, first, total_pts = shard_points(args.points, mode, world, rank)          # this rank's slice
     peak, peak_src = measured_peak()
     prof = profile_numbers()
 
