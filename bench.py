@@ -698,6 +698,23 @@ def run_ours(args):
             "e2e": e2e, "cpu_baseline": cpu,
         }
         line.update(solve)
+        # the other hot-path kernels as top-level scalars (the driver's parse drops `extra`)
+        def _lift(key, src, field):
+            v = extra.get(src, {})
+            for f in field.split("."):
+                v = v.get(f) if isinstance(v, dict) else None
+            if v is not None:
+                line[key] = v
+        _lift("knot_search_gpoints_per_s", "find_knot_interval", "gpoints_per_s")
+        _lift("knot_search_roofline_frac", "find_knot_interval", "roofline_frac")
+        _lift("evaluate_all_k4_gpoints_per_s", "evaluate_all_k4", "gpoints_per_s")
+        _lift("evaluate_all_k4_roofline_frac", "evaluate_all_k4", "roofline_frac")
+        _lift("c4_periodic_eval_gpoints_per_s", "c4_periodic_eval", "gpoints_per_s")
+        _lift("c4_periodic_eval_roofline_frac", "c4_periodic_eval", "roofline_frac")
+        _lift("c4_periodic_eval_frac_of_gather_probe", "c4_periodic_eval", "frac_of_gather_probe")
+        _lift("c4_cyclic_solve_roofline_frac", "c4_cyclic_solve", "roofline_frac")
+        _lift("f32_solve_rhs_per_s", "float32_batched_solve", "auto.rhs_per_s")
+        _lift("f32_solve_roofline_frac", "float32_batched_solve", "auto.roofline_frac")
         line["parity"] = chk
         line["extra"] = extra
         print(json.dumps(line), flush=True)
