@@ -15,4 +15,4 @@ from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, p
                   approximate, approximate_, ApproxByInterpolation, VariationDiminishing, MinimiseL2Error,
                   SplineApproximation, fit, SmoothingSpline, DomainError,
                   Flat, Linear, Smooth, SplineExtrapolation, extrapolate,
-                  galerkin_matrix, galerkin_projection)
+                  galerkin_matrix, galerkin_projection, gausslegendre)

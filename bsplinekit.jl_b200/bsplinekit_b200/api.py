@@ -1419,17 +1419,44 @@ def _gauss_legendre(n):
     return np.ascontiguousarray(x), np.ascontiguousarray(w)
 
 
-def galerkin_matrix(B, derivs=None, quadrature=None, as_band=False):
-    """galerkin_matrix(B, (Derivative(m), Derivative(n))) (Galerkin/linear.jl:60-311): banded matrix of the
-    integrals of D^m b_i D^n b_j, k Gauss-Legendre nodes per knot segment (exact for B-spline products).
-    Returns a CollocationMatrix handle (band store with k - 1 sub / super-diagonals), or the band store
-    itself as a CUDA tensor when as_band=True (needed for k = 8: 15 bands exceed the solver's 13)."""
+def gausslegendre(n):
+    """Galerkin.gausslegendre(Val(n)) (Galerkin/quadratures.jl:3-18): (nodes, weights) on [-1, 1]."""
+    return _gauss_legendre(int(n))
+
+
+def galerkin_matrix(*args, quadrature=None, as_band=False):
+    """galerkin_matrix([f], B, [(Derivative(m), Derivative(n))]; [quadrature]) (Galerkin/linear.jl:60-311): banded
+    matrix of the integrals of f(x) D^m b_i D^n b_j, k Gauss-Legendre nodes per knot segment by default (exact for
+    B-spline products).  Returns a CollocationMatrix handle (band store with k - 1 sub / super-diagonals), a
+    CyclicBandedMatrix for periodic bases, or the band store itself as a CUDA tensor when as_band=True (needed for
+    k = 8: 15 bands exceed the solver's 13)."""
+    args = list(args)
+    f = args.pop(0) if callable(args[0]) and not isinstance(args[0], AbstractBSplineBasis) else None
+    B = args.pop(0)
+    derivs = args.pop(0) if args else None
+    if isinstance(B, (tuple, list)):
+        # a pair of bases must share the parent basis (linear.jl:134-156); only identical bases are built here
+        if len(B) != 2 or B[0].k != B[1].k or not np.array_equal(B[0].knots(), B[1].knots()):
+            raise ArgumentError("all bases must share the same parent B-spline basis")
+        if B[0] is not B[1]:
+            raise _lib.UnsupportedError("Galerkin matrices of two different recombinations of one basis are not built")
+        B = B[0]
     d1, d2 = (0, 0) if derivs is None else (derivs[0].n, derivs[1].n)
     qx, qw = _gauss_legendre(B.k) if quadrature is None else quadrature
+    qx = np.ascontiguousarray(qx, dtype=np.float64); qw = np.ascontiguousarray(qw, dtype=np.float64)
     nb = 2 * (B.k - 1) + 1
     band = torch.empty((len(B), nb), dtype=torch.float64, device="cuda")      # == (nb, n) column-major
-    check(lib.bsk_galerkin_matrix(B._handle, d1, d2, qx.ctypes.data_as(C.c_void_p), qw.ctypes.data_as(C.c_void_p),
-                                  qx.size, _ptr(band), _stream()))
+    fx, nfx = None, 0
+    if f is not None:
+        npts = C.c_int64(0)
+        check(lib.bsk_galerkin_nodes(B._handle, qx.ctypes.data_as(C.c_void_p), qx.size, None, 0, C.byref(npts)))
+        xs = np.empty(npts.value)
+        check(lib.bsk_galerkin_nodes(B._handle, qx.ctypes.data_as(C.c_void_p), qx.size, xs.ctypes.data_as(C.c_void_p),
+                                     xs.size, C.byref(npts)))
+        fx = torch.from_numpy(_apply(f, xs)).cuda()
+        nfx = fx.numel()
+    check(lib.bsk_galerkin_matrix_weighted(B._handle, d1, d2, qx.ctypes.data_as(C.c_void_p), qw.ctypes.data_as(C.c_void_p),
+                                           qx.size, _ptr(fx) if fx is not None else None, nfx, _ptr(band), _stream()))
     if as_band:
         return band
     if isinstance(B, PeriodicBSplineBasis):
@@ -1438,9 +1465,13 @@ def galerkin_matrix(B, derivs=None, quadrature=None, as_band=False):
     return CollocationMatrix(band)
 
 
-def galerkin_projection(f, B, deriv=None):
-    """galerkin_projection(f, B, [Derivative(n)]) (Galerkin/projection.jl:1-99): phi_i = <f, D^n b_i>."""
+def galerkin_projection(f, B, deriv=None, out=None):
+    """galerkin_projection(f, B, [Derivative(n)]) (Galerkin/projection.jl:1-99): phi_i = <f, D^n b_i>; f is any
+    callable, a Spline included (test/galerkin.jl:73-79).  out: galerkin_projection!(f, phi, B) — a vector of the
+    wrong length raises DimensionMismatch (projection.jl:52-55)."""
     nd = 0 if deriv is None else deriv.n
+    if out is not None and np.asarray(out).shape != (len(B),):
+        raise DimensionMismatch("incorrect length of output vector phi")
     qx, qw = _gauss_legendre(B.k)
     npts = C.c_int64(0)
     check(lib.bsk_galerkin_nodes(B._handle, qx.ctypes.data_as(C.c_void_p), qx.size, None, 0, C.byref(npts)))
@@ -1451,6 +1482,9 @@ def galerkin_projection(f, B, deriv=None):
     phi = torch.empty(len(B), dtype=torch.float64, device="cuda")
     check(lib.bsk_galerkin_projection(B._handle, nd, qx.ctypes.data_as(C.c_void_p), qw.ctypes.data_as(C.c_void_p),
                                       qx.size, _ptr(fx), fx.numel(), _ptr(phi), _stream()))
+    if out is not None:
+        out[...] = phi.cpu().numpy()
+        return out
     return phi.cpu().numpy()
 
 

@@ -96,8 +96,8 @@ bsk_status upload(void **d, const std::vector<V> &h) {
 // One thread per band entry.  Band store data[bw + i - j, j], bw = k - 1.
 __global__ void __launch_bounds__(128)
 k_galerkin_gather(const double *__restrict__ bs1, const double *__restrict__ bs2, const int32_t *__restrict__ seg_of_n,
-                  const double *__restrict__ y, int nq, int k, int off, int64_t nt, int64_t N,
-                  double *__restrict__ band) {
+                  const double *__restrict__ y, const double *__restrict__ fx, int nq, int k, int off, int64_t nt,
+                  int64_t N, double *__restrict__ band) {
     const int bw = k - 1, nb = 2 * bw + 1;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N * nb; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = e / nb;
@@ -116,7 +116,9 @@ k_galerkin_gather(const double *__restrict__ bs1, const double *__restrict__ bs2
                 for (int q = 0; q < nq; ++q) {
                     const int64_t p = (int64_t)s * nq + q;
                     const double bi = bs1[p * k + di - 1], bj = bs2[p * k + dj - 1];
-                    acc = xadd(acc, xmul(xmul(y[p], bi), bj));         // A[i, j] += y * bi * bj   (linear.jl:305)
+                    double term = xmul(xmul(y[p], bi), bj);            // A[i, j] += y * bi * bj * f(x)   (linear.jl:305)
+                    if (fx) term = xmul(term, fx[p]);
+                    acc = xadd(acc, term);
                 }
             }
         }
@@ -130,8 +132,8 @@ k_galerkin_gather(const double *__restrict__ bs1, const double *__restrict__ bs2
 // (mod N); the reference visits the segments in increasing n (linear.jl:268), hence the wrapped ones first.
 __global__ void __launch_bounds__(128)
 k_galerkin_gather_periodic(const double *__restrict__ bs1, const double *__restrict__ bs2,
-                           const int32_t *__restrict__ seg_of_n, const double *__restrict__ y, int nq, int k, int64_t N,
-                           double *__restrict__ band) {
+                           const int32_t *__restrict__ seg_of_n, const double *__restrict__ y,
+                           const double *__restrict__ fx, int nq, int k, int64_t N, double *__restrict__ band) {
     const int bw = k - 1, nb = 2 * bw + 1, h = k / 2;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N * nb; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = e / nb;
@@ -156,7 +158,9 @@ k_galerkin_gather_periodic(const double *__restrict__ bs1, const double *__restr
                 for (int q = 0; q < nq; ++q) {
                     const int64_t p = (int64_t)s * nq + q;
                     const double bi = bs1[p * k + di - 1], bj = bs2[p * k + dj - 1];
-                    acc = xadd(acc, xmul(xmul(y[p], bi), bj));
+                    double term = xmul(xmul(y[p], bi), bj);
+                    if (fx) term = xmul(term, fx[p]);
+                    acc = xadd(acc, term);
                 }
             }
         }
@@ -221,6 +225,14 @@ bsk_status bsk_galerkin_nodes(const bsk_basis *b, const double *h_qx, int32_t nq
 // linear.jl:144 has exactly these entries).
 bsk_status bsk_galerkin_matrix(const bsk_basis *b, int32_t deriv1, int32_t deriv2, const double *h_qx,
                                const double *h_qw, int32_t nq, double *d_band, void *stream) {
+    return bsk_galerkin_matrix_weighted(b, deriv1, deriv2, h_qx, h_qw, nq, nullptr, 0, d_band, stream);
+}
+
+// galerkin_matrix(f, B, ...) (linear.jl:60-96,305): the integrand carries the weight f(x); d_fx = f at the nodes
+// bsk_galerkin_nodes lists (NULL: f = 1).
+bsk_status bsk_galerkin_matrix_weighted(const bsk_basis *b, int32_t deriv1, int32_t deriv2, const double *h_qx,
+                                        const double *h_qw, int32_t nq, const double *d_fx, int64_t nfx,
+                                        double *d_band, void *stream) {
     BSK_REQUIRE(b && h_qx && h_qw && d_band && nq >= 1, BSK_ERR_ARGUMENT, "NULL argument");
     BSK_REQUIRE(deriv1 >= 0 && deriv2 >= 0, BSK_ERR_ARGUMENT, "derivative order must be >= 0");
     BSK_REQUIRE(b->kind != BSK_BASIS_PERIODIC || b->len >= 2 * b->k - 1, BSK_ERR_UNSUPPORTED,
@@ -232,6 +244,8 @@ bsk_status bsk_galerkin_matrix(const bsk_basis *b, int32_t deriv1, int32_t deriv
     cudaStream_t st = (cudaStream_t)stream;
     const int k = b->k;
     const int64_t npts = (int64_t)sg.x.size();
+    BSK_REQUIRE(d_fx == nullptr || nfx == npts, BSK_ERR_DIMENSION, "expected the weight at %lld quadrature nodes, got %lld",
+                (long long)npts, (long long)nfx);
     DevBufs d;
     if ((rc = upload(&d.x, sg.x)) != BSK_OK || (rc = upload(&d.y, sg.y)) != BSK_OK ||
         (rc = upload(&d.il, sg.ileft)) != BSK_OK || (rc = upload(&d.seg, sg.seg_of_n)) != BSK_OK)
@@ -252,10 +266,10 @@ bsk_status bsk_galerkin_matrix(const bsk_basis *b, int32_t deriv1, int32_t deriv
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nent + 127) / 128, 148 * 16));
     if (b->kind == BSK_BASIS_PERIODIC)
         k_galerkin_gather_periodic<<<grid, 128, 0, st>>>((const double *)d.bs1, bs2, (const int32_t *)d.seg,
-                                                         (const double *)d.y, nq, k, b->len, d_band);
+                                                         (const double *)d.y, d_fx, nq, k, b->len, d_band);
     else
-        k_galerkin_gather<<<grid, 128, 0, st>>>((const double *)d.bs1, bs2, (const int32_t *)d.seg, (const double *)d.y, nq, k, off,
-                                                b->nt, b->len, d_band);
+        k_galerkin_gather<<<grid, 128, 0, st>>>((const double *)d.bs1, bs2, (const int32_t *)d.seg, (const double *)d.y, d_fx, nq, k,
+                                                off, b->nt, b->len, d_band);
     BSK_CUDA(cudaGetLastError());
     BSK_CUDA(cudaStreamSynchronize(st));                     // temporaries are released on return
     return BSK_OK;

@@ -363,6 +363,11 @@ bsk_status bsk_galerkin_nodes(const bsk_basis *b, const double *h_qx, int32_t nq
                               int64_t capacity, int64_t *npts);
 bsk_status bsk_galerkin_matrix(const bsk_basis *b, int32_t deriv1, int32_t deriv2, const double *h_qx,
                                const double *h_qw, int32_t nq, double *d_band, void *stream);
+/* galerkin_matrix(f, B, ...) (Galerkin/linear.jl:60-96,305): A[i, j] += y * b_i * b_j * f(x); d_fx = f at the
+ * nfx nodes bsk_galerkin_nodes lists for the same quadrature (NULL: f = 1, = bsk_galerkin_matrix). */
+bsk_status bsk_galerkin_matrix_weighted(const bsk_basis *b, int32_t deriv1, int32_t deriv2, const double *h_qx,
+                                        const double *h_qw, int32_t nq, const double *d_fx, int64_t nfx,
+                                        double *d_band, void *stream);
 bsk_status bsk_galerkin_projection(const bsk_basis *b, int32_t deriv, const double *h_qx,
                                    const double *h_qw, int32_t nq, const double *d_fx, int64_t nfx,
                                    double *d_phi, void *stream);

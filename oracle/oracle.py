@@ -415,7 +415,7 @@ def spline_extrapolate(method, k, t, coefs, x):
     return np.where(x > b, vb + sb * (x - b), out)
 
 
-def galerkin_matrix(k, t, d1=0, d2=0, recomb=None):
+def galerkin_matrix(k, t, d1=0, d2=0, recomb=None, f=None, nq=None):
     """galerkin_matrix!(M, B, (Derivative(d1), Derivative(d2))) as a dense matrix, the reference's own
     loop (src/Galerkin/linear.jl:268-311): knot segments in order, k Gauss-Legendre nodes each
     (quadratures.jl:23-65), evaluate_all with ileft, A[i, j] += y * bi * bj."""
@@ -425,7 +425,7 @@ def galerkin_matrix(k, t, d1=0, d2=0, recomb=None):
     Np = t.size - k
     N = Np - (recomb.cl + recomb.cr if recomb is not None else 0)
     xa, xb = t[k - 1], t[Np]
-    qx, qw = np.polynomial.legendre.leggauss(k)
+    qx, qw = np.polynomial.legendre.leggauss(k if nq is None else nq)
     A = np.zeros((N, N))
     for n in range(1, t.size):
         tn, tn1 = t[n - 1], t[n]
@@ -433,12 +433,13 @@ def galerkin_matrix(k, t, d1=0, d2=0, recomb=None):
             continue
         alpha, beta = (tn1 - tn) / 2, (tn + tn1) / 2
         xs = alpha * qx + beta
-        il = np.full(k, n - off, dtype=np.int64)
+        il = np.full(qx.size, n - off, dtype=np.int64)
         _, b1 = evaluate_all(kind, k, t, xs, nderiv=d1, ileft=il, recomb=recomb)
         b2 = b1 if d2 == d1 else evaluate_all(kind, k, t, xs, nderiv=d2, ileft=il, recomb=recomb)[1]
         ilast = n - off
-        for q in range(k):
+        for q in range(qx.size):
             y = alpha * qw[q]
+            fq = None if f is None else float(f(xs[q]))
             for dj in range(1, k + 1):
                 j = ilast + 1 - dj
                 if not 1 <= j <= N:
@@ -447,7 +448,8 @@ def galerkin_matrix(k, t, d1=0, d2=0, recomb=None):
                     i = ilast + 1 - di
                     if not 1 <= i <= N:
                         continue
-                    A[i - 1, j - 1] += y * b1[q, di - 1] * b2[q, dj - 1]
+                    term = y * b1[q, di - 1] * b2[q, dj - 1]              # y * bi * bj * f(x), left to right (:305)
+                    A[i - 1, j - 1] += term if fq is None else term * fq
     return A
 
 

@@ -1144,6 +1144,69 @@ def test_galerkin_matrix_and_projection(bk, oracle, synth, k, nbreaks):
         assert np.array_equal(bk.galerkin_projection(f, R), oracle.galerkin_projection(f, k, t, recomb=rc))
 
 
+def test_galerkin_reference_assertions(bk, oracle):
+    """test/galerkin.jl restated: analytical mass matrix entries for k = 2 on Chebyshev points (:11-27), a pair of
+    bases with different parents is refused (:29-32), galerkin_matrix(f, B) with f = x^2 and the quadrature keyword
+    (:37-69), projection of the constant spline == column sums of the matrix (:71-86), sums of the recombined
+    matrices (:131-146) — and the weighted matrix bit for bit against the oracle's sequential loop."""
+    x = np.array([-np.cos(np.pi * n / 42) for n in range(43)])
+    B = bk.BSplineBasis(2, x.copy())
+    t = B.knots()
+
+    def dense(M, N):
+        w = M.cpu().numpy().T
+        bw = (w.shape[0] - 1) // 2
+        A = np.zeros((N, N))
+        for j in range(N):
+            for i in range(max(0, j - bw), min(N, j + bw + 1)):
+                A[i, j] = w[bw + i - j, j]
+        return A
+
+    G = dense(bk.galerkin_matrix(B, as_band=True), len(B))
+    i = 8                                                   # 1-based in the reference
+    assert G[i - 1, i - 1] == pytest.approx((t[i + 1] - t[i - 1]) / 3, rel=1e-14)
+    assert G[i - 2, i - 1] == pytest.approx((t[i] - t[i - 1]) / 6, rel=1e-14)
+    with pytest.raises(bk.ArgumentError):
+        bk.galerkin_matrix((B, bk.BSplineBasis(3, x.copy())))
+
+    xs = np.array([-np.cos(np.pi * n / 32) for n in range(33)])
+    f = lambda v: v * v
+    B4 = bk.BSplineBasis(4, xs.copy())
+    N4 = len(B4)
+    Gb = dense(bk.galerkin_matrix(B4, as_band=True), N4)
+    Gf = dense(bk.galerkin_matrix(f, B4, as_band=True), N4)
+    assert np.all((Gb == 0) | (Gb > Gf))                      # x in [-1, 1]: the weight only shrinks the integrals
+    assert np.array_equal(Gf, oracle.galerkin_matrix(4, B4.knots(), f=f))
+    Gi = dense(bk.galerkin_matrix(f, B4, quadrature=bk.gausslegendre(5), as_band=True), N4)
+    assert np.max(np.abs(Gf - Gi)) > 1e-8                     # k nodes are not exact for a degree-2k integrand
+    assert np.array_equal(Gi, oracle.galerkin_matrix(4, B4.knots(), f=f, nq=5))
+    G2 = dense(bk.galerkin_matrix(f, B4, quadrature=bk.gausslegendre(6), as_band=True), N4)
+    assert np.max(np.abs(G2 - Gi)) < 1e-16
+
+    for Bp in (B4, bk.RecombinedBSplineBasis(B4, bk.Derivative(1))):
+        S1 = bk.Spline(Bp, np.ones(len(Bp)))
+        for d in (0, 1):
+            M = dense(bk.galerkin_matrix(Bp, (bk.Derivative(0), bk.Derivative(d)), as_band=True), len(Bp))
+            phi = bk.galerkin_projection(S1, Bp, bk.Derivative(d))
+            assert np.allclose(phi, M.sum(axis=0), rtol=1e-12, atol=1e-14)
+    with pytest.raises(bk.DimensionMismatch):
+        bk.galerkin_projection(np.sin, B4, out=np.empty(N4 + 3))
+
+    kn = np.array([-np.cos(np.pi * n / 41) for n in range(42)])
+    B6 = bk.BSplineBasis(6, kn.copy())
+    L = 2.0
+    sums = {}
+    for name, Bx in (("B", B6), ("R0", bk.RecombinedBSplineBasis(B6, bk.Derivative(0))),
+                     ("R1", bk.RecombinedBSplineBasis(B6, bk.Derivative(1))),
+                     ("R2", bk.RecombinedBSplineBasis(B6, bk.Derivative(2)))):
+        A = dense(bk.galerkin_matrix(Bx, as_band=True), len(Bx))
+        assert np.all(np.linalg.eigvalsh(0.5 * (A + A.T)) > 0)         # isposdef
+        sums[name] = A.sum()
+    assert len(bk.RecombinedBSplineBasis(B6, bk.Derivative(0))) == len(B6) - 2
+    assert sums["B"] == pytest.approx(L, rel=1e-13) and sums["R1"] == pytest.approx(L, rel=1e-13)
+    assert sums["R0"] < L and abs(sums["R2"] - L) > 1e-6
+
+
 @pytest.mark.parametrize("k,N", [(2, 12), (3, 9), (4, 40), (5, 33), (6, 200), (8, 60)])
 def test_galerkin_periodic(bk, oracle, synth, k, N):
     """Galerkin matrix / projection of a PeriodicBSplineBasis (src/Galerkin/linear.jl:50-54,144,268-311; the
