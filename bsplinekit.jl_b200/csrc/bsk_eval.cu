@@ -46,6 +46,16 @@ inline int grid_for(int64_t n, int device, int ctas_per_sm) {
 }
 
 // Stage knots (+ LUT) into dynamic shared memory; returns the knot pointer to use.
+// Staging copies nt knots + ncell LUT entries into EVERY CTA's shared memory; on a short point stream that costs
+// more than it saves (evaluate_all on C3's basis at 4096 points: 57 us, nearly all of it the staging loop): stage
+// only when every CTA has a multiple of the table's size in points to amortise it over.
+inline bool worth_staging(const bsk_basis *b, size_t smem, int64_t n, int grid) {
+    if (smem > kSmemStageLimit) return false;
+    if (getenv("BSK_ALWAYS_STAGE")) return true;
+    const int64_t table = (int64_t)b->nt + b->ncell;
+    return n >= 2 * table * (int64_t)grid / 8 || n >= (1ll << 22);
+}
+
 // STAGE is a template parameter so that the knot / LUT reads of the staged kernels compile to LDS (a pointer
 // that may be shared OR global makes every one of them a generic LD).
 template <int STAGE, typename KT>
@@ -578,8 +588,9 @@ bsk_status launch_deboor(const bsk_spline *s, const T *d_x, int64_t n, T *d_out,
     KnotView<T> kv = make_view<T>(b);
     size_t smem = knots_smem_bytes<T>(b) + (size_t)s->ncoef * sizeof(T);
     int stage = smem <= kSmemStageLimit ? 1 : 0;
-    if (!stage) smem = 0;
     int ctas = stage ? std::max<int>(1, (int)std::min<size_t>(8, (220 * 1024) / std::max<size_t>(smem, 1))) : 8;
+    if (stage && !worth_staging(b, smem, n, grid_for(n, b->device, ctas))) { stage = 0; ctas = 8; }
+    if (!stage) smem = 0;
     int grid = grid_for(n, b->device, ctas);
     if (stage) {
         auto kern = k_spline_deboor<K, KIND, T, 1>;
@@ -790,7 +801,7 @@ bsk_status launch_find(const bsk_basis *b, const KT *d_x, int64_t n, int64_t *d_
     KnotView<KT> kv = make_view<KT>(b);
     const size_t smem = knots_smem_bytes<KT>(b);
     const int grid = grid_for(n, b->device, 8);
-    if (smem <= kSmemStageLimit) {
+    if (worth_staging(b, smem, n, grid)) {
         BSK_CUDA(set_smem(k_find_interval<KIND, KT, 1>, smem));
         k_find_interval<KIND, KT, 1><<<grid, kThreads, smem, st>>>(kv, d_x, n, d_idx, d_zone);
     } else {
@@ -860,7 +871,7 @@ bsk_status launch_eval_all_s(const bsk_basis *b, const KT *d_x, int64_t n, int d
 template <int K, int KIND, typename KT, typename VT>
 bsk_status launch_eval_all(const bsk_basis *b, const KT *d_x, int64_t n, int deriv, const int64_t *d_ileft,
                            int64_t *d_idx, VT *d_bs, cudaStream_t st) {
-    if (knots_smem_bytes<KT>(b) <= kSmemStageLimit)
+    if (worth_staging(b, knots_smem_bytes<KT>(b), n, grid_for(n, b->device, 8)))
         return launch_eval_all_s<K, KIND, KT, VT, 1>(b, d_x, n, deriv, d_ileft, d_idx, d_bs, st);
     return launch_eval_all_s<K, KIND, KT, VT, 0>(b, d_x, n, deriv, d_ileft, d_idx, d_bs, st);
 }

@@ -237,22 +237,37 @@ bsk_status spline_multi_t(const bsk_basis *b, const T *d_coefs, int64_t ncoef, i
     T *d_bs = nullptr;
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
-    cudaError_t ae = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_idx, d_idx_s, d_perm, d_perm_s, (int)n, 0, 40, st);
-    // every block is released at the common exit below, also when a later allocation fails
-    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&d_idx, sizeof(int64_t) * n, st);
-    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&d_idx_s, sizeof(int64_t) * n, st);
-    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&d_perm, sizeof(int32_t) * n, st);
-    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&d_perm_s, sizeof(int32_t) * n, st);
-    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&d_bs, sizeof(T) * n * b->k, st);
-    if (ae == cudaSuccess) ae = cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 16, st);
+    // Sort keys = knot-interval indices.  Plain bases: 1 .. nt, so bit_length(nt) key bits (two 8-bit passes for
+    // C3's 4102 knots instead of five).  Periodic indices of points far from the main period can be large or
+    // negative: 40 bits (negative ones sort after the positive ones, which only affects the visiting order).
+    int key_bits = 40;
+    if (b->kind != BSK_BASIS_PERIODIC) {
+        key_bits = 1;
+        while ((1ll << key_bits) <= b->nt + 1 && key_bits < 40) ++key_bits;
+    }
+    cudaError_t ae = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_idx, d_idx_s, d_perm, d_perm_s, (int)n, 0, key_bits, st);
+    // ONE stream-ordered allocation carved into the six scratch arrays (a call on few points is a handful of
+    // microsecond kernels: six allocations and six frees were a visible part of it)
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_idx = 0, o_idx_s = o_idx + up(sizeof(int64_t) * n), o_perm = o_idx_s + up(sizeof(int64_t) * n),
+                 o_perm_s = o_perm + up(sizeof(int32_t) * n), o_bs = o_perm_s + up(sizeof(int32_t) * n),
+                 o_tmp = o_bs + up(sizeof(T) * n * b->k), total = o_tmp + up(tmp_bytes ? tmp_bytes : 16);
+    unsigned char *arena = nullptr;
+    if (ae == cudaSuccess) ae = cudaMallocAsync((void **)&arena, total, st);
+    if (ae == cudaSuccess) {
+        d_idx = (int64_t *)(arena + o_idx);
+        d_idx_s = (int64_t *)(arena + o_idx_s);
+        d_perm = (int32_t *)(arena + o_perm);
+        d_perm_s = (int32_t *)(arena + o_perm_s);
+        d_bs = (T *)(arena + o_bs);
+        d_tmp = arena + o_tmp;
+    }
     bsk_status rc = BSK_OK;
     if (ae != cudaSuccess) { set_error("vector-valued evaluation: scratch allocation failed: %s", cudaGetErrorString(ae)); rc = BSK_ERR_ALLOC; }
     if (rc == BSK_OK) rc = bsk_evaluate_all(b, d_x, n, 0, b->dtype, nullptr, d_idx, d_bs, (void *)st);
     if (rc == BSK_OK) {
         k_iota<<<(unsigned)std::min<int64_t>(1024, (n + 255) / 256), 256, 0, st>>>(d_perm, n);
-        // interval indices fit in 40 bits (periodic indices can be negative: they sort after the
-        // positive ones, which only affects the visiting order)
-        cudaError_t ce = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_idx, d_idx_s, d_perm, d_perm_s, (int)n, 0, 40, st);
+        cudaError_t ce = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_idx, d_idx_s, d_perm, d_perm_s, (int)n, 0, key_bits, st);
         if (ce != cudaSuccess) { set_error("radix sort failed: %s", cudaGetErrorString(ce)); rc = BSK_ERR_CUDA; }
     }
     if (rc == BSK_OK) {
@@ -285,8 +300,7 @@ bsk_status spline_multi_t(const bsk_basis *b, const T *d_coefs, int64_t ncoef, i
         (void)V;
         if (rc == BSK_OK && cudaGetLastError() != cudaSuccess) { set_error("k_spline_multi launch failed"); rc = BSK_ERR_CUDA; }
     }
-    for (void *p : {(void *)d_idx, (void *)d_idx_s, (void *)d_perm, (void *)d_perm_s, (void *)d_bs, d_tmp})
-        if (p) cudaFreeAsync(p, st);
+    if (arena) cudaFreeAsync(arena, st);
     return rc;
 }
 

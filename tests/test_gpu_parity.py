@@ -1729,3 +1729,39 @@ def test_back_to_back_launches_see_the_previous_results(bk, oracle, synth, nbrea
     b = b.abs().mul(0.25).clamp(0.0, 0.999); torch.cuda.synchronize()
     cfin = S.evaluate(b, (0,))[0]; torch.cuda.synchronize()
     assert torch.equal(cfin, y[0])
+
+
+@pytest.mark.parametrize("stage", ["1", None])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_staged_and_unstaged_kernels_agree(bk, oracle, synth, monkeypatch, stage, dt):
+    """K1 / K2 / K3a stage knots + LUT in shared memory only when the point stream is long enough to amortise the
+    staging (short calls read them through L1 / L2): both variants of every kernel against the oracle, bit for bit,
+    on the same small inputs (BSK_ALWAYS_STAGE forces the staged variant)."""
+    if stage:
+        monkeypatch.setenv("BSK_ALWAYS_STAGE", stage)
+    else:
+        monkeypatch.delenv("BSK_ALWAYS_STAGE", raising=False)
+    npdt = np.float64 if dt == "f64" else np.float32
+    for k, periodic in ((4, False), (6, False), (5, True), (4, True)):
+        if periodic:
+            br = (2.0 * synth.breakpoints(8, 301) - 1.0).astype(npdt)
+            B = bk.PeriodicBSplineBasis(k, br)
+            kind, tref = 1, br
+            x = _points(synth, 51, 3000, -3.0, 3.0, extra=list(br)).astype(npdt)
+        else:
+            br = synth.breakpoints(3, 300).astype(npdt)
+            B = bk.BSplineBasis(k, br)
+            kind, tref = 0, B.knots()
+            x = _points(synth, 52, 3000, -0.05, 1.05, extra=list(tref)).astype(npdt)
+        i_ref, z_ref = oracle.find_knot_interval(kind, k, tref, x, kt=dt)
+        i, z = bk.find_knot_interval(B, x)
+        assert np.array_equal(i, i_ref) and np.array_equal(z, z_ref)
+        for nd in (0, 1, k - 1):
+            ir, bsr = oracle.evaluate_all(kind, k, tref, x, nderiv=nd, kt=dt, vt=dt)
+            ig, bsg = bk.evaluate_all(B, x, bk.Derivative(nd))
+            assert np.array_equal(ig, ir) and np.array_equal(bsg, bsr, equal_nan=True)
+        c = (2 * synth.u_numpy(4, 0, len(B)) - 1).astype(npdt)
+        S = bk.Spline(B, c)
+        xin = x[(x >= tref[0]) & (x <= tref[-1])] if not periodic else x
+        got = S.evaluate(xin, (0,), algo=bk.EVAL_DEBOOR)[0]
+        assert np.array_equal(got, oracle.spline_eval(kind, k, tref, c, xin, kt=dt), equal_nan=True)
