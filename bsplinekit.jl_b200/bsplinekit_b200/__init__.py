@@ -15,4 +15,5 @@ from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, p
                   approximate, approximate_, ApproxByInterpolation, VariationDiminishing, MinimiseL2Error,
                   SplineApproximation, fit, SmoothingSpline, DomainError,
                   Flat, Linear, Smooth, SplineExtrapolation, extrapolate,
-                  galerkin_matrix, galerkin_projection, gausslegendre)
+                  galerkin_matrix, galerkin_projection, gausslegendre,
+                  BasisFunction, evaluate, support, nonzero_in_segment, isindomain)

@@ -494,6 +494,75 @@ def evaluate_all(B, x, op=None, T=None, ileft=None):
     return idx.cpu().numpy(), bs.cpu().numpy()
 
 
+# ---- single basis functions (BSplines/basis_function.jl) ----------------------------------------
+
+def support(B, i=None):
+    """support(B, i) / support(b::BasisFunction) -> (first, last) knot indices, 1-based: b_i lives on
+    [t_i, t_{i+k}) (basis_function.jl:58-72)."""
+    if isinstance(B, BasisFunction):
+        B, i = B.basis, B.i
+    return int(i), int(i) + B.k
+
+
+def nonzero_in_segment(B, n):
+    """nonzero_in_segment(B::BSplineBasis, n) -> (first, last) basis functions that are non-zero on the knot
+    segment [t_n, t_{n+1}] (basis_function.jl:74-99)."""
+    return max(n - B.k + 1, 1), min(n, len(B))
+
+
+def isindomain(B, x):
+    """isindomain(B, x): a <= x <= b; always true for periodic bases (BSplines/basis.jl:232-237, periodic.jl:81)."""
+    if isinstance(B, PeriodicBSplineBasis):
+        return True
+    a, b = B.boundaries()
+    return bool(a <= x <= b)
+
+
+def evaluate(B, i, x, op=None, T=None):
+    """evaluate(B, i, x, [op], [T]) — the i-th basis function at x (scalar, array or CUDA tensor)
+    (basis_function.jl:118-197).  The reference recurses on the order (Cox-de Boor); here the value is picked out
+    of the k non-zero functions the batched evaluate_all returns for every point (same numbers up to rounding,
+    one pass over the points whatever k).  i outside eachindex(B) raises DomainError (:136-138)."""
+    N, k = len(B), B.k
+    if not 1 <= int(i) <= N:
+        raise DomainError("Basis function index must be in 1:%d" % N)
+    scalar = np.isscalar(x)
+    xin = np.atleast_1d(np.asarray(x)) if not isinstance(x, torch.Tensor) else x
+    idx, bs = evaluate_all(B, xin, op, T)
+    on_dev = isinstance(bs, torch.Tensor)
+    if not on_dev:
+        idx, bs = torch.from_numpy(idx), torch.from_numpy(bs)
+    j = idx - int(i)                                        # bs[:, j] is b_{idx - j}: reversed order (evaluate_all.jl:9-64)
+    if isinstance(B, PeriodicBSplineBasis):
+        j = torch.remainder(j, N)
+    valid = (j >= 0) & (j < k)
+    out = torch.where(valid, bs.gather(1, j.clamp(0, k - 1).reshape(-1, 1)).reshape(-1), torch.zeros((), dtype=bs.dtype, device=bs.device))
+    if on_dev:
+        return out.reshape(x.shape)
+    out = out.numpy()
+    return out[0] if scalar else out.reshape(np.shape(x))
+
+
+class BasisFunction:
+    """BasisFunction(B, i, [T]) == B[i]; callable: b(x, [op]) (basis_function.jl:1-47,114)."""
+
+    def __init__(self, B, i, T=None):
+        self.basis, self.i, self.T = B, int(i), T
+
+    def __call__(self, x, op=None):
+        return evaluate(self.basis, self.i, x, op, self.T)
+
+    def knots(self):
+        return self.basis.knots()
+
+    @property
+    def k(self):
+        return self.basis.k
+
+
+AbstractBSplineBasis.__getitem__ = lambda self, i: BasisFunction(self, i)      # B[i] (BSplines.jl:75-82)
+
+
 # ---- splines ----------------------------------------------------------------------------------
 
 class Spline:

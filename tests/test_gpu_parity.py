@@ -1765,3 +1765,53 @@ def test_staged_and_unstaged_kernels_agree(bk, oracle, synth, monkeypatch, stage
         xin = x[(x >= tref[0]) & (x <= tref[-1])] if not periodic else x
         got = S.evaluate(xin, (0,), algo=bk.EVAL_DEBOOR)[0]
         assert np.array_equal(got, oracle.spline_eval(kind, k, tref, c, xin, kt=dt), equal_nan=True)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 6])
+def test_basis_function_against_cox_de_boor(bk, oracle, synth, k):
+    """B[i](x, op) / evaluate(B, i, x, op) (BSplines/basis_function.jl:114-197) is picked out of the batched
+    evaluate_all; the oracle's orc_basis_function is the reference's own Cox-de Boor recursion (:146-256) — two
+    independent algorithms (the comparison test/bsplines.jl:76-92 makes).  Also support / nonzero_in_segment /
+    isindomain / DomainError, device input, recombined and periodic bases."""
+    import torch
+    br = synth.breakpoints(21, 12)
+    B = bk.BSplineBasis(k, br)
+    t, N = B.knots(), len(B)
+    x = np.concatenate([_points(synth, 22, 400, -0.05, 1.05), br])
+    for nd in range(0, min(k, 3)):
+        for i in sorted({1, 2, max(1, N // 2), N - 1, N} & set(range(1, N + 1))):
+            ref = np.array([oracle.basis_function(k, t, i, float(v), nd) for v in x])
+            got = bk.evaluate(B, i, x, bk.Derivative(nd))
+            scale = max(1.0, np.max(np.abs(ref)))
+            assert np.max(np.abs(got - ref)) < 1e-12 * scale, (nd, i)
+            assert np.array_equal(B[i](x, bk.Derivative(nd)), got)
+    # scalar and device input
+    assert bk.evaluate(B, 1, float(t[0])) == 1.0 and B[N](float(t[-1])) == 1.0
+    xd = torch.from_numpy(x).cuda()
+    assert np.array_equal(bk.evaluate(B, 2 if N > 1 else 1, xd).cpu().numpy(), bk.evaluate(B, 2 if N > 1 else 1, x))
+    with pytest.raises(bk.DomainError):
+        bk.evaluate(B, 0, 0.5)
+    with pytest.raises(bk.DomainError):
+        bk.evaluate(B, N + 1, 0.5)
+    assert bk.support(B, 3) == (3, 3 + k) and bk.support(B[3]) == (3, 3 + k)
+    assert bk.nonzero_in_segment(B, k) == (1, k) and bk.nonzero_in_segment(B, N + 5)[1] == N
+    assert bk.isindomain(B, 0.0) and bk.isindomain(B, 1.0) and not bk.isindomain(B, 1.0000001)
+    # partition of unity from single functions
+    tot = sum(bk.evaluate(B, i, x) for i in range(1, N + 1))
+    inside = (x >= 0) & (x <= 1)
+    assert np.allclose(tot[inside], 1.0, rtol=0, atol=1e-14) and np.all(tot[~inside] == 0)
+    if k >= 3:
+        # recombined basis: phi_j = sum_i A[i, j] b_i
+        R = bk.RecombinedBSplineBasis(B, bk.Derivative(1))
+        A = R.recombination_matrix()
+        xin = x[inside]
+        allb = np.array([[oracle.basis_function(k, t, i, float(v), 0) for v in xin] for i in range(1, N + 1)])
+        for j in (1, 2, len(R)):
+            assert np.max(np.abs(bk.evaluate(R, j, xin) - A[:, j - 1] @ allb)) < 1e-13
+        # periodic basis: b_j of the wrapped basis, evaluated at points far from the main period too
+        P = bk.PeriodicBSplineBasis(k, br)
+        Np = len(P)
+        xp = np.concatenate([x, x + 3.0, x - 2.0])
+        totp = sum(bk.evaluate(P, j, xp) for j in range(1, Np + 1))
+        assert np.allclose(totp, 1.0, rtol=0, atol=1e-13)
+        assert bk.isindomain(P, 17.0)
