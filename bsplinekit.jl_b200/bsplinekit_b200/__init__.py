@@ -16,4 +16,7 @@ from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, p
                   SplineApproximation, fit, SmoothingSpline, DomainError,
                   Flat, Linear, Smooth, SplineExtrapolation, extrapolate,
                   galerkin_matrix, galerkin_projection, gausslegendre,
-                  BasisFunction, evaluate, support, nonzero_in_segment, isindomain)
+                  BasisFunction, evaluate, support, nonzero_in_segment, isindomain,
+                  AbstractBSplineBasis, basis, coefficients, spline, has_parent_basis, constraints,
+                  recombination_matrix, knots_in_main_period, basis_to_array_index, LeftNormal, RightNormal, dot,
+                  max_order, DerivativeUnitRange)

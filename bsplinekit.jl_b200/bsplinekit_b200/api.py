@@ -98,11 +98,74 @@ class DifferentialOp:
     def max_order(self):
         return max(self.terms) if self.terms else -1
 
+    def __eq__(self, o):                                   # S == S' whatever the order of the terms (DifferentialOps.jl:150-158)
+        return isinstance(o, DifferentialOp) and {m: float(a) for m, a in self.terms.items()} == \
+            {m: float(a) for m, a in o.terms.items()}
+
+    def __hash__(self):
+        return hash(tuple(sorted(self.terms.items())))
+
+    def __repr__(self):
+        return " + ".join(("D{%d}" % m) if a == 1 else ("%s * D{%d}" % (a, m)) for m, a in self.terms.items())
+
+
+class LeftNormal:
+    """LeftNormal() . op: odd-order derivatives change sign on the left boundary (DifferentialOps.jl:36-42,128-131)."""
+
+    def dot(self, op):
+        return DifferentialOp({m: (-a if m % 2 else a) for m, a in op.terms.items()})
+
+
+class RightNormal:
+    """RightNormal() . op == op (DifferentialOps.jl:44-51,78)."""
+
+    def dot(self, op):
+        return DifferentialOp(dict(op.terms))
+
+
+def dot(direction, op):
+    """LinearAlgebra.dot(dir, op) / dir ⋅ op (DifferentialOps.jl:64-78)."""
+    if isinstance(op, (LeftNormal, RightNormal)):
+        direction, op = op, direction
+    return direction.dot(op)
+
+
+def max_order(*ops):
+    """max_order(ops...) (DifferentialOps.jl:56-81): -1 for no operator."""
+    return max((o.max_order for o in ops), default=-1)
+
+
+class DerivativeUnitRange:
+    """Derivative(m:n) (DifferentialOps.jl:162-190): the operators D^m .. D^n as a tuple-like range."""
+
+    def __init__(self, m, n):
+        self.m, self.n = int(m), int(n)
+
+    def __iter__(self):
+        return iter(Derivative(d) for d in range(self.m, self.n + 1))
+
+    def __len__(self):
+        return max(0, self.n - self.m + 1)
+
+    def __eq__(self, o):
+        return isinstance(o, DerivativeUnitRange) and (o.m, o.n) == (self.m, self.n)
+
+    def __repr__(self):
+        return "Derivative(%d:%d)" % (self.m, self.n)
+
 
 class Derivative(DifferentialOp):
+    def __new__(cls, n=1, *rest):
+        if isinstance(n, range):                           # Derivative(2:5) (DifferentialOps.jl:170-176)
+            return DerivativeUnitRange(n.start, n.stop - 1)
+        return super().__new__(cls)
+
     def __init__(self, n=1):
         super().__init__({int(n): 1.0})
         self.n = int(n)
+
+    def __pow__(self, p):                                  # D2^3 === Derivative(6) (DifferentialOps.jl:95-96)
+        return Derivative(self.n * int(p))
 
     def __mul__(self, S):
         if isinstance(S, Spline):
@@ -112,7 +175,9 @@ class Derivative(DifferentialOp):
         return NotImplemented
 
     def __eq__(self, o):
-        return isinstance(o, Derivative) and o.n == self.n
+        if isinstance(o, Derivative):
+            return o.n == self.n
+        return DifferentialOp.__eq__(self, o)              # 1 * D == D (DifferentialOps.jl:124-126)
 
     def __hash__(self):
         return hash(("D", self.n))
@@ -439,6 +504,49 @@ class RecombinedBSplineBasis(AbstractBSplineBasis):
 
 def knots(B):
     return B.knots()
+
+
+def basis(obj):
+    """basis(S) / basis(itp) / basis(b::BasisFunction) (Splines/spline.jl:99, SplineInterpolations.jl:75)."""
+    return obj.basis
+
+
+def coefficients(S):
+    """coefficients(S) (Splines/spline.jl:93-97)."""
+    return S.coefficients()
+
+
+def spline(obj):
+    """spline(itp) / spline(extrapolation) / spline(approximation) (SplineInterpolations.jl:77)."""
+    return obj.spline
+
+
+def has_parent_basis(B):
+    """has_parent_basis(B): true for bases derived from a B-spline basis (BSplines/basis.jl:258-266)."""
+    return isinstance(B, RecombinedBSplineBasis)
+
+
+def constraints(R):
+    """constraints(R) -> (left, right) differential operators (Recombinations/bases.jl:302-312); () for plain bases."""
+    return R.ops if isinstance(R, RecombinedBSplineBasis) else ((), ())
+
+
+def recombination_matrix(R):
+    """recombination_matrix(R) as a dense array (Recombinations/bases.jl:281-286)."""
+    return R.recombination_matrix()
+
+
+def knots_in_main_period(B):
+    """knots_in_main_period(ts::PeriodicKnots): the N knots of one period (BSplines/periodic.jl:68-75)."""
+    return B.knots()[:-1]
+
+
+def basis_to_array_index(B, i):
+    """basis_to_array_index(B, axes, i), 1-based: identity for plain / recombined bases, mod1(i, N) for periodic
+    ones (BSplines/basis.jl:268-283, periodic.jl:245-253)."""
+    if isinstance(B, PeriodicBSplineBasis):
+        return (int(i) - 1) % len(B) + 1
+    return int(i)
 
 
 def order(B):
@@ -817,45 +925,6 @@ def greville_points(k, t, N, cl=0, force_ends=True):
                 xi = b
         x[i] = min(max(xi, a), b)
     return x
-
-
-class ComplexSpline:
-    """Spline with complex coefficients (eltype ComplexF32 / ComplexF64 in the reference: the de Boor recurrence
-    is linear in the coefficients, Splines/spline.jl:180-184): real and imaginary part are two splines sharing
-    one basis, evaluated together by the vector-valued kernel (M = 2)."""
-
-    def __init__(self, B, coefs):
-        self.basis = B
-        self.coefs = coefs                                   # (N,) complex CUDA tensor
-        self._batch = SplineBatch(B, torch.view_as_real(coefs).contiguous())
-
-    def coefficients(self):
-        return self.coefs.cpu().numpy()
-
-    def __call__(self, x):
-        on_dev = isinstance(x, torch.Tensor) and x.is_cuda
-        xd = x if on_dev else torch.from_numpy(np.ascontiguousarray(np.atleast_1d(x), dtype=_NP[self.basis._dt])).cuda()
-        out = torch.view_as_complex(self._batch(xd.reshape(-1)).contiguous()).reshape(xd.shape)
-        if on_dev:
-            return out
-        out = out.cpu().numpy()
-        return out[0] if np.isscalar(x) else out
-
-
-def _periodic_knot(data, k, i):
-    """getindex(::PeriodicKnots, i), 1-based (BSplines/periodic.jl:102-115)."""
-    T = data.dtype.type
-    N = data.size - 1
-    L = data[-1] - data[0]
-    x = T(0)
-    i -= k // 2
-    while i < 1:
-        x = x - L
-        i += N
-    while i > N + 1:
-        x = x + L
-        i -= N
-    return x + data[i - 1]
 
 
 def _greville_raw(k, t, N):

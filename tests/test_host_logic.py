@@ -100,3 +100,41 @@ def test_synth_numpy_torch_identical():
     # slices generated separately concatenate to the full stream (multi-GPU sharding)
     full = synth.u_numpy(9, 0, 1000)
     assert np.array_equal(np.concatenate([synth.u_numpy(9, 0, 400), synth.u_numpy(9, 400, 600)]), full)
+
+
+def test_differential_ops_reference_assertions(bk):
+    """test/diffops.jl:8-50 restated: orders, powers, sums independent of the order of the terms, projections on the
+    boundary normals (odd orders flip on the left), derivative ranges."""
+    D2, D3 = bk.Derivative(2), bk.Derivative(3)
+    assert bk.max_order(D2) == 2 and bk.max_order(D3) == 3
+    assert D2 ** 2 == bk.Derivative(4) and D2 ** 3 == bk.Derivative(6)
+    assert bk.Derivative() == bk.Derivative(1) and bk.Derivative() ** 3 == bk.Derivative(3)
+    S, S2 = D2 + 5 * D3, 5 * D3 + D2
+    assert S == S2 and bk.max_order(S) == bk.max_order(S2) == 3
+    assert bk.max_order() == -1
+    assert bk.dot(bk.LeftNormal(), D2) == D2 == 1 * D2
+    assert bk.dot(bk.RightNormal(), D2) == D2
+    assert bk.dot(bk.LeftNormal(), D3) == -D3 == -1 * D3
+    assert bk.dot(bk.RightNormal(), D3) == D3 == 1 * D3
+    assert bk.dot(bk.LeftNormal(), S) == D2 - 5 * D3
+    assert bk.dot(bk.RightNormal(), S) == D2 + 5 * D3
+    assert bk.dot(D3, bk.LeftNormal()) == -D3                      # dot(op, dir) == dot(dir, op)
+    r = bk.Derivative(range(2, 6))                                 # Derivative(2:5)
+    assert isinstance(r, bk.DerivativeUnitRange) and repr(r) == "Derivative(2:5)"
+    assert r == bk.DerivativeUnitRange(2, 5) and [d.n for d in r] == [2, 3, 4, 5]
+    with pytest.raises(bk.ArgumentError):
+        0 * D2                                                     # "scale factor cannot be zero"
+    assert repr(D2) == "D{2}"
+
+
+def test_accessor_vocabulary(bk):
+    """The small accessors the reference exports next to the hot path: basis_to_array_index (periodic wrap),
+    has_parent_basis, constraints, knots_in_main_period — on objects that need no device."""
+    class P(bk.PeriodicBSplineBasis):
+        def __init__(self, k, t):                                  # no device handle
+            self.k, self.t, self._len = k, np.asarray(t, float), len(t) - 1
+    p = P(4, np.linspace(0.0, 1.0, 11))
+    assert [bk.basis_to_array_index(p, i) for i in (-1, 0, 1, 10, 11, 12)] == [9, 10, 1, 10, 1, 2]
+    assert np.array_equal(bk.knots_in_main_period(p), np.linspace(0.0, 1.0, 11)[:-1])
+    assert not bk.has_parent_basis(p) and bk.constraints(p) == ((), ())
+    assert bk.isindomain(p, 123.0)
