@@ -19,4 +19,4 @@ from .api import (BSplineOrder, Derivative, DifferentialOp, Periodic, Natural, p
                   BasisFunction, evaluate, support, nonzero_in_segment, isindomain,
                   AbstractBSplineBasis, basis, coefficients, spline, has_parent_basis, constraints,
                   recombination_matrix, knots_in_main_period, basis_to_array_index, LeftNormal, RightNormal, dot,
-                  max_order, DerivativeUnitRange)
+                  max_order, DerivativeUnitRange, diff)

@@ -168,7 +168,7 @@ class Derivative(DifferentialOp):
         return Derivative(self.n * int(p))
 
     def __mul__(self, S):
-        if isinstance(S, Spline):
+        if isinstance(S, (Spline, SplineInterpolation)):
             return S.derivative(self.n)                                 # spline.jl:272-282
         if isinstance(S, (int, float)):
             return S * DifferentialOp(self.terms)
@@ -658,6 +658,8 @@ class BasisFunction:
         self.basis, self.i, self.T = B, int(i), T
 
     def __call__(self, x, op=None):
+        if isinstance(op, DerivativeUnitRange):             # b(x, Derivative(0:2)) -> tuple (basis_function.jl:165-175)
+            return tuple(evaluate(self.basis, self.i, x, d, self.T) for d in op)
         return evaluate(self.basis, self.i, x, op, self.T)
 
     def knots(self):
@@ -668,7 +670,16 @@ class BasisFunction:
         return self.basis.k
 
 
-AbstractBSplineBasis.__getitem__ = lambda self, i: BasisFunction(self, i)      # B[i] (BSplines.jl:75-82)
+def _basis_getitem(self, i):
+    """B[i] (BSplines/BSplines.jl:75-82): BoundsError (IndexError) outside 1:length(B)."""
+    if not 1 <= int(i) <= len(self):
+        raise IndexError("attempt to access %d-element basis at index [%d]" % (len(self), int(i)))
+    return BasisFunction(self, i)
+
+
+AbstractBSplineBasis.__getitem__ = _basis_getitem
+AbstractBSplineBasis.__repr__ = lambda self: "%d-element %s of order %d, domain [%s, %s]" % (
+    (len(self), type(self).__name__, self.k) + tuple(self.boundaries()))
 
 
 # ---- splines ----------------------------------------------------------------------------------
@@ -725,6 +736,15 @@ class Spline:
         """Re-point at device-resident coefficients (e.g. a column of a batched solve)."""
         n = len(self.basis)
         check(lib.bsk_spline_set_coefs_device(self._handle, _ptr(d_coefs), n, stride, _stream()))
+
+    def __len__(self):                                                  # length(S) == length(coefficients(S))
+        return int(self.coefficients().size)
+
+    def __eq__(self, o):                                                # spline.jl:105-107: same basis, same coefficients
+        return isinstance(o, Spline) and self.k == o.k and np.array_equal(self.knots(), o.knots()) and \
+            np.array_equal(self.coefficients(), o.coefficients())
+
+    __hash__ = object.__hash__
 
     def derivative(self, n=1):
         """Derivative(n) * S (Splines/spline.jl:272-330)."""
@@ -820,11 +840,19 @@ def _periodic_knot(data, k, i):
     return T(x + data[i - 1])
 
 
+def diff(S, op=None):
+    """diff(S, Derivative(n)) == Derivative(n) * S (Splines/spline.jl:272-282); S may be a SplineInterpolation."""
+    n = 1 if op is None else op.n
+    return S.derivative(n)
+
+
 def integral(S):
     """integral(S) (Splines/spline.jl:354-374; periodic: Splines/periodic.jl:122-140): an antiderivative of S as a
     spline of order k + 1 on basis_integral(B) (BSplines/basis.jl:113-122, periodic.jl:264-276), zero at the left
     boundary.  O(N) host code like Derivative(n) * S, same operation order as the reference; the result is a
     device spline like any other.  Periodic splines give a non-periodic spline over one period plus k knots."""
+    if isinstance(S, SplineInterpolation):
+        S = S.spline
     k = S.k
     if k + 1 > 8:
         raise _lib.UnsupportedError("integral of an order-8 spline has order 9 (orders 1..8 are supported)")
@@ -1484,6 +1512,26 @@ class SplineInterpolation:
 
     def __call__(self, x, **kw):
         return self.spline(x, **kw)
+
+    # SplineWrapper forwarders (Splines/Splines.jl: order / knots / coefficients / integral / diff of a wrapped spline)
+    @property
+    def k(self):
+        return self.basis.k
+
+    def knots(self):
+        return self.basis.knots()
+
+    def coefficients(self):
+        return self.spline.coefficients()
+
+    def derivative(self, n=1):
+        return self.spline.derivative(n)
+
+    def __len__(self):
+        return len(self.basis)
+
+    def __repr__(self):
+        return "SplineInterpolation containing the %d-element Spline of order %d" % (len(self.basis), self.basis.k)
 
 
 def interpolate(x, y, order, bc=None):

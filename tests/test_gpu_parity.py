@@ -1815,3 +1815,76 @@ def test_basis_function_against_cox_de_boor(bk, oracle, synth, k):
         totp = sum(bk.evaluate(P, j, xp) for j in range(1, Np + 1))
         assert np.allclose(totp, 1.0, rtol=0, atol=1e-13)
         assert bk.isindomain(P, 17.0)
+
+
+@pytest.mark.parametrize("k", [3, 4, 5, 6])
+def test_polynomial_reproduction_and_wrappers(bk, oracle, k):
+    """test/splines.jl:13-81 (test_polynomial) restated: a polynomial of degree k - 1 is interpolated exactly,
+    its derivative and antiderivative splines follow it on a fine grid; the wrapper forwards (order / basis /
+    knots / coefficients / integral / diff of an interpolation) and the two DimensionMismatch cases."""
+    x = np.arange(12, dtype=np.float64) ** 1.3 / 6.0
+    P = [float((-d) ** d) for d in range(1, k + 1)]          # P(x) = -1 + 4x - 27x^2 + ... (ntuple(d -> (-d)^d))
+    dP = [d * P[d] for d in range(1, k)]
+    Pint = [0.0] + [P[d] / (d + 1) for d in range(k)]
+    ev = lambda c, v: np.polyval(c[::-1], v)
+    y = ev(P, x)
+    itp = bk.interpolate(x, y, bk.BSplineOrder(k))
+    assert repr(itp).startswith("SplineInterpolation containing")
+    S = bk.spline(itp)
+    assert len(S) == len(x)
+    assert np.allclose(itp(x), y, rtol=1e-12, atol=1e-12 * np.max(np.abs(y)))
+    xm = (x[1] + x[2]) / 3
+    assert itp(np.array([xm]))[0] == S(np.array([xm]))[0]
+    assert bk.order(itp) == bk.order(S) and bk.basis(itp) is bk.basis(S)
+    assert np.array_equal(bk.knots(itp), bk.knots(S)) and np.array_equal(bk.coefficients(itp), bk.coefficients(S))
+    assert bk.integral(itp) == bk.integral(S)
+    assert bk.diff(itp, bk.Derivative(1)) == bk.diff(S, bk.Derivative(1)) == bk.Derivative() * itp
+    with pytest.raises(bk.DimensionMismatch):
+        bk.SplineInterpolation(bk.basis(S), x[:4])            # "incompatible lengths of B-spline basis and collocation points"
+    with pytest.raises(bk.DimensionMismatch):
+        itp.interpolate_(np.random.rand(len(x) - 1))           # "input data has incorrect length"
+    dS = bk.diff(S, bk.Derivative(1))
+    assert bk.Derivative() * S == dS
+    Sint = bk.integral(S)
+    a, b = bk.boundaries(bk.basis(S))
+    assert Sint(np.array([a]), algo=bk.EVAL_DEBOOR)[0] == 0.0
+    xs = np.linspace(a, b, 9 * len(S) + 42)
+    sc = np.max(np.abs(ev(P, xs)))
+    assert np.max(np.abs(S(xs) - ev(P, xs))) < 1e-11 * sc
+    assert np.max(np.abs(dS(xs) - ev(dP, xs))) < 1e-10 * np.max(np.abs(ev(dP, xs)))
+    assert np.max(np.abs(Sint(xs) - (ev(Pint, xs) - ev(Pint, a)))) < 1e-11 * max(1.0, np.max(np.abs(ev(Pint, xs))))
+
+
+@pytest.mark.parametrize("k", [2, 4, 5])
+def test_bsplines_reference_assertions(bk, k):
+    """test/splines.jl:84-140 (test_splines) restated: knot multiplicities of the augmented knots, DomainError /
+    BoundsError, derivative ranges of a basis function, nonzero_in_segment near the boundaries, values at the
+    boundaries, repr."""
+    knots_in = np.array([0.0, 0.1, 0.25, 0.3, 0.55, 0.6, 0.8, 1.0])
+    B = bk.BSplineBasis(k, knots_in)
+    t, N = bk.knots(B), len(B)
+    assert np.all(t[:k] == knots_in[0]) and np.all(t[-k:] == knots_in[-1])
+    assert np.array_equal(t[k:-k], knots_in[1:-1])
+    with pytest.raises(bk.DomainError):
+        bk.evaluate(B, 0, 0.2)
+    with pytest.raises(bk.DomainError):
+        bk.evaluate(B, N + 1, 0.2)
+    b3 = B[3]
+    assert isinstance(b3, bk.BasisFunction)
+    rng = bk.Derivative(range(0, min(k, 3)))
+    assert b3(0.2, rng) == tuple(b3(0.2, bk.Derivative(d)) for d in range(0, min(k, 3)))
+    assert tuple(bk.Derivative(range(2, 6))) == tuple(bk.Derivative(d) for d in (2, 3, 4, 5))
+    for bad in (0, N + 1):
+        with pytest.raises(IndexError):
+            B[bad]
+    rng_of = lambda r: list(range(r[0], r[1] + 1))
+    assert rng_of(bk.nonzero_in_segment(B, k + 1)) == list(range(2, k + 2))
+    assert rng_of(bk.nonzero_in_segment(B, 1)) == [1]
+    assert rng_of(bk.nonzero_in_segment(B, N)) == list(range(N - k + 1, N + 1))
+    assert rng_of(bk.nonzero_in_segment(B, N + 1)) == list(range(N - k + 2, N + 1))
+    assert rng_of(bk.nonzero_in_segment(B, N + k - 1)) == [N]
+    assert rng_of(bk.nonzero_in_segment(B, N + k)) == [] and rng_of(bk.nonzero_in_segment(B, 0)) == []
+    assert rng_of(bk.nonzero_in_segment(B, t.size)) == []
+    a, b = bk.boundaries(B)
+    assert bk.evaluate(B, 1, a) == 1.0 and bk.evaluate(B, N, b) == 1.0
+    assert repr(B).startswith("%d-element BSplineBasis of order %d" % (N, k))
