@@ -1591,6 +1591,10 @@ class SplineExtrapolation:
     def __call__(self, x, algo=EVAL_AUTO):
         return self.evaluate(x, (0,), algo)[0]
 
+    def __repr__(self):
+        return "SplineExtrapolation containing the %d-element Spline of order %d, method %s" % (
+            len(self.spline), self.spline.k, type(self.method).__name__)
+
 
 def extrapolate(sp, method):
     """extrapolate(S, method) (SplineExtrapolations.jl:103-111)."""

@@ -1888,3 +1888,118 @@ def test_bsplines_reference_assertions(bk, k):
     a, b = bk.boundaries(B)
     assert bk.evaluate(B, 1, a) == 1.0 and bk.evaluate(B, N, b) == 1.0
     assert repr(B).startswith("%d-element BSplineBasis of order %d" % (N, k))
+
+
+def test_extrapolation_reference_assertions(bk, synth):
+    """test/extrapolation.jl:5-47 restated.  The reference's `==` identities (itp(a) == ext(a - 1.3), ...) hold bit
+    for bit on the de Boor path (the reference's own arithmetic); on the default table path inside and outside
+    values come from different, individually certified routes and agree to rounding (asserted at 4 ulp)."""
+    xdata = np.round(np.arange(-1.0, 1.0001, 0.2), 10)
+    ydata = 2 * synth.u_numpy(33, 0, xdata.size) - 1
+    itp = bk.interpolate(xdata, ydata, bk.BSplineOrder(4))
+    itp_nat = bk.interpolate(xdata, ydata, bk.BSplineOrder(4), bk.Natural())
+    assert repr(bk.extrapolate(itp, bk.Flat())).startswith("SplineExtrapolation containing the")
+    for algo, same in ((bk.EVAL_DEBOOR, lambda a, b: a == b),
+                       (bk.EVAL_AUTO, lambda a, b: abs(a - b) <= 4 * np.finfo(float).eps * max(abs(a), abs(b), 1.0))):
+        one = lambda f, v: float(f(np.array([v]), algo=algo)[0])
+        ext = bk.extrapolate(itp, bk.Flat())
+        assert same(one(itp, 0.42), one(ext, 0.42))
+        assert same(one(itp, -1.0), one(ext, -2.3)) and same(one(itp, 1.0), one(ext, 2.4))
+        exs = bk.extrapolate(itp_nat, bk.Smooth())
+        for v in (0.42, -1.0, 1.0):
+            assert same(one(itp_nat, v), one(exs, v))
+        # natural BCs: zero second derivative at the boundary, the smooth continuation is locally linear
+        assert one(exs, -1.01) - one(exs, -1.0) == pytest.approx(one(exs, -1.0) - one(exs, -0.99), rel=1e-3)
+        assert one(exs, 1.01) - one(exs, 1.0) == pytest.approx(one(exs, 1.0) - one(exs, 0.99), rel=1e-3)
+        if algo == bk.EVAL_DEBOOR:
+            continue                                   # Linear needs the local-polynomial path (documented)
+        exl = bk.extrapolate(itp, bk.Linear())
+        for v in (0.42, -1.0, 1.0):
+            assert same(one(itp, v), one(exl, v))
+        dS = bk.Derivative() * itp
+        assert one(exl, -1.1) == pytest.approx(one(itp, -1.0) - 0.1 * one(dS, -1.0), rel=1e-13)
+        assert one(exl, 1.1) == pytest.approx(one(itp, 1.0) + 0.1 * one(dS, 1.0), rel=1e-13)
+
+
+def test_smoothing_fit_minimises_its_objective(bk, synth):
+    """test/smoothing.jl:9-200 restated without automatic differentiation: the objective
+    sum_i w_i (y_i - S(x_i))^2 + lambda * int S''^2 is quadratic in the coefficients, its gradient
+    2 A' W (A c - y) + 2 lambda Q c (A: collocation rows, Q: Galerkin matrix of (D^2, D^2), both assembled by the
+    device kernels, independently of `fit`) vanishes at the fitted coefficients — projected on the natural
+    recombination for `Natural()`, directly for `Periodic(L)`; curvature decreases and the distance from the data
+    grows with lambda; a heavier weight pulls the curve to its point."""
+    D2 = bk.Derivative(2)
+
+    def dense_band(band, N):
+        w = band.cpu().numpy().T
+        bw = (w.shape[0] - 1) // 2
+        A = np.zeros((N, N))
+        for j in range(N):
+            for i in range(max(0, j - bw), min(N, j + bw + 1)):
+                A[i, j] = w[bw + i - j, j]
+        return A
+
+    def dense_cyclic(band, N):
+        w = band.cpu().numpy().T
+        bw = (w.shape[0] - 1) // 2
+        A = np.zeros((N, N))
+        for j in range(N):
+            for d in range(-bw, bw + 1):
+                A[(j + d) % N, j] = w[bw + d, j]
+        return A
+
+    def check(S, xs, ys, lam, weights=None):
+        R = S.basis
+        w = np.ones_like(xs) if weights is None else weights
+        if isinstance(R, bk.PeriodicBSplineBasis):
+            Bp, T = R, None
+            Q = dense_cyclic(bk.galerkin_matrix(R, (D2, D2), as_band=True), len(R))
+        else:
+            Bp, T = R.parent, R.recombination_matrix()
+            Q = dense_band(bk.galerkin_matrix(Bp, (D2, D2), as_band=True), len(Bp))
+        A = bk.collocation_rows(Bp, xs, dense=True).cpu().numpy()
+        c = S.coefficients()
+        g = 2 * A.T @ (w * (A @ c - ys)) + 2 * lam * (Q @ c)
+        # scale of every component: |M| |c| + |b| for M = 2 (A' W A + lambda Q), b = 2 A' W y.  The knots of this
+        # data are clustered ((0:0.01:1).^2), Q spans 12 orders of magnitude: a plain norm would compare the
+        # boundary rows with the interior ones; the gradient must vanish to rounding of ITS OWN row (backward error)
+        M = 2 * (A.T @ (w[:, None] * A) + lam * Q)
+        scale = np.abs(M) @ np.abs(c) + np.abs(2 * A.T @ (w * ys))
+        if T is not None:
+            g, scale = T.T @ g, np.abs(T.T) @ scale
+        assert np.max(np.abs(g) / scale) < 1e-11
+        # the reference's own measure (test/smoothing.jl:74-77): roundoff-limited by cond(M) ~ 1e10 at lambda = 1e-2,
+        # where dense numpy LU / Cholesky of the same system reach 1e-11 and this solve 2e-10
+        assert np.sum(g * g) / np.sum(ys * ys) < 1e-8
+        return float(c @ Q @ c), float(np.sqrt(np.mean((A @ c - ys) ** 2)))
+
+    xs = np.arange(0.0, 1.0001, 0.01) ** 2
+    ys = np.cos(2 * np.pi * xs) + 0.1 * np.sin(200 * np.pi * xs)
+    order = bk.BSplineOrder(4)
+    S0 = bk.fit(order, xs, ys, 0.0)
+    Si = bk.spline(bk.interpolate(xs, ys, order, bk.Natural()))
+    assert np.allclose(S0.coefficients(), Si.coefficients(), rtol=1e-9, atol=1e-9)
+    curv, dist = [], []
+    for lam in (0.0, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2):
+        c_, d_ = check(bk.fit(order, xs, ys, lam), xs, ys, lam)
+        curv.append(c_); dist.append(d_)
+    assert curv == sorted(curv, reverse=True) and dist == sorted(dist)
+    lam = 1e-3
+    wts = np.ones_like(xs)
+    S, Sw = bk.fit(order, xs, ys, lam), bk.fit(order, xs, ys, lam, weights=wts)
+    check(Sw, xs, ys, lam, wts)
+    assert np.array_equal(S.coefficients(), Sw.coefficients())
+    wts[2] = 1000.0
+    Sw = bk.fit(order, xs, ys, lam, weights=wts)
+    cw, dw = check(Sw, xs, ys, lam, wts)
+    c1, d1 = check(S, xs, ys, lam)
+    one = lambda f, v: float(f(np.array([v]))[0])
+    assert abs(one(Sw, xs[2]) - ys[2]) < abs(one(S, xs[2]) - ys[2])
+    assert cw > c1 and dw < d1
+    # periodic
+    N = 100
+    xp = np.array([-np.cos(np.pi * n / N) for n in range(N)])
+    yp = np.cos(np.pi * xp) + 0.1 * np.sin(200 * np.pi * xp)
+    check(bk.fit(order, xp, yp, 1e-4, bk.Periodic(2.0)), xp, yp, 1e-4)
+    wp = np.ones_like(xp); wp[2] = 1000.0
+    check(bk.fit(order, xp, yp, 1e-4, bk.Periodic(2.0), weights=wp), xp, yp, 1e-4, wp)
