@@ -2003,3 +2003,30 @@ def test_smoothing_fit_minimises_its_objective(bk, synth):
     check(bk.fit(order, xp, yp, 1e-4, bk.Periodic(2.0)), xp, yp, 1e-4)
     wp = np.ones_like(xp); wp[2] = 1000.0
     check(bk.fit(order, xp, yp, 1e-4, bk.Periodic(2.0), weights=wp), xp, yp, 1e-4, wp)
+
+
+@pytest.mark.parametrize("k", [3, 4, 6, 8])
+def test_interpolation_reference_assertions(bk, k):
+    """test/interpolation.jl:4-52 restated (Float64 data; the other element types are covered above): interpolation
+    at 40 sorted normal deviates without and with natural boundary conditions — S.(xs) ≈ ys, the unique knots of the
+    natural interpolant are the data locations, derivatives 2 .. k/2 vanish at both boundaries."""
+    rng = np.random.default_rng(42)
+    xs = np.sort(rng.standard_normal(40))
+    ys = rng.standard_normal(40)
+    S = bk.spline(bk.interpolate(xs, ys, bk.BSplineOrder(k)))
+    assert np.allclose(S(xs), ys, rtol=1e-9, atol=1e-9)
+    xi = np.arange(11) ** 2                                     # "Integer xdata" (:60-65)
+    yi = rng.random(xi.size)
+    assert np.allclose(bk.interpolate(xi, yi, bk.BSplineOrder(4))(xi.astype(float)), yi, rtol=1e-12, atol=1e-12)
+    if k % 2:
+        return
+    Sn = bk.spline(bk.interpolate(xs, ys, bk.BSplineOrder(k), bk.Natural()))
+    assert np.allclose(Sn(xs), ys, rtol=1e-8, atol=1e-8)
+    ts = bk.knots(Sn)
+    tu = ts[k - 1:ts.size - k + 1]
+    assert np.unique(tu).size == tu.size and tu.size == xs.size and np.array_equal(tu, xs)
+    a, b = bk.boundaries(bk.basis(Sn))
+    for n in range(2, k // 2 + 1):
+        Sd = bk.Derivative(n) * Sn
+        for v in (a, b):
+            assert abs(Sd(np.array([v]), algo=bk.EVAL_DEBOOR)[0]) < abs(Sn(np.array([v]), algo=bk.EVAL_DEBOOR)[0]) * 1e-7
