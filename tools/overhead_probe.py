@@ -1,3 +1,5 @@
+"""Host issue cost vs device time per step of S.evaluate on device-resident points (4096 and 2^25 points, 20 and
+200 back-to-back steps): how much of a short step is launch overhead.  Run on the GPU box."""
 import sys, os, time
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/bsplinekit.jl_b200")
 import torch, numpy as np
