@@ -1,0 +1,150 @@
+"""Randomised differential test of the evaluation and interpolation paths against the oracle (fixed seeds, so the
+run is reproducible): random orders, knot vectors with uneven spacing / clusters / repeated interior knots, plain
+and periodic bases, Float64 and Float32, every derivative order, points on and around every knot and outside the
+domain.  The de Boor path must reproduce the oracle bit for bit; the default path must stay inside the north-star
+tolerance (1e-13 / 1e-5 of the output's magnitude)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from bsplinekit_b200 import synth as s
+    return s
+
+
+def _random_breaks(rng, nb, style):
+    if style == "jitter":
+        i = np.arange(nb, dtype=np.float64)
+        x = (i + 0.45 * (2 * rng.random(nb) - 1)) / (nb - 1)
+    elif style == "geometric":
+        x = np.cumsum(np.exp(rng.uniform(-4.0, 2.0, nb)))
+    elif style == "cluster":
+        x = np.sort(rng.random(nb))
+        j = rng.integers(1, nb - 2)
+        x[j + 1] = x[j] + 1e-9 * (1 + rng.random())
+        x = np.sort(x)
+    else:                                                    # repeated interior knots (multiplicity 2 or 3)
+        x = np.sort(rng.random(nb))
+        for _ in range(2):
+            j = rng.integers(2, nb - 3)
+            x[j + 1] = x[j]
+        x = np.sort(x)
+    x = (x - x[0]) / (x[-1] - x[0])
+    a, L = rng.uniform(-3.0, 3.0), np.exp(rng.uniform(-2.0, 3.0))
+    x = a + L * x
+    x[0], x[-1] = a, a + L
+    return x
+
+
+@pytest.mark.parametrize("seed", list(range(60)))
+def test_random_spline_evaluation(bk, oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    k = int(rng.integers(2, 9))
+    dt = "f32" if seed % 4 == 3 else "f64"
+    npdt = np.float64 if dt == "f64" else np.float32
+    tol = 1e-13 if dt == "f64" else 1e-5
+    periodic = seed % 3 == 2
+    style = ("jitter", "geometric", "cluster", "repeat")[seed % 4] if not periodic else ("jitter", "geometric")[seed % 2]
+    nb = int(rng.integers(max(2 * k + 2, 8), 400))
+    br = _random_breaks(rng, nb, style).astype(npdt)
+    if np.any(np.diff(br) < 0):
+        br = np.sort(br)
+    if periodic:
+        if np.any(np.diff(br) <= 0):
+            br = np.unique(br)
+        B = bk.PeriodicBSplineBasis(k, br)
+        kind, tref = 1, br
+    else:
+        B = bk.BSplineBasis(k, br)
+        kind, tref = 0, B.knots()
+    c = (2 * rng.random(len(B)) - 1).astype(npdt)
+    S = bk.Spline(B, c)
+    a, b = float(br[0]), float(br[-1])
+    L = b - a
+    xs = np.concatenate([a + L * rng.random(4000), br.astype(np.float64),
+                         np.nextafter(br, np.inf).astype(np.float64), np.nextafter(br, -np.inf).astype(np.float64),
+                         [a - 0.3 * L, b + 0.3 * L, a - 2.5 * L, b + 2.5 * L]]).astype(npdt)
+    # bit-exact path, value
+    ref0 = oracle.spline_eval(kind, k, tref, c, xs, kt=dt)
+    got0 = S.evaluate(xs, (0,), algo=bk.EVAL_DEBOOR)[0]
+    assert np.array_equal(got0, ref0, equal_nan=True), (seed, k, dt, periodic, style)
+    # default path, every derivative order (at most 4 outputs per call)
+    refs = [ref0]
+    for d in range(1, k):
+        kd, td, cd = oracle.spline_derivative(kind, k, tref, c, d, kt=dt)
+        refs.append(oracle.spline_eval(kind, kd, td, cd, xs, kt=dt))
+    for lo in range(0, k, 4):
+        ds = tuple(range(lo, min(k, lo + 4)))
+        outs = S.evaluate(xs, ds)
+        for d, o in zip(ds, outs):
+            r = refs[d].astype(np.float64)
+            # D^(k-1) S is piecewise constant: a point within rounding of a knot may legitimately take either side
+            # only if the two paths disagree on the knot interval — they must not (searchsortedlast semantics)
+            scale = np.max(np.abs(r)) or 1.0
+            assert np.max(np.abs(o.astype(np.float64) - r)) <= tol * scale, (seed, k, dt, periodic, style, d)
+
+
+@pytest.mark.parametrize("seed", list(range(20)))
+def test_random_interpolation(bk, oracle, seed):
+    """interpolate(x, Y, BSplineOrder(k)) on random sites, a batch of data sets: against the oracle's banded
+    BANFAC / BANSLV on the same collocation matrix, and S(x_i) == y_i."""
+    import torch
+    rng = np.random.default_rng(2000 + seed)
+    k = int(rng.integers(2, 9))
+    n = int(rng.integers(max(2 * k, 8), 600))
+    x = np.sort(rng.random(n)) * np.exp(rng.uniform(-1, 2))
+    x = x + np.arange(n) * 1e-6                              # strictly increasing
+    M = int(rng.integers(1, 70))
+    Y = 2 * rng.random((n, M)) - 1
+    t = bk.make_knots(x, k)
+    assert np.array_equal(t, oracle.make_knots(x, k))
+    B = bk.BSplineBasis(k, t, augment=False)
+    itp = bk.SplineInterpolation(B, x)
+    Yd = torch.from_numpy(Y.copy()).cuda()
+    itp.interpolate_(Yd)
+    band, _ = oracle.collocation_matrix(0, k, t, x)
+    oracle.banded_lu(band)
+    ref = oracle.banded_solve(band, Y.copy())
+    got = Yd.cpu().numpy()
+    assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))
+    S = itp.spline_of(0)
+    assert np.max(np.abs(S(x) - Y[:, 0])) < 1e-9 * max(1.0, np.max(np.abs(ref[:, 0])))
+
+
+@pytest.mark.parametrize("seed", list(range(20)))
+def test_random_evaluate_all_and_knot_search(bk, oracle, seed):
+    """find_knot_interval and evaluate_all (all derivative orders, Float32 output of Float64 bases, recombined
+    bases with random Robin / Dirichlet / Neumann constraints) bit for bit against the oracle."""
+    rng = np.random.default_rng(3000 + seed)
+    k = int(rng.integers(2, 9))
+    style = ("jitter", "geometric", "cluster", "repeat")[seed % 4]
+    nb = int(rng.integers(max(2 * k + 2, 8), 300))
+    br = _random_breaks(rng, nb, style)
+    B = bk.BSplineBasis(k, br)
+    t = B.knots()
+    a, b = float(br[0]), float(br[-1])
+    x = np.concatenate([a + (b - a) * rng.random(3000), br, np.nextafter(br, np.inf), np.nextafter(br, -np.inf),
+                        [a - 1.0, b + 1.0, np.nan]])
+    i_ref, z_ref = oracle.find_knot_interval(0, k, t, x)
+    i, z = bk.find_knot_interval(B, x)
+    assert np.array_equal(i, i_ref) and np.array_equal(z, z_ref)
+    for nd in range(0, k):
+        ir, bsr = oracle.evaluate_all(0, k, t, x, nderiv=nd)
+        ig, bsg = bk.evaluate_all(B, x, bk.Derivative(nd))
+        assert np.array_equal(ig, ir) and np.array_equal(bsg, bsr, equal_nan=True), (seed, k, nd)
+    ir, bsr = oracle.evaluate_all(0, k, t, x, nderiv=min(1, k - 1), vt="f32")
+    ig, bsg = bk.evaluate_all(B, x, bk.Derivative(min(1, k - 1)), np.float32)
+    assert bsg.dtype == np.float32 and np.array_equal(bsg, bsr, equal_nan=True)
+    if k >= 3 and style in ("jitter", "geometric"):
+        ops = [bk.Derivative(0), bk.Derivative(1), bk.Derivative(0) + float(rng.uniform(0.5, 4.0)) * bk.Derivative(1)]
+        op = ops[seed % 3]
+        R = bk.RecombinedBSplineBasis(B, op)
+        rc = oracle.Recomb(R.cl, R.cr, R.nl, R.nr, R.ul, R.lr)
+        xin = x[:-3]
+        for nd in (0, 1):
+            ir, bsr = oracle.evaluate_all(2, k, t, xin, nderiv=nd, recomb=rc)
+            ig, bsg = bk.evaluate_all(R, xin, bk.Derivative(nd))
+            assert np.array_equal(ig, ir) and np.array_equal(bsg, bsr, equal_nan=True), (seed, k, nd, "recombined")
