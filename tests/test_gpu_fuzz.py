@@ -148,3 +148,53 @@ def test_random_evaluate_all_and_knot_search(bk, oracle, seed):
             ir, bsr = oracle.evaluate_all(2, k, t, xin, nderiv=nd, recomb=rc)
             ig, bsg = bk.evaluate_all(R, xin, bk.Derivative(nd))
             assert np.array_equal(ig, ir) and np.array_equal(bsg, bsr, equal_nan=True), (seed, k, nd, "recombined")
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_float32_interpolation_bitexact(bk, oracle, seed):
+    """The Float32 chain (assembly, BANFAC, BANSLV) on random sites and orders: bit for bit the Float32 restatement."""
+    import torch
+    rng = np.random.default_rng(4000 + seed)
+    k = int(rng.integers(2, 9))
+    n = int(rng.integers(max(2 * k, 8), 500))
+    x = (np.sort(rng.random(n)) + np.arange(n) * 1e-3).astype(np.float32)
+    t = bk.make_knots(x, k)
+    assert t.dtype == np.float32
+    B = bk.BSplineBasis(k, t, augment=False)
+    Cm = bk.collocation_matrix(B, x)
+    ref, nout = oracle.collocation_matrix_f32(0, k, t, x)
+    assert np.array_equal(Cm.data(), ref)
+    lu_ref = ref.copy(order="F")
+    assert oracle.banded_lu(lu_ref) == 0
+    Cm.lu_()
+    assert np.array_equal(Cm.data(), lu_ref)
+    M = int(rng.integers(1, 100))
+    Y = (2 * rng.random((n, M)) - 1).astype(np.float32)
+    Yd = torch.from_numpy(Y.copy()).cuda()
+    Cm.ldiv_(Yd, algo=bk.SOLVE_TWOPASS)
+    assert np.array_equal(Yd.cpu().numpy(), oracle.banded_solve(lu_ref, Y.copy()))
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_periodic_interpolation(bk, oracle, seed):
+    """Periodic interpolation of every order (cyclic tridiagonal for k = 4, Woodbury-corrected band otherwise) on
+    random sites: against a dense pivoted solve of the oracle's periodic collocation matrix; S(x_i) == y_i and
+    S(x + L) == S(x)."""
+    rng = np.random.default_rng(5000 + seed)
+    k = int(rng.integers(2, 8))
+    n = int(rng.integers(4 * k + 2, 300))
+    L = float(np.exp(rng.uniform(-1, 2)))
+    x = -0.3 * L + L * (np.arange(n) + 0.45 * (2 * rng.random(n) - 1)) / n
+    y = 2 * rng.random(n) - 1
+    itp = bk.interpolate(x, y, bk.BSplineOrder(k), bk.Periodic(L))
+    S = itp.spline
+    data = oracle.make_knots_periodic(x, k, L)
+    xc = x if k != 2 else data[:-1]
+    A = oracle.periodic_collocation_dense(k, data, xc)
+    cref = np.linalg.solve(A, y)
+    cond = np.linalg.cond(A)
+    assert np.max(np.abs(S.coefficients() - cref)) <= 1e-13 * cond * np.max(np.abs(cref))
+    assert np.max(np.abs(S(x) - y)) < 1e-12 * cond * max(1.0, np.max(np.abs(cref)))
+    xq = x[0] + L * rng.random(500)
+    assert np.max(np.abs(S(xq + L) - S(xq))) < 1e-11 * max(1.0, np.max(np.abs(cref)))
+    assert np.max(np.abs(S(xq, algo=bk.EVAL_DEBOOR) - oracle.spline_eval(1, k, data, S.coefficients(), xq))) == 0
