@@ -100,6 +100,12 @@ k_probe_gather(const double *__restrict__ x, double *__restrict__ out, int64_t n
             __syncwarp();
             const int64_t Tn = Tc + DEPTH * GW;
             if (lane == 0 && Tn < ntile) {
+                // The LDS above has been ISSUED, not performed: behind a queue of divergent gathers it can sit in
+                // the load/store pipe for longer than a DRAM round trip, and the bulk copy (async proxy) is not
+                // ordered behind it — without this fence the refill overwrote half-read tiles (measured: 7 % of
+                // the points wrong with 512-byte tiles).  The issuing lane took part in the warp-wide LDS, so
+                // fence.proxy.async here waits for that instruction before the copy may start.
+                fence_proxy_async();
                 mbar_expect_tx(bars + 8u * slot, TILEV * 16);
                 bulk_g2s(ring_s + (unsigned)slot * (TILEV * 16), x4 + Tn * TILEV, TILEV * 16, bars + 8u * slot);
             }
