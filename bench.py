@@ -441,6 +441,24 @@ def run_ours(args):
         itp = bk.SplineInterpolation(Bi, xdata)
         torch.cuda.synchronize()
         factor_ms = 1e3 * (time.perf_counter() - t_f0)
+        # lu! alone (elimination + repack + decay analysis + solve records), best of 5, host clock around a
+        # synchronised call: C3's matrix and n = 10^5, k = 8 (the partitioned factorisation, DESIGN K5)
+        lu_ms = {}
+        for tag, (nn, kq) in (("c3", (n, kk)), ("n1e5_k8", (100000, 8))):
+            xq = xdata if tag == "c3" else synth.breakpoints(6, nn)
+            Bq = Bi if tag == "c3" else bk.BSplineBasis(kq, bk.make_knots(xq, kq), augment=False)
+            for mname, lmode in (("fast", bk.LU_FAST), ("exact", bk.LU_EXACT)):
+                best = None
+                for _ in range(5):
+                    Cq = bk.collocation_matrix(Bq, xq)
+                    torch.cuda.synchronize()
+                    t_l0 = time.perf_counter()
+                    Cq.lu_(lmode)
+                    torch.cuda.synchronize()
+                    dt_l = 1e3 * (time.perf_counter() - t_l0)
+                    best = dt_l if best is None else min(best, dt_l)
+                    del Cq
+                lu_ms[tag + "_" + mname] = best
         Y0 = (2 * synth.u_torch(7, rank * n * nrhs, n * nrhs) - 1).reshape(n, nrhs)
         Y = torch.empty_like(Y0)
         res = {}
@@ -467,7 +485,9 @@ def run_ours(args):
                  "solve_rhs_per_s": best["rhs_per_s"], "solve_ms": best["ms"], "solve_roofline_frac": best["frac"],
                  "solve_traffic": (st_ * nrhs / 65536.0) if st_ else None, "solve_algo": best_name,
                  "solve_twopass_ms": res["twopass"]["ms"], "solve_factor_once_ms": factor_ms,
-                 "solve_factor_first_call_ms": factor_first_ms, "solve_halo_rows": itp.C.halo,
+                 "solve_factor_first_call_ms": factor_first_ms, "solve_lu_ms": lu_ms["c3_fast"],
+                 "solve_lu_exact_ms": lu_ms["c3_exact"], "solve_lu_n1e5_k8_ms": lu_ms["n1e5_k8_fast"],
+                 "solve_lu_n1e5_k8_exact_ms": lu_ms["n1e5_k8_exact"], "solve_halo_rows": itp.C.halo,
                  "solve_rhs_per_gpu": nrhs}
         if not args.no_extra_configs:
             # du = F \ (L u), mul! + ldiv! of a collocation time step in one pass
