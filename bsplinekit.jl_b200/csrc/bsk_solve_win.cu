@@ -98,7 +98,6 @@ k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ ur
     double *const cur = ring + (size_t)RW * TB;
     double *const cfw = cur + (size_t)RW * UW;
     const int lane = threadIdx.x;
-    const int hb = H / M;
     double *const my = ring + lane;                          // my[slot * TB]
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     const unsigned cur_s = (unsigned)__cvta_generic_to_shared(cur);
@@ -190,12 +189,14 @@ k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ ur
 #pragma unroll
             for (int j = 0; j < BW; ++j) tf[j] = my[j * TB];
         }
-        for (int b = 0; b < nblk + hb; ++b) {
-            // ---- forward sweep over block b (right-looking: z_i final -> update rows i+1..i+BW) ----
-            if (b < nblk) {
-                const int r1 = min(n_pad, (b + 1) * M);
+        int fpos = 0;                                        // rows forwarded so far
+        for (int bb = 0; bb < nblk; ++bb) {
+            // ---- forward sweep up to the restart row of block bb, (bb + 1) M + H (right-looking: z_i final ->
+            //      update rows i+1..i+BW); H need not be a multiple of M (see k_banded_tmem) ----
+            {
+                const int r1 = min(n_pad, (bb + 1) * M + H);
 #pragma unroll 1
-                for (int r0 = b * M; r0 < r1; r0 += G) {
+                for (int r0 = fpos; r0 < r1; r0 += G) {
                     const unsigned i = (conA - 1) % PG;                    // chunk of rows r0 .. r0+7
                     mbar_wait(barA_s + 8 * (conA % PG), (conA / PG) & 1);  // next chunk (look-ahead rows)
                     ++conA;
@@ -230,10 +231,10 @@ k_banded_windowed(const double *__restrict__ lrec, const double *__restrict__ ur
                     f_slot = n_slot;
                     issue_fwd();
                 }
+                fpos = max(fpos, r1);
             }
-            // ---- backward sweep that finalises block bb = b - hb ------------------------------
-            const int bb = b - hb;
-            if (bb >= 0 && bb * M >= kl0 && bb * M < kl1) {
+            // ---- backward sweep that finalises block bb ------------------------------------------
+            if (bb * M >= kl0 && bb * M < kl1) {
                 const int keep_lo = bb * M;
                 const int keep_hi = min(n_pad, (bb + 1) * M);
                 const int r_top = min(n_pad, (bb + 1) * M + H);   // exclusive, multiple of 8
@@ -400,7 +401,6 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
     const unsigned cfw_s = (unsigned)__cvta_generic_to_shared(cfw);
     const unsigned cmv_s = (unsigned)__cvta_generic_to_shared(cmv);
     const unsigned barA_s = cmv_s + (unsigned)(MWS * 8);
-    const int hb = H / M;
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < PG; ++i) mbar_init(barA_s + 8 * i, 1);
@@ -483,11 +483,16 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
                 for (int j = 0; j < BW; ++j) tf[j] = ys[j * TB];
             }
         }
-        for (int b = 0; b < nblk + hb; ++b) {
-            if (b < nblk) {
-                const int r1 = min(n_pad, (b + 1) * M);
+        // The forward sweep runs in 8-row chunks; block bb (M rows) is finalised by a backward sweep as soon as the
+        // forward sweep has passed its restart row (bb + 1) M + H.  H need not be a multiple of M: the ring holds
+        // M + H rows, the backward sweeps touch every row (M + H) / M times — with M = ring - H that is 1.8 (Float64,
+        // H = 56) or 1.45 (Float32, H = 40) instead of the 2.0 of M = H.
+        int fpos = 0;                                        // rows forwarded so far
+        for (int bb = 0; bb < nblk; ++bb) {
+            {
+                const int r1 = min(n_pad, (bb + 1) * M + H);
 #pragma unroll 1
-                for (int r0 = b * M; r0 < r1; r0 += G) {
+                for (int r0 = fpos; r0 < r1; r0 += G) {
                     const unsigned i = (conA - 1) % PG;
                     const unsigned inext = conA % PG;
                     mbar_wait(barA_s + 8 * inext, (conA / PG) & 1);
@@ -544,9 +549,9 @@ k_banded_tmem(const double *__restrict__ lrec, const double *__restrict__ urec,
                     if (f_slot == RWT) f_slot = 0;
                     issue_fwd();
                 }
+                fpos = max(fpos, r1);
             }
-            const int bb = b - hb;
-            if (bb >= 0 && bb * M >= kl0 && bb * M < kl1) {
+            if (bb * M >= kl0 && bb * M < kl1) {
                 const int keep_lo = bb * M;
                 const int keep_hi = min(n_pad, (bb + 1) * M);
                 const int r_top = min(n_pad, (bb + 1) * M + H);
@@ -719,14 +724,27 @@ bsk_status solve_t(const WinMat &hm, double *d_rhs, int64_t ngroups, int64_t ld,
         if (m >= 8 && m % 8 == 0) M = m;
     }
     if (const char *env = getenv("BSK_WINDOW_CTAS")) per_sm_cap = std::max(1, atoi(env));
-    const int H = ((h->halo + M - 1) / M) * M;
-    const size_t smem = ((size_t)(M + H + PG * G) * (32 + UW) + (size_t)PG * G * LW + PG) * sizeof(double);
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(per_sm_cap, (226 * 1024) / (smem + 1024)));
-    const int64_t slots = (int64_t)sm_count(h->device) * per_sm;
+    int H = ((h->halo + M - 1) / M) * M;
     // TMEM ring: 4 resident CTAs per SM (16 warps, 64 ring rows per lane) when the window fits, else 2 (128 rows)
     int occ = (M + H <= TmemCfg<4>::kRows && !fused) ? 4 : 2;
     if (const char *env = getenv("BSK_TMEM_OCC")) { if (atoi(env) == 2) occ = 2; }
-    const bool tmem_ok = M + H <= TmemCfg<2>::kRows && getenv("BSK_NO_TMEM") == nullptr && get_encoder() != nullptr;
+    bool tmem_ok = M + H <= TmemCfg<2>::kRows && getenv("BSK_NO_TMEM") == nullptr && get_encoder() != nullptr;
+    // The TMEM kernel takes any halo that is a multiple of 8 (k_banded_tmem: the forward position is decoupled from
+    // the backward blocks): H = the validated halo itself, M = what is left of the ring.  The backward sweeps then
+    // touch every row (M + H) / M times instead of twice.
+    if (get_encoder() != nullptr && getenv("BSK_NO_TMEM") == nullptr && getenv("BSK_WINDOW_M") == nullptr &&
+        getenv("BSK_WINDOW_EQUAL") == nullptr && h->halo % G == 0 && h->halo + G <= TmemCfg<2>::kRows) {
+        H = h->halo;
+        // (two CTAs per SM with the long blocks of a 128-row ring beat four CTAs with a 64-row ring also for the
+        //  short halos of tridiagonal systems: C4's cyclic solve 0.527 vs 0.550 ms; BSK_TMEM_OCC=4 keeps the other)
+        const char *eo = getenv("BSK_TMEM_OCC");
+        occ = (!fused && eo && atoi(eo) == 4 && 2 * H <= TmemCfg<4>::kRows) ? 4 : 2;
+        M = (occ == 4 ? TmemCfg<4>::kRows : TmemCfg<2>::kRows) - H;
+        tmem_ok = true;
+    }
+    const size_t smem = ((size_t)(M + H + PG * G) * (32 + UW) + (size_t)PG * G * LW + PG) * sizeof(double);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(per_sm_cap, (226 * 1024) / (smem + 1024)));
+    const int64_t slots = (int64_t)sm_count(h->device) * per_sm;
     // Row segments: only when there are too few column groups to fill the machine and the forward
     // recurrence decays too (halo_f > 0).  Redundant work per segment: (HF + H) rows.
     int nseg = 1, SEG = h->n_pad, HF = 0;
