@@ -24,6 +24,10 @@
  *    legacy default stream and return with their device work complete.  Streams from
  *    bsk_stream_create are BLOCKING streams, which order against the default stream; work a caller
  *    enqueues on its own non-blocking stream must be synchronised before such a call reads it.
+ *  - the evaluation kernels of bsk_spline_eval* are launched with programmatic stream serialization: the
+ *    staging of their (read-only, host-built) tables may overlap the tail of the previous kernel on the
+ *    stream; points are read and results written only after that kernel has completed and flushed, so
+ *    stream order is what the caller sees.
  *  - there is no CPU fallback: with no CUDA device every compute call fails with
  *    BSK_ERR_CUDA.
  */
