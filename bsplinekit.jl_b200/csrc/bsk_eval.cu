@@ -733,9 +733,12 @@ bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout,
         // 1) uniform-cell table in shared memory (bsk_eval_cell.cu): needs every pointer to share
         //    the same 16-byte phase; the unaligned head / tail go through the scalar pp kernel.
         constexpr int VEC = 16 / (int)sizeof(T);
-        // (splines with interval records that are not certified take the interval-table kernel, which
-        //  carries the de Boor route for those records)
-        const bool want_cell = s->cell_valid && s->pp_uncertified == 0 && getenv("BSK_NO_CELL") == nullptr;
+        // (splines with interval records that are not certified take the UNC = 1 variant of the cell kernel, which
+        //  carries the de Boor route for those records out of line; with an extrapolation method they take the
+        //  interval-table kernel as before)
+        const bool unc = s->pp_uncertified > 0;
+        const bool unc_cell_ok = extrap == 0 && getenv("BSK_UNC_PP") == nullptr;
+        const bool want_cell = s->cell_valid && (!unc || unc_cell_ok) && getenv("BSK_NO_CELL") == nullptr;
         if (want_cell) {
             const uintptr_t phase = ((uintptr_t)d_x) & 15;
             bool same = (phase % sizeof(T)) == 0;

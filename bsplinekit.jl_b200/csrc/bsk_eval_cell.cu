@@ -142,13 +142,22 @@ template <int DMASK> struct MaskCount {
 // uncertified records go through k_spline_pp, which carries the de Boor route), so the record's flag
 // is not looked at here.
 template <int K, typename T>
-__device__ __noinline__ void fallback_interval(const PPView<T> pv, T xs, T *cm, T *u) {
-    pp_lookup<K, T>(pv, xs, cm, u);
+__device__ __noinline__ bool fallback_interval(const PPView<T> pv, T xs, T *cm, T *u) {
+    return pp_lookup<K, T>(pv, xs, cm, u);
+}
+
+// UNC = 1 kernels only (splines with interval records that are not certified, e.g. two knots 1e-9 apart): the
+// point is evaluated by the bit-faithful de Boor recurrence, out of line.  Such intervals always sit in cells that
+// take the slow path above (the table builder sends every cell that touches one to the interval table), so this
+// costs the kernels of ordinary splines nothing: they are the UNC = 0 instantiations.
+template <int KIND, typename T>
+__device__ __noinline__ T deboor_exact_ool(KnotView<T> kv, int K, int d, const T *dcoefs, int ncoef, T xs, T xq) {
+    return deboor_exact<KIND, T>(kv, K, d, dcoefs, ncoef, xs, xq);
 }
 
 // EX = 1: extrapolation methods compiled in (SplineExtrapolations.jl:22-71); the plain kernels carry
 // none of that code.
-template <int K, int KIND, typename T, int DMASK, int STAGE, int EX>
+template <int K, int KIND, typename T, int DMASK, int STAGE, int EX, int UNC = 0>
 __global__ void __launch_bounds__(kCellThreads, 1)
 k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *__restrict__ x,
               int64_t nvec, EvalOuts outs) {
@@ -302,9 +311,11 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
             for (int m = 0; m < K; ++m) cm[m] = rec_[q][m];
             T u = xs - fma((T)c_[q] + (T)0.5, cw, x0);
             const bool smooth_out = KIND == 0 && E == BSK_EXTRAP_SMOOTH && outside;
+            bool exact = false;
             if (multi_[q]) {
                 T cm2[K], u2;              // separate locals: keep cm[] itself in registers
-                fallback_interval<K, T>(pv, xs, cm2, &u2);
+                const bool flagged = fallback_interval<K, T>(pv, xs, cm2, &u2);
+                if (UNC) exact = flagged;
 #pragma unroll
                 for (int m = 0; m < K; ++m) cm[m] = cm2[m];
                 u = u2;
@@ -322,6 +333,15 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o)
                         if (o < outs.nout) r1[o] = add_jump_term<K, T>(r1[o], jump_[q], dxk_[q], outs.deriv[o]);
+                }
+            }
+            if (UNC) {
+                if (exact) {
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o)
+                        if (DMASK != 0 || o < outs.nout)
+                            r1[o] = deboor_exact_ool<KIND, T>(kv, K, outs.deriv[o], (const T *)outs.dcoefs[o], ncoef, xs,
+                                                              smooth_out ? xq : xs);
                 }
             }
 #pragma unroll
@@ -383,6 +403,19 @@ bsk_status launch_cell_mask(const bsk_spline *s, const CellView<T> &cv, const PP
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const int ncoef = (int)s->ncoef;
+    if constexpr (EX == 0) {
+        if (s->pp_uncertified > 0) {                     // the variant that carries the de Boor route
+            if (smem > 0) {
+                auto kern = k_spline_cell<K, KIND, T, DMASK, 1, 0, 1>;
+                BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                BSK_CUDA(cudaLaunchKernelEx(&cfg, kern, cv, pv, kv, ncoef, d_x, nvec, outs));
+            } else {
+                auto kern = k_spline_cell<K, KIND, T, DMASK, 0, 0, 1>;
+                BSK_CUDA(cudaLaunchKernelEx(&cfg, kern, cv, pv, kv, ncoef, d_x, nvec, outs));
+            }
+            return BSK_OK;
+        }
+    }
     if (smem > 0) {
         auto kern = k_spline_cell<K, KIND, T, DMASK, 1, EX>;
         BSK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
