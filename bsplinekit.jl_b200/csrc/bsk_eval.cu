@@ -496,6 +496,8 @@ bsk_status build_pp(bsk_spline *s) {
     in.allow_global_cell = getenv("BSK_NO_GLOBAL_CELL") == nullptr;
     const char *e = getenv("BSK_GLOBAL_CELL_MULT2");        // cells per interval, x2
     in.global_cells_x2 = e ? atoi(e) : 64;
+    if (const char *e2 = getenv("BSK_GLOBAL_MAX_REC")) in.global_max_rec = atoll(e2);
+    if (const char *e3 = getenv("BSK_GLOBAL_CAP_MB")) in.global_cap_bytes = atoll(e3) << 20;
     EvalTables<T> tb;
     std::string err;
     if (!build_eval_tables<T>(in, tb, &err)) {

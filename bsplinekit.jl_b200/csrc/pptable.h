@@ -46,6 +46,8 @@ struct TableInput {
     const std::vector<double> *coefs;    // coefficients in the evaluation basis
     bool allow_global_cell;              // tables too large for shared memory may stay in global memory
     int global_cells_x2;                 // cells per interval (x2) of a global-memory table
+    int64_t global_max_rec = 400000;     // most knot intervals a global-memory cell table is built for
+    int64_t global_cap_bytes = 32ll << 20;   // its size cap (the cell count shrinks to fit, down to 3 per interval)
 };
 
 template <typename T>
@@ -360,13 +362,13 @@ struct TableBuilder {
         int64_t nc = (int64_t)((budget - std::min<size_t>(budget, (size_t)(nbp + 8) * side_bytes)) / (RECV * sizeof(T)));
         nc = std::min<int64_t>(nc, 16 * nrec);
         nc = std::min<int64_t>(nc, 60000);
-        const bool in_global = nc < 3 * nrec && nrec <= 400000 && in.allow_global_cell;
+        const bool in_global = nc < 3 * nrec && nrec <= in.global_max_rec && in.allow_global_cell;
         const bool jump = jump_ok && !in_global;
         const bool jpad = jump && cell_jump_pad(k);
         if (in_global) {
             const int m2 = std::max(6, in.global_cells_x2);
             nc = (nrec * m2) / 2;
-            const int64_t cap = (32ll << 20) / (int64_t)(cell_global_stride((int)sizeof(T), RECV) * sizeof(T));
+            const int64_t cap = in.global_cap_bytes / (int64_t)(cell_global_stride((int)sizeof(T), RECV) * sizeof(T));
             nc = std::max<int64_t>(std::min(nc, cap), 3 * nrec);
         }
         for (int attempt = 0; attempt < 6 && nc >= 3 * nrec && nc >= 8; ++attempt, nc = nc * 9 / 10) {
