@@ -2030,3 +2030,46 @@ def test_interpolation_reference_assertions(bk, k):
         Sd = bk.Derivative(n) * Sn
         for v in (a, b):
             assert abs(Sd(np.array([v]), algo=bk.EVAL_DEBOOR)[0]) < abs(Sn(np.array([v]), algo=bk.EVAL_DEBOOR)[0]) * 1e-7
+
+
+def test_concurrent_evaluation_of_one_handle(bk, oracle, synth):
+    """Several host threads evaluate the SAME freshly created spline handle at once, each on its own stream: the
+    lazy table build is serialised by the handle's lock, every thread gets the same, correct results (the C ABI's
+    thread-safety statement in bsk.h)."""
+    import threading
+    import torch
+    k = 4
+    B = bk.BSplineBasis(k, synth.breakpoints(3, 700))
+    c = 2 * synth.u_numpy(4, 0, len(B)) - 1
+    n = 1 << 20
+    xs = [synth.u_torch(90 + t, 0, n) for t in range(4)]
+    for rnd in range(3):
+        S = bk.Spline(B, c)                                   # fresh handle: tables not built yet
+        outs = [None] * 4
+        errs = []
+
+        def work(t):
+            try:
+                st = torch.cuda.Stream()
+                with torch.cuda.stream(st):
+                    v, dv = S.evaluate(xs[t], (0, 1))
+                    w = S.evaluate(xs[t], (0,), algo=bk.EVAL_DEBOOR)[0]
+                st.synchronize()
+                outs[t] = (v, dv, w)
+            except Exception as exc:                          # surfaced below
+                errs.append(exc)
+
+        th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        assert not errs, errs
+        kd, td, cd = oracle.spline_derivative(0, k, B.knots(), c, 1)
+        for t in range(4):
+            xh = xs[t][:20000].cpu().numpy()
+            ref = oracle.spline_eval(0, k, B.knots(), c, xh)
+            refd = oracle.spline_eval(0, kd, td, cd, xh)
+            v, dv, w = outs[t]
+            assert np.array_equal(w[:20000].cpu().numpy(), ref)
+            assert relerr(v[:20000].cpu().numpy(), ref) < TOL64 and relerr(dv[:20000].cpu().numpy(), refd) < TOL64
