@@ -5,7 +5,11 @@
 // repeated calls do not pay cudaMalloc / cudaFree (which synchronises the device).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "handles.cuh"
 
@@ -38,6 +42,105 @@ cudaError_t pool_get(Pool &p, int slot, int b, size_t bytes, void **out) {
     return cudaSuccess;
 }
 
+// Pinned staging for PAGEABLE caller arrays (what a Julia Vector or a numpy array is): the driver's own path for
+// pageable memory stages through one thread at ~10 GB/s and blocks the caller for every chunk; here the caller's
+// chunk is copied to / from page-locked buffers by a few host threads while the previous chunk is on the device.
+struct PinPool {
+    void *buf[kSlots][kBufs] = {{nullptr}};
+    size_t cap[kSlots][kBufs] = {{0}};
+};
+PinPool g_pin[kMaxDev];
+
+cudaError_t pin_get(PinPool &p, int slot, int b, size_t bytes, void **out) {
+    if (p.cap[slot][b] < bytes) {
+        if (p.buf[slot][b]) cudaFreeHost(p.buf[slot][b]);
+        p.buf[slot][b] = nullptr;
+        p.cap[slot][b] = 0;
+        cudaError_t e = cudaHostAlloc(&p.buf[slot][b], bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        p.cap[slot][b] = bytes;
+    }
+    *out = p.buf[slot][b];
+    return cudaSuccess;
+}
+
+bool is_pageable(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// A few persistent copy threads (created on first use, joined at exit): spawning threads per chunk costs more
+// than the copy of a 1 MB piece.
+class CopyPool {
+  public:
+    explicit CopyPool(unsigned n) {
+        for (unsigned t = 0; t < n; ++t) th_.emplace_back([this] { run(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> l(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    unsigned size() const { return (unsigned)th_.size(); }
+    // copy `bytes` in `parts` pieces; the caller copies piece 0 itself and waits for the others
+    void copy(void *dst, const void *src, size_t bytes, unsigned parts) {
+        const size_t step = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            for (unsigned t = 1; t < parts; ++t) {
+                const size_t o = std::min(bytes, (size_t)t * step), m = std::min(step, bytes - o);
+                if (m) { jobs_.push_back({(char *)dst + o, (const char *)src + o, m}); ++pending_; }
+            }
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(step, bytes));
+        std::unique_lock<std::mutex> l(mu_);
+        done_.wait(l, [this] { return pending_ == 0; });
+    }
+
+  private:
+    struct Job { char *d; const char *s; size_t n; };
+    void run() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [this] { return stop_ || !jobs_.empty(); });
+                if (stop_ && jobs_.empty()) return;
+                j = jobs_.back();
+                jobs_.pop_back();
+            }
+            memcpy(j.d, j.s, j.n);
+            {
+                std::lock_guard<std::mutex> l(mu_);
+                --pending_;
+            }
+            done_.notify_all();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::vector<Job> jobs_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    size_t pending_ = 0;
+    bool stop_ = false;
+};
+
+// (called with the device's pool mutex held: one staged call per device at a time; calls on different devices
+//  share the copy threads, serialised by copy_mu)
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    static const unsigned cap = getenv("BSK_HOST_THREADS") ? (unsigned)std::max(1, atoi(getenv("BSK_HOST_THREADS"))) : 8u;
+    static std::mutex copy_mu;
+    const size_t per = (size_t)1 << 20;                       // at least 1 MB per piece
+    const unsigned nt = (unsigned)std::min<size_t>(std::min<unsigned>(cap, hw), (bytes + per - 1) / per);
+    if (nt <= 1) { memcpy(dst, src, bytes); return; }
+    std::lock_guard<std::mutex> l(copy_mu);
+    static CopyPool pool(std::min<unsigned>(cap, hw) - 1);
+    pool.copy(dst, src, bytes, std::min(nt, pool.size() + 1));
+}
+
 cudaError_t pool_stream(Pool &p, int slot, cudaStream_t *out) {
     if (!p.st[slot]) {
         cudaError_t e = cudaStreamCreateWithFlags(&p.st[slot], cudaStreamNonBlocking);
@@ -61,9 +164,13 @@ static bsk_status eval_host_impl(const bsk_spline *s, const void *h_x, int64_t n
     BSK_CUDA(cudaSetDevice(device));
     std::lock_guard<std::mutex> lock(g_pool_mu[device]);
     Pool &pool = g_pool[device];
-    int chunk_log2 = 23;                              // 2^23 points per chunk (64 MB of Float64 points)
+    // pageable caller arrays go through page-locked staging buffers in smaller chunks (see PinPool)
+    bool staged = getenv("BSK_HOST_NO_STAGING") == nullptr && n >= (1 << 14) && is_pageable(h_x);
+    for (int o = 0; o < nout && staged; ++o) staged = is_pageable(h_outs[o]);
+    int chunk_log2 = staged ? (n >= ((int64_t)1 << 24) ? 22 : 20) : 23;      // 2^23 points per chunk (64 MB of Float64 points); staged: 2^20 .. 2^22
     if (const char *ev = getenv("BSK_HOST_CHUNK_LOG2")) chunk_log2 = std::max(16, std::min(27, atoi(ev)));
-    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << chunk_log2);
+    int64_t chunk = std::min<int64_t>(n, (int64_t)1 << chunk_log2);
+    if (staged && n > (1 << 16) && n < 3 * chunk) chunk = ((n + 2) / 3 + 1023) / 1024 * 1024;   // at least three chunks to overlap
     const int nslots = (int)std::min<int64_t>(kSlots, (n + chunk - 1) / chunk);
     cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
     void *dx[kSlots] = {nullptr, nullptr, nullptr};
@@ -75,7 +182,50 @@ static bsk_status eval_host_impl(const bsk_spline *s, const void *h_x, int64_t n
         if (e == cudaSuccess) e = pool_get(pool, i, 0, es * chunk, &dx[i]);
         for (int o = 0; o < nout && e == cudaSuccess; ++o) e = pool_get(pool, i, 1 + o, es * chunk, &dout[i][o]);
     }
-    if (e == cudaSuccess) {
+    void *px[kSlots] = {nullptr, nullptr, nullptr};
+    void *pout[kSlots][4] = {{nullptr}};
+    if (staged) {
+        PinPool &pin = g_pin[device];
+        for (int i = 0; i < nslots && e == cudaSuccess; ++i) {
+            e = pin_get(pin, i, 0, es * chunk, &px[i]);
+            for (int o = 0; o < nout && e == cudaSuccess; ++o) e = pin_get(pin, i, 1 + o, es * chunk, &pout[i][o]);
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); staged = false; e = cudaSuccess; }      // no page-locked memory: plain path
+    }
+    if (e == cudaSuccess && staged) {
+        int64_t pend_off[kSlots] = {-1, -1, -1}, pend_m[kSlots] = {0, 0, 0};
+        auto drain = [&](int slot) -> cudaError_t {           // results of the chunk last issued on `slot` -> caller
+            if (pend_off[slot] < 0) return cudaSuccess;
+            cudaError_t ee = cudaStreamSynchronize(st[slot]);
+            if (ee != cudaSuccess) return ee;
+            for (int o = 0; o < nout; ++o)
+                parallel_memcpy((char *)h_outs[o] + es * pend_off[slot], pout[slot][o], es * pend_m[slot]);
+            pend_off[slot] = -1;
+            return cudaSuccess;
+        };
+        int64_t off = 0;
+        for (int64_t ci = 0; off < n && rc == BSK_OK; ++ci, off += chunk) {
+            const int slot = (int)(ci % nslots);
+            const int64_t m = std::min(chunk, n - off);
+            if ((e = drain(slot)) != cudaSuccess) break;
+            parallel_memcpy(px[slot], (const char *)h_x + es * off, es * m);
+            e = cudaMemcpyAsync(dx[slot], px[slot], es * m, cudaMemcpyHostToDevice, st[slot]);
+            if (e != cudaSuccess) break;
+            if (!copy_only) rc = bsk_spline_eval(s, dx[slot], m, nout, derivs, dout[slot], algo, (void *)st[slot]);
+            if (rc != BSK_OK) break;
+            for (int o = 0; o < nout && e == cudaSuccess; ++o)
+                e = cudaMemcpyAsync(pout[slot][o], dout[slot][o], es * m, cudaMemcpyDeviceToHost, st[slot]);
+            if (e != cudaSuccess) break;
+            pend_off[slot] = off;
+            pend_m[slot] = m;
+        }
+        // the chunks still in flight, oldest first
+        if (e == cudaSuccess && rc == BSK_OK) {
+            const int64_t nchunks = (n + chunk - 1) / chunk;
+            for (int64_t ci = std::max<int64_t>(0, nchunks - nslots); ci < nchunks && e == cudaSuccess; ++ci)
+                e = drain((int)(ci % nslots));
+        }
+    } else if (e == cudaSuccess) {
         int64_t off = 0;
         for (int64_t ci = 0; off < n && rc == BSK_OK; ++ci, off += chunk) {
             const int slot = (int)(ci % nslots);
