@@ -420,6 +420,19 @@ def run_ours(args):
                "copy_only_gbs_per_gpu": 24.0 * ne / dt_copy / 1e9,
                "frac_of_copy_only": dt_copy / dt}
         del xh, oh
+        # the same call with PAGEABLE arrays (what a caller coming from Julia / numpy has): 2^26 points, rank 0 only
+        if rank == 0 and world == 1:
+            npg = min(ne, 1 << 26)
+            xpg = np.array(xnp[:npg])
+            opg = [np.empty(npg), np.empty(npg)]
+            S.evaluate(xpg, (0, 1), algo=algo, out=opg)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                S.evaluate(xpg, (0, 1), algo=algo, out=opg)
+            e2e["pageable_gpoints_per_s"] = 3 * npg / (time.perf_counter() - t0) / 1e9
+            e2e["pageable_points_per_step"] = npg
+            assert np.array_equal(opg[0][:1024], onp[0][:1024])
+            del xpg, opg
 
     # ---- batched interpolation solve, configs[2]: top-level scalars ----------------------------------------
     extra = {}
