@@ -2073,3 +2073,35 @@ def test_concurrent_evaluation_of_one_handle(bk, oracle, synth):
             v, dv, w = outs[t]
             assert np.array_equal(w[:20000].cpu().numpy(), ref)
             assert relerr(v[:20000].cpu().numpy(), ref) < TOL64 and relerr(dv[:20000].cpu().numpy(), refd) < TOL64
+
+
+@pytest.mark.parametrize("k", [4, 6, 8])
+def test_collocation_boundary_value_problem(bk, k):
+    """The collocation work flow the reference's examples are built from (examples/heat.jl, test/airy.jl without the
+    Galerkin tensor): u'' - u = f on [-1, 1] with u(-1) = u(1) = 0 in a Dirichlet-recombined basis
+    (RecombinedBSplineBasis(B, Derivative(0))): assemble C2 - C0 from collocation_matrix(R, x, Derivative(2)) and
+    collocation_matrix(R, x), factor, solve for a BATCH of right-hand sides on the device, evaluate the resulting
+    splines and compare with the manufactured solutions u_m(x) = sin(m pi x)."""
+    import torch
+    N = 160
+    breaks = -np.cos(np.pi * np.arange(N + 1) / N)                  # Chebyshev-type, non-uniform
+    B = bk.BSplineBasis(k, breaks)
+    R = bk.RecombinedBSplineBasis(B, bk.Derivative(0))
+    x = bk.collocation_points(R)
+    C0 = bk.collocation_matrix(R, x)
+    C2 = bk.collocation_matrix(R, x, bk.Derivative(2))
+    A = C2.data() - C0.data()                                        # same band layout (Collocation.jl:165-198)
+    M = bk.CollocationMatrix(torch.from_numpy(np.ascontiguousarray(A.T)).cuda())
+    M.lu_()
+    ms = np.arange(1, 9)
+    F = np.stack([-(1 + (m * np.pi) ** 2) * np.sin(m * np.pi * x) for m in ms], axis=1)      # u_m'' - u_m
+    Fd = torch.from_numpy(np.ascontiguousarray(F)).cuda()
+    M.ldiv_(Fd)                                                      # coefficients in the recombined basis, in place
+    xs = np.linspace(-1.0, 1.0, 2001)
+    for j, m in enumerate(ms):
+        S = bk.Spline(R, Fd[:, j].cpu().numpy())
+        err = np.max(np.abs(S(xs) - np.sin(m * np.pi * xs)))
+        assert err < {4: 1e-3, 6: 2e-5, 8: 1e-6}[k] * m ** (k - 2), (k, m, err)
+        assert abs(S(np.array([-1.0]))[0]) < 1e-14 and abs(S(np.array([1.0]))[0]) < 1e-14     # the BCs hold exactly
+        d2 = (bk.Derivative(2) * S)(x)
+        assert np.max(np.abs(d2 - S(x) - F[:, j])) < 1e-7 * np.max(np.abs(F[:, j]))            # collocation equations
