@@ -2105,3 +2105,41 @@ def test_collocation_boundary_value_problem(bk, k):
         assert abs(S(np.array([-1.0]))[0]) < 1e-14 and abs(S(np.array([1.0]))[0]) < 1e-14     # the BCs hold exactly
         d2 = (bk.Derivative(2) * S)(x)
         assert np.max(np.abs(d2 - S(x) - F[:, j])) < 1e-7 * np.max(np.abs(F[:, j]))            # collocation equations
+
+
+def test_heat_equation_time_stepping_with_the_fused_step(bk):
+    """examples/heat.jl:300-330 in small: u_t = nu u_xx on [-1, 1], u(+-1) = 0, collocation in a
+    Dirichlet-recombined cubic basis; every right-hand-side evaluation is `du = F \\ (L u)` — the fused
+    mat-vec + solve on a batch of 64 initial conditions (modes sin(m pi (x + 1) / 2)) — inside a classical RK4
+    loop that never leaves the device.  Each mode must decay like exp(-nu (m pi / 2)^2 t)."""
+    import torch
+    k, N, nu = 4, 96, 1.0
+    B = bk.BSplineBasis(k, np.linspace(-1.0, 1.0, N + 1))
+    R = bk.RecombinedBSplineBasis(B, bk.Derivative(0))
+    x = bk.collocation_points(R)
+    F = bk.collocation_matrix(R, x)
+    L = bk.collocation_matrix(R, x, bk.Derivative(2))
+    F.lu_()
+    M = 64
+    modes = 1 + np.arange(M) % 4                                     # m = 1..4, sixteen copies each
+    U0 = np.stack([np.sin(m * np.pi * (x + 1) / 2) for m in modes], axis=1)
+    C = torch.from_numpy(np.ascontiguousarray(U0)).cuda()
+    F.ldiv_(C)                                                       # coefficients of the initial conditions
+    dt, steps = 2.0e-5, 400
+    k1, k2, k3, k4, tmp = (torch.empty_like(C) for _ in range(5))
+    for _ in range(steps):                                           # du/dt = nu F \\ (L u), classical RK4
+        F.ldiv_mul(L, C, out=k1)
+        torch.add(C, k1, alpha=0.5 * dt * nu, out=tmp); F.ldiv_mul(L, tmp, out=k2)
+        torch.add(C, k2, alpha=0.5 * dt * nu, out=tmp); F.ldiv_mul(L, tmp, out=k3)
+        torch.add(C, k3, alpha=dt * nu, out=tmp); F.ldiv_mul(L, tmp, out=k4)
+        C.add_(k1 + 2 * k2 + 2 * k3 + k4, alpha=dt * nu / 6)
+    T = dt * steps
+    assert torch.isfinite(C).all()
+    xs = np.linspace(-1.0, 1.0, 501)
+    Ch = C.cpu().numpy()
+    for j in (0, 1, 2, 3, 63):
+        m = modes[j]
+        S = bk.Spline(R, Ch[:, j])
+        exact = np.exp(-nu * (m * np.pi / 2) ** 2 * T) * np.sin(m * np.pi * (xs + 1) / 2)
+        assert np.max(np.abs(S(xs) - exact)) < 2e-4 * m ** 2, (m, np.max(np.abs(S(xs) - exact)))
+    assert np.array_equal(Ch[:, 0], Ch[:, 4])                        # identical columns stay identical
