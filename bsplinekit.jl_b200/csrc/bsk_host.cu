@@ -137,8 +137,17 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes) {
     const unsigned nt = (unsigned)std::min<size_t>(std::min<unsigned>(cap, hw), (bytes + per - 1) / per);
     if (nt <= 1) { memcpy(dst, src, bytes); return; }
     std::lock_guard<std::mutex> l(copy_mu);
-    static CopyPool pool(std::min<unsigned>(cap, hw) - 1);
-    pool.copy(dst, src, bytes, std::min(nt, pool.size() + 1));
+    static bool usable = true;
+    if (usable) {
+        try {                                                 // no exception may cross the C ABI: a process that
+            static CopyPool pool(std::min<unsigned>(cap, hw) - 1);      // cannot start threads copies with one
+            pool.copy(dst, src, bytes, std::min(nt, pool.size() + 1));
+            return;
+        } catch (...) {
+            usable = false;
+        }
+    }
+    memcpy(dst, src, bytes);
 }
 
 cudaError_t pool_stream(Pool &p, int slot, cudaStream_t *out) {
