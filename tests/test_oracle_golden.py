@@ -412,3 +412,35 @@ def test_float32_cyclic_chain(oracle):
     X = oracle.cyclic_solve_f32(a, b, c, Y.copy())
     ref = np.linalg.solve(A, Y.astype(np.float64))
     assert np.max(np.abs(X - ref)) / np.max(np.abs(ref)) < 1e-4
+
+
+def test_oracle_galerkin_identities(oracle):
+    """Pins the oracle's Galerkin restatement (src/Galerkin/linear.jl:268-311, projection.jl:60-99) on the
+    reference's own assertions: analytical mass-matrix entries for k = 2 (test/galerkin.jl:11-27), sum(G) == length
+    of the domain and column sums == (t[j+k] - t[j]) / k (test/galerkin.jl:131-146, test/periodic.jl:184-196) for plain
+    and periodic bases, projection of the constant 1 == those column sums."""
+    import numpy as np
+    x = np.array([-np.cos(np.pi * n / 42) for n in range(43)])
+    t = oracle.augment_knots(x, 2)
+    G = oracle.galerkin_matrix(2, t)
+    i = 8
+    assert abs(G[i - 1, i - 1] - (t[i + 1] - t[i - 1]) / 3) < 1e-15
+    assert abs(G[i - 2, i - 1] - (t[i] - t[i - 1]) / 6) < 1e-15
+    for k in (3, 4, 6):
+        t = oracle.augment_knots(x, k)
+        G = oracle.galerkin_matrix(k, t)
+        N = t.size - k
+        assert abs(G.sum() - 2.0) < 1e-13
+        assert np.allclose(G.sum(axis=0), (t[k:k + N] - t[:N]) / k, rtol=1e-12, atol=1e-15)
+        assert np.allclose(oracle.galerkin_projection(lambda v: 1.0, k, t), (t[k:k + N] - t[:N]) / k, rtol=1e-12, atol=1e-15)
+    rng = np.random.default_rng(5)
+    for k in (2, 3, 4, 5, 6):
+        data = np.sort(np.concatenate([[0.0], 3.0 * rng.random(25), [3.0]]))
+        N = data.size - 1
+        Gp = oracle.galerkin_matrix_periodic(k, data)
+        ts = oracle.periodic_knots(data, k)
+        assert abs(Gp.sum() - 3.0) < 1e-13
+        assert np.allclose(Gp.sum(axis=0), (ts[k:k + N] - ts[:N]) / k, rtol=1e-12, atol=1e-15)
+        assert np.max(np.abs(Gp - Gp.T)) < 1e-15
+        assert np.allclose(oracle.galerkin_projection_periodic(lambda v: 1.0, k, data), (ts[k:k + N] - ts[:N]) / k,
+                           rtol=1e-12, atol=1e-15)
