@@ -198,3 +198,78 @@ def test_random_periodic_interpolation(bk, oracle, seed):
     xq = x[0] + L * rng.random(500)
     assert np.max(np.abs(S(xq + L) - S(xq))) < 1e-11 * max(1.0, np.max(np.abs(cref)))
     assert np.max(np.abs(S(xq, algo=bk.EVAL_DEBOOR) - oracle.spline_eval(1, k, data, S.coefficients(), xq))) == 0
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_random_vector_valued_and_extrapolated_evaluation(bk, oracle, seed):
+    """Vector-valued splines (M splines sharing a basis, the k_spline_multi kernels incl. the TMA ring variant) and
+    the three extrapolation methods on random bases / point sets, against the oracle."""
+    import torch
+    rng = np.random.default_rng(6000 + seed)
+    k = int(rng.integers(2, 9))
+    periodic = seed % 4 == 3
+    nb = int(rng.integers(max(2 * k + 2, 8), 500))
+    br = _random_breaks(rng, nb, ("jitter", "geometric")[seed % 2])
+    a, b = float(br[0]), float(br[-1])
+    L = b - a
+    if periodic:
+        if np.any(np.diff(br) <= 0):
+            br = np.unique(br)
+        B = bk.PeriodicBSplineBasis(k, br)
+        kind, tref = 1, br
+    else:
+        B = bk.BSplineBasis(k, br)
+        kind, tref = 0, B.knots()
+    M = int(rng.choice([1, 2, 3, 4, 7, 32, 130]))
+    Cf = 2 * rng.random((len(B), M)) - 1
+    n = int(rng.integers(1, 3000))
+    x = a - 0.2 * L + 1.4 * L * rng.random(n)
+    if seed % 5 == 0:
+        x = np.sort(x)
+    SB = bk.SplineBatch(B, torch.from_numpy(Cf).cuda())
+    got = SB(torch.from_numpy(x).cuda()).cpu().numpy()
+    for j in sorted(set([0, M - 1, M // 2])):
+        ref = oracle.spline_eval(kind, k, tref, Cf[:, j], x)
+        assert np.max(np.abs(got[:, j] - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref))), (seed, k, M, j)
+    if not periodic:
+        S = bk.Spline(B, Cf[:, 0])
+        for name, meth in (("flat", bk.Flat()), ("linear", bk.Linear()), ("smooth", bk.Smooth())):
+            ref = oracle.spline_extrapolate(name, k, tref, Cf[:, 0], x)
+            out = bk.extrapolate(S, meth)(x)
+            tol = 1e-13 if name != "smooth" else 1e-11          # smooth: a polynomial continued up to 0.2 L outside
+            assert np.max(np.abs(out - ref)) <= tol * max(1.0, np.max(np.abs(ref))), (seed, k, name)
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_collocation_matrices(bk, oracle, seed):
+    """collocation_matrix(B | R, x, Derivative(n)) on random bases, derivative orders and Robin / Dirichlet /
+    Neumann recombinations: the band store bit for bit the oracle's; rectangular row form consistent with it."""
+    rng = np.random.default_rng(7000 + seed)
+    k = int(rng.integers(3, 9))
+    nb = int(rng.integers(max(2 * k + 2, 10), 300))
+    br = _random_breaks(rng, nb, ("jitter", "geometric")[seed % 2])
+    B = bk.BSplineBasis(k, br)
+    t = B.knots()
+    nd = int(rng.integers(0, min(k - 1, 3) + 1))
+    if seed % 3 == 0:
+        basis, rc, kindc = B, None, 0
+    else:
+        ops = [bk.Derivative(0), bk.Derivative(1), bk.Derivative(0) + float(rng.uniform(0.3, 5.0)) * bk.Derivative(1)]
+        basis = bk.RecombinedBSplineBasis(B, ops[seed % 3])
+        rc, kindc = oracle.Recomb(basis.cl, basis.cr, basis.nl, basis.nr, basis.ul, basis.lr), 2
+    x = bk.collocation_points(basis)
+    ref, nout_ref = oracle.collocation_matrix(kindc, k, t, x, nderiv=nd, recomb=rc)
+    Cm, nout = bk.collocation_matrix(basis, x, bk.Derivative(nd), return_outside=True)
+    assert nout == nout_ref and np.array_equal(Cm.data(), ref), (seed, k, nd)
+    # rectangular form at other points: rows agree with evaluate_all
+    xr = np.sort(float(br[0]) + (float(br[-1]) - float(br[0])) * rng.random(2 * len(basis) + 7))
+    D = bk.collocation_rows(basis, xr, bk.Derivative(nd), dense=True).cpu().numpy()
+    idx, bs = oracle.evaluate_all(kindc, k, t, xr, nderiv=nd, recomb=rc)
+    eps = np.finfo(float).eps
+    for r in rng.integers(0, xr.size, 25):
+        row = np.zeros(len(basis))
+        for d in range(k):
+            j = idx[r] - d
+            if 1 <= j <= len(basis) and abs(bs[r, d]) > eps:
+                row[j - 1] = bs[r, d]
+        assert np.array_equal(D[r], row), (seed, r)
