@@ -517,6 +517,7 @@ bsk_status build_pp(bsk_spline *s) {
     s->pp_scale = tb.lut_scale;
     s->pp_rec = tb.rec;
     s->pp_uncertified = tb.n_uncertified;
+    s->range_safe_d = tb.range_safe_d;
     s->cell_valid = false;
     if (tb.cell_valid) {
         BSK_CUDA(bsk::dev_malloc(&s->d_cell_rec, tb.cell_rec.size() * sizeof(T)));
@@ -712,6 +713,13 @@ bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout,
             bsk_status rc = build_pp<T>(sm);
             if (rc != BSK_OK) return rc;
         }
+        // derivative orders whose Horner terms would leave the range of the element type somewhere in the tables
+        // (Float32 splines on very short intervals) are formed the reference's way instead
+        int dmax = 0;
+        for (int o = 0; o < nout; ++o) dmax = std::max(dmax, (int)derivs[o]);
+        if (dmax > s->range_safe_d && extrap != BSK_EXTRAP_LINEAR && algo == BSK_EVAL_AUTO) try_pp = false;
+    }
+    if (try_pp) {
         bsk_status rc = BSK_OK;
         EvalOuts outs;
         memset(&outs, 0, sizeof(outs));

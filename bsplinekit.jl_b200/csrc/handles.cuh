@@ -94,6 +94,7 @@ struct bsk_spline {
     double pp_scale;
     int pp_rec;
     int64_t pp_uncertified;   // interval records flagged for the de Boor route (pptable.h)
+    int range_safe_d = 8;     // largest derivative order the tables can form inside the element type's range (pptable.h)
     bool pp_valid;
     // uniform-cell table (bsk_eval_cell.cu)
     void *d_cell_rec, *d_cell_rc;

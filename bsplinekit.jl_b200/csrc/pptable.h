@@ -18,6 +18,7 @@
 // interval table, interval records that are not certified carry a flag and the kernels evaluate
 // those points with the bit-faithful de Boor recurrence instead.
 #pragma once
+#include <atomic>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -35,8 +36,8 @@ namespace bsk {
 constexpr double kCertBudget = 0.25;     // share of the tolerance granted to the table's own rounding
 
 template <typename T> struct TableTol;
-template <> struct TableTol<double> { static constexpr double tol = 1e-13, u = 1.1102230246251565e-16; };
-template <> struct TableTol<float> { static constexpr double tol = 1e-5, u = 5.9604644775390625e-8; };
+template <> struct TableTol<double> { static constexpr double tol = 1e-13, u = 1.1102230246251565e-16, vmax = 1.0e307; };
+template <> struct TableTol<float> { static constexpr double tol = 1e-5, u = 5.9604644775390625e-8, vmax = 3.0e38; };
 
 struct TableInput {
     int kind;                            // 0 plain, 1 periodic
@@ -60,6 +61,10 @@ struct EvalTables {
     int lut_ncell = 0;
     double lut_scale = 0;
     int64_t n_uncertified = 0;           // records flagged for the de Boor route
+    // largest derivative order d for which every term c_m m!/(m-d)! of every record / cell stays inside the range of
+    // T (Float32: on very short intervals the high coefficients ~ h^-m do not); calls that ask for more take the
+    // de Boor route, which forms D^d S in the reference's own way
+    int range_safe_d = BSK_MAXK;
     // ---- uniform-cell table --------------------------------------------------------------------
     bool cell_valid = false, cell_global = false, cell_jump = false;
     std::vector<T> cell_rec, cell_rc;    // device layout
@@ -262,7 +267,23 @@ struct TableBuilder {
             const double e = Tol::u * (horner_bound(absc, k, d, U) + (extra ? extra[d] : 0.0));
             if (!(e <= kCertBudget * Tol::tol * scale_d[d])) return false;
         }
+        note_range(absc);
         return true;
+    }
+
+    // Range of the element type: the kernels form c_m * m!/(m-d)! before the Horner step scales it down by u^(m-d);
+    // on very short intervals the high coefficients (~ h^-m) leave Float32's range although the sum itself is
+    // harmless (found by the randomised tests: order 7, geometric knots, D^1 S came out as inf at the boundary).
+    // Recorded table-wide as the largest derivative order that is safe everywhere.
+    mutable std::atomic<int> range_safe{BSK_MAXK};
+    void note_range(const double *absc) const {
+        for (int d = 0; d < k; ++d)
+            for (int m = d; m < k; ++m)
+                if (!(absc[m] * falling_d(m, d) <= Tol::vmax)) {
+                    int cur = range_safe.load();
+                    while (d - 1 < cur && !range_safe.compare_exchange_weak(cur, d - 1)) {}
+                    return;
+                }
     }
 
     static T set_lsb(T v, int f) {
@@ -441,7 +462,7 @@ struct TableBuilder {
                                     for (int m = d; m < std::min(k, 4); ++m) { extra[d] += 16.0 * absl[m] * falling_d(m, d) * up; up *= Uc; }
                                 }
                             }
-                            ok = certified(absl, Uc, extra);
+                            ok = certified(absl, Uc, extra) && jmp * (double)k <= Tol::vmax;
                         }
                         if (!ok) { mark_slow(); continue; }
                         s.jump = (T)(cr[k - 1] - cf[k - 1]).value();
@@ -539,6 +560,7 @@ inline bool build_eval_tables(const TableInput &in, EvalTables<T> &out, std::str
     for (int d = 0; d < BSK_MAXK; ++d) out.scale_d[d] = d < in.k ? tb.scale_d[d] : 0.0;
     tb.build_records(out);
     tb.build_cells(out);
+    out.range_safe_d = tb.range_safe.load();
     return true;
 }
 

@@ -273,3 +273,39 @@ def test_random_collocation_matrices(bk, oracle, seed):
             if 1 <= j <= len(basis) and abs(bs[r, d]) > eps:
                 row[j - 1] = bs[r, d]
         assert np.array_equal(D[r], row), (seed, r)
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_random_large_bases_global_tables(bk, oracle, seed):
+    """Bases with 2 000 .. 40 000 intervals: the tables stay in global memory (one or two sectors per record, 256-bit
+    gathers), plain and periodic, Float64 and Float32, value and derivatives in one pass, points at and next to knots."""
+    rng = np.random.default_rng(8000 + seed)
+    k = int(rng.integers(2, 9))
+    dt = "f32" if seed % 4 == 1 else "f64"
+    npdt = np.float64 if dt == "f64" else np.float32
+    tol = 1e-13 if dt == "f64" else 1e-5
+    periodic = seed % 3 == 1
+    nb = int(rng.integers(2000, 40000))
+    br = _random_breaks(rng, nb, ("jitter", "geometric")[seed % 2]).astype(npdt)
+    br = np.unique(br)
+    if periodic:
+        B = bk.PeriodicBSplineBasis(k, br)
+        kind, tref = 1, br
+    else:
+        B = bk.BSplineBasis(k, br)
+        kind, tref = 0, B.knots()
+    c = (2 * rng.random(len(B)) - 1).astype(npdt)
+    S = bk.Spline(B, c)
+    a, b = float(br[0]), float(br[-1])
+    sub = br[rng.integers(0, br.size, 2000)].astype(np.float64)
+    xs = np.concatenate([a + (b - a) * rng.random(30000), sub, np.nextafter(sub, np.inf), np.nextafter(sub, -np.inf),
+                         [a, b, a - 0.1 * (b - a), b + 0.1 * (b - a)]]).astype(npdt)
+    ds = tuple(range(0, min(k, 3)))
+    outs = S.evaluate(xs, ds)
+    for d, o in zip(ds, outs):
+        kd, td, cd = oracle.spline_derivative(kind, k, tref, c, d, kt=dt) if d else (k, tref, c)
+        ref = oracle.spline_eval(kind, kd, td, cd, xs, kt=dt).astype(np.float64)
+        scale = np.max(np.abs(ref)) or 1.0
+        assert np.max(np.abs(o.astype(np.float64) - ref)) <= tol * scale, (seed, k, dt, periodic, d)
+    ti = S.table_info()
+    assert ti["cells"] > 0
