@@ -309,3 +309,46 @@ def test_random_large_bases_global_tables(bk, oracle, seed):
         assert np.max(np.abs(o.astype(np.float64) - ref)) <= tol * scale, (seed, k, dt, periodic, d)
     ti = S.table_info()
     assert ti["cells"] > 0
+
+
+@pytest.mark.parametrize("seed", list(range(40)))
+def test_random_extreme_scalings(bk, oracle, seed):
+    """Domains far from the unit interval (offsets up to 1e6 periods of the knot spacing, lengths 1e-6 .. 1e6),
+    tiny bases (k + 1 .. 2 k breakpoints), coefficient magnitudes 1e-20 .. 1e20: value and all derivatives of the
+    default path inside the tolerance, de Boor path bit for bit."""
+    rng = np.random.default_rng(9000 + seed)
+    k = int(rng.integers(1, 9))
+    dt = "f32" if seed % 3 == 2 else "f64"
+    npdt = np.float64 if dt == "f64" else np.float32
+    tol = 1e-13 if dt == "f64" else 1e-5
+    nb = int(rng.integers(2, 3 * k + 3)) if seed % 2 == 0 else int(rng.integers(20, 3000))
+    L = 10.0 ** rng.uniform(-6, 6) if dt == "f64" else 10.0 ** rng.uniform(-3, 3)
+    a = L * (10.0 ** rng.uniform(-1, 3 if dt == "f64" else 1)) * rng.choice([-1.0, 1.0]) if seed % 4 else 0.0
+    i = np.arange(nb, dtype=np.float64)
+    br = a + L * (i + 0.4 * (2 * rng.random(nb) - 1)) / max(nb - 1, 1)
+    br[0], br[-1] = a, a + L
+    br = np.unique(br.astype(npdt))
+    if br.size < 2:
+        return
+    B = bk.BSplineBasis(k, br)
+    t = B.knots()
+    amp = 10.0 ** rng.uniform(-20, 20) if dt == "f64" else 10.0 ** rng.uniform(-8, 8)
+    c = (amp * (2 * rng.random(len(B)) - 1)).astype(npdt)
+    S = bk.Spline(B, c)
+    lo, hi = float(br[0]), float(br[-1])
+    xs = np.concatenate([lo + (hi - lo) * rng.random(3000), br.astype(np.float64), np.nextafter(br, np.inf).astype(np.float64),
+                         np.nextafter(br, -np.inf).astype(np.float64), [lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo)]]).astype(npdt)
+    ref0 = oracle.spline_eval(0, k, t, c, xs, kt=dt)
+    got0 = S.evaluate(xs, (0,), algo=bk.EVAL_DEBOOR)[0]
+    assert np.array_equal(got0, ref0, equal_nan=True), (seed, k, dt)
+    for lo_d in range(0, k, 4):
+        ds = tuple(range(lo_d, min(k, lo_d + 4)))
+        outs = S.evaluate(xs, ds)
+        for d, o in zip(ds, outs):
+            kd, td, cd = oracle.spline_derivative(0, k, t, c, d, kt=dt) if d else (k, t, c)
+            r = oracle.spline_eval(0, kd, td, cd, xs, kt=dt).astype(np.float64)
+            if not np.all(np.isfinite(r)):
+                assert np.array_equal(np.isfinite(o), np.isfinite(r)), (seed, k, dt, d)     # overflow where the reference overflows
+                continue
+            scale = np.max(np.abs(r)) or 1.0
+            assert np.max(np.abs(o.astype(np.float64) - r)) <= tol * scale, (seed, k, dt, d, L, a, amp)
