@@ -352,3 +352,51 @@ def test_random_extreme_scalings(bk, oracle, seed):
                 continue
             scale = np.max(np.abs(r)) or 1.0
             assert np.max(np.abs(o.astype(np.float64) - r)) <= tol * scale, (seed, k, dt, d, L, a, amp)
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_natural_interpolation_smoothing_and_fused_step(bk, oracle, seed):
+    """Natural interpolation (orders 4, 6, 8), cubic smoothing fit (against the oracle's dense restatement, scaled by
+    the conditioning of the normal matrix) and the fused mat-vec + solve against mul! followed by ldiv!, on random
+    sites, weights and batch widths."""
+    import torch
+    rng = np.random.default_rng(10000 + seed)
+    n = int(rng.integers(12, 400))
+    x = np.sort(rng.random(n)) + np.arange(n) * 2e-3
+    y = 2 * rng.random(n) - 1
+    k = int(rng.choice([4, 6, 8]))
+    if n >= 2 * k:
+        Sn = bk.spline(bk.interpolate(x, y, bk.BSplineOrder(k), bk.Natural()))
+        assert np.max(np.abs(Sn(x) - y)) < 1e-7 * max(1.0, np.max(np.abs(Sn.coefficients())))
+        a, b = bk.boundaries(bk.basis(Sn))
+        sc = np.max(np.abs(Sn.coefficients()))
+        for d in range(2, k // 2 + 1):
+            Sd = bk.Derivative(d) * Sn
+            vals = Sd(np.array([a, b]), algo=bk.EVAL_DEBOOR)
+            assert np.max(np.abs(vals)) < 1e-6 * max(np.max(np.abs(Sd.coefficients())), sc), (seed, k, d)
+    # smoothing
+    lam = 10.0 ** rng.uniform(-8, -2)
+    w = 0.5 + rng.random(n) if seed % 2 else None
+    S = bk.fit(bk.BSplineOrder(4), x, y, lam, weights=w)
+    cs_ref, t, rc = oracle.fit_smoothing(x, y, lam, weights=w)
+    xq = np.linspace(x[0], x[-1], 333)
+    idx, bs = oracle.evaluate_all(2, 4, t, xq, recomb=rc)
+    ref = np.array([sum(bs[p, d] * cs_ref[idx[p] - d - 1] for d in range(4) if 0 <= idx[p] - d - 1 < cs_ref.size)
+                    for p in range(xq.size)])
+    assert np.max(np.abs(S(xq) - ref)) < 1e-6 * max(1.0, np.max(np.abs(ref)))      # cond(M) up to ~1e9 on clustered sites
+    # fused step against the two-call form
+    kk = int(rng.choice([4, 5, 6]))
+    t2 = bk.make_knots(x, kk)
+    B2 = bk.BSplineBasis(kk, t2, augment=False)
+    F = bk.collocation_matrix(B2, x)
+    Lm = bk.collocation_matrix(B2, x, bk.Derivative(int(rng.integers(0, 3))))
+    Fl = bk.collocation_matrix(B2, x).lu_()
+    M = int(rng.choice([1, 5, 32, 64, 200]))
+    U = torch.from_numpy(2 * rng.random((n, M)) - 1).cuda()
+    out = Fl.ldiv_mul(Lm, U)
+    two = torch.empty_like(U)
+    import ctypes
+    from bsplinekit_b200 import _lib as Lb
+    Lb.check(Lb.lib.bsk_banded_matvec(Lm._handle, ctypes.c_void_p(U.data_ptr()), ctypes.c_void_p(two.data_ptr()), M, None))
+    Fl.ldiv_(two)
+    assert torch.max(torch.abs(out - two)).item() <= 1e-12 * max(1.0, torch.max(torch.abs(two)).item()), (seed, kk, M)
