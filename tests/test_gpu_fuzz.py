@@ -400,3 +400,48 @@ def test_random_natural_interpolation_smoothing_and_fused_step(bk, oracle, seed)
     Lb.check(Lb.lib.bsk_banded_matvec(Lm._handle, ctypes.c_void_p(U.data_ptr()), ctypes.c_void_p(two.data_ptr()), M, None))
     Fl.ldiv_(two)
     assert torch.max(torch.abs(out - two)).item() <= 1e-12 * max(1.0, torch.max(torch.abs(two)).item()), (seed, kk, M)
+
+
+@pytest.mark.parametrize("seed", list(range(14)))
+def test_random_solve_shapes_single_pass_vs_banslv(bk, oracle, seed):
+    """The single-pass solve (halo-restarted backward blocks, M = ring - H, row segments when there are few
+    columns) against the BANSLV-order two-pass kernels on the same factors: n = 50 .. 20 000 rows, 1 .. 4096
+    columns, orders 2 .. 8, Float64 and Float32; and the cyclic tridiagonal solve against the oracle."""
+    import torch
+    rng = np.random.default_rng(11000 + seed)
+    f32 = seed % 4 == 3
+    npdt, tdt = (np.float32, torch.float32) if f32 else (np.float64, torch.float64)
+    k = int(rng.integers(2, 9))
+    n = int(10 ** rng.uniform(1.7, 4.3))
+    M = int(rng.choice([1, 2, 31, 32, 33, 64, 96, 500, 1024, 4096]))
+    if n * M > 3e7:
+        M = max(1, int(3e7 // n))
+    i = np.arange(n, dtype=np.float64)
+    x = ((i + 0.45 * (2 * rng.random(n) - 1)) / n).astype(npdt)
+    x = np.unique(x)
+    n = x.size
+    t = bk.make_knots(x, k)
+    B = bk.BSplineBasis(k, t, augment=False)
+    itp = bk.SplineInterpolation(B, x)
+    Y = torch.from_numpy((2 * rng.random((n, M)) - 1).astype(npdt)).cuda()
+    Y1, Y2 = Y.clone(), Y.clone()
+    itp.C.ldiv_(Y1)                                        # AUTO: single pass when a halo was validated
+    itp.C.ldiv_(Y2, algo=bk.SOLVE_TWOPASS)
+    sc = torch.max(torch.abs(Y2)).item()
+    err = torch.max(torch.abs(Y1 - Y2)).item()
+    assert err <= (1e-12 if not f32 else 2e-5) * max(1.0, sc), (seed, k, n, M, f32, err, itp.C.halo)
+    # residual of the default solve against the unfactorised matrix (dense rows on the device)
+    if n <= 3000 and not f32:                              # (the rectangular row form is Float64-only)
+        A = bk.collocation_rows(B, x, dense=True).to(torch.float64)
+        r = A @ Y1[:, :min(M, 8)].to(torch.float64) - Y[:, :min(M, 8)].to(torch.float64)
+        assert torch.max(torch.abs(r)).item() <= (1e-11 if not f32 else 1e-3) * max(1.0, sc)
+    if not f32:
+        nc = int(rng.integers(5, 3000))
+        a_ = 0.2 + rng.random(nc); c_ = 0.2 + rng.random(nc); b_ = 2.5 + rng.random(nc)      # diagonally dominant
+        Mc = int(rng.choice([1, 7, 32, 100, 1000]))
+        D = 2 * rng.random((nc, Mc)) - 1
+        Cy = bk.CyclicTridiagonalMatrix(a_, b_, c_)
+        Dd = torch.from_numpy(D.copy()).cuda()
+        Cy.ldiv_(Dd)
+        ref = oracle.cyclic_solve(a_, b_, c_, D)
+        assert np.max(np.abs(Dd.cpu().numpy() - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref))), (seed, nc, Mc)
