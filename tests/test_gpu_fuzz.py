@@ -445,3 +445,88 @@ def test_random_solve_shapes_single_pass_vs_banslv(bk, oracle, seed):
         Cy.ldiv_(Dd)
         ref = oracle.cyclic_solve(a_, b_, c_, D)
         assert np.max(np.abs(Dd.cpu().numpy() - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref))), (seed, nc, Mc)
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_host_path_chunking_and_staging(bk, synth, dt, monkeypatch):
+    """bsk_spline_eval_host on pageable arrays (page-locked staging, copy threads, 2^20-point chunks) and with the
+    staging disabled, at sizes around every chunking threshold, from views that are not 16-byte aligned, 1 .. 4
+    outputs: bit for bit the results of the device-resident call."""
+    import torch
+    npdt = np.float64 if dt == "f64" else np.float32
+    tdt = torch.float64 if dt == "f64" else torch.float32
+    k = 5
+    B = bk.BSplineBasis(k, synth.breakpoints(3, 300).astype(npdt))
+    S = bk.Spline(B, (2 * synth.u_numpy(4, 0, len(B)) - 1).astype(npdt))
+    nmax = 3 * (1 << 20) + 77
+    big = (1.2 * synth.u_numpy(50, 0, nmax + 3) - 0.1).astype(npdt)
+    bigd = torch.from_numpy(big).cuda()
+    refs = {}
+    for n, off, ds in ((1, 0, (0,)), (2, 1, (0, 1)), ((1 << 14) - 1, 1, (0,)), (1 << 14, 0, (0, 2)), ((1 << 16) + 3, 1, (1,)),
+                       ((1 << 20) + 1, 1, (0, 1, 2, 3)), (3 * (1 << 20) + 5, 0, (0, 1)), (nmax, 3, (0,))):
+        x = big[off:off + n]
+        want = [o.cpu().numpy() for o in S.evaluate(bigd[off:off + n].clone(), ds)]
+        for staging in (True, False):
+            if staging:
+                monkeypatch.delenv("BSK_HOST_NO_STAGING", raising=False)
+            else:
+                monkeypatch.setenv("BSK_HOST_NO_STAGING", "1")
+            outs = [np.full(n + 2, -7.0, dtype=npdt)[1:-1] for _ in ds]     # unaligned views with guard elements
+            bases = [o.base for o in outs]
+            got = S.evaluate(x, ds, out=outs)
+            for g, w, bb in zip(got, want, bases):
+                assert np.array_equal(g, w, equal_nan=True), (n, off, ds, staging)
+                assert bb[0] == -7.0 and bb[-1] == -7.0                     # nothing written outside
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_random_galerkin(bk, oracle, seed):
+    """Galerkin matrices / projections on random plain, recombined and periodic bases, derivative pairs and weight
+    functions: bit for bit the oracle's sequential loops."""
+    rng = np.random.default_rng(12000 + seed)
+    k = int(rng.integers(2, 8))
+    nb = int(rng.integers(2 * k + 2, 120))
+    br = _random_breaks(rng, nb, ("jitter", "geometric")[seed % 2])
+    d1 = int(rng.integers(0, min(k, 3)))
+    d2 = int(rng.integers(0, min(k, 3)))
+    f = (lambda v: 1.0 + 0.3 * np.cos(v)) if seed % 2 else None
+    fs = (lambda v: float(1.0 + 0.3 * np.cos(v))) if f else None
+
+    def dense(band, N, cyclic):
+        w = band.cpu().numpy().T
+        bw = (w.shape[0] - 1) // 2
+        A = np.zeros((N, N))
+        for j in range(N):
+            for d in range(-bw, bw + 1):
+                i = j + d
+                if cyclic:
+                    A[i % N, j] = w[bw + d, j]
+                elif 0 <= i < N:
+                    A[i, j] = w[bw + d, j]
+        return A
+
+    mode = seed % 3
+    if mode == 0:
+        B = bk.BSplineBasis(k, br)
+        args = ((f,) if f else ()) + (B, (bk.Derivative(d1), bk.Derivative(d2)))
+        got = dense(bk.galerkin_matrix(*args, as_band=True), len(B), False)
+        assert np.array_equal(got, oracle.galerkin_matrix(k, B.knots(), d1, d2, f=fs)), (seed, k, d1, d2)
+        g = lambda v: np.exp(-v * v)
+        assert np.array_equal(bk.galerkin_projection(g, B), oracle.galerkin_projection(lambda v: float(np.exp(-v * v)), k, B.knots()))
+    elif mode == 1 and k >= 3:
+        B = bk.BSplineBasis(k, br)
+        R = bk.RecombinedBSplineBasis(B, bk.Derivative(int(rng.integers(0, 2))))
+        rc = oracle.Recomb(R.cl, R.cr, R.nl, R.nr, R.ul, R.lr)
+        got = dense(bk.galerkin_matrix(R, (bk.Derivative(d1), bk.Derivative(d2)), as_band=True), len(R), False)
+        assert np.array_equal(got, oracle.galerkin_matrix(k, B.knots(), d1, d2, recomb=rc)), (seed, k, d1, d2)
+    else:
+        brp = np.unique(br)
+        if brp.size - 1 < 2 * k - 1:
+            return
+        P = bk.PeriodicBSplineBasis(k, brp)
+        got = dense(bk.galerkin_matrix(P, (bk.Derivative(d1), bk.Derivative(d2)), as_band=True), len(P), True)
+        assert np.array_equal(got, oracle.galerkin_matrix_periodic(k, brp, d1, d2)), (seed, k, d1, d2)
+        L = float(brp[-1] - brp[0])
+        g = lambda v: np.cos(2 * np.pi * v / L)
+        assert np.array_equal(bk.galerkin_projection(g, P),
+                              oracle.galerkin_projection_periodic(lambda v: float(np.cos(2 * np.pi * v / L)), k, brp))
