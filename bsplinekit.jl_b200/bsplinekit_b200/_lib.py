@@ -129,6 +129,8 @@ SIGNATURES = {
     "bsk_galerkin_nodes": (_i32, [_vp, _vp, _i32, _vp, _i64, C.POINTER(_i64)]),
     "bsk_galerkin_matrix": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     "bsk_galerkin_matrix_weighted": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "bsk_galerkin_matrix_pair": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _i64, _vp, C.POINTER(_i32),
+                                        C.POINTER(_i32), _vp]),
     "bsk_galerkin_projection": (_i32, [_vp, _i32, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "bsk_event_create": (_i32, [_i32, _pp]),
     "bsk_event_record": (_i32, [_vp, _vp]),

@@ -1625,11 +1625,11 @@ def galerkin_matrix(*args, quadrature=None, as_band=False):
     B = args.pop(0)
     derivs = args.pop(0) if args else None
     if isinstance(B, (tuple, list)):
-        # a pair of bases must share the parent basis (linear.jl:134-156); only identical bases are built here
+        # a pair of bases must share the parent basis (linear.jl:134-156)
         if len(B) != 2 or B[0].k != B[1].k or not np.array_equal(B[0].knots(), B[1].knots()):
             raise ArgumentError("all bases must share the same parent B-spline basis")
         if B[0] is not B[1]:
-            raise _lib.UnsupportedError("Galerkin matrices of two different recombinations of one basis are not built")
+            return _galerkin_matrix_pair(f, B[0], B[1], derivs, quadrature, as_band)
         B = B[0]
     d1, d2 = (0, 0) if derivs is None else (derivs[0].n, derivs[1].n)
     qx, qw = _gauss_legendre(B.k) if quadrature is None else quadrature
@@ -1653,6 +1653,50 @@ def galerkin_matrix(*args, quadrature=None, as_band=False):
         # SparseMatrixCSC in the reference (linear.jl:50-54,144): band + wrap-around corners = the cyclic band store
         return CyclicBandedMatrix(band.cpu().numpy().T, shift=0)
     return CollocationMatrix(band)
+
+
+class BandedRectMatrix:
+    """N1 x N2 banded matrix with l sub- and u super-diagonals, band store data[u + i - j, j] on the device — what
+    galerkin_matrix((B1, B2)) returns in the reference (a BandedMatrix, Galerkin/linear.jl:176-199)."""
+
+    def __init__(self, band, shape, l, u):
+        self.band, self.shape, self.bandwidths = band, shape, (l, u)       # band: (N2, l + u + 1) tensor == column-major store
+
+    def dense(self):
+        N1, N2 = self.shape
+        l, u = self.bandwidths
+        w = self.band.cpu().numpy().T
+        A = np.zeros((N1, N2))
+        for j in range(N2):
+            for i in range(max(0, j - u), min(N1, j + l + 1)):
+                A[i, j] = w[u + i - j, j]
+        return A
+
+    def __matmul__(self, x):                               # Mf * fs (test/airy.jl:69); small host product
+        return self.dense() @ np.asarray(x)
+
+
+def _galerkin_matrix_pair(f, B1, B2, derivs, quadrature, as_band):
+    d1, d2 = (0, 0) if derivs is None else (derivs[0].n, derivs[1].n)
+    qx, qw = _gauss_legendre(B1.k) if quadrature is None else quadrature
+    qx = np.ascontiguousarray(qx, dtype=np.float64); qw = np.ascontiguousarray(qw, dtype=np.float64)
+    l, u = C.c_int32(0), C.c_int32(0)
+    check(lib.bsk_galerkin_matrix_pair(B1._handle, B2._handle, d1, d2, qx.ctypes.data_as(C.c_void_p),
+                                       qw.ctypes.data_as(C.c_void_p), qx.size, None, 0, None, C.byref(l), C.byref(u), None))
+    band = torch.empty((len(B2), l.value + u.value + 1), dtype=torch.float64, device="cuda")
+    fx, nfx = None, 0
+    if f is not None:
+        npts = C.c_int64(0)
+        check(lib.bsk_galerkin_nodes(B1._handle, qx.ctypes.data_as(C.c_void_p), qx.size, None, 0, C.byref(npts)))
+        xs = np.empty(npts.value)
+        check(lib.bsk_galerkin_nodes(B1._handle, qx.ctypes.data_as(C.c_void_p), qx.size, xs.ctypes.data_as(C.c_void_p),
+                                     xs.size, C.byref(npts)))
+        fx = torch.from_numpy(_apply(f, xs)).cuda()
+        nfx = fx.numel()
+    check(lib.bsk_galerkin_matrix_pair(B1._handle, B2._handle, d1, d2, qx.ctypes.data_as(C.c_void_p),
+                                       qw.ctypes.data_as(C.c_void_p), qx.size, _ptr(fx) if fx is not None else None, nfx,
+                                       _ptr(band), C.byref(l), C.byref(u), _stream()))
+    return band if as_band else BandedRectMatrix(band, (len(B1), len(B2)), l.value, u.value)
 
 
 def galerkin_projection(f, B, deriv=None, out=None):

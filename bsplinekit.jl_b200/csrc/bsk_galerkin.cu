@@ -126,6 +126,41 @@ k_galerkin_gather(const double *__restrict__ bs1, const double *__restrict__ bs2
     }
 }
 
+// Two bases derived from the same parent (e.g. (R, B) or two different recombinations; linear.jl:134-199): the
+// matrix is N1 x N2 with l = (k - 1) + dl sub- and u = (k - 1) - dl super-diagonals, dl = cl2 - cl1; one thread per
+// entry of its band store data[u + i - j, j].  Basis 1 indexes the segment's functions from n - off1, basis 2 from
+// n - off2; segments in increasing order, products left to right, like the sequential loop.
+__global__ void __launch_bounds__(128)
+k_galerkin_gather_pair(const double *__restrict__ bs1, const double *__restrict__ bs2, const int32_t *__restrict__ seg_of_n,
+                       const double *__restrict__ y, const double *__restrict__ fx, int nq, int k, int off1, int off2,
+                       int64_t nt, int64_t N1, int64_t N2, int l, int u, double *__restrict__ band) {
+    const int nb = l + u + 1;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N2 * nb; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = e / nb;
+        const int r = (int)(e - j * nb);
+        const int64_t i = j + r - u;
+        double acc = 0.0;
+        if (i >= 0 && i < N1) {
+            const int64_t i1 = i + 1, j1 = j + 1;                  // 1-based indices in their own bases
+            const int64_t a1 = i1 + off1, a2 = j1 + off2;          // first knot segment each function lives on
+            const int64_t lo = a1 > a2 ? a1 : a2, hi = (a1 < a2 ? a1 : a2) + k - 1;
+            for (int64_t n = lo; n <= hi; ++n) {                   // knot segments in increasing order
+                if (n < 1 || n >= nt) continue;
+                const int s = seg_of_n[n];
+                if (s < 0) continue;
+                const int di = (int)(n - off1 + 1 - i1), dj = (int)(n - off2 + 1 - j1);
+                for (int q = 0; q < nq; ++q) {
+                    const int64_t p = (int64_t)s * nq + q;
+                    double term = xmul(xmul(y[p], bs1[p * k + di - 1]), bs2[p * k + dj - 1]);
+                    if (fx) term = xmul(term, fx[p]);
+                    acc = xadd(acc, term);
+                }
+            }
+        }
+        band[e] = acc;
+    }
+}
+
 // Periodic bases: one thread per entry of the CYCLIC band store, data[bw + d, j] = A[(j + d) mod N, j], |d| <= bw =
 // k - 1 (N >= 2 k - 1, so that the 2 k - 1 offsets are distinct entries).  Entry (I, J) collects, for every pair
 // (delta_i, delta_j) with delta_j - delta_i = d, the main-period segment n in h + 1 .. h + N with n + 1 - delta_j = J
@@ -273,6 +308,67 @@ bsk_status bsk_galerkin_matrix_weighted(const bsk_basis *b, int32_t deriv1, int3
     BSK_CUDA(cudaGetLastError());
     BSK_CUDA(cudaStreamSynchronize(st));                     // temporaries are released on return
     return BSK_OK;
+}
+
+// galerkin_matrix((B1, B2), (Derivative(m), Derivative(n))) for two bases that share their parent B-spline basis
+// (linear.jl:134-199,220-311): N1 x N2, band store data[u + i - j, j] with (l + u + 1) x N2 entries, l = (k - 1) + dl,
+// u = (k - 1) - dl, dl = (left constraints of B2) - (left constraints of B1); *h_l / *h_u return them.
+bsk_status bsk_galerkin_matrix_pair(const bsk_basis *b1, const bsk_basis *b2, int32_t deriv1, int32_t deriv2,
+                                    const double *h_qx, const double *h_qw, int32_t nq, const double *d_fx, int64_t nfx,
+                                    double *d_band, int32_t *h_l, int32_t *h_u, void *stream) {
+    BSK_REQUIRE(b1 && b2 && h_qx && h_qw && nq >= 1, BSK_ERR_ARGUMENT, "NULL argument");
+    BSK_REQUIRE(deriv1 >= 0 && deriv2 >= 0, BSK_ERR_ARGUMENT, "derivative order must be >= 0");
+    BSK_REQUIRE(b1->kind != BSK_BASIS_PERIODIC && b2->kind != BSK_BASIS_PERIODIC, BSK_ERR_UNSUPPORTED,
+                "pairs of periodic bases are not built");
+    BSK_REQUIRE(b1->k == b2->k && b1->h_knots == b2->h_knots && b1->device == b2->device, BSK_ERR_ARGUMENT,
+                "all bases must share the same parent B-spline basis");           // linear.jl:146-152
+    const int k = b1->k;
+    const int off1 = b1->rv.enabled ? b1->rv.cl : 0, off2 = b2->rv.enabled ? b2->rv.cl : 0;
+    const int cr1 = b1->rv.enabled ? b1->rv.cr : 0, cr2 = b2->rv.enabled ? b2->rv.cr : 0;
+    const int dl = off2 - off1;
+    BSK_REQUIRE(b1->len == b2->len + dl + (cr2 - cr1), BSK_ERR_DIMENSION, "inconsistent basis lengths");   // linear.jl:192
+    const int l = (k - 1) + dl, u = (k - 1) - dl;
+    BSK_REQUIRE(l >= 0 && u >= 0, BSK_ERR_UNSUPPORTED, "the bases differ by more constraints than the bandwidth");
+    if (h_l) *h_l = l;
+    if (h_u) *h_u = u;
+    if (!d_band) return BSK_OK;                              // size query
+    Segments sg;
+    bsk_status rc = build_segments(b1, h_qx, h_qw, nq, sg);
+    if (rc != BSK_OK) return rc;
+    const int64_t npts = (int64_t)sg.x.size();
+    BSK_REQUIRE(d_fx == nullptr || nfx == npts, BSK_ERR_DIMENSION, "expected the weight at %lld quadrature nodes, got %lld",
+                (long long)npts, (long long)nfx);
+    std::vector<int64_t> il2(sg.ileft);
+    for (auto &v : il2) v += off1 - off2;                    // ileft of basis 2 at the same segment
+    BSK_CUDA(cudaSetDevice(b1->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBufs d;
+    void *d_il2 = nullptr;
+    if ((rc = upload(&d.x, sg.x)) != BSK_OK || (rc = upload(&d.y, sg.y)) != BSK_OK ||
+        (rc = upload(&d.il, sg.ileft)) != BSK_OK || (rc = upload(&d.seg, sg.seg_of_n)) != BSK_OK ||
+        (rc = upload(&d_il2, il2)) != BSK_OK) {
+        if (d_il2) bsk::dev_free(d_il2);
+        return rc;
+    }
+    cudaError_t ce = bsk::dev_malloc(&d.idx, std::max<int64_t>(1, npts) * 8);
+    if (ce == cudaSuccess) ce = bsk::dev_malloc(&d.bs1, std::max<int64_t>(1, npts) * k * 8);
+    if (ce == cudaSuccess) ce = bsk::dev_malloc(&d.bs2, std::max<int64_t>(1, npts) * k * 8);
+    if (ce != cudaSuccess) { bsk::dev_free(d_il2); BSK_CUDA(ce); }
+    rc = bsk_evaluate_all(b1, d.x, npts, deriv1, BSK_F64, (const int64_t *)d.il, (int64_t *)d.idx, d.bs1, stream);
+    if (rc == BSK_OK)
+        rc = bsk_evaluate_all(b2, d.x, npts, deriv2, BSK_F64, (const int64_t *)d_il2, (int64_t *)d.idx, d.bs2, stream);
+    if (rc == BSK_OK) {
+        const int64_t nent = b2->len * (l + u + 1);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nent + 127) / 128, 148 * 16));
+        k_galerkin_gather_pair<<<grid, 128, 0, st>>>((const double *)d.bs1, (const double *)d.bs2, (const int32_t *)d.seg,
+                                                     (const double *)d.y, d_fx, nq, k, off1, off2, b1->nt, b1->len, b2->len,
+                                                     l, u, d_band);
+        cudaError_t le = cudaGetLastError();
+        if (le == cudaSuccess) le = cudaStreamSynchronize(st);
+        if (le != cudaSuccess) { set_error("pair Galerkin assembly failed: %s", cudaGetErrorString(le)); rc = BSK_ERR_CUDA; }
+    }
+    bsk::dev_free(d_il2);
+    return rc;
 }
 
 // phi[i] = sum over segments and nodes of (alpha w f(x)) b_i(x); d_fx = f at the nodes of bsk_galerkin_nodes.

@@ -372,6 +372,13 @@ bsk_status bsk_galerkin_matrix(const bsk_basis *b, int32_t deriv1, int32_t deriv
 bsk_status bsk_galerkin_matrix_weighted(const bsk_basis *b, int32_t deriv1, int32_t deriv2, const double *h_qx,
                                         const double *h_qw, int32_t nq, const double *d_fx, int64_t nfx,
                                         double *d_band, void *stream);
+/* galerkin_matrix((B1, B2), (Derivative(m), Derivative(n))) for two bases that share their parent B-spline basis,
+ * e.g. (R, B) or two recombinations (Galerkin/linear.jl:134-199,220-311; test/airy.jl:66-69): N1 x N2 with
+ * l = (k-1) + dl sub- and u = (k-1) - dl super-diagonals, dl = cl(B2) - cl(B1), band store data[u + i - j, j] of
+ * (l + u + 1) x N2 doubles.  d_band == NULL only returns *h_l, *h_u.  d_fx: optional weight at the nodes (or NULL). */
+bsk_status bsk_galerkin_matrix_pair(const bsk_basis *b1, const bsk_basis *b2, int32_t deriv1, int32_t deriv2,
+                                    const double *h_qx, const double *h_qw, int32_t nq, const double *d_fx, int64_t nfx,
+                                    double *d_band, int32_t *h_l, int32_t *h_u, void *stream);
 bsk_status bsk_galerkin_projection(const bsk_basis *b, int32_t deriv, const double *h_qx,
                                    const double *h_qw, int32_t nq, const double *d_fx, int64_t nfx,
                                    double *d_phi, void *stream);

@@ -480,6 +480,42 @@ def galerkin_projection(f, k, t, nderiv=0, recomb=None):
     return phi
 
 
+def galerkin_matrix_pair(k, t, rc1, rc2, d1=0, d2=0):
+    """galerkin_matrix!(M, (B1, B2), (Derivative(d1), Derivative(d2))) as a dense N1 x N2 matrix: the same loop
+    (src/Galerkin/linear.jl:268-311) with two bases derived from one parent; rc1 / rc2 = Recomb or None (the parent)."""
+    t = _np(t, np.float64)
+    Np = t.size - k
+    kind1 = KIND_RECOMBINED if rc1 is not None else KIND_PLAIN
+    kind2 = KIND_RECOMBINED if rc2 is not None else KIND_PLAIN
+    off1 = rc1.cl if rc1 is not None else 0
+    off2 = rc2.cl if rc2 is not None else 0
+    N1 = Np - ((rc1.cl + rc1.cr) if rc1 is not None else 0)
+    N2 = Np - ((rc2.cl + rc2.cr) if rc2 is not None else 0)
+    xa, xb = t[k - 1], t[Np]
+    qx, qw = np.polynomial.legendre.leggauss(k)
+    A = np.zeros((N1, N2))
+    for n in range(1, t.size):
+        tn, tn1 = t[n - 1], t[n]
+        if tn1 == tn or tn1 <= xa or tn >= xb:
+            continue
+        alpha, beta = (tn1 - tn) / 2, (tn + tn1) / 2
+        xs = alpha * qx + beta
+        _, b1 = evaluate_all(kind1, k, t, xs, nderiv=d1, ileft=np.full(k, n - off1, dtype=np.int64), recomb=rc1)
+        _, b2 = evaluate_all(kind2, k, t, xs, nderiv=d2, ileft=np.full(k, n - off2, dtype=np.int64), recomb=rc2)
+        for q in range(k):
+            y = alpha * qw[q]
+            for dj in range(1, k + 1):
+                j = n - off2 + 1 - dj
+                if not 1 <= j <= N2:
+                    continue
+                for di in range(1, k + 1):
+                    i = n - off1 + 1 - di
+                    if not 1 <= i <= N1:
+                        continue
+                    A[i - 1, j - 1] += y * b1[q, di - 1] * b2[q, dj - 1]
+    return A
+
+
 def galerkin_matrix_periodic(k, data, d1=0, d2=0):
     """galerkin_matrix!(M, B::PeriodicBSplineBasis, (Derivative(d1), Derivative(d2))) as a dense matrix: the same
     loop (src/Galerkin/linear.jl:268-311) over the PeriodicKnots ts[1 .. N+k]; only the segments inside the main

@@ -2143,3 +2143,33 @@ def test_heat_equation_time_stepping_with_the_fused_step(bk):
         exact = np.exp(-nu * (m * np.pi / 2) ** 2 * T) * np.sin(m * np.pi * (xs + 1) / 2)
         assert np.max(np.abs(S(xs) - exact)) < 2e-4 * m ** 2, (m, np.max(np.abs(S(xs) - exact)))
     assert np.array_equal(Ch[:, 0], Ch[:, 4])                        # identical columns stay identical
+
+
+@pytest.mark.parametrize("k", [3, 4, 6])
+def test_galerkin_matrix_pair_of_bases(bk, oracle, synth, k):
+    """galerkin_matrix((B1, B2)) for bases sharing their parent (src/Galerkin/linear.jl:134-199; test/airy.jl:66-69
+    `Mf = galerkin_matrix((R, B))`): rectangular band with shifted bandwidths, bit for bit the oracle's loop, for
+    (R, B), (B, R), two different recombinations and derivative pairs; consistency with the square matrices
+    (R' M_BB R == M_RR through the recombination matrix); a foreign basis is refused."""
+    br = synth.breakpoints(64, 40)
+    B = bk.BSplineBasis(k, br)
+    t = B.knots()
+    R0 = bk.RecombinedBSplineBasis(B, bk.Derivative(0))
+    R1 = bk.RecombinedBSplineBasis(B, bk.Derivative(1))
+    Rm = bk.RecombinedBSplineBasis(B, bk.Derivative(0), bk.Derivative(1))          # different BCs left / right
+    rc = lambda R: oracle.Recomb(R.cl, R.cr, R.nl, R.nr, R.ul, R.lr) if isinstance(R, bk.RecombinedBSplineBasis) else None
+    for B1, B2 in ((R0, B), (B, R0), (R0, R1), (Rm, B), (R1, Rm)):
+        for d1, d2 in ((0, 0), (1, 1), (0, 1)):
+            M = bk.galerkin_matrix((B1, B2), (bk.Derivative(d1), bk.Derivative(d2)))
+            ref = oracle.galerkin_matrix_pair(k, t, rc(B1), rc(B2), d1, d2)
+            assert M.shape == ref.shape == (len(B1), len(B2))
+            dl = (B2.cl if rc(B2) else 0) - (B1.cl if rc(B1) else 0)
+            assert M.bandwidths == (k - 1 + dl, k - 1 - dl)
+            assert np.array_equal(M.dense(), ref), (d1, d2)
+    # M_RB == T' M_BB with the recombination matrix T of R (N x M): rows of the square parent matrix recombined
+    T = R0.recombination_matrix()
+    sq = oracle.galerkin_matrix(k, t)
+    assert np.max(np.abs(bk.galerkin_matrix((R0, B)).dense() - T.T @ sq)) < 1e-15
+    assert np.max(np.abs(bk.galerkin_matrix((R0, B)) @ np.ones(len(B)) - (T.T @ sq).sum(axis=1))) < 1e-14
+    with pytest.raises(bk.ArgumentError):
+        bk.galerkin_matrix((B, bk.BSplineBasis(k, br + 0.1)))
