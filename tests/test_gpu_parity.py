@@ -2173,3 +2173,45 @@ def test_galerkin_matrix_pair_of_bases(bk, oracle, synth, k):
     assert np.max(np.abs(bk.galerkin_matrix((R0, B)) @ np.ones(len(B)) - (T.T @ sq).sum(axis=1))) < 1e-14
     with pytest.raises(bk.ArgumentError):
         bk.galerkin_matrix((B, bk.BSplineBasis(k, br + 0.1)))
+
+
+def test_airy_equation_galerkin(bk):
+    """test/airy.jl:12-95 restated: eps u'' - x u = 0 on [-1, 1] with inhomogeneous Dirichlet data (Olver & Townsend,
+    SIAM Rev. 2013), Galerkin method in a Dirichlet-recombined basis of order 6 on 100 intervals.  The reference builds
+    the multiplication operator from galerkin_tensor((R, R, B)) contracted with the coefficients of c(x) = x; the same
+    matrix <phi_i, x phi_j> is galerkin_matrix(x -> x, R) with k + 1 nodes (the integrand has degree 2k - 1).  Every
+    matrix is assembled on the device; the banded system is factorised and solved there."""
+    import torch
+    from scipy.special import airy
+    eps, N, k = 1e-4, 100, 6
+    breaks = np.linspace(-1.0, 1.0, N + 1)
+    B = bk.BSplineBasis(bk.BSplineOrder(k), breaks)
+    R = bk.RecombinedBSplineBasis(B, bk.Derivative(0))
+    u_exact = lambda x: airy(np.asarray(x) / eps ** (1.0 / 3.0))[0]
+    ua, ub = float(u_exact(-1.0)), float(u_exact(1.0))
+    u_0 = lambda x: ((1 - x) * ua + (1 + x) * ub) / 2
+    xs = bk.collocation_points(B)
+    Cfact = bk.collocation_matrix(B, xs).lu_()
+    Mc = bk.galerkin_matrix(lambda x: x, R, quadrature=bk.gausslegendre(k + 1), as_band=True)
+    Mcd = Mc.cpu().numpy()
+    L11 = bk.galerkin_matrix(R, (bk.Derivative(1), bk.Derivative(1)), as_band=True)
+    # "the matrix is practically symmetric" (:40): band store data[bw + i - j, j]
+    bw = k - 1
+    n = len(R)
+    for j in range(0, n, 7):
+        for d in range(1, bw + 1):
+            if j + d < n:
+                assert abs(Mcd[j, bw + d] - Mcd[j + d, bw - d]) < 1e-15
+    Lfact = bk.CollocationMatrix((eps * L11 + Mc).contiguous()).lu_()
+    f = lambda x: x * u_0(x)
+    fs = f(xs).reshape(-1, 1).copy()
+    Cfact.ldiv_(fs)                                          # coefficients of the right-hand side in B
+    Mf = bk.galerkin_matrix((R, B))
+    rhs = -(Mf @ fs[:, 0])
+    vR = torch.from_numpy(rhs.reshape(-1, 1).copy()).cuda()
+    Lfact.ldiv_(vR)
+    vB = R.recombination_matrix() @ vR[:, 0].cpu().numpy()
+    vsol = bk.Spline(B, vB)
+    xq = np.linspace(-1.0, 1.0, 20001)
+    err2 = np.trapezoid((vsol(xq) + u_0(xq) - u_exact(xq)) ** 2, xq)
+    assert err2 < 1e-6, err2                                 # (:91-92)
