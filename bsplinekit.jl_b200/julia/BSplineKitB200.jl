@@ -434,6 +434,28 @@ function device_galerkin_band(B::AbstractBSplineBasis, deriv = (Derivative(0), D
     reshape(Array(band), 2k - 1, N)
 end
 
+# galerkin_matrix((B1, B2), derivs): two bases sharing their parent (linear.jl:134-199) -> ((l + u + 1) x N2 band store, l, u)
+function device_galerkin_band(Bs::Tuple{AbstractBSplineBasis, AbstractBSplineBasis},
+                              deriv = (Derivative(0), Derivative(0)); device = Int32(0))
+    B1, B2 = Bs
+    qx, qw = BSplineKit.Galerkin.default_quadrature(Bs)
+    qxv = collect(Float64, qx); qwv = collect(Float64, qw)
+    m, n = map(d -> Int32(BSplineKit.DifferentialOps.max_order(d)), deriv)
+    l = Ref{Int32}(0); u = Ref{Int32}(0)
+    GC.@preserve qxv qwv check(ccall((:bsk_galerkin_matrix_pair, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Float64},
+         Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),
+        handle(B1; device).ptr, handle(B2; device).ptr, m, n, pointer(qxv), pointer(qwv), Int32(length(qxv)),
+        C_NULL, 0, C_NULL, l, u, C_NULL))
+    band = DeviceVector{Float64}(undef, (l[] + u[] + 1) * length(B2); device)
+    GC.@preserve qxv qwv check(ccall((:bsk_galerkin_matrix_pair, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Ptr{Float64},
+         Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}),
+        handle(B1; device).ptr, handle(B2; device).ptr, m, n, pointer(qxv), pointer(qwv), Int32(length(qxv)),
+        C_NULL, 0, band.ptr, l, u, C_NULL))
+    reshape(Array(band), Int(l[] + u[] + 1), length(B2)), Int(l[]), Int(u[])
+end
+
 # galerkin_matrix(B::PeriodicBSplineBasis) as the reference's SparseMatrixCSC, assembled on the device
 function device_galerkin_matrix(B::PeriodicBSplineBasis, deriv = (Derivative(0), Derivative(0)); device = Int32(0))
     w = device_galerkin_band(B, deriv; device); k = order(B); N = length(B)
