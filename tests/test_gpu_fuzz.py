@@ -3,10 +3,20 @@ run is reproducible): random orders, knot vectors with uneven spacing / clusters
 and periodic bases, Float64 and Float32, every derivative order, points on and around every knot and outside the
 domain.  The de Boor path must reproduce the oracle bit for bit; the default path must stay inside the north-star
 tolerance (1e-13 / 1e-5 of the output's magnitude)."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+# BSK_FUZZ_OFFSET=<multiple of 1000> shifts every seed: the same tests over fresh random cases (sweeps beyond the
+# committed seeds; a failing seed found that way is added to the fixed list, as seed 23 of the first test was).
+_OFF = int(os.environ.get("BSK_FUZZ_OFFSET", "0"))
+
+
+def _seeds(n):
+    return list(range(_OFF, _OFF + n))
 
 
 @pytest.fixture(scope="module")
@@ -39,7 +49,7 @@ def _random_breaks(rng, nb, style):
     return x
 
 
-@pytest.mark.parametrize("seed", list(range(60)))
+@pytest.mark.parametrize("seed", _seeds(60))
 def test_random_spline_evaluation(bk, oracle, seed):
     rng = np.random.default_rng(1000 + seed)
     k = int(rng.integers(2, 9))
@@ -87,7 +97,7 @@ def test_random_spline_evaluation(bk, oracle, seed):
             assert np.max(np.abs(o.astype(np.float64) - r)) <= tol * scale, (seed, k, dt, periodic, style, d)
 
 
-@pytest.mark.parametrize("seed", list(range(20)))
+@pytest.mark.parametrize("seed", _seeds(20))
 def test_random_interpolation(bk, oracle, seed):
     """interpolate(x, Y, BSplineOrder(k)) on random sites, a batch of data sets: against the oracle's banded
     BANFAC / BANSLV on the same collocation matrix, and S(x_i) == y_i."""
@@ -114,7 +124,7 @@ def test_random_interpolation(bk, oracle, seed):
     assert np.max(np.abs(S(x) - Y[:, 0])) < 1e-9 * max(1.0, np.max(np.abs(ref[:, 0])))
 
 
-@pytest.mark.parametrize("seed", list(range(20)))
+@pytest.mark.parametrize("seed", _seeds(20))
 def test_random_evaluate_all_and_knot_search(bk, oracle, seed):
     """find_knot_interval and evaluate_all (all derivative orders, Float32 output of Float64 bases, recombined
     bases with random Robin / Dirichlet / Neumann constraints) bit for bit against the oracle."""
@@ -150,7 +160,7 @@ def test_random_evaluate_all_and_knot_search(bk, oracle, seed):
             assert np.array_equal(ig, ir) and np.array_equal(bsg, bsr, equal_nan=True), (seed, k, nd, "recombined")
 
 
-@pytest.mark.parametrize("seed", list(range(12)))
+@pytest.mark.parametrize("seed", _seeds(12))
 def test_random_float32_interpolation_bitexact(bk, oracle, seed):
     """The Float32 chain (assembly, BANFAC, BANSLV) on random sites and orders: bit for bit the Float32 restatement."""
     import torch
@@ -175,7 +185,7 @@ def test_random_float32_interpolation_bitexact(bk, oracle, seed):
     assert np.array_equal(Yd.cpu().numpy(), oracle.banded_solve(lu_ref, Y.copy()))
 
 
-@pytest.mark.parametrize("seed", list(range(12)))
+@pytest.mark.parametrize("seed", _seeds(12))
 def test_random_periodic_interpolation(bk, oracle, seed):
     """Periodic interpolation of every order (cyclic tridiagonal for k = 4, Woodbury-corrected band otherwise) on
     random sites: against a dense pivoted solve of the oracle's periodic collocation matrix; S(x_i) == y_i and
@@ -200,7 +210,7 @@ def test_random_periodic_interpolation(bk, oracle, seed):
     assert np.max(np.abs(S(xq, algo=bk.EVAL_DEBOOR) - oracle.spline_eval(1, k, data, S.coefficients(), xq))) == 0
 
 
-@pytest.mark.parametrize("seed", list(range(16)))
+@pytest.mark.parametrize("seed", _seeds(16))
 def test_random_vector_valued_and_extrapolated_evaluation(bk, oracle, seed):
     """Vector-valued splines (M splines sharing a basis, the k_spline_multi kernels incl. the TMA ring variant) and
     the three extrapolation methods on random bases / point sets, against the oracle."""
@@ -240,7 +250,7 @@ def test_random_vector_valued_and_extrapolated_evaluation(bk, oracle, seed):
             assert np.max(np.abs(out - ref)) <= tol * max(1.0, np.max(np.abs(ref))), (seed, k, name)
 
 
-@pytest.mark.parametrize("seed", list(range(12)))
+@pytest.mark.parametrize("seed", _seeds(12))
 def test_random_collocation_matrices(bk, oracle, seed):
     """collocation_matrix(B | R, x, Derivative(n)) on random bases, derivative orders and Robin / Dirichlet /
     Neumann recombinations: the band store bit for bit the oracle's; rectangular row form consistent with it."""
@@ -275,7 +285,7 @@ def test_random_collocation_matrices(bk, oracle, seed):
         assert np.array_equal(D[r], row), (seed, r)
 
 
-@pytest.mark.parametrize("seed", list(range(16)))
+@pytest.mark.parametrize("seed", _seeds(16))
 def test_random_large_bases_global_tables(bk, oracle, seed):
     """Bases with 2 000 .. 40 000 intervals: the tables stay in global memory (one or two sectors per record, 256-bit
     gathers), plain and periodic, Float64 and Float32, value and derivatives in one pass, points at and next to knots."""
@@ -311,7 +321,7 @@ def test_random_large_bases_global_tables(bk, oracle, seed):
     assert ti["cells"] > 0
 
 
-@pytest.mark.parametrize("seed", list(range(40)))
+@pytest.mark.parametrize("seed", _seeds(40))
 def test_random_extreme_scalings(bk, oracle, seed):
     """Domains far from the unit interval (offsets up to 1e6 periods of the knot spacing, lengths 1e-6 .. 1e6),
     tiny bases (k + 1 .. 2 k breakpoints), coefficient magnitudes 1e-20 .. 1e20: value and all derivatives of the
@@ -354,7 +364,7 @@ def test_random_extreme_scalings(bk, oracle, seed):
             assert np.max(np.abs(o.astype(np.float64) - r)) <= tol * scale, (seed, k, dt, d, L, a, amp)
 
 
-@pytest.mark.parametrize("seed", list(range(12)))
+@pytest.mark.parametrize("seed", _seeds(12))
 def test_random_natural_interpolation_smoothing_and_fused_step(bk, oracle, seed):
     """Natural interpolation (orders 4, 6, 8), cubic smoothing fit (against the oracle's dense restatement, scaled by
     the conditioning of the normal matrix) and the fused mat-vec + solve against mul! followed by ldiv!, on random
@@ -402,7 +412,7 @@ def test_random_natural_interpolation_smoothing_and_fused_step(bk, oracle, seed)
     assert torch.max(torch.abs(out - two)).item() <= 1e-12 * max(1.0, torch.max(torch.abs(two)).item()), (seed, kk, M)
 
 
-@pytest.mark.parametrize("seed", list(range(14)))
+@pytest.mark.parametrize("seed", _seeds(14))
 def test_random_solve_shapes_single_pass_vs_banslv(bk, oracle, seed):
     """The single-pass solve (halo-restarted backward blocks, M = ring - H, row segments when there are few
     columns) against the BANSLV-order two-pass kernels on the same factors: n = 50 .. 20 000 rows, 1 .. 4096
@@ -479,7 +489,7 @@ def test_host_path_chunking_and_staging(bk, synth, dt, monkeypatch):
                 assert bb[0] == -7.0 and bb[-1] == -7.0                     # nothing written outside
 
 
-@pytest.mark.parametrize("seed", list(range(10)))
+@pytest.mark.parametrize("seed", _seeds(10))
 def test_random_galerkin(bk, oracle, seed):
     """Galerkin matrices / projections on random plain, recombined and periodic bases, derivative pairs and weight
     functions: bit for bit the oracle's sequential loops."""
