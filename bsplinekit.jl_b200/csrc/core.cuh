@@ -182,7 +182,8 @@ BSK_HD int find_interval(const KnotView<KT> &kv, const KT *t, KT x, int &zone) {
     if (KIND == 1) {
         int i = kv.k / 2;
         zone = 0;
-        if (!(fabs((double)x) <= 1.7e308)) {   // NaN / Inf: the reference loops forever
+        if (!(x == x)) return i + kv.nt;       // NaN passes both wrap loops; searchsortedlast(data, NaN) = length(data)
+        if (!(fabs((double)x) <= 1.7e308)) {   // +-Inf: the reference loops forever
             return i + kv.N;
         }
         KT xw = x;
