@@ -601,3 +601,60 @@ def test_random_extreme_magnitudes_and_special_points(bk, oracle, seed):
                 scale = max(np.max(np.abs(r[fin])), float(tiny))
                 assert np.all(np.isfinite(o[fin])), (seed, k, dt, periodic, expo, d, "non-finite where the reference is finite")
                 assert np.max(np.abs(o[fin] - r[fin])) <= tol * scale, (seed, k, dt, periodic, expo, d)
+
+
+@pytest.mark.parametrize("seed", _seeds(16))
+def test_random_periodic_evaluate_all_and_knot_search(bk, oracle, seed):
+    """Periodic bases: find_knot_interval and evaluate_all bit for bit against the oracle for points in the main
+    period, on and beside every breakpoint, several periods away on both sides, and NaN (which passes both wrap
+    loops of src/BSplines/periodic.jl:85-100 and lands where searchsortedlast puts it)."""
+    rng = np.random.default_rng(12000 + seed)
+    k = int(rng.integers(2, 9))
+    f32 = seed % 4 == 3
+    dt, npdt = ("f32", np.float32) if f32 else ("f64", np.float64)
+    nb = int(rng.integers(max(2 * k + 2, 8), 300))
+    br = np.unique(_random_breaks(rng, nb, ("jitter", "geometric")[seed % 2]).astype(npdt))
+    B = bk.PeriodicBSplineBasis(k, br)
+    a, b = float(br[0]), float(br[-1])
+    L = b - a
+    x = np.concatenate([a + L * rng.random(3000), br.astype(np.float64),
+                        np.nextafter(br, npdt(np.inf)).astype(np.float64), np.nextafter(br, npdt(-np.inf)).astype(np.float64),
+                        a + L * rng.uniform(-6.0, 7.0, 500), [a - 3 * L, b + 3 * L, np.nan]]).astype(npdt)
+    i_ref, z_ref = oracle.find_knot_interval(1, k, br, x, kt=dt)
+    i, z = bk.find_knot_interval(B, x)
+    assert np.array_equal(i, i_ref) and np.array_equal(z, z_ref), (seed, k, dt)
+    for nd in range(0, k):
+        ir, bsr = oracle.evaluate_all(1, k, br, x, nderiv=nd, kt=dt, vt=dt)
+        ig, bsg = bk.evaluate_all(B, x, bk.Derivative(nd))
+        assert np.array_equal(ig, ir) and np.array_equal(bsg, bsr, equal_nan=True), (seed, k, dt, nd)
+
+
+@pytest.mark.parametrize("seed", _seeds(12))
+def test_random_solve_is_exactly_homogeneous(bk, seed):
+    """Size-independent property of the banded solves: scaling the data by a power of two scales every coefficient
+    by exactly that power (no step of LU substitution rounds differently), for every solve algorithm, wide batches
+    (the windowed single-pass kernels) and narrow ones, up to data near the ends of the exponent range."""
+    import torch
+    rng = np.random.default_rng(13000 + seed)
+    k = int(rng.integers(2, 9))
+    n = int(rng.integers(max(2 * k, 8), 3000))
+    M = (7, 64, 257, 1024)[seed % 4]
+    f32 = seed % 3 == 2
+    tdt = torch.float32 if f32 else torch.float64
+    x = (np.sort(rng.random(n)) + np.arange(n) * 1e-3).astype(np.float32 if f32 else np.float64)
+    B = bk.BSplineBasis(k, bk.make_knots(x, k), augment=False)
+    Cm = bk.collocation_matrix(B, x)
+    Cm.lu_()
+    Y = torch.from_numpy(2 * rng.random((n, M)) - 1).to(tdt).cuda()
+    for e in ((-100, 90) if f32 else (-900, 900)):
+        for algo in (bk.SOLVE_AUTO, bk.SOLVE_WINDOWED, bk.SOLVE_TWOPASS):
+            A = Y.clone()
+            try:
+                Cm.ldiv_(A, algo=algo)
+            except (bk.UnsupportedError, bk.ArgumentError):
+                assert algo == bk.SOLVE_WINDOWED           # no validated halo for this matrix
+                continue
+            Bs = torch.ldexp(Y, torch.tensor(e, device="cuda")).to(tdt)
+            Cm.ldiv_(Bs, algo=algo)
+            back = torch.ldexp(Bs, torch.tensor(-e, device="cuda")).to(tdt)
+            assert torch.equal(back, A), (seed, k, n, M, e, algo)
