@@ -8,6 +8,7 @@
 //   (S::Spline)(x)          src/Splines/spline.jl:144-209
 //   Derivative(n) * S       src/Splines/spline.jl:272-330, Splines/periodic.jl:76-117
 #include <algorithm>
+#include <limits>
 #include <cstdlib>
 
 #include "handles.cuh"
@@ -343,7 +344,7 @@ k_spline_pp(KnotView<T> kv, int ncoef, PPView<T> pv, const T *__restrict__ x, in
                         else if (E == BSK_EXTRAP_LINEAR)        // S(a) + S'(a) (x - a), SplineExtrapolations.jl:40-52
                             acc = xadd((T)outs.bval[o][side], xmul((T)outs.bslope[o][side], xsub(xq, xs)));
                     }
-                    if (isnan_) acc = xq;
+                    if (isnan_) acc = outs.template nan_value<T>(o);
                     res[o][q] = acc;
                 }
             }
@@ -739,6 +740,37 @@ bsk_status spline_eval_t(const bsk_spline *s, const T *d_x, int64_t n, int nout,
             }
             if (b->kind != BSK_BASIS_PERIODIC && (extrap == BSK_EXTRAP_FLAT || extrap == BSK_EXTRAP_LINEAR))
                 boundary_constants<T>(s, derivs[o], outs.bval[o], outs.bslope[o]);
+            outs.nanv[o] = std::numeric_limits<double>::quiet_NaN();
+            outs.nanvf[o] = std::numeric_limits<float>::quiet_NaN();
+            if (derivs[o] == b->k - 1) {
+                // the order-1 spline D^(k-1) S at NaN: the coefficient of the interval find_interval gives NaN
+                const bsk_spline *ds = s;
+                if (derivs[o] > 0) {
+                    bsk_spline *dd = nullptr;
+                    rc = get_derivative(s, derivs[o], &dd);
+                    if (rc != BSK_OK) return rc;
+                    ds = dd;
+                }
+                const bsk_basis *db = ds->basis;
+                const int nc = (int)ds->ncoef;
+                std::vector<T> cc(ds->h_coefs.begin(), ds->h_coefs.end());
+                const T nanx = std::numeric_limits<T>::quiet_NaN();
+                T v;
+                if (db->kind == BSK_BASIS_PERIODIC) {
+                    KnotView<T> kd;
+                    memset(&kd, 0, sizeof(kd));
+                    std::vector<T> tt(db->h_knots.begin(), db->h_knots.end());
+                    kd.t = tt.data(); kd.nt = (int)tt.size(); kd.k = 1; kd.N = (int)db->N; kd.kind = 1;
+                    kd.a = tt.front(); kd.b = tt.back(); kd.period = (T)(tt.back() - tt.front());
+                    int z;
+                    const int i = find_interval<1>(kd, kd.t, nanx, z);
+                    v = xadd((T)0, coef_at<1, T>(cc.data(), nc, 1, i));
+                } else {
+                    v = xadd((T)0, coef_at<0, T>(cc.data(), nc, 1, db->ilast));
+                }
+                outs.nanv[o] = (double)v;
+                outs.nanvf[o] = (float)v;
+            }
         }
         // 1) uniform-cell table in shared memory (bsk_eval_cell.cu): needs every pointer to share
         //    the same 16-byte phase; the unaligned head / tail go through the scalar pp kernel.

@@ -354,7 +354,7 @@ k_spline_cell(CellView<T> cv, PPView<T> pv, KnotView<T> kv, int ncoef, const T *
                     else if (E == BSK_EXTRAP_LINEAR)        // S(a) + S'(a) (x - a), SplineExtrapolations.jl:40-52
                         val = xadd((T)outs.bval[o][side], xmul((T)outs.bslope[o][side], xsub(xq, xs)));
                 }
-                if (isnan_) val = xq;
+                if (isnan_) val = outs.template nan_value<T>(o);
                 res[o][q] = val;
             }
             if (KIND == 1 && outside && !isnan_) {

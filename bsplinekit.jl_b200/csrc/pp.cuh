@@ -20,6 +20,15 @@ struct EvalOuts {
     // Flat / Linear extrapolation (plain bases): D^deriv S and its slope at the two boundaries, formed on
     // the host by the reference's own recurrences (de Boor on the differenced coefficients)
     double bval[kMaxOut][2], bslope[kMaxOut][2];
+    // What a NaN point returns: NaN, except for D^(k-1) S — piecewise constant, so the reference's evaluation
+    // never touches x once searchsortedlast has placed NaN past the last knot, and the constant of that piece
+    // comes back (Splines/spline.jl:144-209 with BSplines/evaluate_all.jl:102-119, periodic.jl:85-100)
+    double nanv[kMaxOut];
+    float nanvf[kMaxOut];
+    template <typename T> __host__ __device__ T nan_value(int o) const {
+        if (sizeof(T) == 4) return (T)nanvf[o];
+        return (T)nanv[o];
+    }
 };
 
 template <int K, typename T> struct PPRec {

@@ -586,15 +586,10 @@ def test_random_extreme_magnitudes_and_special_points(bk, oracle, seed):
             assert np.array_equal(g, r, equal_nan=True), (seed, k, dt, periodic, expo, d, "de Boor path")
             o = S.evaluate(xs, (d,))[0].astype(np.float64)
             r = r.astype(np.float64)
-            if d == k - 1:
-                # D^(k-1) S is piecewise constant: the reference touches x only to pick the piece, so a NaN point
-                # comes back as the constant of the piece searchsortedlast assigns to NaN.  The de Boor path (above)
-                # reproduces that; the default path returns NaN for a NaN point at every derivative order
-                # (documented deviation)
-                # (or the reference's constant, when the call was routed to the de Boor kernels)
-                assert np.all(np.isnan(o[np.isnan(xs)]) | (o[np.isnan(xs)] == r[np.isnan(xs)]))
-                keep = ~np.isnan(xs)
-                o, r = o[keep], r[keep]
+            # (D^(k-1) S is piecewise constant: the reference touches x only to pick the piece, so a NaN point comes
+            #  back as the constant of the piece searchsortedlast assigns to NaN — on both paths)
+            nanx = np.isnan(xs)
+            assert np.array_equal(o[nanx], r[nanx], equal_nan=True), (seed, k, dt, periodic, expo, d, "NaN point")
             fin = np.isfinite(r)
             assert not np.any(np.isfinite(o[~fin])), (seed, k, dt, periodic, expo, d, "finite where the reference is not")
             if np.any(fin):
@@ -608,7 +603,7 @@ def test_random_periodic_evaluate_all_and_knot_search(bk, oracle, seed):
     """Periodic bases: find_knot_interval and evaluate_all bit for bit against the oracle for points in the main
     period, on and beside every breakpoint, several periods away on both sides, and NaN (which passes both wrap
     loops of src/BSplines/periodic.jl:85-100 and lands where searchsortedlast puts it)."""
-    rng = np.random.default_rng(12000 + seed)
+    rng = np.random.default_rng(14000 + seed)
     k = int(rng.integers(2, 9))
     f32 = seed % 4 == 3
     dt, npdt = ("f32", np.float32) if f32 else ("f64", np.float64)

@@ -337,7 +337,8 @@ def test_spline_eval_pp_tolerance(bk, oracle, synth, k):
     for nd, got in zip(derivs, outs):
         kd, td, cd = (k, B.knots(), c) if nd == 0 else oracle.spline_derivative(0, k, B.knots(), c, nd)
         ref = oracle.spline_eval(0, kd, td, cd, x)
-        assert np.isnan(got[-1])
+        # NaN in, NaN out — except for D^(k-1) S, whose evaluation in the reference never touches x (order-1 de Boor)
+        assert np.array_equal(got[-1:], ref[-1:], equal_nan=True) and np.isnan(got[-1]) == (nd < k - 1)
         e = relerr(got[:-1], ref[:-1])
         assert e < TOL64, (k, nd, e)
     # outside the domain -> exact zeros (spline.jl:164-168)
