@@ -653,3 +653,47 @@ def test_random_solve_is_exactly_homogeneous(bk, seed):
             Cm.ldiv_(Bs, algo=algo)
             back = torch.ldexp(Bs, torch.tensor(-e, device="cuda")).to(tdt)
             assert torch.equal(back, A), (seed, k, n, M, e, algo)
+
+
+@pytest.mark.parametrize("seed", _seeds(8))
+def test_random_order_one_splines(bk, oracle, seed):
+    """Order 1 (piecewise constants, the lowest order the reference accepts): knot search, evaluate_all and spline
+    evaluation are the oracle's bit for bit — no arithmetic touches x, so there is no rounding to tolerate (Float32
+    default path: one ulp, see below) — plain and periodic, points on and beside every knot, outside, and NaN."""
+    rng = np.random.default_rng(15000 + seed)
+    f32 = seed % 2 == 1
+    periodic = seed % 4 >= 2
+    dt, npdt = ("f32", np.float32) if f32 else ("f64", np.float64)
+    nb = int(rng.integers(4, 400))
+    br = np.unique(_random_breaks(rng, nb, ("jitter", "geometric")[seed % 2]).astype(npdt))
+    if periodic:
+        B = bk.PeriodicBSplineBasis(1, br)
+        kind, tref = 1, br
+    else:
+        B = bk.BSplineBasis(1, br)
+        kind, tref = 0, B.knots()
+    a, b = float(br[0]), float(br[-1])
+    L = b - a
+    x = np.concatenate([a + L * rng.random(3000), br.astype(np.float64),
+                        np.nextafter(br, npdt(np.inf)).astype(np.float64), np.nextafter(br, npdt(-np.inf)).astype(np.float64),
+                        [a - 0.5 * L, b + 0.5 * L, a - 2.25 * L, b + 2.25 * L, np.nan]]).astype(npdt)
+    i_ref, z_ref = oracle.find_knot_interval(kind, 1, tref, x, kt=dt)
+    i, z = bk.find_knot_interval(B, x)
+    assert np.array_equal(i, i_ref) and np.array_equal(z, z_ref), (seed, dt, periodic)
+    ir, bsr = oracle.evaluate_all(kind, 1, tref, x, nderiv=0, kt=dt, vt=dt)
+    ig, bsg = bk.evaluate_all(B, x, bk.Derivative(0))
+    assert np.array_equal(ig, ir) and np.array_equal(bsg, bsr, equal_nan=True), (seed, dt, periodic)
+    c = (2 * rng.random(len(B)) - 1).astype(npdt)
+    S = bk.Spline(B, c)
+    ref = oracle.spline_eval(kind, 1, tref, c, x, kt=dt)
+    got = S.evaluate(x, (0,), algo=bk.EVAL_DEBOOR)[0]
+    assert np.array_equal(got, ref, equal_nan=True), (seed, dt, periodic)
+    got = S.evaluate(x, (0,))[0]
+    if f32:
+        # Float32 cell tables flag knot cells in the last mantissa bit of the record's last slot, which for order 1
+        # is the constant itself: one ulp at most
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert np.all(np.abs(got[ok] - ref[ok]) <= np.spacing(np.abs(ref[ok]))), (seed, dt, periodic)
+    else:
+        assert np.array_equal(got, ref, equal_nan=True), (seed, dt, periodic)
