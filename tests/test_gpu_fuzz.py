@@ -697,3 +697,53 @@ def test_random_order_one_splines(bk, oracle, seed):
         assert np.all(np.abs(got[ok] - ref[ok]) <= np.spacing(np.abs(ref[ok]))), (seed, dt, periodic)
     else:
         assert np.array_equal(got, ref, equal_nan=True), (seed, dt, periodic)
+
+
+@pytest.mark.parametrize("seed", _seeds(10))
+def test_random_solve_columns_are_independent(bk, seed):
+    """Right-hand sides never mix: NaN / Inf / huge columns planted in a batch leave every other column's result
+    bit-identical to the batch without them — for every solve algorithm, including the Float32 kernel that packs two
+    right-hand sides into one lane, and for the cyclic (periodic) solves."""
+    import torch
+    rng = np.random.default_rng(16000 + seed)
+    k = int(rng.integers(2, 9))
+    n = int(rng.integers(max(2 * k, 8), 2500))
+    M = (5, 64, 130, 1024, 2049)[seed % 5]
+    f32 = seed % 3 == 2
+    periodic = seed % 4 == 3 and not f32
+    tdt = torch.float32 if f32 else torch.float64
+    if periodic:
+        br = (np.arange(n + 1) + np.concatenate([0.45 * (2 * rng.random(n) - 1), [0.0]])) / n
+        br[-1] = br[0] + 1.0
+        B = bk.PeriodicBSplineBasis(k, br)
+        Cm = bk.collocation_matrix(B, bk.collocation_points(B))
+        algos = (None,)
+    else:
+        x = (np.sort(rng.random(n)) + np.arange(n) * 1e-3).astype(np.float32 if f32 else np.float64)
+        B = bk.BSplineBasis(k, bk.make_knots(x, k), augment=False)
+        Cm = bk.collocation_matrix(B, x)
+        algos = (bk.SOLVE_AUTO, bk.SOLVE_WINDOWED, bk.SOLVE_TWOPASS)
+    if not periodic:
+        Cm.lu_()                                           # (the cyclic matrices are factored when they are built)
+    Y = torch.from_numpy(2 * rng.random((Cm.n, M)) - 1).to(tdt).cuda()
+    bad = rng.choice(M, size=max(1, M // 7), replace=False)
+    Yb = Y.clone()
+    fmax = torch.finfo(tdt).max
+    for j, col in enumerate(bad):
+        Yb[:, col] = (float("nan"), float("inf"), -float("inf"), fmax)[j % 4]
+        if j % 2:
+            Yb[int(rng.integers(0, Cm.n)), col] = 1.0
+    good = np.setdiff1d(np.arange(M), bad)
+    for algo in algos:
+        A, Bd = Y.clone(), Yb.clone()
+        try:
+            if algo is None:
+                Cm.ldiv_(A); Cm.ldiv_(Bd)
+            else:
+                Cm.ldiv_(A, algo=algo); Cm.ldiv_(Bd, algo=algo)
+        except (bk.UnsupportedError, bk.ArgumentError):
+            assert algo == bk.SOLVE_WINDOWED
+            continue
+        assert torch.equal(A[:, good], Bd[:, good]), (seed, k, n, M, algo)
+        nonfin = [int(c) for j, c in enumerate(bad) if j % 4 != 3]
+        assert not torch.isfinite(Bd[:, nonfin]).all(dim=0).any(), (seed, k, n, M, algo, "planted columns stay non-finite")
