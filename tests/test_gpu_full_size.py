@@ -289,3 +289,59 @@ def test_order6_full_size_eval(bk, oracle, synth):
     assert per_element(v[idx].cpu().numpy()[flagged], ref[flagged], np.max(np.abs(c)) / 32) < TOL64
     assert v.abs().max().item() <= np.abs(c).max() * (1 + 1e-14)
     assert torch.equal(S.evaluate(xd, (0,))[0], v)
+
+
+def test_more_than_2_31_elements(bk, oracle, synth):
+    """Maximum sizes: point streams and right-hand-side batches of more than 2^31 elements (every element index in
+    the kernels is 64-bit).  The one big call must equal, bit for bit, the same work split into calls below 2^31
+    elements, and windows at the start, across element 2^31 and at the end are checked against the oracle."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 80e9:
+        pytest.skip("needs 80 GB of free device memory")
+    n = (1 << 31) + 4096 + 3
+    br = synth.breakpoints(3, 1000).astype(np.float32)
+    B = bk.BSplineBasis(4, br)
+    c = (2 * synth.u_numpy(4, 0, len(B)) - 1).astype(np.float32)
+    S = bk.Spline(B, c)
+    x = synth.u_torch(31, 0, n, dtype=torch.float32)
+    out = torch.empty_like(x)
+    S.evaluate(x, (0,), out=[out])
+    idx, zone = bk.find_knot_interval(B, x)
+    windows = [(0, 4096), ((1 << 31) - 2048, (1 << 31) + 2048), (n - 4099, n)]
+    for lo, hi in windows:
+        xh = x[lo:hi].cpu().numpy()
+        assert relerr(out[lo:hi].cpu().numpy(), oracle.spline_eval(0, 4, B.knots(), c, xh, kt="f32")) < TOL32
+        ri, rz = oracle.find_knot_interval(0, 4, B.knots(), xh, kt="f32")
+        assert np.array_equal(idx[lo:hi].cpu().numpy(), ri) and np.array_equal(zone[lo:hi].cpu().numpy(), rz)
+    step = (1 << 29) + 4                                       # 16-byte aligned pieces, the last one ragged
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        assert torch.equal(S.evaluate(x[lo:hi], (0,))[0], out[lo:hi]), lo
+        pi, pz = bk.find_knot_interval(B, x[lo:hi])
+        assert torch.equal(pi, idx[lo:hi]) and torch.equal(pz, zone[lo:hi]), lo
+    del x, out, idx, zone, pi, pz
+    torch.cuda.empty_cache()
+    # right-hand sides: 2048 x (2^20 + 64) elements, Float32 (packed single-pass kernel) and Float64 (C3's kernel)
+    rows, k, nrhs = 2048, 6, (1 << 20) + 64
+    for dt, tdt, tol in ((np.float32, torch.float32, TOL32), (np.float64, torch.float64, TOL64)):
+        xs = synth.breakpoints(6, rows).astype(dt)
+        Bi = bk.BSplineBasis(k, bk.make_knots(xs, k), augment=False)
+        Cm = bk.collocation_matrix(Bi, xs)
+        band = Cm.data().copy()
+        Cm.lu_()
+        Y0 = (2 * synth.u_torch(7, 0, rows * nrhs, dtype=tdt) - 1).reshape(rows, nrhs)
+        Y = Y0.clone()
+        Cm.ldiv_(Y)
+        cols = [0, 1, 12345, (1 << 19) + 1, nrhs - 2, nrhs - 1]
+        lu = np.asfortranarray(band.astype(np.float64))
+        assert oracle.banded_lu(lu) == 0
+        ref = oracle.banded_solve(lu, Y0[:, cols].cpu().numpy().astype(np.float64))
+        assert relerr(Y[:, cols].cpu().numpy(), ref) < tol
+        blk = 1 << 18
+        for c0 in range(0, nrhs, blk):
+            part = Y0[:, c0:c0 + blk].contiguous()
+            Cm.ldiv_(part)
+            assert torch.equal(part, Y[:, c0:c0 + blk]), (dt, c0)
+        del Y0, Y, part
+        torch.cuda.empty_cache()
