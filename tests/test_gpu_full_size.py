@@ -322,6 +322,43 @@ def test_more_than_2_31_elements(bk, oracle, synth):
         assert torch.equal(pi, idx[lo:hi]) and torch.equal(pz, zone[lo:hi]), lo
     del x, out, idx, zone, pi, pz
     torch.cuda.empty_cache()
+    # evaluate_all: (2^28 + 1027) points x 8 values, value + first derivative, and the headline call (value +
+    # derivative of a Float64 cubic) on 2^31 + 6 points
+    n8 = (1 << 28) + 1027
+    B8 = bk.BSplineBasis(8, synth.breakpoints(5, 3000))
+    x8 = synth.u_torch(33, 0, n8)
+    for nd in (0, 1):
+        i8, bs8 = bk.evaluate_all(B8, x8, bk.Derivative(nd))
+        assert bs8.numel() > (1 << 31)
+        for lo in (0, (1 << 28) - 1500, n8 - 3000):
+            ri, rbs = oracle.evaluate_all(0, 8, B8.knots(), x8[lo:lo + 3000].cpu().numpy(), nderiv=nd)
+            assert np.array_equal(i8[lo:lo + 3000].cpu().numpy(), ri)
+            assert np.array_equal(bs8[lo:lo + 3000].cpu().numpy().reshape(-1, 8), rbs)
+        for lo in range(0, n8, (1 << 27) + 2):
+            hi = min(n8, lo + (1 << 27) + 2)
+            pi, pb = bk.evaluate_all(B8, x8[lo:hi], bk.Derivative(nd))
+            assert torch.equal(pi, i8[lo:hi]) and torch.equal(pb.reshape(-1, 8), bs8.reshape(-1, 8)[lo:hi]), (nd, lo)
+        del i8, bs8, pi, pb
+    del x8
+    torch.cuda.empty_cache()
+    nd_ = (1 << 31) + 6
+    B4 = bk.BSplineBasis(4, synth.breakpoints(3, 1000))
+    c4 = 2 * synth.u_numpy(4, 0, len(B4)) - 1
+    S4 = bk.Spline(B4, c4)
+    xd = synth.u_torch(35, 0, nd_)
+    o0, o1 = torch.empty_like(xd), torch.empty_like(xd)
+    S4.evaluate(xd, (0, 1), out=[o0, o1])
+    kd, td, cd = oracle.spline_derivative(0, 4, B4.knots(), c4, 1)
+    for lo, hi in ((0, 4096), ((1 << 31) - 2048, (1 << 31) + 6)):
+        xh = xd[lo:hi].cpu().numpy()
+        assert relerr(o0[lo:hi].cpu().numpy(), oracle.spline_eval(0, 4, B4.knots(), c4, xh)) < TOL64
+        assert relerr(o1[lo:hi].cpu().numpy(), oracle.spline_eval(0, kd, td, cd, xh)) < TOL64
+    for lo in range(0, nd_, (1 << 30) + 2):
+        hi = min(nd_, lo + (1 << 30) + 2)
+        p0, p1 = S4.evaluate(xd[lo:hi], (0, 1))
+        assert torch.equal(p0, o0[lo:hi]) and torch.equal(p1, o1[lo:hi]), lo
+    del xd, o0, o1, p0, p1
+    torch.cuda.empty_cache()
     # right-hand sides: 2048 x (2^20 + 64) elements, Float32 (packed single-pass kernel) and Float64 (C3's kernel)
     rows, k, nrhs = 2048, 6, (1 << 20) + 64
     for dt, tdt, tol in ((np.float32, torch.float32, TOL32), (np.float64, torch.float64, TOL64)):
