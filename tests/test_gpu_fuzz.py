@@ -241,6 +241,15 @@ def test_random_vector_valued_and_extrapolated_evaluation(bk, oracle, seed):
     for j in sorted(set([0, M - 1, M // 2])):
         ref = oracle.spline_eval(kind, k, tref, Cf[:, j], x)
         assert np.max(np.abs(got[:, j] - ref)) <= 1e-13 * max(1.0, np.max(np.abs(ref))), (seed, k, M, j)
+    # the same batch at every breakpoint, one ulp either side, NaN and (plain bases) +-Inf
+    xs = np.concatenate([br, np.nextafter(br, np.inf), np.nextafter(br, -np.inf), [np.nan],
+                         [] if periodic else [np.inf, -np.inf]])
+    gots = SB(torch.from_numpy(xs).cuda()).cpu().numpy()
+    for j in sorted(set([0, M - 1])):
+        ref = oracle.spline_eval(kind, k, tref, Cf[:, j], xs)
+        assert np.array_equal(np.isnan(gots[:, j]), np.isnan(ref)), (seed, k, M, j)
+        ok = ~np.isnan(ref)
+        assert np.max(np.abs(gots[ok, j] - ref[ok])) <= 1e-13 * max(1.0, np.max(np.abs(ref[ok]))), (seed, k, M, j)
     if not periodic:
         S = bk.Spline(B, Cf[:, 0])
         for name, meth in (("flat", bk.Flat()), ("linear", bk.Linear()), ("smooth", bk.Smooth())):
