@@ -257,6 +257,14 @@ def test_random_vector_valued_and_extrapolated_evaluation(bk, oracle, seed):
             out = bk.extrapolate(S, meth)(x)
             tol = 1e-13 if name != "smooth" else 1e-11          # smooth: a polynomial continued up to 0.2 L outside
             assert np.max(np.abs(out - ref)) <= tol * max(1.0, np.max(np.abs(ref))), (seed, k, name)
+            if name != "smooth":
+                far = np.array([np.inf, -np.inf, np.nan, 1e300, -1e300, b + 1e-300, a - 1e-300])
+                with np.errstate(all="ignore"):
+                    rf = oracle.spline_extrapolate(name, k, tref, Cf[:, 0], far)
+                gf = bk.extrapolate(S, meth)(far)
+                fin = np.isfinite(rf)
+                assert np.array_equal(gf[~fin], rf[~fin], equal_nan=True), (seed, k, name, gf, rf)
+                assert np.all(np.abs(gf[fin] - rf[fin]) <= 1e-13 * np.maximum(1.0, np.abs(rf[fin]))), (seed, k, name, gf, rf)
 
 
 @pytest.mark.parametrize("seed", _seeds(12))
