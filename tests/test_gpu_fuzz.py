@@ -764,3 +764,59 @@ def test_random_solve_columns_are_independent(bk, seed):
         assert torch.equal(A[:, good], Bd[:, good]), (seed, k, n, M, algo)
         nonfin = [int(c) for j, c in enumerate(bad) if j % 4 != 3]
         assert not torch.isfinite(Bd[:, nonfin]).all(dim=0).any(), (seed, k, n, M, algo, "planted columns stay non-finite")
+
+
+@pytest.mark.parametrize("seed", _seeds(16))
+def test_random_pointer_phases(bk, oracle, seed):
+    """Point and result buffers at arbitrary element offsets (every combination of 16-byte phases: the vector kernels
+    need a common phase, anything else takes the scalar kernels), 1 .. 4 outputs, stream lengths from one point to a
+    few vectors past 2^20: the default path stays inside the tolerance and never writes outside its slices; the
+    de Boor path stays bit-identical to the oracle."""
+    import torch
+    rng = np.random.default_rng(17000 + seed)
+    k = int(rng.integers(2, 9))
+    f32 = seed % 3 == 2
+    dt, npdt, tdt, tol = ("f32", np.float32, torch.float32, 1e-5) if f32 else ("f64", np.float64, torch.float64, 1e-13)
+    periodic = seed % 4 == 1
+    nb = int(rng.integers(max(2 * k + 2, 8), 3000))
+    br = np.unique(_random_breaks(rng, nb, ("jitter", "geometric")[seed % 2]).astype(npdt))
+    if periodic:
+        B = bk.PeriodicBSplineBasis(k, br); kind, tref = 1, br
+    else:
+        B = bk.BSplineBasis(k, br); kind, tref = 0, B.knots()
+    c = (2 * rng.random(len(B)) - 1).astype(npdt)
+    S = bk.Spline(B, c)
+    a, b = float(br[0]), float(br[-1])
+    nout = int(rng.integers(1, min(k, 4) + 1))
+    derivs = tuple(int(d) for d in rng.choice(k, size=nout, replace=False))
+    refs_cache = {}
+    for n in (1, 2, 3, int(rng.integers(4, 70)), int(rng.integers(70, 5000)), (1 << 20) + int(rng.integers(0, 9))):
+        xo = int(rng.integers(0, 8))
+        xbuf = torch.full((n + 16,), float("nan"), dtype=tdt, device="cuda")
+        xh = (a - 0.05 * (b - a) + 1.1 * (b - a) * rng.random(n)).astype(npdt)
+        xbuf[xo:xo + n] = torch.from_numpy(xh).cuda()
+        for algo in (bk.EVAL_AUTO, bk.EVAL_DEBOOR):
+            offs = [int(rng.integers(0, 8)) for _ in derivs]
+            bufs = [torch.full((n + 16,), -7.0, dtype=tdt, device="cuda") for _ in derivs]
+            S.evaluate(xbuf[xo:xo + n], derivs, algo=algo, out=[bf[o:o + n] for bf, o in zip(bufs, offs)])
+            for d, bf, o in zip(derivs, bufs, offs):
+                g = bf.cpu().numpy()
+                assert np.all(g[:o] == -7.0) and np.all(g[o + n:] == -7.0), (seed, n, d, "wrote outside the slice")
+                if n > 5000:
+                    sel = np.concatenate([np.arange(0, 600), np.arange(n - 600, n)])
+                else:
+                    sel = np.arange(n)
+                key = (n, d)
+                if key not in refs_cache:
+                    if d == 0:
+                        refs_cache[key] = oracle.spline_eval(kind, k, tref, c, xh[sel], kt=dt)
+                    else:
+                        kd, td, cd = oracle.spline_derivative(kind, k, tref, c, d, kt=dt)
+                        refs_cache[key] = oracle.spline_eval(kind, kd, td, cd, xh[sel], kt=dt)
+                r = refs_cache[key]
+                got = g[o:o + n][sel]
+                if algo == bk.EVAL_DEBOOR:
+                    assert np.array_equal(got, r), (seed, k, dt, n, d, xo, o)
+                else:
+                    scale = max(float(np.max(np.abs(r))), 1e-30)
+                    assert np.max(np.abs(got.astype(np.float64) - r.astype(np.float64))) <= tol * max(scale, 1.0 if d == 0 else scale), (seed, k, dt, n, d, xo, o)
