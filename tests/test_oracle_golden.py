@@ -444,3 +444,26 @@ def test_oracle_galerkin_identities(oracle):
         assert np.max(np.abs(Gp - Gp.T)) < 1e-15
         assert np.allclose(oracle.galerkin_projection_periodic(lambda v: 1.0, k, data), (ts[k:k + N] - ts[:N]) / k,
                            rtol=1e-12, atol=1e-15)
+
+
+def test_oracle_nan_point_semantics(oracle):
+    """What the reference does with a NaN point, read off its code and pinned here because the GPU tests compare with
+    it: `searchsortedlast(t, NaN) == length(t)` (isless sorts NaN last), so a plain basis walks back to the last
+    non-empty interval with zone 0 (BSplines/evaluate_all.jl:102-119) and a periodic one — NaN passes both wrap
+    loops — lands on `k ÷ 2 + N + 1` (BSplines/periodic.jl:85-100); the value is NaN for every order above 1, and the
+    coefficient of that interval for order 1 (no arithmetic touches x)."""
+    br = np.array([0.0, 0.3, 0.45, 0.8, 1.0])
+    x = np.array([np.nan])
+    for k in (1, 2, 4):
+        t = np.concatenate([[br[0]] * (k - 1), br, [br[-1]] * (k - 1)])
+        i, z = oracle.find_knot_interval(0, k, t, x)
+        assert i[0] == len(br) - 1 + (k - 1) and z[0] == 0            # the last interval [0.8, 1.0]
+        c = np.arange(1.0, len(t) - k + 1)
+        v = oracle.spline_eval(0, k, t, c, x)
+        assert (v[0] == c[-1]) if k == 1 else np.isnan(v[0])
+        N = len(br) - 1
+        ip, zp = oracle.find_knot_interval(1, k, br, x)
+        assert ip[0] == k // 2 + N + 1 and zp[0] == 0
+        cp = np.arange(1.0, N + 1)
+        vp = oracle.spline_eval(1, k, br, cp, x)
+        assert (vp[0] == cp[0]) if k == 1 else np.isnan(vp[0])         # order 1: PeriodicVector wraps N + 1 to 1
